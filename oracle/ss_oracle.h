@@ -1,0 +1,78 @@
+/* ss_oracle.h -- CPU restatement of the reference timestep (TEST INFRASTRUCTURE).
+ *
+ * This library is the checker for the CUDA engine.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it;
+ * the product package never does.  Every function cites the reference lines it
+ * restates (paths relative to /root/reference).  Parity is pinned: the restatement
+ * is compared step by step with the unmodified reference run headless
+ * (oracle/ref_harness.py, tests/test_oracle_vs_reference.py) and with the golden
+ * vectors that run produced (tests/golden/).
+ */
+#ifndef SS_ORACLE_H
+#define SS_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same field layout as ss_config in include/sugarscape_b200.h (kept in sync by
+ * tests/test_abi.py) so one ctypes structure fills both. */
+typedef struct {
+    int32_t grid_size;            /* settings view.grid_size.x (== y; square only, Q12)      */
+    int32_t rule_grow;            /* rules.grow                                             */
+    int32_t rule_seasons;         /* rules.seasons                                          */
+    int32_t rule_move_eat;        /* rules.moveEat                                          */
+    int32_t rule_utilicalc;       /* rules.utilicalc (sugar-only variant)                   */
+    int32_t rule_can_starve;      /* rules.canStarve                                        */
+    int32_t rule_pollution;       /* rules.pollution                                        */
+    int32_t season_period;        /* rule_params.seasons.period                             */
+    int32_t season_north[4];      /* start_x, start_y, end_x, end_y (inclusive)             */
+    int32_t season_south[4];
+    int32_t diffusion_rate;       /* rule_params.pollution.diffusion_rate                   */
+    int32_t pollution_start_time;
+    int32_t diffusion_start_time;
+    int32_t rng_mode;             /* 0 = MT19937 (CPython-exact), 1 = keyed                 */
+    double  grow_factor;          /* env.growth_factor.grow_factor                          */
+    double  season_on_factor;     /* grow_factor_on_season                                  */
+    double  season_off_factor;    /* on / grow_factor_off_season_divisor                    */
+    double  pollution_a;          /* rule_params.pollution.A                                */
+    double  pollution_b;          /* rule_params.pollution.B                                */
+    double  max_capacity;         /* env.max_capacity                                       */
+    uint64_t keyed_seed;          /* seed of the keyed word source                          */
+    int64_t iteration;            /* View.iteration at upload                               */
+    int64_t env_time;             /* Environment.time at upload                             */
+} sso_config;
+
+typedef struct {
+    double population;            /* len(self.agents) after the loop   sugarscape.py:604     */
+    double metabolism_mean;       /* sugarscape.py:608-609                                  */
+    double vision_mean;           /* sugarscape.py:614                                      */
+    double gini;                  /* sugarscape.py:619, calculateGini 269-280               */
+    double acted;                 /* agents that took their turn (Q1 skips excluded)        */
+    double deaths;
+} sso_step_stats;
+
+typedef struct sso_world sso_world;
+
+int  sso_create(const sso_config* cfg, sso_world** out);
+void sso_destroy(sso_world* w);
+/* cells are (N,N) row-major with index x*N + y (x = the reference's first index) */
+int  sso_upload_cells(sso_world* w, const double* sugar, const double* cap, const double* pollution);
+/* n agents in LIST ORDER (View.agents); id[] are the reference ids (>=1, unique) */
+int  sso_upload_agents(sso_world* w, int32_t n, const int32_t* id, const int32_t* x, const int32_t* y,
+                       const int32_t* vision, const int32_t* metab, const double* sugar);
+int  sso_set_rng_mt19937(sso_world* w, const uint32_t state[624], int32_t index);
+int  sso_get_rng_mt19937(sso_world* w, uint32_t state[624], int32_t* index);
+int  sso_step(sso_world* w, int32_t nsteps, sso_step_stats* out /* nsteps entries */);
+int  sso_download_cells(sso_world* w, double* sugar, double* cap, double* pollution, int32_t* occ_id);
+int  sso_agent_count(sso_world* w);
+/* living agents in list order */
+int  sso_download_agents(sso_world* w, int32_t* id, int32_t* x, int32_t* y, int32_t* vision,
+                         int32_t* metab, double* sugar);
+const char* sso_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,118 @@
+"""settings.json -> engine configuration (the reference's schema, kept verbatim).
+
+Mirrors the import-time flattening of `sugarscape.py:26-162` and the rule validation
+of `ruleCheck` (`sugarscape.py:182-207`): same exception names, same messages.  Rules
+that are outside the accelerated hot path are refused loudly with
+`UnsupportedRuleError` -- there is no CPU fallback.
+"""
+import json
+
+from .capi import SsConfig, RNG_MT19937, RNG_KEYED
+
+
+class ConflictingRuleException(Exception):
+    """sugarscape.py:165-168"""
+
+    def __init__(self, rule1, rule2):
+        self.message = str(rule1) + " and " + str(rule2) + " cannot be used together"
+        super().__init__(self.message)
+
+
+class MissingRuleException(Exception):
+    """sugarscape.py:171-174"""
+
+    def __init__(self, missingRule, enabledRule):
+        self.message = str(enabledRule) + " is enabled, but needs " + str(missingRule) + " to function properly"
+        super().__init__(self.message)
+
+
+class UnsupportedRuleError(Exception):
+    """A rule (or rule combination) the B200 engine does not accelerate."""
+
+
+#: rules.* keys the engine implements; everything else must be false
+SUPPORTED_RULES = ("grow", "seasons", "moveEat", "canStarve", "pollution", "utilicalc")
+UNSUPPORTED_RULES = ("tags", "combat", "limitedLifespan", "replacement", "procreate", "transmit", "spice",
+                     "trade", "foresight", "credit", "inheritance", "disease")
+
+
+def load_settings(path):
+    with open(path) as f:
+        return json.load(f)
+
+
+def rule_check(settings):
+    """`ruleCheck()` of sugarscape.py:182-207, same order of tests."""
+    rules = settings["rules"]
+    if rules["moveEat"]:
+        if rules["combat"]:
+            raise ConflictingRuleException("moveEat", "combat")
+        if rules["utilicalc"]:
+            raise ConflictingRuleException("moveEat", "utilicalc")
+    if rules["combat"]:
+        if not rules["tags"]:
+            raise MissingRuleException("tags", "combat")
+        if rules["spice"]:
+            raise ConflictingRuleException("combat", "spice")
+    if rules["pollution"]:
+        if rules["spice"]:
+            raise ConflictingRuleException("pollution", "spice")
+    if not rules["spice"]:
+        if rules["trade"]:
+            raise MissingRuleException("spice", "trade")
+        if rules["foresight"]:
+            raise MissingRuleException("spice", "foresight")
+        if rules["credit"]:
+            raise MissingRuleException("spice", "credit")
+        if rules["inheritance"]:
+            raise MissingRuleException("spice", "inheritance")
+
+
+def check_supported(settings):
+    rules = settings["rules"]
+    for r in UNSUPPORTED_RULES:
+        if rules.get(r, False):
+            raise UnsupportedRuleError(
+                "rule '%s' is outside the accelerated hot path (SURVEY.md section 8); refusing -- no CPU fallback" % r)
+    if rules["utilicalc"] and rules["pollution"]:
+        raise UnsupportedRuleError(
+            "utilicalc+pollution raises KeyError: 'duration' in the reference (agent.py:880); parity is unpinned")
+
+
+def config_from_settings(settings, rng_mode="mt", keyed_seed=None, iteration=0, env_time=0):
+    """Fill an `SsConfig` from a settings dict (sugarscape.py:32-160)."""
+    rule_check(settings)
+    check_supported(settings)
+    rules, rp, env = settings["rules"], settings["rule_params"], settings["env"]
+    gx, gy = settings["view"]["grid_size"]["x"], settings["view"]["grid_size"]["y"]
+    if gx != gy:
+        raise UnsupportedRuleError("non-square grids are broken in the reference (environment.py:34,119-122)")
+    cfg = SsConfig()
+    cfg.grid_size = gx
+    cfg.rule_grow = int(bool(rules["grow"]))
+    cfg.rule_seasons = int(bool(rules["seasons"]))
+    cfg.rule_move_eat = int(bool(rules["moveEat"]))
+    cfg.rule_utilicalc = int(bool(rules["utilicalc"]))
+    cfg.rule_can_starve = int(bool(rules["canStarve"]))
+    cfg.rule_pollution = int(bool(rules["pollution"]))
+    s = rp["seasons"]
+    cfg.season_period = int(s["period"])
+    for k, name in enumerate(("start_x", "start_y", "end_x", "end_y")):
+        cfg.season_north[k] = int(s["regions"]["north"][name])
+        cfg.season_south[k] = int(s["regions"]["south"][name])
+    on = s["grow_factor_on_season"]
+    cfg.season_on_factor = float(on)
+    cfg.season_off_factor = float(on) / s["grow_factor_off_season_divisor"]     # sugarscape.py:85
+    p = rp["pollution"]
+    cfg.diffusion_rate = int(p["diffusion_rate"])
+    cfg.pollution_start_time = int(p["pollution_start_time"])
+    cfg.diffusion_start_time = int(p["diffusion_start_time"])
+    cfg.pollution_a = float(p["A"])
+    cfg.pollution_b = float(p["B"])
+    cfg.grow_factor = float(env["growth_factor"]["grow_factor"])
+    cfg.max_capacity = float(env["max_capacity"])
+    cfg.rng_mode = RNG_MT19937 if rng_mode == "mt" else RNG_KEYED
+    cfg.keyed_seed = int(env["random_seed"] if keyed_seed is None else keyed_seed) & ((1 << 64) - 1)
+    cfg.iteration = int(iteration)
+    cfg.env_time = int(env_time)
+    return cfg
