@@ -1,0 +1,135 @@
+/* sugarscape_b200.h -- C-ABI of the B200-native Sugarscape timestep engine.
+ *
+ * Drop-in boundary for the per-timestep hot path of joshuapalicka/sugarscape-utilicalc.
+ * The reference has no FFI of its own; the seam is its L3 entry point
+ *     View.updateGame(self) -> None                     sugarscape.py:506-686
+ * called once per frame from View.step (sugarscape.py:1368-1372).  Everything that call
+ * reads and writes -- the lattice (Environment.grid, environment.py:24-34), the agents
+ * (Agent fields, agent.py:120-165), the rule switches and parameters flattened from
+ * settings.json (sugarscape.py:26-162), the global `random` state (sugarscape.py:160-162)
+ * and the four stat series it appends to (sugarscape.py:603-619) -- crosses this boundary
+ * as plain pointers and sizes.  INTEGRATION.md shows the ctypes stub a maintainer would
+ * add to sugarscape.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; the message is
+ *     available from ss_last_error(engine) (ss_last_error(NULL) for ss_create failures).
+ *   - the caller owns every host buffer; the engine owns device memory and keeps no host
+ *     pointer past a call.
+ *   - one host thread per engine, non-reentrant; the engine owns one CUDA stream.
+ *   - lattice arrays are (N,N) row-major with linear index x*N + y, where x is the
+ *     reference's FIRST grid index (grid[i][j], i = agent.x) -- "lattice-major".
+ *   - unsupported rule combinations fail in ss_create: there is no CPU fallback.
+ */
+#ifndef SUGARSCAPE_B200_H
+#define SUGARSCAPE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_RNG_MT19937 0   /* CPython-exact global stream (serial order; shipped presets) */
+#define SS_RNG_KEYED   1   /* keyed word source (parallel dependency rounds; scale configs) */
+
+#define SS_OK            0
+#define SS_ERR_ARG      -1
+#define SS_ERR_UNSUPPORTED -2
+#define SS_ERR_CUDA     -3
+#define SS_ERR_STATE    -4
+
+/* Replaces the module globals sugarscape.py:32-160 builds from settings.json
+ * (schema kept verbatim; see sugarscape_utilicalc_b200/settings.py). */
+typedef struct {
+    int32_t grid_size;            /* view.grid_size.x (== y; the reference is square-only) */
+    int32_t rule_grow;            /* rules.grow           sugarscape.py:657-659            */
+    int32_t rule_seasons;         /* rules.seasons        sugarscape.py:642-655            */
+    int32_t rule_move_eat;        /* rules.moveEat        sugarscape.py:522-523            */
+    int32_t rule_utilicalc;       /* rules.utilicalc      sugarscape.py:525-529 (sugar-only) */
+    int32_t rule_can_starve;      /* rules.canStarve      sugarscape.py:585-586            */
+    int32_t rule_pollution;       /* rules.pollution      sugarscape.py:566-567, 661-663   */
+    int32_t season_period;        /* rule_params.seasons.period                            */
+    int32_t season_north[4];      /* start_x, start_y, end_x, end_y (inclusive rectangle)  */
+    int32_t season_south[4];
+    int32_t diffusion_rate;       /* rule_params.pollution.diffusion_rate                  */
+    int32_t pollution_start_time; /* rule_params.pollution.pollution_start_time            */
+    int32_t diffusion_start_time; /* rule_params.pollution.diffusion_start_time            */
+    int32_t rng_mode;             /* SS_RNG_*                                              */
+    double  grow_factor;          /* env.growth_factor.grow_factor                         */
+    double  season_on_factor;     /* grow_factor_on_season                                 */
+    double  season_off_factor;    /* on / grow_factor_off_season_divisor (sugarscape.py:85) */
+    double  pollution_a;          /* rule_params.pollution.A (production)                  */
+    double  pollution_b;          /* rule_params.pollution.B (consumption)                 */
+    double  max_capacity;         /* env.max_capacity                                      */
+    uint64_t keyed_seed;          /* seed of the keyed word source (SS_RNG_KEYED)          */
+    int64_t iteration;            /* View.iteration at upload                              */
+    int64_t env_time;             /* Environment.time at upload                            */
+} ss_config;
+
+/* What one updateGame() appends to View.population / metabolismMean / visionMean / gini
+ * (sugarscape.py:603-619), plus two counters. */
+typedef struct {
+    double population;
+    double metabolism_mean;
+    double vision_mean;
+    double gini;
+    double acted;                 /* agents that took their turn this step                 */
+    double deaths;
+} ss_step_stats;
+
+typedef struct ss_engine ss_engine;
+
+const char* ss_version(void);
+
+/* Replaces: module import + Environment(gridSize) + the rule setters of sugarscape.py:1485-1519.
+ * device = CUDA ordinal. */
+int  ss_create(const ss_config* cfg, int32_t device, ss_engine** out);
+void ss_destroy(ss_engine* e);
+const char* ss_last_error(ss_engine* e);
+
+/* Replaces: Environment.grid slots [0] sugar, [2] capacity, [5] pollution (environment.py:24-34).
+ * pollution may be NULL (zeros). */
+int  ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution);
+
+/* Replaces: View.agents (list order = array order) and Environment.grid slot [4].
+ * id[] are the reference's Agent.id (>= 1, unique); x,y = Agent.x,y; vision, metab =
+ * Agent.vision, sugarMetabolism; sugar = Agent.sugar (agent.py:120-165). */
+int  ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, const int32_t* x, const int32_t* y,
+                      const int32_t* vision, const int32_t* metab, const double* sugar);
+
+/* Replaces: the global `random` state (random.getstate()[1]; sugarscape.py:160-162). */
+int  ss_set_rng_mt19937(ss_engine* e, const uint32_t state[624], int32_t index);
+int  ss_get_rng_mt19937(ss_engine* e, uint32_t state[624], int32_t* index);
+int  ss_set_rng_keyed(ss_engine* e, uint64_t seed);
+
+/* Replaces: nsteps calls of View.updateGame() (sugarscape.py:506-686).  out may be NULL,
+ * else it receives nsteps entries. */
+int  ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out);
+
+/* Replaces: len(View.agents). */
+int  ss_agent_count(ss_engine* e);
+
+/* Replaces: reads of Environment.grid (GUI draw, sugarscape.py:713-750).  Any pointer may be
+ * NULL.  occ_id receives the occupant's Agent.id or 0. */
+int  ss_download_cells(ss_engine* e, double* sugar, double* cap, double* pollution, int32_t* occ_id);
+
+/* Replaces: reads of View.agents.  Living agents, in list order for SS_RNG_MT19937 and in
+ * ascending keyed priority of the last step for SS_RNG_KEYED (what the reference's list
+ * holds after its shuffle).  Any pointer may be NULL. */
+int  ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t* y, int32_t* vision,
+                        int32_t* metab, double* sugar);
+
+/* Instrumentation.  counters: [0] kernel launches since create, [1] move passes,
+ * [2] steps, [3] path (0 serial fused, 1 serial + lattice env kernels, 2 lattice),
+ * [4] host syncs, [5] window extent. */
+int  ss_get_counters(ss_engine* e, int64_t* out, int32_t n);
+/* accumulated device milliseconds per kernel class (needs option "profile"=1):
+ * [0] prepare, [1] move passes, [2] stats, [3] grow/seasons, [4] diffusion, [5] serial. */
+int  ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n);
+/* options: "path" (-1 auto, 0 serial, 2 lattice), "profile" (0/1), "reset_times" */
+int  ss_set_option(ss_engine* e, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,500 @@
+// ss_engine.cu -- host side of the C-ABI (include/sugarscape_b200.h): device memory, uploads /
+// downloads and the per-timestep launch sequence.  No compute happens on the host; if a rule
+// combination or geometry is not supported the call fails -- there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ss_world.cuh"
+
+extern "C" {
+cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
+                             int stats_base, cudaStream_t stream);
+cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s);
+size_t ss_pass_smem_bytes(int emax, int ew);
+cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
+                                cudaStream_t s);
+cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s);
+cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
+cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl, cudaStream_t s);
+}
+
+enum { PATH_SERIAL_FUSED = 0, PATH_SERIAL_ENV = 1, PATH_LATTICE = 2 };
+enum { KT_PREPARE = 0, KT_MOVE, KT_STATS, KT_GROW, KT_DIFFUSE, KT_SERIAL, KT_COUNT };
+
+struct ss_engine {
+    ss_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevWorld w;
+    size_t cells = 0;
+    int64_t iteration = 0, env_time = 0;
+    bool have_cells = false, have_agents = false, stepped = false;
+    int path = -1, path_option = -1;
+    PassGeom geom{};
+    int half_x = 0, half_y = 0;
+    int last_passes = 4;
+    int stats_cap = 0;
+    int* d_flags = nullptr;
+    int sm_count = 148;
+    int diffuse_impl = 0;
+    unsigned long long* h_pending = nullptr;   // pinned
+    std::vector<int32_t> upload_order;          // slots in upload order
+    int64_t launches = 0, passes = 0, steps = 0, syncs = 0;
+    bool profile = false;
+    double kt[KT_COUNT] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+};
+
+static std::string g_err;
+static int set_err(ss_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg; else g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return set_err(e, SS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+extern "C" const char* ss_version(void) { return "sugarscape_b200 0.1 (sm_100a)"; }
+extern "C" const char* ss_last_error(ss_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
+
+extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) {
+    ss_engine* e = nullptr;
+    if (!cfg || !out) return set_err(e, SS_ERR_ARG, "null argument");
+    if (cfg->grid_size < 3) return set_err(e, SS_ERR_ARG, "grid_size must be >= 3");
+    if (cfg->grid_size > 46340) return set_err(e, SS_ERR_UNSUPPORTED, "grid_size too large (N*N must fit int32)");
+    if (cfg->rule_move_eat && cfg->rule_utilicalc)
+        return set_err(e, SS_ERR_ARG, "moveEat and utilicalc cannot be used together");          // sugarscape.py:186
+    if (cfg->rule_utilicalc && cfg->rule_pollution)
+        return set_err(e, SS_ERR_UNSUPPORTED,
+                       "utilicalc+pollution raises KeyError 'duration' in the reference (agent.py:880); parity unpinned");
+    if (cfg->rule_pollution && cfg->diffusion_rate < 1) return set_err(e, SS_ERR_ARG, "diffusion_rate must be >= 1");
+    if (cfg->rule_seasons && cfg->season_period < 1) return set_err(e, SS_ERR_ARG, "season period must be >= 1");
+    if (cfg->rng_mode != SS_RNG_MT19937 && cfg->rng_mode != SS_RNG_KEYED) return set_err(e, SS_ERR_ARG, "bad rng_mode");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(e, SS_ERR_CUDA, "no CUDA device: the engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(e, SS_ERR_ARG, "bad device ordinal");
+    e = new ss_engine();
+    e->cfg = *cfg;
+    e->device = device;
+    memset(&e->w, 0, sizeof e->w);
+    e->w.cfg = *cfg;
+    e->w.n = cfg->grid_size;
+    e->cells = (size_t)cfg->grid_size * cfg->grid_size;
+    e->iteration = cfg->iteration;
+    e->env_time = cfg->env_time;
+    auto bail = [&](cudaError_t ce, const char* what) {
+        g_err = std::string(what) + ": " + cudaGetErrorString(ce);
+        ss_destroy(e);
+        return SS_ERR_CUDA;
+    };
+    cudaError_t ce;
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce, "cudaSetDevice");
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "stream");
+    const size_t cb = e->cells * sizeof(double);
+    if ((ce = cudaMalloc(&e->w.sugar, cb)) != cudaSuccess) return bail(ce, "cudaMalloc sugar");
+    if ((ce = cudaMalloc(&e->w.cap, cb)) != cudaSuccess) return bail(ce, "cudaMalloc cap");
+    if ((ce = cudaMalloc(&e->w.poll, cb)) != cudaSuccess) return bail(ce, "cudaMalloc pollution");
+    if ((ce = cudaMalloc(&e->w.occw, e->cells * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc occ");
+    if ((ce = cudaMalloc(&e->w.mt, 624 * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc mt");
+    if ((ce = cudaMalloc(&e->w.mti, sizeof(int32_t))) != cudaSuccess) return bail(ce, "cudaMalloc mti");
+    if ((ce = cudaMalloc(&e->w.n_order, sizeof(int32_t))) != cudaSuccess) return bail(ce, "cudaMalloc n_order");
+    if ((ce = cudaMalloc(&e->w.acc, sizeof(StepAccum))) != cudaSuccess) return bail(ce, "cudaMalloc acc");
+    if ((ce = cudaMalloc(&e->w.hist, SS_GINI_BINS * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc hist");
+    const int nbands = (cfg->grid_size + 31) / 32;
+    if ((ce = cudaMalloc(&e->d_flags, sizeof(int) * (size_t)(nbands + 1))) != cudaSuccess) return bail(ce, "cudaMalloc flags");
+    if ((ce = cudaMallocHost(&e->h_pending, sizeof(unsigned long long))) != cudaSuccess) return bail(ce, "cudaMallocHost");
+    cudaMemset(e->w.sugar, 0, cb);
+    cudaMemset(e->w.cap, 0, cb);
+    cudaMemset(e->w.poll, 0, cb);
+    cudaMemset(e->w.occw, 0, e->cells * sizeof(uint32_t));
+    cudaMemset(e->w.mt, 0, 624 * sizeof(uint32_t));
+    int32_t mti0 = 624;
+    cudaMemcpy(e->w.mti, &mti0, sizeof mti0, cudaMemcpyHostToDevice);
+    cudaMemset(e->w.n_order, 0, sizeof(int32_t));
+    cudaMemset(e->w.acc, 0, sizeof(StepAccum));
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+    *out = e;
+    return SS_OK;
+}
+
+extern "C" void ss_destroy(ss_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->w.sugar); cudaFree(e->w.cap); cudaFree(e->w.poll); cudaFree(e->w.occw);
+    cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
+    cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
+    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags);
+    if (e->h_pending) cudaFreeHost(e->h_pending);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution) {
+    if (!e || !sugar || !cap) return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t cb = e->cells * sizeof(double);
+    CK(cudaMemcpyAsync(e->w.sugar, sugar, cb, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->w.cap, cap, cb, cudaMemcpyHostToDevice, e->stream));
+    if (pollution) CK(cudaMemcpyAsync(e->w.poll, pollution, cb, cudaMemcpyHostToDevice, e->stream));
+    else CK(cudaMemsetAsync(e->w.poll, 0, cb, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_cells = true;
+    return SS_OK;
+}
+
+static int choose_path(ss_engine* e) {
+    const int n = e->w.n, V = e->w.vmax;
+    bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && !e->cfg.rule_utilicalc && V <= 15 && 4 * V + 1 <= n;
+    PassGeom g{};
+    if (lattice_ok) {
+        g.ring = 2 * V;
+        if (n <= 176) {
+            g.nwin = 1; g.emax = n;
+        } else {
+            g.nwin = (n + 127) / 128;
+            g.emax = (n + g.nwin - 1) / g.nwin;
+            const int emin = n / g.nwin;
+            if (emin < 4 * g.ring + 2) lattice_ok = false;
+        }
+        g.ew = (g.emax + 31) / 32;
+        if (g.emax * g.ew > 256 * 5) lattice_ok = false;      // PASS_THREADS * PASS_WPT bitmap words
+        e->half_x = e->half_y = g.nwin > 1 ? n / (2 * g.nwin) : 0;
+    }
+    int path;
+    if (e->path_option == PATH_LATTICE) {
+        if (!lattice_ok)
+            return set_err(e, SS_ERR_UNSUPPORTED,
+                           "lattice path needs keyed RNG, moveEat (no utilicalc), vision <= 15 and windows >= 8*vmax+2");
+        path = PATH_LATTICE;
+    } else if (e->path_option == PATH_SERIAL_FUSED || e->path_option == PATH_SERIAL_ENV) {
+        path = n <= 256 ? PATH_SERIAL_FUSED : PATH_SERIAL_ENV;
+    } else {
+        path = lattice_ok ? PATH_LATTICE : (n <= 256 ? PATH_SERIAL_FUSED : PATH_SERIAL_ENV);
+    }
+    if (path != PATH_LATTICE && e->w.n_slots > (1u << 22))
+        return set_err(e, SS_ERR_UNSUPPORTED, "serial path limited to 4M agents");
+    e->geom = g;
+    e->path = path;
+    return SS_OK;
+}
+
+extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, const int32_t* x, const int32_t* y,
+                                const int32_t* vision, const int32_t* metab, const double* sugar) {
+    if (!e || n < 0 || (n > 0 && (!id || !x || !y || !vision || !metab || !sugar)))
+        return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    const int N = e->w.n;
+    int32_t max_id = 0;
+    int vmax = 1;
+    for (int i = 0; i < n; i++) {
+        if (id[i] < 1) return set_err(e, SS_ERR_ARG, "agent ids must be >= 1");
+        max_id = std::max(max_id, id[i]);
+        if (vision[i] < 1 || vision[i] > SS_MAX_VISION) return set_err(e, SS_ERR_UNSUPPORTED, "vision out of range [1,31]");
+        if (2 * vision[i] + 1 > N) return set_err(e, SS_ERR_UNSUPPORTED, "2*vision+1 exceeds the grid size");
+        if (metab[i] < 1 || metab[i] > 65535) return set_err(e, SS_ERR_ARG, "metabolism out of range [1,65535]");
+        if (x[i] < 0 || x[i] >= N || y[i] < 0 || y[i] >= N) return set_err(e, SS_ERR_ARG, "agent off the grid");
+        vmax = std::max(vmax, vision[i]);
+    }
+    if ((uint32_t)max_id > SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^25-1");
+    const uint32_t ns = (uint32_t)std::max(max_id, 1);
+    std::vector<AgentRec> recs(ns);
+    memset(recs.data(), 0, sizeof(AgentRec) * ns);
+    std::vector<uint32_t> occ(e->cells, 0u);
+    std::vector<int32_t> order((size_t)std::max(n, 1));
+    const uint32_t phase = (uint32_t)(e->iteration & 1);
+    for (int i = 0; i < n; i++) {
+        const uint32_t s = (uint32_t)id[i] - 1u;
+        if (attr_alive(recs[s].attr)) return set_err(e, SS_ERR_ARG, "duplicate agent id");
+        const size_t c = (size_t)x[i] * N + y[i];
+        if (occ[c]) return set_err(e, SS_ERR_ARG, "two agents on one cell");
+        recs[s].sugar = sugar[i];
+        recs[s].pos = (uint32_t)c;
+        recs[s].attr = attr_pack(vision[i], metab[i], true);
+        occ[c] = occ_pack(s, vision[i], phase);
+        order[i] = (int32_t)s;
+    }
+    cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.wealth); cudaFree(e->w.sortkeys);
+    e->w.agents = nullptr; e->w.order = nullptr; e->w.wealth = nullptr; e->w.sortkeys = nullptr;
+    const int P = next_pow2((int)ns);
+    CK(cudaMalloc(&e->w.agents, sizeof(AgentRec) * ns));
+    CK(cudaMalloc(&e->w.order, sizeof(int32_t) * ns));
+    CK(cudaMalloc(&e->w.wealth, sizeof(double) * P));
+    CK(cudaMalloc(&e->w.sortkeys, sizeof(unsigned long long) * P));
+    CK(cudaMemcpyAsync(e->w.agents, recs.data(), sizeof(AgentRec) * ns, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->w.occw, occ.data(), sizeof(uint32_t) * e->cells, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->w.order, order.data(), sizeof(int32_t) * std::max(n, 1), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->w.n_order, &n, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    StepAccum acc;
+    memset(&acc, 0, sizeof acc);
+    acc.population = (unsigned long long)n;
+    CK(cudaMemcpyAsync(e->w.acc, &acc, sizeof acc, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->w.n_slots = ns;
+    e->w.half = ss_order_half_bits(ns);
+    e->w.vmax = vmax;
+    order.resize((size_t)n);
+    e->upload_order.swap(order);
+    e->have_agents = true;
+    e->stepped = false;
+    return choose_path(e);
+}
+
+extern "C" int ss_set_rng_mt19937(ss_engine* e, const uint32_t state[624], int32_t index) {
+    if (!e || !state) return set_err(e, SS_ERR_ARG, "null argument");
+    if (index < 0 || index > 624) return set_err(e, SS_ERR_ARG, "MT19937 index out of range");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->w.mt, state, 624 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->w.mti, &index, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SS_OK;
+}
+
+extern "C" int ss_get_rng_mt19937(ss_engine* e, uint32_t state[624], int32_t* index) {
+    if (!e || !state || !index) return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(state, e->w.mt, 624 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(index, e->w.mti, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SS_OK;
+}
+
+extern "C" int ss_set_rng_keyed(ss_engine* e, uint64_t seed) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (e->cfg.rng_mode != SS_RNG_KEYED) return set_err(e, SS_ERR_STATE, "engine was created with rng_mode MT19937");
+    e->cfg.keyed_seed = seed;
+    e->w.cfg.keyed_seed = seed;
+    return SS_OK;
+}
+
+struct KTimer {
+    ss_engine* e; int k;
+    KTimer(ss_engine* e_, int k_) : e(e_), k(k_) { if (e->profile) cudaEventRecord(e->ev0, e->stream); }
+    ~KTimer() {
+        if (!e->profile) return;
+        cudaEventRecord(e->ev1, e->stream);
+        cudaEventSynchronize(e->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+        e->kt[k] += ms;
+    }
+};
+
+static int ensure_stats(ss_engine* e, int nsteps) {
+    if (nsteps <= e->stats_cap) return SS_OK;
+    cudaFree(e->w.stats);
+    e->w.stats = nullptr;
+    CK(cudaMalloc(&e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps));
+    e->stats_cap = nsteps;
+    return SS_OK;
+}
+
+static int env_phase(ss_engine* e) {
+    {
+        KTimer t(e, KT_GROW);
+        if (e->cfg.rule_grow) { CK(ss_launch_grow(e->w, e->iteration, e->sm_count, e->stream)); e->launches++; }
+    }
+    if (e->cfg.rule_pollution && e->iteration >= e->cfg.diffusion_start_time &&
+        e->iteration % e->cfg.diffusion_rate == 0) {                                  // sugarscape.py:661-663
+        KTimer t(e, KT_DIFFUSE);
+        CK(ss_launch_diffuse(e->w, e->d_flags, e->diffuse_impl, e->stream));
+        e->launches++;
+    }
+    return SS_OK;
+}
+
+static int lattice_step(ss_engine* e, int stats_index) {
+    {
+        KTimer t(e, KT_PREPARE);
+        CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
+        CK(ss_launch_prepare(e->w, e->iteration, e->stream));
+        e->launches += e->cfg.rule_can_starve ? 2 : 1;
+    }
+    {
+        KTimer t(e, KT_MOVE);
+        const int first_check = e->geom.nwin == 1 ? 1 : std::max(2, e->last_passes - 1);
+        int p = 0;
+        for (;;) {
+            PassGeom g = e->geom;
+            g.shift_x = (p & 1) ? e->half_x : 0;                 // tilings: (0,0) (h,h) (0,h) (h,0)
+            g.shift_y = ((p & 3) == 1 || (p & 3) == 2) ? e->half_y : 0;
+            CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
+            e->launches++; e->passes++; p++;
+            if (p >= first_check) {
+                CK(cudaMemcpyAsync(e->h_pending, &e->w.acc->pending, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                   e->stream));
+                CK(cudaStreamSynchronize(e->stream));
+                e->syncs++;
+                if (*e->h_pending == 0ull) break;
+            }
+            if (p > 4096) return set_err(e, SS_ERR_STATE, "move passes did not converge");
+        }
+        e->last_passes = p;
+    }
+    {
+        KTimer t(e, KT_STATS);
+        CK(ss_launch_stats(e->w, stats_index, e->stream));
+        e->launches++;
+    }
+    return env_phase(e);
+}
+
+extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (nsteps < 0) return set_err(e, SS_ERR_ARG, "nsteps < 0");
+    if (!e->have_cells || !e->have_agents) return set_err(e, SS_ERR_STATE, "upload cells and agents before stepping");
+    if (e->path < 0) return set_err(e, SS_ERR_STATE, "no execution path (upload_agents failed?)");
+    if (nsteps == 0) return SS_OK;
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_stats(e, nsteps);
+    if (rc) return rc;
+    if (e->path == PATH_SERIAL_FUSED) {
+        KTimer t(e, KT_SERIAL);
+        CK(ss_launch_serial(e->w, e->iteration, e->env_time, nsteps, 1, 0, e->stream));
+        e->launches++;
+        e->iteration += nsteps; e->env_time += nsteps; e->steps += nsteps;
+    } else {
+        for (int t = 0; t < nsteps; t++) {
+            if (e->path == PATH_SERIAL_ENV) {
+                {
+                    KTimer tm(e, KT_SERIAL);
+                    CK(ss_launch_serial(e->w, e->iteration, e->env_time, 1, 0, t, e->stream));
+                    e->launches++;
+                }
+                rc = env_phase(e);
+            } else {
+                rc = lattice_step(e, t);
+            }
+            if (rc) return rc;
+            e->iteration++; e->env_time++; e->steps++;
+        }
+    }
+    e->stepped = true;
+    if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    return SS_OK;
+}
+
+static int fetch_population(ss_engine* e, std::vector<AgentRec>* recs_out, std::vector<int32_t>* order_out) {
+    // living agents in the reference's list order (see header)
+    const uint32_t ns = e->w.n_slots;
+    std::vector<AgentRec> recs(ns);
+    CK(cudaMemcpyAsync(recs.data(), e->w.agents, sizeof(AgentRec) * ns, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int32_t> order;
+    if (e->path != PATH_LATTICE) {
+        int32_t cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, e->w.n_order, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        order.resize((size_t)cnt);
+        if (cnt) CK(cudaMemcpy(order.data(), e->w.order, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost));
+    } else {
+        CK(cudaStreamSynchronize(e->stream));
+        if (!e->stepped) {
+            for (int32_t s : e->upload_order) if (attr_alive(recs[s].attr)) order.push_back(s);
+        } else {
+            const OrderKey ok = ss_order_key(ss_step_key(e->cfg.keyed_seed, e->iteration - 1), e->w.half);
+            std::vector<std::pair<uint32_t, int32_t>> keyed;
+            for (uint32_t s = 0; s < ns; s++)
+                if (attr_alive(recs[s].attr)) keyed.emplace_back(ss_priority(ok, s), (int32_t)s);
+            std::sort(keyed.begin(), keyed.end());
+            order.reserve(keyed.size());
+            for (auto& kv : keyed) order.push_back(kv.second);
+        }
+    }
+    recs_out->swap(recs);
+    order_out->swap(order);
+    return SS_OK;
+}
+
+extern "C" int ss_agent_count(ss_engine* e) {
+    if (!e || !e->have_agents) return 0;
+    cudaSetDevice(e->device);
+    if (e->path != PATH_LATTICE) {
+        int32_t cnt = 0;
+        cudaMemcpy(&cnt, e->w.n_order, sizeof cnt, cudaMemcpyDeviceToHost);
+        return cnt;
+    }
+    StepAccum acc;
+    cudaMemcpy(&acc, e->w.acc, sizeof acc, cudaMemcpyDeviceToHost);
+    return (int)acc.population;
+}
+
+extern "C" int ss_download_cells(ss_engine* e, double* sugar, double* cap, double* pollution, int32_t* occ_id) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t cb = e->cells * sizeof(double);
+    if (sugar) CK(cudaMemcpyAsync(sugar, e->w.sugar, cb, cudaMemcpyDeviceToHost, e->stream));
+    if (cap) CK(cudaMemcpyAsync(cap, e->w.cap, cb, cudaMemcpyDeviceToHost, e->stream));
+    if (pollution) CK(cudaMemcpyAsync(pollution, e->w.poll, cb, cudaMemcpyDeviceToHost, e->stream));
+    if (occ_id) CK(cudaMemcpyAsync(occ_id, e->w.occw, e->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (occ_id)
+        for (size_t c = 0; c < e->cells; c++) occ_id[c] = (int32_t)((uint32_t)occ_id[c] & OCC_SLOT_MASK);
+    return SS_OK;
+}
+
+extern "C" int ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t* y, int32_t* vision, int32_t* metab,
+                                  double* sugar) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->have_agents) return SS_OK;
+    CK(cudaSetDevice(e->device));
+    std::vector<AgentRec> recs;
+    std::vector<int32_t> order;
+    int rc = fetch_population(e, &recs, &order);
+    if (rc) return rc;
+    const int N = e->w.n;
+    for (size_t i = 0; i < order.size(); i++) {
+        const AgentRec& r = recs[order[i]];
+        if (id) id[i] = order[i] + 1;
+        if (x) x[i] = (int32_t)(r.pos / N);
+        if (y) y[i] = (int32_t)(r.pos % N);
+        if (vision) vision[i] = attr_vision(r.attr);
+        if (metab) metab[i] = attr_metab(r.attr);
+        if (sugar) sugar[i] = r.sugar;
+    }
+    return SS_OK;
+}
+
+extern "C" int ss_get_counters(ss_engine* e, int64_t* out, int32_t n) {
+    if (!e || !out) return set_err(e, SS_ERR_ARG, "null argument");
+    const int64_t v[6] = {e->launches, e->passes, e->steps, e->path, e->syncs, e->geom.emax};
+    for (int i = 0; i < n && i < 6; i++) out[i] = v[i];
+    return SS_OK;
+}
+
+extern "C" int ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n) {
+    if (!e || !ms_out) return set_err(e, SS_ERR_ARG, "null argument");
+    for (int i = 0; i < n && i < KT_COUNT; i++) ms_out[i] = e->kt[i];
+    return SS_OK;
+}
+
+extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
+    if (!e || !name) return set_err(e, SS_ERR_ARG, "null argument");
+    const std::string k(name);
+    if (k == "path") {
+        e->path_option = (int)value;
+        if (e->have_agents) return choose_path(e);
+        return SS_OK;
+    }
+    if (k == "profile") { e->profile = value != 0; return SS_OK; }
+    if (k == "reset_times") { for (double& d : e->kt) d = 0; return SS_OK; }
+    if (k == "diffuse_impl") { e->diffuse_impl = (int)value; return SS_OK; }
+    return set_err(e, SS_ERR_ARG, "unknown option: " + k);
+}

@@ -1,0 +1,415 @@
+// ss_serial.cu -- serial-order timestep kernel (one CTA).
+//
+// Reproduces the reference's sequential agent loop exactly, including CPython's global
+// MT19937 stream (SS_RNG_MT19937) -- the mode that is bit-exact against the unmodified
+// reference on its shipped 50x50 presets -- and also serves as the universal fallback for
+// keyed runs the lattice path refuses.  One launch runs `nsteps` whole timesteps
+// (View.updateGame, sugarscape.py:506-686) back to back: order shuffle, agent loop,
+// statistics, growback / seasons, pollution diffusion.  With a single CTA on one SM the
+// 50x50 working set (70 KB of cells + 10 KB of agent records) stays L1-resident across
+// steps, so the kernel addresses the canonical HBM arrays directly.
+//
+// Warp 0 walks the execution order; its 32 lanes scan an agent's cross in parallel
+// (ballot-compacted candidate list, warp-shuffle argmax); lane 0 performs the inherently
+// sequential parts (Fisher-Yates shuffles on the RNG stream, the commit).  All warps join
+// for the order sort (keyed mode), the Gini sort and the environment phase.
+#include "ss_world.cuh"
+
+#define SERIAL_THREADS 256
+#define FULL 0xffffffffu
+
+struct SerialShared {
+    uint32_t mt[624];
+    int mti;
+    int rng_mode;
+    unsigned long long skey, akey;
+    uint32_t j;
+    int32_t food[SS_MAXC];
+    int32_t neigh[SS_MAXC];
+    double util[SS_MAXC];
+    double nb_inten[SS_MAXC];
+    double nb_metab[SS_MAXC];
+    int32_t nb_x[SS_MAXC], nb_y[SS_MAXC], nb_v[SS_MAXC];
+    double sum_m, sum_v;
+    int nw, kept, acted, deaths;
+};
+
+// ---------------------------------------------------------------- RNG (lane 0 of warp 0) ----
+__device__ static uint32_t mt_next(SerialShared& sh) {
+    uint32_t* mt = sh.mt;
+    if (sh.mti >= 624) {
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < 624 - 397; kk++) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        for (; kk < 623; kk++) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        sh.mti = 0;
+    }
+    uint32_t y = mt[sh.mti++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+__device__ static inline uint32_t rng_word(SerialShared& sh) {
+    if (sh.rng_mode == SS_RNG_MT19937) return mt_next(sh);
+    return ss_keyed_word(sh.akey, sh.j++);
+}
+// random.py:242 _randbelow_with_getrandbits
+__device__ static uint32_t randbelow(SerialShared& sh, uint32_t n) {
+    int k = 32 - __clz(n);
+    uint32_t r = rng_word(sh) >> (32 - k);
+    while (r >= n) r = rng_word(sh) >> (32 - k);
+    return r;
+}
+// random.py:350 shuffle
+__device__ static void shuffle_i32(SerialShared& sh, int32_t* a, int n) {
+    for (int i = n - 1; i >= 1; i--) {
+        uint32_t j = randbelow(sh, (uint32_t)i + 1u);
+        int32_t t = a[i]; a[i] = a[j]; a[j] = t;
+    }
+}
+
+// ------------------------------------------------------------------ CTA-wide bitonic sort ----
+template <class T>
+__device__ static void cta_bitonic_sort(T* a, int P) {
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    bool asc = ((i & k) == 0);
+                    T u = a[i], v = a[ixj];
+                    if ((u > v) == asc) { a[i] = v; a[ixj] = u; }
+                }
+            }
+            __syncthreads();
+        }
+}
+__device__ static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// --------------------------------------------------------------------- warp-level scans ----
+// agent.py:361-371 getFood (free cells, x-arm then y-arm, torus) / agent.py:391-407
+// getVisionNeighbourhood (occupants, own wrapped coordinate excluded).  Unshuffled.
+template <bool NEIGH>
+__device__ static int warp_scan_cross(const DevWorld& w, int x, int y, int v, int32_t* out, int lane) {
+    const int n = w.n, span = 2 * v + 1, K = 2 * span;
+    int m = 0;
+    for (int base = 0; base < K; base += 32) {
+        int k = base + lane;
+        bool take = false;
+        int val = 0;
+        if (k < K) {
+            int c, own;
+            if (k < span) { int wx = ss_wrap(x - v + k, n); c = wx * n + y; own = (wx == x); }
+            else { int wy = ss_wrap(y - v + (k - span), n); c = x * n + wy; own = (wy == y); }
+            uint32_t ow = w.occw[c];
+            if (NEIGH) { take = (ow != 0u) && !own; val = (int)occ_slot(ow); }
+            else { take = (ow == 0u); val = c; }
+        }
+        unsigned b = __ballot_sync(FULL, take);
+        if (take) out[m + __popc(b & ((1u << lane) - 1u))] = val;
+        m += __popc(b);
+    }
+    __syncwarp();
+    return m;
+}
+
+struct Best { double key; int d, p, c, sg; };
+__device__ static inline bool better(const Best& a, const Best& b) {
+    if (a.p < 0) return false;
+    if (b.p < 0) return true;
+    if (a.key != b.key) return a.key > b.key;
+    if (a.d != b.d) return a.d < b.d;
+    return a.p < b.p;
+}
+
+// environment.py:312-315
+__device__ static inline void pollute_site(const DevWorld& w, int64_t env_time, int c, double production,
+                                           double consumption) {
+    if (w.cfg.pollution_start_time <= env_time)
+        w.poll[c] += (production * w.cfg.pollution_a) + (consumption * w.cfg.pollution_b);
+}
+
+// agent.py:794-865 move(), no-spice branch
+__device__ static void warp_move(const DevWorld& w, SerialShared& sh, int s, int64_t env_time, int lane) {
+    const int n = w.n;
+    AgentRec* rec = &w.agents[s];
+    const int pos = (int)rec->pos, x = pos / n, y = pos % n, v = attr_vision(rec->attr);
+    int m = warp_scan_cross<false>(w, x, y, v, sh.food, lane);
+    if (lane == 0) { shuffle_i32(sh, sh.food, m); sh.food[m] = pos; }    // agent.py:369, 806
+    m += 1;
+    __syncwarp();
+    Best best; best.p = -1; best.key = 0; best.d = 0; best.c = 0; best.sg = 0;
+    for (int p = lane; p < m; p += 32) {
+        Best b;
+        b.c = sh.food[p]; b.p = p;
+        b.sg = (int)w.sugar[b.c];                                       // environment.py:98-100
+        b.d = abs(x - b.c / n) + abs(y - b.c % n);                      // agent.py:867-868
+        b.key = w.cfg.rule_pollution ? (double)b.sg / (1.0 + w.poll[b.c]) : (double)b.sg;
+        if (better(b, best)) best = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best b;
+        b.key = __shfl_xor_sync(FULL, best.key, o);
+        b.d = __shfl_xor_sync(FULL, best.d, o);
+        b.p = __shfl_xor_sync(FULL, best.p, o);
+        b.c = __shfl_xor_sync(FULL, best.c, o);
+        b.sg = __shfl_xor_sync(FULL, best.sg, o);
+        if (better(b, best)) best = b;
+    }
+    if (lane == 0) {
+        if (w.cfg.rule_pollution) pollute_site(w, env_time, best.c, (double)best.sg, 0.0);  // agent.py:825
+        rec->sugar = ss_set_sugar(ss_max0(rec->sugar + (double)best.sg));                  // agent.py:832
+        if (best.c != pos) {                                                                // agent.py:856-862
+            uint32_t ow = w.occw[pos];
+            w.occw[pos] = 0u;
+            w.occw[best.c] = ow;
+            rec->pos = (uint32_t)best.c;
+        }
+        w.sugar[best.c] = 0.0;                                                              // agent.py:864
+    }
+    __syncwarp();
+}
+
+// agent.py:1025-1141 utilicalcMove(), sugar-only (utilicalcSugar agent.py:980-992)
+__device__ static void warp_utilicalc(const DevWorld& w, SerialShared& sh, int s, int lane) {
+    const int n = w.n;
+    AgentRec* rec = &w.agents[s];
+    const int pos = (int)rec->pos, x = pos / n, y = pos % n, v = attr_vision(rec->attr);
+    int m = warp_scan_cross<false>(w, x, y, v, sh.food, lane);
+    if (lane == 0) {
+        shuffle_i32(sh, sh.food, m);          // getFood's shuffle, agent.py:369
+        shuffle_i32(sh, sh.food, m);          // agent.py:1033
+        sh.food[m] = pos;                     // agent.py:1035
+    }
+    m += 1;
+    int nb = warp_scan_cross<true>(w, x, y, v, sh.neigh, lane);
+    if (lane == 0) { shuffle_i32(sh, sh.neigh, nb); sh.neigh[nb] = s; }   // agent.py:405, 1039
+    nb += 1;
+    __syncwarp();
+    for (int q = lane; q < nb; q += 32) {
+        const AgentRec* b = &w.agents[sh.neigh[q]];
+        double bm = (double)attr_metab(b->attr);
+        double days = ss_py_floordiv(b->sugar, bm);                      // agent.py:870-872
+        sh.nb_inten[q] = 1.0 / (1.0 + days);
+        sh.nb_metab[q] = bm;
+        sh.nb_x[q] = (int)b->pos / n;
+        sh.nb_y[q] = (int)b->pos % n;
+        sh.nb_v[q] = attr_vision(b->attr);
+    }
+    __syncwarp();
+    const double extent = (double)(nb - 1);
+    double lmax = 0.0;
+    bool have = false;
+    for (int p = lane; p < m; p += 32) {
+        int c = sh.food[p];
+        int mx = c / n, my = c % n;
+        double site = (double)(int)w.sugar[c];
+        double u = 0.0;
+        for (int q = 0; q < nb; q++) {
+            double dur = (site / sh.nb_metab[q]) / w.cfg.max_capacity;
+            int bx = sh.nb_x[q], by = sh.nb_y[q], bv = sh.nb_v[q];
+            int cert = (bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv);
+            double t = 0.0;
+            t += (double)cert * (((sh.nb_inten[q] + dur) + 0.5 * 0.0) + extent);
+            if (sh.neigh[q] != s) t *= -1.0;
+            u += t;
+        }
+        sh.util[p] = u;
+        if (!have || u > lmax) { lmax = u; have = true; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double om = __shfl_xor_sync(FULL, lmax, o);
+        int oh = __shfl_xor_sync(FULL, (int)have, o);
+        if (oh && (!have || om > lmax)) { lmax = om; have = true; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int nmax = 0;
+        for (int p = 0; p < m; p++)
+            if (sh.util[p] == lmax) sh.neigh[nmax++] = sh.food[p];      // neigh[] reused as max_locations
+        int dest = sh.neigh[randbelow(sh, (uint32_t)nmax)];              // random.choice, agent.py:1108
+        uint32_t ow = w.occw[pos];                                       // agent.py:1121-1125
+        w.occw[pos] = 0u;
+        w.occw[dest] = ow;
+        rec->pos = (uint32_t)dest;
+        int sg = (int)w.sugar[dest];                                     // agent.py:1128-1130
+        rec->sugar = ss_set_sugar(ss_max0(rec->sugar + (double)sg));
+        w.sugar[dest] = 0.0;                                             // agent.py:1134
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- environment phase (CTA) ----
+__device__ static inline void grow_cell(const DevWorld& w, int c, double alpha) {      // environment.py:133-139
+    double v = w.sugar[c] + alpha;
+    double cp = w.cap[c];
+    w.sugar[c] = v <= cp ? v : cp;
+}
+__device__ static inline bool in_region(const int32_t r[4], int n, int x, int y) {     // environment.py:146-155
+    int imin = max(r[0], 0), jmin = max(r[1], 0), imax = min(r[2] + 1, n), jmax = min(r[3] + 1, n);
+    return x >= imin && x < imax && y >= jmin && y < jmax;
+}
+__device__ static void cta_environment(const DevWorld& w, int64_t iteration) {
+    const int n = w.n, cells = n * n;
+    if (w.cfg.rule_seasons) {                                             // sugarscape.py:642-655
+        if (w.cfg.rule_grow) {
+            bool summer = (iteration % (2 * (int64_t)w.cfg.season_period)) < w.cfg.season_period;
+            double an = summer ? w.cfg.season_on_factor : w.cfg.season_off_factor;
+            double as = summer ? w.cfg.season_off_factor : w.cfg.season_on_factor;
+            for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+                int x = c / n, y = c % n;
+                if (in_region(w.cfg.season_north, n, x, y)) grow_cell(w, c, an);
+                if (in_region(w.cfg.season_south, n, x, y)) grow_cell(w, c, as);
+            }
+        }
+    } else if (w.cfg.rule_grow) {                                         // sugarscape.py:657-659
+        for (int c = threadIdx.x; c < cells; c += blockDim.x) grow_cell(w, c, w.cfg.grow_factor);
+    }
+    __syncthreads();
+    // sugarscape.py:661-663 + environment.py:317-350: in-place sweep == anti-diagonal wavefront
+    if (w.cfg.rule_pollution && iteration >= w.cfg.diffusion_start_time &&
+        iteration % w.cfg.diffusion_rate == 0) {
+        double* p = w.poll;
+        for (int d = 0; d <= 2 * n - 2; d++) {
+            int x0 = max(0, d - n + 1), x1 = min(d, n - 1);
+            for (int x = x0 + (int)threadIdx.x; x <= x1; x += blockDim.x) {
+                int y = d - x;
+                double t = 0.0;
+                int c = 0;
+                if (y + 1 < n) { t += p[x * n + y + 1]; c++; }
+                if (y - 1 >= 0) { t += p[x * n + y - 1]; c++; }
+                if (x + 1 < n) { t += p[(x + 1) * n + y]; c++; }
+                if (x - 1 >= 0) { t += p[(x - 1) * n + y]; c++; }
+                p[x * n + y] = t / (double)c;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ kernel ----
+__global__ void __launch_bounds__(SERIAL_THREADS, 1)
+ss_serial_kernel(DevWorld w, int64_t iteration0, int64_t env_time0, int nsteps, int fused_env, int stats_base) {
+    __shared__ SerialShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 624; i += blockDim.x) sh.mt[i] = w.mt[i];
+    if (tid == 0) { sh.mti = *w.mti; sh.rng_mode = w.cfg.rng_mode; }
+    __syncthreads();
+    const OrderKey dummy = ss_order_key(0, w.half);
+    for (int step = 0; step < nsteps; step++) {
+        const int64_t iteration = iteration0 + step, env_time = env_time0 + step;
+        int n_order = *w.n_order;
+        // ---- execution order, sugarscape.py:517 ----
+        if (w.cfg.rng_mode == SS_RNG_MT19937) {
+            if (tid == 0) shuffle_i32(sh, w.order, n_order);
+        } else {
+            unsigned long long skey = ss_step_key(w.cfg.keyed_seed, iteration);
+            if (tid == 0) sh.skey = skey;
+            OrderKey ok = ss_order_key(skey, w.half);
+            int P = next_pow2(n_order);
+            for (int i = tid; i < P; i += blockDim.x)
+                w.sortkeys[i] = i < n_order
+                    ? (((unsigned long long)ss_priority(ok, (uint32_t)w.order[i]) << 32) | (uint32_t)w.order[i])
+                    : ~0ull;
+            __syncthreads();
+            cta_bitonic_sort(w.sortkeys, P);
+            for (int i = tid; i < n_order; i += blockDim.x) w.order[i] = (int32_t)(w.sortkeys[i] & 0xffffffffu);
+        }
+        (void)dummy;
+        if (tid == 0) { sh.sum_m = 0.0; sh.sum_v = 0.0; sh.nw = 0; sh.kept = 0; sh.acted = 0; sh.deaths = 0; }
+        __syncthreads();
+        // ---- agent loop, sugarscape.py:520-601 (warp 0) ----
+        if (warp == 0) {
+            int skip_next = 0, kept = 0;
+            for (int i = 0; i < n_order; i++) {
+                const int s = w.order[i];
+                if (skip_next) {                       // Q1: the agent after a dying agent loses its turn
+                    skip_next = 0;
+                    if (lane == 0) w.order[kept] = s;
+                    kept++;
+                    continue;
+                }
+                if (lane == 0 && w.cfg.rng_mode == SS_RNG_KEYED) {
+                    sh.akey = ss_agent_key(sh.skey, (uint32_t)s + 1u);
+                    sh.j = 0;
+                }
+                __syncwarp();
+                if (w.cfg.rule_move_eat) warp_move(w, sh, s, env_time, lane);
+                if (w.cfg.rule_utilicalc) warp_utilicalc(w, sh, s, lane);
+                int died = 0;
+                if (lane == 0) {
+                    AgentRec* rec = &w.agents[s];
+                    const int metab = attr_metab(rec->attr);
+                    if (w.cfg.rule_pollution && rec->sugar > 0.0)                     // sugarscape.py:566-567
+                        pollute_site(w, env_time, (int)rec->pos, 0.0, (double)metab);
+                    rec->sugar = ss_set_sugar(ss_max0(rec->sugar - (double)metab));  // sugarscape.py:569
+                    sh.sum_m += (double)metab;
+                    sh.sum_v += (double)attr_vision(rec->attr);
+                    w.wealth[sh.nw++] = rec->sugar;
+                    sh.acted++;
+                    if (w.cfg.rule_can_starve && rec->sugar <= 0.1) {                 // sugarscape.py:306-309
+                        rec->attr &= ~ATTR_ALIVE;
+                        w.occw[rec->pos] = 0u;                                        // sugarscape.py:595
+                        sh.deaths++;
+                        died = 1;
+                    } else {
+                        w.order[kept] = s;
+                    }
+                }
+                died = __shfl_sync(FULL, died, 0);
+                if (died) skip_next = 1; else kept++;
+            }
+            if (lane == 0) { sh.kept = kept; *w.n_order = kept; }
+        }
+        __syncthreads();
+        // ---- statistics, sugarscape.py:603-619 + calculateGini 269-280 ----
+        {
+            const int nw = sh.nw, kept = sh.kept;
+            int P = next_pow2(nw > 0 ? nw : 1);
+            for (int i = nw + tid; i < P; i += blockDim.x) w.wealth[i] = __longlong_as_double(0x7ff0000000000000ll);
+            __syncthreads();
+            cta_bitonic_sort(w.wealth, P);
+            if (tid == 0) {
+                ss_step_stats st;
+                st.population = (double)kept;
+                st.metabolism_mean = kept > 0 ? sh.sum_m / (double)kept : 0.0;
+                st.vision_mean = kept > 0 ? sh.sum_v / (double)kept : 0.0;
+                double height = 0.0, area = 0.0;
+                for (int i = 0; i < nw; i++) {
+                    double v = w.wealth[i];
+                    height += v;
+                    area += height - v / 2.0;
+                }
+                double fair = height * (double)nw / 2.0;
+                double g = fair == 0.0 ? 1.0 : (fair - area) / fair;
+                st.gini = kept > 0 ? g : 0.0;
+                st.acted = (double)sh.acted;
+                st.deaths = (double)sh.deaths;
+                w.stats[stats_base + step] = st;
+            }
+        }
+        __syncthreads();
+        if (fused_env) cta_environment(w, iteration);
+        __syncthreads();
+    }
+    for (int i = tid; i < 624; i += blockDim.x) w.mt[i] = sh.mt[i];
+    if (tid == 0) *w.mti = sh.mti;
+}
+
+extern "C" cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps,
+                                        int fused_env, int stats_base, cudaStream_t stream) {
+    ss_serial_kernel<<<1, SERIAL_THREADS, 0, stream>>>(w, iteration, env_time, nsteps, fused_env, stats_base);
+    return cudaGetLastError();
+}

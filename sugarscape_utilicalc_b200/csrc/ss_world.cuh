@@ -1,0 +1,48 @@
+// ss_world.cuh -- the device-resident world every kernel receives by value.
+#pragma once
+#include "ss_device.cuh"
+
+#define SS_GINI_BINS 65536          // wealth histogram bins of the lattice path (integer sugar)
+
+struct StepAccum {                  // per-step reduction targets of the lattice path
+    unsigned long long sum_metab;
+    unsigned long long sum_vision;
+    unsigned long long acted;
+    unsigned long long deaths;
+    unsigned long long pending;     // agents not yet resolved in the current step
+    unsigned long long population;  // living agents
+    unsigned long long hist_small;  // agents whose wealth is the 0.01 floor
+    unsigned long long inexact;     // wealth values the histogram cannot represent
+};
+
+struct DevWorld {
+    ss_config cfg;
+    int n;                          // lattice edge N
+    uint32_t n_slots;               // max Agent.id
+    int half;                       // Feistel half width for the keyed order
+    double* sugar;
+    double* cap;
+    double* poll;
+    uint32_t* occw;
+    AgentRec* agents;
+    // serial path (SS_RNG_MT19937, and the universal fallback)
+    int32_t* order;                 // persistent list order (slots)
+    int32_t* n_order;               // device scalar
+    double* wealth;                 // scratch, pow2-padded
+    unsigned long long* sortkeys;   // scratch, pow2-padded
+    uint32_t* mt;                   // 624 words
+    int32_t* mti;
+    ss_step_stats* stats;           // per-step outputs, device
+    // lattice path
+    StepAccum* acc;
+    uint32_t* hist;                 // SS_GINI_BINS
+    int vmax;                       // max vision over all agents
+};
+
+struct PassGeom {                   // window tiling of one move pass
+    int nwin;                       // windows per dimension
+    int emax;                       // max window extent (smem row stride)
+    int ew;                         // bitmap words per row
+    int shift_x, shift_y;           // tiling shift
+    int ring;                       // 2*vmax: agents closer than this to a window edge are not resolved
+};

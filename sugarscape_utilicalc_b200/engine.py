@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference's timestep interface over the C-ABI.
+
+`Engine.step()` is `View.updateGame()` (sugarscape.py:506-686): one call = one timestep; it
+returns what the reference appends to `View.population / metabolismMean / visionMean / gini`.
+State lives in HBM between calls; `download_*` are the reads the GUI would do.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import STATS_DTYPE, SsConfig
+from .settings import config_from_settings
+
+PATH_AUTO, PATH_SERIAL, PATH_LATTICE = -1, 0, 2
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, cfg, device=0, path=PATH_AUTO):
+        if not isinstance(cfg, SsConfig):
+            cfg = SsConfig.from_buffer_copy(bytes(cfg))
+        self._lib = capi.lib()
+        self.cfg = cfg
+        self.n = cfg.grid_size
+        self._h = C.c_void_p()
+        rc = self._lib.ss_create(C.byref(cfg), int(device), C.byref(self._h))
+        if rc != 0:
+            raise EngineError("ss_create: " + self._lib.ss_last_error(None).decode())
+        if path != PATH_AUTO:
+            self.set_option("path", path)
+
+    @classmethod
+    def from_settings(cls, settings, rng="mt", keyed_seed=None, device=0, path=PATH_AUTO, iteration=0, env_time=0):
+        return cls(config_from_settings(settings, rng_mode=rng, keyed_seed=keyed_seed, iteration=iteration,
+                                        env_time=env_time), device=device, path=path)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s: %s" % (what, self._lib.ss_last_error(self._h).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ss_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- uploads ---------------------------------------------------------------------------
+    def upload_cells(self, sugar, cap, pollution=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        s, c, p = f(sugar), f(cap), f(pollution)
+        if s.size != self.n * self.n or c.size != self.n * self.n or (p is not None and p.size != self.n * self.n):
+            raise ValueError("cell arrays must be (N,N)")
+        self._check(self._lib.ss_upload_cells(self._h, _ptr(s), _ptr(c), _ptr(p)), "ss_upload_cells")
+
+    def upload_agents(self, id, x, y, vision, metab, sugar):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        id, x, y, vision, metab = map(i32, (id, x, y, vision, metab))
+        sugar = np.ascontiguousarray(sugar, dtype=np.float64)
+        if not (len(id) == len(x) == len(y) == len(vision) == len(metab) == len(sugar)):
+            raise ValueError("agent arrays must have equal length")
+        self._check(self._lib.ss_upload_agents(self._h, len(id), _ptr(id), _ptr(x), _ptr(y), _ptr(vision),
+                                               _ptr(metab), _ptr(sugar)), "ss_upload_agents")
+
+    def set_rng_mt19937(self, state, index):
+        st = np.ascontiguousarray(state, dtype=np.uint32)
+        if st.size != 624:
+            raise ValueError("MT19937 state has 624 words")
+        self._check(self._lib.ss_set_rng_mt19937(self._h, _ptr(st), int(index)), "ss_set_rng_mt19937")
+
+    def get_rng_mt19937(self):
+        st = np.empty(624, dtype=np.uint32)
+        idx = C.c_int32()
+        self._check(self._lib.ss_get_rng_mt19937(self._h, _ptr(st), C.byref(idx)), "ss_get_rng_mt19937")
+        return st, idx.value
+
+    def set_rng_keyed(self, seed):
+        self._check(self._lib.ss_set_rng_keyed(self._h, int(seed) & ((1 << 64) - 1)), "ss_set_rng_keyed")
+
+    # -- the hot path ----------------------------------------------------------------------
+    def step(self, nsteps=1, want_stats=True):
+        out = np.zeros(nsteps, dtype=STATS_DTYPE) if want_stats else None
+        self._check(self._lib.ss_step(self._h, int(nsteps), _ptr(out)), "ss_step")
+        return out
+
+    # -- downloads -------------------------------------------------------------------------
+    def agent_count(self):
+        return int(self._lib.ss_agent_count(self._h))
+
+    def download_cells(self, sugar=True, cap=True, pollution=True, occ=True):
+        n = self.n
+        mk = lambda on, dt: np.empty((n, n), dtype=dt) if on else None
+        s, c, p, o = mk(sugar, np.float64), mk(cap, np.float64), mk(pollution, np.float64), mk(occ, np.int32)
+        self._check(self._lib.ss_download_cells(self._h, _ptr(s), _ptr(c), _ptr(p), _ptr(o)), "ss_download_cells")
+        return dict(sugar=s, cap=c, pollution=p, occ=o)
+
+    def download_agents(self):
+        k = self.agent_count()
+        id, x, y, vision, metab = (np.empty(k, dtype=np.int32) for _ in range(5))
+        sugar = np.empty(k, dtype=np.float64)
+        self._check(self._lib.ss_download_agents(self._h, _ptr(id), _ptr(x), _ptr(y), _ptr(vision), _ptr(metab),
+                                                 _ptr(sugar)), "ss_download_agents")
+        return dict(id=id, x=x, y=y, vision=vision, metab=metab, sugar=sugar)
+
+    # -- instrumentation -------------------------------------------------------------------
+    def counters(self):
+        out = np.zeros(6, dtype=np.int64)
+        self._check(self._lib.ss_get_counters(self._h, _ptr(out), 6), "ss_get_counters")
+        return dict(launches=int(out[0]), passes=int(out[1]), steps=int(out[2]), path=int(out[3]),
+                    syncs=int(out[4]), window=int(out[5]))
+
+    def kernel_times(self):
+        out = np.zeros(6, dtype=np.float64)
+        self._check(self._lib.ss_get_kernel_times(self._h, _ptr(out), 6), "ss_get_kernel_times")
+        return dict(zip(("prepare", "move", "stats", "grow", "diffuse", "serial"), out.tolist()))
+
+    def set_option(self, name, value):
+        self._check(self._lib.ss_set_option(self._h, name.encode(), int(value)), "ss_set_option")

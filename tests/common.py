@@ -1,0 +1,148 @@
+"""Shared test helpers: golden fixtures, world construction for the CPU oracle and the CUDA
+engine (same call sequence), and the comparison routines."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from sugarscape_utilicalc_b200 import config_from_settings, synthetic  # noqa: E402
+
+GOLDEN_CASES = [
+    "c1_default_utilicalc_mt", "c1_default_moveeat_mt", "c2_seasons_mt", "c2_pollution_mt",
+    "c3_utilicalc_sugar_mt", "c1_default_moveeat_keyed", "c1_default_utilicalc_keyed", "c2_seasons_keyed",
+    "c2_pollution0_keyed", "c4_synth96_poll_keyed", "c4_synth130_nopoll_keyed",
+]
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+    g["settings"] = json.loads(str(g["settings_json"]))
+    g["rng"] = str(g["rng"])
+    g["steps"] = int(g["steps"])
+    return g
+
+
+def oracle_world(cfg):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import OracleWorld
+    return OracleWorld(cfg)
+
+
+def engine_world(cfg, path=-1):
+    from sugarscape_utilicalc_b200.engine import Engine
+    return Engine(cfg, path=path)
+
+
+def init_world(world, init, rng, mt=None, mt_index=None):
+    world.upload_cells(init["sugar"], init["cap"], init["pollution"])
+    world.upload_agents(init["id"], init["x"], init["y"], init["vision"], init["metab"], init["sugar_agent"])
+    if rng == "mt":
+        world.set_rng_mt19937(mt, mt_index)
+
+
+def golden_init(g):
+    return dict(sugar=g["init_sugar"], cap=g["init_cap"], pollution=g["init_pollution"], id=g["init_order"],
+                x=g["init_x"], y=g["init_y"], vision=g["init_vision"], metab=g["init_metab"],
+                sugar_agent=g["init_sugar_agent"])
+
+
+def world_from_golden(g, kind, path=-1):
+    cfg = config_from_settings(g["settings"], rng_mode=g["rng"])
+    w = oracle_world(cfg) if kind == "oracle" else engine_world(cfg, path)
+    init_world(w, golden_init(g), g["rng"], g["init_mt"], int(g["init_mt_index"]))
+    return w
+
+
+def assert_state_equal(cells, agents, exp, ordered=True, what=""):
+    """exp: dict with sugar, pollution, occ, order, x, y, sugar_agent (a reference snapshot)."""
+    assert np.array_equal(cells["occ"], exp["occ"]), what + ": occupancy differs"
+    assert np.array_equal(cells["sugar"], exp["sugar"]), what + ": cell sugar differs"
+    assert np.array_equal(cells["pollution"], exp["pollution"]), what + ": pollution differs"
+    ids, eids = agents["id"], exp["order"]
+    if ordered:
+        assert np.array_equal(ids, eids), what + ": agent list order differs"
+        o = eo = slice(None)
+    else:
+        o, eo = np.argsort(ids, kind="stable"), np.argsort(eids, kind="stable")
+        assert np.array_equal(ids[o], eids[eo]), what + ": set of living agents differs"
+    assert np.array_equal(agents["x"][o], exp["x"][eo]) and np.array_equal(agents["y"][o], exp["y"][eo]), \
+        what + ": agent positions differ"
+    assert np.array_equal(agents["sugar"][o], exp["sugar_agent"][eo]), what + ": agent sugar differs"
+
+
+def run_against_golden(g, world, exact_gini=True, chunk=None, max_steps=None):
+    """Step `world` through the golden run; compare the stat series every step and the full
+    state at every checkpoint."""
+    steps = g["steps"] if max_steps is None else min(max_steps, g["steps"])
+    cps = sorted(int(k[2:].split("_")[0]) for k in g if k.startswith("cp") and k.endswith("_occ"))
+    cps = [c for c in cps if c <= steps]
+    t = 0
+    for cp in cps:
+        while t < cp:
+            k = cp - t if chunk is None else min(chunk, cp - t)
+            st = world.step(k)
+            sl = slice(t, t + k)
+            assert np.array_equal(st["population"], g["population"][sl]), "population differs in steps %d..%d" % (t, t + k)
+            assert np.array_equal(st["metabolism_mean"], g["metabolismMean"][sl]), "metabolismMean differs"
+            assert np.array_equal(st["vision_mean"], g["visionMean"][sl]), "visionMean differs"
+            if exact_gini:
+                assert np.array_equal(st["gini"], g["gini"][sl]), "gini differs in steps %d..%d" % (t, t + k)
+            else:
+                np.testing.assert_allclose(st["gini"], g["gini"][sl], rtol=1e-9, atol=1e-12)
+            t += k
+        exp = {k2: g["cp%d_%s" % (cp, k2)] for k2 in ("sugar", "pollution", "occ", "order", "x", "y", "sugar_agent")}
+        assert_state_equal(world.download_cells(), world.download_agents(), exp, ordered=True, what="step %d" % cp)
+    if g["rng"] == "mt" and steps == g["steps"]:
+        mt, idx = world.get_rng_mt19937()
+        assert idx == int(g["final_mt_index"]) and np.array_equal(mt, g["final_mt"]), "MT19937 state differs"
+    return t
+
+
+def synthetic_case(n, pollution, seed=1234, density=1.0 / 16.0, vision=(1, 6), rng="keyed", seasons=False,
+                   utilicalc=False):
+    w = synthetic.tiled_world(n, density=density, seed=seed, vision=vision)
+    s = synthetic.synthetic_settings(n, pollution=pollution, seasons=seasons, utilicalc=utilicalc)
+    init = dict(sugar=w["sugar"], cap=w["cap"], pollution=w["pollution"], id=w["id"], x=w["x"], y=w["y"],
+                vision=w["vision"], metab=w["metab"], sugar_agent=w["sugar_agent"])
+    return s, init
+
+
+def compare_worlds(a, b, steps, exact_gini=False, every=1, what=""):
+    """Step two worlds (e.g. engine and oracle) side by side and compare."""
+    for t in range(0, steps, every):
+        k = min(every, steps - t)
+        sa, sb = a.step(k), b.step(k)
+        for f in ("population", "metabolism_mean", "vision_mean", "acted", "deaths"):
+            assert np.array_equal(sa[f], sb[f]), "%s: %s differs at steps %d..%d: %s vs %s" % (what, f, t, t + k, sa[f], sb[f])
+        if exact_gini:
+            assert np.array_equal(sa["gini"], sb["gini"]), what + ": gini differs"
+        else:
+            np.testing.assert_allclose(sa["gini"], sb["gini"], rtol=1e-9, atol=1e-12)
+        ca, cb = a.download_cells(), b.download_cells()
+        ga, gb = a.download_agents(), b.download_agents()
+        exp = dict(sugar=cb["sugar"], pollution=cb["pollution"], occ=cb["occ"], order=gb["id"], x=gb["x"], y=gb["y"],
+                   sugar_agent=gb["sugar"])
+        assert_state_equal(ca, ga, exp, ordered=True, what="%s step %d" % (what, t + k))
+
+
+def smoke_check():
+    """__graft_entry__.smoke(): shipped default preset (MT-exact, utilicalc) for 20 steps and a
+    small synthetic keyed lattice run, both checked against the CPU oracle / golden vectors."""
+    g = load_golden("c1_default_utilicalc_mt")
+    w = world_from_golden(g, "engine")
+    run_against_golden(g, w, exact_gini=True, max_steps=20)
+    w.close()
+    s, init = synthetic_case(200, pollution=True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = engine_world(cfg), oracle_world(cfg)
+    init_world(e, init, "keyed")
+    init_world(o, init, "keyed")
+    compare_worlds(e, o, 6, what="synthetic 200x200")
+    assert e.counters()["path"] == 2, "lattice path was not selected"
+    e.close()

@@ -1,0 +1,153 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI, against the golden vectors of
+the unmodified reference and against the CPU oracle on the same seeded inputs.
+
+Bar: cells, occupancy, agent positions / sugar / list order, population, means and the
+MT19937 state are bit-exact; the Gini coefficient of the lattice path (histogram formula
+instead of a sequential float sum) agrees to 1e-9 relative."""
+import numpy as np
+import pytest
+
+import common
+from sugarscape_utilicalc_b200 import config_from_settings
+
+pytestmark = pytest.mark.gpu
+
+MT_CASES = [c for c in common.GOLDEN_CASES if c.endswith("_mt")]
+KEYED_CASES = [c for c in common.GOLDEN_CASES if c.endswith("_keyed")]
+KEYED_MOVE_CASES = [c for c in KEYED_CASES if "utilicalc" not in c]
+
+
+@pytest.mark.parametrize("name", MT_CASES)
+def test_mt_exact_presets(name):
+    """Shipped presets, CPython-exact MT19937 stream: bit-exact trajectories, every step."""
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "engine")
+    assert w.counters()["path"] == 0
+    assert common.run_against_golden(g, w, exact_gini=True) == g["steps"]
+    w.close()
+
+
+def test_mt_exact_single_steps_equal_fused_steps():
+    g = common.load_golden("c2_pollution_mt")
+    w = common.world_from_golden(g, "engine")
+    common.run_against_golden(g, w, exact_gini=True, chunk=1, max_steps=120)
+    w.close()
+
+
+@pytest.mark.parametrize("name", KEYED_CASES)
+def test_keyed_serial_path(name):
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "engine", path=0)
+    assert w.counters()["path"] == 0
+    common.run_against_golden(g, w, exact_gini=True)
+    w.close()
+
+
+@pytest.mark.parametrize("name", KEYED_MOVE_CASES)
+def test_keyed_lattice_path(name):
+    """Parallel dependency rounds reproduce the sequential loop of the reference (keyed words)."""
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "engine", path=2)
+    assert w.counters()["path"] == 2
+    common.run_against_golden(g, w, exact_gini=False)
+    w.close()
+
+
+@pytest.mark.parametrize("n,pollution,steps,vision", [
+    (64, True, 12, (1, 6)), (177, True, 10, (1, 6)), (200, False, 10, (1, 6)), (257, True, 8, (1, 6)),
+    (300, True, 8, (1, 10)), (512, True, 8, (1, 6)), (1000, True, 5, (1, 6)), (1024, False, 6, (1, 6)),
+])
+def test_lattice_vs_oracle_synthetic(n, pollution, steps, vision):
+    s, init = common.synthetic_case(n, pollution, vision=vision)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert e.counters()["path"] == 2
+    common.compare_worlds(e, o, steps, what="synthetic %d" % n)
+    e.close()
+    o.close()
+
+
+def test_lattice_dense_population():
+    """density 1/3: deep dependency chains, many ties, many deaths (Q1 skips)."""
+    s, init = common.synthetic_case(150, True, density=1.0 / 3.0)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(e, o, 15, what="dense 150")
+    s, init = common.synthetic_case(400, False, density=1.0 / 3.0)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(e, o, 10, what="dense 400")
+
+
+def test_lattice_seasons():
+    s, init = common.synthetic_case(260, False, seasons=True)
+    s["rule_params"]["seasons"]["period"] = 3
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(e, o, 9, what="seasons 260")
+
+
+def test_diffusion_wavefront_equals_diagonal_sweep():
+    s, init = common.synthetic_case(700, True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    a, b = common.engine_world(cfg), common.engine_world(cfg)
+    b.set_option("diffuse_impl", 1)
+    for w in (a, b):
+        common.init_world(w, init, "keyed")
+        w.step(4)
+    assert np.array_equal(a.download_cells()["pollution"], b.download_cells()["pollution"])
+
+
+def test_mt_serial_env_path_large_grid():
+    """MT19937 mode on a grid too large for the fused kernel: serial agents + lattice env kernels."""
+    s, init = common.synthetic_case(300, True, density=1.0 / 64.0)
+    cfg = config_from_settings(s, rng_mode="mt")
+    mt = np.arange(624, dtype=np.uint32) * np.uint32(2654435761) + np.uint32(12345)
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "mt", mt, 624)
+    common.init_world(o, init, "mt", mt, 624)
+    assert e.counters()["path"] == 1
+    common.compare_worlds(e, o, 5, exact_gini=True, what="mt 300")
+    me, ie = e.get_rng_mt19937()
+    mo, io = o.get_rng_mt19937()
+    assert ie == io and np.array_equal(me, mo)
+
+
+def test_unsupported_configurations_fail_loudly():
+    from sugarscape_utilicalc_b200.engine import Engine, EngineError
+    s, init = common.synthetic_case(64, True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    cfg.rule_utilicalc, cfg.rule_move_eat = 1, 0
+    with pytest.raises(EngineError):
+        Engine(cfg)                       # utilicalc + pollution: the reference crashes
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e = Engine(cfg)
+    with pytest.raises(EngineError):
+        e.step(1)                         # nothing uploaded
+    bad = dict(init)
+    bad["x"] = init["x"].copy(); bad["y"] = init["y"].copy()
+    bad["x"][1], bad["y"][1] = bad["x"][0], bad["y"][0]
+    e.upload_cells(init["sugar"], init["cap"], init["pollution"])
+    with pytest.raises(EngineError):
+        e.upload_agents(bad["id"], bad["x"], bad["y"], bad["vision"], bad["metab"], bad["sugar_agent"])
+
+
+def test_empty_population_and_extinction():
+    s, init = common.synthetic_case(64, False)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    for path in (0, 2):
+        e, o = common.engine_world(cfg, path), common.oracle_world(cfg)
+        for w in (e, o):
+            w.upload_cells(np.zeros((64, 64)), np.zeros((64, 64)), None)      # barren: everyone starves
+            w.upload_agents(init["id"][:40], init["x"][:40], init["y"][:40], init["vision"][:40], init["metab"][:40],
+                            np.full(40, 3.0))
+        common.compare_worlds(e, o, 14, what="extinction path %d" % path)
+        assert e.agent_count() == len(o.download_agents()["id"]) == 0

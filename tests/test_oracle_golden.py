@@ -1,0 +1,19 @@
+"""CPU: the C oracle against the golden vectors the unmodified reference produced."""
+import pytest
+
+import common
+
+
+@pytest.mark.parametrize("name", common.GOLDEN_CASES)
+def test_oracle_matches_reference_golden(name):
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "oracle")
+    assert common.run_against_golden(g, w, exact_gini=True) == g["steps"]
+    w.close()
+
+
+def test_oracle_chunked_steps_equal_single_steps():
+    g = common.load_golden("c2_pollution_mt")
+    w = common.world_from_golden(g, "oracle")
+    common.run_against_golden(g, w, exact_gini=True, chunk=7, max_steps=100)
+    w.close()
