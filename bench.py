@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the Sugarscape timestep hot path on synthetic NxN lattices.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|<n>] [--impl reference]
+
+One "step" = one whole timestep (View.updateGame, sugarscape.py:506-686) over the workload.
+Workloads:
+  c5 (default)  16384 x 16384 tiled two-peak landscape, 16,777,216 agents, vision 1-6,
+                grow + moveEat + canStarve, keyed RNG seed 18        <- the metric's config
+  c4            4096 x 4096, 1,048,576 agents, same rules + pollution (A=B=1, diffusion every step)
+The JSON line carries: value (state resident in HBM, device-timed with CUDA events on the
+engine's stream), e2e (through the public Python API with host buffers: upload + K steps
+with per-step stats read-back + download), roofline of the dominant kernel class measured
+live with CUDA events in a second instrumented run, cpu_baseline (the C oracle port on a
+bounded sample of the same world) and the GPU clocks sampled during the timed region.
+
+--impl reference times the reference's CPU algorithm (the oracle port, oracle/ss_oracle.c --
+the Python reference itself cannot travel to the GPU box) on the host, single-threaded
+like the reference's loop.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sugarscape_utilicalc_b200 import config_from_settings, synthetic  # noqa: E402
+
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def workload(name):
+    if name == "c5":
+        return dict(n=16384, pollution=False, label="c5: 16384x16384 tiled landscape, 16777216 agents, "
+                    "grow+moveEat+canStarve, vision 1-6, keyed RNG seed 18")
+    if name == "c4":
+        return dict(n=4096, pollution=True, label="c4: 4096x4096 tiled landscape, 1048576 agents, "
+                    "grow+moveEat+canStarve+pollution(A=B=1, diffusion every step), vision 1-6, keyed RNG seed 18")
+    n = int(name)
+    return dict(n=n, pollution=False, label="synthetic %dx%d tiled landscape, %d agents, grow+moveEat+canStarve"
+                % (n, n, n * n // 16))
+
+
+def make_world(wl):
+    t0 = time.time()
+    w = synthetic.tiled_world(wl["n"])
+    s = synthetic.synthetic_settings(wl["n"], pollution=wl["pollution"])
+    sys.stderr.write("[bench] world %dx%d, %d agents generated in %.1fs\n" % (wl["n"], wl["n"], len(w["id"]),
+                                                                               time.time() - t0))
+    return s, w
+
+
+def upload(world, w):
+    world.upload_cells(w["sugar"], w["cap"], w["pollution"])
+    world.upload_agents(w["id"], w["x"], w["y"], w["vision"], w["metab"], w["sugar_agent"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_sample(settings, w, n_sample, steps, warmup=0):
+    """The C oracle (port of the reference loop) on the top-left n_sample^2 sub-lattice of the world."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import OracleWorld
+    n = w["cap"].shape[0]
+    ns = min(n_sample, n)
+    keep = (w["x"] < ns) & (w["y"] < ns)
+    s = json.loads(json.dumps(settings))
+    s["view"]["grid_size"] = {"x": ns, "y": ns}
+    cfg = config_from_settings(s, rng_mode="keyed")
+    o = OracleWorld(cfg)
+    o.upload_cells(np.ascontiguousarray(w["sugar"][:ns, :ns]), np.ascontiguousarray(w["cap"][:ns, :ns]),
+                   np.ascontiguousarray(w["pollution"][:ns, :ns]))
+    k = int(keep.sum())
+    o.upload_agents(np.arange(1, k + 1, dtype=np.int32), w["x"][keep], w["y"][keep], w["vision"][keep],
+                    w["metab"][keep], w["sugar_agent"][keep])
+    pop = k
+    if warmup:
+        pop = int(o.step(warmup)["population"][-1])
+    t0 = time.perf_counter()
+    st = o.step(steps)
+    dt = time.perf_counter() - t0
+    pops = np.concatenate([[pop], st["population"][:-1]])
+    o.close()
+    return dict(agent_steps=float(pops.sum()), seconds=dt, n=ns, agents=k, steps=steps)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    settings, w = make_world(dict(wl, n=min(wl["n"], 4096)))
+    ns = 2048 if wl["pollution"] else 4096
+    ns = min(ns, w["cap"].shape[0])
+    r = oracle_sample(settings, w, ns, args.steps, args.warmup)
+    value = r["agent_steps"] / r["seconds"]
+    sample = ("C port of the reference's sequential loop (oracle/ss_oracle.c; the Python reference cannot travel to the "
+              "GPU box), 1 thread, %dx%d sub-lattice of the workload's landscape with %d agents, %d steps after %d warm-up"
+              % (r["n"], r["n"], r["agents"], r["steps"], args.warmup))
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "timing": "host wall clock, bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cell_updates_per_s": r["n"] * r["n"] * r["steps"] / r["seconds"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def algorithmic_bytes(n, pollution, acted, mean_vision=3.5):
+    """grow 24 B/cell, diffusion 16 B/cell, move 100+80v (pollution) / 76+48v B/agent-step."""
+    per_agent = (100 + 80 * mean_vision) if pollution else (76 + 48 * mean_vision)
+    return dict(grow=24.0 * n * n, diffuse=16.0 * n * n if pollution else 0.0, move=per_agent * acted)
+
+
+def run_engine_single(args, wl):
+    from sugarscape_utilicalc_b200.engine import Engine
+    settings, w = make_world(wl)
+    n = wl["n"]
+    cfg = config_from_settings(settings, rng_mode="keyed")
+    peak, peak_src = measured_peak()
+    K, W = args.steps, args.warmup
+    # ---------------- value: state resident in HBM, device-timed ----------------
+    eng = Engine(cfg)
+    t0 = time.perf_counter()
+    upload(eng, w)
+    t_upload = time.perf_counter() - t0
+    pop0 = len(w["id"])
+    if W:
+        st = eng.step(W)
+        pop0 = int(st["population"][-1])
+    eng.set_option("reset_counters", 0)
+    sampler = ClockSampler(0)
+    sampler.start()
+    st = eng.step(K)
+    ms = eng.kernel_times()["last_call"]
+    clocks = sampler.stop()
+    cnt = eng.counters()
+    pops = np.concatenate([[pop0], st["population"][:-1]])
+    agent_steps = float(pops.sum())
+    value = agent_steps / (ms * 1e-3)
+    acted = float(st["acted"].sum())
+    # ---------------- instrumented run: per-kernel-class device time (CUDA events) ----------------
+    eng.set_option("profile", 1)
+    eng.set_option("reset_times", 0)
+    st2 = eng.step(K)
+    kt = eng.kernel_times()
+    eng.set_option("profile", 0)
+    acted2 = float(st2["acted"].sum())
+    ab = algorithmic_bytes(n, wl["pollution"], acted2 / K)
+    classes = {"move": ("move", ab["move"]), "grow": ("grow", ab["grow"]), "diffuse": ("diffuse", ab["diffuse"])}
+    kernels = {}
+    tot = sum(kt[k] for k in ("prepare", "move", "stats", "grow", "diffuse"))
+    for name, (key, nbytes) in classes.items():
+        t = kt[key] / K
+        if t > 0:
+            kernels[name] = {"ms_per_step": t, "share": kt[key] / tot, "algorithmic_bytes_per_step": nbytes,
+                             "achieved_gbs": nbytes / (t * 1e-3) / 1e9, "frac": nbytes / (t * 1e-3) / 1e9 / peak}
+    kernels["prepare+stats"] = {"ms_per_step": (kt["prepare"] + kt["stats"]) / K,
+                                "share": (kt["prepare"] + kt["stats"]) / tot}
+    dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
+    roofline = {"bound": "hbm", "kernel": {"move": "ss_move_pass_kernel (all passes of a step)",
+                                           "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
+                "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "ms_per_launch_set": kernels[dom]["ms_per_step"]}
+    whole_bytes = ab["move"] + ab["grow"] + ab["diffuse"]
+    step_frac = whole_bytes / (ms / K * 1e-3) / 1e9 / peak
+    eng.close()
+    # ---------------- e2e: public API with host buffers ----------------
+    Ke = min(K, args.e2e_steps)
+    t0 = time.perf_counter()
+    eng = Engine(cfg)
+    upload(eng, w)
+    ste = eng.step(Ke)                       # per-step stats are read back to the host
+    cells = eng.download_cells(cap=False)
+    ags = eng.download_agents()
+    t_e2e = time.perf_counter() - t0
+    eng.close()
+    popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
+    e2e_value = float(popse.sum()) / t_e2e
+    h2d = (3 * 8 * n * n + 4 * n * n + 32 * len(w["id"])) / Ke
+    d2h = ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke
+    del cells, ags
+    # ---------------- cpu baseline: oracle port on a bounded sample ----------------
+    cpu = None
+    if not args.no_cpu:
+        ns = 1024 if wl["pollution"] else 2048
+        r = oracle_sample(settings, w, ns, 5)
+        cpu = {"value": r["agent_steps"] / r["seconds"], "unit": "agent-steps/s", "cores": 1, "kind": "port",
+               "sample": "oracle/ss_oracle.c (C port of the reference loop), 1 thread, %dx%d sub-lattice of the same "
+                         "world, %d agents, 5 steps (%.1f s)" % (r["n"], r["n"], r["agents"], r["seconds"]),
+               "host_cpus": os.cpu_count()}
+    line = {
+        "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "grid": n, "agents": len(w["id"]),
+                   "l2": "working set %.1f GB >> 126 MB L2, no flush needed" % ((28.0 if wl["pollution"] else 20.0) * n * n / 1e9),
+                   "timing": "CUDA events on the engine stream around ss_step(K)"},
+        "cell_updates_per_s": n * n * K / (ms * 1e-3),
+        "population": [int(pop0), int(st["population"][-1])],
+        "passes_per_step": cnt["passes"] / K, "gpu_launches": cnt["launches"],
+        "host_syncs_per_step": cnt["syncs"] / K,
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "seconds": t_e2e,
+                "what": "Engine(cfg); upload_cells/agents from host numpy; step(K) with stats read-back; "
+                        "download_cells+download_agents to host"},
+        "roofline": roofline,
+        "step_roofline": {"algorithmic_bytes_per_step": whole_bytes, "frac_of_peak": step_frac},
+        "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "upload_s": t_upload,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SS_BENCH_WORKLOAD", "c5"))
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from sugarscape_utilicalc_b200 import sharded
+        sharded.bench_main(args, wl)
+        return
+    run_engine_single(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,7 @@ cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl,
 }
 
 enum { PATH_SERIAL_FUSED = 0, PATH_SERIAL_ENV = 1, PATH_LATTICE = 2 };
-enum { KT_PREPARE = 0, KT_MOVE, KT_STATS, KT_GROW, KT_DIFFUSE, KT_SERIAL, KT_COUNT };
+enum { KT_PREPARE = 0, KT_MOVE, KT_STATS, KT_GROW, KT_DIFFUSE, KT_SERIAL, KT_LAST_CALL, KT_COUNT };
 
 struct ss_engine {
     ss_config cfg;
@@ -46,8 +46,8 @@ struct ss_engine {
     std::vector<int32_t> upload_order;          // slots in upload order
     int64_t launches = 0, passes = 0, steps = 0, syncs = 0;
     bool profile = false;
-    double kt[KT_COUNT] = {0, 0, 0, 0, 0, 0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double kt[KT_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr, eve = nullptr;
     std::string err;
 };
 
@@ -127,6 +127,8 @@ extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) 
     cudaMemset(e->w.acc, 0, sizeof(StepAccum));
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
+    cudaEventCreate(&e->evs);
+    cudaEventCreate(&e->eve);
     *out = e;
     return SS_OK;
 }
@@ -142,6 +144,8 @@ extern "C" void ss_destroy(ss_engine* e) {
     if (e->h_pending) cudaFreeHost(e->h_pending);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->evs) cudaEventDestroy(e->evs);
+    if (e->eve) cudaEventDestroy(e->eve);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -364,6 +368,7 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     CK(cudaSetDevice(e->device));
     int rc = ensure_stats(e, nsteps);
     if (rc) return rc;
+    CK(cudaEventRecord(e->evs, e->stream));
     if (e->path == PATH_SERIAL_FUSED) {
         KTimer t(e, KT_SERIAL);
         CK(ss_launch_serial(e->w, e->iteration, e->env_time, nsteps, 1, 0, e->stream));
@@ -386,9 +391,15 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
         }
     }
     e->stepped = true;
+    CK(cudaEventRecord(e->eve, e->stream));
     if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->syncs++;
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->evs, e->eve);      // device time of this call, events on the engine's stream
+        e->kt[KT_LAST_CALL] = ms;
+    }
     return SS_OK;
 }
 
@@ -495,6 +506,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     }
     if (k == "profile") { e->profile = value != 0; return SS_OK; }
     if (k == "reset_times") { for (double& d : e->kt) d = 0; return SS_OK; }
+    if (k == "reset_counters") { e->launches = e->passes = e->syncs = 0; return SS_OK; }
     if (k == "diffuse_impl") { e->diffuse_impl = (int)value; return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }
