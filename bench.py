@@ -211,6 +211,7 @@ def run_engine_single(args, wl):
     eng.set_option("profile", 0)
     acted2 = float(st2["acted"].sum())
     ab = algorithmic_bytes(n, wl["pollution"], acted2 / K)
+    kt["move"] += kt["settle"]          # the agent phase = move passes + the deferred settle pass
     classes = {"move": ("move", ab["move"]), "grow": ("grow", ab["grow"]), "diffuse": ("diffuse", ab["diffuse"])}
     kernels = {}
     tot = sum(kt[k] for k in ("prepare", "move", "stats", "grow", "diffuse"))
@@ -222,7 +223,7 @@ def run_engine_single(args, wl):
     kernels["prepare+stats"] = {"ms_per_step": (kt["prepare"] + kt["stats"]) / K,
                                 "share": (kt["prepare"] + kt["stats"]) / tot}
     dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
-    roofline = {"bound": "hbm", "kernel": {"move": "ss_move_pass_kernel (all passes of a step)",
+    roofline = {"bound": "hbm", "kernel": {"move": "ss_move_pass_kernel (all passes of a step) + ss_settle_kernel",
                                            "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,

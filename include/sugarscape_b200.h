@@ -125,10 +125,12 @@ int  ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t* y, int32
 int  ss_get_counters(ss_engine* e, int64_t* out, int32_t n);
 /* accumulated device milliseconds per kernel class (needs option "profile"=1):
  * [0] prepare, [1] move passes, [2] stats, [3] grow/seasons, [4] diffusion, [5] serial;
- * [6] device milliseconds of the last ss_step call (CUDA events on the engine's stream, always on). */
+ * [6] device milliseconds of the last ss_step call (CUDA events on the engine's stream, always on);
+ * [7] settle. */
 int  ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n);
 /* options: "path" (-1 auto, 0 serial, 2 lattice), "profile" (0/1), "reset_times",
- * "reset_counters", "diffuse_impl" (0 wavefront, 1 diagonal sweep for A/B checks) */
+ * "reset_counters", "diffuse_impl" (0 wavefront, 1 diagonal sweep for A/B checks),
+ * "window" (max window extent of the move passes, 32..176) */
 int  ss_set_option(ss_engine* e, const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -6,8 +6,11 @@
 //     occw[c]                    : u32   occupancy word, 0 = free, else
 //                                          bit 31      phase  (pending in step t  <=>  phase == (t & 1))
 //                                          bit 30      Q1 flag (at-risk predecessor, lattice path)
-//                                          bits 29..25 vision (1..31)
-//                                          bits 24..0  slot+1 (slot = Agent.id - 1)
+//                                          bit 29      at-risk flag (may starve this step)
+//                                          bits 28..24 vision (1..31, so an occupied word is non-zero)
+//                                          bits 23..0  slot (= Agent.id - 1)
+//     isugar[c]                  : u8    int(sugar[c]) mirror (what agents compare and harvest,
+//                                        environment.py:98-100); lattice path only
 //   agent store: one 32-byte record per slot (exactly one DRAM sector, so the random
 //   gather/scatter by slot that movement implies costs one sector per agent).
 //
@@ -28,7 +31,7 @@ struct __align__(32) AgentRec {
     uint32_t status;      // ((step + 1) << 2) | code : outcome of the agent's turn in `step`
     uint32_t pred;        // Q1: slot+1 of the at-risk predecessor in the execution order ...
     uint32_t pred_step;   // ... valid iff pred_step == step + 1
-    uint32_t pad;
+    uint32_t turn;        // ((step + 1) << 8) | harvest : deferred turn of a safe agent (ss_settle_kernel)
 };
 static_assert(sizeof(AgentRec) == 32, "AgentRec must be one 32-byte sector");
 
@@ -42,14 +45,17 @@ __host__ __device__ inline int attr_vision(uint32_t a) { return (int)(a & 0xffu)
 __host__ __device__ inline int attr_metab(uint32_t a) { return (int)((a >> 8) & 0xffffu); }
 __host__ __device__ inline bool attr_alive(uint32_t a) { return (a & ATTR_ALIVE) != 0; }
 
-#define OCC_Q1 0x40000000u          // the agent has an at-risk predecessor in this step's order (Q1)
-#define OCC_SLOT_BITS 25
+#define OCC_Q1   0x40000000u         // the agent has an at-risk predecessor in this step's order (Q1)
+#define OCC_RISK 0x20000000u         // the agent may starve this step (its turn is settled synchronously)
+#define OCC_FLAGS (OCC_Q1 | OCC_RISK)
+#define OCC_SLOT_BITS 24
 #define OCC_SLOT_MASK ((1u << OCC_SLOT_BITS) - 1u)
-#define SS_MAX_SLOTS OCC_SLOT_MASK
+#define SS_MAX_SLOTS (1u << OCC_SLOT_BITS)
+// vision >= 1, so an occupied cell's word is never 0
 __host__ __device__ inline uint32_t occ_pack(uint32_t slot, int vision, uint32_t phase) {
-    return (phase << 31) | ((uint32_t)vision << OCC_SLOT_BITS) | (slot + 1u);
+    return (phase << 31) | ((uint32_t)vision << OCC_SLOT_BITS) | slot;
 }
-__host__ __device__ inline uint32_t occ_slot(uint32_t w) { return (w & OCC_SLOT_MASK) - 1u; }
+__host__ __device__ inline uint32_t occ_slot(uint32_t w) { return w & OCC_SLOT_MASK; }
 __host__ __device__ inline int occ_vision(uint32_t w) { return (int)((w >> OCC_SLOT_BITS) & 31u); }
 __host__ __device__ inline uint32_t occ_phase(uint32_t w) { return w >> 31; }
 

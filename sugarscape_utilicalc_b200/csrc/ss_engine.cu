@@ -15,16 +15,17 @@ extern "C" {
 cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
                              int stats_base, cudaStream_t stream);
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s);
-size_t ss_pass_smem_bytes(int emax, int ew);
+size_t ss_pass_smem_bytes(int emax, int ew, int vmax);
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
 cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s);
+cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_time, cudaStream_t s);
 cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
 cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl, cudaStream_t s);
 }
 
 enum { PATH_SERIAL_FUSED = 0, PATH_SERIAL_ENV = 1, PATH_LATTICE = 2 };
-enum { KT_PREPARE = 0, KT_MOVE, KT_STATS, KT_GROW, KT_DIFFUSE, KT_SERIAL, KT_LAST_CALL, KT_COUNT };
+enum { KT_PREPARE = 0, KT_MOVE, KT_STATS, KT_GROW, KT_DIFFUSE, KT_SERIAL, KT_LAST_CALL, KT_SETTLE, KT_COUNT };
 
 struct ss_engine {
     ss_config cfg;
@@ -36,17 +37,20 @@ struct ss_engine {
     bool have_cells = false, have_agents = false, stepped = false;
     int path = -1, path_option = -1;
     PassGeom geom{};
-    int half_x = 0, half_y = 0;
+    int ntile = 1, emin = 0;
     int last_passes = 4;
     int stats_cap = 0;
     int* d_flags = nullptr;
     int sm_count = 148;
     int diffuse_impl = 0;
+    int window_max = 128;
+    int trace = 0;
+    bool cap_fits_u8 = true;
     unsigned long long* h_pending = nullptr;   // pinned
     std::vector<int32_t> upload_order;          // slots in upload order
     int64_t launches = 0, passes = 0, steps = 0, syncs = 0;
     bool profile = false;
-    double kt[KT_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    double kt[KT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr, eve = nullptr;
     std::string err;
 };
@@ -108,6 +112,7 @@ extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) 
     if ((ce = cudaMalloc(&e->w.cap, cb)) != cudaSuccess) return bail(ce, "cudaMalloc cap");
     if ((ce = cudaMalloc(&e->w.poll, cb)) != cudaSuccess) return bail(ce, "cudaMalloc pollution");
     if ((ce = cudaMalloc(&e->w.occw, e->cells * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc occ");
+    if ((ce = cudaMalloc(&e->w.isugar, e->cells + 16)) != cudaSuccess) return bail(ce, "cudaMalloc isugar");
     if ((ce = cudaMalloc(&e->w.mt, 624 * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc mt");
     if ((ce = cudaMalloc(&e->w.mti, sizeof(int32_t))) != cudaSuccess) return bail(ce, "cudaMalloc mti");
     if ((ce = cudaMalloc(&e->w.n_order, sizeof(int32_t))) != cudaSuccess) return bail(ce, "cudaMalloc n_order");
@@ -137,7 +142,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->w.sugar); cudaFree(e->w.cap); cudaFree(e->w.poll); cudaFree(e->w.occw);
+    cudaFree(e->w.sugar); cudaFree(e->w.cap); cudaFree(e->w.poll); cudaFree(e->w.occw); cudaFree(e->w.isugar);
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
     cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags);
@@ -150,6 +155,8 @@ extern "C" void ss_destroy(ss_engine* e) {
     delete e;
 }
 
+static int choose_path(ss_engine* e);
+
 extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution) {
     if (!e || !sugar || !cap) return set_err(e, SS_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));
@@ -158,34 +165,57 @@ extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* 
     CK(cudaMemcpyAsync(e->w.cap, cap, cb, cudaMemcpyHostToDevice, e->stream));
     if (pollution) CK(cudaMemcpyAsync(e->w.poll, pollution, cb, cudaMemcpyHostToDevice, e->stream));
     else CK(cudaMemsetAsync(e->w.poll, 0, cb, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    {   // int(sugar) byte mirror for the lattice path; needs capacities < 256
+        std::vector<uint8_t> isg(e->cells);
+        bool fits = true;
+        for (size_t c = 0; c < e->cells; c++) {
+            const double v = sugar[c];
+            if (!(v >= 0.0 && v < 256.0) || !(cap[c] < 256.0)) { fits = false; isg[c] = 0; }
+            else isg[c] = (uint8_t)(int)v;
+        }
+        e->cap_fits_u8 = fits;
+        CK(cudaMemcpyAsync(e->w.isugar, isg.data(), e->cells, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
     e->have_cells = true;
+    if (e->have_agents) return choose_path(e);
     return SS_OK;
 }
 
 static int choose_path(ss_engine* e) {
     const int n = e->w.n, V = e->w.vmax;
-    bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && !e->cfg.rule_utilicalc && V <= 15 && 4 * V + 1 <= n;
+    bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && !e->cfg.rule_utilicalc && V <= 15 && 4 * V + 1 <= n &&
+                      e->cap_fits_u8 && e->w.n_slots <= SS_MAX_SLOTS;
     PassGeom g{};
     if (lattice_ok) {
         g.ring = 2 * V;
+        g.align = (n % 4 == 0) ? 4 : 1;
+        const int nu = n / g.align;
+        const int wmax = std::max(32, std::min(e->window_max, 176));
+        int emin;
         if (n <= 176) {
-            g.nwin = 1; g.emax = n;
+            g.nwin = 1; g.emax = n; emin = n;
+            e->ntile = 1;
         } else {
-            g.nwin = (n + 127) / 128;
-            g.emax = (n + g.nwin - 1) / g.nwin;
-            const int emin = n / g.nwin;
-            if (emin < 4 * g.ring + 2) lattice_ok = false;
+            g.nwin = (n + wmax - 1) / wmax;
+            g.emax = g.align * ((nu + g.nwin - 1) / g.nwin);
+            emin = g.align * (nu / g.nwin);
+            // three diagonal tilings shifted by thirds of a window resolve every cell (a cell can be in
+            // the ring of at most two of them: once through x, once through y) if the ring strips of
+            // the three tilings are disjoint; otherwise four half-shifted tilings
+            if (emin >= 6 * g.ring + 3 * g.align) e->ntile = 3;
+            else if (emin >= 4 * g.ring + 2 + 2 * g.align) e->ntile = 4;
+            else lattice_ok = false;
         }
         g.ew = (g.emax + 31) / 32;
-        if (g.emax * g.ew > 256 * 5) lattice_ok = false;      // PASS_THREADS * PASS_WPT bitmap words
-        e->half_x = e->half_y = g.nwin > 1 ? n / (2 * g.nwin) : 0;
+        e->emin = emin;
+        if (ss_pass_smem_bytes(g.emax, g.ew, V) > 216 * 1024) lattice_ok = false;
     }
     int path;
     if (e->path_option == PATH_LATTICE) {
         if (!lattice_ok)
             return set_err(e, SS_ERR_UNSUPPORTED,
-                           "lattice path needs keyed RNG, moveEat (no utilicalc), vision <= 15 and windows >= 8*vmax+2");
+                           "lattice path needs keyed RNG, moveEat (no utilicalc), vision <= 15, capacities < 256, <= 2^24 agents and windows >= 8*vmax+2");
         path = PATH_LATTICE;
     } else if (e->path_option == PATH_SERIAL_FUSED || e->path_option == PATH_SERIAL_ENV) {
         path = n <= 256 ? PATH_SERIAL_FUSED : PATH_SERIAL_ENV;
@@ -216,7 +246,7 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
         if (x[i] < 0 || x[i] >= N || y[i] < 0 || y[i] >= N) return set_err(e, SS_ERR_ARG, "agent off the grid");
         vmax = std::max(vmax, vision[i]);
     }
-    if ((uint32_t)max_id > SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^25-1");
+    if ((uint32_t)max_id > SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^24");
     const uint32_t ns = (uint32_t)std::max(max_id, 1);
     std::vector<AgentRec> recs(ns);
     memset(recs.data(), 0, sizeof(AgentRec) * ns);
@@ -336,20 +366,34 @@ static int lattice_step(ss_engine* e, int stats_index) {
         int p = 0;
         for (;;) {
             PassGeom g = e->geom;
-            g.shift_x = (p & 1) ? e->half_x : 0;                 // tilings: (0,0) (h,h) (0,h) (h,0)
-            g.shift_y = ((p & 3) == 1 || (p & 3) == 2) ? e->half_y : 0;
+            if (e->ntile == 3) {                                  // diagonal shifts by thirds of a window
+                const int t = p % 3;
+                g.shift_x = g.shift_y = g.align * ((t * e->emin / 3) / g.align);
+            } else if (e->ntile == 4) {                           // (0,0) (h,h) (0,h) (h,0)
+                const int h = g.align * ((e->emin / 2) / g.align);
+                g.shift_x = (p & 1) ? h : 0;
+                g.shift_y = ((p & 3) == 1 || (p & 3) == 2) ? h : 0;
+            } else {
+                g.shift_x = g.shift_y = 0;
+            }
             CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
             e->launches++; e->passes++; p++;
-            if (p >= first_check) {
+            if (p >= first_check || e->trace) {
                 CK(cudaMemcpyAsync(e->h_pending, &e->w.acc->pending, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                    e->stream));
                 CK(cudaStreamSynchronize(e->stream));
                 e->syncs++;
+                if (e->trace) fprintf(stderr, "[ss] step %lld pass %d pending %llu\n", (long long)e->iteration, p, *e->h_pending);
                 if (*e->h_pending == 0ull) break;
             }
             if (p > 4096) return set_err(e, SS_ERR_STATE, "move passes did not converge");
         }
         e->last_passes = p;
+    }
+    {
+        KTimer t(e, KT_SETTLE);
+        CK(ss_launch_settle(e->w, e->iteration, e->env_time, e->stream));
+        e->launches++;
     }
     {
         KTimer t(e, KT_STATS);
@@ -457,7 +501,7 @@ extern "C" int ss_download_cells(ss_engine* e, double* sugar, double* cap, doubl
     if (occ_id) CK(cudaMemcpyAsync(occ_id, e->w.occw, e->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (occ_id)
-        for (size_t c = 0; c < e->cells; c++) occ_id[c] = (int32_t)((uint32_t)occ_id[c] & OCC_SLOT_MASK);
+        for (size_t c = 0; c < e->cells; c++) occ_id[c] = occ_id[c] ? (int32_t)(occ_slot((uint32_t)occ_id[c]) + 1u) : 0;
     return SS_OK;
 }
 
@@ -487,6 +531,17 @@ extern "C" int ss_get_counters(ss_engine* e, int64_t* out, int32_t n) {
     if (!e || !out) return set_err(e, SS_ERR_ARG, "null argument");
     const int64_t v[6] = {e->launches, e->passes, e->steps, e->path, e->syncs, e->geom.emax};
     for (int i = 0; i < n && i < 6; i++) out[i] = v[i];
+    if (n > 6 && !e->w.dbg && e->path == PATH_LATTICE) {
+        StepAccum acc;
+        cudaMemcpy(&acc, e->w.acc, sizeof acc, cudaMemcpyDeviceToHost);
+        const int64_t v2[5] = {(int64_t)acc.watchdog, (int64_t)acc.wd_info[0], (int64_t)acc.wd_info[1], (int64_t)acc.wd_info[2], (int64_t)acc.fault};
+        for (int i = 6; i < n && i < 11; i++) out[i] = v2[i - 6];
+    }
+    if (n > 6 && e->w.dbg) {       // instrumentation counters of the move passes (option "debug")
+        unsigned long long d[32];
+        cudaMemcpy(d, e->w.dbg, sizeof d, cudaMemcpyDeviceToHost);
+        for (int i = 6; i < n && i < 38; i++) out[i] = (int64_t)d[i - 6];
+    }
     return SS_OK;
 }
 
@@ -508,5 +563,12 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "reset_times") { for (double& d : e->kt) d = 0; return SS_OK; }
     if (k == "reset_counters") { e->launches = e->passes = e->syncs = 0; return SS_OK; }
     if (k == "diffuse_impl") { e->diffuse_impl = (int)value; return SS_OK; }
+    if (k == "debug") {
+        if (value && !e->w.dbg) { CK(cudaMalloc(&e->w.dbg, 32 * sizeof(unsigned long long))); CK(cudaMemset(e->w.dbg, 0, 32 * 8)); }
+        if (!value && e->w.dbg) { cudaFree(e->w.dbg); e->w.dbg = nullptr; }
+        return SS_OK;
+    }
+    if (k == "trace") { e->trace = (int)value; return SS_OK; }
+    if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }

@@ -25,18 +25,32 @@
 
 #define FULL 0xffffffffu
 #define PASS_THREADS 256
-#define PASS_WPT 5                      // bitmap words per thread (covers extents up to 192)
+#define PASS_WARPS (PASS_THREADS / 32)
+#define PASS_RGX 2                      // regions per window: PASS_RGX x PASS_RGY == PASS_WARPS
+#define PASS_RGY 4
 
 // ------------------------------------------------------------------------ prepare (Q1) ----
+// An agent is SAFE if it cannot starve this step whatever happens before its turn: it
+// harvests at least int(sugar) of its own cell (nobody else can take an occupied cell and
+// growback runs after the agent loop; with pollution the winner of the sugar/(1+p) ratio has
+// sugar >= 1 whenever the own cell has).  Everything else is AT RISK: its turn is settled
+// synchronously and its successor in the execution order waits for the outcome (Q1).
 __global__ void ss_prepare_kernel(DevWorld w, int64_t iteration) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= w.n_slots) return;
     AgentRec* rec = &w.agents[slot];
     const uint32_t attr = rec->attr;
     if (!attr_alive(attr)) return;
-    // safe  <=>  cannot starve this step even with an empty harvest (sugarscape.py:569, 306-309)
-    const double after = ss_set_sugar(ss_max0(rec->sugar - (double)attr_metab(attr)));
-    if (after > 0.1) return;
+    const double metab = (double)attr_metab(attr);
+    if (ss_set_sugar(ss_max0(rec->sugar - metab)) > 0.1) return;          // sugarscape.py:569, 306-309
+    const uint32_t pos = rec->pos;
+    int hmin = 0;
+    if (w.cfg.rule_move_eat) {
+        hmin = (int)w.isugar[pos];
+        if (w.cfg.rule_pollution && hmin > 1) hmin = 1;
+    }
+    if (ss_set_sugar(ss_max0(ss_set_sugar(ss_max0(rec->sugar + (double)hmin)) - metab)) > 0.1) return;
+    atomicOr(&w.occw[pos], OCC_RISK);
     const OrderKey ok = ss_order_key(ss_step_key(w.cfg.keyed_seed, iteration), w.half);
     const uint32_t domain = 1u << (2 * w.half);
     for (uint32_t p = ss_priority(ok, slot) + 1u; p < domain; p++) {
@@ -58,36 +72,20 @@ __global__ void ss_begin_step_kernel(DevWorld w) {
 }
 
 // --------------------------------------------------------------------------- move pass ----
-__device__ static inline uint32_t bits_mask(int len) { return len >= 32 ? 0xffffffffu : ((1u << len) - 1u); }
-
+// Shared-memory image of one window: occupancy words and int(sugar) of every cell.
 struct WinCtx {
     uint32_t* occ_s;      // [ex][emax]
-    uint32_t* pend_s;     // [ex][ew]
-    int ex, ey, emax, ew;
+    uint8_t* isug_s;      // [ex][emax]
+    int ex, ey, emax;
     int gx0, gy0;         // global coordinate of local (0,0)
     bool full_x, full_y;  // window spans the whole torus in that dimension (wrap inside)
     int n;
 };
-
-// pending bits of local row r, columns [c0, c0+len), len <= 32
-__device__ static inline uint32_t pend_bits(const WinCtx& c, int r, int c0, int len) {
-    const uint32_t* row = c.pend_s + r * c.ew;
-    if (c0 >= 0 && c0 + len <= c.ey) {
-        const int w0 = c0 >> 5, sh = c0 & 31;
-        const uint32_t lo = row[w0];
-        const uint32_t hi = (w0 + 1 < c.ew) ? row[w0 + 1] : 0u;
-        return __funnelshift_r(lo, hi, sh) & bits_mask(len);
-    }
-    uint32_t out = 0;                                   // torus seam inside a full-span window
-    for (int i = 0; i < len; i++) {
-        int cc = c0 + i;
-        if (c.full_y) cc = ss_wrap(cc, c.ey); else if (cc < 0 || cc >= c.ey) continue;
-        out |= ((row[cc >> 5] >> (cc & 31)) & 1u) << i;
-    }
-    return out;
-}
 __device__ static inline int wrap_row(const WinCtx& c, int r) { return c.full_x ? ss_wrap(r, c.ex) : r; }
 __device__ static inline int wrap_col(const WinCtx& c, int q) { return c.full_y ? ss_wrap(q, c.ey) : q; }
+__device__ static inline bool in_core(const WinCtx& c, int r, int q, int R) {
+    return (c.full_x || (r >= R && r < c.ex - R)) && (c.full_y || (q >= R && q < c.ey - R));
+}
 
 // crosses of A (vision a) and B (vision b, displaced by dx,dy) share a cell
 __device__ static inline bool crosses_meet(int dx, int dy, int a, int b) {
@@ -96,301 +94,554 @@ __device__ static inline bool crosses_meet(int dx, int dy, int a, int b) {
            (dx == 0 && ady <= a + b);
 }
 
-// Scan the conflict zone of the agent at local (lx,ly); returns the local position
-// (r << 8 | q) + 1 of the pending conflicting agent with the LARGEST priority below `pa`
-// (the blocker most likely to resolve last), or 0 if nothing blocks.
-__device__ static uint32_t find_blocker(const WinCtx& c, const OrderKey& ok, int lx, int ly, int a, uint32_t pa,
-                                        uint32_t self_slot, int V) {
-    uint32_t best_p = 0, best_pos = 0;
-    bool found = false;
-    auto consider = [&](int r, int q, int dx, int dy) {
-        const uint32_t ow = c.occ_s[r * c.emax + q];
-        const uint32_t sb = occ_slot(ow);
-        if (sb == self_slot) return;
-        if (!crosses_meet(dx, dy, a, occ_vision(ow))) return;
-        const uint32_t pb = ss_priority(ok, sb);
-        if (pb < pa && (!found || pb > best_p)) { found = true; best_p = pb; best_pos = ((uint32_t)r << 8 | (uint32_t)q) + 1u; }
-    };
-    // box |dx| <= V, |dy| <= V
-    for (int dx = -V; dx <= V; dx++) {
-        const int r = wrap_row(c, lx + dx);
-        uint32_t bits = pend_bits(c, r, ly - V, 2 * V + 1);
-        while (bits) {
-            const int i = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int dy = i - V;
-            consider(r, wrap_col(c, ly + dy), dx, dy);
-        }
-    }
-    // same x (dx == 0), V < |dy| <= a + V
-    {
-        const int r = lx;
-        uint32_t lo = pend_bits(c, r, ly - V - a, a);
-        while (lo) { const int i = __ffs(lo) - 1; lo &= lo - 1; const int dy = i - V - a; consider(r, wrap_col(c, ly + dy), 0, dy); }
-        uint32_t hi = pend_bits(c, r, ly + V + 1, a);
-        while (hi) { const int i = __ffs(hi) - 1; hi &= hi - 1; const int dy = V + 1 + i; consider(r, wrap_col(c, ly + dy), 0, dy); }
-    }
-    // same y (dy == 0), V < |dx| <= a + V
-    for (int k = V + 1; k <= V + a; k++) {
-#pragma unroll
-        for (int sgn = -1; sgn <= 1; sgn += 2) {
-            const int dx = sgn * k;
-            const int r = wrap_row(c, lx + dx);
-            if ((c.pend_s[r * c.ew + (ly >> 5)] >> (ly & 31)) & 1u) consider(r, ly, dx, 0);
-        }
-    }
-    return found ? best_pos : 0u;
-}
-
 struct ThreadStats { unsigned sum_m, sum_v, acted, deaths, resolved, small, inexact; };
 
-// One agent's whole turn (thread-per-agent): getFood + move + pollute + metabolise + starve.
-__device__ static void agent_turn(const DevWorld& w, const WinCtx& c, int lx, int ly, uint32_t ow, int64_t iteration,
-                                  int64_t env_time, uint64_t skey, uint32_t next_phase, ThreadStats& ts) {
+struct Choice { int lr, lq, sg; };
+
+// agent.py:361-371 getFood + agent.py:794-823 move(), one warp per agent: lane k evaluates
+// candidate k of the cross (x-arm by ascending raw x, then y-arm; K = 2(2a+1) <= 62, so at
+// most two candidates per lane).  Occupancy and int(sugar) come from the window's
+// shared-memory copy; with the pollution rule each lane fetches its candidate's pollution
+// from HBM (32 loads in flight).  Best = (key desc, distance asc, shuffled position asc).
+// Without pollution key and distance pack into one integer and a single warp REDUX finds the
+// best; ties are broken by replaying the agent's keyed Fisher-Yates draws (agent.py:369,
+// random.py:350/242), each tied lane tracking the position of its own candidate; positions
+// are finalised from the top, so the replay stops once a single tied candidate is left.
+__device__ static Choice warp_choose_cell(const DevWorld& w, const WinCtx& c, int lx, int ly, int gx, int gy, int a,
+                                          uint32_t slot, uint64_t skey, int lane) {
     const int n = c.n;
-    const uint32_t slot = occ_slot(ow);
+    const bool pol = w.cfg.rule_pollution != 0;
+    const int span = 2 * a + 1, K = 2 * span;
+    int dist[2] = {0, 0}, cell[2] = {0, 0}, sg[2] = {0, 0}, qidx[2] = {-1, -1};
+    uint32_t loc[2] = {0, 0};
+    int n_free = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = h * 32 + lane;
+        bool fr = false;
+        if (h * 32 < K) {
+            if (k < K) {
+                int r, q, cx, cy;
+                if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap(gx + o, n); cy = gy; }
+                else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap(gy + o, n); }
+                const int li = r * c.emax + q;
+                if (c.occ_s[li] == 0u) {
+                    fr = true;
+                    loc[h] = (uint32_t)(r << 8 | q); cell[h] = cx * n + cy; sg[h] = (int)c.isug_s[li];
+                    dist[h] = abs(gx - cx) + abs(gy - cy);                       // agent.py:867-868
+                }
+            }
+            const unsigned fb = __ballot_sync(FULL, fr);
+            if (fr) qidx[h] = n_free + __popc(fb & ((1u << lane) - 1u));
+            n_free += __popc(fb);
+        }
+    }
+    // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
+    const int sg0 = (int)c.isug_s[lx * c.emax + ly];
+    Choice stay; stay.lr = lx; stay.lq = ly; stay.sg = sg0;
+    if (n_free == 0) return stay;
+    bool tie0, tie1;
+    if (!pol) {
+        const uint32_t k0 = qidx[0] >= 0 ? (((uint32_t)sg[0] << 20) | (0xfffffu - (uint32_t)dist[0])) + 1u : 0u;
+        const uint32_t k1 = qidx[1] >= 0 ? (((uint32_t)sg[1] << 20) | (0xfffffu - (uint32_t)dist[1])) + 1u : 0u;
+        const uint32_t kmax = __reduce_max_sync(FULL, k0 > k1 ? k0 : k1);
+        if (sg0 >= (int)((kmax - 1u) >> 20)) return stay;
+        tie0 = k0 == kmax; tie1 = k1 == kmax;
+    } else {
+        double key[2] = {-1.0, -1.0};
+        double p0 = 0.0, p1 = 0.0, pown = 0.0;
+        if (qidx[0] >= 0 && sg[0] > 0) p0 = __ldcg(&w.poll[cell[0]]);
+        if (qidx[1] >= 0 && sg[1] > 0) p1 = __ldcg(&w.poll[cell[1]]);
+        if (sg0 > 0) pown = __ldcg(&w.poll[gx * n + gy]);
+        if (qidx[0] >= 0) key[0] = (double)sg[0] / (1.0 + p0);
+        if (qidx[1] >= 0) key[1] = (double)sg[1] / (1.0 + p1);
+        const double key0 = (double)sg0 / (1.0 + pown);
+        double kmax = key[0] > key[1] ? key[0] : key[1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(FULL, kmax, o); kmax = t > kmax ? t : kmax; }
+        if (key0 >= kmax) return stay;
+        int dmin = 0x7fffffff;
+        if (qidx[0] >= 0 && key[0] == kmax) dmin = dist[0];
+        if (qidx[1] >= 0 && key[1] == kmax && dist[1] < dmin) dmin = dist[1];
+        dmin = __reduce_min_sync(FULL, dmin);
+        tie0 = qidx[0] >= 0 && key[0] == kmax && dist[0] == dmin;
+        tie1 = qidx[1] >= 0 && key[1] == kmax && dist[1] == dmin;
+    }
+    int left = __popc(__ballot_sync(FULL, tie0)) + __popc(__ballot_sync(FULL, tie1));
+    if (left > 1) {
+        const uint64_t akey = ss_agent_key(skey, slot + 1u);
+        uint32_t j = 0;
+        int p0 = qidx[0], p1 = qidx[1];
+        for (int i = n_free - 1; i >= 1 && left > 1; i--) {           // random.py:350 shuffle
+            const uint32_t nn = (uint32_t)i + 1u;
+            const int kbits = 32 - __clz(nn);
+            uint32_t rj = ss_keyed_word(akey, j++) >> (32 - kbits);  // random.py:242 _randbelow
+            while (rj >= nn) {
+                rj = ss_keyed_word(akey, j++) >> (32 - kbits);
+                if (j > 100000u) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x3333; break; }
+            }
+            // the element at index rj moves to index i and is final there; L[i] moves to rj
+            bool fin = false;
+            if (tie0) { if (p0 == (int)rj) { tie0 = false; fin = true; } else if (p0 == i) p0 = (int)rj; }
+            if (tie1) { if (p1 == (int)rj) { tie1 = false; fin = true; } else if (p1 == i) p1 = (int)rj; }
+            left -= __popc(__ballot_sync(FULL, fin));
+        }
+    }
+    // the surviving tied candidate ends lowest in the shuffled list
+    const unsigned who = __ballot_sync(FULL, tie0 || tie1);
+    const int src = __ffs(who) - 1;
+    const uint32_t payload = tie0 ? (((uint32_t)sg[0] << 16) | loc[0]) : (((uint32_t)sg[1] << 16) | loc[1]);
+    const uint32_t got = __shfl_sync(FULL, payload, src);
+    Choice ch;
+    ch.lr = (int)((got >> 8) & 255u); ch.lq = (int)(got & 255u); ch.sg = (int)(got >> 16);
+    return ch;
+}
+
+// One agent's turn (one warp per agent; lane 0 commits).  SAFE agents (no OCC_RISK flag)
+// cannot starve, so only their move is done here -- shared-memory reads, fire-and-forget
+// HBM stores; harvest, pollution, metabolism and statistics are deferred to ss_settle_kernel
+// (nobody can observe them before the agent loop ends: the destination stays occupied).
+// AT-RISK agents are settled synchronously because a death frees the cell and decides the
+// successor's turn (Q1).
+__device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int lx, int ly, uint32_t ow, uint32_t slot,
+                                       int64_t iteration, int64_t env_time, uint64_t skey, uint32_t next_phase,
+                                       ThreadStats& ts, int lane) {
+    const int n = c.n;
     const int a = occ_vision(ow);
-    AgentRec* recp = &w.agents[slot];
-    AgentRec rec = *recp;
     const int gx = ss_wrap(c.gx0 + lx, n), gy = ss_wrap(c.gy0 + ly, n);
     const int pos = gx * n + gy;
-    const bool pol = w.cfg.rule_pollution != 0;
-    // ---- scan the cross: x-arm ascending raw x, then y-arm (agent.py:361-368) ----
-    double best_key = -1.0;
-    int best_d = 0, best_sg = 0, best_cell = -1, best_lr = 0, best_lq = 0;
-    int ties[8];                 // pre-shuffle indices of the candidates tied with the best
-    int tie_cell[8], tie_lr[8], tie_lq[8], tie_sg[8];
-    int n_ties = 0, n_free = 0;
-    if (w.cfg.rule_move_eat) {
-        const int span = 2 * a + 1;
-        for (int k = 0; k < 2 * span; k++) {
-            int r, q, cx, cy;
-            if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap(gx + o, n); cy = gy; }
-            else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap(gy + o, n); }
-            if (c.occ_s[r * c.emax + q] != 0u) continue;
-            const int cell = cx * n + cy;
-            const int sg = (int)__ldcg(&w.sugar[cell]);                              // environment.py:98-100
-            const int d = abs(gx - cx) + abs(gy - cy);                               // agent.py:867-868
-            const double key = pol ? (double)sg / (1.0 + __ldcg(&w.poll[cell])) : (double)sg;
-            const int q_idx = n_free++;
-            if (key > best_key || (key == best_key && d < best_d)) {
-                best_key = key; best_d = d; n_ties = 0;
-            } else if (!(key == best_key && d == best_d)) {
-                continue;
-            }
-            if (n_ties < 8) { ties[n_ties] = q_idx; tie_cell[n_ties] = cell; tie_lr[n_ties] = r; tie_lq[n_ties] = q; tie_sg[n_ties] = sg; }
-            n_ties++;
+    const bool risky = (ow & OCC_RISK) != 0;
+    AgentRec* recp = &w.agents[slot];
+    double sugar = 0.0;
+    uint32_t attr = 0;
+    if (risky && lane == 0) { sugar = recp->sugar; attr = recp->attr; }   // issued early, used after the scan
+    Choice ch;
+    if (w.cfg.rule_move_eat) ch = warp_choose_cell(w, c, lx, ly, gx, gy, a, slot, skey, lane);
+    else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
+    if (lane != 0) return;
+    const int li_old = lx * c.emax + ly, li_new = ch.lr * c.emax + ch.lq;
+    const int cell = (ch.lr == lx && ch.lq == ly) ? pos
+                   : ss_wrap(c.gx0 + ch.lr, n) * n + ss_wrap(c.gy0 + ch.lq, n);
+    uint32_t new_word = occ_pack(slot, a, next_phase);
+    ts.resolved++;
+    if (!risky) {
+        c.occ_s[li_old] = 0u;
+        c.occ_s[li_new] = new_word;
+        if (cell != pos) w.occw[pos] = 0u;
+        w.occw[cell] = new_word;
+        if (w.cfg.rule_move_eat) {
+            c.isug_s[li_new] = 0;
+            w.sugar[cell] = 0.0;                                      // agent.py:864
+            w.isugar[cell] = 0;
         }
-        // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
-        const int sg0 = (int)__ldcg(&w.sugar[pos]);
-        const double key0 = pol ? (double)sg0 / (1.0 + __ldcg(&w.poll[pos])) : (double)sg0;
-        if (n_free == 0 || key0 >= best_key) {
-            best_cell = pos; best_sg = sg0; best_lr = lx; best_lq = ly;
-        } else {
-            int pick = 0;
-            if (n_ties > 1) {
-                // Tie among free cells: the winner is the first in the Fisher-Yates-shuffled
-                // list (agent.py:369, random.py:350).  Replay the agent's keyed draws and track
-                // only the tied candidates' positions.
-                if (n_ties > 8) n_ties = 8;
-                const uint64_t akey = ss_agent_key(skey, slot + 1u);
-                uint32_t j = 0;
-                int posn[8];
-                for (int t = 0; t < n_ties; t++) posn[t] = ties[t];
-                for (int i = n_free - 1; i >= 1; i--) {
-                    const uint32_t nn = (uint32_t)i + 1u;
-                    const int kbits = 32 - __clz(nn);
-                    uint32_t rj = ss_keyed_word(akey, j++) >> (32 - kbits);
-                    while (rj >= nn) rj = ss_keyed_word(akey, j++) >> (32 - kbits);
-                    for (int t = 0; t < n_ties; t++) {
-                        if (posn[t] == i) posn[t] = (int)rj;
-                        else if (posn[t] == (int)rj) posn[t] = i;
-                    }
-                }
-                for (int t = 1; t < n_ties; t++) if (posn[t] < posn[pick]) pick = t;
-            }
-            best_cell = tie_cell[pick]; best_lr = tie_lr[pick]; best_lq = tie_lq[pick]; best_sg = tie_sg[pick];
-        }
-        // ---- commit (agent.py:825-865) ----
-        if (pol && w.cfg.pollution_start_time <= env_time)
-            w.poll[best_cell] = __ldcg(&w.poll[best_cell]) + (((double)best_sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));
-        rec.sugar = ss_set_sugar(ss_max0(rec.sugar + (double)best_sg));
-        w.sugar[best_cell] = 0.0;
-    } else {
-        best_cell = pos; best_lr = lx; best_lq = ly;
+        recp->pos = (uint32_t)cell;
+        recp->turn = ((uint32_t)(iteration + 1) << 8) | (uint32_t)ch.sg;
+        return;
     }
-    // ---- sugarscape.py:566-601 ----
-    const int metab = attr_metab(rec.attr);
-    if (pol && rec.sugar > 0.0 && w.cfg.pollution_start_time <= env_time)
-        w.poll[best_cell] = __ldcg(&w.poll[best_cell]) + ((0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b));
-    rec.sugar = ss_set_sugar(ss_max0(rec.sugar - (double)metab));
+    const bool pol = w.cfg.rule_pollution != 0 && w.cfg.pollution_start_time <= env_time;
+    const int metab = attr_metab(attr);
+    if (w.cfg.rule_move_eat) {
+        if (pol) w.poll[cell] = __ldcg(&w.poll[cell]) + (((double)ch.sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));
+        sugar = ss_set_sugar(ss_max0(sugar + (double)ch.sg));         // agent.py:832
+        c.isug_s[li_new] = 0;
+        w.sugar[cell] = 0.0;
+        w.isugar[cell] = 0;
+    }
+    if (pol && sugar > 0.0)                                           // sugarscape.py:566-567
+        w.poll[cell] = __ldcg(&w.poll[cell]) + ((0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b));
+    sugar = ss_set_sugar(ss_max0(sugar - (double)metab));             // sugarscape.py:569
     ts.sum_m += (unsigned)metab;
     ts.sum_v += (unsigned)a;
     ts.acted++;
-    ts.resolved++;
-    {   // wealth histogram for the Gini coefficient
-        const double ws = rec.sugar;
-        if (ws == 0.01) ts.small++;
-        else if (ws >= 0.0 && ws < (double)SS_GINI_BINS && ws == (double)(int)ws) atomicAdd(&w.hist[(int)ws], 1u);
-        else ts.inexact++;
-    }
-    const bool died = w.cfg.rule_can_starve && rec.sugar <= 0.1;
-    const uint32_t new_word = died ? 0u : occ_pack(slot, a, next_phase);
-    c.occ_s[lx * c.emax + ly] = 0u;
-    c.occ_s[best_lr * c.emax + best_lq] = new_word;
-    if (best_cell != pos) w.occw[pos] = 0u;
-    w.occw[best_cell] = new_word;
-    rec.pos = (uint32_t)best_cell;
-    rec.status = ((uint32_t)(iteration + 1) << 2) | (died ? ST_DIED : ST_ACTED);
-    if (died) { rec.attr &= ~ATTR_ALIVE; ts.deaths++; }
-    recp->sugar = rec.sugar;
-    recp->pos = rec.pos;
-    recp->attr = rec.attr;
+    if (sugar == 0.01) ts.small++;
+    else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
+    else ts.inexact++;
+    const bool died = w.cfg.rule_can_starve && sugar <= 0.1;          // sugarscape.py:306-309
+    if (died) new_word = 0u;
+    c.occ_s[li_old] = 0u;
+    c.occ_s[li_new] = new_word;
+    if (cell != pos) w.occw[pos] = 0u;
+    w.occw[cell] = new_word;
+    if (died) { attr &= ~ATTR_ALIVE; ts.deaths++; }
+    recp->sugar = sugar;
+    recp->pos = (uint32_t)cell;
+    recp->attr = attr;
     __threadfence();                       // the turn's effects before its status (Q1 readers)
-    *((volatile uint32_t*)&recp->status) = rec.status;
+    *((volatile uint32_t*)&recp->status) = ((uint32_t)(iteration + 1) << 2) | (died ? ST_DIED : ST_ACTED);
 }
+
+// ------------------------------------------------------------------------------------------
+// Move pass = conservative parallel discrete-event simulation with the execution priority as
+// the time stamp.  A CTA stages one window in shared memory and splits it into PASS_WARPS
+// regions, one warp each.  A warp takes the pending agents of its region strictly in
+// ascending priority (repeated warp-min selection over keys held in registers), so agents of
+// one region never need a conflict test against each other.  Before an agent A acts, the warp
+// publishes its frontier f = priority(A) ("everything below f in my region is finished") and
+// waits until every region its conflict zone reaches has a frontier above priority(A): then
+// all conflicting agents of lower priority have finished, and all of higher priority are still
+// waiting for A.  The region holding the globally smallest unfinished priority never waits,
+// so the scheme cannot deadlock.  Agents that cannot be resolved in this launch (window ring,
+// unresolved Q1 predecessor, conflict with such an agent) are appended to the region's
+// blocked set, which later agents within reach check with the exact cross-intersection test.
+#define PASS_LIST 256                    // listed agents per region and launch
+#define PASS_KPL (PASS_LIST / 32)
+#define PRIO_INF 0xffffffffu
+#define PASS_BROWS 6                     // 16x16-cell blocks per region: up to 6 x 5 (regions up to 96 x 80 cells)
+#define PASS_BCOLS 5
+struct RegionShared {
+    volatile uint32_t bfront[32];        // per block: lowest priority among its unfinished listed agents
+    volatile int n_list;
+    volatile int done;                   // the region's launch is over (fronts may stay finite if the list was trimmed)
+    uint64_t list[PASS_LIST];            // staging for the per-lane keys: priority << 16 | pos
+};
+struct PassShared {
+    unsigned red[PASS_WARPS];
+    int go;
+    int count[PASS_WARPS];
+};
 
 __global__ void __launch_bounds__(PASS_THREADS, 2)
 ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
-    extern __shared__ uint32_t smem[];
-    __shared__ unsigned red[8];
-    const int n = w.n, tid = threadIdx.x, lane = tid & 31;
-    __shared__ int go;
-    if (tid == 0) go = (w.acc->pending != 0ull);
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ PassShared sh;
+    const int n = w.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sh.go = (w.acc->pending != 0ull);
     __syncthreads();
-    if (!go) return;
-    // ---- window geometry (balanced boundaries b_k = floor(k*N/nwin), shifted tiling) ----
+    if (!sh.go) return;
+    // ---- window geometry: balanced boundaries in units of `align` cells, shifted tiling ----
     const int bx = blockIdx.x % g.nwin, by = blockIdx.x / g.nwin;
-    const int x_lo = (int)(((long long)bx * n) / g.nwin), x_hi = (int)(((long long)(bx + 1) * n) / g.nwin);
-    const int y_lo = (int)(((long long)by * n) / g.nwin), y_hi = (int)(((long long)(by + 1) * n) / g.nwin);
+    const int nu = n / g.align;
+    const int x_lo = g.align * (int)(((long long)bx * nu) / g.nwin), x_hi = g.align * (int)(((long long)(bx + 1) * nu) / g.nwin);
+    const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
+    const int V = w.vmax, R = g.ring;
     WinCtx c;
-    c.n = n; c.ex = x_hi - x_lo; c.ey = y_hi - y_lo; c.emax = g.emax; c.ew = g.ew;
+    c.n = n; c.ex = x_hi - x_lo; c.ey = y_hi - y_lo; c.emax = g.emax;
     c.gx0 = x_lo + g.shift_x; c.gy0 = y_lo + g.shift_y;
     c.full_x = (c.ex == n); c.full_y = (c.ey == n);
     c.occ_s = smem;
-    c.pend_s = smem + g.emax * g.emax;
+    c.isug_s = (uint8_t*)(smem + g.emax * g.emax);
+    RegionShared* regs = (RegionShared*)((uint8_t*)smem + (((size_t)g.emax * g.emax * 5 + 15) & ~(size_t)15));
+    uint32_t* blk_bits = (uint32_t*)(regs + PASS_WARPS);     // [emax][ew]: pending agents this launch cannot resolve
+    const int ew = g.ew;
     const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
-    const int V = w.vmax, R = g.ring;
-    // ---- stage occupancy words, derive the pending bitmap ----
-    const int eyp = c.ew * 32;
-    for (int idx = tid; idx < c.ex * eyp; idx += blockDim.x) {
-        const int lx = idx / eyp, ly = idx - lx * eyp;
-        uint32_t ow = 0u;
-        if (ly < c.ey) {
-            const int gx = ss_wrap(c.gx0 + lx, n), gy = ss_wrap(c.gy0 + ly, n);
-            ow = __ldcg(&w.occw[(size_t)gx * n + gy]);
-            c.occ_s[lx * c.emax + ly] = ow;
+    const long long t_start = clock64();
+    long long t_wait = 0, t_turn = 0, t_m;
+    int n_turns = 0, n_blocked_me = 0;
+    // ---- stage 1: copy occupancy words + int(sugar) into shared memory ----
+    if (g.align == 4) {           // 128-bit / 32-bit vector loads, 4 cells per request, 4 requests in flight
+        const int gpr = c.ey >> 2, total = c.ex * gpr;
+        for (int base = 0; base < total; base += 4 * PASS_THREADS) {
+            uint4 ov[4];
+            uchar4 sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * PASS_THREADS + tid;
+                if (idx < total) {
+                    const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
+                    const size_t gi = (size_t)ss_wrap(c.gx0 + lx, n) * n + ss_wrap(c.gy0 + ly, n);
+                    ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + gi));
+                    sv[u] = __ldcg(reinterpret_cast<const uchar4*>(w.isugar + gi));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * PASS_THREADS + tid;
+                if (idx < total) {
+                    const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
+                    uint32_t* o = c.occ_s + lx * c.emax + ly;
+                    o[0] = ov[u].x; o[1] = ov[u].y; o[2] = ov[u].z; o[3] = ov[u].w;
+                    uint8_t* q = c.isug_s + lx * c.emax + ly;
+                    q[0] = sv[u].x; q[1] = sv[u].y; q[2] = sv[u].z; q[3] = sv[u].w;
+                }
+            }
         }
-        const unsigned b = __ballot_sync(FULL, ow != 0u && (ow >> 31) == cur_phase);
-        if (lane == 0) c.pend_s[lx * c.ew + (ly >> 5)] = b;
+    } else {
+        for (int idx = tid; idx < c.ex * c.ey; idx += PASS_THREADS) {
+            const int lx = idx / c.ey, ly = idx - lx * c.ey;
+            const size_t gi = (size_t)ss_wrap(c.gx0 + lx, n) * n + ss_wrap(c.gy0 + ly, n);
+            c.occ_s[lx * c.emax + ly] = __ldcg(&w.occw[gi]);
+            c.isug_s[lx * c.emax + ly] = __ldcg(&w.isugar[gi]);
+        }
     }
+    RegionShared& me = regs[warp];
+    if (lane == 0) { me.n_list = 0; me.done = 0; sh.count[warp] = 0; }
+    me.bfront[lane] = PRIO_INF;
+    for (int i = tid; i < g.emax * ew; i += PASS_THREADS) blk_bits[i] = 0u;
     __syncthreads();
-    // ---- my bitmap words; active = pending agents of the core ----
+    const long long t_loaded = clock64();
+    // ---- stage 2 (all threads, one pass over the window): pending agents -> their region's list
+    //      (core) or blocked set (ring); per-block frontiers start at the block's lowest priority ----
     const uint64_t skey = ss_step_key(w.cfg.keyed_seed, iteration);
     const OrderKey ok = ss_order_key(skey, w.half);
-    const int nwords = c.ex * c.ew;
-    uint32_t active[PASS_WPT];
-    uint16_t* blk_s = (uint16_t*)(c.pend_s + g.emax * g.ew);     // cached blocker per cell
-#pragma unroll
-    for (int k = 0; k < PASS_WPT; k++) {
-        const int wi = tid + k * PASS_THREADS;
-        uint32_t m = 0u;
-        if (wi < nwords) {
-            const int lx = wi / c.ew, wc = wi - lx * c.ew;
-            if (c.full_x || (lx >= R && lx < c.ex - R)) {
-                m = c.pend_s[wi];
-                if (!c.full_y) {
-                    const int lo = R - wc * 32, hi = (c.ey - R) - wc * 32;     // core columns [lo, hi)
-                    uint32_t cm = 0u;
-                    if (hi > 0 && lo < 32) cm = bits_mask(hi < 32 ? hi : 32) & ~bits_mask(lo > 0 ? lo : 0);
-                    m &= cm;
-                }
-            }
-            uint32_t t = m;
-            while (t) { const int i = __ffs(t) - 1; t &= t - 1; blk_s[lx * c.emax + wc * 32 + i] = 0; }
+    auto rg_of_x = [&](int x) { int r = (x * PASS_RGX) / c.ex; while (r > 0 && (r * c.ex) / PASS_RGX > x) r--; while (r + 1 < PASS_RGX && ((r + 1) * c.ex) / PASS_RGX <= x) r++; return r; };
+    auto rg_of_y = [&](int y) { int r = (y * PASS_RGY) / c.ey; while (r > 0 && (r * c.ey) / PASS_RGY > y) r--; while (r + 1 < PASS_RGY && ((r + 1) * c.ey) / PASS_RGY <= y) r++; return r; };
+    auto rg_x0 = [&](int ix) { return (ix * c.ex) / PASS_RGX; };
+    auto rg_y0 = [&](int iy) { return (iy * c.ey) / PASS_RGY; };
+    for (int idx = tid; idx < c.ex * c.ey; idx += PASS_THREADS) {
+        const int lx = idx / c.ey, ly = idx - lx * c.ey;
+        const uint32_t ow = c.occ_s[lx * c.emax + ly];
+        if (ow == 0u || (ow >> 31) != cur_phase) continue;
+        const uint32_t p = ss_priority(ok, occ_slot(ow));
+        const int ix = rg_of_x(lx), iy = rg_of_y(ly);
+        RegionShared& rg = regs[iy * PASS_RGX + ix];
+        if (in_core(c, lx, ly, R)) {
+            const int at = atomicAdd((int*)&rg.n_list, 1);
+            if (at < PASS_LIST) rg.list[at] = ((uint64_t)p << 16) | (uint64_t)((lx << 8) | ly);
+            const int b = (((lx - rg_x0(ix)) >> 4) * PASS_BCOLS) + ((ly - rg_y0(iy)) >> 4);
+            atomicMin((uint32_t*)&rg.bfront[b], p);
+        } else {                                            // ring agents belong to a later launch
+            atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
         }
-        active[k] = m;
     }
+    __syncthreads();
+    // ---- my region ----
+    const int rgx = warp % PASS_RGX, rgy = warp / PASS_RGX;
+    const int rx0 = rg_x0(rgx), rx1 = rg_x0(rgx + 1), ry0 = rg_y0(rgy), ry1 = rg_y0(rgy + 1);
+    uint32_t thr = PRIO_INF;              // listed agents have priority < thr
+    int n_mine = me.n_list;
+    if (n_mine > PASS_LIST) {
+        // too many for one launch: keep the lower priorities (their possible blockers are lower still);
+        // the unlisted agents keep their blocks' frontiers finite, so neighbours above them give up
+        // bisection on the priority threshold: largest tested thr whose count fits the list
+        const int rw = ry1 - ry0, cells = (rx1 - rx0) * rw;
+        auto fill = [&](uint32_t t) {
+            int cnt = 0;
+            for (int base = 0; base < cells; base += 32) {
+                const int i = base + lane;
+                bool want = false;
+                uint64_t key = 0;
+                if (i < cells) {
+                    const int lx = rx0 + i / rw, ly = ry0 + i % rw;
+                    const uint32_t ow = c.occ_s[lx * c.emax + ly];
+                    if (ow != 0u && (ow >> 31) == cur_phase && in_core(c, lx, ly, R)) {
+                        const uint32_t p = ss_priority(ok, occ_slot(ow));
+                        if (p < t) { want = true; key = ((uint64_t)p << 16) | (uint64_t)((lx << 8) | ly); }
+                    }
+                }
+                const unsigned m = __ballot_sync(FULL, want);
+                if (want) {
+                    const int at = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (at < PASS_LIST) me.list[at] = key;
+                }
+                cnt += __popc(m);
+            }
+            return cnt;
+        };
+        uint32_t lo = 0u, hi = 1u << (2 * w.half);
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + (hi - lo) / 2u;
+            if (fill(mid) <= PASS_LIST) lo = mid; else hi = mid;
+        }
+        thr = lo;
+        n_mine = fill(thr);
+        __syncwarp();
+    }
+    uint64_t keys[PASS_KPL];
+#pragma unroll
+    for (int k = 0; k < PASS_KPL; k++) {
+        const int at = k * 32 + lane;
+        keys[k] = at < n_mine ? me.list[at] : ~0ull;
+    }
+    // a window without a single resolvable agent leaves right away
+    if (lane == 0 && n_mine > 0) atomicAdd(&sh.count[0], 1);
+    __syncthreads();
+    if (sh.count[0] == 0) return;
+    const long long t_listed = clock64();
     ThreadStats ts = {0, 0, 0, 0, 0, 0, 0};
-    // ---- dependency rounds ----
-    for (;;) {
-        uint32_t ready[PASS_WPT];
-        int any = 0;
+    // ---- the region's agents in ascending priority ----
+    for (int iter = 0;; iter++) {
+        if (iter > PASS_LIST + 8) { if (lane == 0) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x2222; } break; }
+        uint64_t km = keys[0];
 #pragma unroll
-        for (int k = 0; k < PASS_WPT; k++) {
-            ready[k] = 0u;
-            const int wi = tid + k * PASS_THREADS;
-            uint32_t t = active[k];
-            if (t == 0u) continue;
-            const int lx = wi / c.ew, wc = wi - lx * c.ew;
-            while (t) {
-                const int i = __ffs(t) - 1;
-                t &= t - 1;
-                const int ly = wc * 32 + i;
-                const uint32_t bl = blk_s[lx * c.emax + ly];
-                if (bl) {   // cached blocker still pending?
-                    const int br = (bl - 1) >> 8, bq = (bl - 1) & 255;
-                    if ((c.pend_s[br * c.ew + (bq >> 5)] >> (bq & 31)) & 1u) continue;
-                }
-                const uint32_t ow = c.occ_s[lx * c.emax + ly];
-                const uint32_t slot = occ_slot(ow);
-                const uint32_t pa = ss_priority(ok, slot);
-                const uint32_t nb = find_blocker(c, ok, lx, ly, occ_vision(ow), pa, slot, V);
-                if (nb) {
-                    blk_s[lx * c.emax + ly] = (uint16_t)nb;
-                    // a blocker outside the core is never resolved by this launch
-                    const int br = (nb - 1) >> 8, bq = (nb - 1) & 255;
-                    const bool bcore = (c.full_x || (br >= R && br < c.ex - R)) && (c.full_y || (bq >= R && bq < c.ey - R));
-                    if (!bcore) active[k] &= ~(1u << i);
-                    continue;
-                }
-                blk_s[lx * c.emax + ly] = 0;
-                if (ow & OCC_Q1) {      // Q1: wait for the at-risk predecessor's outcome
-                    const AgentRec* rec = &w.agents[slot];
-                    if (rec->pred_step == (uint32_t)(iteration + 1)) {
-                        const uint32_t st = *((volatile const uint32_t*)&w.agents[rec->pred - 1u].status);
-                        if ((st >> 2) != (uint32_t)(iteration + 1)) continue;       // not resolved yet
+        for (int k = 1; k < PASS_KPL; k++) km = keys[k] < km ? keys[k] : km;
+        uint64_t kmin = km;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(FULL, kmin, o); kmin = t < kmin ? t : kmin; }
+        if (kmin == ~0ull) break;
+        const uint32_t pa = (uint32_t)(kmin >> 16);
+        const int lx = (int)((kmin >> 8) & 255u), ly = (int)(kmin & 255u);
+        const uint32_t ow = c.occ_s[lx * c.emax + ly];
+        const int a = occ_vision(ow);
+        bool blocked = false;
+        // conflict zone of A: box |d| <= V plus the arm extensions a + V.  Wait until every block of
+        // another region that the zone touches has its frontier above priority(A).
+        unsigned reach = 0u;
+        {
+            t_m = clock64();
+            const int zx0 = lx - V, zx1 = lx + V, zy0 = ly - V, zy1 = ly + V;
+            const int ax0 = lx - a - V, ax1 = lx + a + V, ay0 = ly - a - V, ay1 = ly + a + V;
+            const bool torus = c.full_x || c.full_y;
+            int stuck = 0;
+            for (int y = 0; y < PASS_WARPS; y++) {
+                if (y == warp) continue;
+                const int yx0 = rg_x0(y % PASS_RGX), yx1 = rg_x0(y % PASS_RGX + 1) - 1;
+                const int yy0 = rg_y0(y / PASS_RGX), yy1 = rg_y0(y / PASS_RGX + 1) - 1;
+                bool touch;
+                if (torus) touch = true;               // torus inside the window: stay conservative
+                else touch = (zx0 <= yx1 && zx1 >= yx0 && zy0 <= yy1 && zy1 >= yy0) ||
+                             (ax0 <= yx1 && ax1 >= yx0 && ly >= yy0 && ly <= yy1) ||
+                             (lx >= yx0 && lx <= yx1 && ay0 <= yy1 && ay1 >= yy0);
+                if (!touch) continue;
+                reach |= 1u << y;
+                // lane = block of region y
+                const int bxl = yx0 + ((lane / PASS_BCOLS) << 4), byl = yy0 + ((lane % PASS_BCOLS) << 4);
+                const int bxh = min(bxl + 15, yx1), byh = min(byl + 15, yy1);
+                bool mine = bxl <= yx1 && byl <= yy1 && lane < PASS_BCOLS * PASS_BROWS;
+                if (mine && !torus)
+                    mine = (zx0 <= bxh && zx1 >= bxl && zy0 <= byh && zy1 >= byl) ||
+                           (ax0 <= bxh && ax1 >= bxl && ly >= byl && ly <= byh) ||
+                           (lx >= bxl && lx <= bxh && ay0 <= byh && ay1 >= byl);
+                unsigned bm = __ballot_sync(FULL, mine);
+                if (lane == 0) {                      // a single lane spins; the others wait at the shuffle below
+                    while (bm) {
+                        const int b = __ffs(bm) - 1;
+                        bm &= bm - 1;
+                        const volatile uint32_t* f = &regs[y].bfront[b];
+                        int spins = 0;
+                        while (*f <= pa) {
+                            if (regs[y].done) { if (*f <= pa) stuck = 1; break; }    // trimmed list: stopped below pa
+                            __nanosleep(40);
+                            if (++spins > 20000) {     // watchdog (~10 ms): never hang the GPU; retry in a later launch
+                                stuck = 1;
+                                if (atomicAdd(&w.acc->watchdog, 1ull) == 0ull) {
+                                    w.acc->wd_info[0] = ((unsigned long long)warp << 48) | ((unsigned long long)y << 40) | ((unsigned long long)b << 32) | pa;
+                                    w.acc->wd_info[1] = ((unsigned long long)*f << 32) | (unsigned)regs[y].done;
+                                    w.acc->wd_info[2] = ((unsigned long long)blockIdx.x << 32) | (unsigned)((lx << 8) | ly);
+                                }
+                                break;
+                            }
+                        }
+                        if (stuck) break;
                     }
                 }
-                ready[k] |= 1u << i;
-                any = 1;
+                stuck = __shfl_sync(FULL, stuck, 0);
+                if (stuck) break;
+            }
+            blocked = stuck != 0;
+            __threadfence_block();
+            t_wait += clock64() - t_m;
+        }
+        // exact conflict test against the pending agents this launch cannot resolve (ring agents,
+        // unresolved Q1 successors, and everything already blocked by those): lane l < 2V+1 owns zone
+        // row dx = l - V of the blocked bitmap, lane 31 the same-row arm extensions, lanes < 2a the
+        // same-column arm extension cells
+        if (!blocked) {
+            bool hit = false;
+            auto consider = [&](int r, int q, int dx, int dy) {
+                const uint32_t bw = c.occ_s[r * c.emax + q];
+                if (bw == 0u || (r == lx && q == ly)) return;
+                if (!crosses_meet(dx, dy, a, occ_vision(bw))) return;
+                if (ss_priority(ok, occ_slot(bw)) < pa) hit = true;
+            };
+            auto bits_of = [&](int r, int c0, int len) {
+                uint32_t out = 0u;
+                if (c0 >= 0 && c0 + len <= c.ey) {
+                    const volatile uint32_t* row = blk_bits + r * ew;
+                    const int w0 = c0 >> 5, shf = c0 & 31;
+                    const uint32_t lo = row[w0], hi = (w0 + 1 < ew) ? row[w0 + 1] : 0u;
+                    out = __funnelshift_r(lo, hi, shf) & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u));
+                } else {
+                    for (int i = 0; i < len; i++) {
+                        int cc = c0 + i;
+                        if (c.full_y) cc = ss_wrap(cc, c.ey); else if (cc < 0 || cc >= c.ey) continue;
+                        out |= ((((const volatile uint32_t*)blk_bits)[r * ew + (cc >> 5)] >> (cc & 31)) & 1u) << i;
+                    }
+                }
+                return out;
+            };
+            if (lane < 2 * V + 1) {
+                const int dx = lane - V, r = wrap_row(c, lx + dx);
+                if (r >= 0 && r < c.ex) {
+                    uint32_t bits = bits_of(r, ly - V, 2 * V + 1);
+                    while (bits) { const int i = __ffs(bits) - 1; bits &= bits - 1; consider(r, wrap_col(c, ly + i - V), dx, i - V); }
+                }
+            } else if (lane == 31) {
+                uint32_t lo = bits_of(lx, ly - V - a, a);
+                while (lo) { const int i = __ffs(lo) - 1; lo &= lo - 1; const int dy = i - V - a; consider(lx, wrap_col(c, ly + dy), 0, dy); }
+                uint32_t hi = bits_of(lx, ly + V + 1, a);
+                while (hi) { const int i = __ffs(hi) - 1; hi &= hi - 1; const int dy = V + 1 + i; consider(lx, wrap_col(c, ly + dy), 0, dy); }
+            }
+            if (lane < 2 * a) {
+                const int dx = (lane & 1) ? (V + 1 + (lane >> 1)) : -(V + 1 + (lane >> 1));
+                const int r = wrap_row(c, lx + dx);
+                if (r >= 0 && r < c.ex && ((((const volatile uint32_t*)blk_bits)[r * ew + (ly >> 5)] >> (ly & 31)) & 1u)) consider(r, ly, dx, 0);
+            }
+            blocked = __any_sync(FULL, hit);
+        }
+        uint32_t slot = 0;
+        bool skipped = false;
+        if (!blocked) {
+            slot = occ_slot(ow);
+            if (ow & OCC_Q1) {      // Q1: the at-risk predecessor decides whether A gets its turn
+                const AgentRec* rec = &w.agents[slot];
+                if (rec->pred_step == (uint32_t)(iteration + 1)) {
+                    const volatile uint32_t* stp = &w.agents[rec->pred - 1u].status;
+                    uint32_t st = *stp;
+                    for (int tries = 0; tries < 4 && (st >> 2) != (uint32_t)(iteration + 1); tries++) { __nanosleep(250); st = *stp; }
+                    if ((st >> 2) != (uint32_t)(iteration + 1)) blocked = true;     // retry in a later launch
+                    else skipped = ((st & 3u) == ST_DIED);
+                }
             }
         }
-        if (!__syncthreads_or(any)) break;
-#pragma unroll
-        for (int k = 0; k < PASS_WPT; k++) {
-            uint32_t t = ready[k];
-            if (t == 0u) continue;
-            const int wi = tid + k * PASS_THREADS;
-            const int lx = wi / c.ew, wc = wi - lx * c.ew;
-            active[k] &= ~t;
-            c.pend_s[wi] &= ~t;
-            while (t) {
-                const int i = __ffs(t) - 1;
-                t &= t - 1;
-                const int ly = wc * 32 + i;
-                const uint32_t ow = c.occ_s[lx * c.emax + ly];
-                bool skipped = false;
-                if (ow & OCC_Q1) {
-                    const uint32_t slot = occ_slot(ow);
-                    const AgentRec* rec = &w.agents[slot];
-                    if (rec->pred_step == (uint32_t)(iteration + 1)) {
-                        const uint32_t st = *((volatile const uint32_t*)&w.agents[rec->pred - 1u].status);
-                        skipped = ((st & 3u) == ST_DIED);
-                    }
-                    if (skipped) {      // loses its turn: stays put, no metabolism (Q1)
-                        const uint32_t nw = occ_pack(slot, occ_vision(ow), next_phase);
-                        c.occ_s[lx * c.emax + ly] = nw;
-                        const int gx = ss_wrap(c.gx0 + lx, n), gy = ss_wrap(c.gy0 + ly, n);
-                        w.occw[(size_t)gx * n + gy] = nw;
+        if (blocked) {
+            n_blocked_me++;
+            if (lane == 0) atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+        } else {
+            t_m = clock64();
+            if (skipped) {
+                if (lane == 0) {      // loses its turn: stays put, no metabolism (Q1)
+                    const uint32_t nw = occ_pack(slot, a, next_phase);
+                    c.occ_s[lx * c.emax + ly] = nw;
+                    const int gx = ss_wrap(c.gx0 + lx, n), gy = ss_wrap(c.gy0 + ly, n);
+                    w.occw[(size_t)gx * n + gy] = nw;
+                    if (ow & OCC_RISK)
                         *((volatile uint32_t*)&w.agents[slot].status) = ((uint32_t)(iteration + 1) << 2) | ST_SKIPPED;
-                        ts.resolved++;
+                    ts.resolved++;
+                }
+            } else {
+                warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
+                n_turns++;
+            }
+            t_turn += clock64() - t_m;
+        }
+        // A is finished (or parked in the blocked set): advance the frontier of its block
+        __syncwarp();
+        __threadfence_block();
+        {
+            const int bx_a = (lx - rx0) >> 4, by_a = (ly - ry0) >> 4;
+            uint32_t mn = PRIO_INF;
+#pragma unroll
+            for (int k = 0; k < PASS_KPL; k++) {
+                if (keys[k] == kmin) keys[k] = ~0ull;
+                if (keys[k] != ~0ull) {
+                    const int kx = (int)((keys[k] >> 8) & 255u), ky = (int)(keys[k] & 255u);
+                    if (((kx - rx0) >> 4) == bx_a && ((ky - ry0) >> 4) == by_a) {
+                        const uint32_t kp = (uint32_t)(keys[k] >> 16);
+                        mn = kp < mn ? kp : mn;
                     }
                 }
-                if (!skipped) agent_turn(w, c, lx, ly, ow & ~OCC_Q1, iteration, env_time, skey, next_phase, ts);
             }
+            mn = __reduce_min_sync(FULL, mn);
+            if (thr != PRIO_INF && mn == PRIO_INF) mn = thr;      // unlisted agents may sit in this block
+            if (lane == 0) me.bfront[bx_a * PASS_BCOLS + by_a] = mn;
         }
-        __syncthreads();
+    }
+    if (lane == 0) { __threadfence_block(); me.done = 1; }
+    __syncthreads();
+    if (w.dbg) {
+        if (lane == 0) {
+            atomicAdd(&w.dbg[9], (unsigned long long)n_turns);
+            atomicAdd(&w.dbg[12], (unsigned long long)n_blocked_me);
+            atomicAdd(&w.dbg[15], (unsigned long long)t_turn);
+            atomicAdd(&w.dbg[16], (unsigned long long)t_wait);
+            atomicAdd(&w.dbg[13], (unsigned long long)n_mine);
+        }
+        if (tid == 0) {
+            atomicAdd(&w.dbg[0], 1ull);                                   // windows with work
+            atomicAdd(&w.dbg[3], (unsigned long long)(t_listed - t_start));
+            atomicAdd(&w.dbg[11], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&w.dbg[6], (unsigned long long)(clock64() - t_start));
+        }
     }
     // ---- block reduction of the step accumulators ----
     unsigned vals[7] = {ts.sum_m, ts.sum_v, ts.acted, ts.deaths, ts.resolved, ts.small, ts.inexact};
@@ -400,15 +651,65 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     for (int q = 0; q < 7; q++) {
         unsigned v = vals[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == 0) red[tid >> 5] = v;
+        if (lane == 0) sh.red[tid >> 5] = v;
         __syncthreads();
         if (tid == 0) {
             unsigned long long s = 0;
-            for (int i = 0; i < PASS_THREADS / 32; i++) s += red[i];
+            for (int i = 0; i < PASS_WARPS; i++) s += sh.red[i];
             if (s) {
                 if (q == 4) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)s));
                 else atomicAdd(dst[q], s);
             }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ settle ----
+// Deferred part of every SAFE agent's turn, one coalesced streaming pass over the agent store:
+// harvest (agent.py:832), production + consumption pollution at the destination
+// (agent.py:825-826, sugarscape.py:566-567; environment.py:312-315), metabolism
+// (sugarscape.py:569), statistics (sugarscape.py:575-583).
+__global__ void __launch_bounds__(256)
+ss_settle_kernel(DevWorld w, int64_t iteration, int64_t env_time) {
+    __shared__ unsigned long long red[8];
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sum_m = 0, sum_v = 0, acted = 0, small = 0, inexact = 0, fault = 0;
+    if (slot < w.n_slots) {
+        AgentRec* rec = &w.agents[slot];
+        const uint32_t attr = rec->attr, turn = rec->turn;
+        if (attr_alive(attr) && (turn >> 8) == ((uint32_t)(iteration + 1) & 0xffffffu)) {
+            const int h = (int)(turn & 255u), metab = attr_metab(attr);
+            double sugar = rec->sugar;
+            if (w.cfg.rule_move_eat) sugar = ss_set_sugar(ss_max0(sugar + (double)h));
+            if (w.cfg.rule_pollution && w.cfg.pollution_start_time <= env_time) {
+                double p = w.poll[rec->pos];
+                if (w.cfg.rule_move_eat) p += ((double)h * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b);
+                if (sugar > 0.0) p += (0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b);
+                w.poll[rec->pos] = p;
+            }
+            sugar = ss_set_sugar(ss_max0(sugar - (double)metab));
+            rec->sugar = sugar;
+            sum_m = (unsigned)metab; sum_v = (unsigned)attr_vision(attr); acted = 1;
+            if (sugar == 0.01) small = 1;
+            else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
+            else inexact = 1;
+            if (w.cfg.rule_can_starve && sugar <= 0.1) fault = 1;      // a "safe" agent starved: must not happen
+        }
+    }
+    unsigned long long vals[6] = {sum_m, sum_v, acted, small, inexact, fault};
+    unsigned long long* dst[6] = {&w.acc->sum_metab, &w.acc->sum_vision, &w.acc->acted, &w.acc->hist_small,
+                                  &w.acc->inexact, &w.acc->fault};
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        unsigned long long v = vals[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long s = 0;
+            for (int i = 0; i < 8; i++) s += red[i];
+            if (s) atomicAdd(dst[q], s);
         }
         __syncthreads();
     }
@@ -461,7 +762,7 @@ ss_stats_kernel(DevWorld w, int stats_index) {
         const double total_area = s_area[0] + 0.01 * c0 * c0 / 2.0;
         const double fair = height * nw / 2.0;
         double gini = fair == 0.0 ? 1.0 : (fair - total_area) / fair;
-        if (a->inexact) gini = __longlong_as_double(0x7ff8000000000000ll);
+        if (a->inexact || a->fault) gini = __longlong_as_double(0x7ff8000000000000ll);
         a->population -= a->deaths;
         const double pop = (double)a->population;
         ss_step_stats st;
@@ -477,35 +778,32 @@ ss_stats_kernel(DevWorld w, int stats_index) {
 
 // ---------------------------------------------------------------------------- growback ----
 // environment.py:133-144: sugar = min(sugar + alpha, cap), pointwise -> 24 B/cell, HBM-bound.
+// Each thread handles 4 consecutive cells (two 128-bit loads per array) and also refreshes
+// the int(sugar) byte mirror (+1 B/cell) the move passes stage into shared memory.
+__device__ static inline double grow1(double s, double alpha, double c) { const double v = s + alpha; return v <= c ? v : c; }
+
 __global__ void __launch_bounds__(256)
-ss_grow_kernel(double* __restrict__ sugar, const double* __restrict__ cap, double alpha, size_t cells) {
-    const size_t nvec = cells / 2;
+ss_grow_kernel(double* __restrict__ sugar, const double* __restrict__ cap, uint8_t* __restrict__ isugar, double alpha,
+               size_t cells) {
+    const size_t nquad = cells / 4;
     double2* s2 = reinterpret_cast<double2*>(sugar);
     const double2* c2 = reinterpret_cast<const double2*>(cap);
+    uchar4* i4 = reinterpret_cast<uchar4*>(isugar);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-        double2 s[4], c[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { s[u] = s2[i + u * stride]; c[u] = __ldcs(&c2[i + u * stride]); }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            double a = s[u].x + alpha, b = s[u].y + alpha;
-            s[u].x = a <= c[u].x ? a : c[u].x;
-            s[u].y = b <= c[u].y ? b : c[u].y;
-            s2[i + u * stride] = s[u];
-        }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquad; i += stride) {
+        double2 a = s2[2 * i], b = s2[2 * i + 1];
+        const double2 ca = __ldcs(&c2[2 * i]), cb = __ldcs(&c2[2 * i + 1]);
+        a.x = grow1(a.x, alpha, ca.x); a.y = grow1(a.y, alpha, ca.y);
+        b.x = grow1(b.x, alpha, cb.x); b.y = grow1(b.y, alpha, cb.y);
+        s2[2 * i] = a; s2[2 * i + 1] = b;
+        if (isugar) i4[i] = make_uchar4((unsigned char)(int)a.x, (unsigned char)(int)a.y, (unsigned char)(int)b.x,
+                                        (unsigned char)(int)b.y);
     }
-    for (; i < nvec; i += stride) {
-        double2 s = s2[i], c = __ldcs(&c2[i]);
-        double a = s.x + alpha, b = s.y + alpha;
-        s.x = a <= c.x ? a : c.x;
-        s.y = b <= c.y ? b : c.y;
-        s2[i] = s;
-    }
-    if ((cells & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        double a = sugar[cells - 1] + alpha, c = cap[cells - 1];
-        sugar[cells - 1] = a <= c ? a : c;
+    if (blockIdx.x == 0 && threadIdx.x < (cells & 3)) {
+        const size_t c = nquad * 4 + threadIdx.x;
+        const double v = grow1(sugar[c], alpha, cap[c]);
+        sugar[c] = v;
+        if (isugar) isugar[c] = (unsigned char)(int)v;
     }
 }
 
@@ -525,9 +823,10 @@ ss_seasons_kernel(DevWorld w, double alpha_north, double alpha_south) {
         if (!in_n && !in_s) continue;
         double s = w.sugar[c];
         const double cp = w.cap[c];
-        if (in_n) { const double v = s + alpha_north; s = v <= cp ? v : cp; }
-        if (in_s) { const double v = s + alpha_south; s = v <= cp ? v : cp; }
+        if (in_n) s = grow1(s, alpha_north, cp);
+        if (in_s) s = grow1(s, alpha_south, cp);
         w.sugar[c] = s;
+        if (w.isugar) w.isugar[c] = (unsigned char)(int)s;
     }
 }
 
@@ -672,14 +971,20 @@ cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t
     return cudaGetLastError();
 }
 
-size_t ss_pass_smem_bytes(int emax, int ew) {
-    return (size_t)emax * emax * 4 + (size_t)emax * ew * 4 + (size_t)emax * emax * 2;
+size_t ss_pass_smem_bytes(int emax, int ew, int vmax) {
+    (void)vmax;
+    return (((size_t)emax * emax * 5 + 15) & ~(size_t)15) + sizeof(RegionShared) * PASS_WARPS + (size_t)emax * ew * 4 + 16;
+}
+
+cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_time, cudaStream_t s) {
+    if (w.n_slots > 0) ss_settle_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w, iteration, env_time);
+    return cudaGetLastError();
 }
 
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s) {
     static size_t configured = 0;
-    const size_t smem = ss_pass_smem_bytes(g.emax, g.ew);
+    const size_t smem = ss_pass_smem_bytes(g.emax, g.ew, w.vmax);
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(ss_move_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -705,10 +1010,10 @@ cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, c
         if (blocks > (size_t)sm_count * 16) blocks = (size_t)sm_count * 16;
         ss_seasons_kernel<<<(unsigned)blocks, 256, 0, s>>>(w, an, as);
     } else if (w.cfg.rule_grow) {
-        size_t blocks = (cells / 2 + 255) / 256;
-        if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
+        size_t blocks = (cells / 4 + 255) / 256;
+        if (blocks > (size_t)sm_count * 16) blocks = (size_t)sm_count * 16;
         if (blocks < 1) blocks = 1;
-        ss_grow_kernel<<<(unsigned)blocks, 256, 0, s>>>(w.sugar, w.cap, w.cfg.grow_factor, cells);
+        ss_grow_kernel<<<(unsigned)blocks, 256, 0, s>>>(w.sugar, w.cap, w.isugar, w.cfg.grow_factor, cells);
     }
     return cudaGetLastError();
 }

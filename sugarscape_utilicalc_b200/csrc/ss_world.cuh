@@ -13,6 +13,9 @@ struct StepAccum {                  // per-step reduction targets of the lattice
     unsigned long long population;  // living agents
     unsigned long long hist_small;  // agents whose wealth is the 0.01 floor
     unsigned long long inexact;     // wealth values the histogram cannot represent
+    unsigned long long fault;       // internal consistency violations (must stay 0)
+    unsigned long long watchdog;    // spin-wait watchdog firings since upload (diagnostic; 0 in healthy runs)
+    unsigned long long wd_info[3];
 };
 
 struct DevWorld {
@@ -24,6 +27,7 @@ struct DevWorld {
     double* cap;
     double* poll;
     uint32_t* occw;
+    uint8_t* isugar;                // int(sugar) mirror (lattice path)
     AgentRec* agents;
     // serial path (SS_RNG_MT19937, and the universal fallback)
     int32_t* order;                 // persistent list order (slots)
@@ -37,6 +41,7 @@ struct DevWorld {
     StepAccum* acc;
     uint32_t* hist;                 // SS_GINI_BINS
     int vmax;                       // max vision over all agents
+    unsigned long long* dbg;        // optional instrumentation counters (32 entries) or null
 };
 
 struct PassGeom {                   // window tiling of one move pass
@@ -45,4 +50,5 @@ struct PassGeom {                   // window tiling of one move pass
     int ew;                         // bitmap words per row
     int shift_x, shift_y;           // tiling shift
     int ring;                       // 2*vmax: agents closer than this to a window edge are not resolved
+    int align;                      // window boundaries are multiples of this many cells (4: vector loads)
 };

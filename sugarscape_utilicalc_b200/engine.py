@@ -128,9 +128,9 @@ class Engine:
                     syncs=int(out[4]), window=int(out[5]))
 
     def kernel_times(self):
-        out = np.zeros(7, dtype=np.float64)
-        self._check(self._lib.ss_get_kernel_times(self._h, _ptr(out), 7), "ss_get_kernel_times")
-        return dict(zip(("prepare", "move", "stats", "grow", "diffuse", "serial", "last_call"), out.tolist()))
+        out = np.zeros(8, dtype=np.float64)
+        self._check(self._lib.ss_get_kernel_times(self._h, _ptr(out), 8), "ss_get_kernel_times")
+        return dict(zip(("prepare", "move", "stats", "grow", "diffuse", "serial", "last_call", "settle"), out.tolist()))
 
     def set_option(self, name, value):
         self._check(self._lib.ss_set_option(self._h, name.encode(), int(value)), "ss_set_option")
