@@ -133,6 +133,20 @@ int  ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n);
  * "window" (max window extent of the move passes, 32..176) */
 int  ss_set_option(ss_engine* e, const char* name, int64_t value);
 
+/* Multi-GPU (one process per GPU; sugarscape_utilicalc_b200/sharded.py).  Every rank holds a replica of the
+ * state and resolves the agents of its share of the window rows; the turns it resolved are exchanged as 48-byte
+ * log entries (NCCL all-gather) and replayed on the other replicas.  One step =
+ *   ss_shard_begin_step; { ss_shard_pass; <all-gather logs>; ss_shard_apply(each other rank's entries) }
+ *   until ss_shard_pending == 0; ss_shard_end_step.
+ * log_base/log_begin/log_end describe this rank's entries of the pass in device memory. */
+int  ss_shard_enable(ss_engine* e, int32_t rank, int32_t world);
+int  ss_shard_begin_step(ss_engine* e);
+int  ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base);
+int  ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n);
+int  ss_shard_pending(ss_engine* e, uint64_t* pending);
+int  ss_shard_end_step(ss_engine* e, ss_step_stats* out);
+#define SS_SHARD_ENTRY_BYTES 48
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,7 +45,8 @@ EXPORTS = (
     "ss_create", "ss_destroy", "ss_last_error", "ss_upload_cells", "ss_upload_agents",
     "ss_set_rng_mt19937", "ss_get_rng_mt19937", "ss_set_rng_keyed", "ss_step", "ss_agent_count",
     "ss_download_cells", "ss_download_agents", "ss_get_counters", "ss_get_kernel_times",
-    "ss_set_option", "ss_version",
+    "ss_set_option", "ss_version", "ss_shard_enable", "ss_shard_begin_step", "ss_shard_pass", "ss_shard_apply",
+    "ss_shard_pending", "ss_shard_end_step",
 )
 
 _lib = None
@@ -84,5 +85,11 @@ def lib():
     L.ss_get_counters.argtypes = [vp, vp, C.c_int32]
     L.ss_get_kernel_times.argtypes = [vp, vp, C.c_int32]
     L.ss_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.ss_shard_enable.argtypes = [vp, C.c_int32, C.c_int32]
+    L.ss_shard_begin_step.argtypes = [vp]
+    L.ss_shard_pass.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp)]
+    L.ss_shard_apply.argtypes = [vp, vp, C.c_uint64]
+    L.ss_shard_pending.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.ss_shard_end_step.argtypes = [vp, vp]
     _lib = L
     return L

@@ -20,6 +20,8 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
                                 cudaStream_t s);
 cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s);
 cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_time, cudaStream_t s);
+cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int64_t iteration, int64_t env_time,
+                                cudaStream_t s);
 cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
 cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl, cudaStream_t s);
 }
@@ -38,6 +40,8 @@ struct ss_engine {
     int path = -1, path_option = -1;
     PassGeom geom{};
     int ntile = 1, emin = 0;
+    int shard_rank = 0, shard_world = 1;       // multi-GPU replicas (sharded.py)
+    int shard_pass = 0;
     int last_passes = 4;
     int stats_cap = 0;
     int* d_flags = nullptr;
@@ -145,7 +149,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.sugar); cudaFree(e->w.cap); cudaFree(e->w.poll); cudaFree(e->w.occw); cudaFree(e->w.isugar);
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
-    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags);
+    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->w.log); cudaFree(e->w.log_count);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -353,6 +357,22 @@ static int env_phase(ss_engine* e) {
     return SS_OK;
 }
 
+static void pass_geometry(ss_engine* e, int p, PassGeom* out) {
+    PassGeom g = e->geom;
+    if (e->ntile == 3) {                                  // diagonal shifts by thirds of a window
+        const int t = p % 3;
+        g.shift_x = g.shift_y = g.align * ((t * e->emin / 3) / g.align);
+    } else if (e->ntile == 4) {                           // (0,0) (h,h) (0,h) (h,0)
+        const int h = g.align * ((e->emin / 2) / g.align);
+        g.shift_x = (p & 1) ? h : 0;
+        g.shift_y = ((p & 3) == 1 || (p & 3) == 2) ? h : 0;
+    } else {
+        g.shift_x = g.shift_y = 0;
+    }
+    g.bx_lo = 0; g.bx_cnt = g.nwin;
+    *out = g;
+}
+
 static int lattice_step(ss_engine* e, int stats_index) {
     {
         KTimer t(e, KT_PREPARE);
@@ -365,17 +385,8 @@ static int lattice_step(ss_engine* e, int stats_index) {
         const int first_check = e->geom.nwin == 1 ? 1 : std::max(2, e->last_passes - 1);
         int p = 0;
         for (;;) {
-            PassGeom g = e->geom;
-            if (e->ntile == 3) {                                  // diagonal shifts by thirds of a window
-                const int t = p % 3;
-                g.shift_x = g.shift_y = g.align * ((t * e->emin / 3) / g.align);
-            } else if (e->ntile == 4) {                           // (0,0) (h,h) (0,h) (h,0)
-                const int h = g.align * ((e->emin / 2) / g.align);
-                g.shift_x = (p & 1) ? h : 0;
-                g.shift_y = ((p & 3) == 1 || (p & 3) == 2) ? h : 0;
-            } else {
-                g.shift_x = g.shift_y = 0;
-            }
+            PassGeom g;
+            pass_geometry(e, p, &g);
             CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
             e->launches++; e->passes++; p++;
             if (p >= first_check || e->trace) {
@@ -571,4 +582,91 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "trace") { e->trace = (int)value; return SS_OK; }
     if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
+}
+
+// ------------------------------------------------------------------ multi-GPU replicas ----
+// sharded.py drives one step as: ss_shard_begin_step -> { ss_shard_pass -> all-gather of the
+// ranks' turn logs -> ss_shard_apply } until nothing is pending -> ss_shard_end_step.
+extern "C" int ss_shard_enable(ss_engine* e, int32_t rank, int32_t world) {
+    if (!e || world < 1 || rank < 0 || rank >= world) return set_err(e, SS_ERR_ARG, "bad rank/world");
+    if (!e->have_agents || e->path != PATH_LATTICE) return set_err(e, SS_ERR_STATE, "sharding needs the lattice path (upload first)");
+    if (e->cfg.rule_pollution && (e->cfg.pollution_a < 0.0 || e->cfg.pollution_b < 0.0))
+        return set_err(e, SS_ERR_UNSUPPORTED, "sharded replicas need non-negative pollution coefficients");
+    static_assert(sizeof(ShardLogEntry) == SS_SHARD_ENTRY_BYTES, "log entry size");
+    CK(cudaSetDevice(e->device));
+    e->shard_rank = rank; e->shard_world = world;
+    if (!e->w.log) {
+        e->w.log_cap = e->w.n_slots;
+        CK(cudaMalloc(&e->w.log, sizeof(ShardLogEntry) * (size_t)e->w.log_cap));
+        CK(cudaMalloc(&e->w.log_count, sizeof(unsigned long long)));
+    }
+    CK(cudaMemset(e->w.log_count, 0, sizeof(unsigned long long)));
+    return SS_OK;
+}
+
+extern "C" int ss_shard_begin_step(ss_engine* e) {
+    if (!e || !e->w.log) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(e->w.log_count, 0, sizeof(unsigned long long), e->stream));
+    CK(ss_launch_prepare(e->w, e->iteration, e->stream));
+    e->launches += e->cfg.rule_can_starve ? 2 : 1;
+    e->shard_pass = 0;
+    int rc = ensure_stats(e, 1);
+    return rc;
+}
+
+// runs pass `shard_pass` on this rank's share of the window rows; returns the log range it appended
+extern "C" int ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base) {
+    if (!e || !e->w.log || !log_begin || !log_end || !log_base) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
+    CK(cudaSetDevice(e->device));
+    unsigned long long before = 0, after = 0;
+    CK(cudaMemcpyAsync(&before, e->w.log_count, sizeof before, cudaMemcpyDeviceToHost, e->stream));
+    PassGeom g;
+    pass_geometry(e, e->shard_pass, &g);
+    const int nw = g.nwin, W = e->shard_world, r = e->shard_rank;
+    g.bx_lo = (int)(((long long)r * nw) / W);
+    g.bx_cnt = (int)(((long long)(r + 1) * nw) / W) - g.bx_lo;
+    CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
+    e->launches++; e->passes++; e->shard_pass++;
+    CK(cudaMemcpyAsync(&after, e->w.log_count, sizeof after, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    *log_begin = before; *log_end = after; *log_base = e->w.log;
+    return SS_OK;
+}
+
+// replays `n` entries (device pointer) resolved by another rank on this replica
+extern "C" int ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n) {
+    if (!e || !e->w.log) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
+    CK(cudaSetDevice(e->device));
+    CK(ss_launch_apply_log(e->w, dev_entries, n, e->iteration, e->env_time, e->stream));
+    if (n) e->launches++;
+    return SS_OK;
+}
+
+extern "C" int ss_shard_pending(ss_engine* e, uint64_t* pending) {
+    if (!e || !pending) return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->h_pending, &e->w.acc->pending, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    *pending = *e->h_pending;
+    return SS_OK;
+}
+
+extern "C" int ss_shard_end_step(ss_engine* e, ss_step_stats* out) {
+    if (!e || !e->w.log) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
+    CK(cudaSetDevice(e->device));
+    CK(ss_launch_settle(e->w, e->iteration, e->env_time, e->stream));
+    CK(ss_launch_stats(e->w, 0, e->stream));
+    e->launches += 2;
+    int rc = env_phase(e);
+    if (rc) return rc;
+    e->iteration++; e->env_time++; e->steps++;
+    e->stepped = true;
+    if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    return SS_OK;
 }

@@ -236,6 +236,12 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
         }
         recp->pos = (uint32_t)cell;
         recp->turn = ((uint32_t)(iteration + 1) << 8) | (uint32_t)ch.sg;
+        if (w.log) {
+            ShardLogEntry en;
+            en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
+            en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.status = 0u; en.turn = recp->turn; en.kind_harvest = 0u | ((uint32_t)ch.sg << 8);
+            w.log[atomicAdd(w.log_count, 1ull)] = en;
+        }
         return;
     }
     const bool pol = w.cfg.rule_pollution != 0 && w.cfg.pollution_start_time <= env_time;
@@ -267,7 +273,15 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
     recp->pos = (uint32_t)cell;
     recp->attr = attr;
     __threadfence();                       // the turn's effects before its status (Q1 readers)
-    *((volatile uint32_t*)&recp->status) = ((uint32_t)(iteration + 1) << 2) | (died ? ST_DIED : ST_ACTED);
+    const uint32_t status = ((uint32_t)(iteration + 1) << 2) | (died ? ST_DIED : ST_ACTED);
+    *((volatile uint32_t*)&recp->status) = status;
+    if (w.log) {
+        ShardLogEntry en;
+        en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
+        en.sugar = sugar; en.poll = w.cfg.rule_pollution ? w.poll[cell] : 0.0; en.attr = attr; en.status = status; en.turn = 0u;
+        en.kind_harvest = 1u | ((uint32_t)ch.sg << 8);
+        w.log[atomicAdd(w.log_count, 1ull)] = en;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -309,7 +323,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     __syncthreads();
     if (!sh.go) return;
     // ---- window geometry: balanced boundaries in units of `align` cells, shifted tiling ----
-    const int bx = blockIdx.x % g.nwin, by = blockIdx.x / g.nwin;
+    const int bx = g.bx_lo + (int)blockIdx.x / g.nwin, by = (int)blockIdx.x % g.nwin;
     const int nu = n / g.align;
     const int x_lo = g.align * (int)(((long long)bx * nu) / g.nwin), x_hi = g.align * (int)(((long long)(bx + 1) * nu) / g.nwin);
     const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
@@ -597,6 +611,13 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                     if (ow & OCC_RISK)
                         *((volatile uint32_t*)&w.agents[slot].status) = ((uint32_t)(iteration + 1) << 2) | ST_SKIPPED;
                     ts.resolved++;
+                    if (w.log) {
+                        ShardLogEntry en;
+                        en.slot = slot; en.old_cell = en.new_cell = (uint32_t)(gx * n + gy); en.new_word = nw;
+                        en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.turn = 0u; en.kind_harvest = 2u;
+                        en.status = (ow & OCC_RISK) ? (((uint32_t)(iteration + 1) << 2) | ST_SKIPPED) : 0u;
+                        w.log[atomicAdd(w.log_count, 1ull)] = en;
+                    }
                 }
             } else {
                 warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
@@ -663,6 +684,55 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         }
         __syncthreads();
     }
+}
+
+// -------------------------------------------------------------------- multi-GPU replicas ----
+// Every rank holds the whole lattice and agent store and runs the move pass on its share of the
+// window rows; the turns it resolved travel as ShardLogEntry records (NCCL all-gather, sharded.py)
+// and are replayed here on the other ranks' replicas, so the replicas stay bit-identical.
+// A cell can be touched by several entries of one launch (A leaves it, B enters; or an at-risk
+// agent dies on it and another moves in), always in the order leave/die ... enter, and at most one
+// entry leaves a living agent on it.  Replay therefore runs in two phases: 0 = clears (cells left,
+// cells agents died on), 1 = sets (living agents' words) and everything that commutes.
+__global__ void __launch_bounds__(256)
+ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsigned long long n_entries, int phase) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (phase == 1 && i == 0 && n_entries) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)n_entries));
+    if (i >= n_entries) return;
+    const ShardLogEntry en = entries[i];
+    const uint32_t kind = en.kind_harvest & 255u;
+    if (phase == 0) {
+        if (kind == 2u) return;
+        if (en.old_cell != en.new_cell) w.occw[en.old_cell] = 0u;
+        if (en.new_word == 0u) w.occw[en.new_cell] = 0u;
+        return;
+    }
+    AgentRec* rec = &w.agents[en.slot];
+    if (kind == 2u) {                              // skipped (Q1)
+        w.occw[en.new_cell] = en.new_word;
+        if (en.status) rec->status = en.status;
+        return;
+    }
+    if (en.new_word != 0u) w.occw[en.new_cell] = en.new_word;
+    if (w.cfg.rule_move_eat) { w.sugar[en.new_cell] = 0.0; w.isugar[en.new_cell] = 0; }
+    rec->pos = en.new_cell;
+    if (kind == 0u) { rec->turn = en.turn; return; }
+    // at-risk agent, settled synchronously by its rank: take over the results.  Pollution only grows
+    // during the agent loop (A, B >= 0), so the last writer of a cell holds the largest value and the
+    // bit pattern of a non-negative double orders like an integer.
+    if (w.cfg.rule_pollution)
+        atomicMax((unsigned long long*)&w.poll[en.new_cell], (unsigned long long)__double_as_longlong(en.poll));
+    rec->sugar = en.sugar;
+    rec->attr = en.attr;
+    rec->status = en.status;
+    atomicAdd(&w.acc->sum_metab, (unsigned long long)attr_metab(en.attr));
+    atomicAdd(&w.acc->sum_vision, (unsigned long long)attr_vision(en.attr));
+    atomicAdd(&w.acc->acted, 1ull);
+    if (!attr_alive(en.attr)) atomicAdd(&w.acc->deaths, 1ull);
+    const double sugar = en.sugar;
+    if (sugar == 0.01) atomicAdd(&w.acc->hist_small, 1ull);
+    else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
+    else atomicAdd(&w.acc->inexact, 1ull);
 }
 
 // ------------------------------------------------------------------------------ settle ----
@@ -976,6 +1046,15 @@ size_t ss_pass_smem_bytes(int emax, int ew, int vmax) {
     return (((size_t)emax * emax * 5 + 15) & ~(size_t)15) + sizeof(RegionShared) * PASS_WARPS + (size_t)emax * ew * 4 + 16;
 }
 
+cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int64_t iteration, int64_t env_time,
+                                cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    (void)iteration; (void)env_time;
+    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, 0);
+    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, 1);
+    return cudaGetLastError();
+}
+
 cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_time, cudaStream_t s) {
     if (w.n_slots > 0) ss_settle_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w, iteration, env_time);
     return cudaGetLastError();
@@ -990,7 +1069,8 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    ss_move_pass_kernel<<<g.nwin * g.nwin, PASS_THREADS, smem, s>>>(w, g, iteration, env_time);
+    if (g.bx_cnt <= 0) return cudaSuccess;
+    ss_move_pass_kernel<<<g.nwin * g.bx_cnt, PASS_THREADS, smem, s>>>(w, g, iteration, env_time);
     return cudaGetLastError();
 }
 

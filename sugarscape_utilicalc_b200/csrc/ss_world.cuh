@@ -18,6 +18,15 @@ struct StepAccum {                  // per-step reduction targets of the lattice
     unsigned long long wd_info[3];
 };
 
+// One resolved turn, as shipped to the other ranks' replicas (multi-GPU, see sharded.py)
+struct ShardLogEntry {
+    uint32_t slot, old_cell, new_cell, new_word;
+    double sugar;                   // at-risk agents: sugar after the turn
+    double poll;                    // at-risk agents: pollution of new_cell after the turn
+    uint32_t attr, status, turn;
+    uint32_t kind_harvest;          // bits 0..7 kind (0 safe, 1 at-risk, 2 skipped), bits 8.. harvest
+};
+
 struct DevWorld {
     ss_config cfg;
     int n;                          // lattice edge N
@@ -42,6 +51,9 @@ struct DevWorld {
     uint32_t* hist;                 // SS_GINI_BINS
     int vmax;                       // max vision over all agents
     unsigned long long* dbg;        // optional instrumentation counters (32 entries) or null
+    struct ShardLogEntry* log;      // multi-GPU: turns resolved by this rank (null on a single GPU)
+    unsigned long long* log_count;
+    unsigned long long log_cap;
 };
 
 struct PassGeom {                   // window tiling of one move pass
@@ -51,4 +63,5 @@ struct PassGeom {                   // window tiling of one move pass
     int shift_x, shift_y;           // tiling shift
     int ring;                       // 2*vmax: agents closer than this to a window edge are not resolved
     int align;                      // window boundaries are multiples of this many cells (4: vector loads)
+    int bx_lo, bx_cnt;              // window rows [bx_lo, bx_lo + bx_cnt) of this launch (multi-GPU: this rank's share)
 };

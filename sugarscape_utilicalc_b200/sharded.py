@@ -1,0 +1,298 @@
+"""Multi-GPU timestep: one process per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing.
+
+Decomposition.  Every rank holds a replica of the lattice and the agent store
+(C5 needs 8.3 GB of the 180 GB) and, in every move pass, resolves only the agents of ITS contiguous
+share of the window rows -- windows of one launch are disjoint, so ranks never touch the same cells.
+The turns a rank resolved are appended on the device to a log of 48-byte entries (agent, old cell,
+new cell, new occupancy word, deferred-turn stamp or the synchronously settled state).  After the
+pass the ranks all-gather their log slices and replay the other ranks' entries on their replica
+(`ss_apply_log_kernel`: same stores, same arithmetic -> replicas stay bit-identical).  This is the
+exchange step of the path: what crosses NVLink per step is 48 B per agent (0.8 GB at C5) instead
+of lattice halos; agent migration is implicit in the log.  Growback, settle, statistics and
+diffusion run on every replica (1.3 ms of the 88 ms C5 step).  Passes repeat until the (replicated)
+pending counter is zero.
+
+`VirtualRanks` runs P replicas inside one process on one GPU with the same code path (device
+pointers instead of NCCL) -- the GPU parity test of the N>1 path; the gloo test
+(tests/test_sharded_gloo.py) covers the host-side collective helpers on CPU.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import capi
+from .engine import Engine, EngineError
+from .capi import STATS_DTYPE
+
+ENTRY_BYTES = 48
+
+
+def window_rows_for_rank(nwin, rank, world):
+    """Contiguous share [lo, hi) of the `nwin` window rows (same rule as ss_shard_pass)."""
+    return (rank * nwin) // world, ((rank + 1) * nwin) // world
+
+
+def pad_and_gather(local_bytes, n_local, world, gather_counts, gather_padded):
+    """Variable-length all-gather through two fixed-size collectives.
+    local_bytes: 1-D uint8 tensor with n_local*ENTRY_BYTES valid bytes; returns (counts, list of per-rank
+    uint8 tensors trimmed to their length)."""
+    import torch
+    counts_t = torch.tensor([int(n_local)], dtype=torch.int64, device=local_bytes.device)
+    all_counts = gather_counts(counts_t)                      # (world,) int64
+    counts = [int(c) for c in all_counts.tolist()]
+    mx = max(counts) if counts else 0
+    if mx == 0:
+        return counts, [local_bytes[:0] for _ in range(world)]
+    buf = torch.zeros(mx * ENTRY_BYTES, dtype=torch.uint8, device=local_bytes.device)
+    buf[: n_local * ENTRY_BYTES] = local_bytes[: n_local * ENTRY_BYTES]
+    allb = gather_padded(buf)                                 # (world, mx*ENTRY_BYTES)
+    return counts, [allb[r, : counts[r] * ENTRY_BYTES] for r in range(world)]
+
+
+class _DevView:
+    """Zero-copy torch view of engine device memory (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class ShardRank:
+    """One rank's replica: an Engine plus the shard entry points of the C-ABI."""
+
+    def __init__(self, cfg, rank, world, device=0):
+        self.eng = Engine(cfg, device=device)
+        self.rank, self.world = rank, world
+        self._lib = capi.lib()
+
+    def upload(self, w):
+        self.eng.upload_cells(w["sugar"], w["cap"], w["pollution"])
+        self.eng.upload_agents(w["id"], w["x"], w["y"], w["vision"], w["metab"], w["sugar_agent"])
+        if self.eng.counters()["path"] != 2:
+            raise EngineError("multi-GPU needs the lattice path (keyed RNG, moveEat)")
+        self._check(self._lib.ss_shard_enable(self.eng._h, self.rank, self.world), "ss_shard_enable")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s: %s" % (what, self._lib.ss_last_error(self.eng._h).decode()))
+
+    def begin_step(self):
+        self._check(self._lib.ss_shard_begin_step(self.eng._h), "ss_shard_begin_step")
+
+    def run_pass(self):
+        b, e, base = C.c_uint64(), C.c_uint64(), C.c_void_p()
+        self._check(self._lib.ss_shard_pass(self.eng._h, C.byref(b), C.byref(e), C.byref(base)), "ss_shard_pass")
+        return int(base.value) + b.value * ENTRY_BYTES, int(e.value - b.value)
+
+    def apply(self, dev_ptr, n):
+        self._check(self._lib.ss_shard_apply(self.eng._h, C.c_void_p(int(dev_ptr)), int(n)), "ss_shard_apply")
+
+    def pending(self):
+        p = C.c_uint64()
+        self._check(self._lib.ss_shard_pending(self.eng._h, C.byref(p)), "ss_shard_pending")
+        return int(p.value)
+
+    def end_step(self):
+        out = np.zeros(1, dtype=STATS_DTYPE)
+        self._check(self._lib.ss_shard_end_step(self.eng._h, out.ctypes.data_as(C.c_void_p)), "ss_shard_end_step")
+        return out
+
+    def close(self):
+        self.eng.close()
+
+
+class VirtualRanks:
+    """P replicas in one process on one GPU: the N>1 code path without NCCL (log slices are handed over
+    as device pointers).  Same interface as Engine for the parity tests."""
+
+    def __init__(self, cfg, world, device=0):
+        self.ranks = [ShardRank(cfg, r, world, device) for r in range(world)]
+        self.world = world
+        self.passes = 0
+
+    def upload_cells(self, sugar, cap, pollution=None):
+        self._cells = (sugar, cap, pollution)
+
+    def upload_agents(self, id, x, y, vision, metab, sugar):
+        s, c, p = self._cells
+        for r in self.ranks:
+            r.upload(dict(sugar=s, cap=c, pollution=p, id=id, x=x, y=y, vision=vision, metab=metab, sugar_agent=sugar))
+
+    def step(self, nsteps=1):
+        out = np.zeros(nsteps, dtype=STATS_DTYPE)
+        for t in range(nsteps):
+            for r in self.ranks:
+                r.begin_step()
+            while True:
+                logs = [r.run_pass() for r in self.ranks]
+                self.passes += 1
+                for i, r in enumerate(self.ranks):
+                    for j, (ptr, n) in enumerate(logs):
+                        if j != i:
+                            r.apply(ptr, n)
+                pend = [r.pending() for r in self.ranks]
+                assert len(set(pend)) == 1, "replicas disagree on the pending count: %s" % pend
+                if pend[0] == 0:
+                    break
+                if self.passes > 100000:
+                    raise EngineError("move passes did not converge")
+            stats = [r.end_step() for r in self.ranks]
+            for s in stats[1:]:
+                assert s.tobytes() == stats[0].tobytes(), "replicas disagree on the step statistics"
+            out[t] = stats[0][0]
+        return out
+
+    def download_cells(self):
+        cells = [r.eng.download_cells() for r in self.ranks]
+        for c in cells[1:]:
+            for k in ("sugar", "pollution", "occ"):
+                assert np.array_equal(c[k], cells[0][k]), "replicas diverged in " + k
+        return cells[0]
+
+    def download_agents(self):
+        return self.ranks[0].eng.download_agents()
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
+
+
+class DistributedEngine:
+    """One rank of a torchrun job (backend nccl).  Interface of Engine.step()."""
+
+    def __init__(self, cfg, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = int(os.environ.get("LOCAL_RANK", self.rank)) if device is None else device
+        torch.cuda.set_device(self.device)
+        self.r = ShardRank(cfg, self.rank, self.world, device=self.device)
+        self.passes = 0
+        self.bytes_sent = 0
+
+    def upload(self, w):
+        self.r.upload(w)
+
+    def _gather_counts(self, t):
+        out = self.torch.empty(self.world, dtype=self.torch.int64, device=t.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return out
+
+    def _gather_padded(self, buf):
+        out = self.torch.empty((self.world, buf.numel()), dtype=self.torch.uint8, device=buf.device)
+        self.dist.all_gather_into_tensor(out.view(-1), buf)
+        return out
+
+    def step(self, nsteps=1):
+        torch = self.torch
+        out = np.zeros(nsteps, dtype=STATS_DTYPE)
+        for t in range(nsteps):
+            self.r.begin_step()
+            while True:
+                ptr, n = self.r.run_pass()                   # engine stream is synchronised on return
+                self.passes += 1
+                local = torch.as_tensor(_DevView(ptr, max(n, 1) * ENTRY_BYTES), device="cuda:%d" % self.device)
+                counts, parts = pad_and_gather(local, n, self.world, self._gather_counts, self._gather_padded)
+                torch.cuda.current_stream().synchronize()    # NCCL results before the engine's stream reads them
+                self.bytes_sent += n * ENTRY_BYTES
+                for j in range(self.world):
+                    if j != self.rank and counts[j]:
+                        self.r.apply(parts[j].data_ptr(), counts[j])
+                if self.r.pending() == 0:
+                    break
+            out[t] = self.r.end_step()[0]
+        return out
+
+    def close(self):
+        self.r.close()
+
+
+# ------------------------------------------------------------------------------ bench ----
+def bench_main(args, wl):
+    """`torchrun ... bench.py --gpus N`: strong scaling of the same workload over N replicas."""
+    import torch
+    import torch.distributed as dist
+    from . import config_from_settings, synthetic
+    dist.init_process_group(backend="nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    t0 = time.time()
+    w = synthetic.tiled_world(wl["n"])
+    settings = synthetic.synthetic_settings(wl["n"], pollution=wl["pollution"])
+    cfg = config_from_settings(settings, rng_mode="keyed")
+    if rank == 0:
+        sys.stderr.write("[bench] world %d^2 generated in %.1fs on every rank\n" % (wl["n"], time.time() - t0))
+    K, W = args.steps, args.warmup
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    de = DistributedEngine(cfg, device=local)
+    de.upload(w)
+    pop0 = len(w["id"])
+    if W:
+        pop0 = int(de.step(W)["population"][-1])
+    sync_all()
+    from .clocks import ClockSampler
+    p0, l0, b0 = de.passes, de.r.eng.counters()["launches"], de.bytes_sent
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t1 = time.perf_counter()
+    st = de.step(K)
+    sync_all()
+    wall = time.perf_counter() - t1
+    clocks = sampler.stop() if rank == 0 else None
+    wallt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(wallt, op=dist.ReduceOp.MAX)
+    # the engine runs on its own stream, so the torch-stream events only bracket the collectives:
+    # the step time is the max over ranks of the host wall clock between the two barriers
+    step_ms = 1e3 * float(wallt.item()) / K
+    pops = np.concatenate([[pop0], st["population"][:-1]])
+    value = float(pops.sum()) / (step_ms * K * 1e-3)
+    # e2e: upload on every rank + K steps + download on rank 0
+    sync_all()
+    t2 = time.perf_counter()
+    de2 = DistributedEngine(cfg, device=local)
+    de2.upload(w)
+    Ke = min(K, args.e2e_steps)
+    ste = de2.step(Ke)
+    if rank == 0:
+        de2.r.eng.download_cells(cap=False)
+        de2.r.eng.download_agents()
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t2], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
+    n = wl["n"]
+    if rank == 0:
+        line = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl["label"], "grid": n, "agents": len(w["id"]),
+                       "parallelism": "replicated lattice, window rows sharded over %d ranks, turn logs all-gathered (NCCL)" % world,
+                       "timing": "max over ranks of the wall clock between two barrier+synchronize pairs around K steps",
+                       "l2": "working set >> 126 MB L2"},
+            "cell_updates_per_s": n * n * K / (step_ms * K * 1e-3),
+            "population": [int(pop0), int(st["population"][-1])],
+            "passes_per_step": (de.passes - p0) / K, "gpu_launches": de.r.eng.counters()["launches"] - l0,
+            "nccl_bytes_sent_per_rank_per_step": (de.bytes_sent - b0) / K,
+            "e2e": {"value": float(popse.sum()) / float(e2e_s.item()), "unit": "agent-steps/s",
+                    "h2d_bytes_per_step": (3 * 8 * n * n + 4 * n * n + 32 * len(w["id"])) / Ke,
+                    "d2h_bytes_per_step": ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke, "steps": Ke,
+                    "what": "per rank: Engine + upload from host numpy; K sharded steps; rank 0 downloads cells+agents"},
+            "roofline": None, "cpu_baseline": None,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    de.close()
+    de2.close()
+    dist.destroy_process_group()

@@ -151,3 +151,28 @@ def test_empty_population_and_extinction():
                             np.full(40, 3.0))
         common.compare_worlds(e, o, 14, what="extinction path %d" % path)
         assert e.agent_count() == len(o.download_agents()["id"]) == 0
+
+
+@pytest.mark.parametrize("world,n,pollution", [(2, 300, True), (3, 512, False), (4, 130, True)])
+def test_multi_gpu_replicas_equal_single_gpu_and_oracle(world, n, pollution):
+    """The N>1 code path (window rows sharded over replicas, turn logs replayed) on one GPU with
+    virtual ranks: replicas stay identical to each other and to the CPU oracle."""
+    from sugarscape_utilicalc_b200.sharded import VirtualRanks
+    s, init = common.synthetic_case(n, pollution)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    v, o = VirtualRanks(cfg, world), common.oracle_world(cfg)
+    common.init_world(v, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(v, o, 6, what="virtual ranks %d" % world)
+    v.close()
+    o.close()
+
+
+def test_multi_gpu_replicas_on_reference_golden():
+    from sugarscape_utilicalc_b200.sharded import VirtualRanks
+    g = common.load_golden("c2_pollution0_keyed")
+    cfg = config_from_settings(g["settings"], rng_mode="keyed")
+    v = VirtualRanks(cfg, 2)
+    common.init_world(v, common.golden_init(g), "keyed")
+    common.run_against_golden(g, v, exact_gini=False, max_steps=50)
+    v.close()
