@@ -147,3 +147,5 @@ __device__ inline double ss_py_floordiv(double vx, double wx) {
     return fl;
 }
 __device__ inline int ss_wrap(int v, int n) { int r = v % n; return r < 0 ? r + n : r; }
+// same for v in [-n, 2n): no integer division
+__device__ inline int ss_wrap1(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }

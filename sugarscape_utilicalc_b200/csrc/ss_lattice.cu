@@ -81,8 +81,8 @@ struct WinCtx {
     bool full_x, full_y;  // window spans the whole torus in that dimension (wrap inside)
     int n;
 };
-__device__ static inline int wrap_row(const WinCtx& c, int r) { return c.full_x ? ss_wrap(r, c.ex) : r; }
-__device__ static inline int wrap_col(const WinCtx& c, int q) { return c.full_y ? ss_wrap(q, c.ey) : q; }
+__device__ static inline int wrap_row(const WinCtx& c, int r) { return c.full_x ? ss_wrap1(r, c.ex) : r; }
+__device__ static inline int wrap_col(const WinCtx& c, int q) { return c.full_y ? ss_wrap1(q, c.ey) : q; }
 __device__ static inline bool in_core(const WinCtx& c, int r, int q, int R) {
     return (c.full_x || (r >= R && r < c.ex - R)) && (c.full_y || (q >= R && q < c.ey - R));
 }
@@ -122,8 +122,8 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const WinCtx& c, in
         if (h * 32 < K) {
             if (k < K) {
                 int r, q, cx, cy;
-                if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap(gx + o, n); cy = gy; }
-                else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap(gy + o, n); }
+                if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap1(gx + o, n); cy = gy; }
+                else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap1(gy + o, n); }
                 const int li = r * c.emax + q;
                 if (c.occ_s[li] == 0u) {
                     fr = true;
@@ -208,7 +208,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
                                        ThreadStats& ts, int lane) {
     const int n = c.n;
     const int a = occ_vision(ow);
-    const int gx = ss_wrap(c.gx0 + lx, n), gy = ss_wrap(c.gy0 + ly, n);
+    const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
     const int pos = gx * n + gy;
     const bool risky = (ow & OCC_RISK) != 0;
     AgentRec* recp = &w.agents[slot];
@@ -221,7 +221,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
     if (lane != 0) return;
     const int li_old = lx * c.emax + ly, li_new = ch.lr * c.emax + ch.lq;
     const int cell = (ch.lr == lx && ch.lq == ly) ? pos
-                   : ss_wrap(c.gx0 + ch.lr, n) * n + ss_wrap(c.gy0 + ch.lq, n);
+                   : ss_wrap1(c.gx0 + ch.lr, n) * n + ss_wrap1(c.gy0 + ch.lq, n);
     uint32_t new_word = occ_pack(slot, a, next_phase);
     ts.resolved++;
     if (!risky) {
@@ -352,7 +352,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 const int idx = base + u * PASS_THREADS + tid;
                 if (idx < total) {
                     const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
-                    const size_t gi = (size_t)ss_wrap(c.gx0 + lx, n) * n + ss_wrap(c.gy0 + ly, n);
+                    const size_t gi = (size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n);
                     ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + gi));
                     sv[u] = __ldcg(reinterpret_cast<const uchar4*>(w.isugar + gi));
                 }
@@ -372,7 +372,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     } else {
         for (int idx = tid; idx < c.ex * c.ey; idx += PASS_THREADS) {
             const int lx = idx / c.ey, ly = idx - lx * c.ey;
-            const size_t gi = (size_t)ss_wrap(c.gx0 + lx, n) * n + ss_wrap(c.gy0 + ly, n);
+            const size_t gi = (size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n);
             c.occ_s[lx * c.emax + ly] = __ldcg(&w.occw[gi]);
             c.isug_s[lx * c.emax + ly] = __ldcg(&w.isugar[gi]);
         }
@@ -391,10 +391,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     auto rg_of_y = [&](int y) { int r = (y * PASS_RGY) / c.ey; while (r > 0 && (r * c.ey) / PASS_RGY > y) r--; while (r + 1 < PASS_RGY && ((r + 1) * c.ey) / PASS_RGY <= y) r++; return r; };
     auto rg_x0 = [&](int ix) { return (ix * c.ex) / PASS_RGX; };
     auto rg_y0 = [&](int iy) { return (iy * c.ey) / PASS_RGY; };
-    for (int idx = tid; idx < c.ex * c.ey; idx += PASS_THREADS) {
-        const int lx = idx / c.ey, ly = idx - lx * c.ey;
-        const uint32_t ow = c.occ_s[lx * c.emax + ly];
-        if (ow == 0u || (ow >> 31) != cur_phase) continue;
+    auto enlist = [&](int lx, int ly, uint32_t ow) {
         const uint32_t p = ss_priority(ok, occ_slot(ow));
         const int ix = rg_of_x(lx), iy = rg_of_y(ly);
         RegionShared& rg = regs[iy * PASS_RGX + ix];
@@ -405,6 +402,23 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             atomicMin((uint32_t*)&rg.bfront[b], p);
         } else {                                            // ring agents belong to a later launch
             atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+        }
+    };
+    if (g.align == 4 && (c.emax & 3) == 0) {                // four cells per 128-bit shared-memory load
+        const int gpr = c.ey >> 2, total = c.ex * gpr;
+        for (int idx = tid; idx < total; idx += PASS_THREADS) {
+            const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
+            const uint4 o4 = *reinterpret_cast<const uint4*>(c.occ_s + lx * c.emax + ly);
+            if (o4.x != 0u && (o4.x >> 31) == cur_phase) enlist(lx, ly, o4.x);
+            if (o4.y != 0u && (o4.y >> 31) == cur_phase) enlist(lx, ly + 1, o4.y);
+            if (o4.z != 0u && (o4.z >> 31) == cur_phase) enlist(lx, ly + 2, o4.z);
+            if (o4.w != 0u && (o4.w >> 31) == cur_phase) enlist(lx, ly + 3, o4.w);
+        }
+    } else {
+        for (int idx = tid; idx < c.ex * c.ey; idx += PASS_THREADS) {
+            const int lx = idx / c.ey, ly = idx - lx * c.ey;
+            const uint32_t ow = c.occ_s[lx * c.emax + ly];
+            if (ow != 0u && (ow >> 31) == cur_phase) enlist(lx, ly, ow);
         }
     }
     __syncthreads();
@@ -486,16 +500,24 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             const int ax0 = lx - a - V, ax1 = lx + a + V, ay0 = ly - a - V, ay1 = ly + a + V;
             const bool torus = c.full_x || c.full_y;
             int stuck = 0;
-            for (int y = 0; y < PASS_WARPS; y++) {
-                if (y == warp) continue;
+            // lane y < PASS_WARPS tests region y; then only the touched regions are visited
+            unsigned touched;
+            {
+                bool touch = false;
+                if (lane < PASS_WARPS && lane != warp) {
+                    const int yx0 = rg_x0(lane % PASS_RGX), yx1 = rg_x0(lane % PASS_RGX + 1) - 1;
+                    const int yy0 = rg_y0(lane / PASS_RGX), yy1 = rg_y0(lane / PASS_RGX + 1) - 1;
+                    touch = torus || (zx0 <= yx1 && zx1 >= yx0 && zy0 <= yy1 && zy1 >= yy0) ||
+                            (ax0 <= yx1 && ax1 >= yx0 && ly >= yy0 && ly <= yy1) ||
+                            (lx >= yx0 && lx <= yx1 && ay0 <= yy1 && ay1 >= yy0);
+                }
+                touched = __ballot_sync(FULL, touch);
+            }
+            while (touched) {
+                const int y = __ffs(touched) - 1;
+                touched &= touched - 1;
                 const int yx0 = rg_x0(y % PASS_RGX), yx1 = rg_x0(y % PASS_RGX + 1) - 1;
                 const int yy0 = rg_y0(y / PASS_RGX), yy1 = rg_y0(y / PASS_RGX + 1) - 1;
-                bool touch;
-                if (torus) touch = true;               // torus inside the window: stay conservative
-                else touch = (zx0 <= yx1 && zx1 >= yx0 && zy0 <= yy1 && zy1 >= yy0) ||
-                             (ax0 <= yx1 && ax1 >= yx0 && ly >= yy0 && ly <= yy1) ||
-                             (lx >= yx0 && lx <= yx1 && ay0 <= yy1 && ay1 >= yy0);
-                if (!touch) continue;
                 reach |= 1u << y;
                 // lane = block of region y
                 const int bxl = yx0 + ((lane / PASS_BCOLS) << 4), byl = yy0 + ((lane % PASS_BCOLS) << 4);
@@ -557,7 +579,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 } else {
                     for (int i = 0; i < len; i++) {
                         int cc = c0 + i;
-                        if (c.full_y) cc = ss_wrap(cc, c.ey); else if (cc < 0 || cc >= c.ey) continue;
+                        if (c.full_y) cc = ss_wrap1(cc, c.ey); else if (cc < 0 || cc >= c.ey) continue;
                         out |= ((((const volatile uint32_t*)blk_bits)[r * ew + (cc >> 5)] >> (cc & 31)) & 1u) << i;
                     }
                 }
@@ -606,7 +628,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 if (lane == 0) {      // loses its turn: stays put, no metabolism (Q1)
                     const uint32_t nw = occ_pack(slot, a, next_phase);
                     c.occ_s[lx * c.emax + ly] = nw;
-                    const int gx = ss_wrap(c.gx0 + lx, n), gy = ss_wrap(c.gy0 + ly, n);
+                    const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
                     w.occw[(size_t)gx * n + gy] = nw;
                     if (ow & OCC_RISK)
                         *((volatile uint32_t*)&w.agents[slot].status) = ((uint32_t)(iteration + 1) << 2) | ST_SKIPPED;
