@@ -25,6 +25,9 @@
 
 #define FULL 0xffffffffu
 #define PASS_THREADS 256
+#ifndef PASS_MIN_CTAS
+#define PASS_MIN_CTAS 2
+#endif
 #define PASS_WARPS (PASS_THREADS / 32)
 #define PASS_RGX 2                      // regions per window: PASS_RGX x PASS_RGY == PASS_WARPS
 #define PASS_RGY 4
@@ -314,7 +317,7 @@ struct PassShared {
     int count[PASS_WARPS];
 };
 
-__global__ void __launch_bounds__(PASS_THREADS, 2)
+__global__ void __launch_bounds__(PASS_THREADS, PASS_MIN_CTAS)
 ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ PassShared sh;
@@ -933,10 +936,10 @@ ss_seasons_kernel(DevWorld w, double alpha_north, double alpha_south) {
 // and written back coalesced; bands are chained through global progress flags (band b+1
 // needs the new last row of band b).  Bands take tickets in launch order, so a waiting
 // band only ever waits on a band that is already running.
-#define DIFF_RING 96
+#define DIFF_RING 128                    // columns held per row (power of two): chunks j-1, j, j+1 (+ spare)
 // x / 3.0, correctly rounded, without the long DDIV sequence on the wavefront's critical
 // path: q = RN(x*r), one FMA residual correction (Markstein); exact IEEE division outside the
-// comfortably-normal range.  Checked against x / 3.0 on the CPU (tests/test_div3.py).
+// comfortably-normal range.  Checked against x / 3.0 on the CPU (tests/ctests/div3_check.c).
 __device__ static inline double div3(double x) {
     const double ax = fabs(x);
     if (!(ax > 1e-280 && ax < 1e280)) return x / 3.0;
@@ -953,6 +956,13 @@ __device__ static inline int ld_acquire(const int* p) {
 __device__ static inline void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ static inline void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ static inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ static inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 __global__ void __launch_bounds__(32)
 ss_diffuse_kernel(double* __restrict__ p, int n, int* ticket, int* progress) {
@@ -966,18 +976,18 @@ ss_diffuse_kernel(double* __restrict__ p, int n, int* ticket, int* progress) {
     const int r = x0 + lane;
     const bool row_ok = lane < rows;
     const bool has_above = x0 > 0, has_below = x0 + 32 < n;
+    const bool has_e = r + 1 < n, has_w = r >= 1;
     const int nchunks = (n + 31) / 32;
     const int nblocks = (n + 31 + 31) / 32;          // iterations 0 .. n+30
-    auto load_chunk = [&](int ch, bool with_above) { // columns [32ch, 32ch+32)
+    // asynchronous chunk load (cp.async, no register staging): columns [32ch, 32ch+32) of my rows + the row below
+    auto load_chunk = [&](int ch) {
         const int col = 32 * ch + lane;
-        if (ch >= nchunks || col >= n) return;
-        const int slot = col % DIFF_RING;
-#pragma unroll 8
-        for (int rr = 1; rr <= 33; rr++) {
-            const int gr = x0 - 1 + rr;
-            if (rr <= rows || (rr == 33 && has_below)) tile[rr][slot] = __ldcg(&p[(size_t)gr * n + col]);
+        if (ch < nchunks && col < n) {
+            const int slot = col & (DIFF_RING - 1);
+            for (int rr = 1; rr <= rows; rr++) cp_async8(&tile[rr][slot], &p[(size_t)(x0 - 1 + rr) * n + col]);
+            if (has_below) cp_async8(&tile[33][slot], &p[(size_t)(x0 + 32) * n + col]);
         }
-        (void)with_above;
+        cp_async_commit();
     };
     auto load_above = [&](int ch) {
         const int col = 32 * ch + lane;
@@ -985,50 +995,70 @@ ss_diffuse_kernel(double* __restrict__ p, int n, int* ticket, int* progress) {
         const int need = min(n, 32 * (ch + 1));
         if (lane == 0) while (ld_acquire(&progress[b - 1]) < need) { }
         __syncwarp();
-        if (col < n) tile[0][col % DIFF_RING] = __ldcg(&p[(size_t)(x0 - 1) * n + col]);
+        if (col < n) tile[0][col & (DIFF_RING - 1)] = __ldcg(&p[(size_t)(x0 - 1) * n + col]);
     };
     auto flush_chunk = [&](int ch) {
         if (ch < 0 || ch >= nchunks) return;
         const int col = 32 * ch + lane;
         if (col < n) {
-            const int slot = col % DIFF_RING;
+            const int slot = col & (DIFF_RING - 1);
             for (int rr = 1; rr <= rows; rr++) p[(size_t)(x0 - 1 + rr) * n + col] = tile[rr][slot];
         }
         __threadfence();
         __syncwarp();
         if (lane == 0) st_release(&progress[b], min(n, 32 * (ch + 1)));
     };
-    load_chunk(0, false);
-    load_chunk(1, false);
+    load_chunk(0);
+    load_chunk(1);
     double res_prev = 0.0;
     for (int j = 0; j < nblocks; j++) {
-        if (j >= 1) load_chunk(j + 1, false);
+        load_chunk(j + 2);                      // chunk j+2 lands while blocks j, j+1 compute
+        cp_async_wait<1>();                     // chunks <= j+1 have landed
         load_above(j);
         __syncwarp();
-        for (int k = 32 * j; k < 32 * j + 32; k++) {
-            const int y = k - lane;
-            const bool act = row_ok && y >= 0 && y < n;
-            const bool has_n = row_ok && (y + 1 >= 0) && (y + 1 < n);
-            const double n_val = has_n ? tile[lane + 1][(y + 1) % DIFF_RING] : 0.0;
-            double e_val = __shfl_down_sync(FULL, n_val, 1);
-            if (lane == 31 && act && has_below) e_val = tile[33][y % DIFF_RING];
-            double w_val = __shfl_up_sync(FULL, res_prev, 1);
-            if (lane == 0 && act && has_above) w_val = tile[0][y % DIFF_RING];
-            if (act) {
-                double t = 0.0;
-                int cnt = 0;
-                if (y + 1 < n) { t += n_val; cnt++; }
-                if (y - 1 >= 0) { t += res_prev; cnt++; }
-                if (r + 1 < n) { t += e_val; cnt++; }
-                if (r - 1 >= 0) { t += w_val; cnt++; }
-                const double res = cnt == 4 ? t * 0.25 : (cnt == 2 ? t * 0.5 : div3(t));
-                tile[lane + 1][y % DIFF_RING] = res;
+        const int k0 = 32 * j;
+        const bool interior = row_ok && rows == 32 && has_above && has_below && (k0 - 31 >= 1) && (k0 + 32 < n);
+        if (__all_sync(FULL, interior)) {
+            // every lane has all four neighbours: ((n + s) + e) + w, times 0.25
+#pragma unroll 4
+            for (int k = k0; k < k0 + 32; k++) {
+                const int y = k - lane;
+                const double n_val = tile[lane + 1][(y + 1) & (DIFF_RING - 1)];
+                double e_val = __shfl_down_sync(FULL, n_val, 1);
+                double w_val = __shfl_up_sync(FULL, res_prev, 1);
+                if (lane == 31) e_val = tile[33][y & (DIFF_RING - 1)];
+                if (lane == 0) w_val = tile[0][y & (DIFF_RING - 1)];
+                const double res = (((n_val + res_prev) + e_val) + w_val) * 0.25;
+                tile[lane + 1][y & (DIFF_RING - 1)] = res;
                 res_prev = res;
+            }
+        } else {
+            for (int k = k0; k < k0 + 32; k++) {
+                const int y = k - lane;
+                const bool act = row_ok && y >= 0 && y < n;
+                const bool has_n = y + 1 < n, has_s = y >= 1;
+                const double n_val = (row_ok && y + 1 >= 0 && has_n) ? tile[lane + 1][(y + 1) & (DIFF_RING - 1)] : 0.0;
+                double e_val = __shfl_down_sync(FULL, n_val, 1);
+                double w_val = __shfl_up_sync(FULL, res_prev, 1);
+                if (lane == 31 && act && has_below) e_val = tile[33][y & (DIFF_RING - 1)];
+                if (lane == 0 && act && has_above) w_val = tile[0][y & (DIFF_RING - 1)];
+                if (act) {
+                    double t = 0.0;
+                    int cnt = 0;
+                    if (has_n) { t += n_val; cnt++; }
+                    if (has_s) { t += res_prev; cnt++; }
+                    if (has_e) { t += e_val; cnt++; }
+                    if (has_w) { t += w_val; cnt++; }
+                    const double res = cnt == 4 ? t * 0.25 : (cnt == 2 ? t * 0.5 : div3(t));
+                    tile[lane + 1][y & (DIFF_RING - 1)] = res;
+                    res_prev = res;
+                }
             }
         }
         __syncwarp();
         flush_chunk(j - 1);
     }
+    cp_async_wait<0>();
     flush_chunk(nblocks - 1);
     __syncwarp();
     if (lane == 0) st_release(&progress[b], n);
