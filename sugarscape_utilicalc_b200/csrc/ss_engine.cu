@@ -48,6 +48,7 @@ struct ss_engine {
     int sm_count = 148;
     int diffuse_impl = 0;
     int window_max = 128;
+    int use_pendmap = 1;
     int trace = 0;
     bool cap_fits_u8 = true;
     unsigned long long* h_pending = nullptr;   // pinned
@@ -149,6 +150,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.sugar); cudaFree(e->w.cap); cudaFree(e->w.poll); cudaFree(e->w.occw); cudaFree(e->w.isugar);
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
+    cudaFree(e->w.pendmap);
     cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->w.log); cudaFree(e->w.log_count);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -230,6 +232,10 @@ static int choose_path(ss_engine* e) {
         return set_err(e, SS_ERR_UNSUPPORTED, "serial path limited to 4M agents");
     e->geom = g;
     e->path = path;
+    if (path == PATH_LATTICE && g.nwin > 1 && n % 32 == 0 && !e->w.pendmap) {
+        e->w.pend_nb = n / 32;
+        if (cudaMalloc(&e->w.pendmap, sizeof(uint32_t) * 2 * (size_t)e->w.pend_nb * e->w.pend_nb) != cudaSuccess) e->w.pendmap = nullptr;
+    }
     return SS_OK;
 }
 
@@ -370,6 +376,7 @@ static void pass_geometry(ss_engine* e, int p, PassGeom* out) {
         g.shift_x = g.shift_y = 0;
     }
     g.bx_lo = 0; g.bx_cnt = g.nwin;
+    g.map_read = g.map_write = -1;
     *out = g;
 }
 
@@ -387,6 +394,12 @@ static int lattice_step(ss_engine* e, int stats_index) {
         for (;;) {
             PassGeom g;
             pass_geometry(e, p, &g);
+            if (e->w.pendmap && e->use_pendmap) {
+                g.map_write = p & 1;
+                g.map_read = p > 0 ? ((p - 1) & 1) : -1;
+                CK(cudaMemsetAsync(e->w.pendmap + (size_t)g.map_write * e->w.pend_nb * e->w.pend_nb, 0,
+                                   sizeof(uint32_t) * (size_t)e->w.pend_nb * e->w.pend_nb, e->stream));
+            }
             CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
             e->launches++; e->passes++; p++;
             if (p >= first_check || e->trace) {
@@ -579,6 +592,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
         if (!value && e->w.dbg) { cudaFree(e->w.dbg); e->w.dbg = nullptr; }
         return SS_OK;
     }
+    if (k == "pendmap") { e->use_pendmap = (int)value; return SS_OK; }
     if (k == "trace") { e->trace = (int)value; return SS_OK; }
     if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);

@@ -314,6 +314,7 @@ struct RegionShared {
 struct PassShared {
     unsigned red[PASS_WARPS];
     int go;
+    int dirty;
     int count[PASS_WARPS];
 };
 
@@ -341,6 +342,53 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     uint32_t* blk_bits = (uint32_t*)(regs + PASS_WARPS);     // [emax][ew]: pending agents this launch cannot resolve
     const int ew = g.ew;
     const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
+    // ---- coarse pending map: a window whose core holds no agent left over by the previous launch
+    //      hands the map entries of its blocks on and leaves without staging anything ----
+    const int nb = w.pend_nb;
+    if (g.map_read >= 0) {
+        const uint32_t* mr = w.pendmap + (size_t)g.map_read * nb * nb;
+        const int cx0 = (c.gx0 + R) >> 5, cx1 = (c.gx0 + c.ex - R - 1) >> 5;      // blocks overlapping the core
+        const int cy0 = (c.gy0 + R) >> 5, cy1 = (c.gy0 + c.ey - R - 1) >> 5;
+        const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
+        int any = 0;
+        for (int i = tid; i < ncx * ncy; i += PASS_THREADS)
+            any |= mr[((cx0 + i / ncy) % nb) * nb + ((cy0 + i % ncy) % nb)] != 0u;
+        if (!__syncthreads_or(any)) {
+            if (g.map_write >= 0) {
+                uint32_t* mw = w.pendmap + (size_t)g.map_write * nb * nb;
+                const int wx0 = c.gx0 >> 5, wx1 = (c.gx0 + c.ex - 1) >> 5, wy0 = c.gy0 >> 5, wy1 = (c.gy0 + c.ey - 1) >> 5;
+                const int nwx = wx1 - wx0 + 1, nwy = wy1 - wy0 + 1;
+                for (int i = tid; i < nwx * nwy; i += PASS_THREADS) {
+                    const int bi = ((wx0 + i / nwy) % nb) * nb + ((wy0 + i % nwy) % nb);
+                    const uint32_t v = mr[bi];
+                    if (v) atomicAdd(&mw[bi], v);
+                }
+            }
+            return;
+        }
+    }
+    if (tid == 0) sh.dirty = 0;
+    // what this launch leaves pending (ring + blocked agents; everything if a region's list was trimmed)
+    auto write_map = [&]() {
+        if (g.map_write < 0) return;
+        uint32_t* mw = w.pendmap + (size_t)g.map_write * nb * nb;
+        if (sh.dirty) {
+            const int wx0 = c.gx0 >> 5, wx1 = (c.gx0 + c.ex - 1) >> 5, wy0 = c.gy0 >> 5, wy1 = (c.gy0 + c.ey - 1) >> 5;
+            const int nwx = wx1 - wx0 + 1, nwy = wy1 - wy0 + 1;
+            for (int i = tid; i < nwx * nwy; i += PASS_THREADS)
+                atomicAdd(&mw[((wx0 + i / nwy) % nb) * nb + ((wy0 + i % nwy) % nb)], 1u);
+            return;
+        }
+        for (int wi = tid; wi < c.ex * ew; wi += PASS_THREADS) {
+            const uint32_t bits = blk_bits[wi];
+            if (bits == 0u) continue;
+            const int lx = wi / ew, ly0 = (wi - lx * ew) << 5;
+            const int bxi = (ss_wrap1(c.gx0 + lx, n) >> 5) * nb;
+            const int ya = ss_wrap1(c.gy0 + ly0, n) >> 5, yb = ss_wrap1(c.gy0 + min(ly0 + 31, c.ey - 1), n) >> 5;
+            atomicAdd(&mw[bxi + ya], 1u);
+            if (yb != ya) atomicAdd(&mw[bxi + yb], 1u);
+        }
+    };
     const long long t_start = clock64();
     long long t_wait = 0, t_turn = 0, t_m;
     int n_turns = 0, n_blocked_me = 0;
@@ -465,6 +513,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         }
         thr = lo;
         n_mine = fill(thr);
+        if (lane == 0) sh.dirty = 1;
         __syncwarp();
     }
     uint64_t keys[PASS_KPL];
@@ -476,7 +525,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     // a window without a single resolvable agent leaves right away
     if (lane == 0 && n_mine > 0) atomicAdd(&sh.count[0], 1);
     __syncthreads();
-    if (sh.count[0] == 0) return;
+    if (sh.count[0] == 0) { write_map(); return; }
     const long long t_listed = clock64();
     ThreadStats ts = {0, 0, 0, 0, 0, 0, 0};
     // ---- the region's agents in ascending priority ----
@@ -674,6 +723,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     }
     if (lane == 0) { __threadfence_block(); me.done = 1; }
     __syncthreads();
+    write_map();
     if (w.dbg) {
         if (lane == 0) {
             atomicAdd(&w.dbg[9], (unsigned long long)n_turns);

@@ -51,6 +51,8 @@ struct DevWorld {
     uint32_t* hist;                 // SS_GINI_BINS
     int vmax;                       // max vision over all agents
     unsigned long long* dbg;        // optional instrumentation counters (32 entries) or null
+    uint32_t* pendmap;              // 2 x pend_nb^2 counters: agents a launch left pending, per 32x32-cell block
+    int pend_nb;
     struct ShardLogEntry* log;      // multi-GPU: turns resolved by this rank (null on a single GPU)
     unsigned long long* log_count;
     unsigned long long log_cap;
@@ -64,4 +66,5 @@ struct PassGeom {                   // window tiling of one move pass
     int ring;                       // 2*vmax: agents closer than this to a window edge are not resolved
     int align;                      // window boundaries are multiples of this many cells (4: vector loads)
     int bx_lo, bx_cnt;              // window rows [bx_lo, bx_lo + bx_cnt) of this launch (multi-GPU: this rank's share)
+    int map_read, map_write;        // coarse pending maps (32x32-cell blocks) of the previous / this launch, -1 = unused
 };
