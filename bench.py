@@ -53,6 +53,8 @@ def workload(name):
     if name == "c4":
         return dict(n=4096, pollution=True, label="c4: 4096x4096 tiled landscape, 1048576 agents, "
                     "grow+moveEat+canStarve+pollution(A=B=1, diffusion every step), vision 1-6, keyed RNG seed 18")
+    if name.startswith("preset:"):
+        return dict(preset=name.split(":", 1)[1], n=50, pollution=False, label="shipped preset " + name.split(":", 1)[1])
     n = int(name)
     return dict(n=n, pollution=False, label="synthetic %dx%d tiled landscape, %d agents, grow+moveEat+canStarve"
                 % (n, n, n * n // 16))
@@ -232,6 +234,35 @@ def run_engine_single(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def run_preset(args, wl):
+    """Shipped 50x50 presets through the serial MT-exact kernel, from the golden vectors' initial state
+    (tests/golden/<name>.npz, recorded from the unmodified reference): agent-steps/s over the golden run."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    from sugarscape_utilicalc_b200.engine import Engine
+    g = common.load_golden(wl["preset"])
+    cfg = config_from_settings(g["settings"], rng_mode=g["rng"])
+    T = g["steps"]
+    best = None
+    for rep in range(max(1, args.warmup) + 1):
+        eng = Engine(cfg)
+        common.init_world(eng, common.golden_init(g), g["rng"], g["init_mt"], int(g["init_mt_index"]))
+        st = eng.step(T)
+        ms = eng.kernel_times()["last_call"]
+        ok = bool(np.array_equal(st["population"], g["population"]) and np.array_equal(st["gini"], g["gini"]))
+        eng.close()
+        best = ms if best is None else min(best, ms)
+    pops = np.concatenate([[len(g["init_order"])], g["population"][:-1]])
+    line = {"metric": "agent-steps/sec", "value": float(pops.sum()) / (best * 1e-3), "unit": "agent-steps/s", "n_gpus": 1,
+            "steps": T, "warmup": args.warmup, "ms_per_step": best / T, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "reference preset (golden initial state)",
+            "config": {"workload": wl["label"], "rng": g["rng"], "kernel": "ss_serial_kernel, %d steps in one launch" % T,
+                       "timing": "CUDA events on the engine stream"},
+            "matches_reference_series": ok, "gpu_launches": 1,
+            "reference_python_loop": "BASELINE.md section 2 (measured in the build container): 4.7k-36k agent-steps/s"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,6 +274,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = workload(args.workload)
+    if "preset" in wl:
+        run_preset(args, wl)
+        return
     if args.impl == "reference":
         run_reference(args, wl)
         return
