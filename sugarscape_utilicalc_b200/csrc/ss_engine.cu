@@ -610,7 +610,7 @@ extern "C" int ss_shard_enable(ss_engine* e, int32_t rank, int32_t world) {
     CK(cudaSetDevice(e->device));
     e->shard_rank = rank; e->shard_world = world;
     if (!e->w.log) {
-        e->w.log_cap = e->w.n_slots;
+        e->w.log_cap = 8ull * e->w.n_slots + 4096;     // warps reserve 8 entries at a time: <= 7 unused per valid one
         CK(cudaMalloc(&e->w.log, sizeof(ShardLogEntry) * (size_t)e->w.log_cap));
         CK(cudaMalloc(&e->w.log_count, sizeof(unsigned long long)));
     }

@@ -25,6 +25,12 @@
 
 #define FULL 0xffffffffu
 #define PASS_THREADS 256
+// PASS_CLOCK() instrumentation of the move pass (tools/dbg_pass.py, option "debug"): compile with -DSS_PASS_TIMING
+#ifdef SS_PASS_TIMING
+#define PASS_CLOCK() clock64()
+#else
+#define PASS_CLOCK() 0ll
+#endif
 #ifndef PASS_MIN_CTAS
 #define PASS_MIN_CTAS 2
 #endif
@@ -97,7 +103,16 @@ __device__ static inline bool crosses_meet(int dx, int dy, int a, int b) {
            (dx == 0 && ady <= a + b);
 }
 
-struct ThreadStats { unsigned sum_m, sum_v, acted, deaths, resolved, small, inexact; };
+struct ThreadStats {
+    unsigned sum_m, sum_v, acted, deaths, resolved, small, inexact;
+    unsigned long long log_pos, log_end;      // multi-GPU: this warp's reserved slice of the turn log
+};
+#define LOG_CHUNK 8
+// next free entry of the rank's turn log: one global atomic per LOG_CHUNK entries of a warp
+__device__ static inline ShardLogEntry* log_slot(const DevWorld& w, ThreadStats& ts) {
+    if (ts.log_pos == ts.log_end) { ts.log_pos = atomicAdd(w.log_count, (unsigned long long)LOG_CHUNK); ts.log_end = ts.log_pos + LOG_CHUNK; }
+    return &w.log[ts.log_pos++];
+}
 
 struct Choice { int lr, lq, sg; };
 
@@ -243,7 +258,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
             ShardLogEntry en;
             en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
             en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.status = 0u; en.turn = recp->turn; en.kind_harvest = 0u | ((uint32_t)ch.sg << 8);
-            w.log[atomicAdd(w.log_count, 1ull)] = en;
+            *log_slot(w, ts) = en;
         }
         return;
     }
@@ -283,7 +298,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
         en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
         en.sugar = sugar; en.poll = w.cfg.rule_pollution ? w.poll[cell] : 0.0; en.attr = attr; en.status = status; en.turn = 0u;
         en.kind_harvest = 1u | ((uint32_t)ch.sg << 8);
-        w.log[atomicAdd(w.log_count, 1ull)] = en;
+        *log_slot(w, ts) = en;
     }
 }
 
@@ -389,7 +404,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             if (yb != ya) atomicAdd(&mw[bxi + yb], 1u);
         }
     };
-    const long long t_start = clock64();
+    const long long t_start = PASS_CLOCK();
     long long t_wait = 0, t_turn = 0, t_m;
     int n_turns = 0, n_blocked_me = 0;
     // ---- stage 1: copy occupancy words + int(sugar) into shared memory ----
@@ -433,7 +448,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     me.bfront[lane] = PRIO_INF;
     for (int i = tid; i < g.emax * ew; i += PASS_THREADS) blk_bits[i] = 0u;
     __syncthreads();
-    const long long t_loaded = clock64();
+    const long long t_loaded = PASS_CLOCK();
     // ---- stage 2 (all threads, one pass over the window): pending agents -> their region's list
     //      (core) or blocked set (ring); per-block frontiers start at the block's lowest priority ----
     const uint64_t skey = ss_step_key(w.cfg.keyed_seed, iteration);
@@ -526,8 +541,8 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     if (lane == 0 && n_mine > 0) atomicAdd(&sh.count[0], 1);
     __syncthreads();
     if (sh.count[0] == 0) { write_map(); return; }
-    const long long t_listed = clock64();
-    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0};
+    const long long t_listed = PASS_CLOCK();
+    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
     // ---- the region's agents in ascending priority ----
     for (int iter = 0;; iter++) {
         if (iter > PASS_LIST + 8) { if (lane == 0) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x2222; } break; }
@@ -547,7 +562,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         // another region that the zone touches has its frontier above priority(A).
         unsigned reach = 0u;
         {
-            t_m = clock64();
+            t_m = PASS_CLOCK();
             const int zx0 = lx - V, zx1 = lx + V, zy0 = ly - V, zy1 = ly + V;
             const int ax0 = lx - a - V, ax1 = lx + a + V, ay0 = ly - a - V, ay1 = ly + a + V;
             const bool torus = c.full_x || c.full_y;
@@ -607,7 +622,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             }
             blocked = stuck != 0;
             __threadfence_block();
-            t_wait += clock64() - t_m;
+            t_wait += PASS_CLOCK() - t_m;
         }
         // exact conflict test against the pending agents this launch cannot resolve (ring agents,
         // unresolved Q1 successors, and everything already blocked by those): lane l < 2V+1 owns zone
@@ -675,7 +690,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             n_blocked_me++;
             if (lane == 0) atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
         } else {
-            t_m = clock64();
+            t_m = PASS_CLOCK();
             if (skipped) {
                 if (lane == 0) {      // loses its turn: stays put, no metabolism (Q1)
                     const uint32_t nw = occ_pack(slot, a, next_phase);
@@ -690,14 +705,14 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                         en.slot = slot; en.old_cell = en.new_cell = (uint32_t)(gx * n + gy); en.new_word = nw;
                         en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.turn = 0u; en.kind_harvest = 2u;
                         en.status = (ow & OCC_RISK) ? (((uint32_t)(iteration + 1) << 2) | ST_SKIPPED) : 0u;
-                        w.log[atomicAdd(w.log_count, 1ull)] = en;
+                        *log_slot(w, ts) = en;
                     }
                 }
             } else {
                 warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
                 n_turns++;
             }
-            t_turn += clock64() - t_m;
+            t_turn += PASS_CLOCK() - t_m;
         }
         // A is finished (or parked in the blocked set): advance the frontier of its block
         __syncwarp();
@@ -721,7 +736,10 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             if (lane == 0) me.bfront[bx_a * PASS_BCOLS + by_a] = mn;
         }
     }
-    if (lane == 0) { __threadfence_block(); me.done = 1; }
+    if (lane == 0) {
+        __threadfence_block(); me.done = 1;
+        while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;      // unused part of the reserved slice
+    }
     __syncthreads();
     write_map();
     if (w.dbg) {
@@ -736,7 +754,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             atomicAdd(&w.dbg[0], 1ull);                                   // windows with work
             atomicAdd(&w.dbg[3], (unsigned long long)(t_listed - t_start));
             atomicAdd(&w.dbg[11], (unsigned long long)(t_loaded - t_start));
-            atomicAdd(&w.dbg[6], (unsigned long long)(clock64() - t_start));
+            atomicAdd(&w.dbg[6], (unsigned long long)(PASS_CLOCK() - t_start));
         }
     }
     // ---- block reduction of the step accumulators ----
@@ -772,10 +790,15 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 __global__ void __launch_bounds__(256)
 ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsigned long long n_entries, int phase) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (phase == 1 && i == 0 && n_entries) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)n_entries));
-    if (i >= n_entries) return;
-    const ShardLogEntry en = entries[i];
-    const uint32_t kind = en.kind_harvest & 255u;
+    const bool in_range = i < n_entries;
+    ShardLogEntry en;
+    uint32_t kind = 255u;
+    if (in_range) { en = entries[i]; kind = en.kind_harvest & 255u; }
+    if (phase == 1) {          // the replicated pending counter drops by the number of valid entries
+        const unsigned m = __ballot_sync(FULL, kind != 255u);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)__popc(m)));
+    }
+    if (kind == 255u) return;
     if (phase == 0) {
         if (kind == 2u) return;
         if (en.old_cell != en.new_cell) w.occw[en.old_cell] = 0u;

@@ -173,6 +173,7 @@ class DistributedEngine:
         self.r = ShardRank(cfg, self.rank, self.world, device=self.device)
         self.passes = 0
         self.bytes_sent = 0
+        self.t = {"begin": 0.0, "pass": 0.0, "gather": 0.0, "apply+pending": 0.0, "end": 0.0}
 
     def upload(self, w):
         self.r.upload(w)
@@ -190,21 +191,31 @@ class DistributedEngine:
     def step(self, nsteps=1):
         torch = self.torch
         out = np.zeros(nsteps, dtype=STATS_DTYPE)
+        pc = time.perf_counter
         for t in range(nsteps):
+            t0 = pc()
             self.r.begin_step()
+            t1 = pc(); self.t["begin"] += t1 - t0
             while True:
+                t1 = pc()
                 ptr, n = self.r.run_pass()                   # engine stream is synchronised on return
+                t2 = pc(); self.t["pass"] += t2 - t1
                 self.passes += 1
                 local = torch.as_tensor(_DevView(ptr, max(n, 1) * ENTRY_BYTES), device="cuda:%d" % self.device)
                 counts, parts = pad_and_gather(local, n, self.world, self._gather_counts, self._gather_padded)
                 torch.cuda.current_stream().synchronize()    # NCCL results before the engine's stream reads them
+                t3 = pc(); self.t["gather"] += t3 - t2
                 self.bytes_sent += n * ENTRY_BYTES
                 for j in range(self.world):
                     if j != self.rank and counts[j]:
                         self.r.apply(parts[j].data_ptr(), counts[j])
-                if self.r.pending() == 0:
+                done = self.r.pending() == 0
+                self.t["apply+pending"] += pc() - t3
+                if done:
                     break
+            t4 = pc()
             out[t] = self.r.end_step()[0]
+            self.t["end"] += pc() - t4
         return out
 
     def close(self):
@@ -242,6 +253,8 @@ def bench_main(args, wl):
     sync_all()
     from .clocks import ClockSampler
     p0, l0, b0 = de.passes, de.r.eng.counters()["launches"], de.bytes_sent
+    for k in de.t:
+        de.t[k] = 0.0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -285,6 +298,7 @@ def bench_main(args, wl):
             "population": [int(pop0), int(st["population"][-1])],
             "passes_per_step": (de.passes - p0) / K, "gpu_launches": de.r.eng.counters()["launches"] - l0,
             "nccl_bytes_sent_per_rank_per_step": (de.bytes_sent - b0) / K,
+            "rank0_ms_per_step": {k: 1e3 * v / K for k, v in de.t.items()},
             "e2e": {"value": float(popse.sum()) / float(e2e_s.item()), "unit": "agent-steps/s",
                     "h2d_bytes_per_step": (3 * 8 * n * n + 4 * n * n + 32 * len(w["id"])) / Ke,
                     "d2h_bytes_per_step": ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke, "steps": Ke,
