@@ -176,3 +176,46 @@ def test_multi_gpu_replicas_on_reference_golden():
     common.init_world(v, common.golden_init(g), "keyed")
     common.run_against_golden(g, v, exact_gini=False, max_steps=50)
     v.close()
+
+
+def test_full_size_c4_against_oracle():
+    """BASELINE config 4 at full size (4096 x 4096, 1,048,576 agents, pollution with diffusion every step):
+    the lattice path against the CPU oracle, bit-exact, three whole timesteps."""
+    s, init = common.synthetic_case(4096, True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert e.counters()["path"] == 2
+    common.compare_worlds(e, o, 3, what="C4 full size")
+    e.close()
+    o.close()
+
+
+def test_full_size_c5_invariants():
+    """BASELINE config 5 at full size (16384 x 16384, 16,777,216 agents): size-independent properties after
+    two steps -- every living agent stands on the cell that carries its id, cells are unique, the population
+    series equals the number of living agents, sugar never exceeds capacity, harvested cells are empty, and
+    the run is reproducible (two engines, same inputs -> identical state)."""
+    n = 16384
+    s, init = common.synthetic_case(n, False)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    digests = []
+    for rep in range(2):
+        e = common.engine_world(cfg)
+        common.init_world(e, init, "keyed")
+        st = e.step(2)
+        ags = e.download_agents()
+        cells = e.download_cells(cap=False, pollution=False)
+        assert len(ags["id"]) == int(st["population"][-1]) == e.agent_count()
+        assert st["acted"][0] == len(init["id"]) and st["deaths"].sum() == len(init["id"]) - len(ags["id"])
+        lin = ags["x"].astype(np.int64) * n + ags["y"]
+        assert len(np.unique(lin)) == len(lin)
+        occ = cells["occ"].ravel()
+        assert np.array_equal(occ[lin], ags["id"]) and int((occ != 0).sum()) == len(lin)
+        assert (cells["sugar"] <= init["cap"]).all() and (cells["sugar"] >= 0).all()
+        assert (ags["sugar"] > 0.1).all()
+        digests.append((int(lin.sum()), float(ags["sugar"].sum()), float(cells["sugar"].sum()), st.tobytes()))
+        e.close()
+        del cells, ags
+    assert digests[0] == digests[1]
