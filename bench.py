@@ -200,7 +200,7 @@ def run_engine_single(args, wl):
     eng.close()
     popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
     e2e_value = float(popse.sum()) / t_e2e
-    h2d = (3 * 8 * n * n + 4 * n * n + 32 * len(w["id"])) / Ke
+    h2d = (3 * 8 * n * n + 28 * len(w["id"])) / Ke                 # sugar, cap, pollution + six agent columns
     d2h = ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke
     del cells, ags
     # ---------------- cpu baseline: oracle port on a bounded sample ----------------

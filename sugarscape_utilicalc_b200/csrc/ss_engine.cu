@@ -15,6 +15,10 @@ extern "C" {
 cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
                              int stats_base, cudaStream_t stream);
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s);
+cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
+cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
+                                   const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
+cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s);
 size_t ss_pass_smem_bytes(int emax, int ew, int vmax);
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
@@ -171,17 +175,13 @@ extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* 
     CK(cudaMemcpyAsync(e->w.cap, cap, cb, cudaMemcpyHostToDevice, e->stream));
     if (pollution) CK(cudaMemcpyAsync(e->w.poll, pollution, cb, cudaMemcpyHostToDevice, e->stream));
     else CK(cudaMemsetAsync(e->w.poll, 0, cb, e->stream));
-    {   // int(sugar) byte mirror for the lattice path; needs capacities < 256
-        std::vector<uint8_t> isg(e->cells);
-        bool fits = true;
-        for (size_t c = 0; c < e->cells; c++) {
-            const double v = sugar[c];
-            if (!(v >= 0.0 && v < 256.0) || !(cap[c] < 256.0)) { fits = false; isg[c] = 0; }
-            else isg[c] = (uint8_t)(int)v;
-        }
-        e->cap_fits_u8 = fits;
-        CK(cudaMemcpyAsync(e->w.isugar, isg.data(), e->cells, cudaMemcpyHostToDevice, e->stream));
+    {   // int(sugar) byte mirror for the lattice path (built on the device); needs capacities < 256
+        int flag = 0;
+        CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
+        CK(ss_launch_isugar(e->w, e->d_flags, e->stream));
+        CK(cudaMemcpyAsync(&flag, e->d_flags, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
+        e->cap_fits_u8 = flag == 0;
     }
     e->have_cells = true;
     if (e->have_agents) return choose_path(e);
@@ -258,22 +258,7 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
     }
     if ((uint32_t)max_id > SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^24");
     const uint32_t ns = (uint32_t)std::max(max_id, 1);
-    std::vector<AgentRec> recs(ns);
-    memset(recs.data(), 0, sizeof(AgentRec) * ns);
-    std::vector<uint32_t> occ(e->cells, 0u);
-    std::vector<int32_t> order((size_t)std::max(n, 1));
     const uint32_t phase = (uint32_t)(e->iteration & 1);
-    for (int i = 0; i < n; i++) {
-        const uint32_t s = (uint32_t)id[i] - 1u;
-        if (attr_alive(recs[s].attr)) return set_err(e, SS_ERR_ARG, "duplicate agent id");
-        const size_t c = (size_t)x[i] * N + y[i];
-        if (occ[c]) return set_err(e, SS_ERR_ARG, "two agents on one cell");
-        recs[s].sugar = sugar[i];
-        recs[s].pos = (uint32_t)c;
-        recs[s].attr = attr_pack(vision[i], metab[i], true);
-        occ[c] = occ_pack(s, vision[i], phase);
-        order[i] = (int32_t)s;
-    }
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.wealth); cudaFree(e->w.sortkeys);
     e->w.agents = nullptr; e->w.order = nullptr; e->w.wealth = nullptr; e->w.sortkeys = nullptr;
     const int P = next_pow2((int)ns);
@@ -281,19 +266,39 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
     CK(cudaMalloc(&e->w.order, sizeof(int32_t) * ns));
     CK(cudaMalloc(&e->w.wealth, sizeof(double) * P));
     CK(cudaMalloc(&e->w.sortkeys, sizeof(unsigned long long) * P));
-    CK(cudaMemcpyAsync(e->w.agents, recs.data(), sizeof(AgentRec) * ns, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->w.occw, occ.data(), sizeof(uint32_t) * e->cells, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->w.order, order.data(), sizeof(int32_t) * std::max(n, 1), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->w.n_order, &n, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-    StepAccum acc;
-    memset(&acc, 0, sizeof acc);
-    acc.population = (unsigned long long)n;
-    CK(cudaMemcpyAsync(e->w.acc, &acc, sizeof acc, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    {   // stage the six View.agents columns and build the agent store + occupancy words on the device
+        const size_t nn = (size_t)std::max(n, 1);
+        int32_t* d_i32 = nullptr;
+        double* d_f64 = nullptr;
+        CK(cudaMalloc(&d_i32, sizeof(int32_t) * 5 * nn));
+        CK(cudaMalloc(&d_f64, sizeof(double) * nn));
+        const int32_t* cols[5] = {id, x, y, vision, metab};
+        for (int k = 0; k < 5 && n > 0; k++)
+            CK(cudaMemcpyAsync(d_i32 + k * nn, cols[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+        if (n > 0) CK(cudaMemcpyAsync(d_f64, sugar, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemsetAsync(e->w.agents, 0, sizeof(AgentRec) * ns, e->stream));
+        CK(cudaMemsetAsync(e->w.occw, 0, sizeof(uint32_t) * e->cells, e->stream));
+        CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
+        CK(ss_launch_build_agents(e->w, n, phase, d_i32, d_i32 + nn, d_i32 + 2 * nn, d_i32 + 3 * nn, d_i32 + 4 * nn, d_f64,
+                                  e->d_flags, e->stream));
+        int err = 0;
+        CK(cudaMemcpyAsync(&err, e->d_flags, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->w.n_order, &n, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        StepAccum acc;
+        memset(&acc, 0, sizeof acc);
+        acc.population = (unsigned long long)n;
+        CK(cudaMemcpyAsync(e->w.acc, &acc, sizeof acc, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(d_i32);
+        cudaFree(d_f64);
+        if (err == 1) return set_err(e, SS_ERR_ARG, "duplicate agent id");
+        if (err == 2) return set_err(e, SS_ERR_ARG, "two agents on one cell");
+    }
+    std::vector<int32_t> order((size_t)n);
+    for (int i = 0; i < n; i++) order[i] = id[i] - 1;
     e->w.n_slots = ns;
     e->w.half = ss_order_half_bits(ns);
     e->w.vmax = vmax;
-    order.resize((size_t)n);
     e->upload_order.swap(order);
     e->have_agents = true;
     e->stepped = false;
@@ -407,7 +412,13 @@ static int lattice_step(ss_engine* e, int stats_index) {
                                    e->stream));
                 CK(cudaStreamSynchronize(e->stream));
                 e->syncs++;
-                if (e->trace) fprintf(stderr, "[ss] step %lld pass %d pending %llu\n", (long long)e->iteration, p, *e->h_pending);
+                if (e->trace) {
+                    static double t_prev = 0;
+                    struct timespec ts_; clock_gettime(CLOCK_MONOTONIC, &ts_);
+                    const double now = ts_.tv_sec * 1e3 + ts_.tv_nsec * 1e-6;
+                    fprintf(stderr, "[ss] step %lld pass %d pending %llu  (+%.3f ms)\n", (long long)e->iteration, p, *e->h_pending, now - t_prev);
+                    t_prev = now;
+                }
                 if (*e->h_pending == 0ull) break;
             }
             if (p > 4096) return set_err(e, SS_ERR_STATE, "move passes did not converge");
@@ -489,12 +500,21 @@ static int fetch_population(ss_engine* e, std::vector<AgentRec>* recs_out, std::
             for (int32_t s : e->upload_order) if (attr_alive(recs[s].attr)) order.push_back(s);
         } else {
             const OrderKey ok = ss_order_key(ss_step_key(e->cfg.keyed_seed, e->iteration - 1), e->w.half);
-            std::vector<std::pair<uint32_t, int32_t>> keyed;
+            std::vector<uint64_t> keyed, tmp;
+            keyed.reserve(ns);
             for (uint32_t s = 0; s < ns; s++)
-                if (attr_alive(recs[s].attr)) keyed.emplace_back(ss_priority(ok, s), (int32_t)s);
-            std::sort(keyed.begin(), keyed.end());
+                if (attr_alive(recs[s].attr)) keyed.push_back(((uint64_t)ss_priority(ok, s) << 32) | s);
+            tmp.resize(keyed.size());
+            for (int pass = 0; pass < 4; pass++) {                    // LSD radix sort on the 32-bit priority
+                const int shift = 32 + 8 * pass;
+                size_t cnt[257] = {0};
+                for (uint64_t k : keyed) cnt[((k >> shift) & 0xff) + 1]++;
+                for (int i = 0; i < 256; i++) cnt[i + 1] += cnt[i];
+                for (uint64_t k : keyed) tmp[cnt[(k >> shift) & 0xff]++] = k;
+                keyed.swap(tmp);
+            }
             order.reserve(keyed.size());
-            for (auto& kv : keyed) order.push_back(kv.second);
+            for (uint64_t k : keyed) order.push_back((int32_t)(k & 0xffffffffu));
         }
     }
     recs_out->swap(recs);
@@ -522,10 +542,14 @@ extern "C" int ss_download_cells(ss_engine* e, double* sugar, double* cap, doubl
     if (sugar) CK(cudaMemcpyAsync(sugar, e->w.sugar, cb, cudaMemcpyDeviceToHost, e->stream));
     if (cap) CK(cudaMemcpyAsync(cap, e->w.cap, cb, cudaMemcpyDeviceToHost, e->stream));
     if (pollution) CK(cudaMemcpyAsync(pollution, e->w.poll, cb, cudaMemcpyDeviceToHost, e->stream));
-    if (occ_id) CK(cudaMemcpyAsync(occ_id, e->w.occw, e->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    int32_t* d_ids = nullptr;
+    if (occ_id) {
+        CK(cudaMalloc(&d_ids, e->cells * sizeof(int32_t)));
+        CK(ss_launch_occ_ids(e->w, d_ids, e->stream));
+        CK(cudaMemcpyAsync(occ_id, d_ids, e->cells * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    }
     CK(cudaStreamSynchronize(e->stream));
-    if (occ_id)
-        for (size_t c = 0; c < e->cells; c++) occ_id[c] = occ_id[c] ? (int32_t)(occ_slot((uint32_t)occ_id[c]) + 1u) : 0;
+    cudaFree(d_ids);
     return SS_OK;
 }
 

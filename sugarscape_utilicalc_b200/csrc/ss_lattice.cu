@@ -1156,8 +1156,57 @@ ss_diffuse_diag_kernel(double* p, int n) {
     }
 }
 
+// ----------------------------------------------------------------- upload / download helpers ----
+// int(sugar) mirror from the uploaded sugar (and a flag if a value or capacity does not fit a byte)
+__global__ void ss_isugar_kernel(const double* __restrict__ sugar, const double* __restrict__ cap, uint8_t* __restrict__ isugar,
+                                 size_t cells, int* flag) {
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const double v = sugar[c];
+        if (!(v >= 0.0 && v < 256.0) || !(cap[c] < 256.0)) { *flag = 1; isugar[c] = 0; }
+        else isugar[c] = (uint8_t)(int)v;
+    }
+}
+// agent store + occupancy words from the uploaded View.agents arrays; err: 1 duplicate id, 2 two agents on a cell
+__global__ void ss_build_agents_kernel(int n, int N, uint32_t phase, const int32_t* __restrict__ id, const int32_t* __restrict__ x,
+                                       const int32_t* __restrict__ y, const int32_t* __restrict__ vision,
+                                       const int32_t* __restrict__ metab, const double* __restrict__ sugar, AgentRec* recs,
+                                       uint32_t* occw, int32_t* order, int* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = (uint32_t)id[i] - 1u;
+    const uint32_t c = (uint32_t)x[i] * (uint32_t)N + (uint32_t)y[i];
+    const uint32_t attr = attr_pack(vision[i], metab[i], true);
+    if (atomicCAS(&recs[s].attr, 0u, attr) != 0u) { atomicMax(err, 1); return; }
+    if (atomicCAS(&occw[c], 0u, occ_pack(s, vision[i], phase)) != 0u) { atomicMax(err, 2); return; }
+    recs[s].sugar = sugar[i];
+    recs[s].pos = c;
+    order[i] = (int32_t)s;
+}
+__global__ void ss_occ_ids_kernel(const uint32_t* __restrict__ occw, int32_t* __restrict__ ids, size_t cells) {
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t w = occw[c];
+        ids[c] = w ? (int32_t)(occ_slot(w) + 1u) : 0;
+    }
+}
+
 // ---------------------------------------------------------------------------- launchers ----
 extern "C" {
+
+cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s) {
+    ss_isugar_kernel<<<148 * 8, 256, 0, s>>>(w.sugar, w.cap, w.isugar, (size_t)w.n * w.n, flag);
+    return cudaGetLastError();
+}
+cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
+                                   const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s) {
+    if (n > 0)
+        ss_build_agents_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, w.n, phase, id, x, y, vision, metab, sugar, w.agents, w.occw,
+                                                               w.order, err);
+    return cudaGetLastError();
+}
+cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s) {
+    ss_occ_ids_kernel<<<148 * 8, 256, 0, s>>>(w.occw, ids, (size_t)w.n * w.n);
+    return cudaGetLastError();
+}
 
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s) {
     ss_begin_step_kernel<<<1, 1, 0, s>>>(w);

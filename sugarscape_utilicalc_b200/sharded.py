@@ -300,7 +300,7 @@ def bench_main(args, wl):
             "nccl_bytes_sent_per_rank_per_step": (de.bytes_sent - b0) / K,
             "rank0_ms_per_step": {k: 1e3 * v / K for k, v in de.t.items()},
             "e2e": {"value": float(popse.sum()) / float(e2e_s.item()), "unit": "agent-steps/s",
-                    "h2d_bytes_per_step": (3 * 8 * n * n + 4 * n * n + 32 * len(w["id"])) / Ke,
+                    "h2d_bytes_per_step": (3 * 8 * n * n + 28 * len(w["id"])) / Ke,
                     "d2h_bytes_per_step": ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke, "steps": Ke,
                     "what": "per rank: Engine + upload from host numpy; K sharded steps; rank 0 downloads cells+agents"},
             "roofline": None, "cpu_baseline": None,
