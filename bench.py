@@ -177,6 +177,7 @@ def run_engine_single(args, wl):
         if t > 0:
             kernels[name] = {"ms_per_step": t, "share": kt[key] / tot, "algorithmic_bytes_per_step": nbytes,
                              "achieved_gbs": nbytes / (t * 1e-3) / 1e9, "frac": nbytes / (t * 1e-3) / 1e9 / peak}
+    kernels["settle (part of move)"] = {"ms_per_step": kt["settle"] / K}
     kernels["prepare+stats"] = {"ms_per_step": (kt["prepare"] + kt["stats"]) / K,
                                 "share": (kt["prepare"] + kt["stats"]) / tot}
     dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])

@@ -838,48 +838,60 @@ ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsig
 // harvest (agent.py:832), production + consumption pollution at the destination
 // (agent.py:825-826, sugarscape.py:566-567; environment.py:312-315), metabolism
 // (sugarscape.py:569), statistics (sugarscape.py:575-583).
+#define SETTLE_BINS 2048            // low wealth bins kept in shared memory per CTA
+#define SETTLE_PER_THREAD 8
 __global__ void __launch_bounds__(256)
 ss_settle_kernel(DevWorld w, int64_t iteration, int64_t env_time) {
-    __shared__ unsigned long long red[8];
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long sum_m = 0, sum_v = 0, acted = 0, small = 0, inexact = 0, fault = 0;
-    if (slot < w.n_slots) {
+    __shared__ unsigned hist_s[SETTLE_BINS];
+    __shared__ unsigned long long acc_s[6];
+    for (int i = threadIdx.x; i < SETTLE_BINS; i += blockDim.x) hist_s[i] = 0u;
+    if (threadIdx.x < 6) acc_s[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned sum_m = 0, sum_v = 0, acted = 0, small = 0, inexact = 0, fault = 0;
+    const uint32_t stamp = (uint32_t)(iteration + 1) & 0xffffffu;
+    const bool pol = w.cfg.rule_pollution && w.cfg.pollution_start_time <= env_time;
+    // a CTA streams SETTLE_PER_THREAD * 256 consecutive records (coalesced 32-byte loads)
+    const uint32_t base = blockIdx.x * (256u * SETTLE_PER_THREAD);
+#pragma unroll 2
+    for (int u = 0; u < SETTLE_PER_THREAD; u++) {
+        const uint32_t slot = base + u * 256u + threadIdx.x;
+        if (slot >= w.n_slots) break;
         AgentRec* rec = &w.agents[slot];
         const uint32_t attr = rec->attr, turn = rec->turn;
-        if (attr_alive(attr) && (turn >> 8) == ((uint32_t)(iteration + 1) & 0xffffffu)) {
-            const int h = (int)(turn & 255u), metab = attr_metab(attr);
-            double sugar = rec->sugar;
-            if (w.cfg.rule_move_eat) sugar = ss_set_sugar(ss_max0(sugar + (double)h));
-            if (w.cfg.rule_pollution && w.cfg.pollution_start_time <= env_time) {
-                double p = w.poll[rec->pos];
-                if (w.cfg.rule_move_eat) p += ((double)h * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b);
-                if (sugar > 0.0) p += (0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b);
-                w.poll[rec->pos] = p;
-            }
-            sugar = ss_set_sugar(ss_max0(sugar - (double)metab));
-            rec->sugar = sugar;
-            sum_m = (unsigned)metab; sum_v = (unsigned)attr_vision(attr); acted = 1;
-            if (sugar == 0.01) small = 1;
-            else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
-            else inexact = 1;
-            if (w.cfg.rule_can_starve && sugar <= 0.1) fault = 1;      // a "safe" agent starved: must not happen
+        if (!attr_alive(attr) || (turn >> 8) != stamp) continue;
+        const int h = (int)(turn & 255u), metab = attr_metab(attr);
+        double sugar = rec->sugar;
+        if (w.cfg.rule_move_eat) sugar = ss_set_sugar(ss_max0(sugar + (double)h));
+        if (pol) {
+            double p = w.poll[rec->pos];
+            if (w.cfg.rule_move_eat) p += ((double)h * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b);
+            if (sugar > 0.0) p += (0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b);
+            w.poll[rec->pos] = p;
         }
+        sugar = ss_set_sugar(ss_max0(sugar - (double)metab));
+        rec->sugar = sugar;
+        sum_m += (unsigned)metab; sum_v += (unsigned)attr_vision(attr); acted++;
+        if (sugar == 0.01) small++;
+        else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) {
+            const int bin = (int)sugar;
+            if (bin < SETTLE_BINS) atomicAdd(&hist_s[bin], 1u); else atomicAdd(&w.hist[bin], 1u);
+        } else inexact++;
+        if (w.cfg.rule_can_starve && sugar <= 0.1) fault++;           // a "safe" agent starved: must not happen
     }
-    unsigned long long vals[6] = {sum_m, sum_v, acted, small, inexact, fault};
-    unsigned long long* dst[6] = {&w.acc->sum_metab, &w.acc->sum_vision, &w.acc->acted, &w.acc->hist_small,
-                                  &w.acc->inexact, &w.acc->fault};
+    unsigned vals[6] = {sum_m, sum_v, acted, small, inexact, fault};
 #pragma unroll
     for (int q = 0; q < 6; q++) {
-        unsigned long long v = vals[q];
+        unsigned v = vals[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long s = 0;
-            for (int i = 0; i < 8; i++) s += red[i];
-            if (s) atomicAdd(dst[q], s);
-        }
-        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&acc_s[q], (unsigned long long)v);
+    }
+    __syncthreads();
+    unsigned long long* dst[6] = {&w.acc->sum_metab, &w.acc->sum_vision, &w.acc->acted, &w.acc->hist_small,
+                                  &w.acc->inexact, &w.acc->fault};
+    if (threadIdx.x < 6 && acc_s[threadIdx.x]) atomicAdd(dst[threadIdx.x], acc_s[threadIdx.x]);
+    for (int i = threadIdx.x; i < SETTLE_BINS; i += blockDim.x) {
+        const unsigned c = hist_s[i];
+        if (c) atomicAdd(&w.hist[i], c);
     }
 }
 
@@ -1230,7 +1242,8 @@ cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned
 }
 
 cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_time, cudaStream_t s) {
-    if (w.n_slots > 0) ss_settle_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w, iteration, env_time);
+    if (w.n_slots > 0)
+        ss_settle_kernel<<<(w.n_slots + 256 * SETTLE_PER_THREAD - 1) / (256 * SETTLE_PER_THREAD), 256, 0, s>>>(w, iteration, env_time);
     return cudaGetLastError();
 }
 
