@@ -190,20 +190,35 @@ def run_engine_single(args, wl):
     step_frac = whole_bytes / (ms / K * 1e-3) / 1e9 / peak
     eng.close()
     # ---------------- e2e: public API with host buffers ----------------
+    # The caller's arrays live in page-locked host memory (ss_host_alloc), allocated and filled before the clock starts;
+    # the timed region is create + upload (H2D) + K steps with per-step stats read back + download (D2H) of the state.
+    from sugarscape_utilicalc_b200.engine import pinned_copy, pinned_empty
     Ke = min(K, args.e2e_steps)
+    cell_keys, agent_keys = ("sugar", "cap", "pollution"), ("id", "x", "y", "vision", "metab")
+    hw = {k: pinned_copy(w[k], np.float64) for k in cell_keys}
+    hw.update({k: pinned_copy(w[k], np.int32) for k in agent_keys})
+    hw["sugar_agent"] = pinned_copy(w["sugar_agent"], np.float64)
+    hout = dict(sugar=pinned_empty((n, n)), pollution=pinned_empty((n, n)), occ=pinned_empty((n, n), np.int32))
+    aout = {k: pinned_empty(len(w["id"]), np.int32) for k in agent_keys}
+    aout["sugar"] = pinned_empty(len(w["id"]), np.float64)
     t0 = time.perf_counter()
     eng = Engine(cfg)
-    upload(eng, w)
+    t1 = time.perf_counter()
+    upload(eng, hw)
+    t2 = time.perf_counter()
     ste = eng.step(Ke)                       # per-step stats are read back to the host
-    cells = eng.download_cells(cap=False)
-    ags = eng.download_agents()
-    t_e2e = time.perf_counter() - t0
+    t3 = time.perf_counter()
+    cells = eng.download_cells(cap=False, out=hout)
+    ags = eng.download_agents(out=aout)
+    t4 = time.perf_counter()
+    t_e2e = t4 - t0
     eng.close()
     popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
     e2e_value = float(popse.sum()) / t_e2e
     h2d = (3 * 8 * n * n + 28 * len(w["id"])) / Ke                 # sugar, cap, pollution + six agent columns
-    d2h = ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke
-    del cells, ags
+    d2h = ((2 * 8 + 4) * n * n + 28 * len(ags["id"]) + 48 * Ke) / Ke
+    e2e_parts = {"create": t1 - t0, "upload": t2 - t1, "steps": t3 - t2, "download": t4 - t3}
+    del cells, ags, hw, hout, aout
     # ---------------- cpu baseline: oracle port on a bounded sample ----------------
     cpu = None
     if not args.no_cpu:
@@ -225,9 +240,9 @@ def run_engine_single(args, wl):
         "passes_per_step": cnt["passes"] / K, "gpu_launches": cnt["launches"],
         "host_syncs_per_step": cnt["syncs"] / K,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "seconds": t_e2e,
-                "what": "Engine(cfg); upload_cells/agents from host numpy; step(K) with stats read-back; "
-                        "download_cells+download_agents to host"},
+                "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts,
+                "what": "Engine(cfg); upload_cells/agents from page-locked host numpy arrays; step(K) with stats "
+                        "read-back; download_cells+download_agents into page-locked host arrays"},
         "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": whole_bytes, "frac_of_peak": step_frac},
         "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "upload_s": t_upload,

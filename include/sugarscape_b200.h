@@ -23,6 +23,7 @@
  */
 #ifndef SUGARSCAPE_B200_H
 #define SUGARSCAPE_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -118,6 +119,11 @@ int  ss_download_cells(ss_engine* e, double* sugar, double* cap, double* polluti
  * holds after its shuffle).  Any pointer may be NULL. */
 int  ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t* y, int32_t* vision,
                         int32_t* metab, double* sugar);
+
+/* Page-locked host buffers for the arrays that cross the boundary (the copies then run at PCIe speed without a
+ * staging pass).  Optional: every entry point accepts ordinary pageable memory too.  NULL on failure. */
+void* ss_host_alloc(size_t bytes);
+void  ss_host_free(void* p);
 
 /* Instrumentation.  counters: [0] kernel launches since create, [1] move passes,
  * [2] steps, [3] path (0 serial fused, 1 serial + lattice env kernels, 2 lattice),

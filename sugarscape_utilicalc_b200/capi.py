@@ -46,7 +46,7 @@ EXPORTS = (
     "ss_set_rng_mt19937", "ss_get_rng_mt19937", "ss_set_rng_keyed", "ss_step", "ss_agent_count",
     "ss_download_cells", "ss_download_agents", "ss_get_counters", "ss_get_kernel_times",
     "ss_set_option", "ss_version", "ss_shard_enable", "ss_shard_begin_step", "ss_shard_pass", "ss_shard_apply",
-    "ss_shard_pending", "ss_shard_end_step",
+    "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free",
 )
 
 _lib = None
@@ -91,5 +91,9 @@ def lib():
     L.ss_shard_apply.argtypes = [vp, vp, C.c_uint64]
     L.ss_shard_pending.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ss_shard_end_step.argtypes = [vp, vp]
+    L.ss_host_alloc.argtypes = [C.c_size_t]
+    L.ss_host_alloc.restype = vp
+    L.ss_host_free.argtypes = [vp]
+    L.ss_host_free.restype = None
     _lib = L
     return L

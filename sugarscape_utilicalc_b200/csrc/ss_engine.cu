@@ -19,6 +19,9 @@ cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s);
+uint32_t ss_export_blocks(uint32_t domain);
+cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32_t* blockcnt, uint32_t* total, int32_t* cols,
+                                    size_t stride, double* sugar, cudaStream_t s);
 size_t ss_pass_smem_bytes(int emax, int ew, int vmax);
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
@@ -558,6 +561,39 @@ extern "C" int ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t
     if (!e) return set_err(e, SS_ERR_ARG, "null argument");
     if (!e->have_agents) return SS_OK;
     CK(cudaSetDevice(e->device));
+    if (e->path == PATH_LATTICE && e->stepped) {
+        // keyed order after a step: compaction of the inverse priority map on the device, columns copied straight out
+        const uint32_t domain = 1u << (2 * e->w.half);
+        const uint32_t nb = ss_export_blocks(domain);
+        StepAccum acc;
+        CK(cudaMemcpyAsync(&acc, e->w.acc, sizeof acc, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        const size_t pop = (size_t)acc.population, stride = std::max<size_t>(pop, 1);
+        uint32_t* d_cnt = nullptr;
+        int32_t* d_cols = nullptr;
+        double* d_sugar = nullptr;
+        cudaError_t ce;
+        if ((ce = cudaMalloc(&d_cnt, sizeof(uint32_t) * ((size_t)nb + 1))) != cudaSuccess ||
+            (ce = cudaMalloc(&d_cols, sizeof(int32_t) * 5 * stride)) != cudaSuccess ||
+            (ce = cudaMalloc(&d_sugar, sizeof(double) * stride)) != cudaSuccess) {
+            cudaFree(d_cnt); cudaFree(d_cols); cudaFree(d_sugar);
+            return set_err(e, SS_ERR_CUDA, cudaGetErrorString(ce));
+        }
+        uint32_t total = 0;
+        ce = ss_launch_export_agents(e->w, ss_step_key(e->cfg.keyed_seed, e->iteration - 1), d_cnt, d_cnt + nb, d_cols, stride,
+                                     d_sugar, e->stream);
+        e->launches += 3;
+        int32_t* outs[5] = {id, x, y, vision, metab};
+        for (int k = 0; k < 5 && ce == cudaSuccess; k++)
+            if (outs[k] && pop) ce = cudaMemcpyAsync(outs[k], d_cols + k * stride, sizeof(int32_t) * pop, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess && sugar && pop) ce = cudaMemcpyAsync(sugar, d_sugar, sizeof(double) * pop, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total, d_cnt + nb, sizeof total, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        cudaFree(d_cnt); cudaFree(d_cols); cudaFree(d_sugar);
+        if (ce != cudaSuccess) return set_err(e, SS_ERR_CUDA, cudaGetErrorString(ce));
+        if ((size_t)total != pop) return set_err(e, SS_ERR_STATE, "agent export count differs from the population counter");
+        return SS_OK;
+    }
     std::vector<AgentRec> recs;
     std::vector<int32_t> order;
     int rc = fetch_population(e, &recs, &order);
@@ -573,6 +609,15 @@ extern "C" int ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t
         if (sugar) sugar[i] = r.sugar;
     }
     return SS_OK;
+}
+
+extern "C" void* ss_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void ss_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int ss_get_counters(ss_engine* e, int64_t* out, int32_t n) {

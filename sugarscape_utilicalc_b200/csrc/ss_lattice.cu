@@ -1201,6 +1201,97 @@ __global__ void ss_occ_ids_kernel(const uint32_t* __restrict__ occw, int32_t* __
     }
 }
 
+
+// ss_download_agents for the keyed order: the reference's list after its shuffle is the living agents in ascending
+// execution priority (sugarscape.py:511-512 as restated by oracle/keyed_rng.py).  The priority is a bijection of the
+// slot, so the list is the stream compaction of priority_inverse(0..domain-1): count, scan, emit -- no sort.
+#define EXPORT_PER_THREAD 8
+#define EXPORT_THREADS 256
+#define EXPORT_PER_BLOCK (EXPORT_PER_THREAD * EXPORT_THREADS)
+__device__ static inline bool export_slot(const AgentRec* __restrict__ agents, const OrderKey& ok, uint32_t n_slots,
+                                          uint32_t p, uint32_t domain, uint32_t* slot) {
+    if (p >= domain) return false;
+    const uint32_t s = ss_priority_inverse(ok, p);
+    *slot = s;
+    return s < n_slots && attr_alive(agents[s].attr);
+}
+__global__ void __launch_bounds__(EXPORT_THREADS)
+ss_export_count_kernel(const AgentRec* __restrict__ agents, OrderKey ok, uint32_t n_slots, uint32_t domain,
+                       uint32_t* __restrict__ blockcnt) {
+    __shared__ uint32_t wsum[EXPORT_THREADS / 32];
+    const uint32_t p0 = blockIdx.x * EXPORT_PER_BLOCK + threadIdx.x * EXPORT_PER_THREAD;
+    uint32_t c = 0, s;
+#pragma unroll
+    for (int k = 0; k < EXPORT_PER_THREAD; k++) c += export_slot(agents, ok, n_slots, p0 + k, domain, &s) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < EXPORT_THREADS / 32; i++) t += wsum[i];
+        blockcnt[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024)
+ss_export_scan_kernel(uint32_t* __restrict__ blockcnt, uint32_t nblocks, uint32_t* __restrict__ total) {
+    // exclusive scan of the block counts, in place, by one CTA (nblocks <= 2^24 / 2048)
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? blockcnt[i] : 0u;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = wsum[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += t; }
+            wsum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t before = carry + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0u) + inc - v;
+        if (i < nblocks) blockcnt[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(EXPORT_THREADS)
+ss_export_emit_kernel(const AgentRec* __restrict__ agents, OrderKey ok, uint32_t n_slots, uint32_t domain, int n,
+                      const uint32_t* __restrict__ blockoff, int32_t* __restrict__ id, int32_t* __restrict__ x,
+                      int32_t* __restrict__ y, int32_t* __restrict__ vision, int32_t* __restrict__ metab,
+                      double* __restrict__ sugar) {
+    __shared__ uint32_t wsum[EXPORT_THREADS / 32];
+    const uint32_t p0 = blockIdx.x * EXPORT_PER_BLOCK + threadIdx.x * EXPORT_PER_THREAD;
+    uint32_t slot[EXPORT_PER_THREAD];
+    uint32_t live = 0, c = 0;
+#pragma unroll
+    for (int k = 0; k < EXPORT_PER_THREAD; k++)
+        if (export_slot(agents, ok, n_slots, p0 + k, domain, &slot[k])) { live |= 1u << k; c++; }
+    uint32_t inc = c;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint32_t at = blockoff[blockIdx.x] + inc - c;
+    for (int i = 0; i < (int)(threadIdx.x >> 5); i++) at += wsum[i];
+#pragma unroll
+    for (int k = 0; k < EXPORT_PER_THREAD; k++) {
+        if (!((live >> k) & 1u)) continue;
+        const AgentRec r = agents[slot[k]];
+        id[at] = (int32_t)(slot[k] + 1u);
+        x[at] = (int32_t)(r.pos / (uint32_t)n);
+        y[at] = (int32_t)(r.pos % (uint32_t)n);
+        vision[at] = attr_vision(r.attr);
+        metab[at] = attr_metab(r.attr);
+        sugar[at] = r.sugar;
+        at++;
+    }
+}
+
 // ---------------------------------------------------------------------------- launchers ----
 extern "C" {
 
@@ -1213,6 +1304,19 @@ cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, con
     if (n > 0)
         ss_build_agents_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, w.n, phase, id, x, y, vision, metab, sugar, w.agents, w.occw,
                                                                w.order, err);
+    return cudaGetLastError();
+}
+uint32_t ss_export_blocks(uint32_t domain) { return (domain + EXPORT_PER_BLOCK - 1) / EXPORT_PER_BLOCK; }
+cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32_t* blockcnt, uint32_t* total, int32_t* cols,
+                                    size_t stride, double* sugar, cudaStream_t s) {
+    // cols = five int32 columns (id, x, y, vision, metab) of `stride` entries each; *total receives the population
+    const OrderKey ok = ss_order_key(step_key, w.half);
+    const uint32_t domain = 1u << (2 * w.half);
+    const uint32_t nb = ss_export_blocks(domain);
+    ss_export_count_kernel<<<nb, EXPORT_THREADS, 0, s>>>(w.agents, ok, w.n_slots, domain, blockcnt);
+    ss_export_scan_kernel<<<1, 1024, 0, s>>>(blockcnt, nb, total);
+    ss_export_emit_kernel<<<nb, EXPORT_THREADS, 0, s>>>(w.agents, ok, w.n_slots, domain, w.n, blockcnt, cols, cols + stride,
+                                                       cols + 2 * stride, cols + 3 * stride, cols + 4 * stride, sugar);
     return cudaGetLastError();
 }
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s) {

@@ -23,6 +23,29 @@ class EngineError(RuntimeError):
     pass
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory (ss_host_alloc): uploads and downloads on such arrays run at PCIe
+    speed.  The memory is released when the array (and every view of it) is garbage-collected."""
+    import weakref
+    lib = capi.lib()
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = lib.ss_host_alloc(max(nbytes, 1))
+    if not p:
+        raise EngineError("ss_host_alloc(%d) failed (no CUDA device or out of pinned memory)" % nbytes)
+    buf = (C.c_char * max(nbytes, 1)).from_address(p)
+    weakref.finalize(buf, lib.ss_host_free, C.c_void_p(p))
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pinned_copy(a, dtype=None):
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, dtype or a.dtype)
+    out[...] = a
+    return out
+
+
 class Engine:
     def __init__(self, cfg, device=0, path=PATH_AUTO):
         if not isinstance(cfg, SsConfig):
@@ -105,17 +128,40 @@ class Engine:
     def agent_count(self):
         return int(self._lib.ss_agent_count(self._h))
 
-    def download_cells(self, sugar=True, cap=True, pollution=True, occ=True):
+    def download_cells(self, sugar=True, cap=True, pollution=True, occ=True, out=None):
+        """`out` may hold preallocated (N,N) arrays (e.g. from pinned_empty) under 'sugar', 'cap', 'pollution', 'occ'."""
         n = self.n
-        mk = lambda on, dt: np.empty((n, n), dtype=dt) if on else None
-        s, c, p, o = mk(sugar, np.float64), mk(cap, np.float64), mk(pollution, np.float64), mk(occ, np.int32)
+        out = out or {}
+
+        def mk(on, key, dt):
+            if not on:
+                return None
+            a = out.get(key)
+            if a is None:
+                return np.empty((n, n), dtype=dt)
+            if a.dtype != dt or a.size != n * n or not a.flags.c_contiguous:
+                raise ValueError("out[%r] must be a contiguous (N,N) %s array" % (key, np.dtype(dt).name))
+            return a
+        s, c, p, o = (mk(sugar, "sugar", np.float64), mk(cap, "cap", np.float64), mk(pollution, "pollution", np.float64),
+                      mk(occ, "occ", np.int32))
         self._check(self._lib.ss_download_cells(self._h, _ptr(s), _ptr(c), _ptr(p), _ptr(o)), "ss_download_cells")
         return dict(sugar=s, cap=c, pollution=p, occ=o)
 
-    def download_agents(self):
+    def download_agents(self, out=None):
+        """`out` may hold preallocated 1-D arrays of at least agent_count() entries (e.g. from pinned_empty) under
+        'id', 'x', 'y', 'vision', 'metab' (int32) and 'sugar' (float64); the result are views of their first entries."""
         k = self.agent_count()
-        id, x, y, vision, metab = (np.empty(k, dtype=np.int32) for _ in range(5))
-        sugar = np.empty(k, dtype=np.float64)
+        out = out or {}
+
+        def mk(key, dt):
+            a = out.get(key)
+            if a is None:
+                return np.empty(k, dtype=dt)
+            if a.dtype != dt or a.ndim != 1 or a.size < k or not a.flags.c_contiguous:
+                raise ValueError("out[%r] must be a contiguous 1-D %s array of >= %d entries" % (key, np.dtype(dt).name, k))
+            return a[:k]
+        id, x, y, vision, metab = (mk(key, np.int32) for key in ("id", "x", "y", "vision", "metab"))
+        sugar = mk("sugar", np.float64)
         self._check(self._lib.ss_download_agents(self._h, _ptr(id), _ptr(x), _ptr(y), _ptr(vision), _ptr(metab),
                                                  _ptr(sugar)), "ss_download_agents")
         return dict(id=id, x=x, y=y, vision=vision, metab=metab, sugar=sugar)

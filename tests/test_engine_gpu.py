@@ -219,3 +219,34 @@ def test_full_size_c5_invariants():
         e.close()
         del cells, ags
     assert digests[0] == digests[1]
+
+
+def test_page_locked_buffers_and_out_arguments():
+    """ss_host_alloc buffers through upload/download give the same state as ordinary numpy arrays, and the
+    device-side export of View.agents (keyed order) equals the oracle's list."""
+    from sugarscape_utilicalc_b200.engine import pinned_copy, pinned_empty
+    n = 300
+    s, init = common.synthetic_case(n, True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    pinned = {k: pinned_copy(v) for k, v in init.items() if isinstance(v, np.ndarray)}
+    common.init_world(e, dict(init, **pinned), "keyed")
+    common.init_world(o, init, "keyed")
+    e.step(4)
+    o.step(4)
+    k = e.agent_count()
+    aout = {key: pinned_empty(k + 7, np.int32) for key in ("id", "x", "y", "vision", "metab")}
+    aout["sugar"] = pinned_empty(k + 7, np.float64)
+    cout = dict(sugar=pinned_empty((n, n)), pollution=pinned_empty((n, n)), occ=pinned_empty((n, n), np.int32))
+    a, b = e.download_agents(out=aout), o.download_agents()
+    for key in ("id", "x", "y", "vision", "metab", "sugar"):
+        assert a[key].base is not None and len(a[key]) == k
+        assert np.array_equal(a[key], b[key]), key
+    c, d = e.download_cells(cap=False, out=cout), o.download_cells()
+    assert c["sugar"] is cout["sugar"] and c["cap"] is None
+    for key in ("sugar", "pollution", "occ"):
+        assert np.array_equal(c[key], d[key]), key
+    with pytest.raises(ValueError):
+        e.download_agents(out={"id": np.empty(3, np.int32)})
+    e.close()
+    o.close()
