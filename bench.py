@@ -69,7 +69,12 @@ def make_world(wl):
     return s, w
 
 
+ENGINE_OPTS = {}
+
+
 def upload(world, w):
+    for k, v in ENGINE_OPTS.items():
+        world.set_option(k, v)
     world.upload_cells(w["sugar"], w["cap"], w["pollution"])
     world.upload_agents(w["id"], w["x"], w["y"], w["vision"], w["metab"], w["sugar_agent"])
 
@@ -238,6 +243,7 @@ def run_engine_single(args, wl):
         "cell_updates_per_s": n * n * K / (ms * 1e-3),
         "population": [int(pop0), int(st["population"][-1])],
         "passes_per_step": cnt["passes"] / K, "gpu_launches": cnt["launches"],
+        "move_pass": {"impl": ["cta_per_window", "warp_per_window"][cnt["pass_impl"]], "window": cnt["window"]},
         "host_syncs_per_step": cnt["syncs"] / K,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts,
@@ -288,7 +294,10 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SS_BENCH_WORKLOAD", "c5"))
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine option (ss_set_option) for A/B runs, e.g. --opt pass_impl=0")
     args = ap.parse_args()
+    ENGINE_OPTS.update({kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt})
     wl = workload(args.workload)
     if "preset" in wl:
         run_preset(args, wl)

@@ -127,7 +127,7 @@ void  ss_host_free(void* p);
 
 /* Instrumentation.  counters: [0] kernel launches since create, [1] move passes,
  * [2] steps, [3] path (0 serial fused, 1 serial + lattice env kernels, 2 lattice),
- * [4] host syncs, [5] window extent. */
+ * [4] host syncs, [5] window extent | move-pass implementation << 16 (0 = CTA per window, 1 = warp per window). */
 int  ss_get_counters(ss_engine* e, int64_t* out, int32_t n);
 /* accumulated device milliseconds per kernel class (needs option "profile"=1):
  * [0] prepare, [1] move passes, [2] stats, [3] grow/seasons, [4] diffusion, [5] serial;
@@ -136,7 +136,8 @@ int  ss_get_counters(ss_engine* e, int64_t* out, int32_t n);
 int  ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n);
 /* options: "path" (-1 auto, 0 serial, 2 lattice), "profile" (0/1), "reset_times",
  * "reset_counters", "diffuse_impl" (0 wavefront, 1 diagonal sweep for A/B checks),
- * "window" (max window extent of the move passes, 32..176) */
+ * "window" (max window extent of the CTA-per-window move pass, 32..176), "pass_impl" (-1 auto, 0 CTA per window,
+ * 1 warp per window), "solo_window" (max window extent of the warp-per-window move pass) */
 int  ss_set_option(ss_engine* e, const char* name, int64_t value);
 
 /* Multi-GPU (one process per GPU; sugarscape_utilicalc_b200/sharded.py).  Every rank holds a replica of the

@@ -23,6 +23,8 @@ uint32_t ss_export_blocks(uint32_t domain);
 cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32_t* blockcnt, uint32_t* total, int32_t* cols,
                                     size_t stride, double* sugar, cudaStream_t s);
 size_t ss_pass_smem_bytes(int emax, int ew, int vmax);
+size_t ss_solo_smem_bytes(int emax, int ew);
+cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time, cudaStream_t s);
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
 cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s);
@@ -47,6 +49,10 @@ struct ss_engine {
     int path = -1, path_option = -1;
     PassGeom geom{};
     int ntile = 1, emin = 0;
+    // move-pass implementation: 0 = one CTA per window, a warp per region (ss_move_pass_kernel);
+    // 1 = one warp per window (ss_move_solo_kernel); -1 = by window count
+    int pass_impl_option = -1, pass_impl = 0;
+    int solo_window_max = 96;
     int shard_rank = 0, shard_world = 1;       // multi-GPU replicas (sharded.py)
     int shard_pass = 0;
     int last_passes = 4;
@@ -196,29 +202,45 @@ static int choose_path(ss_engine* e) {
     bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && !e->cfg.rule_utilicalc && V <= 15 && 4 * V + 1 <= n &&
                       e->cap_fits_u8 && e->w.n_slots <= SS_MAX_SLOTS;
     PassGeom g{};
+    int ntile = 1, emin = 0, impl = 0;
     if (lattice_ok) {
-        g.ring = 2 * V;
-        g.align = (n % 4 == 0) ? 4 : 1;
-        const int nu = n / g.align;
-        const int wmax = std::max(32, std::min(e->window_max, 176));
-        int emin;
-        if (n <= 176) {
-            g.nwin = 1; g.emax = n; emin = n;
-            e->ntile = 1;
-        } else {
-            g.nwin = (n + wmax - 1) / wmax;
-            g.emax = g.align * ((nu + g.nwin - 1) / g.nwin);
-            emin = g.align * (nu / g.nwin);
-            // three diagonal tilings shifted by thirds of a window resolve every cell (a cell can be in
-            // the ring of at most two of them: once through x, once through y) if the ring strips of
-            // the three tilings are disjoint; otherwise four half-shifted tilings
-            if (emin >= 6 * g.ring + 3 * g.align) e->ntile = 3;
-            else if (emin >= 4 * g.ring + 2 + 2 * g.align) e->ntile = 4;
-            else lattice_ok = false;
-        }
-        g.ew = (g.emax + 31) / 32;
-        e->emin = emin;
-        if (ss_pass_smem_bytes(g.emax, g.ew, V) > 216 * 1024) lattice_ok = false;
+        // window tiling for a maximum window extent; false if the lattice cannot be tiled with it
+        auto tiling = [&](int wmax, PassGeom* out, int* ntile_out, int* emin_out) {
+            PassGeom t{};
+            t.ring = 2 * V;
+            t.align = (n % 4 == 0) ? 4 : 1;
+            const int nu = n / t.align;
+            int em;
+            if (n <= wmax) {
+                t.nwin = 1; t.emax = n; em = n;
+                *ntile_out = 1;
+            } else {
+                t.nwin = (n + wmax - 1) / wmax;
+                t.emax = t.align * ((nu + t.nwin - 1) / t.nwin);
+                em = t.align * (nu / t.nwin);
+                // three diagonal tilings shifted by thirds of a window resolve every cell (a cell can be in
+                // the ring of at most two of them: once through x, once through y) if the ring strips of
+                // the three tilings are disjoint; otherwise four half-shifted tilings
+                if (em >= 6 * t.ring + 3 * t.align) *ntile_out = 3;
+                else if (em >= 4 * t.ring + 2 + 2 * t.align) *ntile_out = 4;
+                else return false;
+            }
+            t.ew = (t.emax + 31) / 32;
+            *emin_out = em;
+            *out = t;
+            return true;
+        };
+        const bool cta_ok = tiling(std::max(32, std::min(e->window_max, 176)), &g, &ntile, &emin) &&
+                            ss_pass_smem_bytes(g.emax, g.ew, V) <= 216 * 1024;
+        PassGeom gs{};
+        int ntile_s = 1, emin_s = 0;
+        // the solo kernel needs many windows to fill the GPU (one warp each, 32 per SM) and window coordinates < 256
+        const bool solo_ok = tiling(std::max(32, std::min(e->solo_window_max, 176)), &gs, &ntile_s, &emin_s) && gs.nwin > 1 &&
+                             ss_solo_smem_bytes(gs.emax, gs.ew) <= 48 * 1024;
+        const bool want_solo = e->pass_impl_option == 1 ||
+                               (e->pass_impl_option < 0 && solo_ok && (long long)gs.nwin * gs.nwin >= 8ll * e->sm_count);
+        if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = 1; }
+        else if (!cta_ok) lattice_ok = false;
     }
     int path;
     if (e->path_option == PATH_LATTICE) {
@@ -234,6 +256,7 @@ static int choose_path(ss_engine* e) {
     if (path != PATH_LATTICE && e->w.n_slots > (1u << 22))
         return set_err(e, SS_ERR_UNSUPPORTED, "serial path limited to 4M agents");
     e->geom = g;
+    e->ntile = ntile; e->emin = emin; e->pass_impl = impl;
     e->path = path;
     if (path == PATH_LATTICE && g.nwin > 1 && n % 32 == 0 && !e->w.pendmap) {
         e->w.pend_nb = n / 32;
@@ -408,7 +431,8 @@ static int lattice_step(ss_engine* e, int stats_index) {
                 CK(cudaMemsetAsync(e->w.pendmap + (size_t)g.map_write * e->w.pend_nb * e->w.pend_nb, 0,
                                    sizeof(uint32_t) * (size_t)e->w.pend_nb * e->w.pend_nb, e->stream));
             }
-            CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
+            if (e->pass_impl == 1) CK(ss_launch_move_solo(e->w, g, e->iteration, e->env_time, e->stream));
+            else CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
             e->launches++; e->passes++; p++;
             if (p >= first_check || e->trace) {
                 CK(cudaMemcpyAsync(e->h_pending, &e->w.acc->pending, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -622,7 +646,7 @@ extern "C" void ss_host_free(void* p) {
 
 extern "C" int ss_get_counters(ss_engine* e, int64_t* out, int32_t n) {
     if (!e || !out) return set_err(e, SS_ERR_ARG, "null argument");
-    const int64_t v[6] = {e->launches, e->passes, e->steps, e->path, e->syncs, e->geom.emax};
+    const int64_t v[6] = {e->launches, e->passes, e->steps, e->path, e->syncs, (int64_t)e->geom.emax | ((int64_t)e->pass_impl << 16)};
     for (int i = 0; i < n && i < 6; i++) out[i] = v[i];
     if (n > 6 && !e->w.dbg && e->path == PATH_LATTICE) {
         StepAccum acc;
@@ -664,6 +688,8 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "pendmap") { e->use_pendmap = (int)value; return SS_OK; }
     if (k == "trace") { e->trace = (int)value; return SS_OK; }
     if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
+    if (k == "solo_window") { e->solo_window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
+    if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }
 
@@ -710,7 +736,8 @@ extern "C" int ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_en
     const int nw = g.nwin, W = e->shard_world, r = e->shard_rank;
     g.bx_lo = (int)(((long long)r * nw) / W);
     g.bx_cnt = (int)(((long long)(r + 1) * nw) / W) - g.bx_lo;
-    CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
+    if (e->pass_impl == 1) CK(ss_launch_move_solo(e->w, g, e->iteration, e->env_time, e->stream));
+    else CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
     e->launches++; e->passes++; e->shard_pass++;
     CK(cudaMemcpyAsync(&after, e->w.log_count, sizeof after, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

@@ -89,11 +89,33 @@ struct WinCtx {
     int gx0, gy0;         // global coordinate of local (0,0)
     bool full_x, full_y;  // window spans the whole torus in that dimension (wrap inside)
     int n;
+    // cell accessors: (r,q) = window coordinates, cell = the same cell's lattice index
+    __device__ inline uint32_t occ(int r, int q, int) const { return occ_s[r * emax + q]; }
+    __device__ inline int isug(int r, int q, int) const { return (int)isug_s[r * emax + q]; }
+    __device__ inline void put_occ(int r, int q, uint32_t v) const { occ_s[r * emax + q] = v; }
+    __device__ inline void clear_isug(int r, int q) const { isug_s[r * emax + q] = 0; }
 };
-__device__ static inline int wrap_row(const WinCtx& c, int r) { return c.full_x ? ss_wrap1(r, c.ex) : r; }
-__device__ static inline int wrap_col(const WinCtx& c, int q) { return c.full_y ? ss_wrap1(q, c.ey) : q; }
-__device__ static inline bool in_core(const WinCtx& c, int r, int q, int R) {
+// The same window read straight from the lattice in HBM/L2 (ss_move_solo_kernel: one warp owns the whole window,
+// so nothing else touches its cells during the launch); stores go to the lattice only.
+struct GlobCtx {
+    const uint32_t* occw;
+    const uint8_t* isugar;
+    int ex, ey, emax;
+    int gx0, gy0;
+    bool full_x, full_y;
+    int n;
+    __device__ inline uint32_t occ(int, int, int cell) const { return __ldcg(&occw[cell]); }
+    __device__ inline int isug(int, int, int cell) const { return (int)__ldcg(&isugar[cell]); }
+    __device__ inline void put_occ(int, int, uint32_t) const {}
+    __device__ inline void clear_isug(int, int) const {}
+};
+template <class Ctx> __device__ static inline int wrap_row(const Ctx& c, int r) { return c.full_x ? ss_wrap1(r, c.ex) : r; }
+template <class Ctx> __device__ static inline int wrap_col(const Ctx& c, int q) { return c.full_y ? ss_wrap1(q, c.ey) : q; }
+template <class Ctx> __device__ static inline bool in_core(const Ctx& c, int r, int q, int R) {
     return (c.full_x || (r >= R && r < c.ex - R)) && (c.full_y || (q >= R && q < c.ey - R));
+}
+template <class Ctx> __device__ static inline int cell_of(const Ctx& c, int r, int q) {
+    return ss_wrap1(c.gx0 + r, c.n) * c.n + ss_wrap1(c.gy0 + q, c.n);
 }
 
 // crosses of A (vision a) and B (vision b, displaced by dx,dy) share a cell
@@ -125,7 +147,8 @@ struct Choice { int lr, lq, sg; };
 // best; ties are broken by replaying the agent's keyed Fisher-Yates draws (agent.py:369,
 // random.py:350/242), each tied lane tracking the position of its own candidate; positions
 // are finalised from the top, so the replay stops once a single tied candidate is left.
-__device__ static Choice warp_choose_cell(const DevWorld& w, const WinCtx& c, int lx, int ly, int gx, int gy, int a,
+template <class Ctx>
+__device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int lx, int ly, int gx, int gy, int a,
                                           uint32_t slot, uint64_t skey, int lane) {
     const int n = c.n;
     const bool pol = w.cfg.rule_pollution != 0;
@@ -142,10 +165,12 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const WinCtx& c, in
                 int r, q, cx, cy;
                 if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap1(gx + o, n); cy = gy; }
                 else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap1(gy + o, n); }
-                const int li = r * c.emax + q;
-                if (c.occ_s[li] == 0u) {
+                const int ci = cx * n + cy;
+                const uint32_t o_w = c.occ(r, q, ci);
+                const int s_w = c.isug(r, q, ci);
+                if (o_w == 0u) {
                     fr = true;
-                    loc[h] = (uint32_t)(r << 8 | q); cell[h] = cx * n + cy; sg[h] = (int)c.isug_s[li];
+                    loc[h] = (uint32_t)(r << 8 | q); cell[h] = ci; sg[h] = s_w;
                     dist[h] = abs(gx - cx) + abs(gy - cy);                       // agent.py:867-868
                 }
             }
@@ -155,7 +180,7 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const WinCtx& c, in
         }
     }
     // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
-    const int sg0 = (int)c.isug_s[lx * c.emax + ly];
+    const int sg0 = c.isug(lx, ly, gx * n + gy);
     Choice stay; stay.lr = lx; stay.lq = ly; stay.sg = sg0;
     if (n_free == 0) return stay;
     bool tie0, tie1;
@@ -221,7 +246,8 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const WinCtx& c, in
 // (nobody can observe them before the agent loop ends: the destination stays occupied).
 // AT-RISK agents are settled synchronously because a death frees the cell and decides the
 // successor's turn (Q1).
-__device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int lx, int ly, uint32_t ow, uint32_t slot,
+template <class Ctx>
+__device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, int ly, uint32_t ow, uint32_t slot,
                                        int64_t iteration, int64_t env_time, uint64_t skey, uint32_t next_phase,
                                        ThreadStats& ts, int lane) {
     const int n = c.n;
@@ -237,18 +263,17 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
     if (w.cfg.rule_move_eat) ch = warp_choose_cell(w, c, lx, ly, gx, gy, a, slot, skey, lane);
     else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
     if (lane != 0) return;
-    const int li_old = lx * c.emax + ly, li_new = ch.lr * c.emax + ch.lq;
     const int cell = (ch.lr == lx && ch.lq == ly) ? pos
                    : ss_wrap1(c.gx0 + ch.lr, n) * n + ss_wrap1(c.gy0 + ch.lq, n);
     uint32_t new_word = occ_pack(slot, a, next_phase);
     ts.resolved++;
     if (!risky) {
-        c.occ_s[li_old] = 0u;
-        c.occ_s[li_new] = new_word;
+        c.put_occ(lx, ly, 0u);
+        c.put_occ(ch.lr, ch.lq, new_word);
         if (cell != pos) w.occw[pos] = 0u;
         w.occw[cell] = new_word;
         if (w.cfg.rule_move_eat) {
-            c.isug_s[li_new] = 0;
+            c.clear_isug(ch.lr, ch.lq);
             w.sugar[cell] = 0.0;                                      // agent.py:864
             w.isugar[cell] = 0;
         }
@@ -267,7 +292,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
     if (w.cfg.rule_move_eat) {
         if (pol) w.poll[cell] = __ldcg(&w.poll[cell]) + (((double)ch.sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));
         sugar = ss_set_sugar(ss_max0(sugar + (double)ch.sg));         // agent.py:832
-        c.isug_s[li_new] = 0;
+        c.clear_isug(ch.lr, ch.lq);
         w.sugar[cell] = 0.0;
         w.isugar[cell] = 0;
     }
@@ -282,8 +307,8 @@ __device__ static void warp_agent_turn(const DevWorld& w, const WinCtx& c, int l
     else ts.inexact++;
     const bool died = w.cfg.rule_can_starve && sugar <= 0.1;          // sugarscape.py:306-309
     if (died) new_word = 0u;
-    c.occ_s[li_old] = 0u;
-    c.occ_s[li_new] = new_word;
+    c.put_occ(lx, ly, 0u);
+    c.put_occ(ch.lr, ch.lq, new_word);
     if (cell != pos) w.occw[pos] = 0u;
     w.occw[cell] = new_word;
     if (died) { attr &= ~ATTR_ALIVE; ts.deaths++; }
@@ -776,6 +801,280 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Solo move pass: ONE WARP owns one whole window, so a launch has no inter-warp dependency at all -- the warp
+// takes the pending agents of the window's core in ascending priority, one after the other, and every conflict
+// partner of lower priority is either earlier in its own list or in the blocked set (ring agents, unresolved Q1
+// successors and whatever those block).  Cells are read straight from the lattice (L2/HBM) instead of a staged
+// shared-memory image, which leaves room for 32 resident warps per SM, each with an independent window: the
+// latency of one agent's turn is hidden by the other windows instead of stalling a CTA.  Shared memory per warp:
+// the sorted key list and the blocked bitmap.
+#define SOLO_LIST 512
+#ifndef SOLO_MIN_CTAS
+#define SOLO_MIN_CTAS 24
+#endif
+__global__ void __launch_bounds__(32, SOLO_MIN_CTAS)
+ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int cnt_s;
+    const int n = w.n, lane = threadIdx.x;
+    if (*((volatile unsigned long long*)&w.acc->pending) == 0ull) return;
+    const int bx = g.bx_lo + (int)blockIdx.x / g.nwin, by = (int)blockIdx.x % g.nwin;
+    const int nu = n / g.align;
+    const int x_lo = g.align * (int)(((long long)bx * nu) / g.nwin), x_hi = g.align * (int)(((long long)(bx + 1) * nu) / g.nwin);
+    const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
+    const int V = w.vmax, R = g.ring;
+    GlobCtx c;
+    c.occw = w.occw; c.isugar = w.isugar;
+    c.n = n; c.ex = x_hi - x_lo; c.ey = y_hi - y_lo; c.emax = g.emax;
+    c.gx0 = x_lo + g.shift_x; c.gy0 = y_lo + g.shift_y;
+    c.full_x = (c.ex == n); c.full_y = (c.ey == n);
+    uint64_t* list = (uint64_t*)smem;                       // [SOLO_LIST] priority << 16 | lx << 8 | ly
+    uint32_t* blk_bits = smem + 2 * SOLO_LIST;              // [emax][ew]
+    const int ew = g.ew;
+    const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
+    const int nb = w.pend_nb;
+    if (g.map_read >= 0) {          // coarse pending map: nothing left in this window's core -> hand the entries on
+        const uint32_t* mr = w.pendmap + (size_t)g.map_read * nb * nb;
+        const int cx0 = (c.gx0 + R) >> 5, cx1 = (c.gx0 + c.ex - R - 1) >> 5;
+        const int cy0 = (c.gy0 + R) >> 5, cy1 = (c.gy0 + c.ey - R - 1) >> 5;
+        const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
+        int any = 0;
+        for (int i = lane; i < ncx * ncy; i += 32)
+            any |= mr[((cx0 + i / ncy) % nb) * nb + ((cy0 + i % ncy) % nb)] != 0u;
+        if (!__any_sync(FULL, any)) {
+            if (g.map_write >= 0) {
+                uint32_t* mw = w.pendmap + (size_t)g.map_write * nb * nb;
+                const int wx0 = c.gx0 >> 5, wx1 = (c.gx0 + c.ex - 1) >> 5, wy0 = c.gy0 >> 5, wy1 = (c.gy0 + c.ey - 1) >> 5;
+                const int nwx = wx1 - wx0 + 1, nwy = wy1 - wy0 + 1;
+                for (int i = lane; i < nwx * nwy; i += 32) {
+                    const int bi = ((wx0 + i / nwy) % nb) * nb + ((wy0 + i % nwy) % nb);
+                    const uint32_t v = mr[bi];
+                    if (v) atomicAdd(&mw[bi], v);
+                }
+            }
+            return;
+        }
+    }
+    bool dirty = false;
+    auto write_map = [&]() {
+        if (g.map_write < 0) return;
+        uint32_t* mw = w.pendmap + (size_t)g.map_write * nb * nb;
+        if (dirty) {
+            const int wx0 = c.gx0 >> 5, wx1 = (c.gx0 + c.ex - 1) >> 5, wy0 = c.gy0 >> 5, wy1 = (c.gy0 + c.ey - 1) >> 5;
+            const int nwx = wx1 - wx0 + 1, nwy = wy1 - wy0 + 1;
+            for (int i = lane; i < nwx * nwy; i += 32)
+                atomicAdd(&mw[((wx0 + i / nwy) % nb) * nb + ((wy0 + i % nwy) % nb)], 1u);
+            return;
+        }
+        for (int wi = lane; wi < c.ex * ew; wi += 32) {
+            const uint32_t bits = blk_bits[wi];
+            if (bits == 0u) continue;
+            const int lx = wi / ew, ly0 = (wi - lx * ew) << 5;
+            const int bxi = (ss_wrap1(c.gx0 + lx, n) >> 5) * nb;
+            const int ya = ss_wrap1(c.gy0 + ly0, n) >> 5, yb = ss_wrap1(c.gy0 + min(ly0 + 31, c.ey - 1), n) >> 5;
+            atomicAdd(&mw[bxi + ya], 1u);
+            if (yb != ya) atomicAdd(&mw[bxi + yb], 1u);
+        }
+    };
+    // ---- scan the window: pending core agents -> key list, pending ring agents -> blocked set ----
+    const uint64_t skey = ss_step_key(w.cfg.keyed_seed, iteration);
+    const OrderKey ok = ss_order_key(skey, w.half);
+    for (int i = lane; i < g.emax * ew; i += 32) blk_bits[i] = 0u;
+    if (lane == 0) cnt_s = 0;
+    __syncwarp();
+    uint32_t pmin = PRIO_INF;       // lowest pending priority of the core (per lane)
+    auto visit = [&](int lx, int ly, uint32_t ow, uint32_t thr, bool first) {
+        if (ow == 0u || (ow >> 31) != cur_phase) return;
+        if (in_core(c, lx, ly, R)) {
+            const uint32_t p = ss_priority(ok, occ_slot(ow));
+            pmin = p < pmin ? p : pmin;
+            if (p < thr) {
+                const int at = atomicAdd(&cnt_s, 1);
+                if (at < SOLO_LIST) list[at] = ((uint64_t)p << 16) | (uint64_t)((lx << 8) | ly);
+            }
+        } else if (first) {
+            atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+        }
+    };
+    auto scan = [&](uint32_t thr, bool first) {
+        if (g.align == 4) {
+            const int gpr = c.ey >> 2, total = c.ex * gpr;
+            for (int base = 0; base < total; base += 4 * 32) {
+                uint4 ov[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int idx = base + u * 32 + lane;
+                    if (idx < total) {
+                        const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
+                        ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + (size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n)));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int idx = base + u * 32 + lane;
+                    if (idx < total) {
+                        const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
+                        visit(lx, ly, ov[u].x, thr, first);
+                        visit(lx, ly + 1, ov[u].y, thr, first);
+                        visit(lx, ly + 2, ov[u].z, thr, first);
+                        visit(lx, ly + 3, ov[u].w, thr, first);
+                    }
+                }
+            }
+        } else {
+            for (int idx = lane; idx < c.ex * c.ey; idx += 32) {
+                const int lx = idx / c.ey, ly = idx - lx * c.ey;
+                visit(lx, ly, __ldcg(&w.occw[(size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n)]), thr, first);
+            }
+        }
+        __syncwarp();
+    };
+    scan(PRIO_INF, true);
+    int n_mine = *((volatile int*)&cnt_s);
+    if (n_mine > SOLO_LIST) {
+        // too many for one launch: keep the lowest priorities (nothing they depend on has a higher one); the
+        // unlisted agents stay pending, and the window reports itself dirty to the pending map
+        dirty = true;
+        // pending priorities are spread over [lowest pending, domain): threshold for ~13/16 of the list
+        const uint32_t domain = 1u << (2 * w.half);
+        const uint32_t p0 = __reduce_min_sync(FULL, pmin);
+        uint32_t span = (uint32_t)((((unsigned long long)(domain - p0) * SOLO_LIST) / (unsigned long long)n_mine) * 13ull / 16ull);
+        for (;;) {
+            if (span < 1u) span = 1u;
+            __syncwarp();
+            if (lane == 0) cnt_s = 0;
+            __syncwarp();
+            scan(p0 + span, false);
+            n_mine = *((volatile int*)&cnt_s);
+            if (n_mine <= SOLO_LIST) break;
+            span >>= 1;
+        }
+    }
+    if (n_mine == 0) { write_map(); return; }
+    {   // bitonic sort of the keys (unique), padded to a power of two
+        int P = 32;
+        while (P < n_mine) P <<= 1;
+        for (int i = n_mine + lane; i < P; i += 32) list[i] = ~0ull;
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < (P >> 1); i += 32) {
+                    const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                    const uint64_t x = list[lo], y = list[hi];
+                    const bool up = (lo & k) == 0;
+                    if ((x > y) == up) { list[lo] = y; list[hi] = x; }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
+    for (int it = 0; it < n_mine; it++) {
+        const uint64_t key = list[it];
+        const uint32_t pa = (uint32_t)(key >> 16);
+        const int lx = (int)((key >> 8) & 255u), ly = (int)(key & 255u);
+        const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
+        const uint32_t ow = __ldcg(&w.occw[(size_t)gx * n + gy]);
+        const int a = occ_vision(ow);
+        bool blocked = false;
+        {   // exact conflict test against the blocked set (same lane layout as ss_move_pass_kernel)
+            bool hit = false;
+            auto consider = [&](int r, int q, int dx, int dy) {
+                if (r == lx && q == ly) return;
+                const uint32_t bw = __ldcg(&w.occw[cell_of(c, r, q)]);
+                if (bw == 0u) return;
+                if (!crosses_meet(dx, dy, a, occ_vision(bw))) return;
+                if (ss_priority(ok, occ_slot(bw)) < pa) hit = true;
+            };
+            auto bits_of = [&](int r, int c0, int len) {
+                uint32_t out = 0u;
+                if (c0 >= 0 && c0 + len <= c.ey) {
+                    const volatile uint32_t* row = blk_bits + r * ew;
+                    const int w0 = c0 >> 5, shf = c0 & 31;
+                    const uint32_t lo = row[w0], hi = (w0 + 1 < ew) ? row[w0 + 1] : 0u;
+                    out = __funnelshift_r(lo, hi, shf) & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u));
+                } else {
+                    for (int i = 0; i < len; i++) {
+                        int cc = c0 + i;
+                        if (c.full_y) cc = ss_wrap1(cc, c.ey); else if (cc < 0 || cc >= c.ey) continue;
+                        out |= ((((const volatile uint32_t*)blk_bits)[r * ew + (cc >> 5)] >> (cc & 31)) & 1u) << i;
+                    }
+                }
+                return out;
+            };
+            if (lane < 2 * V + 1) {
+                const int dx = lane - V, r = wrap_row(c, lx + dx);
+                if (r >= 0 && r < c.ex) {
+                    uint32_t bits = bits_of(r, ly - V, 2 * V + 1);
+                    while (bits) { const int i = __ffs(bits) - 1; bits &= bits - 1; consider(r, wrap_col(c, ly + i - V), dx, i - V); }
+                }
+            } else if (lane == 31) {
+                uint32_t lo = bits_of(lx, ly - V - a, a);
+                while (lo) { const int i = __ffs(lo) - 1; lo &= lo - 1; const int dy = i - V - a; consider(lx, wrap_col(c, ly + dy), 0, dy); }
+                uint32_t hi = bits_of(lx, ly + V + 1, a);
+                while (hi) { const int i = __ffs(hi) - 1; hi &= hi - 1; const int dy = V + 1 + i; consider(lx, wrap_col(c, ly + dy), 0, dy); }
+            }
+            if (lane < 2 * a) {
+                const int dx = (lane & 1) ? (V + 1 + (lane >> 1)) : -(V + 1 + (lane >> 1));
+                const int r = wrap_row(c, lx + dx);
+                if (r >= 0 && r < c.ex && ((((const volatile uint32_t*)blk_bits)[r * ew + (ly >> 5)] >> (ly & 31)) & 1u)) consider(r, ly, dx, 0);
+            }
+            blocked = __any_sync(FULL, hit);
+        }
+        uint32_t slot = 0;
+        bool skipped = false;
+        if (!blocked) {
+            slot = occ_slot(ow);
+            if (ow & OCC_Q1) {      // Q1: the at-risk predecessor decides whether A gets its turn
+                const AgentRec* rec = &w.agents[slot];
+                if (rec->pred_step == (uint32_t)(iteration + 1)) {
+                    const volatile uint32_t* stp = &w.agents[rec->pred - 1u].status;
+                    uint32_t st = *stp;
+                    for (int tries = 0; tries < 4 && (st >> 2) != (uint32_t)(iteration + 1); tries++) { __nanosleep(250); st = *stp; }
+                    if ((st >> 2) != (uint32_t)(iteration + 1)) blocked = true;     // retry in a later launch
+                    else skipped = ((st & 3u) == ST_DIED);
+                }
+            }
+        }
+        if (blocked) {
+            if (lane == 0) atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+        } else if (skipped) {
+            if (lane == 0) {      // loses its turn: stays put, no metabolism (Q1)
+                const uint32_t nw = occ_pack(slot, a, next_phase);
+                w.occw[(size_t)gx * n + gy] = nw;
+                if (ow & OCC_RISK)
+                    *((volatile uint32_t*)&w.agents[slot].status) = ((uint32_t)(iteration + 1) << 2) | ST_SKIPPED;
+                ts.resolved++;
+                if (w.log) {
+                    ShardLogEntry en;
+                    en.slot = slot; en.old_cell = en.new_cell = (uint32_t)(gx * n + gy); en.new_word = nw;
+                    en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.turn = 0u; en.kind_harvest = 2u;
+                    en.status = (ow & OCC_RISK) ? (((uint32_t)(iteration + 1) << 2) | ST_SKIPPED) : 0u;
+                    *log_slot(w, ts) = en;
+                }
+            }
+        } else {
+            warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+        while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;      // unused part of the reserved slice
+    __syncwarp();
+    write_map();
+    // only lane 0 commits turns, so its counters are the warp's
+    if (lane == 0) {
+        if (ts.sum_m) atomicAdd(&w.acc->sum_metab, (unsigned long long)ts.sum_m);
+        if (ts.sum_v) atomicAdd(&w.acc->sum_vision, (unsigned long long)ts.sum_v);
+        if (ts.acted) atomicAdd(&w.acc->acted, (unsigned long long)ts.acted);
+        if (ts.deaths) atomicAdd(&w.acc->deaths, (unsigned long long)ts.deaths);
+        if (ts.small) atomicAdd(&w.acc->hist_small, (unsigned long long)ts.small);
+        if (ts.inexact) atomicAdd(&w.acc->inexact, (unsigned long long)ts.inexact);
+        if (ts.resolved) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)ts.resolved));
     }
 }
 
@@ -1362,6 +1661,14 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
     }
     if (g.bx_cnt <= 0) return cudaSuccess;
     ss_move_pass_kernel<<<g.nwin * g.bx_cnt, PASS_THREADS, smem, s>>>(w, g, iteration, env_time);
+    return cudaGetLastError();
+}
+
+size_t ss_solo_smem_bytes(int emax, int ew) { return (size_t)SOLO_LIST * 8 + (size_t)emax * ew * 4; }
+cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
+                                cudaStream_t s) {
+    if (g.bx_cnt <= 0) return cudaSuccess;
+    ss_move_solo_kernel<<<g.nwin * g.bx_cnt, 32, ss_solo_smem_bytes(g.emax, g.ew), s>>>(w, g, iteration, env_time);
     return cudaGetLastError();
 }
 

@@ -171,7 +171,7 @@ class Engine:
         out = np.zeros(6, dtype=np.int64)
         self._check(self._lib.ss_get_counters(self._h, _ptr(out), 6), "ss_get_counters")
         return dict(launches=int(out[0]), passes=int(out[1]), steps=int(out[2]), path=int(out[3]),
-                    syncs=int(out[4]), window=int(out[5]))
+                    syncs=int(out[4]), window=int(out[5]) & 0xffff, pass_impl=int(out[5]) >> 16)
 
     def kernel_times(self):
         out = np.zeros(8, dtype=np.float64)

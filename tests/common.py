@@ -34,9 +34,13 @@ def oracle_world(cfg):
     return OracleWorld(cfg)
 
 
-def engine_world(cfg, path=-1):
+def engine_world(cfg, path=-1, options=None):
+    """options: ss_set_option settings applied before the upload, e.g. {"pass_impl": 1, "solo_window": 64}."""
     from sugarscape_utilicalc_b200.engine import Engine
-    return Engine(cfg, path=path)
+    e = Engine(cfg, path=path)
+    for k, v in (options or {}).items():
+        e.set_option(k, v)
+    return e
 
 
 def init_world(world, init, rng, mt=None, mt_index=None):
