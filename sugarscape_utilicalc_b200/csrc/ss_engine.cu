@@ -52,7 +52,7 @@ struct ss_engine {
     // move-pass implementation: 0 = one CTA per window, a warp per region (ss_move_pass_kernel);
     // 1 = one warp per window (ss_move_solo_kernel); -1 = by window count
     int pass_impl_option = -1, pass_impl = 0;
-    int solo_window_max = 96;
+    int solo_window_max = 128;
     int shard_rank = 0, shard_world = 1;       // multi-GPU replicas (sharded.py)
     int shard_pass = 0;
     int last_passes = 4;

@@ -94,6 +94,7 @@ struct WinCtx {
     __device__ inline int isug(int r, int q, int) const { return (int)isug_s[r * emax + q]; }
     __device__ inline void put_occ(int r, int q, uint32_t v) const { occ_s[r * emax + q] = v; }
     __device__ inline void clear_isug(int r, int q) const { isug_s[r * emax + q] = 0; }
+    static constexpr bool kGlobal = false;
 };
 // The same window read straight from the lattice in HBM/L2 (ss_move_solo_kernel: one warp owns the whole window,
 // so nothing else touches its cells during the launch); stores go to the lattice only.
@@ -102,12 +103,13 @@ struct GlobCtx {
     const uint8_t* isugar;
     int ex, ey, emax;
     int gx0, gy0;
-    bool full_x, full_y;
+    static constexpr bool full_x = false, full_y = false;   // used with several windows per dimension only
     int n;
     __device__ inline uint32_t occ(int, int, int cell) const { return __ldcg(&occw[cell]); }
     __device__ inline int isug(int, int, int cell) const { return (int)__ldcg(&isugar[cell]); }
     __device__ inline void put_occ(int, int, uint32_t) const {}
     __device__ inline void clear_isug(int, int) const {}
+    static constexpr bool kGlobal = true;
 };
 template <class Ctx> __device__ static inline int wrap_row(const Ctx& c, int r) { return c.full_x ? ss_wrap1(r, c.ex) : r; }
 template <class Ctx> __device__ static inline int wrap_col(const Ctx& c, int q) { return c.full_y ? ss_wrap1(q, c.ey) : q; }
@@ -155,7 +157,12 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
     const int span = 2 * a + 1, K = 2 * span;
     int dist[2] = {0, 0}, cell[2] = {0, 0}, sg[2] = {0, 0}, qidx[2] = {-1, -1};
     uint32_t loc[2] = {0, 0};
+    double pspec[2] = {0.0, 0.0};     // lattice-direct windows fetch the pollution with the cell, not after it
     int n_free = 0;
+    // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
+    const int sg0 = c.isug(lx, ly, gx * n + gy);
+    double pown_spec = 0.0;
+    if (Ctx::kGlobal && pol) pown_spec = __ldcg(&w.poll[gx * n + gy]);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k = h * 32 + lane;
@@ -168,6 +175,7 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
                 const int ci = cx * n + cy;
                 const uint32_t o_w = c.occ(r, q, ci);
                 const int s_w = c.isug(r, q, ci);
+                if (Ctx::kGlobal && pol) pspec[h] = __ldcg(&w.poll[ci]);
                 if (o_w == 0u) {
                     fr = true;
                     loc[h] = (uint32_t)(r << 8 | q); cell[h] = ci; sg[h] = s_w;
@@ -179,8 +187,6 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
             n_free += __popc(fb);
         }
     }
-    // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
-    const int sg0 = c.isug(lx, ly, gx * n + gy);
     Choice stay; stay.lr = lx; stay.lq = ly; stay.sg = sg0;
     if (n_free == 0) return stay;
     bool tie0, tie1;
@@ -193,9 +199,9 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
     } else {
         double key[2] = {-1.0, -1.0};
         double p0 = 0.0, p1 = 0.0, pown = 0.0;
-        if (qidx[0] >= 0 && sg[0] > 0) p0 = __ldcg(&w.poll[cell[0]]);
-        if (qidx[1] >= 0 && sg[1] > 0) p1 = __ldcg(&w.poll[cell[1]]);
-        if (sg0 > 0) pown = __ldcg(&w.poll[gx * n + gy]);
+        if (qidx[0] >= 0 && sg[0] > 0) p0 = Ctx::kGlobal ? pspec[0] : __ldcg(&w.poll[cell[0]]);
+        if (qidx[1] >= 0 && sg[1] > 0) p1 = Ctx::kGlobal ? pspec[1] : __ldcg(&w.poll[cell[1]]);
+        if (sg0 > 0) pown = Ctx::kGlobal ? pown_spec : __ldcg(&w.poll[gx * n + gy]);
         if (qidx[0] >= 0) key[0] = (double)sg[0] / (1.0 + p0);
         if (qidx[1] >= 0) key[1] = (double)sg[1] / (1.0 + p1);
         const double key0 = (double)sg0 / (1.0 + pown);
@@ -812,7 +818,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 // shared-memory image, which leaves room for 32 resident warps per SM, each with an independent window: the
 // latency of one agent's turn is hidden by the other windows instead of stalling a CTA.  Shared memory per warp:
 // the sorted key list and the blocked bitmap.
-#define SOLO_LIST 512
+#define SOLO_LIST 1024
 #ifndef SOLO_MIN_CTAS
 #define SOLO_MIN_CTAS 24
 #endif
@@ -831,8 +837,7 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     c.occw = w.occw; c.isugar = w.isugar;
     c.n = n; c.ex = x_hi - x_lo; c.ey = y_hi - y_lo; c.emax = g.emax;
     c.gx0 = x_lo + g.shift_x; c.gy0 = y_lo + g.shift_y;
-    c.full_x = (c.ex == n); c.full_y = (c.ey == n);
-    uint64_t* list = (uint64_t*)smem;                       // [SOLO_LIST] priority << 16 | lx << 8 | ly
+    uint64_t* list = (uint64_t*)smem;                       // [SOLO_LIST] priority << 24 | lx << 16 | ly << 8 | vision + flags
     uint32_t* blk_bits = smem + 2 * SOLO_LIST;              // [emax][ew]
     const int ew = g.ew;
     const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
@@ -881,78 +886,76 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         }
     };
     // ---- scan the window: pending core agents -> key list, pending ring agents -> blocked set ----
+    // (one copy of the per-cell code, rolled loops: the kernel's instruction footprint is what limits it)
     const uint64_t skey = ss_step_key(w.cfg.keyed_seed, iteration);
     const OrderKey ok = ss_order_key(skey, w.half);
     for (int i = lane; i < g.emax * ew; i += 32) blk_bits[i] = 0u;
     if (lane == 0) cnt_s = 0;
     __syncwarp();
     uint32_t pmin = PRIO_INF;       // lowest pending priority of the core (per lane)
-    auto visit = [&](int lx, int ly, uint32_t ow, uint32_t thr, bool first) {
-        if (ow == 0u || (ow >> 31) != cur_phase) return;
-        if (in_core(c, lx, ly, R)) {
-            const uint32_t p = ss_priority(ok, occ_slot(ow));
-            pmin = p < pmin ? p : pmin;
-            if (p < thr) {
-                const int at = atomicAdd(&cnt_s, 1);
-                if (at < SOLO_LIST) list[at] = ((uint64_t)p << 16) | (uint64_t)((lx << 8) | ly);
-            }
-        } else if (first) {
-            atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
-        }
-    };
-    auto scan = [&](uint32_t thr, bool first) {
-        if (g.align == 4) {
-            const int gpr = c.ey >> 2, total = c.ex * gpr;
-            for (int base = 0; base < total; base += 4 * 32) {
-                uint4 ov[4];
+    uint32_t thr = PRIO_INF, p0 = 0u, span = 0u;
+    bool first = true;
+    int n_mine;
+    const int per = g.align == 4 ? 4 : 1;                   // cells per load
+    const int gpr = c.ey / per, total = c.ex * gpr;
+    for (;;) {
+#pragma unroll 1
+        for (int base = 0; base < total; base += 4 * 32) {
+            uint4 ov[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int idx = base + u * 32 + lane;
-                    if (idx < total) {
-                        const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
-                        ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + (size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n)));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int idx = base + u * 32 + lane;
-                    if (idx < total) {
-                        const int lx = idx / gpr, ly = (idx - lx * gpr) << 2;
-                        visit(lx, ly, ov[u].x, thr, first);
-                        visit(lx, ly + 1, ov[u].y, thr, first);
-                        visit(lx, ly + 2, ov[u].z, thr, first);
-                        visit(lx, ly + 3, ov[u].w, thr, first);
-                    }
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * 32 + lane;
+                ov[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (idx < total) {
+                    const int lx = idx / gpr, ly = (idx - lx * gpr) * per;
+                    const size_t gi = (size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n);
+                    if (per == 4) ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + gi));
+                    else ov[u].x = __ldcg(&w.occw[gi]);
                 }
             }
-        } else {
-            for (int idx = lane; idx < c.ex * c.ey; idx += 32) {
-                const int lx = idx / c.ey, ly = idx - lx * c.ey;
-                visit(lx, ly, __ldcg(&w.occw[(size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n)]), thr, first);
+#pragma unroll 1
+            for (int u = 0; u < 4; u++) {
+                const uint4 o = u == 0 ? ov[0] : u == 1 ? ov[1] : u == 2 ? ov[2] : ov[3];
+                if ((o.x | o.y | o.z | o.w) == 0u) continue;
+                const int idx = base + u * 32 + lane;
+                const int lx = idx / gpr, ly0 = (idx - lx * gpr) * per;
+#pragma unroll 1
+                for (int j = 0; j < per; j++) {
+                    const uint32_t ow = j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w;
+                    if (ow == 0u || (ow >> 31) != cur_phase) continue;
+                    const int ly = ly0 + j;
+                    if (in_core(c, lx, ly, R)) {
+                        const uint32_t p = ss_priority(ok, occ_slot(ow));
+                        pmin = p < pmin ? p : pmin;
+                        if (p < thr) {
+                            const int at = atomicAdd(&cnt_s, 1);
+                            if (at < SOLO_LIST) list[at] = ((uint64_t)p << 24) | (uint64_t)((lx << 16) | (ly << 8) | (int)((ow >> 24) & 0x7fu));
+                        }
+                    } else if (first) {
+                        atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+                    }
+                }
             }
         }
         __syncwarp();
-    };
-    scan(PRIO_INF, true);
-    int n_mine = *((volatile int*)&cnt_s);
-    if (n_mine > SOLO_LIST) {
+        n_mine = *((volatile int*)&cnt_s);
+        if (n_mine <= SOLO_LIST) break;
         // too many for one launch: keep the lowest priorities (nothing they depend on has a higher one); the
-        // unlisted agents stay pending, and the window reports itself dirty to the pending map
-        dirty = true;
-        // pending priorities are spread over [lowest pending, domain): threshold for ~13/16 of the list
-        const uint32_t domain = 1u << (2 * w.half);
-        const uint32_t p0 = __reduce_min_sync(FULL, pmin);
-        uint32_t span = (uint32_t)((((unsigned long long)(domain - p0) * SOLO_LIST) / (unsigned long long)n_mine) * 13ull / 16ull);
-        for (;;) {
-            if (span < 1u) span = 1u;
-            __syncwarp();
-            if (lane == 0) cnt_s = 0;
-            __syncwarp();
-            scan(p0 + span, false);
-            n_mine = *((volatile int*)&cnt_s);
-            if (n_mine <= SOLO_LIST) break;
+        // unlisted agents stay pending, and the window reports itself dirty to the pending map.  Pending
+        // priorities are spread over [lowest pending, domain): threshold for ~13/16 of the list, halved until it fits
+        if (first) {
+            dirty = true;
+            first = false;
+            p0 = __reduce_min_sync(FULL, pmin);
+            span = (uint32_t)((((unsigned long long)((1u << (2 * w.half)) - p0) * SOLO_LIST) / (unsigned long long)n_mine) * 13ull / 16ull);
+        } else {
             span >>= 1;
         }
+        if (span < 1u) span = 1u;
+        thr = p0 + span;
+        __syncwarp();
+        if (lane == 0) cnt_s = 0;
+        __syncwarp();
     }
     if (n_mine == 0) { write_map(); return; }
     {   // bitonic sort of the keys (unique), padded to a power of two
@@ -974,54 +977,41 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     }
     ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
     for (int it = 0; it < n_mine; it++) {
+        // the key carries everything of the agent's occupancy word: the slot is the inverse of the priority, and
+        // nobody else changes the word before the agent's own turn
         const uint64_t key = list[it];
-        const uint32_t pa = (uint32_t)(key >> 16);
-        const int lx = (int)((key >> 8) & 255u), ly = (int)(key & 255u);
+        const uint32_t pa = (uint32_t)(key >> 24);
+        const int lx = (int)((key >> 16) & 255u), ly = (int)((key >> 8) & 255u);
         const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
-        const uint32_t ow = __ldcg(&w.occw[(size_t)gx * n + gy]);
+        const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | ss_priority_inverse(ok, pa);
         const int a = occ_vision(ow);
         bool blocked = false;
-        {   // exact conflict test against the blocked set (same lane layout as ss_move_pass_kernel)
+        {   // exact conflict test against the blocked set.  The zone of A is cut into segments of one bitmap row
+            // each -- 2V+1 rows of the box |d| <= V, the two same-row arm extensions, and the 2a cells of the
+            // same-column arm extensions -- and every lane takes segments lane, lane + 32 (windows are never
+            // full here, and the zone of a core agent lies inside the window)
             bool hit = false;
-            auto consider = [&](int r, int q, int dx, int dy) {
-                if (r == lx && q == ly) return;
-                const uint32_t bw = __ldcg(&w.occw[cell_of(c, r, q)]);
-                if (bw == 0u) return;
-                if (!crosses_meet(dx, dy, a, occ_vision(bw))) return;
-                if (ss_priority(ok, occ_slot(bw)) < pa) hit = true;
-            };
-            auto bits_of = [&](int r, int c0, int len) {
-                uint32_t out = 0u;
-                if (c0 >= 0 && c0 + len <= c.ey) {
-                    const volatile uint32_t* row = blk_bits + r * ew;
-                    const int w0 = c0 >> 5, shf = c0 & 31;
-                    const uint32_t lo = row[w0], hi = (w0 + 1 < ew) ? row[w0 + 1] : 0u;
-                    out = __funnelshift_r(lo, hi, shf) & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u));
-                } else {
-                    for (int i = 0; i < len; i++) {
-                        int cc = c0 + i;
-                        if (c.full_y) cc = ss_wrap1(cc, c.ey); else if (cc < 0 || cc >= c.ey) continue;
-                        out |= ((((const volatile uint32_t*)blk_bits)[r * ew + (cc >> 5)] >> (cc & 31)) & 1u) << i;
-                    }
+            const int nseg = 2 * V + 3 + 2 * a;
+#pragma unroll 1
+            for (int seg = lane; seg < nseg; seg += 32) {
+                int dx, c0, len, dy0;
+                if (seg <= 2 * V) { dx = seg - V; c0 = ly - V; len = 2 * V + 1; dy0 = -V; }
+                else if (seg == 2 * V + 1) { dx = 0; c0 = ly - V - a; len = a; dy0 = -V - a; }
+                else if (seg == 2 * V + 2) { dx = 0; c0 = ly + V + 1; len = a; dy0 = V + 1; }
+                else { const int k = seg - (2 * V + 3); dx = (k & 1) ? (V + 1 + (k >> 1)) : -(V + 1 + (k >> 1)); c0 = ly; len = 1; dy0 = 0; }
+                const int r = lx + dx;
+                const volatile uint32_t* row = blk_bits + r * ew;
+                const int w0 = c0 >> 5, shf = c0 & 31;
+                const uint32_t lo = row[w0], hi = (w0 + 1 < ew) ? row[w0 + 1] : 0u;
+                uint32_t bits = __funnelshift_r(lo, hi, shf) & ((1u << len) - 1u);
+                while (bits) {
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int q = c0 + i, dy = dy0 + i;
+                    if (dx == 0 && dy == 0) continue;
+                    const uint32_t bw = __ldcg(&w.occw[cell_of(c, r, q)]);
+                    if (bw != 0u && crosses_meet(dx, dy, a, occ_vision(bw)) && ss_priority(ok, occ_slot(bw)) < pa) hit = true;
                 }
-                return out;
-            };
-            if (lane < 2 * V + 1) {
-                const int dx = lane - V, r = wrap_row(c, lx + dx);
-                if (r >= 0 && r < c.ex) {
-                    uint32_t bits = bits_of(r, ly - V, 2 * V + 1);
-                    while (bits) { const int i = __ffs(bits) - 1; bits &= bits - 1; consider(r, wrap_col(c, ly + i - V), dx, i - V); }
-                }
-            } else if (lane == 31) {
-                uint32_t lo = bits_of(lx, ly - V - a, a);
-                while (lo) { const int i = __ffs(lo) - 1; lo &= lo - 1; const int dy = i - V - a; consider(lx, wrap_col(c, ly + dy), 0, dy); }
-                uint32_t hi = bits_of(lx, ly + V + 1, a);
-                while (hi) { const int i = __ffs(hi) - 1; hi &= hi - 1; const int dy = V + 1 + i; consider(lx, wrap_col(c, ly + dy), 0, dy); }
-            }
-            if (lane < 2 * a) {
-                const int dx = (lane & 1) ? (V + 1 + (lane >> 1)) : -(V + 1 + (lane >> 1));
-                const int r = wrap_row(c, lx + dx);
-                if (r >= 0 && r < c.ex && ((((const volatile uint32_t*)blk_bits)[r * ew + (ly >> 5)] >> (ly & 31)) & 1u)) consider(r, ly, dx, 0);
             }
             blocked = __any_sync(FULL, hit);
         }
