@@ -149,38 +149,64 @@ struct Choice { int lr, lq, sg; };
 // best; ties are broken by replaying the agent's keyed Fisher-Yates draws (agent.py:369,
 // random.py:350/242), each tied lane tracking the position of its own candidate; positions
 // are finalised from the top, so the replay stops once a single tied candidate is left.
+// The loads of one agent's cross, issued ahead of their use (the warp-per-window kernel overlaps them with its
+// conflict test): per lane the occupancy word, int(sugar) and -- lattice-direct windows with the pollution rule --
+// the pollution of its two candidates, plus the agent's own cell.
+struct CrossLoads {
+    uint32_t occ[2];
+    int sg[2];
+    double poll[2];
+    int sg0;
+    double pown;
+};
+template <class Ctx>
+__device__ static inline void warp_load_cross(const DevWorld& w, const Ctx& c, int lx, int ly, int gx, int gy, int a,
+                                              int lane, CrossLoads& L) {
+    const int n = c.n;
+    const bool pol = w.cfg.rule_pollution != 0;
+    const int span = 2 * a + 1, K = 2 * span;
+    L.sg0 = c.isug(lx, ly, gx * n + gy);
+    L.pown = 0.0;
+    if (Ctx::kGlobal && pol) L.pown = __ldcg(&w.poll[gx * n + gy]);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = h * 32 + lane;
+        L.occ[h] = 1u; L.sg[h] = 0; L.poll[h] = 0.0;
+        if (k < K) {
+            int r, q, cx, cy;
+            if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap1(gx + o, n); cy = gy; }
+            else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap1(gy + o, n); }
+            const int ci = cx * n + cy;
+            L.occ[h] = c.occ(r, q, ci);
+            L.sg[h] = c.isug(r, q, ci);
+            if (Ctx::kGlobal && pol) L.poll[h] = __ldcg(&w.poll[ci]);
+        }
+    }
+}
+
 template <class Ctx>
 __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int lx, int ly, int gx, int gy, int a,
-                                          uint32_t slot, uint64_t skey, int lane) {
+                                          uint32_t slot, uint64_t skey, int lane, const CrossLoads& L) {
     const int n = c.n;
     const bool pol = w.cfg.rule_pollution != 0;
     const int span = 2 * a + 1, K = 2 * span;
     int dist[2] = {0, 0}, cell[2] = {0, 0}, sg[2] = {0, 0}, qidx[2] = {-1, -1};
     uint32_t loc[2] = {0, 0};
-    double pspec[2] = {0.0, 0.0};     // lattice-direct windows fetch the pollution with the cell, not after it
     int n_free = 0;
     // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
-    const int sg0 = c.isug(lx, ly, gx * n + gy);
-    double pown_spec = 0.0;
-    if (Ctx::kGlobal && pol) pown_spec = __ldcg(&w.poll[gx * n + gy]);
+    const int sg0 = L.sg0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k = h * 32 + lane;
         bool fr = false;
         if (h * 32 < K) {
-            if (k < K) {
+            if (k < K && L.occ[h] == 0u) {
                 int r, q, cx, cy;
                 if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap1(gx + o, n); cy = gy; }
                 else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap1(gy + o, n); }
-                const int ci = cx * n + cy;
-                const uint32_t o_w = c.occ(r, q, ci);
-                const int s_w = c.isug(r, q, ci);
-                if (Ctx::kGlobal && pol) pspec[h] = __ldcg(&w.poll[ci]);
-                if (o_w == 0u) {
-                    fr = true;
-                    loc[h] = (uint32_t)(r << 8 | q); cell[h] = ci; sg[h] = s_w;
-                    dist[h] = abs(gx - cx) + abs(gy - cy);                       // agent.py:867-868
-                }
+                fr = true;
+                loc[h] = (uint32_t)(r << 8 | q); cell[h] = cx * n + cy; sg[h] = L.sg[h];
+                dist[h] = abs(gx - cx) + abs(gy - cy);                       // agent.py:867-868
             }
             const unsigned fb = __ballot_sync(FULL, fr);
             if (fr) qidx[h] = n_free + __popc(fb & ((1u << lane) - 1u));
@@ -199,9 +225,9 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
     } else {
         double key[2] = {-1.0, -1.0};
         double p0 = 0.0, p1 = 0.0, pown = 0.0;
-        if (qidx[0] >= 0 && sg[0] > 0) p0 = Ctx::kGlobal ? pspec[0] : __ldcg(&w.poll[cell[0]]);
-        if (qidx[1] >= 0 && sg[1] > 0) p1 = Ctx::kGlobal ? pspec[1] : __ldcg(&w.poll[cell[1]]);
-        if (sg0 > 0) pown = Ctx::kGlobal ? pown_spec : __ldcg(&w.poll[gx * n + gy]);
+        if (qidx[0] >= 0 && sg[0] > 0) p0 = Ctx::kGlobal ? L.poll[0] : __ldcg(&w.poll[cell[0]]);
+        if (qidx[1] >= 0 && sg[1] > 0) p1 = Ctx::kGlobal ? L.poll[1] : __ldcg(&w.poll[cell[1]]);
+        if (sg0 > 0) pown = Ctx::kGlobal ? L.pown : __ldcg(&w.poll[gx * n + gy]);
         if (qidx[0] >= 0) key[0] = (double)sg[0] / (1.0 + p0);
         if (qidx[1] >= 0) key[1] = (double)sg[1] / (1.0 + p1);
         const double key0 = (double)sg0 / (1.0 + pown);
@@ -255,7 +281,7 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
 template <class Ctx>
 __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, int ly, uint32_t ow, uint32_t slot,
                                        int64_t iteration, int64_t env_time, uint64_t skey, uint32_t next_phase,
-                                       ThreadStats& ts, int lane) {
+                                       ThreadStats& ts, int lane, const CrossLoads& L) {
     const int n = c.n;
     const int a = occ_vision(ow);
     const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
@@ -266,7 +292,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
     uint32_t attr = 0;
     if (risky && lane == 0) { sugar = recp->sugar; attr = recp->attr; }   // issued early, used after the scan
     Choice ch;
-    if (w.cfg.rule_move_eat) ch = warp_choose_cell(w, c, lx, ly, gx, gy, a, slot, skey, lane);
+    if (w.cfg.rule_move_eat) ch = warp_choose_cell(w, c, lx, ly, gx, gy, a, slot, skey, lane, L);
     else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
     if (lane != 0) return;
     const int cell = (ch.lr == lx && ch.lq == ly) ? pos
@@ -740,7 +766,9 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                     }
                 }
             } else {
-                warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
+                CrossLoads cl;
+                if (w.cfg.rule_move_eat) warp_load_cross(w, c, lx, ly, ss_wrap1(c.gx0 + lx, n), ss_wrap1(c.gy0 + ly, n), a, lane, cl);
+                warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
                 n_turns++;
             }
             t_turn += PASS_CLOCK() - t_m;
@@ -919,22 +947,23 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 if ((o.x | o.y | o.z | o.w) == 0u) continue;
                 const int idx = base + u * 32 + lane;
                 const int lx = idx / gpr, ly0 = (idx - lx * gpr) * per;
+                uint32_t ringbits = 0u;
 #pragma unroll 1
                 for (int j = 0; j < per; j++) {
                     const uint32_t ow = j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w;
                     if (ow == 0u || (ow >> 31) != cur_phase) continue;
                     const int ly = ly0 + j;
-                    if (in_core(c, lx, ly, R)) {
+                    if (!in_core(c, lx, ly, R)) { ringbits |= 1u << (ly & 31); continue; }
+                    uint64_t key = ((uint64_t)ow << 16) | (uint64_t)((lx << 8) | ly);      // first scan: hashed below
+                    if (!first) {
                         const uint32_t p = ss_priority(ok, occ_slot(ow));
-                        pmin = p < pmin ? p : pmin;
-                        if (p < thr) {
-                            const int at = atomicAdd(&cnt_s, 1);
-                            if (at < SOLO_LIST) list[at] = ((uint64_t)p << 24) | (uint64_t)((lx << 16) | (ly << 8) | (int)((ow >> 24) & 0x7fu));
-                        }
-                    } else if (first) {
-                        atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+                        if (p >= thr) continue;
+                        key = ((uint64_t)p << 24) | (uint64_t)((lx << 16) | (ly << 8) | (int)((ow >> 24) & 0x7fu));
                     }
+                    const int at = atomicAdd(&cnt_s, 1);
+                    if (at < SOLO_LIST) list[at] = key;
                 }
+                if (first && ringbits) atomicOr(&blk_bits[lx * ew + (ly0 >> 5)], ringbits);
             }
         }
         __syncwarp();
@@ -946,6 +975,11 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         if (first) {
             dirty = true;
             first = false;
+            // lowest priority among the SOLO_LIST agents that made it into the list (>= the lowest pending one)
+            for (int i = lane; i < SOLO_LIST; i += 32) {
+                const uint32_t p = ss_priority(ok, occ_slot((uint32_t)(list[i] >> 16)));
+                pmin = p < pmin ? p : pmin;
+            }
             p0 = __reduce_min_sync(FULL, pmin);
             span = (uint32_t)((((unsigned long long)((1u << (2 * w.half)) - p0) * SOLO_LIST) / (unsigned long long)n_mine) * 13ull / 16ull);
         } else {
@@ -958,6 +992,14 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         __syncwarp();
     }
     if (n_mine == 0) { write_map(); return; }
+    if (first) {        // every pending core agent is listed: hash them now, 32 at a time
+        for (int i = lane; i < n_mine; i += 32) {
+            const uint64_t raw = list[i];
+            const uint32_t ow = (uint32_t)(raw >> 16);
+            list[i] = ((uint64_t)ss_priority(ok, occ_slot(ow)) << 24) | (uint64_t)((((uint32_t)raw & 0xff00u) << 8) | (((uint32_t)raw & 0xffu) << 8) | ((ow >> 24) & 0x7fu));
+        }
+        __syncwarp();
+    }
     {   // bitonic sort of the keys (unique), padded to a power of two
         int P = 32;
         while (P < n_mine) P <<= 1;
@@ -986,6 +1028,8 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | ss_priority_inverse(ok, pa);
         const int a = occ_vision(ow);
         bool blocked = false;
+        CrossLoads cl;              // issued now, consumed after the conflict test (wasted if A turns out blocked)
+        if (w.cfg.rule_move_eat) warp_load_cross(w, c, lx, ly, gx, gy, a, lane, cl);
         {   // exact conflict test against the blocked set.  The zone of A is cut into segments of one bitmap row
             // each -- 2V+1 rows of the box |d| <= V, the two same-row arm extensions, and the 2a cells of the
             // same-column arm extensions -- and every lane takes segments lane, lane + 32 (windows are never
@@ -1048,7 +1092,7 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 }
             }
         } else {
-            warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
+            warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
         }
         __syncwarp();
     }
