@@ -52,7 +52,7 @@ struct ss_engine {
     // move-pass implementation: 0 = one CTA per window, a warp per region (ss_move_pass_kernel);
     // 1 = one warp per window (ss_move_solo_kernel); -1 = by window count
     int pass_impl_option = -1, pass_impl = 0;
-    int solo_window_max = 128;
+    int solo_window_max = 0;                   // 0 = by lattice size
     int shard_rank = 0, shard_world = 1;       // multi-GPU replicas (sharded.py)
     int shard_pass = 0;
     int last_passes = 4;
@@ -235,8 +235,18 @@ static int choose_path(ss_engine* e) {
         PassGeom gs{};
         int ntile_s = 1, emin_s = 0;
         // the solo kernel needs many windows to fill the GPU (one warp each, 32 per SM) and window coordinates < 256
-        const bool solo_ok = tiling(std::max(32, std::min(e->solo_window_max, 176)), &gs, &ntile_s, &emin_s) && gs.nwin > 1 &&
-                             ss_solo_smem_bytes(gs.emax, gs.ew) <= 48 * 1024;
+        auto solo_tiling = [&](int wmax) {
+            return tiling(wmax, &gs, &ntile_s, &emin_s) && gs.nwin > 1 && ss_solo_smem_bytes(gs.emax, gs.ew) <= 48 * 1024;
+        };
+        bool solo_ok = false;
+        if (e->solo_window_max > 0) {
+            solo_ok = solo_tiling(std::max(32, std::min(e->solo_window_max, 176)));
+        } else {
+            // largest window that still leaves ~17 windows per SM; small lattices take the smallest window that tiles
+            const int sizes[5] = {128, 112, 96, 80, 64};
+            for (int k = 0; k < 5 && !solo_ok; k++)
+                solo_ok = solo_tiling(sizes[k]) && ((long long)gs.nwin * gs.nwin >= 17ll * e->sm_count || k == 4);
+        }
         const bool want_solo = e->pass_impl_option == 1 ||
                                (e->pass_impl_option < 0 && solo_ok && (long long)gs.nwin * gs.nwin >= 8ll * e->sm_count);
         if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = 1; }

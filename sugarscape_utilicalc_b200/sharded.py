@@ -63,8 +63,10 @@ class _DevView:
 class ShardRank:
     """One rank's replica: an Engine plus the shard entry points of the C-ABI."""
 
-    def __init__(self, cfg, rank, world, device=0):
+    def __init__(self, cfg, rank, world, device=0, options=None):
         self.eng = Engine(cfg, device=device)
+        for k, v in (options or {}).items():
+            self.eng.set_option(k, v)
         self.rank, self.world = rank, world
         self._lib = capi.lib()
 
@@ -108,8 +110,8 @@ class VirtualRanks:
     """P replicas in one process on one GPU: the N>1 code path without NCCL (log slices are handed over
     as device pointers).  Same interface as Engine for the parity tests."""
 
-    def __init__(self, cfg, world, device=0):
-        self.ranks = [ShardRank(cfg, r, world, device) for r in range(world)]
+    def __init__(self, cfg, world, device=0, options=None):
+        self.ranks = [ShardRank(cfg, r, world, device, options) for r in range(world)]
         self.world = world
         self.passes = 0
 
