@@ -848,7 +848,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 // the sorted key list and the blocked bitmap.
 #define SOLO_LIST 1024
 #ifndef SOLO_MIN_CTAS
-#define SOLO_MIN_CTAS 24
+#define SOLO_MIN_CTAS 25
 #endif
 __global__ void __launch_bounds__(32, SOLO_MIN_CTAS)
 ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
@@ -865,8 +865,9 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     c.occw = w.occw; c.isugar = w.isugar;
     c.n = n; c.ex = x_hi - x_lo; c.ey = y_hi - y_lo; c.emax = g.emax;
     c.gx0 = x_lo + g.shift_x; c.gy0 = y_lo + g.shift_y;
-    uint64_t* list = (uint64_t*)smem;                       // [SOLO_LIST] priority << 24 | lx << 16 | ly << 8 | vision + flags
-    uint32_t* blk_bits = smem + 2 * SOLO_LIST;              // [emax][ew]
+    uint32_t* keys = smem;                                  // [SOLO_LIST] priority << 7 | vision + flags (sort key)
+    uint32_t* blk_bits = smem + SOLO_LIST;                  // [emax][ew]
+    uint16_t* poss = (uint16_t*)(blk_bits + g.emax * g.ew); // [SOLO_LIST] lx << 8 | ly, permuted with the keys
     const int ew = g.ew;
     const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
     const int nb = w.pend_nb;
@@ -954,14 +955,14 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                     if (ow == 0u || (ow >> 31) != cur_phase) continue;
                     const int ly = ly0 + j;
                     if (!in_core(c, lx, ly, R)) { ringbits |= 1u << (ly & 31); continue; }
-                    uint64_t key = ((uint64_t)ow << 16) | (uint64_t)((lx << 8) | ly);      // first scan: hashed below
+                    uint32_t key = ow;                                      // first scan: hashed below
                     if (!first) {
                         const uint32_t p = ss_priority(ok, occ_slot(ow));
                         if (p >= thr) continue;
-                        key = ((uint64_t)p << 24) | (uint64_t)((lx << 16) | (ly << 8) | (int)((ow >> 24) & 0x7fu));
+                        key = (p << 7) | ((ow >> 24) & 0x7fu);
                     }
                     const int at = atomicAdd(&cnt_s, 1);
-                    if (at < SOLO_LIST) list[at] = key;
+                    if (at < SOLO_LIST) { keys[at] = key; poss[at] = (uint16_t)((lx << 8) | ly); }
                 }
                 if (first && ringbits) atomicOr(&blk_bits[lx * ew + (ly0 >> 5)], ringbits);
             }
@@ -977,7 +978,7 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
             first = false;
             // lowest priority among the SOLO_LIST agents that made it into the list (>= the lowest pending one)
             for (int i = lane; i < SOLO_LIST; i += 32) {
-                const uint32_t p = ss_priority(ok, occ_slot((uint32_t)(list[i] >> 16)));
+                const uint32_t p = ss_priority(ok, occ_slot(keys[i]));
                 pmin = p < pmin ? p : pmin;
             }
             p0 = __reduce_min_sync(FULL, pmin);
@@ -994,24 +995,26 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     if (n_mine == 0) { write_map(); return; }
     if (first) {        // every pending core agent is listed: hash them now, 32 at a time
         for (int i = lane; i < n_mine; i += 32) {
-            const uint64_t raw = list[i];
-            const uint32_t ow = (uint32_t)(raw >> 16);
-            list[i] = ((uint64_t)ss_priority(ok, occ_slot(ow)) << 24) | (uint64_t)((((uint32_t)raw & 0xff00u) << 8) | (((uint32_t)raw & 0xffu) << 8) | ((ow >> 24) & 0x7fu));
+            const uint32_t ow = keys[i];
+            keys[i] = (ss_priority(ok, occ_slot(ow)) << 7) | ((ow >> 24) & 0x7fu);
         }
         __syncwarp();
     }
     {   // bitonic sort of the keys (unique), padded to a power of two
         int P = 32;
         while (P < n_mine) P <<= 1;
-        for (int i = n_mine + lane; i < P; i += 32) list[i] = ~0ull;
+        for (int i = n_mine + lane; i < P; i += 32) keys[i] = 0xffffffffu;
         __syncwarp();
         for (int k = 2; k <= P; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int i = lane; i < (P >> 1); i += 32) {
                     const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
-                    const uint64_t x = list[lo], y = list[hi];
+                    const uint32_t x = keys[lo], y = keys[hi];
                     const bool up = (lo & k) == 0;
-                    if ((x > y) == up) { list[lo] = y; list[hi] = x; }
+                    if ((x > y) == up) {
+                        keys[lo] = y; keys[hi] = x;
+                        const uint16_t t = poss[lo]; poss[lo] = poss[hi]; poss[hi] = t;
+                    }
                 }
                 __syncwarp();
             }
@@ -1021,9 +1024,9 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     for (int it = 0; it < n_mine; it++) {
         // the key carries everything of the agent's occupancy word: the slot is the inverse of the priority, and
         // nobody else changes the word before the agent's own turn
-        const uint64_t key = list[it];
-        const uint32_t pa = (uint32_t)(key >> 24);
-        const int lx = (int)((key >> 16) & 255u), ly = (int)((key >> 8) & 255u);
+        const uint32_t key = keys[it];
+        const uint32_t pa = key >> 7;
+        const int lx = (int)(poss[it] >> 8), ly = (int)(poss[it] & 255u);
         const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
         const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | ss_priority_inverse(ok, pa);
         const int a = occ_vision(ow);
@@ -1698,7 +1701,7 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
     return cudaGetLastError();
 }
 
-size_t ss_solo_smem_bytes(int emax, int ew) { return (size_t)SOLO_LIST * 8 + (size_t)emax * ew * 4; }
+size_t ss_solo_smem_bytes(int emax, int ew) { return (size_t)SOLO_LIST * 6 + (size_t)emax * ew * 4; }
 cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s) {
     if (g.bx_cnt <= 0) return cudaSuccess;
