@@ -152,18 +152,19 @@ struct Choice { int lr, lq, sg; };
 // The loads of one agent's cross, issued ahead of their use (the warp-per-window kernel overlaps them with its
 // conflict test): per lane the occupancy word, int(sugar) and -- lattice-direct windows with the pollution rule --
 // the pollution of its two candidates, plus the agent's own cell.
-struct CrossLoads {
-    uint32_t occ[2];
+struct CrossLoads {         // raw loaded values: nothing may depend on them before they are consumed
+    uint32_t occ[2];        // occupancy word of the candidate (1 = no candidate for this lane)
     int sg[2];
     double poll[2];
     int sg0;
     double pown;
 };
-template <class Ctx>
+// POLT: pollution rule known at compile time (0/1) or read from the configuration (-1)
+template <int POLT, class Ctx>
 __device__ static inline void warp_load_cross(const DevWorld& w, const Ctx& c, int lx, int ly, int gx, int gy, int a,
                                               int lane, CrossLoads& L) {
     const int n = c.n;
-    const bool pol = w.cfg.rule_pollution != 0;
+    const bool pol = POLT < 0 ? (w.cfg.rule_pollution != 0) : (POLT != 0);
     const int span = 2 * a + 1, K = 2 * span;
     L.sg0 = c.isug(lx, ly, gx * n + gy);
     L.pown = 0.0;
@@ -184,11 +185,11 @@ __device__ static inline void warp_load_cross(const DevWorld& w, const Ctx& c, i
     }
 }
 
-template <class Ctx>
+template <int POLT, class Ctx>
 __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int lx, int ly, int gx, int gy, int a,
                                           uint32_t slot, uint64_t skey, int lane, const CrossLoads& L) {
     const int n = c.n;
-    const bool pol = w.cfg.rule_pollution != 0;
+    const bool pol = POLT < 0 ? (w.cfg.rule_pollution != 0) : (POLT != 0);
     const int span = 2 * a + 1, K = 2 * span;
     int dist[2] = {0, 0}, cell[2] = {0, 0}, sg[2] = {0, 0}, qidx[2] = {-1, -1};
     uint32_t loc[2] = {0, 0};
@@ -278,7 +279,7 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
 // (nobody can observe them before the agent loop ends: the destination stays occupied).
 // AT-RISK agents are settled synchronously because a death frees the cell and decides the
 // successor's turn (Q1).
-template <class Ctx>
+template <int POLT, class Ctx>
 __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, int ly, uint32_t ow, uint32_t slot,
                                        int64_t iteration, int64_t env_time, uint64_t skey, uint32_t next_phase,
                                        ThreadStats& ts, int lane, const CrossLoads& L) {
@@ -292,7 +293,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
     uint32_t attr = 0;
     if (risky && lane == 0) { sugar = recp->sugar; attr = recp->attr; }   // issued early, used after the scan
     Choice ch;
-    if (w.cfg.rule_move_eat) ch = warp_choose_cell(w, c, lx, ly, gx, gy, a, slot, skey, lane, L);
+    if (w.cfg.rule_move_eat) ch = warp_choose_cell<POLT>(w, c, lx, ly, gx, gy, a, slot, skey, lane, L);
     else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
     if (lane != 0) return;
     const int cell = (ch.lr == lx && ch.lq == ly) ? pos
@@ -767,8 +768,8 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 }
             } else {
                 CrossLoads cl;
-                if (w.cfg.rule_move_eat) warp_load_cross(w, c, lx, ly, ss_wrap1(c.gx0 + lx, n), ss_wrap1(c.gy0 + ly, n), a, lane, cl);
-                warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
+                if (w.cfg.rule_move_eat) warp_load_cross<-1>(w, c, lx, ly, ss_wrap1(c.gx0 + lx, n), ss_wrap1(c.gy0 + ly, n), a, lane, cl);
+                warp_agent_turn<-1>(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
                 n_turns++;
             }
             t_turn += PASS_CLOCK() - t_m;
@@ -850,6 +851,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 #ifndef SOLO_MIN_CTAS
 #define SOLO_MIN_CTAS 25
 #endif
+template <int POLT>
 __global__ void __launch_bounds__(32, SOLO_MIN_CTAS)
 ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -1031,8 +1033,10 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | ss_priority_inverse(ok, pa);
         const int a = occ_vision(ow);
         bool blocked = false;
-        CrossLoads cl;              // issued now, consumed after the conflict test (wasted if A turns out blocked)
-        if (w.cfg.rule_move_eat) warp_load_cross(w, c, lx, ly, gx, gy, a, lane, cl);
+        // A's cross: loads issued now, consumed after the conflict test (wasted if A turns out blocked).  Issuing them
+        // a whole turn earlier (when the previous agent's cross cannot meet A's) was measured and is slower.
+        CrossLoads cl;
+        if (w.cfg.rule_move_eat) warp_load_cross<POLT>(w, c, lx, ly, gx, gy, a, lane, cl);
         {   // exact conflict test against the blocked set.  The zone of A is cut into segments of one bitmap row
             // each -- 2V+1 rows of the box |d| <= V, the two same-row arm extensions, and the 2a cells of the
             // same-column arm extensions -- and every lane takes segments lane, lane + 32 (windows are never
@@ -1095,7 +1099,7 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
                 }
             }
         } else {
-            warp_agent_turn(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
+            warp_agent_turn<POLT>(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
         }
         __syncwarp();
     }
@@ -1705,7 +1709,10 @@ size_t ss_solo_smem_bytes(int emax, int ew) { return (size_t)SOLO_LIST * 6 + (si
 cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s) {
     if (g.bx_cnt <= 0) return cudaSuccess;
-    ss_move_solo_kernel<<<g.nwin * g.bx_cnt, 32, ss_solo_smem_bytes(g.emax, g.ew), s>>>(w, g, iteration, env_time);
+    const size_t smem = ss_solo_smem_bytes(g.emax, g.ew);
+    const int grid = g.nwin * g.bx_cnt;
+    if (w.cfg.rule_pollution) ss_move_solo_kernel<1><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+    else ss_move_solo_kernel<0><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
     return cudaGetLastError();
 }
 
