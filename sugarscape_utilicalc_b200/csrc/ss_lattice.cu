@@ -928,45 +928,51 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     bool first = true;
     int n_mine;
     const int per = g.align == 4 ? 4 : 1;                   // cells per load
-    const int gpr = c.ey / per, total = c.ex * gpr;
-    for (;;) {
-#pragma unroll 1
-        for (int base = 0; base < total; base += 4 * 32) {
-            uint4 ov[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int idx = base + u * 32 + lane;
-                ov[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (idx < total) {
-                    const int lx = idx / gpr, ly = (idx - lx * gpr) * per;
-                    const size_t gi = (size_t)ss_wrap1(c.gx0 + lx, n) * n + ss_wrap1(c.gy0 + ly, n);
-                    if (per == 4) ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + gi));
-                    else ov[u].x = __ldcg(&w.occw[gi]);
-                }
+    const int gpr = c.ey / per;                             // loads per window row
+    // one group of `per` cells of window row lx, starting at column ly0
+    auto visit = [&](int lx, int ly0, const uint4& o) {
+        unsigned m = (o.x != 0u && (o.x >> 31) == cur_phase ? 1u : 0u) | (o.y != 0u && (o.y >> 31) == cur_phase ? 2u : 0u) |
+                     (o.z != 0u && (o.z >> 31) == cur_phase ? 4u : 0u) | (o.w != 0u && (o.w >> 31) == cur_phase ? 8u : 0u);
+        if (m == 0u) return;
+        const bool row_core = lx >= R && lx < c.ex - R;
+        uint32_t ringbits = 0u;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t ow = j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w;
+            const int ly = ly0 + j;
+            if (!(row_core && ly >= R && ly < c.ey - R)) { ringbits |= 1u << (ly & 31); continue; }
+            uint32_t key = ow;                                      // first scan: hashed below
+            if (!first) {
+                const uint32_t p = ss_priority(ok, occ_slot(ow));
+                if (p >= thr) continue;
+                key = (p << 7) | ((ow >> 24) & 0x7fu);
             }
+            const int at = atomicAdd(&cnt_s, 1);
+            if (at < SOLO_LIST) { keys[at] = key; poss[at] = (uint16_t)((lx << 8) | ly); }
+        }
+        if (first && ringbits) atomicOr(&blk_bits[lx * ew + (ly0 >> 5)], ringbits);
+    };
+    for (;;) {
+        // four window rows per iteration (four loads in flight per lane), lanes across the row
 #pragma unroll 1
-            for (int u = 0; u < 4; u++) {
-                const uint4 o = u == 0 ? ov[0] : u == 1 ? ov[1] : u == 2 ? ov[2] : ov[3];
-                if ((o.x | o.y | o.z | o.w) == 0u) continue;
-                const int idx = base + u * 32 + lane;
-                const int lx = idx / gpr, ly0 = (idx - lx * gpr) * per;
-                uint32_t ringbits = 0u;
+        for (int lx0 = 0; lx0 < c.ex; lx0 += 4) {
 #pragma unroll 1
-                for (int j = 0; j < per; j++) {
-                    const uint32_t ow = j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w;
-                    if (ow == 0u || (ow >> 31) != cur_phase) continue;
-                    const int ly = ly0 + j;
-                    if (!in_core(c, lx, ly, R)) { ringbits |= 1u << (ly & 31); continue; }
-                    uint32_t key = ow;                                      // first scan: hashed below
-                    if (!first) {
-                        const uint32_t p = ss_priority(ok, occ_slot(ow));
-                        if (p >= thr) continue;
-                        key = (p << 7) | ((ow >> 24) & 0x7fu);
+            for (int g0 = 0; g0 < gpr; g0 += 32) {
+                const int grp = g0 + lane, ly0 = grp * per;
+                const int gyw = ss_wrap1(c.gy0 + ly0, n);
+                uint4 ov[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    ov[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (grp < gpr && lx0 + u < c.ex) {
+                        const size_t gi = (size_t)ss_wrap1(c.gx0 + lx0 + u, n) * n + gyw;
+                        if (per == 4) ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + gi));
+                        else ov[u].x = __ldcg(&w.occw[gi]);
                     }
-                    const int at = atomicAdd(&cnt_s, 1);
-                    if (at < SOLO_LIST) { keys[at] = key; poss[at] = (uint16_t)((lx << 8) | ly); }
                 }
-                if (first && ringbits) atomicOr(&blk_bits[lx * ew + (ly0 >> 5)], ringbits);
+#pragma unroll
+                for (int u = 0; u < 4; u++) visit(lx0 + u, ly0, ov[u]);
             }
         }
         __syncwarp();
