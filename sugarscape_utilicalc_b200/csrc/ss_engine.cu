@@ -245,10 +245,10 @@ static int choose_path(ss_engine* e) {
             // largest window that still leaves ~17 windows per SM; small lattices take the smallest window that tiles
             const int sizes[5] = {128, 112, 96, 80, 64};
             for (int k = 0; k < 5 && !solo_ok; k++)
-                solo_ok = solo_tiling(sizes[k]) && ((long long)gs.nwin * gs.nwin >= 17ll * e->sm_count || k == 4);
+                solo_ok = solo_tiling(sizes[k]) && ((long long)gs.nwin * gs.nwin >= 17ll * e->sm_count * e->shard_world || k == 4);
         }
         const bool want_solo = e->pass_impl_option == 1 ||
-                               (e->pass_impl_option < 0 && solo_ok && (long long)gs.nwin * gs.nwin >= 8ll * e->sm_count);
+                               (e->pass_impl_option < 0 && solo_ok && (long long)gs.nwin * gs.nwin >= 8ll * e->sm_count * e->shard_world);
         if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = 1; }
         else if (!cta_ok) lattice_ok = false;
     }
@@ -714,6 +714,11 @@ extern "C" int ss_shard_enable(ss_engine* e, int32_t rank, int32_t world) {
     static_assert(sizeof(ShardLogEntry) == SS_SHARD_ENTRY_BYTES, "log entry size");
     CK(cudaSetDevice(e->device));
     e->shard_rank = rank; e->shard_world = world;
+    {   // the window size depends on the number of windows per rank (same choice on every rank)
+        const int rc = choose_path(e);
+        if (rc) return rc;
+        if (e->path != PATH_LATTICE) return set_err(e, SS_ERR_STATE, "sharding needs the lattice path");
+    }
     if (!e->w.log) {
         e->w.log_cap = 8ull * e->w.n_slots + 4096;     // warps reserve 8 entries at a time: <= 7 unused per valid one
         CK(cudaMalloc(&e->w.log, sizeof(ShardLogEntry) * (size_t)e->w.log_cap));

@@ -165,14 +165,14 @@ class VirtualRanks:
 class DistributedEngine:
     """One rank of a torchrun job (backend nccl).  Interface of Engine.step()."""
 
-    def __init__(self, cfg, device=None):
+    def __init__(self, cfg, device=None, options=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = int(os.environ.get("LOCAL_RANK", self.rank)) if device is None else device
         torch.cuda.set_device(self.device)
-        self.r = ShardRank(cfg, self.rank, self.world, device=self.device)
+        self.r = ShardRank(cfg, self.rank, self.world, device=self.device, options=options)
         self.passes = 0
         self.bytes_sent = 0
         self.t = {"begin": 0.0, "pass": 0.0, "gather": 0.0, "apply+pending": 0.0, "end": 0.0}
@@ -247,7 +247,8 @@ def bench_main(args, wl):
         dist.barrier()
         torch.cuda.synchronize()
 
-    de = DistributedEngine(cfg, device=local)
+    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in getattr(args, "opt", [])}
+    de = DistributedEngine(cfg, device=local, options=opts)
     de.upload(w)
     pop0 = len(w["id"])
     if W:
@@ -260,22 +261,24 @@ def bench_main(args, wl):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t1 = time.perf_counter()
+    # device clock: CUDA events on the (idle) torch stream, the first right after the barrier, the second once
+    # every stream of this rank has drained -- the engine stream (kernels) and the torch stream (collectives)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     st = de.step(K)
+    torch.cuda.synchronize()
+    ev1.record()
     sync_all()
-    wall = time.perf_counter() - t1
     clocks = sampler.stop() if rank == 0 else None
-    wallt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    wallt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device="cuda")
     dist.all_reduce(wallt, op=dist.ReduceOp.MAX)
-    # the engine runs on its own stream, so the torch-stream events only bracket the collectives:
-    # the step time is the max over ranks of the host wall clock between the two barriers
     step_ms = 1e3 * float(wallt.item()) / K
     pops = np.concatenate([[pop0], st["population"][:-1]])
     value = float(pops.sum()) / (step_ms * K * 1e-3)
     # e2e: upload on every rank + K steps + download on rank 0
     sync_all()
     t2 = time.perf_counter()
-    de2 = DistributedEngine(cfg, device=local)
+    de2 = DistributedEngine(cfg, device=local, options=opts)
     de2.upload(w)
     Ke = min(K, args.e2e_steps)
     ste = de2.step(Ke)
@@ -294,11 +297,13 @@ def bench_main(args, wl):
             "data": "synthetic",
             "config": {"workload": wl["label"], "grid": n, "agents": len(w["id"]),
                        "parallelism": "replicated lattice, window rows sharded over %d ranks, turn logs all-gathered (NCCL)" % world,
-                       "timing": "max over ranks of the wall clock between two barrier+synchronize pairs around K steps",
+                       "timing": "max over ranks of the CUDA-event interval (device clock) from the barrier before the K steps to the drain of all of the rank's streams after them",
                        "l2": "working set >> 126 MB L2"},
             "cell_updates_per_s": n * n * K / (step_ms * K * 1e-3),
             "population": [int(pop0), int(st["population"][-1])],
             "passes_per_step": (de.passes - p0) / K, "gpu_launches": de.r.eng.counters()["launches"] - l0,
+            "move_pass": {"impl": ["cta_per_window", "warp_per_window"][de.r.eng.counters()["pass_impl"]],
+                          "window": de.r.eng.counters()["window"]},
             "nccl_bytes_sent_per_rank_per_step": (de.bytes_sent - b0) / K,
             "rank0_ms_per_step": {k: 1e3 * v / K for k, v in de.t.items()},
             "e2e": {"value": float(popse.sum()) / float(e2e_s.item()), "unit": "agent-steps/s",
