@@ -186,7 +186,8 @@ def run_engine_single(args, wl):
     kernels["prepare+stats"] = {"ms_per_step": (kt["prepare"] + kt["stats"]) / K,
                                 "share": (kt["prepare"] + kt["stats"]) / tot}
     dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
-    roofline = {"bound": "hbm", "kernel": {"move": "ss_move_pass_kernel (all passes of a step) + ss_settle_kernel",
+    move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel"][cnt["pass_impl"]]
+    roofline = {"bound": "hbm", "kernel": {"move": move_kernel + " (all passes of a step) + ss_settle_kernel",
                                            "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
