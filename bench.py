@@ -210,7 +210,11 @@ def run_engine_single(args, wl):
     t0 = time.perf_counter()
     eng = Engine(cfg)
     t1 = time.perf_counter()
-    upload(eng, hw)
+    for k, v in ENGINE_OPTS.items():
+        eng.set_option(k, v)
+    eng.upload_cells(hw["sugar"], hw["cap"], hw["pollution"])
+    t1b = time.perf_counter()
+    eng.upload_agents(hw["id"], hw["x"], hw["y"], hw["vision"], hw["metab"], hw["sugar_agent"])
     t2 = time.perf_counter()
     ste = eng.step(Ke)                       # per-step stats are read back to the host
     t3 = time.perf_counter()
@@ -223,7 +227,7 @@ def run_engine_single(args, wl):
     e2e_value = float(popse.sum()) / t_e2e
     h2d = (3 * 8 * n * n + 28 * len(w["id"])) / Ke                 # sugar, cap, pollution + six agent columns
     d2h = ((2 * 8 + 4) * n * n + 28 * len(ags["id"]) + 48 * Ke) / Ke
-    e2e_parts = {"create": t1 - t0, "upload": t2 - t1, "steps": t3 - t2, "download": t4 - t3}
+    e2e_parts = {"create": t1 - t0, "upload_cells": t1b - t1, "upload_agents": t2 - t1b, "steps": t3 - t2, "download": t4 - t3}
     del cells, ags, hw, hout, aout
     # ---------------- cpu baseline: oracle port on a bounded sample ----------------
     cpu = None

@@ -19,6 +19,8 @@ cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s);
+cudaError_t ss_launch_validate_agents(int n, int N, const int32_t* id, const int32_t* x, const int32_t* y, const int32_t* vision,
+                                      const int32_t* metab, int* out3, cudaStream_t s);
 uint32_t ss_export_blocks(uint32_t domain);
 cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32_t* blockcnt, uint32_t* total, int32_t* cols,
                                     size_t stride, double* sugar, cudaStream_t s);
@@ -65,7 +67,7 @@ struct ss_engine {
     int trace = 0;
     bool cap_fits_u8 = true;
     unsigned long long* h_pending = nullptr;   // pinned
-    std::vector<int32_t> upload_order;          // slots in upload order
+    int n_uploaded = 0;                        // agents of the last upload (w.order holds their slots in list order)
     int64_t launches = 0, passes = 0, steps = 0, syncs = 0;
     bool profile = false;
     double kt[KT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -281,17 +283,37 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
         return set_err(e, SS_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));
     const int N = e->w.n;
-    int32_t max_id = 0;
-    int vmax = 1;
-    for (int i = 0; i < n; i++) {
-        if (id[i] < 1) return set_err(e, SS_ERR_ARG, "agent ids must be >= 1");
-        max_id = std::max(max_id, id[i]);
-        if (vision[i] < 1 || vision[i] > SS_MAX_VISION) return set_err(e, SS_ERR_UNSUPPORTED, "vision out of range [1,31]");
-        if (2 * vision[i] + 1 > N) return set_err(e, SS_ERR_UNSUPPORTED, "2*vision+1 exceeds the grid size");
-        if (metab[i] < 1 || metab[i] > 65535) return set_err(e, SS_ERR_ARG, "metabolism out of range [1,65535]");
-        if (x[i] < 0 || x[i] >= N || y[i] < 0 || y[i] >= N) return set_err(e, SS_ERR_ARG, "agent off the grid");
-        vmax = std::max(vmax, vision[i]);
+    // stage the six View.agents columns; argument checks, the agent store and the occupancy words are built on the device
+    const size_t nn = (size_t)std::max(n, 1);
+    int32_t* d_i32 = nullptr;
+    double* d_f64 = nullptr;
+    int* d_chk = nullptr;
+    struct Staging {        // freed on every exit
+        int32_t*& a; double*& b; int*& c;
+        ~Staging() { cudaFree(a); cudaFree(b); cudaFree(c); }
+    } staging{d_i32, d_f64, d_chk};
+    CK(cudaMalloc(&d_i32, sizeof(int32_t) * 5 * nn));
+    CK(cudaMalloc(&d_f64, sizeof(double) * nn));
+    CK(cudaMalloc(&d_chk, sizeof(int) * 4));
+    const int32_t* cols[5] = {id, x, y, vision, metab};
+    for (int k = 0; k < 5 && n > 0; k++)
+        CK(cudaMemcpyAsync(d_i32 + k * nn, cols[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    if (n > 0) CK(cudaMemcpyAsync(d_f64, sugar, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    int chk[4] = {0, 0, 1, 0};
+    CK(cudaMemcpyAsync(d_chk, chk, sizeof chk, cudaMemcpyHostToDevice, e->stream));
+    CK(ss_launch_validate_agents(n, N, d_i32, d_i32 + nn, d_i32 + 2 * nn, d_i32 + 3 * nn, d_i32 + 4 * nn, d_chk, e->stream));
+    CK(cudaMemcpyAsync(chk, d_chk, sizeof chk, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    switch (chk[0]) {
+        case 0: break;
+        case 3: return set_err(e, SS_ERR_ARG, "agent ids must be >= 1");
+        case 4: return set_err(e, SS_ERR_UNSUPPORTED, "vision out of range [1,31]");
+        case 5: return set_err(e, SS_ERR_UNSUPPORTED, "2*vision+1 exceeds the grid size");
+        case 6: return set_err(e, SS_ERR_ARG, "metabolism out of range [1,65535]");
+        default: return set_err(e, SS_ERR_ARG, "agent off the grid");
     }
+    const int32_t max_id = chk[1];
+    const int vmax = std::max(chk[2], 1);
     if ((uint32_t)max_id > SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^24");
     const uint32_t ns = (uint32_t)std::max(max_id, 1);
     const uint32_t phase = (uint32_t)(e->iteration & 1);
@@ -302,16 +324,7 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
     CK(cudaMalloc(&e->w.order, sizeof(int32_t) * ns));
     CK(cudaMalloc(&e->w.wealth, sizeof(double) * P));
     CK(cudaMalloc(&e->w.sortkeys, sizeof(unsigned long long) * P));
-    {   // stage the six View.agents columns and build the agent store + occupancy words on the device
-        const size_t nn = (size_t)std::max(n, 1);
-        int32_t* d_i32 = nullptr;
-        double* d_f64 = nullptr;
-        CK(cudaMalloc(&d_i32, sizeof(int32_t) * 5 * nn));
-        CK(cudaMalloc(&d_f64, sizeof(double) * nn));
-        const int32_t* cols[5] = {id, x, y, vision, metab};
-        for (int k = 0; k < 5 && n > 0; k++)
-            CK(cudaMemcpyAsync(d_i32 + k * nn, cols[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-        if (n > 0) CK(cudaMemcpyAsync(d_f64, sugar, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    {
         CK(cudaMemsetAsync(e->w.agents, 0, sizeof(AgentRec) * ns, e->stream));
         CK(cudaMemsetAsync(e->w.occw, 0, sizeof(uint32_t) * e->cells, e->stream));
         CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
@@ -325,17 +338,13 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
         acc.population = (unsigned long long)n;
         CK(cudaMemcpyAsync(e->w.acc, &acc, sizeof acc, cudaMemcpyHostToDevice, e->stream));
         CK(cudaStreamSynchronize(e->stream));
-        cudaFree(d_i32);
-        cudaFree(d_f64);
         if (err == 1) return set_err(e, SS_ERR_ARG, "duplicate agent id");
         if (err == 2) return set_err(e, SS_ERR_ARG, "two agents on one cell");
     }
-    std::vector<int32_t> order((size_t)n);
-    for (int i = 0; i < n; i++) order[i] = id[i] - 1;
     e->w.n_slots = ns;
     e->w.half = ss_order_half_bits(ns);
     e->w.vmax = vmax;
-    e->upload_order.swap(order);
+    e->n_uploaded = n;
     e->have_agents = true;
     e->stepped = false;
     return choose_path(e);
@@ -534,7 +543,9 @@ static int fetch_population(ss_engine* e, std::vector<AgentRec>* recs_out, std::
     } else {
         CK(cudaStreamSynchronize(e->stream));
         if (!e->stepped) {
-            for (int32_t s : e->upload_order) if (attr_alive(recs[s].attr)) order.push_back(s);
+            std::vector<int32_t> up((size_t)e->n_uploaded);            // list order of the upload
+            if (e->n_uploaded) CK(cudaMemcpy(up.data(), e->w.order, sizeof(int32_t) * up.size(), cudaMemcpyDeviceToHost));
+            for (int32_t s : up) if (attr_alive(recs[s].attr)) order.push_back(s);
         } else {
             const OrderKey ok = ss_order_key(ss_step_key(e->cfg.keyed_seed, e->iteration - 1), e->w.half);
             std::vector<uint64_t> keyed, tmp;

@@ -1540,6 +1540,29 @@ __global__ void ss_build_agents_kernel(int n, int N, uint32_t phase, const int32
     recs[s].pos = c;
     order[i] = (int32_t)s;
 }
+// argument checks of ss_upload_agents on the staged columns: out[0] = error code (0 ok), out[1] = max id, out[2] = max vision
+__global__ void ss_validate_agents_kernel(int n, int N, const int32_t* __restrict__ id, const int32_t* __restrict__ x,
+                                          const int32_t* __restrict__ y, const int32_t* __restrict__ vision,
+                                          const int32_t* __restrict__ metab, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int err = 0, mid = 0, mv = 0;
+    if (i < n) {
+        if (id[i] < 1) err = 3;
+        else if (vision[i] < 1 || vision[i] > SS_MAX_VISION) err = 4;
+        else if (2 * vision[i] + 1 > N) err = 5;
+        else if (metab[i] < 1 || metab[i] > 65535) err = 6;
+        else if (x[i] < 0 || x[i] >= N || y[i] < 0 || y[i] >= N) err = 7;
+        mid = id[i]; mv = vision[i];
+    }
+    err = __reduce_max_sync(0xffffffffu, err);
+    mid = __reduce_max_sync(0xffffffffu, mid);
+    mv = __reduce_max_sync(0xffffffffu, mv);
+    if ((threadIdx.x & 31) == 0) {
+        if (err) atomicMax(&out[0], err);
+        atomicMax(&out[1], mid);
+        atomicMax(&out[2], mv);
+    }
+}
 __global__ void ss_occ_ids_kernel(const uint32_t* __restrict__ occw, int32_t* __restrict__ ids, size_t cells) {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
         const uint32_t w = occw[c];
@@ -1663,6 +1686,11 @@ cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32
     ss_export_scan_kernel<<<1, 1024, 0, s>>>(blockcnt, nb, total);
     ss_export_emit_kernel<<<nb, EXPORT_THREADS, 0, s>>>(w.agents, ok, w.n_slots, domain, w.n, blockcnt, cols, cols + stride,
                                                        cols + 2 * stride, cols + 3 * stride, cols + 4 * stride, sugar);
+    return cudaGetLastError();
+}
+cudaError_t ss_launch_validate_agents(int n, int N, const int32_t* id, const int32_t* x, const int32_t* y, const int32_t* vision,
+                                      const int32_t* metab, int* out3, cudaStream_t s) {
+    if (n > 0) ss_validate_agents_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, N, id, x, y, vision, metab, out3);
     return cudaGetLastError();
 }
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s) {
