@@ -94,10 +94,13 @@ struct WinCtx {
     __device__ inline int isug(int r, int q, int) const { return (int)isug_s[r * emax + q]; }
     __device__ inline void put_occ(int r, int q, uint32_t v) const { occ_s[r * emax + q] = v; }
     __device__ inline void clear_isug(int r, int q) const { isug_s[r * emax + q] = 0; }
+    __device__ static inline int gw(int v, int n) { return ss_wrap1(v, n); }      // lattice coordinate on the torus
     static constexpr bool kGlobal = false;
 };
 // The same window read straight from the lattice in HBM/L2 (ss_move_solo_kernel: one warp owns the whole window,
-// so nothing else touches its cells during the launch); stores go to the lattice only.
+// so nothing else touches its cells during the launch); stores go to the lattice only.  WRAP = the window straddles
+// the torus edge; all other windows (almost all) skip the coordinate wraps.
+template <bool WRAP>
 struct GlobCtx {
     const uint32_t* occw;
     const uint8_t* isugar;
@@ -109,6 +112,7 @@ struct GlobCtx {
     __device__ inline int isug(int, int, int cell) const { return (int)__ldcg(&isugar[cell]); }
     __device__ inline void put_occ(int, int, uint32_t) const {}
     __device__ inline void clear_isug(int, int) const {}
+    __device__ static inline int gw(int v, int n) { return WRAP ? ss_wrap1(v, n) : v; }
     static constexpr bool kGlobal = true;
 };
 template <class Ctx> __device__ static inline int wrap_row(const Ctx& c, int r) { return c.full_x ? ss_wrap1(r, c.ex) : r; }
@@ -117,7 +121,7 @@ template <class Ctx> __device__ static inline bool in_core(const Ctx& c, int r, 
     return (c.full_x || (r >= R && r < c.ex - R)) && (c.full_y || (q >= R && q < c.ey - R));
 }
 template <class Ctx> __device__ static inline int cell_of(const Ctx& c, int r, int q) {
-    return ss_wrap1(c.gx0 + r, c.n) * c.n + ss_wrap1(c.gy0 + q, c.n);
+    return Ctx::gw(c.gx0 + r, c.n) * c.n + Ctx::gw(c.gy0 + q, c.n);
 }
 
 // crosses of A (vision a) and B (vision b, displaced by dx,dy) share a cell
@@ -175,8 +179,8 @@ __device__ static inline void warp_load_cross(const DevWorld& w, const Ctx& c, i
         L.occ[h] = 1u; L.sg[h] = 0; L.poll[h] = 0.0;
         if (k < K) {
             int r, q, cx, cy;
-            if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap1(gx + o, n); cy = gy; }
-            else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap1(gy + o, n); }
+            if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = Ctx::gw(gx + o, n); cy = gy; }
+            else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = Ctx::gw(gy + o, n); }
             const int ci = cx * n + cy;
             L.occ[h] = c.occ(r, q, ci);
             L.sg[h] = c.isug(r, q, ci);
@@ -203,8 +207,8 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
         if (h * 32 < K) {
             if (k < K && L.occ[h] == 0u) {
                 int r, q, cx, cy;
-                if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = ss_wrap1(gx + o, n); cy = gy; }
-                else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = ss_wrap1(gy + o, n); }
+                if (k < span) { const int o = k - a; r = wrap_row(c, lx + o); q = ly; cx = Ctx::gw(gx + o, n); cy = gy; }
+                else { const int o = k - span - a; r = lx; q = wrap_col(c, ly + o); cx = gx; cy = Ctx::gw(gy + o, n); }
                 fr = true;
                 loc[h] = (uint32_t)(r << 8 | q); cell[h] = cx * n + cy; sg[h] = L.sg[h];
                 dist[h] = abs(gx - cx) + abs(gy - cy);                       // agent.py:867-868
@@ -285,7 +289,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
                                        ThreadStats& ts, int lane, const CrossLoads& L) {
     const int n = c.n;
     const int a = occ_vision(ow);
-    const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
+    const int gx = Ctx::gw(c.gx0 + lx, n), gy = Ctx::gw(c.gy0 + ly, n);
     const int pos = gx * n + gy;
     const bool risky = (ow & OCC_RISK) != 0;
     AgentRec* recp = &w.agents[slot];
@@ -297,7 +301,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
     else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
     if (lane != 0) return;
     const int cell = (ch.lr == lx && ch.lq == ly) ? pos
-                   : ss_wrap1(c.gx0 + ch.lr, n) * n + ss_wrap1(c.gy0 + ch.lq, n);
+                   : Ctx::gw(c.gx0 + ch.lr, n) * n + Ctx::gw(c.gy0 + ch.lq, n);
     uint32_t new_word = occ_pack(slot, a, next_phase);
     ts.resolved++;
     if (!risky) {
@@ -851,22 +855,16 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 #ifndef SOLO_MIN_CTAS
 #define SOLO_MIN_CTAS 25
 #endif
-template <int POLT>
-__global__ void __launch_bounds__(32, SOLO_MIN_CTAS)
-ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int cnt_s;
+template <int POLT, bool WRAP>
+__device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
+                                            uint32_t* smem, int& cnt_s, int gx0, int gy0, int ex, int ey) {
+    typedef GlobCtx<WRAP> GC;
     const int n = w.n, lane = threadIdx.x;
-    if (*((volatile unsigned long long*)&w.acc->pending) == 0ull) return;
-    const int bx = g.bx_lo + (int)blockIdx.x / g.nwin, by = (int)blockIdx.x % g.nwin;
-    const int nu = n / g.align;
-    const int x_lo = g.align * (int)(((long long)bx * nu) / g.nwin), x_hi = g.align * (int)(((long long)(bx + 1) * nu) / g.nwin);
-    const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
     const int V = w.vmax, R = g.ring;
-    GlobCtx c;
+    GC c;
     c.occw = w.occw; c.isugar = w.isugar;
-    c.n = n; c.ex = x_hi - x_lo; c.ey = y_hi - y_lo; c.emax = g.emax;
-    c.gx0 = x_lo + g.shift_x; c.gy0 = y_lo + g.shift_y;
+    c.n = n; c.ex = ex; c.ey = ey; c.emax = g.emax;
+    c.gx0 = gx0; c.gy0 = gy0;
     uint32_t* keys = smem;                                  // [SOLO_LIST] priority << 7 | vision + flags (sort key)
     uint32_t* blk_bits = smem + SOLO_LIST;                  // [emax][ew]
     uint16_t* poss = (uint16_t*)(blk_bits + g.emax * g.ew); // [SOLO_LIST] lx << 8 | ly, permuted with the keys
@@ -960,13 +958,13 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 #pragma unroll 1
             for (int g0 = 0; g0 < gpr; g0 += 32) {
                 const int grp = g0 + lane, ly0 = grp * per;
-                const int gyw = ss_wrap1(c.gy0 + ly0, n);
+                const int gyw = GC::gw(c.gy0 + ly0, n);
                 uint4 ov[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     ov[u] = make_uint4(0u, 0u, 0u, 0u);
                     if (grp < gpr && lx0 + u < c.ex) {
-                        const size_t gi = (size_t)ss_wrap1(c.gx0 + lx0 + u, n) * n + gyw;
+                        const size_t gi = (size_t)GC::gw(c.gx0 + lx0 + u, n) * n + gyw;
                         if (per == 4) ov[u] = __ldcg(reinterpret_cast<const uint4*>(w.occw + gi));
                         else ov[u].x = __ldcg(&w.occw[gi]);
                     }
@@ -1035,7 +1033,7 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         const uint32_t key = keys[it];
         const uint32_t pa = key >> 7;
         const int lx = (int)(poss[it] >> 8), ly = (int)(poss[it] & 255u);
-        const int gx = ss_wrap1(c.gx0 + lx, n), gy = ss_wrap1(c.gy0 + ly, n);
+        const int gx = GC::gw(c.gx0 + lx, n), gy = GC::gw(c.gy0 + ly, n);
         const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | ss_priority_inverse(ok, pa);
         const int a = occ_vision(ow);
         bool blocked = false;
@@ -1123,6 +1121,23 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
         if (ts.inexact) atomicAdd(&w.acc->inexact, (unsigned long long)ts.inexact);
         if (ts.resolved) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)ts.resolved));
     }
+}
+
+template <int POLT>
+__global__ void __launch_bounds__(32, SOLO_MIN_CTAS)
+ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int cnt_s;
+    const int n = w.n;
+    if (*((volatile unsigned long long*)&w.acc->pending) == 0ull) return;
+    const int bx = g.bx_lo + (int)blockIdx.x / g.nwin, by = (int)blockIdx.x % g.nwin;
+    const int nu = n / g.align;
+    const int x_lo = g.align * (int)(((long long)bx * nu) / g.nwin), x_hi = g.align * (int)(((long long)(bx + 1) * nu) / g.nwin);
+    const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
+    const int ex = x_hi - x_lo, ey = y_hi - y_lo;
+    const int gx0 = ss_wrap1(x_lo + g.shift_x, n), gy0 = ss_wrap1(y_lo + g.shift_y, n);
+    if (gx0 + ex > n || gy0 + ey > n) solo_window<POLT, true>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
+    else solo_window<POLT, false>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
 }
 
 // -------------------------------------------------------------------- multi-GPU replicas ----
