@@ -201,10 +201,13 @@ def run_engine_single(args, wl):
     from sugarscape_utilicalc_b200.engine import pinned_copy, pinned_empty
     Ke = min(K, args.e2e_steps)
     cell_keys, agent_keys = ("sugar", "cap", "pollution"), ("id", "x", "y", "vision", "metab")
-    hw = {k: pinned_copy(w[k], np.float64) for k in cell_keys}
+    pol_on = bool(wl["pollution"])      # without the pollution rule the slot is all zeros: passed as NULL, not downloaded
+    hw = {k: (pinned_copy(w[k], np.float64) if (k != "pollution" or pol_on) else None) for k in cell_keys}
     hw.update({k: pinned_copy(w[k], np.int32) for k in agent_keys})
     hw["sugar_agent"] = pinned_copy(w["sugar_agent"], np.float64)
-    hout = dict(sugar=pinned_empty((n, n)), pollution=pinned_empty((n, n)), occ=pinned_empty((n, n), np.int32))
+    hout = dict(sugar=pinned_empty((n, n)), occ=pinned_empty((n, n), np.int32))
+    if pol_on:
+        hout["pollution"] = pinned_empty((n, n))
     aout = {k: pinned_empty(len(w["id"]), np.int32) for k in agent_keys}
     aout["sugar"] = pinned_empty(len(w["id"]), np.float64)
     t0 = time.perf_counter()
@@ -218,15 +221,16 @@ def run_engine_single(args, wl):
     t2 = time.perf_counter()
     ste = eng.step(Ke)                       # per-step stats are read back to the host
     t3 = time.perf_counter()
-    cells = eng.download_cells(cap=False, out=hout)
+    cells = eng.download_cells(cap=False, pollution=pol_on, out=hout)
     ags = eng.download_agents(out=aout)
     t4 = time.perf_counter()
     t_e2e = t4 - t0
     eng.close()
     popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
     e2e_value = float(popse.sum()) / t_e2e
-    h2d = (3 * 8 * n * n + 28 * len(w["id"])) / Ke                 # sugar, cap, pollution + six agent columns
-    d2h = ((2 * 8 + 4) * n * n + 28 * len(ags["id"]) + 48 * Ke) / Ke
+    ncell_arrays = 3 if pol_on else 2                             # sugar, cap (, pollution) + six agent columns
+    h2d = (ncell_arrays * 8 * n * n + 28 * len(w["id"])) / Ke
+    d2h = (((ncell_arrays - 1) * 8 + 4) * n * n + 28 * len(ags["id"]) + 48 * Ke) / Ke       # sugar (, pollution), occupant ids
     e2e_parts = {"create": t1 - t0, "upload_cells": t1b - t1, "upload_agents": t2 - t1b, "steps": t3 - t2, "download": t4 - t3}
     del cells, ags, hw, hout, aout
     # ---------------- cpu baseline: oracle port on a bounded sample ----------------
@@ -253,7 +257,8 @@ def run_engine_single(args, wl):
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts,
                 "what": "Engine(cfg); upload_cells/agents from page-locked host numpy arrays; step(K) with stats "
-                        "read-back; download_cells+download_agents into page-locked host arrays"},
+                        "read-back; download_cells+download_agents into page-locked host arrays (capacity is not read "
+                        "back; the pollution slot crosses the bus only when the pollution rule is on)"},
         "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": whole_bytes, "frac_of_peak": step_frac},
         "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "upload_s": t_upload,

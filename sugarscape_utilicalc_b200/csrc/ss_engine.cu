@@ -34,7 +34,8 @@ cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_t
 cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
 cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
-cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl, cudaStream_t s);
+size_t ss_diffuse_handoff_bytes(int n);
+cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, double* handoff, int impl, cudaStream_t s);
 }
 
 enum { PATH_SERIAL_FUSED = 0, PATH_SERIAL_ENV = 1, PATH_LATTICE = 2 };
@@ -60,6 +61,7 @@ struct ss_engine {
     int last_passes = 4;
     int stats_cap = 0;
     int* d_flags = nullptr;
+    double* d_handoff = nullptr;                // diffusion: last rows handed from band to band
     int sm_count = 148;
     int diffuse_impl = 0;
     int window_max = 128;
@@ -166,7 +168,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
     cudaFree(e->w.pendmap);
-    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->w.log); cudaFree(e->w.log_count);
+    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -407,7 +409,8 @@ static int env_phase(ss_engine* e) {
     if (e->cfg.rule_pollution && e->iteration >= e->cfg.diffusion_start_time &&
         e->iteration % e->cfg.diffusion_rate == 0) {                                  // sugarscape.py:661-663
         KTimer t(e, KT_DIFFUSE);
-        CK(ss_launch_diffuse(e->w, e->d_flags, e->diffuse_impl, e->stream));
+        if (!e->d_handoff) CK(cudaMalloc(&e->d_handoff, ss_diffuse_handoff_bytes(e->w.n)));
+        CK(ss_launch_diffuse(e->w, e->d_flags, e->d_handoff, e->diffuse_impl, e->stream));
         e->launches++;
     }
     return SS_OK;

@@ -249,15 +249,21 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
     }
     int left = __popc(__ballot_sync(FULL, tie0)) + __popc(__ballot_sync(FULL, tie1));
     if (left > 1) {
+        // the agent's keyed words 32 at a time (lane l holds word base + l), handed round by shuffle
         const uint64_t akey = ss_agent_key(skey, slot + 1u);
-        uint32_t j = 0;
+        uint32_t j = 0, base = 0;
+        uint32_t batch = ss_keyed_word(akey, (uint32_t)lane);
+        auto next_word = [&]() {
+            if (j - base >= 32u) { base += 32u; batch = ss_keyed_word(akey, base + (uint32_t)lane); }
+            return __shfl_sync(FULL, batch, (int)(j++ - base));
+        };
         int p0 = qidx[0], p1 = qidx[1];
         for (int i = n_free - 1; i >= 1 && left > 1; i--) {           // random.py:350 shuffle
             const uint32_t nn = (uint32_t)i + 1u;
             const int kbits = 32 - __clz(nn);
-            uint32_t rj = ss_keyed_word(akey, j++) >> (32 - kbits);  // random.py:242 _randbelow
+            uint32_t rj = next_word() >> (32 - kbits);               // random.py:242 _randbelow
             while (rj >= nn) {
-                rj = ss_keyed_word(akey, j++) >> (32 - kbits);
+                rj = next_word() >> (32 - kbits);
                 if (j > 100000u) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x3333; break; }
             }
             // the element at index rj moves to index i and is final there; L[i] moves to rj
@@ -1386,9 +1392,12 @@ ss_seasons_kernel(DevWorld w, double alpha_north, double alpha_south) {
 // x / 3.0, correctly rounded, without the long DDIV sequence on the wavefront's critical
 // path: q = RN(x*r), one FMA residual correction (Markstein); exact IEEE division outside the
 // comfortably-normal range.  Checked against x / 3.0 on the CPU (tests/ctests/div3_check.c).
+// (the IEEE fallback is a call the compiler cannot hoist or if-convert: speculated, its zero/denormal slow path
+// would run for every cell of an unpolluted region)
+__device__ static __noinline__ double div3_ieee(double x) { return x / 3.0; }
 __device__ static inline double div3(double x) {
     const double ax = fabs(x);
-    if (!(ax > 1e-280 && ax < 1e280)) return x / 3.0;
+    if (!(ax > 1e-280 && ax < 1e280)) return div3_ieee(x);
     const double r = 1.0 / 3.0;
     const double q = x * r;
     const double rem = __fma_rn(-3.0, q, x);
@@ -1439,7 +1448,7 @@ ss_diffuse_kernel(double* __restrict__ p, int n, int* ticket, int* progress) {
         const int col = 32 * ch + lane;
         if (!has_above || ch >= nchunks) return;
         const int need = min(n, 32 * (ch + 1));
-        if (lane == 0) while (ld_acquire(&progress[b - 1]) < need) { }
+        while (ld_acquire(&progress[b - 1]) < need) { }       // all lanes (same address): the warp stays converged
         __syncwarp();
         if (col < n) tile[0][col & (DIFF_RING - 1)] = __ldcg(&p[(size_t)(x0 - 1) * n + col]);
     };
@@ -1508,6 +1517,263 @@ ss_diffuse_kernel(double* __restrict__ p, int n, int* ticket, int* progress) {
     flush_chunk(nblocks - 1);
     __syncwarp();
     if (lane == 0) st_release(&progress[b], n);
+}
+
+// Column-chain wavefront.  The reference adds the four neighbours in the order n, s, e, w = (x,y+1), (x,y-1),
+// (x+1,y), (x-1,y): the NEW value of the row above enters LAST.  A thread that walks DOWN a column segment therefore
+// carries only one add and one multiply per cell on its dependent chain (res[r] = (t[r] + res[r-1]) * 0.25 with
+// t[r] = (n + s) + e known a step earlier), against three adds, a multiply and a shuffle per cell when it walks along
+// a row (ss_diffuse_kernel).  A CTA owns a band of 32 * DCOL_R rows.  Warp 0 computes: lane l owns DCOL_R consecutive
+// rows, works on column k - S*l in step k and receives the new value above its first row from lane l-1 by shuffle
+// (S = 2: the value has a whole step to travel).  DCOL_H helper warps (one per scheduler, so they never take issue
+// slots from the compute warp) keep a shared ring of old values filled with cp.async, write finished chunks back, load
+// the row above the band once the previous band (previous ticket) has published it through its global progress flag,
+// and publish this band's progress.  Producer/consumer counters live in shared memory.
+#define DCOL_R 4
+#define DCOL_ROWS (32 * DCOL_R)
+#define DCOL_H 3
+__device__ __forceinline__ double dcol_lds(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void dcol_sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+// x / 3.0 for the fast path: Markstein step in the normal range (also exact for zeros), IEEE division otherwise
+__device__ __forceinline__ double dcol_div3(double x) {
+    const double r3 = 1.0 / 3.0;
+    const double q = x * r3;
+    double d = __fma_rn(__fma_rn(-3.0, q, x), r3, q);
+    const double ax = fabs(x);
+    if (!(ax > 1e-280 && ax < 1e280) && x != 0.0) d = div3_ieee(x);
+    return d;
+}
+struct DcolState {
+    double s_prev[DCOL_R], old_cur[DCOL_R], hand[2];
+    uint32_t a_row;         // shared address of (my first row, slot 0)
+    uint32_t a_above;       // shared address of (row above the band, slot 0)
+    uint32_t off_s;         // byte offset of my current column's ring slot
+    double* out;            // lane 31: where the band below picks up my last row (column of this step)
+};
+// 32 steps of the column-chain wavefront for a full band.  TOP / BOT: the band holds the lattice's first / last
+// row (lane 0's first row has no w, lane 31's last row no e: three neighbours, x/3).  START: the first and the last
+// blocks of the sweep, where lanes are waiting to enter or have left (column < 0 or >= n: idle) or stand on the first
+// / last column (no s / no n neighbour: the missing operand is 0.0 -- the initial s_prev, a masked load -- which
+// adds exactly; one neighbour less in the divisor); otherwise every lane is on columns 1 .. n-2.
+template <int S, int RING, bool TOP, bool BOT, bool START>
+__device__ __forceinline__ void dcol_fast_block(DcolState& st, int lane, int k0, int n) {
+    constexpr uint32_t ROWB = RING * 8u;
+    int y = k0 - S * lane;
+#pragma unroll 2
+    for (int k = 0; k < 32; k++, y++) {
+        const uint32_t off_n = st.off_s + 8u == ROWB ? 0u : st.off_s + 8u;
+        const bool act = !START || (y >= 0 && y < n), col0 = START && (y == 0 || y == n - 1);
+        double w_in = __shfl_up_sync(FULL, st.hand[0], 1);
+        double nv[DCOL_R];
+#pragma unroll
+        for (int r = 0; r < DCOL_R; r++) nv[r] = dcol_lds(st.a_row + r * ROWB + off_n);
+        double e_last = 0.0;
+        if (!BOT || lane != 31) e_last = dcol_lds(st.a_row + DCOL_R * ROWB + st.off_s);
+        if (!TOP) { const double ab = dcol_lds(st.a_above + st.off_s); if (lane == 0) w_in = ab; }
+        double t[DCOL_R];
+#pragma unroll
+        for (int r = 0; r < DCOL_R; r++) {
+            t[r] = ((START && y == n - 1) ? 0.0 : nv[r]) + st.s_prev[r];
+            if (r + 1 < DCOL_R) t[r] = t[r] + st.old_cur[r + 1];
+        }
+        const double t_last_e = t[DCOL_R - 1] + e_last;     // the usual last row: n, s, e (, w)
+        double up = w_in;
+#pragma unroll
+        for (int r = 0; r < DCOL_R; r++) {
+            // sum of the present neighbours in the reference's order; `edge` = this cell is on the first / last row
+            const bool edge = (TOP && r == 0 && lane == 0) || (BOT && r == DCOL_R - 1 && lane == 31);
+            double sum;
+            if (r + 1 < DCOL_R) sum = (TOP && r == 0 && lane == 0) ? t[0] : t[r] + up;
+            else sum = (BOT && lane == 31) ? t[r] + up : t_last_e + up;
+            double res = sum * 0.25;
+            if (TOP && r == 0 || BOT && r == DCOL_R - 1 || START) {
+                const double d3 = dcol_div3(sum);
+                if (START) res = col0 ? (edge ? sum * 0.5 : d3) : (edge ? d3 : res);
+                else if (edge) res = d3;
+            }
+            if (act) dcol_sts(st.a_row + r * ROWB + st.off_s, res);
+            if (START) { st.s_prev[r] = act ? res : 0.0; up = act ? res : up; }
+            else { st.s_prev[r] = res; up = res; }
+            st.old_cur[r] = nv[r];
+        }
+#pragma unroll
+        for (int i = 0; i + 1 < S; i++) st.hand[i] = st.hand[i + 1];
+        st.hand[S - 1] = up;
+        if (!BOT && lane == 31 && act) *st.out = up;
+        st.out++;
+        st.off_s = off_n;
+    }
+}
+// The same 32 steps for blocks that touch the lattice border or start / end the skewed sweep: per cell the present
+// neighbours are added in the reference's order (n, s, e, w) behind select masks, the divisor follows their count,
+// lanes outside the lattice idle -- branch-free, so the first blocks of a band (which every later band waits for)
+// cost little more than the interior ones.
+template <int S, int RING>
+__device__ __forceinline__ void dcol_edge_block(DcolState& st, int lane, int k0, int n, int x_first, bool has_above,
+                                                bool has_below) {
+    constexpr uint32_t ROWB = RING * 8u;
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) {
+        const int y = k0 + k - S * lane;
+        const bool col_ok = y >= 0 && y < n, has_n = y + 1 < n, has_s = y >= 1;
+        const uint32_t off_n = st.off_s + 8u == ROWB ? 0u : st.off_s + 8u;
+        double w_in = __shfl_up_sync(FULL, st.hand[0], 1);
+        double nv[DCOL_R];
+#pragma unroll
+        for (int r = 0; r < DCOL_R; r++) nv[r] = dcol_lds(st.a_row + r * ROWB + off_n);
+        const double e_last = dcol_lds(st.a_row + DCOL_R * ROWB + st.off_s);
+        const double ab = dcol_lds(st.a_above + st.off_s);
+        if (lane == 0) w_in = ab;
+        double up = w_in;
+#pragma unroll
+        for (int r = 0; r < DCOL_R; r++) {
+            const int x = x_first + r;
+            const bool has_e = x + 1 < n, has_w = x >= 1 && (r > 0 || lane > 0 || has_above);
+            const double e = r + 1 < DCOL_R ? st.old_cur[r + 1] : e_last;
+            double t = 0.0 + (has_n ? nv[r] : 0.0);
+            t = t + (has_s ? st.s_prev[r] : 0.0);
+            t = t + (has_e ? e : 0.0);
+            t = t + (has_w ? up : 0.0);
+            const int cnt = (int)has_n + (int)has_s + (int)has_e + (int)has_w;
+            const double d3 = dcol_div3(t);
+            const double res = cnt == 4 ? t * 0.25 : (cnt == 3 ? d3 : (cnt == 2 ? t * 0.5 : t));
+            const bool active = col_ok && x < n;
+            if (active) dcol_sts(st.a_row + r * ROWB + st.off_s, res);
+            st.s_prev[r] = active ? res : st.s_prev[r];
+            up = active ? res : up;
+            st.old_cur[r] = nv[r];
+        }
+#pragma unroll
+        for (int i = 0; i + 1 < S; i++) st.hand[i] = st.hand[i + 1];
+        st.hand[S - 1] = up;
+        if (lane == 31 && has_below && col_ok) st.out[k] = up;
+        st.off_s = off_n;
+    }
+    st.out += 32;
+}
+struct DcolShared {
+    volatile int loaded[DCOL_H];    // chunks whose rows of helper h have landed in the ring
+    volatile int above;             // chunks of the row above the band that are in the ring
+    volatile int done;              // blocks of 32 steps the compute warp has finished
+};
+template <int S>
+__global__ void __launch_bounds__(32 * (1 + DCOL_H), 1)
+ss_diffuse_col_kernel(double* __restrict__ p, int n, int* ticket, double* handoff) {
+    constexpr int NR = S + 3;                           // ring chunks: j-S .. j+2 are live in block j
+    constexpr int RING = 32 * NR;
+    extern __shared__ __align__(16) double dcol_tile[]; // [DCOL_ROWS + 2][RING]: row 0 = above (new), last = below (old)
+    __shared__ DcolShared sh;
+    __shared__ int band_s;
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        band_s = atomicAdd(ticket, 1);
+        for (int h = 0; h < DCOL_H; h++) sh.loaded[h] = 0;
+        sh.above = 0; sh.done = 0;
+    }
+    __syncthreads();
+    const int b = band_s;
+    const int x0 = b * DCOL_ROWS;
+    const int rows = min(DCOL_ROWS, n - x0);
+    const bool has_above = x0 > 0, has_below = x0 + DCOL_ROWS < n;
+    const int nchunks = (n + 31) / 32;
+    const int nsteps = n + 31 * S;                      // steps 0 .. n-1+31*S
+    const int nblocks = (nsteps + 31) / 32;
+    // every lane polls (one broadcast read): a single spinning lane would leave the warp split in two
+    // independently scheduled halves afterwards, and every shuffle of the compute loop would take the divergent path
+    auto wait_ge = [&](const volatile int* f, int need) {
+        while (*f < need) { if (wq > 0) __nanosleep(100); }
+        __syncwarp();
+        __threadfence_block();
+    };
+    if (wq > 0) {
+        // ------------------------------------------------------------------ helper warps ----
+        const int h = wq - 1;
+        // tile rows of this helper: an even share of the band's rows; the last helper also owns the row below
+        const int per = (DCOL_ROWS + DCOL_H - 1) / DCOL_H;
+        const int r_lo = 1 + h * per, r_hi = min(rows, (h + 1) * per);         // tile rows r_lo .. r_hi
+        const bool last = h == DCOL_H - 1, first = h == 0;
+        for (int i = 0; i < nchunks + 2 + S; i++) {
+            if (i < nchunks) {                          // (a) load chunk i (its ring slot was written back in (c) of i-1)
+                const int col = 32 * i + lane;
+                if (col < n) {
+                    double* dst = dcol_tile + (size_t)(32 * (i % NR) + lane);
+                    for (int rr = r_lo; rr <= r_hi; rr++) cp_async8(dst + (size_t)rr * RING, &p[(size_t)(x0 - 1 + rr) * n + col]);
+                    if (last && has_below) cp_async8(dst + (size_t)(DCOL_ROWS + 1) * RING, &p[(size_t)(x0 + DCOL_ROWS) * n + col]);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); sh.loaded[h] = i + 1; }
+            }
+            if (first && i >= 1 && i - 1 < nchunks) {   // (b) row above the band, chunk i-1 (needed by block i-1)
+                const int ch = i - 1;
+                if (has_above) {
+                    // the band above (previous ticket) stores its last row's new values into handoff[] as it computes
+                    // them; the buffer starts as all-ones NaNs, so a value is its own "ready" flag -- no fences
+                    const int col = 32 * ch + lane;
+                    const volatile double* src = handoff + (size_t)(b - 1) * n + col;
+                    double v = 0.0;
+                    bool got = col >= n;
+                    for (;;) {
+                        if (!got) { v = *src; got = __double_as_longlong(v) != -1ll; }
+                        if (__all_sync(FULL, got)) break;
+                    }
+                    if (col < n) dcol_tile[32 * (ch % NR) + lane] = v;
+                    __syncwarp();
+                }
+                if (lane == 0) { __threadfence_block(); sh.above = ch + 1; }
+            }
+            const int f = i - 2 - S;                    // (c) write chunk f back once every lane has passed it
+            if (f >= 0 && f < nchunks) {
+                wait_ge(&sh.done, min(f + S + 1, nblocks));
+                const int col = 32 * f + lane;
+                if (col < n) {
+                    const double* src = dcol_tile + (size_t)(32 * (f % NR) + lane);
+                    for (int rr = r_lo; rr <= r_hi; rr++) p[(size_t)(x0 - 1 + rr) * n + col] = src[(size_t)rr * RING];
+                }
+                __syncwarp();
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- compute warp ----
+    const int row0 = 1 + DCOL_R * lane;                 // tile row of my first lattice row
+    DcolState st;                                       // new values of column y-1, old values of column y (my rows), ...
+#pragma unroll
+    for (int r = 0; r < DCOL_R; r++) { st.s_prev[r] = 0.0; st.old_cur[r] = 0.0; }
+    st.hand[0] = st.hand[1] = 0.0;                      // my last row's results of the last S steps (oldest first)
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(dcol_tile);
+    st.a_row = tile_s + (uint32_t)(row0 * RING) * 8u;
+    st.a_above = tile_s;
+    st.off_s = (uint32_t)((RING - ((S * lane) % RING)) % RING) * 8u;    // ring slot of my column y = k - S*lane at k = 0
+    st.out = handoff + (size_t)b * n - S * 31;          // lane 31's column of step 0
+    for (int j = 0; j < nblocks; j++) {
+        for (int h = 0; h < DCOL_H; h++) wait_ge(&sh.loaded[h], min(j + 2, nchunks));
+        wait_ge(&sh.above, min(j + 1, nchunks));
+        if (j == 0) {                                   // old values of my first column (lane 0 starts right away)
+#pragma unroll
+            for (int r = 0; r < DCOL_R; r++) st.old_cur[r] = dcol_lds(st.a_row + r * (RING * 8u) + st.off_s);
+        }
+        const int k0 = 32 * j;
+        // interior blocks: a full band, every lane on columns 1 .. n-2.  The lattice's first and last row (three
+        // neighbours: no w / no e) are handled by the two lanes that own them, so the first and the last band --
+        // the first paces every other band -- run them too.
+        const bool full = rows == DCOL_ROWS && (has_above || has_below) && n >= 64 + 31 * S;
+        const bool interior = full && (k0 - 31 * S >= 1) && (k0 + 32 < n);
+        if (interior) {
+            if (!has_above) dcol_fast_block<S, RING, true, false, false>(st, lane, k0, n);
+            else if (!has_below) dcol_fast_block<S, RING, false, true, false>(st, lane, k0, n);
+            else dcol_fast_block<S, RING, false, false, false>(st, lane, k0, n);
+        } else if (full) {          // the sweep is starting or ending: lanes enter / leave one after the other
+            if (!has_above) dcol_fast_block<S, RING, true, false, true>(st, lane, k0, n);
+            else if (!has_below) dcol_fast_block<S, RING, false, true, true>(st, lane, k0, n);
+            else dcol_fast_block<S, RING, false, false, true>(st, lane, k0, n);
+        } else {
+            dcol_edge_block<S, RING>(st, lane, k0, n, x0 + DCOL_R * lane, has_above, has_below);
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); sh.done = j + 1; }
+    }
 }
 
 // simple reference implementation on the device (anti-diagonal sweep, one CTA): A/B check only
@@ -1789,7 +2055,8 @@ cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, c
     return cudaGetLastError();
 }
 
-cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl, cudaStream_t s) {
+size_t ss_diffuse_handoff_bytes(int n) { return sizeof(double) * (size_t)((n + DCOL_ROWS - 1) / DCOL_ROWS) * n; }
+cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, double* handoff, int impl, cudaStream_t s) {
     const int n = w.n;
     if (impl == 1) {
         ss_diffuse_diag_kernel<<<1, 1024, 0, s>>>(w.poll, n);
@@ -1798,7 +2065,20 @@ cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, int impl,
     const int nbands = (n + 31) / 32;
     cudaError_t e = cudaMemsetAsync(ticket_progress, 0, sizeof(int) * (size_t)(nbands + 1), s);
     if (e != cudaSuccess) return e;
-    ss_diffuse_kernel<<<nbands, 32, 0, s>>>(w.poll, n, ticket_progress, ticket_progress + 1);
+    if (impl == 2) {        // one warp per band, one band per CTA, every hand-off through global flags
+        ss_diffuse_kernel<<<nbands, 32, 0, s>>>(w.poll, n, ticket_progress, ticket_progress + 1);
+        return cudaGetLastError();
+    }
+    static bool configured = false;
+    constexpr int S = 2;
+    const size_t smem = sizeof(double) * (DCOL_ROWS + 2) * 32 * (S + 3);
+    if (!configured) {
+        e = cudaFuncSetAttribute(ss_diffuse_col_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int ncol = (n + DCOL_ROWS - 1) / DCOL_ROWS;
+    ss_diffuse_col_kernel<S><<<ncol, 32 * (1 + DCOL_H), smem, s>>>(w.poll, n, ticket_progress, handoff);
     return cudaGetLastError();
 }
 

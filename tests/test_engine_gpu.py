@@ -110,15 +110,22 @@ def test_lattice_seasons(opts):
     common.compare_worlds(e, o, 9, what="seasons 260")
 
 
-def test_diffusion_wavefront_equals_diagonal_sweep():
-    s, init = common.synthetic_case(700, True)
+@pytest.mark.parametrize("n", [700, 193, 1025])
+def test_diffusion_wavefront_equals_diagonal_sweep(n):
+    """The three diffusion kernels agree bit for bit: 0 = wavefront, six 32-row bands per CTA with shared-memory
+    hand-off (default); 2 = wavefront, one band per CTA, hand-off through global flags; 1 = anti-diagonal sweep of one
+    CTA (the simple restatement).  Sizes: several CTAs, a partial last band, a single partial CTA."""
+    s, init = common.synthetic_case(n, True)
     cfg = config_from_settings(s, rng_mode="keyed")
-    a, b = common.engine_world(cfg), common.engine_world(cfg)
-    b.set_option("diffuse_impl", 1)
-    for w in (a, b):
+    worlds = [common.engine_world(cfg, options={"diffuse_impl": k}) for k in (0, 1, 2)]
+    for w in worlds:
         common.init_world(w, init, "keyed")
         w.step(4)
-    assert np.array_equal(a.download_cells()["pollution"], b.download_cells()["pollution"])
+    ref = worlds[1].download_cells()["pollution"]
+    assert np.array_equal(worlds[0].download_cells()["pollution"], ref)
+    assert np.array_equal(worlds[2].download_cells()["pollution"], ref)
+    for w in worlds:
+        w.close()
 
 
 def test_mt_serial_env_path_large_grid():
