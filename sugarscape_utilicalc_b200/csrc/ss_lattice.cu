@@ -2078,6 +2078,8 @@ cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, double* h
         configured = true;
     }
     const int ncol = (n + DCOL_ROWS - 1) / DCOL_ROWS;
+    e = cudaMemsetAsync(handoff, 0xff, sizeof(double) * (size_t)ncol * n, s);       // all-ones NaN = "not there yet"
+    if (e != cudaSuccess) return e;
     ss_diffuse_col_kernel<S><<<ncol, 32 * (1 + DCOL_H), smem, s>>>(w.poll, n, ticket_progress, handoff);
     return cudaGetLastError();
 }
