@@ -110,11 +110,11 @@ def test_lattice_seasons(opts):
     common.compare_worlds(e, o, 9, what="seasons 260")
 
 
-@pytest.mark.parametrize("n", [700, 193, 1025])
+@pytest.mark.parametrize("n", [700, 129, 177, 193, 256, 257, 1025])
 def test_diffusion_wavefront_equals_diagonal_sweep(n):
-    """The three diffusion kernels agree bit for bit: 0 = wavefront, six 32-row bands per CTA with shared-memory
-    hand-off (default); 2 = wavefront, one band per CTA, hand-off through global flags; 1 = anti-diagonal sweep of one
-    CTA (the simple restatement).  Sizes: several CTAs, a partial last band, a single partial CTA."""
+    """The three diffusion kernels agree bit for bit: 0 = column-chain wavefront (128-row bands, a compute warp and
+    three staging warps per CTA; default); 2 = row-wise wavefront (32-row bands, one warp); 1 = anti-diagonal sweep of
+    one CTA (the simple restatement).  Sizes: several bands, partial last bands of 1..65 rows, ring-sized lattices."""
     s, init = common.synthetic_case(n, True)
     cfg = config_from_settings(s, rng_mode="keyed")
     worlds = [common.engine_world(cfg, options={"diffuse_impl": k}) for k in (0, 1, 2)]
