@@ -48,10 +48,10 @@ def measured_peak():
 
 def workload(name):
     if name == "c5":
-        return dict(n=16384, pollution=False, label="c5: 16384x16384 tiled landscape, 16777216 agents, "
+        return dict(key="c5", n=16384, pollution=False, label="c5: 16384x16384 tiled landscape, 16777216 agents, "
                     "grow+moveEat+canStarve, vision 1-6, keyed RNG seed 18")
     if name == "c4":
-        return dict(n=4096, pollution=True, label="c4: 4096x4096 tiled landscape, 1048576 agents, "
+        return dict(key="c4", n=4096, pollution=True, label="c4: 4096x4096 tiled landscape, 1048576 agents, "
                     "grow+moveEat+canStarve+pollution(A=B=1, diffusion every step), vision 1-6, keyed RNG seed 18")
     if name.startswith("preset:"):
         return dict(preset=name.split(":", 1)[1], n=50, pollution=False, label="shipped preset " + name.split(":", 1)[1])
@@ -186,11 +186,17 @@ def run_engine_single(args, wl):
     kernels["prepare+stats"] = {"ms_per_step": (kt["prepare"] + kt["stats"]) / K,
                                 "share": (kt["prepare"] + kt["stats"]) / tot}
     dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
+    # DRAM bytes of the dominant kernel's launches of one step, from the committed ncu --set full captures
+    # (profiles/r01c_*.csv: dram__bytes_read.sum + dram__bytes_write.sum, summed over the step's launches)
+    traffic_tbl = {("c5", "move", 1): 25.1e9, ("c4", "move", 1): 1.515e9, ("c4", "diffuse", 1): 210.7e6, ("c4", "diffuse", 0): 210.7e6}
+    traffic = traffic_tbl.get((wl.get("key"), dom, cnt["pass_impl"]))
     move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel"][cnt["pass_impl"]]
     roofline = {"bound": "hbm", "kernel": {"move": move_kernel + " (all passes of a step) + ss_settle_kernel",
                                            "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic,
+                "traffic_source": "profiles/r01c_ncu_full_*.csv (bytes per step, same launch set)" if traffic else None,
+                "peak_source": peak_src,
                 "ms_per_launch_set": kernels[dom]["ms_per_step"]}
     whole_bytes = ab["move"] + ab["grow"] + ab["diffuse"]
     step_frac = whole_bytes / (ms / K * 1e-3) / 1e9 / peak
