@@ -190,7 +190,7 @@ def run_engine_single(args, wl):
     # (profiles/r01c_*.csv: dram__bytes_read.sum + dram__bytes_write.sum, summed over the step's launches)
     traffic_tbl = {("c5", "move", 1): 25.1e9, ("c4", "move", 1): 1.515e9, ("c4", "diffuse", 1): 210.7e6, ("c4", "diffuse", 0): 210.7e6}
     traffic = traffic_tbl.get((wl.get("key"), dom, cnt["pass_impl"]))
-    move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel"][cnt["pass_impl"]]
+    move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel", "ss_move_solo_kernel (lanes)"][cnt["pass_impl"]]
     roofline = {"bound": "hbm", "kernel": {"move": move_kernel + " (all passes of a step) + ss_settle_kernel",
                                            "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -258,7 +258,7 @@ def run_engine_single(args, wl):
         "cell_updates_per_s": n * n * K / (ms * 1e-3),
         "population": [int(pop0), int(st["population"][-1])],
         "passes_per_step": cnt["passes"] / K, "gpu_launches": cnt["launches"],
-        "move_pass": {"impl": ["cta_per_window", "warp_per_window"][cnt["pass_impl"]], "window": cnt["window"]},
+        "move_pass": {"impl": ["cta_per_window", "warp_per_window", "lane_per_agent"][cnt["pass_impl"]], "window": cnt["window"]},
         "host_syncs_per_step": cnt["syncs"] / K,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts,

@@ -137,7 +137,8 @@ int  ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n);
 /* options: "path" (-1 auto, 0 serial, 2 lattice), "profile" (0/1), "reset_times",
  * "reset_counters", "diffuse_impl" (0 wavefront with several bands per CTA, 1 diagonal sweep and 2 one band per CTA, for A/B checks),
  * "window" (max window extent of the CTA-per-window move pass, 32..176), "pass_impl" (-1 auto, 0 CTA per window,
- * 1 warp per window), "solo_window" (max window extent of the warp-per-window move pass; 0 = chosen from the lattice size) */
+ * 1 warp per window taking its agents one at a time, 2 warp per window with one lane per agent -- bit-identical results,
+ * measured slower, kept for A/B runs), "pendmap" (0/1 coarse pending map), "solo_window" (max window extent of the warp-per-window move pass; 0 = chosen from the lattice size) */
 int  ss_set_option(ss_engine* e, const char* name, int64_t value);
 
 /* Multi-GPU (one process per GPU; sugarscape_utilicalc_b200/sharded.py).  Every rank holds a replica of the

@@ -25,8 +25,8 @@ uint32_t ss_export_blocks(uint32_t domain);
 cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32_t* blockcnt, uint32_t* total, int32_t* cols,
                                     size_t stride, double* sugar, cudaStream_t s);
 size_t ss_pass_smem_bytes(int emax, int ew, int vmax);
-size_t ss_solo_smem_bytes(int emax, int ew);
-cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time, cudaStream_t s);
+size_t ss_solo_smem_bytes(int emax, int ew, int lanes);
+cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time, int lanes, cudaStream_t s);
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
 cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s);
@@ -201,6 +201,9 @@ extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* 
     return SS_OK;
 }
 
+#ifndef SS_DEFAULT_SOLO_IMPL
+#define SS_DEFAULT_SOLO_IMPL 1
+#endif
 static int choose_path(ss_engine* e) {
     const int n = e->w.n, V = e->w.vmax;
     bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && !e->cfg.rule_utilicalc && V <= 15 && 4 * V + 1 <= n &&
@@ -240,7 +243,7 @@ static int choose_path(ss_engine* e) {
         int ntile_s = 1, emin_s = 0;
         // the solo kernel needs many windows to fill the GPU (one warp each, 32 per SM) and window coordinates < 256
         auto solo_tiling = [&](int wmax) {
-            return tiling(wmax, &gs, &ntile_s, &emin_s) && gs.nwin > 1 && ss_solo_smem_bytes(gs.emax, gs.ew) <= 48 * 1024;
+            return tiling(wmax, &gs, &ntile_s, &emin_s) && gs.nwin > 1 && ss_solo_smem_bytes(gs.emax, gs.ew, 1) <= 48 * 1024;
         };
         bool solo_ok = false;
         if (e->solo_window_max > 0) {
@@ -251,9 +254,10 @@ static int choose_path(ss_engine* e) {
             for (int k = 0; k < 5 && !solo_ok; k++)
                 solo_ok = solo_tiling(sizes[k]) && ((long long)gs.nwin * gs.nwin >= 17ll * e->sm_count * e->shard_world || k == 4);
         }
-        const bool want_solo = e->pass_impl_option == 1 ||
+        const bool want_solo = e->pass_impl_option >= 1 ||
                                (e->pass_impl_option < 0 && solo_ok && (long long)gs.nwin * gs.nwin >= 8ll * e->sm_count * e->shard_world);
-        if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = 1; }
+        // 1 = the warp takes its agents one at a time, 2 = one lane per agent in batches of 32 (SS_DEFAULT_SOLO_IMPL)
+        if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = e->pass_impl_option >= 1 ? e->pass_impl_option : SS_DEFAULT_SOLO_IMPL; }
         else if (!cta_ok) lattice_ok = false;
     }
     int path;
@@ -453,7 +457,7 @@ static int lattice_step(ss_engine* e, int stats_index) {
                 CK(cudaMemsetAsync(e->w.pendmap + (size_t)g.map_write * e->w.pend_nb * e->w.pend_nb, 0,
                                    sizeof(uint32_t) * (size_t)e->w.pend_nb * e->w.pend_nb, e->stream));
             }
-            if (e->pass_impl == 1) CK(ss_launch_move_solo(e->w, g, e->iteration, e->env_time, e->stream));
+            if (e->pass_impl >= 1) CK(ss_launch_move_solo(e->w, g, e->iteration, e->env_time, e->pass_impl == 2, e->stream));
             else CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
             e->launches++; e->passes++; p++;
             if (p >= first_check || e->trace) {
@@ -765,7 +769,24 @@ extern "C" int ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_en
     const int nw = g.nwin, W = e->shard_world, r = e->shard_rank;
     g.bx_lo = (int)(((long long)r * nw) / W);
     g.bx_cnt = (int)(((long long)(r + 1) * nw) / W) - g.bx_lo;
-    if (e->pass_impl == 1) CK(ss_launch_move_solo(e->w, g, e->iteration, e->env_time, e->stream));
+    if (e->w.pendmap && e->use_pendmap) {
+        // coarse pending map, per rank and without communication: a rank knows exactly what its own windows left
+        // pending; the 32-row blocks that are not entirely inside its window rows of this pass start as "pending"
+        const int nb = e->w.pend_nb, n = e->w.n, nu = n / g.align;
+        const size_t words = (size_t)nb * nb;
+        g.map_write = e->shard_pass & 1;
+        g.map_read = e->shard_pass > 0 ? ((e->shard_pass - 1) & 1) : -1;
+        uint32_t* mw = e->w.pendmap + (size_t)g.map_write * words;
+        CK(cudaMemsetAsync(mw, 0x01, sizeof(uint32_t) * words, e->stream));
+        const long long x_lo = (long long)g.align * (((long long)g.bx_lo * nu) / nw) + g.shift_x;
+        const long long x_hi = (long long)g.align * (((long long)(g.bx_lo + g.bx_cnt) * nu) / nw) + g.shift_x;
+        const long long first = (x_lo + 31) / 32, last = x_hi / 32;             // block rows [first, last) are mine
+        const long long cnt = std::min<long long>(std::max<long long>(last - first, 0), nb);
+        const long long f0 = first % nb, c0 = std::min<long long>(cnt, nb - f0);
+        if (c0 > 0) CK(cudaMemsetAsync(mw + (size_t)f0 * nb, 0, sizeof(uint32_t) * (size_t)c0 * nb, e->stream));
+        if (cnt - c0 > 0) CK(cudaMemsetAsync(mw, 0, sizeof(uint32_t) * (size_t)(cnt - c0) * nb, e->stream));
+    }
+    if (e->pass_impl >= 1) CK(ss_launch_move_solo(e->w, g, e->iteration, e->env_time, e->pass_impl == 2, e->stream));
     else CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
     e->launches++; e->passes++; e->shard_pass++;
     CK(cudaMemcpyAsync(&after, e->w.log_count, sizeof after, cudaMemcpyDeviceToHost, e->stream));

@@ -289,43 +289,31 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
 // (nobody can observe them before the agent loop ends: the destination stays occupied).
 // AT-RISK agents are settled synchronously because a death frees the cell and decides the
 // successor's turn (Q1).
-template <int POLT, class Ctx>
-__device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, int ly, uint32_t ow, uint32_t slot,
-                                       int64_t iteration, int64_t env_time, uint64_t skey, uint32_t next_phase,
-                                       ThreadStats& ts, int lane, const CrossLoads& L) {
-    const int n = c.n;
-    const int a = occ_vision(ow);
-    const int gx = Ctx::gw(c.gx0 + lx, n), gy = Ctx::gw(c.gy0 + ly, n);
-    const int pos = gx * n + gy;
-    const bool risky = (ow & OCC_RISK) != 0;
+// Commit of one agent's turn by ONE thread, once the destination is chosen: (lx,ly) -> (lr,lq) in window coordinates,
+// pos -> cell on the lattice, harvest sg.  sugar / attr are the agent's record fields (read only for at-risk agents).
+template <class Ctx>
+__device__ static inline void commit_turn(const DevWorld& w, const Ctx& c, int lx, int ly, int lr, int lq, int pos, int cell,
+                                          int sg, int a, bool risky, uint32_t slot, double sugar, uint32_t attr,
+                                          int64_t iteration, int64_t env_time, uint32_t next_phase, ThreadStats& ts) {
     AgentRec* recp = &w.agents[slot];
-    double sugar = 0.0;
-    uint32_t attr = 0;
-    if (risky && lane == 0) { sugar = recp->sugar; attr = recp->attr; }   // issued early, used after the scan
-    Choice ch;
-    if (w.cfg.rule_move_eat) ch = warp_choose_cell<POLT>(w, c, lx, ly, gx, gy, a, slot, skey, lane, L);
-    else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
-    if (lane != 0) return;
-    const int cell = (ch.lr == lx && ch.lq == ly) ? pos
-                   : Ctx::gw(c.gx0 + ch.lr, n) * n + Ctx::gw(c.gy0 + ch.lq, n);
     uint32_t new_word = occ_pack(slot, a, next_phase);
     ts.resolved++;
     if (!risky) {
         c.put_occ(lx, ly, 0u);
-        c.put_occ(ch.lr, ch.lq, new_word);
+        c.put_occ(lr, lq, new_word);
         if (cell != pos) w.occw[pos] = 0u;
         w.occw[cell] = new_word;
         if (w.cfg.rule_move_eat) {
-            c.clear_isug(ch.lr, ch.lq);
+            c.clear_isug(lr, lq);
             w.sugar[cell] = 0.0;                                      // agent.py:864
             w.isugar[cell] = 0;
         }
         recp->pos = (uint32_t)cell;
-        recp->turn = ((uint32_t)(iteration + 1) << 8) | (uint32_t)ch.sg;
+        recp->turn = ((uint32_t)(iteration + 1) << 8) | (uint32_t)sg;
         if (w.log) {
             ShardLogEntry en;
             en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
-            en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.status = 0u; en.turn = recp->turn; en.kind_harvest = 0u | ((uint32_t)ch.sg << 8);
+            en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.status = 0u; en.turn = recp->turn; en.kind_harvest = 0u | ((uint32_t)sg << 8);
             *log_slot(w, ts) = en;
         }
         return;
@@ -333,9 +321,9 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
     const bool pol = w.cfg.rule_pollution != 0 && w.cfg.pollution_start_time <= env_time;
     const int metab = attr_metab(attr);
     if (w.cfg.rule_move_eat) {
-        if (pol) w.poll[cell] = __ldcg(&w.poll[cell]) + (((double)ch.sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));
-        sugar = ss_set_sugar(ss_max0(sugar + (double)ch.sg));         // agent.py:832
-        c.clear_isug(ch.lr, ch.lq);
+        if (pol) w.poll[cell] = __ldcg(&w.poll[cell]) + (((double)sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));
+        sugar = ss_set_sugar(ss_max0(sugar + (double)sg));            // agent.py:832
+        c.clear_isug(lr, lq);
         w.sugar[cell] = 0.0;
         w.isugar[cell] = 0;
     }
@@ -351,7 +339,7 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
     const bool died = w.cfg.rule_can_starve && sugar <= 0.1;          // sugarscape.py:306-309
     if (died) new_word = 0u;
     c.put_occ(lx, ly, 0u);
-    c.put_occ(ch.lr, ch.lq, new_word);
+    c.put_occ(lr, lq, new_word);
     if (cell != pos) w.occw[pos] = 0u;
     w.occw[cell] = new_word;
     if (died) { attr &= ~ATTR_ALIVE; ts.deaths++; }
@@ -365,9 +353,138 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
         ShardLogEntry en;
         en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
         en.sugar = sugar; en.poll = w.cfg.rule_pollution ? w.poll[cell] : 0.0; en.attr = attr; en.status = status; en.turn = 0u;
-        en.kind_harvest = 1u | ((uint32_t)ch.sg << 8);
+        en.kind_harvest = 1u | ((uint32_t)sg << 8);
         *log_slot(w, ts) = en;
     }
+}
+
+// One agent's turn (one warp per agent; lane 0 commits).  SAFE agents (no OCC_RISK flag)
+// cannot starve, so only their move is done here -- shared-memory reads, fire-and-forget
+// HBM stores; harvest, pollution, metabolism and statistics are deferred to ss_settle_kernel
+// (nobody can observe them before the agent loop ends: the destination stays occupied).
+// AT-RISK agents are settled synchronously because a death frees the cell and decides the
+// successor's turn (Q1).
+template <int POLT, class Ctx>
+__device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, int ly, uint32_t ow, uint32_t slot,
+                                       int64_t iteration, int64_t env_time, uint64_t skey, uint32_t next_phase,
+                                       ThreadStats& ts, int lane, const CrossLoads& L) {
+    const int n = c.n;
+    const int a = occ_vision(ow);
+    const int gx = Ctx::gw(c.gx0 + lx, n), gy = Ctx::gw(c.gy0 + ly, n);
+    const int pos = gx * n + gy;
+    const bool risky = (ow & OCC_RISK) != 0;
+    const AgentRec* recp = &w.agents[slot];
+    double sugar = 0.0;
+    uint32_t attr = 0;
+    if (risky && lane == 0) { sugar = recp->sugar; attr = recp->attr; }   // issued early, used after the scan
+    Choice ch;
+    if (w.cfg.rule_move_eat) ch = warp_choose_cell<POLT>(w, c, lx, ly, gx, gy, a, slot, skey, lane, L);
+    else { ch.lr = lx; ch.lq = ly; ch.sg = 0; }
+    if (lane != 0) return;
+    const int cell = (ch.lr == lx && ch.lq == ly) ? pos
+                   : Ctx::gw(c.gx0 + ch.lr, n) * n + Ctx::gw(c.gy0 + ch.lq, n);
+    commit_turn(w, c, lx, ly, ch.lr, ch.lq, pos, cell, ch.sg, a, risky, slot, sugar, attr, iteration, env_time, next_phase, ts);
+}
+
+// ------------------------------------------------------------------------------------------
+// Lane-per-agent turn (ss_move_solo_kernel<POLT, true>): one THREAD scans its agent's cross and chooses the cell --
+// agent.py:361-371 getFood + agent.py:794-823 move().  Candidates are numbered as in warp_choose_cell (x-arm by
+// ascending offset, then y-arm); best = (key desc, raw Manhattan distance asc, position in the shuffled food list
+// asc).  At most four candidates can tie on (key, distance) -- one distance, two arms, two sides -- so the tied set
+// is four (harvest, index) pairs in a register; the Fisher-Yates replay tracks their positions as warp_choose_cell does.
+struct LaneChoice { int cell, sg; };
+template <int POLT, bool WRAP>
+__device__ static inline LaneChoice lane_choose_cell(const DevWorld& w, int gx, int gy, int a, uint32_t slot, uint64_t skey) {
+    const int n = w.n;
+    constexpr bool pol = POLT != 0;
+    const int span = 2 * a + 1;
+    const int pos = gx * n + gy;
+    const int sg0 = (int)__ldcg(&w.isugar[pos]);
+    double pown = 0.0;
+    if (pol) pown = __ldcg(&w.poll[pos]);
+    unsigned long long fm = 0ull;           // free candidates, bit = candidate index k
+    unsigned long long tl = 0ull;           // tied best candidates, 16 bits each: harvest << 8 | k
+    int nt = 0, dmin = 0x7fffffff;
+    uint32_t ikmax = 0u;
+    double dkmax = -1.0;
+#pragma unroll 1
+    for (int d = 1; d <= a; d++) {
+        int cx[4], cy[4], kk[4];
+        cx[0] = WRAP ? ss_wrap1(gx - d, n) : gx - d; cy[0] = gy; kk[0] = a - d;
+        cx[1] = WRAP ? ss_wrap1(gx + d, n) : gx + d; cy[1] = gy; kk[1] = a + d;
+        cx[2] = gx; cy[2] = WRAP ? ss_wrap1(gy - d, n) : gy - d; kk[2] = span + a - d;
+        cx[3] = gx; cy[3] = WRAP ? ss_wrap1(gy + d, n) : gy + d; kk[3] = span + a + d;
+        uint32_t oc[4];
+        int sg[4];
+        double pp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int ci = cx[u] * n + cy[u];
+            oc[u] = __ldcg(&w.occw[ci]);
+            sg[u] = (int)__ldcg(&w.isugar[ci]);
+            pp[u] = pol ? __ldcg(&w.poll[ci]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (oc[u] != 0u) continue;
+            fm |= 1ull << kk[u];
+            const int dist = WRAP ? abs(gx - cx[u]) + abs(gy - cy[u]) : d;          // agent.py:867-868 (raw coordinates)
+            const unsigned long long ent = ((unsigned long long)sg[u] << 8) | (unsigned long long)kk[u];
+            if (!pol) {
+                const uint32_t ik = (((uint32_t)sg[u] << 20) | (0xfffffu - (uint32_t)dist)) + 1u;
+                if (ik > ikmax) { ikmax = ik; tl = ent; nt = 1; }
+                else if (ik == ikmax) { tl = (tl << 16) | ent; nt++; }
+            } else {
+                const double key = (double)sg[u] / (1.0 + (sg[u] > 0 ? pp[u] : 0.0));
+                if (key > dkmax || (key == dkmax && dist < dmin)) { dkmax = key; dmin = dist; tl = ent; nt = 1; }
+                else if (key == dkmax && dist == dmin) { tl = (tl << 16) | ent; nt++; }
+            }
+        }
+    }
+    LaneChoice ch;
+    ch.cell = pos; ch.sg = sg0;
+    if (nt == 0) return ch;                                                         // no free cell in sight
+    // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
+    if (!pol) { if (sg0 >= (int)((ikmax - 1u) >> 20)) return ch; }
+    else { if ((double)sg0 / (1.0 + (sg0 > 0 ? pown : 0.0)) >= dkmax) return ch; }
+    int win = 0;
+    if (nt > 1) {
+        if (nt > 4) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x4444; nt = 4; }
+        const int n_free = __popcll(fm);
+        int p[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) p[t] = t < nt ? __popcll(fm & ((1ull << (int)((tl >> (16 * t)) & 255ull)) - 1ull)) : -1;
+        const uint64_t akey = ss_agent_key(skey, slot + 1u);
+        uint32_t j = 0;
+        int left = nt;
+#pragma unroll 1
+        for (int i = n_free - 1; i >= 1 && left > 1; i--) {                         // random.py:350 shuffle
+            const uint32_t nn = (uint32_t)i + 1u;
+            const int kbits = 32 - __clz(nn);
+            uint32_t rj = ss_keyed_word(akey, j++) >> (32 - kbits);                 // random.py:242 _randbelow
+            while (rj >= nn) {
+                rj = ss_keyed_word(akey, j++) >> (32 - kbits);
+                if (j > 100000u) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x3333; break; }
+            }
+            // the element at index rj moves to index i and is final there; L[i] moves to rj
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (p[t] < 0) continue;
+                if (p[t] == (int)rj) { p[t] = -1; left--; }
+                else if (p[t] == i) p[t] = (int)rj;
+            }
+        }
+        // the surviving tied candidate ends lowest in the shuffled list
+#pragma unroll
+        for (int t = 3; t >= 0; t--) if (p[t] >= 0) win = t;
+    }
+    const uint32_t ent = (uint32_t)((tl >> (16 * win)) & 0xffffull);
+    const int k = (int)(ent & 255u);
+    int cx, cy;
+    if (k < span) { const int o = k - a; cx = WRAP ? ss_wrap1(gx + o, n) : gx + o; cy = gy; }
+    else { const int o = k - span - a; cx = gx; cy = WRAP ? ss_wrap1(gy + o, n) : gy + o; }
+    ch.cell = cx * n + cy; ch.sg = (int)(ent >> 8);
+    return ch;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -858,10 +975,16 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 // latency of one agent's turn is hidden by the other windows instead of stalling a CTA.  Shared memory per warp:
 // the sorted key list and the blocked bitmap.
 #define SOLO_LIST 1024
+__device__ static inline void ss_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifdef SS_PASS_TIMING       // phase clocks of the warp-per-window kernels -> w.dbg[17..31] (tools/dbg_solo.py)
+#define SOLO_TICK(acc) do { const long long t_now_ = clock64(); (acc) += t_now_ - t_mark; t_mark = t_now_; } while (0)
+#else
+#define SOLO_TICK(acc) do { } while (0)
+#endif
 #ifndef SOLO_MIN_CTAS
 #define SOLO_MIN_CTAS 25
 #endif
-template <int POLT, bool WRAP>
+template <int POLT, bool WRAP, bool LANES>
 __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                             uint32_t* smem, int& cnt_s, int gx0, int gy0, int ex, int ey) {
     typedef GlobCtx<WRAP> GC;
@@ -874,6 +997,8 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     uint32_t* keys = smem;                                  // [SOLO_LIST] priority << 7 | vision + flags (sort key)
     uint32_t* blk_bits = smem + SOLO_LIST;                  // [emax][ew]
     uint16_t* poss = (uint16_t*)(blk_bits + g.emax * g.ew); // [SOLO_LIST] lx << 8 | ly, permuted with the keys
+    uint32_t* shd_bits = (uint32_t*)(poss + SOLO_LIST);     // [emax][ew] lane-per-agent loop: crosses of the core agents blocked in this launch
+    (void)shd_bits;
     const int ew = g.ew;
     const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
     const int nb = w.pend_nb;
@@ -899,6 +1024,10 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
             return;
         }
     }
+    long long t_mark = PASS_CLOCK(), t_scan = 0, t_sort = 0, t_blk = 0, t_dep = 0, t_q1 = 0, t_act = 0, t_fill = 0;
+    unsigned n_rounds = 0, n_blocked = 0, n_lane_slots = 0;
+    (void)t_mark; (void)t_scan; (void)t_sort; (void)t_blk; (void)t_dep; (void)t_q1; (void)t_act; (void)t_fill;
+    (void)n_rounds; (void)n_blocked; (void)n_lane_slots;
     bool dirty = false;
     auto write_map = [&]() {
         if (g.map_write < 0) return;
@@ -925,6 +1054,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     const uint64_t skey = ss_step_key(w.cfg.keyed_seed, iteration);
     const OrderKey ok = ss_order_key(skey, w.half);
     for (int i = lane; i < g.emax * ew; i += 32) blk_bits[i] = 0u;
+    if (LANES) for (int i = lane; i < g.emax * ew; i += 32) shd_bits[i] = 0u;
     if (lane == 0) cnt_s = 0;
     __syncwarp();
     uint32_t pmin = PRIO_INF;       // lowest pending priority of the core (per lane)
@@ -1004,6 +1134,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         if (lane == 0) cnt_s = 0;
         __syncwarp();
     }
+    SOLO_TICK(t_scan);
     if (n_mine == 0) { write_map(); return; }
     if (first) {        // every pending core agent is listed: hash them now, 32 at a time
         for (int i = lane; i < n_mine; i += 32) {
@@ -1032,7 +1163,184 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
             }
         }
     }
+    SOLO_TICK(t_sort);
     ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
+    if (LANES) {
+        // ---- one LANE per agent.  The warp holds the (up to) 32 unresolved list entries of lowest priority, in list
+        // order.  An entry acts in this round iff no blocked agent of lower priority conflicts with it (exact test
+        // against the blocked set, as below) and its cross meets the cross of no earlier entry of the batch; entries
+        // that conflict inside the batch stay for the next round, blocked ones join the blocked set.  Lanes that act
+        // in the same round have disjoint crosses, so their turns commute; the first entry of the batch never waits,
+        // so every round resolves at least one entry.  Everything of lower priority outside the batch is finished
+        // or blocked -- the same invariant as the one-agent-at-a-time loop.
+        int my = -1, next = 0;
+#pragma unroll 1
+        for (;;) {
+            {   // order-preserving refill: waiting entries move to the low lanes, new entries follow
+                const unsigned wm = __ballot_sync(FULL, my >= 0);
+                const int nwait = __popc(wm);
+                const int src = (int)__fns(wm, 0u, lane + 1) & 31;
+                const int moved = __shfl_sync(FULL, my, src);
+                const int fresh = next + lane - nwait;
+                my = lane < nwait ? moved : (fresh < n_mine ? fresh : -1);
+                next = min(n_mine, next + 32 - nwait);
+            }
+            if (!__any_sync(FULL, my >= 0)) break;
+            const bool have = my >= 0;
+            SOLO_TICK(t_fill);
+#ifdef SS_PASS_TIMING
+            n_rounds++; n_lane_slots += __popc(__ballot_sync(FULL, have));
+#endif
+            const uint32_t key = have ? keys[my] : 0u;
+            const uint32_t pa = key >> 7;
+            const int lx = have ? (int)(poss[my] >> 8) : 0, ly = have ? (int)(poss[my] & 255u) : 0;
+            const int a = (int)((key >> 0) & 31u);
+            const int gx = GC::gw(c.gx0 + lx, n), gy = GC::gw(c.gy0 + ly, n);
+            const uint32_t info = have ? ((uint32_t)lx | ((uint32_t)ly << 8) | ((uint32_t)a << 16)) : 0xffffffffu;
+            bool blocked = false, dep = false;
+            {   // conflicts inside the batch: lane m < lane with meeting crosses (four shuffles in flight)
+                const int nb_lanes = __popc(__ballot_sync(FULL, have));        // entries sit in lanes 0 .. nb_lanes-1
+#pragma unroll 1
+                for (int m0 = 0; m0 + 1 < nb_lanes; m0 += 4) {
+                    uint32_t im[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) im[u] = __shfl_sync(FULL, info, (m0 + u) & 31);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (m0 + u < lane && have)
+                            dep |= crosses_meet((int)(im[u] & 255u) - lx, (int)((im[u] >> 8) & 255u) - ly, a, (int)(im[u] >> 16));
+                }
+            }
+            SOLO_TICK(t_dep);
+            const bool cand = have && !dep;
+            if (cand && w.cfg.rule_move_eat) {      // the cross is wanted soon: start it on its way into L2
+                const bool polp = POLT != 0;
+#pragma unroll 1
+                for (int d = 1; d <= a; d++) {
+                    const int ci0 = GC::gw(gx - d, n) * n + gy, ci1 = GC::gw(gx + d, n) * n + gy;
+                    const int ci2 = gx * n + GC::gw(gy - d, n), ci3 = gx * n + GC::gw(gy + d, n);
+                    ss_prefetch_l2(&w.occw[ci0]); ss_prefetch_l2(&w.occw[ci1]);
+                    ss_prefetch_l2(&w.isugar[ci0]); ss_prefetch_l2(&w.isugar[ci1]);
+                    if (d == 1 || ((gy - d) & 7) == 7) ss_prefetch_l2(&w.occw[ci2]);        // 8 words per sector along y
+                    if (d == 1 || ((gy + d) & 7) == 0) ss_prefetch_l2(&w.occw[ci3]);
+                    if (d == 1 || ((gy - d) & 31) == 31) ss_prefetch_l2(&w.isugar[ci2]);
+                    if (d == 1 || ((gy + d) & 31) == 0) ss_prefetch_l2(&w.isugar[ci3]);
+                    if (polp) {
+                        ss_prefetch_l2(&w.poll[ci0]); ss_prefetch_l2(&w.poll[ci1]);
+                        if (d == 1 || ((gy - d) & 3) == 3) ss_prefetch_l2(&w.poll[ci2]);
+                        if (d == 1 || ((gy + d) & 3) == 0) ss_prefetch_l2(&w.poll[ci3]);
+                    }
+                }
+            }
+            // Conflict test against the blocked set.  Filter, per lane: A can only be blocked if it stands within reach
+            // of the ring (ring agents are blocked from the start) or its cross touches the shadow -- the union of the
+            // crosses of the core agents blocked during this launch.  Everything else is free without looking further.
+            bool flagged = false;
+            if (cand) {
+                flagged = lx - a - V < R || lx + a + V >= c.ex - R || ly - a - V < R || ly + a + V >= c.ey - R;
+                if (!flagged) {
+                    const volatile uint32_t* row = shd_bits + lx * ew;
+                    const int c0 = ly - a, w0 = c0 >> 5;
+                    const uint32_t lo = row[w0], hi = (w0 + 1 < ew) ? row[w0 + 1] : 0u;
+                    uint32_t hitbits = __funnelshift_r(lo, hi, c0 & 31) & ((2u << (2 * a)) - 1u);
+                    const volatile uint32_t* col = shd_bits + (lx - a) * ew + (ly >> 5);
+#pragma unroll 1
+                    for (int o = 0; o <= 2 * a; o++) hitbits |= (col[o * ew] >> (ly & 31)) & 1u;
+                    flagged = hitbits != 0u;
+                }
+            }
+            // Exact test for the flagged lanes, one after the other with the whole warp (as in the one-at-a-time loop):
+            // the zone of A cut into segments of one bitmap row each, a segment per lane
+            for (unsigned fl = __ballot_sync(FULL, flagged); fl != 0u; fl &= fl - 1u) {
+                const int f = __ffs(fl) - 1;
+                const uint32_t iF = __shfl_sync(FULL, info, f), paF = __shfl_sync(FULL, pa, f);
+                const int lxF = (int)(iF & 255u), lyF = (int)((iF >> 8) & 255u), aF = (int)(iF >> 16);
+                bool hit = false;
+                const int nseg = 2 * V + 3 + 2 * aF;
+#pragma unroll 1
+                for (int seg = lane; seg < nseg; seg += 32) {
+                    int dx, c0, len, dy0;
+                    if (seg <= 2 * V) { dx = seg - V; c0 = lyF - V; len = 2 * V + 1; dy0 = -V; }
+                    else if (seg == 2 * V + 1) { dx = 0; c0 = lyF - V - aF; len = aF; dy0 = -V - aF; }
+                    else if (seg == 2 * V + 2) { dx = 0; c0 = lyF + V + 1; len = aF; dy0 = V + 1; }
+                    else { const int k = seg - (2 * V + 3); dx = (k & 1) ? (V + 1 + (k >> 1)) : -(V + 1 + (k >> 1)); c0 = lyF; len = 1; dy0 = 0; }
+                    const int r = lxF + dx;
+                    const volatile uint32_t* row = blk_bits + r * ew;
+                    const int w0 = c0 >> 5, shf = c0 & 31;
+                    const uint32_t lo = row[w0], hi = (w0 + 1 < ew) ? row[w0 + 1] : 0u;
+                    uint32_t bits = __funnelshift_r(lo, hi, shf) & ((1u << len) - 1u);
+                    while (bits) {
+                        const int i = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int q = c0 + i, dy = dy0 + i;
+                        if (dx == 0 && dy == 0) continue;
+                        const uint32_t bw = __ldcg(&w.occw[cell_of(c, r, q)]);
+                        if (bw != 0u && crosses_meet(dx, dy, aF, occ_vision(bw)) && ss_priority(ok, occ_slot(bw)) < paF) hit = true;
+                    }
+                }
+                const bool any_hit = __any_sync(FULL, hit);
+                if (lane == f) blocked = any_hit;
+            }
+            __syncwarp();
+            SOLO_TICK(t_blk);
+            const uint32_t slot = ss_priority_inverse(ok, pa);
+            const uint32_t ow = (cur_phase << 31) | ((key & 0x7fu) << 24) | slot;
+            bool skipped = false;
+            const bool go = have && !blocked && !dep;
+            if (go && (ow & OCC_Q1)) {      // Q1: the at-risk predecessor decides whether A gets its turn
+                const AgentRec* rec = &w.agents[slot];
+                if (rec->pred_step == (uint32_t)(iteration + 1)) {
+                    const volatile uint32_t* stp = &w.agents[rec->pred - 1u].status;
+                    uint32_t st = *stp;
+                    for (int tries = 0; tries < 4 && (st >> 2) != (uint32_t)(iteration + 1); tries++) { __nanosleep(250); st = *stp; }
+                    if ((st >> 2) != (uint32_t)(iteration + 1)) blocked = true;     // retry in a later launch
+                    else skipped = ((st & 3u) == ST_DIED);
+                }
+            }
+            __syncwarp();
+            SOLO_TICK(t_q1);
+#ifdef SS_PASS_TIMING
+            n_blocked += __popc(__ballot_sync(FULL, have && blocked));
+#endif
+            if (have && blocked) {          // joins the blocked set; its cross joins the shadow
+                atomicOr(&blk_bits[lx * ew + (ly >> 5)], 1u << (ly & 31));
+                const int c0 = ly - a, w0 = c0 >> 5, shf = c0 & 31;
+                const unsigned long long m = (unsigned long long)((2u << (2 * a)) - 1u) << shf;
+                atomicOr(&shd_bits[lx * ew + w0], (uint32_t)m);
+                if ((uint32_t)(m >> 32) != 0u) atomicOr(&shd_bits[lx * ew + w0 + 1], (uint32_t)(m >> 32));
+#pragma unroll 1
+                for (int o = -a; o <= a; o++) atomicOr(&shd_bits[(lx + o) * ew + (ly >> 5)], 1u << (ly & 31));
+                my = -1;
+            } else if (go && skipped) {     // loses its turn: stays put, no metabolism (Q1)
+                const uint32_t nw = occ_pack(slot, a, next_phase);
+                w.occw[(size_t)gx * n + gy] = nw;
+                if (ow & OCC_RISK)
+                    *((volatile uint32_t*)&w.agents[slot].status) = ((uint32_t)(iteration + 1) << 2) | ST_SKIPPED;
+                ts.resolved++;
+                if (w.log) {
+                    ShardLogEntry en;
+                    en.slot = slot; en.old_cell = en.new_cell = (uint32_t)(gx * n + gy); en.new_word = nw;
+                    en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.turn = 0u; en.kind_harvest = 2u;
+                    en.status = (ow & OCC_RISK) ? (((uint32_t)(iteration + 1) << 2) | ST_SKIPPED) : 0u;
+                    *log_slot(w, ts) = en;
+                }
+                my = -1;
+            } else if (go) {
+                const bool risky = (ow & OCC_RISK) != 0;
+                double sugar = 0.0;
+                uint32_t attr = 0u;
+                if (risky) { sugar = w.agents[slot].sugar; attr = w.agents[slot].attr; }
+                LaneChoice ch;
+                if (w.cfg.rule_move_eat) ch = lane_choose_cell<POLT, WRAP>(w, gx, gy, a, slot, skey);
+                else { ch.cell = gx * n + gy; ch.sg = 0; }
+                commit_turn(w, c, lx, ly, lx, ly, gx * n + gy, ch.cell, ch.sg, a, risky, slot, sugar, attr, iteration, env_time,
+                            next_phase, ts);
+                my = -1;
+            }
+            __syncwarp();
+            SOLO_TICK(t_act);
+        }
+    } else
     for (int it = 0; it < n_mine; it++) {
         // the key carries everything of the agent's occupancy word: the slot is the inverse of the priority, and
         // nobody else changes the word before the agent's own turn
@@ -1113,11 +1421,27 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         }
         __syncwarp();
     }
-    if (lane == 0)
-        while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;      // unused part of the reserved slice
+    while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;      // unused part of the reserved slice
     __syncwarp();
+    if (!LANES) SOLO_TICK(t_act);
     write_map();
-    // only lane 0 commits turns, so its counters are the warp's
+#ifdef SS_PASS_TIMING
+    if (w.dbg && lane == 0) {
+        atomicAdd(&w.dbg[17], 1ull); atomicAdd(&w.dbg[18], (unsigned long long)t_scan); atomicAdd(&w.dbg[19], (unsigned long long)t_sort);
+        atomicAdd(&w.dbg[20], (unsigned long long)t_fill); atomicAdd(&w.dbg[21], (unsigned long long)t_blk);
+        atomicAdd(&w.dbg[22], (unsigned long long)t_dep); atomicAdd(&w.dbg[23], (unsigned long long)t_q1);
+        atomicAdd(&w.dbg[24], (unsigned long long)t_act); atomicAdd(&w.dbg[25], (unsigned long long)n_rounds);
+        atomicAdd(&w.dbg[26], (unsigned long long)n_lane_slots); atomicAdd(&w.dbg[27], (unsigned long long)n_blocked);
+        atomicAdd(&w.dbg[28], (unsigned long long)n_mine);
+    }
+#endif
+    if (LANES) {            // every lane commits turns: add the counters up
+        ts.sum_m = __reduce_add_sync(FULL, ts.sum_m); ts.sum_v = __reduce_add_sync(FULL, ts.sum_v);
+        ts.acted = __reduce_add_sync(FULL, ts.acted); ts.deaths = __reduce_add_sync(FULL, ts.deaths);
+        ts.small = __reduce_add_sync(FULL, ts.small); ts.inexact = __reduce_add_sync(FULL, ts.inexact);
+        ts.resolved = __reduce_add_sync(FULL, ts.resolved);
+    }
+    // (otherwise only lane 0 commits turns, so its counters are the warp's)
     if (lane == 0) {
         if (ts.sum_m) atomicAdd(&w.acc->sum_metab, (unsigned long long)ts.sum_m);
         if (ts.sum_v) atomicAdd(&w.acc->sum_vision, (unsigned long long)ts.sum_v);
@@ -1129,8 +1453,11 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     }
 }
 
-template <int POLT>
-__global__ void __launch_bounds__(32, SOLO_MIN_CTAS)
+#ifndef LANES_MIN_CTAS
+#define LANES_MIN_CTAS 20
+#endif
+template <int POLT, bool LANES>
+__global__ void __launch_bounds__(32, LANES ? LANES_MIN_CTAS : SOLO_MIN_CTAS)
 ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int cnt_s;
@@ -1142,8 +1469,8 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
     const int ex = x_hi - x_lo, ey = y_hi - y_lo;
     const int gx0 = ss_wrap1(x_lo + g.shift_x, n), gy0 = ss_wrap1(y_lo + g.shift_y, n);
-    if (gx0 + ex > n || gy0 + ey > n) solo_window<POLT, true>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
-    else solo_window<POLT, false>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
+    if (gx0 + ex > n || gy0 + ey > n) solo_window<POLT, true, LANES>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
+    else solo_window<POLT, false, LANES>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
 }
 
 // -------------------------------------------------------------------- multi-GPU replicas ----
@@ -2020,14 +2347,20 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
     return cudaGetLastError();
 }
 
-size_t ss_solo_smem_bytes(int emax, int ew) { return (size_t)SOLO_LIST * 6 + (size_t)emax * ew * 4; }
-cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
+// key list + positions + blocked bitmap (+ the shadow bitmap of the lane-per-agent loop)
+size_t ss_solo_smem_bytes(int emax, int ew, int lanes) { return (size_t)SOLO_LIST * 6 + (size_t)emax * ew * (lanes ? 8 : 4); }
+cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time, int lanes,
                                 cudaStream_t s) {
     if (g.bx_cnt <= 0) return cudaSuccess;
-    const size_t smem = ss_solo_smem_bytes(g.emax, g.ew);
+    const size_t smem = ss_solo_smem_bytes(g.emax, g.ew, lanes);
     const int grid = g.nwin * g.bx_cnt;
-    if (w.cfg.rule_pollution) ss_move_solo_kernel<1><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
-    else ss_move_solo_kernel<0><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+    if (lanes) {
+        if (w.cfg.rule_pollution) ss_move_solo_kernel<1, true><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+        else ss_move_solo_kernel<0, true><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+    } else {
+        if (w.cfg.rule_pollution) ss_move_solo_kernel<1, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+        else ss_move_solo_kernel<0, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+    }
     return cudaGetLastError();
 }
 

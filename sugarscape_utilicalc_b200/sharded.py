@@ -302,7 +302,7 @@ def bench_main(args, wl):
             "cell_updates_per_s": n * n * K / (step_ms * K * 1e-3),
             "population": [int(pop0), int(st["population"][-1])],
             "passes_per_step": (de.passes - p0) / K, "gpu_launches": de.r.eng.counters()["launches"] - l0,
-            "move_pass": {"impl": ["cta_per_window", "warp_per_window"][de.r.eng.counters()["pass_impl"]],
+            "move_pass": {"impl": ["cta_per_window", "warp_per_window", "lane_per_agent"][de.r.eng.counters()["pass_impl"]],
                           "window": de.r.eng.counters()["window"]},
             "nccl_bytes_sent_per_rank_per_step": (de.bytes_sent - b0) / K,
             "rank0_ms_per_step": {k: 1e3 * v / K for k, v in de.t.items()},

@@ -57,24 +57,27 @@ def test_keyed_lattice_path(name):
     (64, True, 12, (1, 6)), (177, True, 10, (1, 6)), (200, False, 10, (1, 6)), (257, True, 8, (1, 6)),
     (300, True, 8, (1, 10)), (512, True, 8, (1, 6)), (1000, True, 5, (1, 6)), (1024, False, 6, (1, 6)),
 ])
-@pytest.mark.parametrize("impl", ["cta_per_window", "warp_per_window"])
+@pytest.mark.parametrize("impl", ["cta_per_window", "warp_per_window", "lane_per_agent"])
 def test_lattice_vs_oracle_synthetic(n, pollution, steps, vision, impl):
-    """Both move-pass kernels (ss_move_pass_kernel: a CTA per window, a warp per region; ss_move_solo_kernel: a warp
-    per window, here with windows of at most 96 cells so that small lattices have several) against the CPU oracle."""
+    """The move-pass kernels (ss_move_pass_kernel: a CTA per window, a warp per region; ss_move_solo_kernel: a warp
+    per window, here with windows of at most 96 cells so that small lattices have several, taking its agents one at a
+    time or -- pass_impl 2 -- 32 at a time, one lane each) against the CPU oracle."""
     s, init = common.synthetic_case(n, pollution, vision=vision)
     cfg = config_from_settings(s, rng_mode="keyed")
-    opts = {"pass_impl": 0} if impl == "cta_per_window" else {"pass_impl": 1, "solo_window": 96 if vision[1] <= 6 else 120}
+    solo = {"warp_per_window": 1, "lane_per_agent": 2}.get(impl, 0)
+    opts = {"pass_impl": 0} if not solo else {"pass_impl": solo, "solo_window": 96 if vision[1] <= 6 else 120}
     e, o = common.engine_world(cfg, options=opts), common.oracle_world(cfg)
     common.init_world(e, init, "keyed")
     common.init_world(o, init, "keyed")
     assert e.counters()["path"] == 2
-    assert e.counters()["pass_impl"] == (1 if impl == "warp_per_window" and n >= 177 else 0)
+    assert e.counters()["pass_impl"] == (solo if n >= 177 else 0)
     common.compare_worlds(e, o, steps, what="synthetic %d %s" % (n, impl))
     e.close()
     o.close()
 
 
-@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 1, "solo_window": 128}])
+@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 1, "solo_window": 128},
+                                  {"pass_impl": 2, "solo_window": 72}])
 def test_lattice_dense_population(opts):
     """density 1/3: deep dependency chains, many ties, many deaths (Q1 skips); density 0.9 overflows the key lists
     of the warp-per-window kernel (priority-threshold trimming)."""
@@ -99,7 +102,7 @@ def test_lattice_dense_population(opts):
     common.compare_worlds(e, o, 4, what="dense 256 (0.9)")
 
 
-@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}])
+@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 2, "solo_window": 72}])
 def test_lattice_seasons(opts):
     s, init = common.synthetic_case(260, False, seasons=True)
     s["rule_params"]["seasons"]["period"] = 3
@@ -175,7 +178,7 @@ def test_empty_population_and_extinction():
         assert e.agent_count() == len(o.download_agents()["id"]) == 0
 
 
-@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}])
+@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 2, "solo_window": 72}])
 @pytest.mark.parametrize("world,n,pollution", [(2, 300, True), (3, 512, False), (4, 130, True)])
 def test_multi_gpu_replicas_equal_single_gpu_and_oracle(world, n, pollution, opts):
     """The N>1 code path (window rows sharded over replicas, turn logs replayed) on one GPU with
