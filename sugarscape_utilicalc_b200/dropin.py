@@ -16,6 +16,7 @@ import random as _pyrandom
 
 import numpy as np
 
+from . import outputs
 from .settings import config_from_settings
 
 
@@ -36,21 +37,57 @@ def _snapshot_view(view):
 
 
 class DropinHandle:
-    def __init__(self, ss, view, world, rng):
+    def __init__(self, ss, view, world, rng, keyed_seed=None, events=True, gui=False):
         self.ss, self.view, self.world, self.rng = ss, view, world, rng
         self.by_id = {a.id: a for a in view.agents}
         self.original_update = view.updateGame
+        self.events, self.gui = events, gui
+        self.keyed_seed = ss.seed if keyed_seed is None else keyed_seed
+        self.list_ids = [a.id for a in view.agents]
+        self.n_slots = max(self.list_ids, default=1)
+
+    def _order_before_step(self):
+        """The order `updateGame` walks the agents in (sugarscape.py:517-520), recomputed on the host."""
+        if self.rng == "mt":
+            mt, idx = self.world.get_rng_mt19937()
+            return outputs.execution_order_mt(self.list_ids, mt, idx)
+        pr = outputs.keyed_priorities(self.keyed_seed, self.view.iteration, self.list_ids, self.n_slots)
+        return [self.list_ids[k] for k in np.argsort(pr, kind="stable")]
 
     def update_game(self):
-        """One `updateGame()`: same observable effects on the View (sugarscape.py:603-619, 670-671)."""
+        """One `updateGame()`: same observable effects on the View -- stat series (sugarscape.py:603-619), death
+        events in execution order (:598-600), iteration / env.time (:670-671), the GUI refresh calls (:665-675, with
+        `gui=True`: the state is synced back first), the step-100 sample and the plateau rule (:676-686)."""
         v = self.view
+        order = self._order_before_step() if self.events else None
         st = self.world.step(1)[0]
+        if self.events:
+            self.list_ids = [int(i) for i in self.world.download_agents()["id"]]
+            for i in outputs.deaths_in_order(order, self.list_ids):
+                v.appendToLog("Agent " + str(i) + " died of starvation", indent="    ")
         v.population.append(int(st["population"]))
         v.metabolismMean.append(float(st["metabolism_mean"]))
         v.visionMean.append(float(st["vision_mean"]))
         v.gini.append(float(st["gini"]))
+        if self.gui:
+            self.sync_back()
+            if v.iteration % self.ss.graphUpdateFrequency == 0 and len(v.onGraphs) > 0:
+                v.updateGraphs()
         v.iteration += 1
         v.env.incrementTime()
+        if self.gui:
+            v.updateStatsWindow()
+            v.updateLocationStatsWindow()
+            v.drawLocationCanvas()
+        if v.iteration == 100:
+            v.pop_at_100 = v.population[-1]
+            v.gini_at_100 = v.gini[-1]
+        if v.iteration >= 200:
+            v.population_200_ago = v.population[len(v.population) - 200]
+        if v.population[-1] == v.population_200_ago:
+            data_to_write = [self.ss.seed, v.pop_at_100, round(v.gini_at_100, 2), str(v.population[-1])]
+            outputs.update_data_file("data_collection/data.txt", data_to_write)
+            raise outputs.PlateauReached()
 
     def sync_back(self):
         """HBM -> Environment.grid slots 0/4/5 and Agent.x/y/sugar/alive; View.agents in list order."""
@@ -87,10 +124,12 @@ class DropinHandle:
         self.view.updateGame = self.original_update
 
 
-def install(ss, view, rng="mt", keyed_seed=None, world_factory=None):
+def install(ss, view, rng="mt", keyed_seed=None, world_factory=None, events=True, gui=False):
     """Replace `view.updateGame` by the engine.  `ss` is the imported reference module (its
     `settings` dict is the settings.json the run was started with).  `world_factory(cfg)` builds the
-    backend; default = the CUDA engine (tests inject the CPU oracle to check this glue without a GPU)."""
+    backend; default = the CUDA engine (tests inject the CPU oracle to check this glue without a GPU).
+    `events`: keep `view.log` complete (one id read-back per step -- GUI-scale worlds; switch off for large ones).
+    `gui`: sync the state back and call the reference's per-step window refreshes, as `updateGame` does."""
     cfg = config_from_settings(ss.settings, rng_mode=rng, keyed_seed=keyed_seed, iteration=view.iteration,
                                env_time=view.env.getTime())
     if world_factory is None:
@@ -103,6 +142,6 @@ def install(ss, view, rng="mt", keyed_seed=None, world_factory=None):
     if rng == "mt":
         st = _pyrandom.getstate()[1]
         world.set_rng_mt19937(np.array(st[:624], dtype=np.uint32), int(st[624]))
-    h = DropinHandle(ss, view, world, rng)
+    h = DropinHandle(ss, view, world, rng, keyed_seed=keyed_seed, events=events, gui=gui)
     view.updateGame = h.update_game
     return h

@@ -150,3 +150,38 @@ def smoke_check():
     compare_worlds(e, o, 6, what="synthetic 200x200")
     assert e.counters()["path"] == 2, "lattice path was not selected"
     e.close()
+
+
+OUTPUT_CASES = ["c1_default_moveeat_mt", "c1_default_moveeat_keyed", "c2_pollution_mt"]
+
+
+def check_outputs_against_golden(name, kind, tmp_dir, path=-1):
+    """SURVEY 8 f1 without the reference at hand: `outputs.RunRecorder` over `kind` ("oracle" | "engine") reproduces
+    the event log, the plateau exit, the data.txt column and the createLogFile text recorded from the unmodified
+    reference (tests/golden/outputs.json, made by tests/golden/make_outputs_golden.py)."""
+    from sugarscape_utilicalc_b200 import outputs
+    with open(os.path.join(GOLDEN, "outputs.json")) as f:
+        exp = json.load(f)[name]
+    g = load_golden(name)
+    w = world_from_golden(g, kind, path)
+    data_file = os.path.join(str(tmp_dir), "data.txt")
+    rec = outputs.RunRecorder(g["settings"], w, rng=g["rng"], data_file=data_file)
+    exited = None
+    for _ in range(exp["steps"]):
+        try:
+            rec.step()
+        except outputs.PlateauReached:
+            exited = rec.iteration
+            break
+    assert exited == exp["exited_at"]
+    assert rec.log == exp["log"]
+    assert (rec.pop_at_100, rec.gini_at_100) == (exp["pop_at_100"], exp["gini_at_100"]) or kind == "engine"
+    assert rec.pop_at_100 == exp["pop_at_100"] and abs(rec.gini_at_100 - exp["gini_at_100"]) <= 1e-9
+    got_data = open(data_file).read() if os.path.exists(data_file) else None
+    assert got_data == exp["data_txt"]
+    stats = rec.stats()
+    assert stats == exp["stats"]
+    text = outputs.log_file_text(g["settings"], g["settings"]["env"]["random_seed"], rec.metabolismMean, rec.visionMean,
+                                 rec.gini, stats, rec.log)
+    assert text == exp["log_file_text"]
+    w.close()

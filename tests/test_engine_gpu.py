@@ -27,6 +27,12 @@ def test_mt_exact_presets(name):
     w.close()
 
 
+@pytest.mark.parametrize("name", common.OUTPUT_CASES)
+def test_on_disk_outputs_match_reference_golden(name, tmp_path):
+    """SURVEY 8 f1 on the GPU: event log in execution order, plateau exit, data.txt and createLogFile text."""
+    common.check_outputs_against_golden(name, "engine", tmp_path)
+
+
 def test_mt_exact_single_steps_equal_fused_steps():
     g = common.load_golden("c2_pollution_mt")
     w = common.world_from_golden(g, "engine")

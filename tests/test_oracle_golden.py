@@ -17,3 +17,8 @@ def test_oracle_chunked_steps_equal_single_steps():
     w = common.world_from_golden(g, "oracle")
     common.run_against_golden(g, w, exact_gini=True, chunk=7, max_steps=100)
     w.close()
+
+
+@pytest.mark.parametrize("name", common.OUTPUT_CASES)
+def test_run_recorder_outputs_match_reference_golden(name, tmp_path):
+    common.check_outputs_against_golden(name, "oracle", tmp_path)

@@ -108,3 +108,92 @@ def test_dropin_install_glue_with_reference_view():
     a, b = run.snapshot(), ref.snapshot()
     for k in ("sugar", "pollution", "occ", "order", "x", "y", "sugar_agent", "mt"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def _moveeat_settings(rh):
+    s = rh.load_settings(None)
+    s["rules"]["moveEat"], s["rules"]["utilicalc"] = True, False
+    return s
+
+
+@pytest.mark.parametrize("rng", ["mt", "keyed"])
+def test_dropin_event_log_plateau_rule_and_log_file(rng, tmp_path):
+    """the installed updateGame leaves the same `View.log` (death events in execution order), step-100
+    sample, plateau exit with the same `data_collection/data.txt`, and `createLogFile` text as the reference."""
+    import glob
+    import os
+    import ref_harness as rh
+    from sugarscape_utilicalc_b200 import dropin, outputs
+    s = _moveeat_settings(rh)
+    limit = 330
+    ref = rh.ReferenceRun(s, rng=rng)
+    ref.run(limit)                  # MT stream: the reference exits at iteration 307 through the plateau rule
+    assert rng != "mt" or ref.exited_at is not None
+    with rh._cwd(ref.scratch):
+        ref.view.createLogFile()
+        ref_log_text = open(glob.glob(os.path.join(ref.scratch, "logs", "log_*.txt"))[0]).read()
+    data_path = os.path.join(ref.scratch, "data_collection", "data.txt")
+    ref_data = open(data_path).read() if os.path.exists(data_path) else None
+    exp_log, exited_at = list(ref.view.log), ref.exited_at
+
+    run = rh.ReferenceRun(s, rng="mt")                  # a fresh reference View; the engine side draws its own words
+    h = dropin.install(run.ss, run.view, rng=rng, world_factory=common.oracle_world)
+    got_exit = None
+    with rh._cwd(run.scratch):
+        for _ in range(limit):
+            try:
+                run.view.updateGame()
+            except outputs.PlateauReached:
+                got_exit = run.view.iteration
+                break
+        data_path = os.path.join(run.scratch, "data_collection", "data.txt")
+        got_data = open(data_path).read() if os.path.exists(data_path) else None
+    assert got_exit == exited_at
+    assert run.view.log == exp_log[:len(run.view.log)] and len(run.view.log) > 50
+    if ref_data is None:
+        assert got_data is None and run.view.log == exp_log
+    else:       # the reference (exit() swallowed) appends one more column per further step: ours is its first column
+        assert got_data == "\n".join(l.split(", ")[0] for l in ref_data.strip().split("\n")) + "\n"
+    assert (run.view.pop_at_100, run.view.gini_at_100) == (ref.view.population[99], ref.view.gini[99])
+    # the reference kept stepping after its swallowed exit(): compare the log file over the common prefix
+    h.sync_back()
+    k = got_exit if got_exit is not None else limit
+    stats = outputs.ending_stats(k, run.view.population, run.view.metabolismMean, run.view.visionMean, run.view.gini,
+                                 [a.getSugar() for a in run.view.agents])
+    text = outputs.log_file_text(run.ss.settings, run.ss.seed, run.view.metabolismMean, run.view.visionMean, run.view.gini,
+                                 stats, run.view.log)
+    ref2 = rh.ReferenceRun(s, rng=rng)
+    ref2.run(k)
+    with rh._cwd(ref2.scratch):
+        ref2.view.createLogFile()
+        ref2_text = open(glob.glob(os.path.join(ref2.scratch, "logs", "log_*.txt"))[0]).read()
+    assert text == ref2_text
+    assert stats == ref2.view.stats
+    assert ref_log_text.startswith(text[:text.index("\nStat lists:")])
+
+
+def test_run_recorder_headless_equals_reference(tmp_path):
+    """`outputs.RunRecorder` (no reference objects at all) on the shipped pollution preset: event log, series and
+    data file equal the reference's."""
+    import os
+    import ref_harness as rh
+    from sugarscape_utilicalc_b200 import outputs
+    s = rh.load_settings("pollution")
+    ref = rh.ReferenceRun(s)
+    init = ref.snapshot()
+    mt0, idx0 = ref.mt_state()
+    ref.run(120)
+    cfg = config_from_settings(s, rng_mode="mt")
+    w = common.oracle_world(cfg)
+    w.upload_cells(init["sugar"], init["cap"], init["pollution"])
+    w.upload_agents(init["order"], init["x"], init["y"], init["vision"], init["metab"], init["sugar_agent"])
+    w.set_rng_mt19937(mt0, idx0)
+    rec = outputs.RunRecorder(s, w, rng="mt", data_file=str(tmp_path / "data.txt"))
+    for _ in range(120):
+        rec.step()
+    assert rec.log == ref.view.log and len(rec.log) > 20
+    assert rec.population == ref.view.population and rec.gini == ref.view.gini
+    assert (rec.pop_at_100, rec.gini_at_100) == (ref.view.pop_at_100, ref.view.gini_at_100)
+    ref.view.makeStatsDict()
+    assert rec.stats() == ref.view.stats
+    assert not os.path.exists(str(tmp_path / "data.txt"))
