@@ -975,6 +975,9 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 // latency of one agent's turn is hidden by the other windows instead of stalling a CTA.  Shared memory per warp:
 // the sorted key list and the blocked bitmap.
 #define SOLO_LIST 1024
+#ifndef SOLO_SCAN_ROWS
+#define SOLO_SCAN_ROWS 8
+#endif
 __device__ static inline void ss_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifdef SS_PASS_TIMING       // phase clocks of the warp-per-window kernels -> w.dbg[17..31] (tools/dbg_solo.py)
 #define SOLO_TICK(acc) do { const long long t_now_ = clock64(); (acc) += t_now_ - t_mark; t_mark = t_now_; } while (0)
@@ -1088,16 +1091,16 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         if (first && ringbits) atomicOr(&blk_bits[lx * ew + (ly0 >> 5)], ringbits);
     };
     for (;;) {
-        // four window rows per iteration (four loads in flight per lane), lanes across the row
+        // SOLO_SCAN_ROWS window rows per iteration (as many loads in flight per lane), lanes across the row
 #pragma unroll 1
-        for (int lx0 = 0; lx0 < c.ex; lx0 += 4) {
+        for (int lx0 = 0; lx0 < c.ex; lx0 += SOLO_SCAN_ROWS) {
 #pragma unroll 1
             for (int g0 = 0; g0 < gpr; g0 += 32) {
                 const int grp = g0 + lane, ly0 = grp * per;
                 const int gyw = GC::gw(c.gy0 + ly0, n);
-                uint4 ov[4];
+                uint4 ov[SOLO_SCAN_ROWS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < SOLO_SCAN_ROWS; u++) {
                     ov[u] = make_uint4(0u, 0u, 0u, 0u);
                     if (grp < gpr && lx0 + u < c.ex) {
                         const size_t gi = (size_t)GC::gw(c.gx0 + lx0 + u, n) * n + gyw;
@@ -1106,7 +1109,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) visit(lx0 + u, ly0, ov[u]);
+                for (int u = 0; u < SOLO_SCAN_ROWS; u++) visit(lx0 + u, ly0, ov[u]);
             }
         }
         __syncwarp();
@@ -1165,6 +1168,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     }
     SOLO_TICK(t_sort);
     ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
+    uint32_t slot_batch = 0u;
     if (LANES) {
         // ---- one LANE per agent.  The warp holds the (up to) 32 unresolved list entries of lowest priority, in list
         // order.  An entry acts in this round iff no blocked agent of lower priority conflicts with it (exact test
@@ -1342,13 +1346,14 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         }
     } else
     for (int it = 0; it < n_mine; it++) {
-        // the key carries everything of the agent's occupancy word: the slot is the inverse of the priority, and
-        // nobody else changes the word before the agent's own turn
+        // the key carries everything of the agent's occupancy word: the slot is the inverse of the priority (computed
+        // for 32 list entries at a time, one per lane), and nobody else changes the word before the agent's own turn
+        if ((it & 31) == 0) slot_batch = ss_priority_inverse(ok, keys[min(it + lane, n_mine - 1)] >> 7);
         const uint32_t key = keys[it];
         const uint32_t pa = key >> 7;
         const int lx = (int)(poss[it] >> 8), ly = (int)(poss[it] & 255u);
         const int gx = GC::gw(c.gx0 + lx, n), gy = GC::gw(c.gy0 + ly, n);
-        const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | ss_priority_inverse(ok, pa);
+        const uint32_t ow = (cur_phase << 31) | (((uint32_t)key & 0x7fu) << 24) | __shfl_sync(FULL, slot_batch, it & 31);
         const int a = occ_vision(ow);
         bool blocked = false;
         // A's cross: loads issued now, consumed after the conflict test (wasted if A turns out blocked).  Issuing them
