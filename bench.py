@@ -187,15 +187,16 @@ def run_engine_single(args, wl):
                                 "share": (kt["prepare"] + kt["stats"]) / tot}
     dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
     # DRAM bytes of the dominant kernel's launches of one step, from the committed ncu --set full captures
-    # (profiles/r01c_*.csv: dram__bytes_read.sum + dram__bytes_write.sum, summed over the step's launches)
-    traffic_tbl = {("c5", "move", 1): 25.1e9, ("c4", "move", 1): 1.515e9, ("c4", "diffuse", 1): 210.7e6, ("c4", "diffuse", 0): 210.7e6}
+    # (profiles/r01d_ncu_full_move_solo_c5.csv, r01c_*_c4.csv: dram__bytes_read.sum + dram__bytes_write.sum, summed over
+    # the step's launches)
+    traffic_tbl = {("c5", "move", 1): 24.4e9, ("c4", "move", 1): 1.515e9, ("c4", "diffuse", 1): 210.7e6, ("c4", "diffuse", 0): 210.7e6}
     traffic = traffic_tbl.get((wl.get("key"), dom, cnt["pass_impl"]))
     move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel", "ss_move_solo_kernel (lanes)"][cnt["pass_impl"]]
     roofline = {"bound": "hbm", "kernel": {"move": move_kernel + " (all passes of a step) + ss_settle_kernel",
                                            "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic,
-                "traffic_source": "profiles/r01c_ncu_full_*.csv (bytes per step, same launch set)" if traffic else None,
+                "traffic_source": "profiles/r01d_ncu_full_move_solo_c5.csv / r01c_ncu_full_*_c4.csv (bytes per step, same launch set)" if traffic else None,
                 "peak_source": peak_src,
                 "ms_per_launch_set": kernels[dom]["ms_per_step"]}
     whole_bytes = ab["move"] + ab["grow"] + ab["diffuse"]

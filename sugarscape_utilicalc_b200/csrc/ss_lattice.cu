@@ -1277,7 +1277,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
                         const int i = __ffs(bits) - 1;
                         bits &= bits - 1;
                         const int q = c0 + i, dy = dy0 + i;
-                        if (dx == 0 && dy == 0) continue;
+                        if ((dx == 0 && dy == 0) || !crosses_meet(dx, dy, aF, V)) continue;
                         const uint32_t bw = __ldcg(&w.occw[cell_of(c, r, q)]);
                         if (bw != 0u && crosses_meet(dx, dy, aF, occ_vision(bw)) && ss_priority(ok, occ_slot(bw)) < paF) hit = true;
                     }
@@ -1382,7 +1382,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
                     const int i = __ffs(bits) - 1;
                     bits &= bits - 1;
                     const int q = c0 + i, dy = dy0 + i;
-                    if (dx == 0 && dy == 0) continue;
+                    if ((dx == 0 && dy == 0) || !crosses_meet(dx, dy, a, V)) continue;     // V >= the blocker's vision: no load needed
                     const uint32_t bw = __ldcg(&w.occw[cell_of(c, r, q)]);
                     if (bw != 0u && crosses_meet(dx, dy, a, occ_vision(bw)) && ss_priority(ok, occ_slot(bw)) < pa) hit = true;
                 }

@@ -200,6 +200,20 @@ def test_multi_gpu_replicas_equal_single_gpu_and_oracle(world, n, pollution, opt
     o.close()
 
 
+def test_multi_gpu_eight_replicas():
+    """World size 8 (the largest the bench is launched with): 16 window rows, two per rank."""
+    from sugarscape_utilicalc_b200.sharded import VirtualRanks
+    s, init = common.synthetic_case(1024, False)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    v, o = VirtualRanks(cfg, 8, options={"pass_impl": 1, "solo_window": 64}), common.oracle_world(cfg)
+    common.init_world(v, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert v.ranks[0].eng.counters()["pass_impl"] == 1
+    common.compare_worlds(v, o, 4, what="virtual ranks 8")
+    v.close()
+    o.close()
+
+
 def test_multi_gpu_replicas_on_reference_golden():
     from sugarscape_utilicalc_b200.sharded import VirtualRanks
     g = common.load_golden("c2_pollution0_keyed")
