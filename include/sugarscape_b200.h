@@ -88,6 +88,37 @@ int  ss_create(const ss_config* cfg, int32_t device, ss_engine** out);
 void ss_destroy(ss_engine* e);
 const char* ss_last_error(ss_engine* e);
 
+/* Replaces: `random.seed(seed)` at import (sugarscape.py:160-162) for a non-negative integer seed: CPython seeds
+ * MT19937 with init_by_array over the seed's 32-bit words (Modules/_randommodule.c). */
+int  ss_seed_mt19937(ss_engine* e, uint64_t seed);
+
+/* The world the reference's `__main__` builds before the first step (sugarscape.py:1485-1555), SURVEY 8 f4. */
+typedef struct {
+    int32_t n_sites;              /* sugar sites added with addSugarSite (sugarscape.py:1494-1497: ne, sw) */
+    int32_t site_x[4], site_y[4], site_radius[4];     /* env.sites.<name>.{x,y,radius}                     */
+    int32_t grow_to_capacity;     /* rules.grow: env.grow(maxCapacity) before the agents (sugarscape.py:1525) */
+    int32_t n_groups;             /* entries of `distributions` (sugarscape.py:141-146): blue, red         */
+    int32_t group_count[4];       /* env.total_agents.{blue,red}                                           */
+    int32_t max_metabolism;       /* agents.max_agent_metabolism                                           */
+    int32_t max_vision;           /* agents.max_agent_vision                                               */
+    int32_t endowment_min, endowment_max;             /* agents.initial_endowments                         */
+    int32_t age_min, age_max;     /* agents.death_age_range (drawn, unused without limitedLifespan)        */
+    int32_t childbearing[2][4];   /* by the drawn sex 0/1: (min_start, max_start, min_end, max_end) of
+                                     `childbearing = fertility[0], fertility[1]` (sugarscape.py:103-108): the
+                                     reference indexes the "male" tuple with sex 0                          */
+    int32_t foresight_lo, foresight_hi;               /* Environment.foresightRange, (0,0) without the rule:
+                                     Agent.__init__ draws from it regardless (agent.py:165, 329-333)        */
+} ss_init_params;
+
+/* Replaces: Environment.addSugarSite x n_sites (environment.py:114-126), setMaxCapacity, env.grow(maxCapacity),
+ * and per agent `Agent(env)` + `initAgent` (sugarscape.py:242-265: getRandomFreeLocation environment.py:173-182 over
+ * range(0, N-1) x range(0, N-1), metabolism, endowment, vision, age, sex, fertility) with every draw taken from the
+ * engine's MT19937 stream in the reference's order; agents get ids 1.. in creation order (an agent that finds no free
+ * cell keeps its id and is dropped).  Leaves the engine as after ss_upload_cells + ss_upload_agents.  Needs
+ * SS_RNG_MT19937 state (ss_seed_mt19937 / ss_set_rng_mt19937); keyed engines may call it too -- the initial world is
+ * then the same one, the stepping differs. */
+int  ss_init_world(ss_engine* e, const ss_init_params* p);
+
 /* Replaces: Environment.grid slots [0] sugar, [2] capacity, [5] pollution (environment.py:24-34).
  * pollution may be NULL (zeros). */
 int  ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution);

@@ -6,8 +6,8 @@ reference's step interface (engine, dropin).
 """
 from .capi import SsConfig, SsStepStats, STATS_DTYPE, RNG_MT19937, RNG_KEYED, EngineLibraryMissing  # noqa: F401
 from .settings import (ConflictingRuleException, MissingRuleException, UnsupportedRuleError,  # noqa: F401
-                       config_from_settings, load_settings, rule_check)
+                       config_from_settings, init_params_from_settings, load_settings, rule_check)
 
 __all__ = ["SsConfig", "SsStepStats", "STATS_DTYPE", "RNG_MT19937", "RNG_KEYED", "EngineLibraryMissing",
            "ConflictingRuleException", "MissingRuleException", "UnsupportedRuleError",
-           "config_from_settings", "load_settings", "rule_check"]
+           "config_from_settings", "init_params_from_settings", "load_settings", "rule_check"]

@@ -37,6 +37,17 @@ class SsStepStats(C.Structure):
                 ("gini", C.c_double), ("acted", C.c_double), ("deaths", C.c_double)]
 
 
+class SsInitParams(C.Structure):
+    """`ss_init_params` of include/sugarscape_b200.h."""
+    _fields_ = [
+        ("n_sites", C.c_int32), ("site_x", C.c_int32 * 4), ("site_y", C.c_int32 * 4), ("site_radius", C.c_int32 * 4),
+        ("grow_to_capacity", C.c_int32), ("n_groups", C.c_int32), ("group_count", C.c_int32 * 4),
+        ("max_metabolism", C.c_int32), ("max_vision", C.c_int32), ("endowment_min", C.c_int32), ("endowment_max", C.c_int32),
+        ("age_min", C.c_int32), ("age_max", C.c_int32), ("childbearing", (C.c_int32 * 4) * 2),
+        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32),
+    ]
+
+
 STATS_DTYPE = np.dtype([("population", "f8"), ("metabolism_mean", "f8"), ("vision_mean", "f8"),
                         ("gini", "f8"), ("acted", "f8"), ("deaths", "f8")])
 
@@ -46,7 +57,7 @@ EXPORTS = (
     "ss_set_rng_mt19937", "ss_get_rng_mt19937", "ss_set_rng_keyed", "ss_step", "ss_agent_count",
     "ss_download_cells", "ss_download_agents", "ss_get_counters", "ss_get_kernel_times",
     "ss_set_option", "ss_version", "ss_shard_enable", "ss_shard_begin_step", "ss_shard_pass", "ss_shard_apply",
-    "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free",
+    "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free", "ss_seed_mt19937", "ss_init_world",
 )
 
 _lib = None
@@ -78,6 +89,8 @@ def lib():
     L.ss_set_rng_mt19937.argtypes = [vp, vp, C.c_int32]
     L.ss_get_rng_mt19937.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     L.ss_set_rng_keyed.argtypes = [vp, C.c_uint64]
+    L.ss_seed_mt19937.argtypes = [vp, C.c_uint64]
+    L.ss_init_world.argtypes = [vp, C.POINTER(SsInitParams)]
     L.ss_step.argtypes = [vp, C.c_int32, vp]
     L.ss_agent_count.argtypes = [vp]
     L.ss_download_cells.argtypes = [vp, vp, vp, vp, vp]

@@ -16,6 +16,10 @@ cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_t
                              int stats_base, cudaStream_t stream);
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s);
 cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
+cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D, double max_capacity,
+                                 int grow, int sm_count, cudaStream_t stream);
+cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, int32_t* rowfree, int32_t* superfree, int32_t* cols,
+                                  size_t stride, double* sugar, int32_t* result, cudaStream_t stream);
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s);
@@ -179,15 +183,10 @@ extern "C" void ss_destroy(ss_engine* e) {
 }
 
 static int choose_path(ss_engine* e);
+static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, double* d_f64, int* d_chk);
 
-extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution) {
-    if (!e || !sugar || !cap) return set_err(e, SS_ERR_ARG, "null argument");
-    CK(cudaSetDevice(e->device));
-    const size_t cb = e->cells * sizeof(double);
-    CK(cudaMemcpyAsync(e->w.sugar, sugar, cb, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->w.cap, cap, cb, cudaMemcpyHostToDevice, e->stream));
-    if (pollution) CK(cudaMemcpyAsync(e->w.poll, pollution, cb, cudaMemcpyHostToDevice, e->stream));
-    else CK(cudaMemsetAsync(e->w.poll, 0, cb, e->stream));
+// the cell arrays are in place on the device: derive what the kernels keep beside them
+static int finish_cells(ss_engine* e) {
     {   // int(sugar) byte mirror for the lattice path (built on the device); needs capacities < 256
         int flag = 0;
         CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
@@ -199,6 +198,17 @@ extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* 
     e->have_cells = true;
     if (e->have_agents) return choose_path(e);
     return SS_OK;
+}
+
+extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution) {
+    if (!e || !sugar || !cap) return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t cb = e->cells * sizeof(double);
+    CK(cudaMemcpyAsync(e->w.sugar, sugar, cb, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->w.cap, cap, cb, cudaMemcpyHostToDevice, e->stream));
+    if (pollution) CK(cudaMemcpyAsync(e->w.poll, pollution, cb, cudaMemcpyHostToDevice, e->stream));
+    else CK(cudaMemsetAsync(e->w.poll, 0, cb, e->stream));
+    return finish_cells(e);
 }
 
 #ifndef SS_DEFAULT_SOLO_IMPL
@@ -288,7 +298,6 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
     if (!e || n < 0 || (n > 0 && (!id || !x || !y || !vision || !metab || !sugar)))
         return set_err(e, SS_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));
-    const int N = e->w.n;
     // stage the six View.agents columns; argument checks, the agent store and the occupancy words are built on the device
     const size_t nn = (size_t)std::max(n, 1);
     int32_t* d_i32 = nullptr;
@@ -305,6 +314,13 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
     for (int k = 0; k < 5 && n > 0; k++)
         CK(cudaMemcpyAsync(d_i32 + k * nn, cols[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     if (n > 0) CK(cudaMemcpyAsync(d_f64, sugar, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    return finish_agents(e, n, d_i32, nn, d_f64, d_chk);
+}
+
+// the six View.agents columns are staged on the device (five int32 columns `nn` apart: id, x, y, vision, metabolism;
+// sugar): argument checks, agent store, occupancy words, execution path
+static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, double* d_f64, int* d_chk) {
+    const int N = e->w.n;
     int chk[4] = {0, 0, 1, 0};
     CK(cudaMemcpyAsync(d_chk, chk, sizeof chk, cudaMemcpyHostToDevice, e->stream));
     CK(ss_launch_validate_agents(n, N, d_i32, d_i32 + nn, d_i32 + 2 * nn, d_i32 + 3 * nn, d_i32 + 4 * nn, d_chk, e->stream));
@@ -373,6 +389,78 @@ extern "C" int ss_get_rng_mt19937(ss_engine* e, uint32_t state[624], int32_t* in
     CK(cudaMemcpyAsync(index, e->w.mti, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return SS_OK;
+}
+
+// sugarscape.py:162 random.seed(seed): CPython's random_seed for an int -> init_by_array over the 32-bit words of abs(seed)
+extern "C" int ss_seed_mt19937(ss_engine* e, uint64_t seed) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    uint32_t key[2] = {(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+    const int klen = key[1] ? 2 : 1;
+    uint32_t mt[624];
+    mt[0] = 19650218u;                                                                  // init_genrand
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for (int k = 624 > klen ? 624 : klen; k; k--) {                                     // init_by_array
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        i++; j++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        if (j >= klen) j = 0;
+    }
+    for (int k = 623; k; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    return ss_set_rng_mt19937(e, mt, 624);
+}
+
+extern "C" int ss_init_world(ss_engine* e, const ss_init_params* p) {
+    if (!e || !p) return set_err(e, SS_ERR_ARG, "null argument");
+    if (p->n_sites < 0 || p->n_sites > 4 || p->n_groups < 0 || p->n_groups > 4) return set_err(e, SS_ERR_ARG, "at most 4 sites / 4 agent groups");
+    if (p->max_metabolism < 1 || p->max_vision < 1 || p->endowment_max < p->endowment_min || p->age_max < p->age_min ||
+        p->foresight_hi < p->foresight_lo)
+        return set_err(e, SS_ERR_ARG, "empty draw range in ss_init_params");
+    for (int s = 0; s < 2; s++)
+        if (p->childbearing[s][1] < p->childbearing[s][0] || p->childbearing[s][3] < p->childbearing[s][2])
+            return set_err(e, SS_ERR_ARG, "empty fertility range in ss_init_params");
+    CK(cudaSetDevice(e->device));
+    const int N = e->w.n;
+    double D[4] = {1, 1, 1, 1};
+    for (int s = 0; s < p->n_sites; s++) {                                              // environment.py:118
+        if (p->site_radius[s] <= 0) return set_err(e, SS_ERR_ARG, "site radius must be positive");
+        const long long a = std::max(p->site_x[s], N - p->site_x[s]), b = std::max(p->site_y[s], N - p->site_y[s]);
+        D[s] = sqrt((double)(a * a + b * b)) * ((double)p->site_radius[s] / (double)N);
+    }
+    CK(ss_launch_init_sites(e->w, p->n_sites, p->site_x, p->site_y, D, e->cfg.max_capacity, p->grow_to_capacity, e->sm_count,
+                            e->stream));
+    long long total = 0;
+    for (int g = 0; g < p->n_groups; g++) {
+        if (p->group_count[g] < 0) return set_err(e, SS_ERR_ARG, "negative agent count");
+        total += p->group_count[g];
+    }
+    if (total > (long long)SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^24");
+    const size_t nn = (size_t)std::max<long long>(total, 1);
+    int32_t *d_i32 = nullptr, *d_scratch = nullptr;
+    double* d_f64 = nullptr;
+    int* d_chk = nullptr;
+    struct Staging {
+        int32_t*& a; double*& b; int*& c; int32_t*& d;
+        ~Staging() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); }
+    } staging{d_i32, d_f64, d_chk, d_scratch};
+    CK(cudaMalloc(&d_i32, sizeof(int32_t) * 5 * nn));
+    CK(cudaMalloc(&d_f64, sizeof(double) * nn));
+    CK(cudaMalloc(&d_chk, sizeof(int) * 4));
+    const int nsuper = (N + 30) / 32 + 1;
+    CK(cudaMalloc(&d_scratch, sizeof(int32_t) * ((size_t)N + nsuper + 2)));
+    int32_t* d_result = d_scratch + N + nsuper;
+    CK(ss_launch_init_agents(e->w, p, d_scratch, d_scratch + N, d_i32, nn, d_f64, d_result, e->stream));
+    int32_t result[2] = {0, 0};
+    CK(cudaMemcpyAsync(result, d_result, sizeof result, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = finish_cells(e);
+    if (rc) return rc;
+    return finish_agents(e, result[0], d_i32, nn, d_f64, d_chk);
 }
 
 extern "C" int ss_set_rng_keyed(ss_engine* e, uint64_t seed) {

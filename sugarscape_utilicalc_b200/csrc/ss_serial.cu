@@ -413,3 +413,146 @@ extern "C" cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, in
     ss_serial_kernel<<<1, SERIAL_THREADS, 0, stream>>>(w, iteration, env_time, nsteps, fused_env, stats_base);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------
+// World initialisation of the reference's `__main__` (sugarscape.py:1485-1555), SURVEY 8 f4.
+//
+// ss_init_sites_kernel: Environment.addSiteHelper (environment.py:114-122) for every sugar site, then
+// env.grow(maxCapacity) (environment.py:133-139) -- a cell's capacity is the largest radial term; pointwise.
+struct InitSites {
+    int n_sites;
+    int sx[4], sy[4];
+    double D[4];            // distance(max(si, W-si), max(sj, H-sj)) * (r / float(W)), computed on the host
+    double max_capacity;
+    int grow;
+};
+__global__ void ss_init_sites_kernel(DevWorld w, InitSites sp) {
+    const int n = w.n;
+    const size_t cells = (size_t)n * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < cells; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / n), j = (int)(idx % n);
+        double cap = 0.0;
+        for (int s = 0; s < sp.n_sites; s++) {
+            const int di = sp.sx[s] - i, dj = sp.sy[s] - j;
+            const double d = sqrt((double)((long long)di * di + (long long)dj * dj));
+            double c = 1.0 + sp.max_capacity * (1.0 - d / sp.D[s]);
+            c = c <= sp.max_capacity ? c : sp.max_capacity;                   // min(c, maxCapacity)
+            if (c > cap) cap = c;
+        }
+        w.cap[idx] = cap;
+        const double grown = 0.0 + sp.max_capacity;                           // environment.py:137: min(cur + alpha, cap)
+        w.sugar[idx] = sp.grow ? (grown <= cap ? grown : cap) : 0.0;
+        w.poll[idx] = 0.0;
+        w.occw[idx] = 0u;
+    }
+}
+
+// ss_init_agents_kernel: `Agent(env)` + `initAgent` per agent, one warp.  Lane 0 owns the MT19937 stream (every draw
+// in the reference's order); the warp finds the k-th free cell of range(0, N-1) x range(0, N-1) in row-major order
+// (environment.py:173-182 builds that list and indexes it) through per-row and per-32-row free counts.
+struct InitAgents {
+    int n_groups;
+    int group_count[4];
+    int max_metabolism, max_vision, endow_min, endow_max, age_min, age_max;
+    int childbearing[2][4];
+    int foresight_lo, foresight_hi;
+};
+// position of the k-th unit (0-based) in the prefix sums of 32 lane values; returns the lane and leaves k relative to it
+__device__ static inline int warp_select(int v, int lane, long long& k, long long& total_out) {
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    total_out = __shfl_sync(FULL, incl, 31);
+    if (k >= total_out) return -1;
+    const unsigned b = __ballot_sync(FULL, incl > k);
+    const int L = __ffs(b) - 1;
+    const long long excl = __shfl_sync(FULL, incl - v, L);
+    k -= excl;
+    return L;
+}
+__global__ void __launch_bounds__(32)
+ss_init_agents_kernel(DevWorld w, InitAgents ip, int32_t* rowfree, int32_t* superfree, int32_t* id_out, int32_t* x_out,
+                      int32_t* y_out, int32_t* vision_out, int32_t* metab_out, double* sugar_out, int32_t* result) {
+    __shared__ SerialShared sh;
+    const int lane = threadIdx.x, n = w.n, n1 = n - 1, nsuper = (n1 + 31) / 32;
+    for (int i = lane; i < 624; i += 32) sh.mt[i] = w.mt[i];
+    if (lane == 0) { sh.mti = *w.mti; sh.rng_mode = SS_RNG_MT19937; }
+    for (int i = lane; i < n1; i += 32) rowfree[i] = n1;
+    for (int s = lane; s < nsuper; s += 32) superfree[s] = n1 * min(32, n1 - s * 32);
+    __syncwarp();
+    long long F = (long long)n1 * n1;
+    int nid = 0, count = 0;
+    for (int g = 0; g < ip.n_groups; g++) {
+        for (int a = 0; a < ip.group_count[g]; a++) {
+            nid++;
+            long long k = 0;
+            if (lane == 0) {
+                (void)randbelow(sh, (uint32_t)(ip.foresight_hi - ip.foresight_lo + 1));        // agent.py:165 generateForesight
+                if (F > 0) k = (long long)randbelow(sh, (uint32_t)F);                         // environment.py:181
+            }
+            if (F == 0) continue;                                                             // initAgent returns False
+            k = __shfl_sync(FULL, k, 0);
+            int sr = -1;
+            for (int base = 0; base < nsuper && sr < 0; base += 32) {
+                long long tot;
+                const int L = warp_select(base + lane < nsuper ? superfree[base + lane] : 0, lane, k, tot);
+                if (L >= 0) sr = base + L; else k -= tot;
+            }
+            long long tot;
+            const int rl = warp_select(sr * 32 + lane < n1 ? rowfree[sr * 32 + lane] : 0, lane, k, tot);
+            const int row = sr * 32 + rl;
+            int col = -1;
+            for (int base = 0; base < n1 && col < 0; base += 32) {
+                const int c = base + lane;
+                const unsigned b = __ballot_sync(FULL, c < n1 && w.occw[(size_t)row * n + c] == 0u);
+                const int cnt = __popc(b);
+                if (k < cnt) col = base + (int)__fns(b, 0u, (int)k + 1); else k -= cnt;
+            }
+            if (lane == 0) {
+                w.occw[(size_t)row * n + col] = 1u;
+                rowfree[row]--; superfree[sr]--;
+                const int metab = 1 + (int)randbelow(sh, (uint32_t)ip.max_metabolism);            // sugarscape.py:250
+                const int endow = ip.endow_min + (int)randbelow(sh, (uint32_t)(ip.endow_max - ip.endow_min + 1));
+                const int vision = 1 + (int)randbelow(sh, (uint32_t)ip.max_vision);               // :256
+                (void)randbelow(sh, (uint32_t)(ip.age_max - ip.age_min + 1));                     // :257
+                const int sex = (int)randbelow(sh, 2u);                                           // :258
+                (void)randbelow(sh, (uint32_t)(ip.childbearing[sex][1] - ip.childbearing[sex][0] + 1));   // :260
+                (void)randbelow(sh, (uint32_t)(ip.childbearing[sex][3] - ip.childbearing[sex][2] + 1));   // :261
+                id_out[count] = nid; x_out[count] = row; y_out[count] = col;
+                vision_out[count] = vision; metab_out[count] = metab; sugar_out[count] = (double)endow;
+            }
+            F--; count++;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < 624; i += 32) w.mt[i] = sh.mt[i];
+    if (lane == 0) { *w.mti = sh.mti; result[0] = count; result[1] = nid; }
+}
+
+extern "C" cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D,
+                                            double max_capacity, int grow, int sm_count, cudaStream_t stream) {
+    InitSites sp;
+    sp.n_sites = n_sites;
+    for (int s = 0; s < 4; s++) { sp.sx[s] = s < n_sites ? sx[s] : 0; sp.sy[s] = s < n_sites ? sy[s] : 0; sp.D[s] = s < n_sites ? D[s] : 1.0; }
+    sp.max_capacity = max_capacity; sp.grow = grow;
+    ss_init_sites_kernel<<<sm_count * 8, 256, 0, stream>>>(w, sp);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, int32_t* rowfree, int32_t* superfree,
+                                             int32_t* cols, size_t stride, double* sugar, int32_t* result, cudaStream_t stream) {
+    InitAgents ip;
+    ip.n_groups = p->n_groups;
+    for (int g = 0; g < 4; g++) ip.group_count[g] = g < p->n_groups ? p->group_count[g] : 0;
+    ip.max_metabolism = p->max_metabolism; ip.max_vision = p->max_vision;
+    ip.endow_min = p->endowment_min; ip.endow_max = p->endowment_max; ip.age_min = p->age_min; ip.age_max = p->age_max;
+    for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) ip.childbearing[s][k] = p->childbearing[s][k];
+    ip.foresight_lo = p->foresight_lo; ip.foresight_hi = p->foresight_hi;
+    ss_init_agents_kernel<<<1, 32, 0, stream>>>(w, ip, rowfree, superfree, cols, cols + stride, cols + 2 * stride, cols + 3 * stride,
+                                                 cols + 4 * stride, sugar, result);
+    return cudaGetLastError();
+}

@@ -115,6 +115,16 @@ class Engine:
         self._check(self._lib.ss_get_rng_mt19937(self._h, _ptr(st), C.byref(idx)), "ss_get_rng_mt19937")
         return st, idx.value
 
+    def seed_mt19937(self, seed):
+        """`random.seed(seed)` of sugarscape.py:162 (non-negative int) on the engine's MT19937 stream."""
+        self._check(self._lib.ss_seed_mt19937(self._h, int(seed)), "ss_seed_mt19937")
+
+    def init_world(self, params):
+        """The world of the reference's `__main__` (sugarscape.py:1485-1555), built on the device: sugar sites,
+        growback to capacity and the agents, every draw from the MT19937 stream.  `params`: SsInitParams
+        (settings.init_params_from_settings)."""
+        self._check(self._lib.ss_init_world(self._h, C.byref(params)), "ss_init_world")
+
     def set_rng_keyed(self, seed):
         self._check(self._lib.ss_set_rng_keyed(self._h, int(seed) & ((1 << 64) - 1)), "ss_set_rng_keyed")
 

@@ -116,3 +116,31 @@ def config_from_settings(settings, rng_mode="mt", keyed_seed=None, iteration=0, 
     cfg.iteration = int(iteration)
     cfg.env_time = int(env_time)
     return cfg
+
+
+def init_params_from_settings(settings):
+    """`ss_init_params` for `ss_init_world`: what the reference's `__main__` reads from settings.json to build the
+    initial world (sugarscape.py:48-108, 138-146, 1494-1497, 1525-1547)."""
+    from .capi import SsInitParams
+    check_supported(settings)
+    env, ag, rules = settings["env"], settings["agents"], settings["rules"]
+    p = SsInitParams()
+    sites = [env["sites"]["ne"], env["sites"]["sw"]]                    # northeast, southwest: the two sugar peaks
+    p.n_sites = len(sites)
+    for k, s in enumerate(sites):
+        p.site_x[k], p.site_y[k], p.site_radius[k] = s["x"], s["y"], s["radius"]
+    p.grow_to_capacity = 1 if rules["grow"] else 0
+    groups = [env["total_agents"]["blue"], env["total_agents"]["red"]]  # `distributions`: blues first
+    p.n_groups = len(groups)
+    for k, c in enumerate(groups):
+        p.group_count[k] = c
+    p.max_metabolism, p.max_vision = ag["max_agent_metabolism"], ag["max_agent_vision"]
+    p.endowment_min, p.endowment_max = ag["initial_endowments"]["min"], ag["initial_endowments"]["max"]
+    p.age_min, p.age_max = ag["death_age_range"]["min"], ag["death_age_range"]["max"]
+    fa = ag["fertility_age_ranges"]
+    for sex, who in enumerate(("male", "female")):                      # fertility[0] = male tuple is indexed by sex 0
+        r = fa[who]
+        for k, key in enumerate(("min_start", "max_start", "min_end", "max_end")):
+            p.childbearing[sex][k] = r[key]
+    p.foresight_lo, p.foresight_hi = 0, 0                               # Environment.foresightRange without the rule
+    return p

@@ -33,6 +33,82 @@ def test_on_disk_outputs_match_reference_golden(name, tmp_path):
     common.check_outputs_against_golden(name, "engine", tmp_path)
 
 
+@pytest.mark.parametrize("name", MT_CASES)
+def test_world_initialisation_on_device_equals_reference(name):
+    """`random.seed(seed)` + the reference's `__main__` set-up (sugar sites, growback to capacity,
+    Agent() + initAgent per agent) run on the device -- capacity / sugar fields, every agent's id, cell, vision,
+    metabolism and endowment and the MT19937 state afterwards equal what the unmodified reference built (the golden
+    initial state); the run that follows stays on the golden trajectory."""
+    from sugarscape_utilicalc_b200 import init_params_from_settings
+    g = common.load_golden(name)
+    cfg = config_from_settings(g["settings"], rng_mode="mt")
+    e = common.engine_world(cfg)
+    e.seed_mt19937(g["settings"]["env"]["random_seed"])
+    e.init_world(init_params_from_settings(g["settings"]))
+    cells, ags = e.download_cells(), e.download_agents()
+    assert np.array_equal(cells["cap"], g["init_cap"]) and np.array_equal(cells["sugar"], g["init_sugar"])
+    assert np.array_equal(cells["pollution"], g["init_pollution"])
+    for key, gk in (("id", "init_order"), ("x", "init_x"), ("y", "init_y"), ("vision", "init_vision"), ("metab", "init_metab"),
+                    ("sugar", "init_sugar_agent")):
+        assert np.array_equal(ags[key], g[gk]), key
+    mt, idx = e.get_rng_mt19937()
+    assert np.array_equal(mt, g["init_mt"]) and idx == int(g["init_mt_index"])
+    common.run_against_golden(g, e, exact_gini=True, max_steps=40)
+    e.close()
+
+
+def test_headless_run_of_settings_json_equals_reference_outputs(tmp_path, monkeypatch):
+    """`python -m sugarscape_utilicalc_b200 settings.json`: seed, device-side world, steps until the plateau exit --
+    data.txt column and event log equal the reference's run of the same file (tests/golden/outputs.json)."""
+    import json
+    import os
+    from sugarscape_utilicalc_b200 import __main__ as runner
+    g = common.load_golden("c1_default_moveeat_mt")
+    with open(os.path.join(common.GOLDEN, "outputs.json")) as f:
+        exp = json.load(f)["c1_default_moveeat_mt"]
+    s = dict(g["settings"])
+    s["view"] = {**s["view"], "create_log_on_exit": True}
+    (tmp_path / "settings.json").write_text(json.dumps(s))
+    monkeypatch.chdir(tmp_path)
+    assert runner.main(["settings.json", "--quiet"]) == 0
+    assert (tmp_path / "data_collection" / "data.txt").read_text() == exp["data_txt"]
+    logs = list((tmp_path / "logs").glob("log_*.txt"))
+    assert len(logs) == 1
+    text = logs[0].read_text()
+    assert text[text.index("\nStat lists:"):] == exp["log_file_text"][exp["log_file_text"].index("\nStat lists:"):]
+
+
+def test_world_initialisation_fills_the_lattice_and_large_grids():
+    """More agents than free cells of range(0, N-1)^2: the surplus agents keep their ids and are dropped
+    (initAgent returns False); and a 1000^2 lattice goes through the two-level free-cell search."""
+    from sugarscape_utilicalc_b200 import init_params_from_settings
+    s = common.load_golden("c1_default_moveeat_mt")["settings"]
+    s = {**s, "view": {**s["view"], "grid_size": {"x": 8, "y": 8}}, "env": {**s["env"], "total_agents": {"blue": 40, "red": 20}}}
+    for k in ("ne", "sw"):
+        s["env"]["sites"] = {**s["env"]["sites"], k: {"x": 3, "y": 4, "radius": 3}}
+    s["agents"] = {**s["agents"], "max_agent_vision": 3}
+    cfg = config_from_settings(s, rng_mode="mt")
+    e = common.engine_world(cfg)
+    e.seed_mt19937(7)
+    e.init_world(init_params_from_settings(s))
+    ags = e.download_agents()
+    assert len(ags["id"]) == 49 and ags["id"].max() == 49 and ags["x"].max() == 6 and ags["y"].max() == 6
+    assert len(set(zip(ags["x"].tolist(), ags["y"].tolist()))) == 49
+    e.close()
+    s = common.load_golden("c1_default_moveeat_mt")["settings"]
+    s = {**s, "view": {**s["view"], "grid_size": {"x": 1000, "y": 1000}}, "env": {**s["env"], "total_agents": {"blue": 30000, "red": 20000}}}
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e = common.engine_world(cfg)
+    e.seed_mt19937(2**40 + 5)
+    e.init_world(init_params_from_settings(s))
+    ags = e.download_agents()
+    assert len(ags["id"]) == 50000 and len(set((ags["x"].astype(np.int64) * 1000 + ags["y"]).tolist())) == 50000
+    assert ags["x"].max() <= 998 and ags["vision"].min() >= 1 and ags["vision"].max() <= 5
+    assert e.counters()["path"] == 2
+    e.step(3)
+    e.close()
+
+
 def test_mt_exact_single_steps_equal_fused_steps():
     g = common.load_golden("c2_pollution_mt")
     w = common.world_from_golden(g, "engine")

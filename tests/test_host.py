@@ -110,6 +110,25 @@ def test_struct_layouts_match_the_header(tmp_path):
     assert out[4] == capi.SsConfig.env_time.offset
 
 
+def test_init_params_layout_and_mapping(tmp_path):
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sugarscape_b200.h"\n'
+                    'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(ss_init_params), offsetof(ss_init_params, group_count),'
+                    ' offsetof(ss_init_params, childbearing), offsetof(ss_init_params, foresight_hi));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
+    out = list(map(int, subprocess.check_output([str(exe)]).split()))
+    P = capi.SsInitParams
+    assert out == [C.sizeof(P), P.group_count.offset, P.childbearing.offset, P.foresight_hi.offset]
+    from sugarscape_utilicalc_b200 import init_params_from_settings
+    import common
+    p = init_params_from_settings(common.load_golden("c1_default_moveeat_mt")["settings"])     # the shipped settings.json
+    assert (p.n_sites, list(p.site_x)[:2], list(p.site_y)[:2], list(p.site_radius)[:2]) == (2, [35, 15], [15, 35], [18, 18])
+    assert (p.n_groups, list(p.group_count)[:2], p.grow_to_capacity) == (2, [150, 150], 1)
+    assert (p.max_metabolism, p.max_vision, p.endowment_min, p.endowment_max, p.age_min, p.age_max) == (5, 5, 20, 30, 60, 100)
+    assert [list(r) for r in p.childbearing] == [[12, 15, 50, 60], [12, 15, 40, 50]]
+
+
 def test_engine_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
