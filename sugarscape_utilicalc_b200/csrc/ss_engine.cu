@@ -29,7 +29,7 @@ uint32_t ss_export_blocks(uint32_t domain);
 cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32_t* blockcnt, uint32_t* total, int32_t* cols,
                                     size_t stride, double* sugar, cudaStream_t s);
 size_t ss_pass_smem_bytes(int emax, int ew, int vmax);
-size_t ss_solo_smem_bytes(int emax, int ew, int lanes);
+size_t ss_solo_smem_bytes(int emax, int ew, int mode);
 cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time, int lanes, cudaStream_t s);
 cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                 cudaStream_t s);
@@ -216,7 +216,8 @@ extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* 
 #endif
 static int choose_path(ss_engine* e) {
     const int n = e->w.n, V = e->w.vmax;
-    bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && !e->cfg.rule_utilicalc && V <= 15 && 4 * V + 1 <= n &&
+    // (the utilicalc rule runs on the lattice through the warp-per-window kernel only: several windows needed)
+    bool lattice_ok = e->cfg.rng_mode == SS_RNG_KEYED && V <= 15 && 4 * V + 1 <= n &&
                       e->cap_fits_u8 && e->w.n_slots <= SS_MAX_SLOTS;
     PassGeom g{};
     int ntile = 1, emin = 0, impl = 0;
@@ -253,7 +254,7 @@ static int choose_path(ss_engine* e) {
         int ntile_s = 1, emin_s = 0;
         // the solo kernel needs many windows to fill the GPU (one warp each, 32 per SM) and window coordinates < 256
         auto solo_tiling = [&](int wmax) {
-            return tiling(wmax, &gs, &ntile_s, &emin_s) && gs.nwin > 1 && ss_solo_smem_bytes(gs.emax, gs.ew, 1) <= 48 * 1024;
+            return tiling(wmax, &gs, &ntile_s, &emin_s) && gs.nwin > 1 && ss_solo_smem_bytes(gs.emax, gs.ew, e->cfg.rule_utilicalc ? 2 : 1) <= 48 * 1024;
         };
         bool solo_ok = false;
         if (e->solo_window_max > 0) {
@@ -267,14 +268,21 @@ static int choose_path(ss_engine* e) {
         const bool want_solo = e->pass_impl_option >= 1 ||
                                (e->pass_impl_option < 0 && solo_ok && (long long)gs.nwin * gs.nwin >= 8ll * e->sm_count * e->shard_world);
         // 1 = the warp takes its agents one at a time, 2 = one lane per agent in batches of 32 (SS_DEFAULT_SOLO_IMPL)
-        if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = e->pass_impl_option >= 1 ? e->pass_impl_option : SS_DEFAULT_SOLO_IMPL; }
+        if (e->cfg.rule_utilicalc) {
+            if (!solo_ok && e->solo_window_max <= 0) {      // any tiling with several windows beats the serial kernel
+                const int sizes[5] = {64, 80, 96, 112, 128};
+                for (int k = 0; k < 5 && !solo_ok; k++) solo_ok = solo_tiling(sizes[k]);
+            }
+            if (solo_ok && e->pass_impl_option != 0) { g = gs; ntile = ntile_s; emin = emin_s; impl = 1; }
+            else lattice_ok = false;
+        } else if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = e->pass_impl_option >= 1 ? e->pass_impl_option : SS_DEFAULT_SOLO_IMPL; }
         else if (!cta_ok) lattice_ok = false;
     }
     int path;
     if (e->path_option == PATH_LATTICE) {
         if (!lattice_ok)
             return set_err(e, SS_ERR_UNSUPPORTED,
-                           "lattice path needs keyed RNG, moveEat (no utilicalc), vision <= 15, capacities < 256, <= 2^24 agents and windows >= 8*vmax+2");
+                           "lattice path needs keyed RNG, vision <= 15, capacities < 256, <= 2^24 agents and windows >= 8*vmax+2 (utilicalc: several windows)");
         path = PATH_LATTICE;
     } else if (e->path_option == PATH_SERIAL_FUSED || e->path_option == PATH_SERIAL_ENV) {
         path = n <= 256 ? PATH_SERIAL_FUSED : PATH_SERIAL_ENV;

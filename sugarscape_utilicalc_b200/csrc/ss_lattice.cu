@@ -291,10 +291,13 @@ __device__ static Choice warp_choose_cell(const DevWorld& w, const Ctx& c, int l
 // successor's turn (Q1).
 // Commit of one agent's turn by ONE thread, once the destination is chosen: (lx,ly) -> (lr,lq) in window coordinates,
 // pos -> cell on the lattice, harvest sg.  sugar / attr are the agent's record fields (read only for at-risk agents).
+// risky: settle the whole turn now (at-risk agents; every agent under the utilicalc rule, whose neighbours read its
+// sugar); publish: somebody may be waiting for the outcome (Q1) -- fence and status word.
 template <class Ctx>
 __device__ static inline void commit_turn(const DevWorld& w, const Ctx& c, int lx, int ly, int lr, int lq, int pos, int cell,
                                           int sg, int a, bool risky, uint32_t slot, double sugar, uint32_t attr,
-                                          int64_t iteration, int64_t env_time, uint32_t next_phase, ThreadStats& ts) {
+                                          int64_t iteration, int64_t env_time, uint32_t next_phase, ThreadStats& ts,
+                                          bool publish = true) {
     AgentRec* recp = &w.agents[slot];
     uint32_t new_word = occ_pack(slot, a, next_phase);
     ts.resolved++;
@@ -320,9 +323,9 @@ __device__ static inline void commit_turn(const DevWorld& w, const Ctx& c, int l
     }
     const bool pol = w.cfg.rule_pollution != 0 && w.cfg.pollution_start_time <= env_time;
     const int metab = attr_metab(attr);
-    if (w.cfg.rule_move_eat) {
+    if (w.cfg.rule_move_eat || w.cfg.rule_utilicalc) {
         if (pol) w.poll[cell] = __ldcg(&w.poll[cell]) + (((double)sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));
-        sugar = ss_set_sugar(ss_max0(sugar + (double)sg));            // agent.py:832
+        sugar = ss_set_sugar(ss_max0(sugar + (double)sg));            // agent.py:832 / 1128-1130
         c.clear_isug(lr, lq);
         w.sugar[cell] = 0.0;
         w.isugar[cell] = 0;
@@ -346,9 +349,11 @@ __device__ static inline void commit_turn(const DevWorld& w, const Ctx& c, int l
     recp->sugar = sugar;
     recp->pos = (uint32_t)cell;
     recp->attr = attr;
-    __threadfence();                       // the turn's effects before its status (Q1 readers)
     const uint32_t status = ((uint32_t)(iteration + 1) << 2) | (died ? ST_DIED : ST_ACTED);
-    *((volatile uint32_t*)&recp->status) = status;
+    if (publish) {
+        __threadfence();                   // the turn's effects before its status (Q1 readers)
+        *((volatile uint32_t*)&recp->status) = status;
+    }
     if (w.log) {
         ShardLogEntry en;
         en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
@@ -384,6 +389,118 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
     const int cell = (ch.lr == lx && ch.lq == ly) ? pos
                    : Ctx::gw(c.gx0 + ch.lr, n) * n + Ctx::gw(c.gy0 + ch.lq, n);
     commit_turn(w, c, lx, ly, ch.lr, ch.lq, pos, cell, ch.sg, a, risky, slot, sugar, attr, iteration, env_time, next_phase, ts);
+}
+
+// ------------------------------------------------------------------------------------------
+// agent.py:1025-1141 utilicalcMove(), sugar-only (utilicalcSugar agent.py:980-992), one warp per agent in the
+// warp-per-window kernel -- the welfare evaluation is fused into the movement scan: the lanes scan the cross once for
+// free cells (moves) and occupants (the vision neighbourhood), lane 0 replays the three Fisher-Yates shuffles on the
+// agent's keyed words, the utility of every move is summed by one lane over the neighbours in list order (the sums are
+// compared for equality, agent.py:1105) and never leaves shared memory.  Every turn is settled on the spot: the
+// neighbours' utilities read Agent.sugar.
+#define UT_MAXC 64                      // >= 2(2v+1)+1 for v <= 15
+struct UtilShared {
+    double util[UT_MAXC], nb_inten[UT_MAXC], nb_metab[UT_MAXC];
+    int32_t food[UT_MAXC], neigh[UT_MAXC], nb_x[UT_MAXC], nb_y[UT_MAXC], nb_v[UT_MAXC];
+};
+struct KeyedStream { uint64_t akey; uint32_t j; };
+__device__ static inline uint32_t ks_randbelow(KeyedStream& ks, uint32_t nn) {          // random.py:242
+    const int k = 32 - __clz(nn);
+    uint32_t r = ss_keyed_word(ks.akey, ks.j++) >> (32 - k);
+    while (r >= nn) r = ss_keyed_word(ks.akey, ks.j++) >> (32 - k);
+    return r;
+}
+__device__ static inline void ks_shuffle(KeyedStream& ks, int32_t* a, int n) {           // random.py:350
+    for (int i = n - 1; i >= 1; i--) {
+        const uint32_t j = ks_randbelow(ks, (uint32_t)i + 1u);
+        const int32_t t = a[i]; a[i] = a[j]; a[j] = t;
+    }
+}
+template <bool WRAP, class Ctx>
+__device__ static void warp_utilicalc_turn(const DevWorld& w, const Ctx& c, UtilShared& us, int lx, int ly, int gx, int gy,
+                                           int a, uint32_t ow, uint32_t slot, int64_t iteration, int64_t env_time,
+                                           uint64_t skey, uint32_t next_phase, ThreadStats& ts, int lane) {
+    const int n = w.n, pos = gx * n + gy, span = 2 * a + 1, K = 2 * span;
+    int m = 0, nb = 0;
+    for (int base = 0; base < K; base += 32) {          // agent.py:361-371 getFood / 391-407 getVisionNeighbourhood
+        const int k = base + lane;
+        bool fr = false, oc = false;
+        int cell = 0;
+        uint32_t word = 0u;
+        if (k < K) {
+            int cx, cy;
+            bool own;
+            if (k < span) { cx = WRAP ? ss_wrap1(gx - a + k, n) : gx - a + k; cy = gy; own = cx == gx; }
+            else { cx = gx; cy = WRAP ? ss_wrap1(gy - a + (k - span), n) : gy - a + (k - span); own = cy == gy; }
+            cell = cx * n + cy;
+            word = __ldcg(&w.occw[cell]);
+            fr = word == 0u;
+            oc = word != 0u && !own;
+        }
+        const unsigned bf = __ballot_sync(FULL, fr), bo = __ballot_sync(FULL, oc), lt = (1u << lane) - 1u;
+        if (fr) us.food[m + __popc(bf & lt)] = cell;
+        if (oc) us.neigh[nb + __popc(bo & lt)] = (int32_t)occ_slot(word);
+        m += __popc(bf); nb += __popc(bo);
+    }
+    __syncwarp();
+    KeyedStream ks;
+    ks.akey = ss_agent_key(skey, slot + 1u); ks.j = 0u;
+    if (lane == 0) {
+        ks_shuffle(ks, us.food, m);           // getFood's shuffle, agent.py:369
+        ks_shuffle(ks, us.food, m);           // agent.py:1033
+        us.food[m] = pos;                     // agent.py:1035
+        ks_shuffle(ks, us.neigh, nb);         // agent.py:405
+        us.neigh[nb] = (int32_t)slot;         // agent.py:1039
+    }
+    m += 1; nb += 1;
+    __syncwarp();
+    for (int q = lane; q < nb; q += 32) {
+        const AgentRec* b = &w.agents[us.neigh[q]];
+        const double bs = __ldcg(&b->sugar);
+        const uint32_t battr = __ldcg(&b->attr), bpos = __ldcg(&b->pos);
+        const double bm = (double)attr_metab(battr);
+        us.nb_inten[q] = 1.0 / (1.0 + ss_py_floordiv(bs, bm));                      // agent.py:870-872, 984
+        us.nb_metab[q] = bm;
+        us.nb_x[q] = (int)bpos / n; us.nb_y[q] = (int)bpos % n; us.nb_v[q] = attr_vision(battr);
+    }
+    __syncwarp();
+    const double extent = (double)(nb - 1);
+    double lmax = 0.0;
+    bool have = false;
+    for (int p = lane; p < m; p += 32) {
+        const int cell = us.food[p], mx = cell / n, my = cell % n;
+        const double site = (double)(int)__ldcg(&w.isugar[cell]);
+        double u = 0.0;
+        for (int q = 0; q < nb; q++) {
+            const double dur = (site / us.nb_metab[q]) / w.cfg.max_capacity;
+            const int bx = us.nb_x[q], by = us.nb_y[q], bv = us.nb_v[q];
+            const int cert = (bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv);
+            double t = 0.0;
+            t += (double)cert * (((us.nb_inten[q] + dur) + 0.5 * 0.0) + extent);
+            if (us.neigh[q] != (int32_t)slot) t *= -1.0;
+            u += t;
+        }
+        us.util[p] = u;
+        if (!have || u > lmax) { lmax = u; have = true; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(FULL, lmax, o);
+        const int oh = __shfl_xor_sync(FULL, (int)have, o);
+        if (oh && (!have || om > lmax)) { lmax = om; have = true; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int nmax = 0;
+        for (int p = 0; p < m; p++)
+            if (us.util[p] == lmax) us.neigh[nmax++] = us.food[p];                  // neigh[] reused as max_locations
+        const int dest = us.neigh[ks_randbelow(ks, (uint32_t)nmax)];                // random.choice, agent.py:1108
+        const int sg = (int)__ldcg(&w.isugar[dest]);                                // agent.py:1128-1130
+        const AgentRec* recp = &w.agents[slot];
+        commit_turn(w, c, lx, ly, lx, ly, pos, dest, sg, a, true, slot, recp->sugar, recp->attr, iteration, env_time, next_phase,
+                    ts, (ow & OCC_RISK) != 0u);
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -987,7 +1104,7 @@ __device__ static inline void ss_prefetch_l2(const void* p) { asm volatile("pref
 #ifndef SOLO_MIN_CTAS
 #define SOLO_MIN_CTAS 25
 #endif
-template <int POLT, bool WRAP, bool LANES>
+template <int POLT, bool WRAP, bool LANES, bool UTIL>
 __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time,
                                             uint32_t* smem, int& cnt_s, int gx0, int gy0, int ex, int ey) {
     typedef GlobCtx<WRAP> GC;
@@ -1002,6 +1119,8 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     uint16_t* poss = (uint16_t*)(blk_bits + g.emax * g.ew); // [SOLO_LIST] lx << 8 | ly, permuted with the keys
     uint32_t* shd_bits = (uint32_t*)(poss + SOLO_LIST);     // [emax][ew] lane-per-agent loop: crosses of the core agents blocked in this launch
     (void)shd_bits;
+    UtilShared* us = (UtilShared*)(((uintptr_t)(poss + SOLO_LIST) + 7u) & ~(uintptr_t)7u);      // utilicalc rule: moves / neighbours
+    (void)us;
     const int ew = g.ew;
     const uint32_t cur_phase = (uint32_t)(iteration & 1), next_phase = cur_phase ^ 1u;
     const int nb = w.pend_nb;
@@ -1421,6 +1540,8 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
                     *log_slot(w, ts) = en;
                 }
             }
+        } else if (UTIL) {
+            warp_utilicalc_turn<WRAP>(w, c, *us, lx, ly, gx, gy, a, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane);
         } else {
             warp_agent_turn<POLT>(w, c, lx, ly, ow & ~OCC_Q1, slot, iteration, env_time, skey, next_phase, ts, lane, cl);
         }
@@ -1461,8 +1582,11 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
 #ifndef LANES_MIN_CTAS
 #define LANES_MIN_CTAS 20
 #endif
-template <int POLT, bool LANES>
-__global__ void __launch_bounds__(32, LANES ? LANES_MIN_CTAS : SOLO_MIN_CTAS)
+#ifndef UTIL_MIN_CTAS
+#define UTIL_MIN_CTAS 16
+#endif
+template <int POLT, bool LANES, bool UTIL>
+__global__ void __launch_bounds__(32, UTIL ? UTIL_MIN_CTAS : LANES ? LANES_MIN_CTAS : SOLO_MIN_CTAS)
 ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int cnt_s;
@@ -1474,8 +1598,8 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     const int y_lo = g.align * (int)(((long long)by * nu) / g.nwin), y_hi = g.align * (int)(((long long)(by + 1) * nu) / g.nwin);
     const int ex = x_hi - x_lo, ey = y_hi - y_lo;
     const int gx0 = ss_wrap1(x_lo + g.shift_x, n), gy0 = ss_wrap1(y_lo + g.shift_y, n);
-    if (gx0 + ex > n || gy0 + ey > n) solo_window<POLT, true, LANES>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
-    else solo_window<POLT, false, LANES>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
+    if (gx0 + ex > n || gy0 + ey > n) solo_window<POLT, true, LANES, UTIL>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
+    else solo_window<POLT, false, LANES, UTIL>(w, g, iteration, env_time, smem, cnt_s, gx0, gy0, ex, ey);
 }
 
 // -------------------------------------------------------------------- multi-GPU replicas ----
@@ -1511,7 +1635,7 @@ ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsig
         return;
     }
     if (en.new_word != 0u) w.occw[en.new_cell] = en.new_word;
-    if (w.cfg.rule_move_eat) { w.sugar[en.new_cell] = 0.0; w.isugar[en.new_cell] = 0; }
+    if (w.cfg.rule_move_eat || w.cfg.rule_utilicalc) { w.sugar[en.new_cell] = 0.0; w.isugar[en.new_cell] = 0; }
     rec->pos = en.new_cell;
     if (kind == 0u) { rec->turn = en.turn; return; }
     // at-risk agent, settled synchronously by its rank: take over the results.  Pollution only grows
@@ -2353,18 +2477,23 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
 }
 
 // key list + positions + blocked bitmap (+ the shadow bitmap of the lane-per-agent loop)
-size_t ss_solo_smem_bytes(int emax, int ew, int lanes) { return (size_t)SOLO_LIST * 6 + (size_t)emax * ew * (lanes ? 8 : 4); }
+// mode: 0 one agent at a time, 1 lane per agent (+ shadow bitmap), 2 utilicalc rule (+ the moves / neighbours of one agent)
+size_t ss_solo_smem_bytes(int emax, int ew, int mode) {
+    return (size_t)SOLO_LIST * 6 + (size_t)emax * ew * (mode == 1 ? 8 : 4) + (mode == 2 ? sizeof(UtilShared) + 8 : 0);
+}
 cudaError_t ss_launch_move_solo(const DevWorld& w, const PassGeom& g, int64_t iteration, int64_t env_time, int lanes,
                                 cudaStream_t s) {
     if (g.bx_cnt <= 0) return cudaSuccess;
-    const size_t smem = ss_solo_smem_bytes(g.emax, g.ew, lanes);
+    const size_t smem = ss_solo_smem_bytes(g.emax, g.ew, w.cfg.rule_utilicalc ? 2 : lanes ? 1 : 0);
     const int grid = g.nwin * g.bx_cnt;
-    if (lanes) {
-        if (w.cfg.rule_pollution) ss_move_solo_kernel<1, true><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
-        else ss_move_solo_kernel<0, true><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+    if (w.cfg.rule_utilicalc) {
+        ss_move_solo_kernel<0, false, true><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+    } else if (lanes) {
+        if (w.cfg.rule_pollution) ss_move_solo_kernel<1, true, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+        else ss_move_solo_kernel<0, true, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
     } else {
-        if (w.cfg.rule_pollution) ss_move_solo_kernel<1, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
-        else ss_move_solo_kernel<0, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+        if (w.cfg.rule_pollution) ss_move_solo_kernel<1, false, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
+        else ss_move_solo_kernel<0, false, false><<<grid, 32, smem, s>>>(w, g, iteration, env_time);
     }
     return cudaGetLastError();
 }

@@ -184,6 +184,40 @@ def test_lattice_dense_population(opts):
     common.compare_worlds(e, o, 4, what="dense 256 (0.9)")
 
 
+@pytest.mark.parametrize("n,density,vision,steps,window", [(260, 1 / 16, (1, 6), 10, 96), (300, 1 / 8, (1, 6), 8, 96),
+                                                            (512, 1 / 16, (1, 10), 6, 128), (257, 1 / 3, (1, 4), 8, 96),
+                                                            (1000, 1 / 16, (1, 6), 4, 0)])
+def test_lattice_utilicalc_vs_oracle(n, density, vision, steps, window):
+    """The utilicalc rule (agent.py:1025-1141) in the warp-per-window kernel, keyed words: the welfare evaluation fused
+    into the movement scan, every agent settled on the spot -- bit-exact against the CPU oracle (positions, sugar,
+    deaths incl. the Q1 skips, statistics)."""
+    s, init = common.synthetic_case(n, False, density=density, vision=vision, utilicalc=True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg, options={"solo_window": window} if window else None), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 1
+    common.compare_worlds(e, o, steps, what="utilicalc %d" % n)
+    e.close()
+    o.close()
+
+
+def test_lattice_utilicalc_equals_serial_kernel_and_small_lattices_stay_serial():
+    g = common.load_golden("c1_default_utilicalc_keyed")
+    w = common.world_from_golden(g, "engine")
+    assert w.counters()["path"] == 0                      # 50 x 50: a single window -> the serial kernel
+    w.close()
+    s, init = common.synthetic_case(400, False, utilicalc=True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    a, b = common.engine_world(cfg), common.engine_world(cfg, path=0)
+    common.init_world(a, init, "keyed")
+    common.init_world(b, init, "keyed")
+    assert (a.counters()["path"], b.counters()["path"]) == (2, 1)
+    common.compare_worlds(a, b, 6, exact_gini=False, what="utilicalc lattice vs serial")
+    a.close()
+    b.close()
+
+
 @pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 2, "solo_window": 72}])
 def test_lattice_seasons(opts):
     s, init = common.synthetic_case(260, False, seasons=True)
