@@ -8,6 +8,7 @@ Workloads:
   c5 (default)  16384 x 16384 tiled two-peak landscape, 16,777,216 agents, vision 1-6,
                 grow + moveEat + canStarve, keyed RNG seed 18        <- the metric's config
   c4            4096 x 4096, 1,048,576 agents, same rules + pollution (A=B=1, diffusion every step)
+  c5u / c4u     the c5 / c4 worlds under the utilicalc rule instead of moveEat (no pollution)
 The JSON line carries: value (state resident in HBM, device-timed with CUDA events on the
 engine's stream), e2e (through the public Python API with host buffers: upload + K steps
 with per-step stats read-back + download), roofline of the dominant kernel class measured
@@ -53,6 +54,11 @@ def workload(name):
     if name == "c4":
         return dict(key="c4", n=4096, pollution=True, label="c4: 4096x4096 tiled landscape, 1048576 agents, "
                     "grow+moveEat+canStarve+pollution(A=B=1, diffusion every step), vision 1-6, keyed RNG seed 18")
+    if name in ("c5u", "c4u"):      # the same worlds under the utilicalc rule (agent.py:1025-1141) instead of moveEat
+        n = 16384 if name == "c5u" else 4096
+        return dict(key=name, n=n, pollution=False, utilicalc=True,
+                    label="%s: %dx%d tiled landscape, %d agents, grow+utilicalc+canStarve, vision 1-6, keyed RNG seed 18"
+                    % (name, n, n, n * n // 16))
     if name.startswith("preset:"):
         return dict(preset=name.split(":", 1)[1], n=50, pollution=False, label="shipped preset " + name.split(":", 1)[1])
     n = int(name)
@@ -63,7 +69,7 @@ def workload(name):
 def make_world(wl):
     t0 = time.time()
     w = synthetic.tiled_world(wl["n"])
-    s = synthetic.synthetic_settings(wl["n"], pollution=wl["pollution"])
+    s = synthetic.synthetic_settings(wl["n"], pollution=wl["pollution"], utilicalc=wl.get("utilicalc", False))
     sys.stderr.write("[bench] world %dx%d, %d agents generated in %.1fs\n" % (wl["n"], wl["n"], len(w["id"]),
                                                                                time.time() - t0))
     return s, w

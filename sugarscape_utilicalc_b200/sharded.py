@@ -227,6 +227,9 @@ class DistributedEngine:
 # ------------------------------------------------------------------------------ bench ----
 def bench_main(args, wl):
     """`torchrun ... bench.py --gpus N`: strong scaling of the same workload over N replicas."""
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        # NCCL writes its debug output (the version banner included) to stdout, where the one JSON line belongs
+        os.environ["NCCL_DEBUG_FILE"] = "/tmp/nccl_debug_%h_%p.log"
     import torch
     import torch.distributed as dist
     from . import config_from_settings, synthetic
@@ -236,7 +239,7 @@ def bench_main(args, wl):
     torch.cuda.set_device(local)
     t0 = time.time()
     w = synthetic.tiled_world(wl["n"])
-    settings = synthetic.synthetic_settings(wl["n"], pollution=wl["pollution"])
+    settings = synthetic.synthetic_settings(wl["n"], pollution=wl["pollution"], utilicalc=wl.get("utilicalc", False))
     cfg = config_from_settings(settings, rng_mode="keyed")
     if rank == 0:
         sys.stderr.write("[bench] world %d^2 generated in %.1fs on every rank\n" % (wl["n"], time.time() - t0))
@@ -275,22 +278,51 @@ def bench_main(args, wl):
     step_ms = 1e3 * float(wallt.item()) / K
     pops = np.concatenate([[pop0], st["population"][:-1]])
     value = float(pops.sum()) / (step_ms * K * 1e-3)
-    # e2e: upload on every rank + K steps + download on rank 0
+    # e2e: upload on every rank (page-locked host arrays, as in the single-GPU line) + K steps + download on rank 0
+    from .engine import pinned_copy, pinned_empty
+    pol_on = bool(wl["pollution"])
+    hw = {k: (pinned_copy(w[k], np.float64) if (k != "pollution" or pol_on) else None) for k in ("sugar", "cap", "pollution")}
+    hw.update({k: pinned_copy(w[k], np.int32) for k in ("id", "x", "y", "vision", "metab")})
+    hw["sugar_agent"] = pinned_copy(w["sugar_agent"], np.float64)
+    hout = aout = None
+    if rank == 0:
+        hout = dict(sugar=pinned_empty((wl["n"], wl["n"])), occ=pinned_empty((wl["n"], wl["n"]), np.int32))
+        if pol_on:
+            hout["pollution"] = pinned_empty((wl["n"], wl["n"]))
+        aout = {k: pinned_empty(len(w["id"]), np.int32) for k in ("id", "x", "y", "vision", "metab")}
+        aout["sugar"] = pinned_empty(len(w["id"]), np.float64)
     sync_all()
     t2 = time.perf_counter()
     de2 = DistributedEngine(cfg, device=local, options=opts)
-    de2.upload(w)
+    de2.upload(hw)
     Ke = min(K, args.e2e_steps)
     ste = de2.step(Ke)
     if rank == 0:
-        de2.r.eng.download_cells(cap=False)
-        de2.r.eng.download_agents()
+        de2.r.eng.download_cells(cap=False, pollution=pol_on, out=hout)
+        de2.r.eng.download_agents(out=aout)
     sync_all()
     e2e_s = torch.tensor([time.perf_counter() - t2], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
     n = wl["n"]
     if rank == 0:
+        # dominant kernel: the move passes of rank 0 (its share of the windows) against the HBM roofline, algorithmic bytes
+        # as in the single-GPU line (76+48v / 100+80v B per agent-step, E[v] = 3.5); the exchange against NVLink
+        try:
+            with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
+                peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        per_agent = (100 + 80 * 3.5) if wl["pollution"] else (76 + 48 * 3.5)
+        move_bytes = per_agent * float(st["acted"].sum()) / K / world
+        pass_s = max(de.t["pass"] / K, 1e-12)
+        roofline = {"bound": "hbm", "kernel": "ss_move_solo_kernel, rank 0's share of every pass (host-timed incl. launch + sync)",
+                    "achieved": move_bytes / pass_s / 1e9, "peak": peak, "unit": "GB/s", "frac": move_bytes / pass_s / 1e9 / peak,
+                    "traffic": None, "peak_source": peak_src, "ms_per_launch_set": 1e3 * pass_s}
+        recv = (world - 1) * (de.bytes_sent - b0) / K
+        gather_s = max(de.t["gather"] / K, 1e-12)
+        nvlink = {"what": "all-gather of the turn logs: bytes received per rank and step / time in the collectives (rank 0)",
+                  "achieved": recv / gather_s / 1e9, "peak": 900.0, "unit": "GB/s", "frac": recv / gather_s / 1e9 / 900.0}
         line = {
             "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -307,10 +339,10 @@ def bench_main(args, wl):
             "nccl_bytes_sent_per_rank_per_step": (de.bytes_sent - b0) / K,
             "rank0_ms_per_step": {k: 1e3 * v / K for k, v in de.t.items()},
             "e2e": {"value": float(popse.sum()) / float(e2e_s.item()), "unit": "agent-steps/s",
-                    "h2d_bytes_per_step": (3 * 8 * n * n + 28 * len(w["id"])) / Ke,
-                    "d2h_bytes_per_step": ((2 * 8 + 4) * n * n + 32 * len(w["id"]) + 48 * Ke) / Ke, "steps": Ke,
-                    "what": "per rank: Engine + upload from host numpy; K sharded steps; rank 0 downloads cells+agents"},
-            "roofline": None, "cpu_baseline": None,
+                    "h2d_bytes_per_step": ((2 + pol_on) * 8 * n * n + 28 * len(w["id"])) / Ke,
+                    "d2h_bytes_per_step": (((1 + pol_on) * 8 + 4) * n * n + 28 * len(w["id"]) + 48 * Ke) / Ke, "steps": Ke,
+                    "what": "per rank: Engine + upload from page-locked host arrays; K sharded steps with per-step stats read-back; rank 0 downloads cells+agents"},
+            "roofline": roofline, "nvlink": nvlink, "cpu_baseline": None,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

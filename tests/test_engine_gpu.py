@@ -310,6 +310,19 @@ def test_multi_gpu_replicas_equal_single_gpu_and_oracle(world, n, pollution, opt
     o.close()
 
 
+def test_multi_gpu_replicas_utilicalc():
+    """The utilicalc rule through the sharded path: every turn travels as a fully settled log entry."""
+    from sugarscape_utilicalc_b200.sharded import VirtualRanks
+    s, init = common.synthetic_case(300, False, utilicalc=True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    v, o = VirtualRanks(cfg, 3, options={"solo_window": 96}), common.oracle_world(cfg)
+    common.init_world(v, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(v, o, 6, what="virtual ranks utilicalc")
+    v.close()
+    o.close()
+
+
 def test_multi_gpu_eight_replicas():
     """World size 8 (the largest the bench is launched with): 16 window rows, two per rank."""
     from sugarscape_utilicalc_b200.sharded import VirtualRanks
