@@ -227,9 +227,9 @@ class DistributedEngine:
 # ------------------------------------------------------------------------------ bench ----
 def bench_main(args, wl):
     """`torchrun ... bench.py --gpus N`: strong scaling of the same workload over N replicas."""
-    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-        # NCCL writes its debug output (the version banner included) to stdout, where the one JSON line belongs
-        os.environ["NCCL_DEBUG_FILE"] = "/tmp/nccl_debug_%h_%p.log"
+    # NCCL writes its debug output (the version banner included, whether asked for through the environment or
+    # /etc/nccl.conf) to stdout, where the one JSON line belongs
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
     import torch
     import torch.distributed as dist
     from . import config_from_settings, synthetic
@@ -251,9 +251,17 @@ def bench_main(args, wl):
         torch.cuda.synchronize()
 
     opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in getattr(args, "opt", [])}
+    # page-locked copies of the world (both uploads read them; the pageable originals are dropped: N ranks share one host)
+    from .engine import pinned_copy, pinned_empty
+    pol_on = bool(wl["pollution"])
+    hw = {k: (pinned_copy(w[k], np.float64) if (k != "pollution" or pol_on) else None) for k in ("sugar", "cap", "pollution")}
+    hw.update({k: pinned_copy(w[k], np.int32) for k in ("id", "x", "y", "vision", "metab")})
+    hw["sugar_agent"] = pinned_copy(w["sugar_agent"], np.float64)
+    n_agents0 = len(w["id"])
+    w = {"id": hw["id"]}
     de = DistributedEngine(cfg, device=local, options=opts)
-    de.upload(w)
-    pop0 = len(w["id"])
+    de.upload(hw)
+    pop0 = n_agents0
     if W:
         pop0 = int(de.step(W)["population"][-1])
     sync_all()
@@ -279,11 +287,6 @@ def bench_main(args, wl):
     pops = np.concatenate([[pop0], st["population"][:-1]])
     value = float(pops.sum()) / (step_ms * K * 1e-3)
     # e2e: upload on every rank (page-locked host arrays, as in the single-GPU line) + K steps + download on rank 0
-    from .engine import pinned_copy, pinned_empty
-    pol_on = bool(wl["pollution"])
-    hw = {k: (pinned_copy(w[k], np.float64) if (k != "pollution" or pol_on) else None) for k in ("sugar", "cap", "pollution")}
-    hw.update({k: pinned_copy(w[k], np.int32) for k in ("id", "x", "y", "vision", "metab")})
-    hw["sugar_agent"] = pinned_copy(w["sugar_agent"], np.float64)
     hout = aout = None
     if rank == 0:
         hout = dict(sugar=pinned_empty((wl["n"], wl["n"])), occ=pinned_empty((wl["n"], wl["n"]), np.int32))
