@@ -230,6 +230,9 @@ def bench_main(args, wl):
     # NCCL writes its debug output (the version banner included, whether asked for through the environment or
     # /etc/nccl.conf) to stdout, where the one JSON line belongs
     os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
+    sys.stdout.flush()
+    json_fd = os.dup(1)             # ... and whatever else a library prints: stdout proper is kept for the JSON line only
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from . import config_from_settings, synthetic
@@ -348,7 +351,9 @@ def bench_main(args, wl):
             "roofline": roofline, "nvlink": nvlink, "cpu_baseline": None,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     de.close()
     de2.close()
     dist.destroy_process_group()
