@@ -173,15 +173,19 @@ int  ss_get_kernel_times(ss_engine* e, double* ms_out, int32_t n);
 int  ss_set_option(ss_engine* e, const char* name, int64_t value);
 
 /* Multi-GPU (one process per GPU; sugarscape_utilicalc_b200/sharded.py).  Every rank holds a replica of the
- * state and resolves the agents of its share of the window rows; the turns it resolved are exchanged as 48-byte
- * log entries (NCCL all-gather) and replayed on the other replicas.  One step =
+ * state and resolves the agents of its share of the window rows; the turns it resolved are exchanged as log entries
+ * (NCCL all-gather) and replayed on the other replicas: 8 bytes for the turn of an agent that cannot starve (slot |
+ * harvest << 24, new cell -- the rest follows from the replica's own record), 48 bytes (SS_SHARD_ENTRY_BYTES) for a
+ * synchronously settled turn or a Q1 skip.  One step =
  *   ss_shard_begin_step; { ss_shard_pass; <all-gather logs>; ss_shard_apply(each other rank's entries) }
  *   until ss_shard_pending == 0; ss_shard_end_step.
- * log_base/log_begin/log_end describe this rank's entries of the pass in device memory. */
+ * log_base/log_begin/log_end (48-byte entries) and clog_* (8-byte entries) describe this rank's entries of the pass in
+ * device memory. */
 int  ss_shard_enable(ss_engine* e, int32_t rank, int32_t world);
 int  ss_shard_begin_step(ss_engine* e);
-int  ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base);
-int  ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n);
+int  ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base, uint64_t* clog_begin,
+                   uint64_t* clog_end, const void** clog_base);
+int  ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n, const void* dev_compact, uint64_t n_compact);
 int  ss_shard_pending(ss_engine* e, uint64_t* pending);
 int  ss_shard_end_step(ss_engine* e, ss_step_stats* out);
 #define SS_SHARD_ENTRY_BYTES 48

@@ -100,8 +100,9 @@ def lib():
     L.ss_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.ss_shard_enable.argtypes = [vp, C.c_int32, C.c_int32]
     L.ss_shard_begin_step.argtypes = [vp]
-    L.ss_shard_pass.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp)]
-    L.ss_shard_apply.argtypes = [vp, vp, C.c_uint64]
+    L.ss_shard_pass.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp),
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp)]
+    L.ss_shard_apply.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
     L.ss_shard_pending.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ss_shard_end_step.argtypes = [vp, vp]
     L.ss_host_alloc.argtypes = [C.c_size_t]

@@ -35,8 +35,9 @@ cudaError_t ss_launch_move_pass(const DevWorld& w, const PassGeom& g, int64_t it
                                 cudaStream_t s);
 cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s);
 cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_time, cudaStream_t s);
-cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int64_t iteration, int64_t env_time,
-                                cudaStream_t s);
+cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int phase, cudaStream_t s);
+cudaError_t ss_launch_apply_clog(const DevWorld& w, const void* entries, unsigned long long n, int phase, int64_t iteration,
+                                 cudaStream_t s);
 cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
 size_t ss_diffuse_handoff_bytes(int n);
 cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, double* handoff, int impl, cudaStream_t s);
@@ -172,7 +173,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
     cudaFree(e->w.pendmap);
-    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count);
+    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -837,8 +838,12 @@ extern "C" int ss_shard_enable(ss_engine* e, int32_t rank, int32_t world) {
         e->w.log_cap = 8ull * e->w.n_slots + 4096;     // warps reserve 8 entries at a time: <= 7 unused per valid one
         CK(cudaMalloc(&e->w.log, sizeof(ShardLogEntry) * (size_t)e->w.log_cap));
         CK(cudaMalloc(&e->w.log_count, sizeof(unsigned long long)));
+        e->w.clog_cap = e->w.log_cap;
+        CK(cudaMalloc(&e->w.clog, sizeof(uint2) * (size_t)e->w.clog_cap));
+        CK(cudaMalloc(&e->w.clog_count, sizeof(unsigned long long)));
     }
     CK(cudaMemset(e->w.log_count, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(e->w.clog_count, 0, sizeof(unsigned long long)));
     return SS_OK;
 }
 
@@ -847,6 +852,7 @@ extern "C" int ss_shard_begin_step(ss_engine* e) {
     CK(cudaSetDevice(e->device));
     CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
     CK(cudaMemsetAsync(e->w.log_count, 0, sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->w.clog_count, 0, sizeof(unsigned long long), e->stream));
     CK(ss_launch_prepare(e->w, e->iteration, e->stream));
     e->launches += e->cfg.rule_can_starve ? 2 : 1;
     e->shard_pass = 0;
@@ -854,12 +860,15 @@ extern "C" int ss_shard_begin_step(ss_engine* e) {
     return rc;
 }
 
-// runs pass `shard_pass` on this rank's share of the window rows; returns the log range it appended
-extern "C" int ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base) {
-    if (!e || !e->w.log || !log_begin || !log_end || !log_base) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
+// runs pass `shard_pass` on this rank's share of the window rows; returns the ranges it appended to the two logs
+extern "C" int ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base, uint64_t* clog_begin,
+                             uint64_t* clog_end, const void** clog_base) {
+    if (!e || !e->w.log || !log_begin || !log_end || !log_base || !clog_begin || !clog_end || !clog_base)
+        return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
     CK(cudaSetDevice(e->device));
-    unsigned long long before = 0, after = 0;
+    unsigned long long before = 0, after = 0, cbefore = 0, cafter = 0;
     CK(cudaMemcpyAsync(&before, e->w.log_count, sizeof before, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&cbefore, e->w.clog_count, sizeof cbefore, cudaMemcpyDeviceToHost, e->stream));
     PassGeom g;
     pass_geometry(e, e->shard_pass, &g);
     const int nw = g.nwin, W = e->shard_world, r = e->shard_rank;
@@ -886,18 +895,25 @@ extern "C" int ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_en
     else CK(ss_launch_move_pass(e->w, g, e->iteration, e->env_time, e->stream));
     e->launches++; e->passes++; e->shard_pass++;
     CK(cudaMemcpyAsync(&after, e->w.log_count, sizeof after, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&cafter, e->w.clog_count, sizeof cafter, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->syncs++;
+    if (after > e->w.log_cap || cafter > e->w.clog_cap) return set_err(e, SS_ERR_STATE, "turn log overflow");
     *log_begin = before; *log_end = after; *log_base = e->w.log;
+    *clog_begin = cbefore; *clog_end = cafter; *clog_base = e->w.clog;
     return SS_OK;
 }
 
-// replays `n` entries (device pointer) resolved by another rank on this replica
-extern "C" int ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n) {
+// replays the entries (device pointers) another rank resolved in one pass on this replica: the clears of both logs, then
+// the sets (a cell can be left by a safe agent and entered by an at-risk one, or the other way round, in the same pass)
+extern "C" int ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n, const void* dev_compact, uint64_t n_compact) {
     if (!e || !e->w.log) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
     CK(cudaSetDevice(e->device));
-    CK(ss_launch_apply_log(e->w, dev_entries, n, e->iteration, e->env_time, e->stream));
-    if (n) e->launches++;
+    for (int phase = 0; phase < 2; phase++) {
+        CK(ss_launch_apply_log(e->w, dev_entries, n, phase, e->stream));
+        CK(ss_launch_apply_clog(e->w, dev_compact, n_compact, phase, e->iteration, e->stream));
+    }
+    e->launches += 2 * ((n ? 1 : 0) + (n_compact ? 1 : 0));
     return SS_OK;
 }
 

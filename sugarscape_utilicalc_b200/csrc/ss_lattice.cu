@@ -134,12 +134,24 @@ __device__ static inline bool crosses_meet(int dx, int dy, int a, int b) {
 struct ThreadStats {
     unsigned sum_m, sum_v, acted, deaths, resolved, small, inexact;
     unsigned long long log_pos, log_end;      // multi-GPU: this warp's reserved slice of the turn log
+    unsigned long long clog_pos, clog_end;    // ... and of the compact log of safe turns
 };
 #define LOG_CHUNK 8
 // next free entry of the rank's turn log: one global atomic per LOG_CHUNK entries of a warp
 __device__ static inline ShardLogEntry* log_slot(const DevWorld& w, ThreadStats& ts) {
     if (ts.log_pos == ts.log_end) { ts.log_pos = atomicAdd(w.log_count, (unsigned long long)LOG_CHUNK); ts.log_end = ts.log_pos + LOG_CHUNK; }
     return &w.log[ts.log_pos++];
+}
+
+#define CLOG_UNUSED 0xffffffffu
+__device__ static inline uint2* clog_slot(const DevWorld& w, ThreadStats& ts) {
+    if (ts.clog_pos == ts.clog_end) { ts.clog_pos = atomicAdd(w.clog_count, (unsigned long long)LOG_CHUNK); ts.clog_end = ts.clog_pos + LOG_CHUNK; }
+    return &w.clog[ts.clog_pos++];
+}
+// the reserved but unused entries of a warp's log slices are marked before the kernel ends
+__device__ static inline void close_log_slices(const DevWorld& w, ThreadStats& ts) {
+    while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;
+    while (ts.clog_pos < ts.clog_end) w.clog[ts.clog_pos++] = make_uint2(CLOG_UNUSED, 0u);
 }
 
 struct Choice { int lr, lq, sg; };
@@ -313,12 +325,7 @@ __device__ static inline void commit_turn(const DevWorld& w, const Ctx& c, int l
         }
         recp->pos = (uint32_t)cell;
         recp->turn = ((uint32_t)(iteration + 1) << 8) | (uint32_t)sg;
-        if (w.log) {
-            ShardLogEntry en;
-            en.slot = slot; en.old_cell = (uint32_t)pos; en.new_cell = (uint32_t)cell; en.new_word = new_word;
-            en.sugar = 0.0; en.poll = 0.0; en.attr = 0u; en.status = 0u; en.turn = recp->turn; en.kind_harvest = 0u | ((uint32_t)sg << 8);
-            *log_slot(w, ts) = en;
-        }
+        if (w.log) *clog_slot(w, ts) = make_uint2(slot | ((uint32_t)sg << 24), (uint32_t)cell);
         return;
     }
     const bool pol = w.cfg.rule_pollution != 0 && w.cfg.pollution_start_time <= env_time;
@@ -844,7 +851,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     __syncthreads();
     if (sh.count[0] == 0) { write_map(); return; }
     const long long t_listed = PASS_CLOCK();
-    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
+    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull, 0ull, 0ull};
     // ---- the region's agents in ascending priority ----
     for (int iter = 0;; iter++) {
         if (iter > PASS_LIST + 8) { if (lane == 0) { atomicAdd(&w.acc->fault, 1ull); w.acc->wd_info[2] = 0x2222; } break; }
@@ -1042,7 +1049,7 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
     }
     if (lane == 0) {
         __threadfence_block(); me.done = 1;
-        while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;      // unused part of the reserved slice
+        close_log_slices(w, ts);
     }
     __syncthreads();
     write_map();
@@ -1126,8 +1133,9 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     const int nb = w.pend_nb;
     if (g.map_read >= 0) {          // coarse pending map: nothing left in this window's core -> hand the entries on
         const uint32_t* mr = w.pendmap + (size_t)g.map_read * nb * nb;
-        const int cx0 = (c.gx0 + R) >> 5, cx1 = (c.gx0 + c.ex - R - 1) >> 5;
-        const int cy0 = (c.gy0 + R) >> 5, cy1 = (c.gy0 + c.ey - R - 1) >> 5;
+        const int Rm = V + 1;           // core of the smallest vision
+        const int cx0 = (c.gx0 + Rm) >> 5, cx1 = (c.gx0 + c.ex - Rm - 1) >> 5;
+        const int cy0 = (c.gy0 + Rm) >> 5, cy1 = (c.gy0 + c.ey - Rm - 1) >> 5;
         const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
         int any = 0;
         for (int i = lane; i < ncx * ncy; i += 32)
@@ -1190,14 +1198,16 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         unsigned m = (o.x != 0u && (o.x >> 31) == cur_phase ? 1u : 0u) | (o.y != 0u && (o.y >> 31) == cur_phase ? 2u : 0u) |
                      (o.z != 0u && (o.z >> 31) == cur_phase ? 4u : 0u) | (o.w != 0u && (o.w >> 31) == cur_phase ? 8u : 0u);
         if (m == 0u) return;
-        const bool row_core = lx >= R && lx < c.ex - R;
+        // an agent of vision a is core iff it stands >= a + vmax from every window edge: then no agent outside the
+        // window can share a cell with its cross (R = 2 vmax is that bound for the largest vision)
         uint32_t ringbits = 0u;
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
             const uint32_t ow = j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w;
             const int ly = ly0 + j;
-            if (!(row_core && ly >= R && ly < c.ey - R)) { ringbits |= 1u << (ly & 31); continue; }
+            const int Ra = (int)((ow >> 24) & 31u) + V;
+            if (!(lx >= Ra && lx < c.ex - Ra && ly >= Ra && ly < c.ey - Ra)) { ringbits |= 1u << (ly & 31); continue; }
             uint32_t key = ow;                                      // first scan: hashed below
             if (!first) {
                 const uint32_t p = ss_priority(ok, occ_slot(ow));
@@ -1286,7 +1296,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         }
     }
     SOLO_TICK(t_sort);
-    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull};
+    ThreadStats ts = {0, 0, 0, 0, 0, 0, 0, 0ull, 0ull, 0ull, 0ull};
     uint32_t slot_batch = 0u;
     if (LANES) {
         // ---- one LANE per agent.  The warp holds the (up to) 32 unresolved list entries of lowest priority, in list
@@ -1547,7 +1557,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
         }
         __syncwarp();
     }
-    while (ts.log_pos < ts.log_end) w.log[ts.log_pos++].kind_harvest = 255u;      // unused part of the reserved slice
+    close_log_slices(w, ts);
     __syncwarp();
     if (!LANES) SOLO_TICK(t_act);
     write_map();
@@ -1654,6 +1664,32 @@ ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsig
     if (sugar == 0.01) atomicAdd(&w.acc->hist_small, 1ull);
     else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
     else atomicAdd(&w.acc->inexact, 1ull);
+}
+
+// The compact entries (safe agents: move now, settle later).  Phase 0 clears the cell the agent left -- its position in
+// the replica's own record --, phase 1 seats it on the new cell and stamps the deferred turn, exactly as commit_turn does.
+__global__ void __launch_bounds__(256)
+ss_apply_clog_kernel(DevWorld w, const uint2* __restrict__ entries, unsigned long long n_entries, int phase, int64_t iteration) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 en = make_uint2(CLOG_UNUSED, 0u);
+    if (i < n_entries) en = entries[i];
+    const bool valid = en.x != CLOG_UNUSED;
+    if (phase == 1) {
+        const unsigned m = __ballot_sync(FULL, valid);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.acc->pending, (unsigned long long)(-(long long)__popc(m)));
+    }
+    if (!valid) return;
+    const uint32_t slot = en.x & OCC_SLOT_MASK, sg = en.x >> 24, cell = en.y;
+    AgentRec* rec = &w.agents[slot];
+    if (phase == 0) {
+        const uint32_t old = rec->pos;
+        if (old != cell) w.occw[old] = 0u;
+        return;
+    }
+    w.occw[cell] = occ_pack(slot, attr_vision(rec->attr), (uint32_t)((iteration + 1) & 1));
+    if (w.cfg.rule_move_eat) { w.sugar[cell] = 0.0; w.isugar[cell] = 0; }
+    rec->pos = cell;
+    rec->turn = ((uint32_t)(iteration + 1) << 8) | sg;
 }
 
 // ------------------------------------------------------------------------------ settle ----
@@ -2447,12 +2483,17 @@ size_t ss_pass_smem_bytes(int emax, int ew, int vmax) {
     return (((size_t)emax * emax * 5 + 15) & ~(size_t)15) + sizeof(RegionShared) * PASS_WARPS + (size_t)emax * ew * 4 + 16;
 }
 
-cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int64_t iteration, int64_t env_time,
-                                cudaStream_t s) {
+// one phase (0 clears, 1 sets) of the replay of another rank's entries; the caller runs phase 0 of both logs before phase 1
+cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int phase, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    (void)iteration; (void)env_time;
-    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, 0);
-    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, 1);
+    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, phase);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_apply_clog(const DevWorld& w, const void* entries, unsigned long long n, int phase, int64_t iteration,
+                                 cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    ss_apply_clog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const uint2*)entries, n, phase, iteration);
     return cudaGetLastError();
 }
 

@@ -53,9 +53,12 @@ struct DevWorld {
     unsigned long long* dbg;        // optional instrumentation counters (32 entries) or null
     uint32_t* pendmap;              // 2 x pend_nb^2 counters: agents a launch left pending, per 32x32-cell block
     int pend_nb;
-    struct ShardLogEntry* log;      // multi-GPU: turns resolved by this rank (null on a single GPU)
+    struct ShardLogEntry* log;      // multi-GPU: turns resolved by this rank (null on a single GPU): at-risk agents, Q1 skips
     unsigned long long* log_count;
     unsigned long long log_cap;
+    uint2* clog;                    // ... and the turns of safe agents, 8 bytes each: x = slot | harvest << 24, y = new cell
+    unsigned long long* clog_count; //     (old cell, occupancy word and turn stamp follow from the replica's own record)
+    unsigned long long clog_cap;
 };
 
 struct PassGeom {                   // window tiling of one move pass

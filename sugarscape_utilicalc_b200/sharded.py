@@ -28,7 +28,8 @@ from . import capi
 from .engine import Engine, EngineError
 from .capi import STATS_DTYPE
 
-ENTRY_BYTES = 48
+ENTRY_BYTES = 48         # synchronously settled turns, Q1 skips (ShardLogEntry)
+COMPACT_BYTES = 8        # turns of agents that cannot starve: slot | harvest << 24, new cell
 
 
 def window_rows_for_rank(nwin, rank, world):
@@ -36,21 +37,32 @@ def window_rows_for_rank(nwin, rank, world):
     return (rank * nwin) // world, ((rank + 1) * nwin) // world
 
 
-def pad_and_gather(local_bytes, n_local, world, gather_counts, gather_padded):
+def pad_and_gather(local_bytes, n_local, world, gather_counts, gather_padded, entry_bytes=ENTRY_BYTES, local2=None, n2=0,
+                   entry_bytes2=COMPACT_BYTES):
     """Variable-length all-gather through two fixed-size collectives.
-    local_bytes: 1-D uint8 tensor with n_local*ENTRY_BYTES valid bytes; returns (counts, list of per-rank
-    uint8 tensors trimmed to their length)."""
+    local_bytes: 1-D uint8 tensor with n_local*entry_bytes valid bytes; optionally a second log (local2, n2 entries of
+    entry_bytes2) travels in the same buffer.  Returns (counts, parts) or, with a second log, (counts, parts, counts2,
+    parts2): per-rank uint8 tensors trimmed to their length."""
     import torch
-    counts_t = torch.tensor([int(n_local)], dtype=torch.int64, device=local_bytes.device)
-    all_counts = gather_counts(counts_t)                      # (world,) int64
-    counts = [int(c) for c in all_counts.tolist()]
-    mx = max(counts) if counts else 0
-    if mx == 0:
-        return counts, [local_bytes[:0] for _ in range(world)]
-    buf = torch.zeros(mx * ENTRY_BYTES, dtype=torch.uint8, device=local_bytes.device)
-    buf[: n_local * ENTRY_BYTES] = local_bytes[: n_local * ENTRY_BYTES]
-    allb = gather_padded(buf)                                 # (world, mx*ENTRY_BYTES)
-    return counts, [allb[r, : counts[r] * ENTRY_BYTES] for r in range(world)]
+    two = local2 is not None
+    counts_t = torch.tensor([int(n_local), int(n2)], dtype=torch.int64, device=local_bytes.device)
+    all_counts = gather_counts(counts_t).reshape(world, 2).tolist()           # (world, 2) int64
+    counts = [int(c[0]) for c in all_counts]
+    counts2 = [int(c[1]) for c in all_counts]
+    mx, mx2 = max(counts), max(counts2)
+    if mx == 0 and mx2 == 0:
+        empty = [local_bytes[:0] for _ in range(world)]
+        return (counts, empty, counts2, list(empty)) if two else (counts, empty)
+    off2 = (mx * entry_bytes + 15) // 16 * 16
+    buf = torch.empty(off2 + mx2 * entry_bytes2, dtype=torch.uint8, device=local_bytes.device)
+    buf[: n_local * entry_bytes] = local_bytes[: n_local * entry_bytes]
+    if two and n2:
+        buf[off2: off2 + n2 * entry_bytes2] = local2[: n2 * entry_bytes2]
+    allb = gather_padded(buf)                                 # (world, len(buf))
+    parts = [allb[r, : counts[r] * entry_bytes] for r in range(world)]
+    if not two:
+        return counts, parts
+    return counts, parts, counts2, [allb[r, off2: off2 + counts2[r] * entry_bytes2] for r in range(world)]
 
 
 class _DevView:
@@ -85,12 +97,17 @@ class ShardRank:
         self._check(self._lib.ss_shard_begin_step(self.eng._h), "ss_shard_begin_step")
 
     def run_pass(self):
+        """One pass over this rank's window rows -> (ptr, n) of its 48-byte entries, (ptr, n) of its 8-byte entries."""
         b, e, base = C.c_uint64(), C.c_uint64(), C.c_void_p()
-        self._check(self._lib.ss_shard_pass(self.eng._h, C.byref(b), C.byref(e), C.byref(base)), "ss_shard_pass")
-        return int(base.value) + b.value * ENTRY_BYTES, int(e.value - b.value)
+        cb, ce, cbase = C.c_uint64(), C.c_uint64(), C.c_void_p()
+        self._check(self._lib.ss_shard_pass(self.eng._h, C.byref(b), C.byref(e), C.byref(base), C.byref(cb), C.byref(ce),
+                                            C.byref(cbase)), "ss_shard_pass")
+        return (int(base.value) + b.value * ENTRY_BYTES, int(e.value - b.value),
+                int(cbase.value) + cb.value * COMPACT_BYTES, int(ce.value - cb.value))
 
-    def apply(self, dev_ptr, n):
-        self._check(self._lib.ss_shard_apply(self.eng._h, C.c_void_p(int(dev_ptr)), int(n)), "ss_shard_apply")
+    def apply(self, dev_ptr, n, compact_ptr=0, n_compact=0):
+        self._check(self._lib.ss_shard_apply(self.eng._h, C.c_void_p(int(dev_ptr)), int(n), C.c_void_p(int(compact_ptr)),
+                                             int(n_compact)), "ss_shard_apply")
 
     def pending(self):
         p = C.c_uint64()
@@ -132,9 +149,9 @@ class VirtualRanks:
                 logs = [r.run_pass() for r in self.ranks]
                 self.passes += 1
                 for i, r in enumerate(self.ranks):
-                    for j, (ptr, n) in enumerate(logs):
+                    for j, (ptr, n, cptr, cn) in enumerate(logs):
                         if j != i:
-                            r.apply(ptr, n)
+                            r.apply(ptr, n, cptr, cn)
                 pend = [r.pending() for r in self.ranks]
                 assert len(set(pend)) == 1, "replicas disagree on the pending count: %s" % pend
                 if pend[0] == 0:
@@ -181,7 +198,7 @@ class DistributedEngine:
         self.r.upload(w)
 
     def _gather_counts(self, t):
-        out = self.torch.empty(self.world, dtype=self.torch.int64, device=t.device)
+        out = self.torch.empty(self.world * t.numel(), dtype=self.torch.int64, device=t.device)
         self.dist.all_gather_into_tensor(out, t)
         return out
 
@@ -200,17 +217,21 @@ class DistributedEngine:
             t1 = pc(); self.t["begin"] += t1 - t0
             while True:
                 t1 = pc()
-                ptr, n = self.r.run_pass()                   # engine stream is synchronised on return
+                ptr, n, cptr, cn = self.r.run_pass()         # engine stream is synchronised on return
                 t2 = pc(); self.t["pass"] += t2 - t1
                 self.passes += 1
-                local = torch.as_tensor(_DevView(ptr, max(n, 1) * ENTRY_BYTES), device="cuda:%d" % self.device)
-                counts, parts = pad_and_gather(local, n, self.world, self._gather_counts, self._gather_padded)
+                dev = "cuda:%d" % self.device
+                local = torch.as_tensor(_DevView(ptr, max(n, 1) * ENTRY_BYTES), device=dev)
+                local2 = torch.as_tensor(_DevView(cptr, max(cn, 1) * COMPACT_BYTES), device=dev)
+                counts, parts, counts2, parts2 = pad_and_gather(local, n, self.world, self._gather_counts,
+                                                                self._gather_padded, local2=local2, n2=cn)
                 torch.cuda.current_stream().synchronize()    # NCCL results before the engine's stream reads them
                 t3 = pc(); self.t["gather"] += t3 - t2
-                self.bytes_sent += n * ENTRY_BYTES
+                self.bytes_sent += n * ENTRY_BYTES + cn * COMPACT_BYTES
                 for j in range(self.world):
-                    if j != self.rank and counts[j]:
-                        self.r.apply(parts[j].data_ptr(), counts[j])
+                    if j != self.rank and (counts[j] or counts2[j]):
+                        self.r.apply(parts[j].data_ptr() if counts[j] else 0, counts[j],
+                                     parts2[j].data_ptr() if counts2[j] else 0, counts2[j])
                 done = self.r.pending() == 0
                 self.t["apply+pending"] += pc() - t3
                 if done:

@@ -45,6 +45,17 @@ def _worker(rank, world, port, q):
                 exp = np.random.default_rng(100 * rnd + r).integers(0, 256, size=max(lens[r], 1) * sharded.ENTRY_BYTES,
                                                                     dtype=np.uint8)[: lens[r] * sharded.ENTRY_BYTES]
                 ok &= np.array_equal(parts[r].numpy(), exp)
+            # both logs in one buffer: 48-byte entries and the 8-byte compact entries
+            lens2 = (5 * rnd + 1, 2)
+            n2 = lens2[rank]
+            pay2 = torch.from_numpy(np.random.default_rng(7000 + 100 * rnd + rank).integers(
+                0, 256, size=max(n2, 1) * sharded.COMPACT_BYTES, dtype=np.uint8))
+            c1, p1, c2, p2 = sharded.pad_and_gather(payload, n, world, gather_counts, gather_padded, local2=pay2, n2=n2)
+            ok &= c1 == list(lens) and c2 == list(lens2)
+            for r in range(world):
+                exp2 = np.random.default_rng(7000 + 100 * rnd + r).integers(
+                    0, 256, size=max(lens2[r], 1) * sharded.COMPACT_BYTES, dtype=np.uint8)[: lens2[r] * sharded.COMPACT_BYTES]
+                ok &= np.array_equal(p2[r].numpy(), exp2) and np.array_equal(p1[r].numpy(), parts[r].numpy())
             # termination: every rank derives the same pending count from the gathered lengths
             pend = torch.tensor([100 - sum(counts)])
             dist.all_reduce(pend, op=dist.ReduceOp.MAX)
