@@ -183,6 +183,13 @@ class Engine:
         return dict(launches=int(out[0]), passes=int(out[1]), steps=int(out[2]), path=int(out[3]),
                     syncs=int(out[4]), window=int(out[5]) & 0xffff, pass_impl=int(out[5]) >> 16)
 
+    def health(self):
+        """Device-side consistency counters of the lattice path: watchdog firings of the spin waits and internal
+        faults (a draw loop that did not terminate, more tied candidates than the geometry allows).  Both must be 0."""
+        out = np.zeros(11, dtype=np.int64)
+        self._check(self._lib.ss_get_counters(self._h, _ptr(out), 11), "ss_get_counters")
+        return dict(watchdog=int(out[6]), fault=int(out[10]))
+
     def kernel_times(self):
         out = np.zeros(8, dtype=np.float64)
         self._check(self._lib.ss_get_kernel_times(self._h, _ptr(out), 8), "ss_get_kernel_times")

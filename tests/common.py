@@ -133,6 +133,10 @@ def compare_worlds(a, b, steps, exact_gini=False, every=1, what=""):
         exp = dict(sugar=cb["sugar"], pollution=cb["pollution"], occ=cb["occ"], order=gb["id"], x=gb["x"], y=gb["y"],
                    sugar_agent=gb["sugar"])
         assert_state_equal(ca, ga, exp, ordered=True, what="%s step %d" % (what, t + k))
+    for w in (a, b):            # engines: no watchdog firing, no internal fault on the device
+        engines = [r.eng for r in w.ranks] if hasattr(w, "ranks") else [w] if hasattr(w, "health") else []
+        for e in engines:
+            assert e.health() == dict(watchdog=0, fault=0), what
 
 
 def smoke_check():
