@@ -1098,7 +1098,9 @@ ss_move_pass_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 // shared-memory image, which leaves room for 32 resident warps per SM, each with an independent window: the
 // latency of one agent's turn is hidden by the other windows instead of stalling a CTA.  Shared memory per warp:
 // the sorted key list and the blocked bitmap.
+#ifndef SOLO_LIST
 #define SOLO_LIST 1024
+#endif
 #ifndef SOLO_SCAN_ROWS
 #define SOLO_SCAN_ROWS 8
 #endif
