@@ -186,6 +186,10 @@ int  ss_shard_begin_step(ss_engine* e);
 int  ss_shard_pass(ss_engine* e, uint64_t* log_begin, uint64_t* log_end, const void** log_base, uint64_t* clog_begin,
                    uint64_t* clog_end, const void** clog_base);
 int  ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n, const void* dev_compact, uint64_t n_compact);
+/* ss_shard_apply for every other rank at once, straight from the all-gathered buffer: rank j's slice starts at
+ * base + j * stride (48-byte entries first, 8-byte entries at off_compact); counts = device int64 [world][2]. */
+int  ss_shard_apply_gathered(ss_engine* e, const void* base, uint64_t stride, uint64_t off_compact, const int64_t* counts,
+                             int32_t world, uint64_t max_full, uint64_t max_compact);
 int  ss_shard_pending(ss_engine* e, uint64_t* pending);
 int  ss_shard_end_step(ss_engine* e, ss_step_stats* out);
 #define SS_SHARD_ENTRY_BYTES 48

@@ -57,7 +57,7 @@ EXPORTS = (
     "ss_set_rng_mt19937", "ss_get_rng_mt19937", "ss_set_rng_keyed", "ss_step", "ss_agent_count",
     "ss_download_cells", "ss_download_agents", "ss_get_counters", "ss_get_kernel_times",
     "ss_set_option", "ss_version", "ss_shard_enable", "ss_shard_begin_step", "ss_shard_pass", "ss_shard_apply",
-    "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free", "ss_seed_mt19937", "ss_init_world",
+    "ss_shard_apply_gathered", "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free", "ss_seed_mt19937", "ss_init_world",
 )
 
 _lib = None
@@ -103,6 +103,7 @@ def lib():
     L.ss_shard_pass.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp),
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp)]
     L.ss_shard_apply.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
+    L.ss_shard_apply_gathered.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_int32, C.c_uint64, C.c_uint64]
     L.ss_shard_pending.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ss_shard_end_step.argtypes = [vp, vp]
     L.ss_host_alloc.argtypes = [C.c_size_t]

@@ -38,6 +38,9 @@ cudaError_t ss_launch_settle(const DevWorld& w, int64_t iteration, int64_t env_t
 cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int phase, cudaStream_t s);
 cudaError_t ss_launch_apply_clog(const DevWorld& w, const void* entries, unsigned long long n, int phase, int64_t iteration,
                                  cudaStream_t s);
+cudaError_t ss_launch_apply_gathered(const DevWorld& w, const void* base, unsigned long long stride, unsigned long long off_compact,
+                                     const long long* counts, int world, int skip_rank, unsigned long long max_full,
+                                     unsigned long long max_compact, int phase, int64_t iteration, cudaStream_t s);
 cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
 size_t ss_diffuse_handoff_bytes(int n);
 cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, double* handoff, int impl, cudaStream_t s);
@@ -914,6 +917,20 @@ extern "C" int ss_shard_apply(ss_engine* e, const void* dev_entries, uint64_t n,
         CK(ss_launch_apply_clog(e->w, dev_compact, n_compact, phase, e->iteration, e->stream));
     }
     e->launches += 2 * ((n ? 1 : 0) + (n_compact ? 1 : 0));
+    return SS_OK;
+}
+
+// the same for every other rank at once, straight from the all-gathered buffer: rank j's slice starts at base + j * stride
+// (48-byte entries at offset 0, 8-byte entries at off_compact), counts = device int64 [world][2] (entries per log)
+extern "C" int ss_shard_apply_gathered(ss_engine* e, const void* base, uint64_t stride, uint64_t off_compact, const int64_t* counts,
+                                       int32_t world, uint64_t max_full, uint64_t max_compact) {
+    if (!e || !e->w.log) return set_err(e, SS_ERR_STATE, "ss_shard_enable first");
+    if (!base || !counts || world != e->shard_world) return set_err(e, SS_ERR_ARG, "bad gathered log buffer");
+    CK(cudaSetDevice(e->device));
+    for (int phase = 0; phase < 2; phase++)
+        CK(ss_launch_apply_gathered(e->w, base, stride, off_compact, (const long long*)counts, world, e->shard_rank, max_full,
+                                    max_compact, phase, e->iteration, e->stream));
+    e->launches += 2 * ((max_full ? 1 : 0) + (max_compact ? 1 : 0));
     return SS_OK;
 }
 

@@ -1622,8 +1622,26 @@ ss_move_solo_kernel(DevWorld w, PassGeom g, int64_t iteration, int64_t env_time)
 // agent dies on it and another moves in), always in the order leave/die ... enter, and at most one
 // entry leaves a living agent on it.  Replay therefore runs in two phases: 0 = clears (cells left,
 // cells agents died on), 1 = sets (living agents' words) and everything that commutes.
+// Gathered form (all ranks' slices in one buffer, NCCL all-gather layout): blockIdx.y = source rank, its slice starts
+// `stride` bytes after the previous one, its entry count is counts[2 * rank + which]; the own rank's slice is skipped.
+struct GatheredLogs {
+    const unsigned char* base;      // null: plain form (entries, n_entries)
+    unsigned long long stride, offset;
+    const long long* counts;
+    int which, skip_rank;
+};
+template <class Entry>
+__device__ static inline bool gathered_slice(const GatheredLogs& gl, const Entry*& entries, unsigned long long& n_entries) {
+    if (!gl.base) return true;
+    const int j = (int)blockIdx.y;
+    if (j == gl.skip_rank) return false;
+    entries = (const Entry*)(gl.base + (unsigned long long)j * gl.stride + gl.offset);
+    n_entries = (unsigned long long)gl.counts[2 * j + gl.which];
+    return true;
+}
 __global__ void __launch_bounds__(256)
-ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsigned long long n_entries, int phase) {
+ss_apply_log_kernel(DevWorld w, const ShardLogEntry* entries, unsigned long long n_entries, int phase, GatheredLogs gl) {
+    if (!gathered_slice(gl, entries, n_entries)) return;
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i < n_entries;
     ShardLogEntry en;
@@ -1671,7 +1689,9 @@ ss_apply_log_kernel(DevWorld w, const ShardLogEntry* __restrict__ entries, unsig
 // The compact entries (safe agents: move now, settle later).  Phase 0 clears the cell the agent left -- its position in
 // the replica's own record --, phase 1 seats it on the new cell and stamps the deferred turn, exactly as commit_turn does.
 __global__ void __launch_bounds__(256)
-ss_apply_clog_kernel(DevWorld w, const uint2* __restrict__ entries, unsigned long long n_entries, int phase, int64_t iteration) {
+ss_apply_clog_kernel(DevWorld w, const uint2* entries, unsigned long long n_entries, int phase, int64_t iteration,
+                     GatheredLogs gl) {
+    if (!gathered_slice(gl, entries, n_entries)) return;
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint2 en = make_uint2(CLOG_UNUSED, 0u);
     if (i < n_entries) en = entries[i];
@@ -2488,14 +2508,32 @@ size_t ss_pass_smem_bytes(int emax, int ew, int vmax) {
 // one phase (0 clears, 1 sets) of the replay of another rank's entries; the caller runs phase 0 of both logs before phase 1
 cudaError_t ss_launch_apply_log(const DevWorld& w, const void* entries, unsigned long long n, int phase, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, phase);
+    GatheredLogs gl{};
+    ss_apply_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const ShardLogEntry*)entries, n, phase, gl);
+    return cudaGetLastError();
+}
+// one phase of the replay of every other rank's slices of an all-gathered buffer: one launch per log
+cudaError_t ss_launch_apply_gathered(const DevWorld& w, const void* base, unsigned long long stride, unsigned long long off_compact,
+                                     const long long* counts, int world, int skip_rank, unsigned long long max_full,
+                                     unsigned long long max_compact, int phase, int64_t iteration, cudaStream_t s) {
+    GatheredLogs gl;
+    gl.base = (const unsigned char*)base; gl.stride = stride; gl.counts = counts; gl.skip_rank = skip_rank;
+    if (max_full) {
+        gl.offset = 0; gl.which = 0;
+        ss_apply_log_kernel<<<dim3((unsigned)((max_full + 255) / 256), (unsigned)world), 256, 0, s>>>(w, nullptr, 0, phase, gl);
+    }
+    if (max_compact) {
+        gl.offset = off_compact; gl.which = 1;
+        ss_apply_clog_kernel<<<dim3((unsigned)((max_compact + 255) / 256), (unsigned)world), 256, 0, s>>>(w, nullptr, 0, phase, iteration, gl);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t ss_launch_apply_clog(const DevWorld& w, const void* entries, unsigned long long n, int phase, int64_t iteration,
                                  cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    ss_apply_clog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const uint2*)entries, n, phase, iteration);
+    GatheredLogs gl{};
+    ss_apply_clog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, (const uint2*)entries, n, phase, iteration, gl);
     return cudaGetLastError();
 }
 

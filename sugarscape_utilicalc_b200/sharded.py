@@ -37,6 +37,27 @@ def window_rows_for_rank(nwin, rank, world):
     return (rank * nwin) // world, ((rank + 1) * nwin) // world
 
 
+def gather_logs(local_bytes, n_local, local2, n2, world, gather_counts, gather_padded):
+    """Both logs of a pass through one counts collective and one payload collective.  Returns the raw all-gathered
+    buffer and its layout: dict(buf=(world, stride) uint8 tensor or None, stride, off2, counts_dev=(world, 2) int64 device
+    tensor, mx, mx2) -- what ss_shard_apply_gathered takes."""
+    import torch
+    counts_t = torch.tensor([int(n_local), int(n2)], dtype=torch.int64, device=local_bytes.device)
+    counts_dev = gather_counts(counts_t).reshape(world, 2)
+    host = counts_dev.tolist()
+    mx, mx2 = max(int(c[0]) for c in host), max(int(c[1]) for c in host)
+    if mx == 0 and mx2 == 0:
+        return dict(buf=None, stride=0, off2=0, counts_dev=counts_dev, mx=0, mx2=0)
+    off2 = (mx * ENTRY_BYTES + 15) // 16 * 16
+    buf = torch.empty(off2 + mx2 * COMPACT_BYTES, dtype=torch.uint8, device=local_bytes.device)
+    if n_local:
+        buf[: n_local * ENTRY_BYTES] = local_bytes[: n_local * ENTRY_BYTES]
+    if n2:
+        buf[off2: off2 + n2 * COMPACT_BYTES] = local2[: n2 * COMPACT_BYTES]
+    allb = gather_padded(buf)
+    return dict(buf=allb, stride=buf.numel(), off2=off2, counts_dev=counts_dev, mx=mx, mx2=mx2)
+
+
 def pad_and_gather(local_bytes, n_local, world, gather_counts, gather_padded, entry_bytes=ENTRY_BYTES, local2=None, n2=0,
                    entry_bytes2=COMPACT_BYTES):
     """Variable-length all-gather through two fixed-size collectives.
@@ -105,6 +126,14 @@ class ShardRank:
         return (int(base.value) + b.value * ENTRY_BYTES, int(e.value - b.value),
                 int(cbase.value) + cb.value * COMPACT_BYTES, int(ce.value - cb.value))
 
+    def apply_gathered(self, g):
+        """Replay every other rank's slices of a gather_logs() result."""
+        if g["buf"] is None:
+            return
+        self._check(self._lib.ss_shard_apply_gathered(self.eng._h, C.c_void_p(g["buf"].data_ptr()), int(g["stride"]),
+                                                      int(g["off2"]), C.c_void_p(g["counts_dev"].data_ptr()), self.world,
+                                                      int(g["mx"]), int(g["mx2"])), "ss_shard_apply_gathered")
+
     def apply(self, dev_ptr, n, compact_ptr=0, n_compact=0):
         self._check(self._lib.ss_shard_apply(self.eng._h, C.c_void_p(int(dev_ptr)), int(n), C.c_void_p(int(compact_ptr)),
                                              int(n_compact)), "ss_shard_apply")
@@ -127,10 +156,14 @@ class VirtualRanks:
     """P replicas in one process on one GPU: the N>1 code path without NCCL (log slices are handed over
     as device pointers).  Same interface as Engine for the parity tests."""
 
-    def __init__(self, cfg, world, device=0, options=None):
+    def __init__(self, cfg, world, device=0, options=None, gathered=False):
+        """gathered: hand the logs over in the all-gather layout (torch copies on the one GPU) and replay them with
+        ss_shard_apply_gathered, as DistributedEngine does; default: per-rank device pointers and ss_shard_apply."""
         self.ranks = [ShardRank(cfg, r, world, device, options) for r in range(world)]
         self.world = world
         self.passes = 0
+        self.gathered = gathered
+        self.device = device
 
     def upload_cells(self, sugar, cap, pollution=None):
         self._cells = (sugar, cap, pollution)
@@ -148,7 +181,9 @@ class VirtualRanks:
             while True:
                 logs = [r.run_pass() for r in self.ranks]
                 self.passes += 1
-                for i, r in enumerate(self.ranks):
+                if self.gathered:
+                    self._apply_gathered(logs)
+                for i, r in enumerate(self.ranks if not self.gathered else []):
                     for j, (ptr, n, cptr, cn) in enumerate(logs):
                         if j != i:
                             r.apply(ptr, n, cptr, cn)
@@ -163,6 +198,30 @@ class VirtualRanks:
                 assert s.tobytes() == stats[0].tobytes(), "replicas disagree on the step statistics"
             out[t] = stats[0][0]
         return out
+
+    def _apply_gathered(self, logs):
+        import torch
+        dev = "cuda:%d" % self.device
+        locs = [(torch.as_tensor(_DevView(p, max(n, 1) * ENTRY_BYTES), device=dev), n,
+                 torch.as_tensor(_DevView(cp, max(cn, 1) * COMPACT_BYTES), device=dev), cn) for p, n, cp, cn in logs]
+        counts = torch.tensor([[n, cn] for _, n, _, cn in locs], dtype=torch.int64, device=dev)
+        bufs = []
+
+        def gather_counts(t):
+            return counts.reshape(-1)
+
+        def gather_padded(buf):
+            bufs.append(buf)
+            return None
+        for loc, n, loc2, cn in locs:                       # every "rank" packs its buffer exactly as gather_logs does
+            g = gather_logs(loc, n, loc2, cn, self.world, gather_counts, gather_padded)
+        if g["mx"] == 0 and g["mx2"] == 0:
+            return
+        g["buf"] = torch.stack(bufs)
+        torch.cuda.synchronize()
+        for r in self.ranks:
+            r.apply_gathered(g)
+        torch.cuda.synchronize()
 
     def download_cells(self):
         cells = [r.eng.download_cells() for r in self.ranks]
@@ -223,15 +282,11 @@ class DistributedEngine:
                 dev = "cuda:%d" % self.device
                 local = torch.as_tensor(_DevView(ptr, max(n, 1) * ENTRY_BYTES), device=dev)
                 local2 = torch.as_tensor(_DevView(cptr, max(cn, 1) * COMPACT_BYTES), device=dev)
-                counts, parts, counts2, parts2 = pad_and_gather(local, n, self.world, self._gather_counts,
-                                                                self._gather_padded, local2=local2, n2=cn)
+                g = gather_logs(local, n, local2, cn, self.world, self._gather_counts, self._gather_padded)
                 torch.cuda.current_stream().synchronize()    # NCCL results before the engine's stream reads them
                 t3 = pc(); self.t["gather"] += t3 - t2
                 self.bytes_sent += n * ENTRY_BYTES + cn * COMPACT_BYTES
-                for j in range(self.world):
-                    if j != self.rank and (counts[j] or counts2[j]):
-                        self.r.apply(parts[j].data_ptr() if counts[j] else 0, counts[j],
-                                     parts2[j].data_ptr() if counts2[j] else 0, counts2[j])
+                self.r.apply_gathered(g)                     # every other rank's slices: two launches per log
                 done = self.r.pending() == 0
                 self.t["apply+pending"] += pc() - t3
                 if done:

@@ -310,6 +310,21 @@ def test_multi_gpu_replicas_equal_single_gpu_and_oracle(world, n, pollution, opt
     o.close()
 
 
+@pytest.mark.parametrize("world,n,pollution", [(4, 300, True), (8, 512, False)])
+def test_multi_gpu_gathered_replay(world, n, pollution):
+    """The replay path of the real multi-GPU run: all ranks' log slices in the all-gather layout, replayed by
+    ss_shard_apply_gathered (one launch per log and phase for all other ranks)."""
+    from sugarscape_utilicalc_b200.sharded import VirtualRanks
+    s, init = common.synthetic_case(n, pollution)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    v, o = VirtualRanks(cfg, world, options={"solo_window": 72}, gathered=True), common.oracle_world(cfg)
+    common.init_world(v, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(v, o, 6, what="virtual ranks %d gathered" % world)
+    v.close()
+    o.close()
+
+
 def test_multi_gpu_replicas_utilicalc():
     """The utilicalc rule through the sharded path: every turn travels as a fully settled log entry."""
     from sugarscape_utilicalc_b200.sharded import VirtualRanks
