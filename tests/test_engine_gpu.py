@@ -99,7 +99,12 @@ def test_world_initialisation_fills_the_lattice_and_large_grids():
     s = {**s, "view": {**s["view"], "grid_size": {"x": 1000, "y": 1000}}, "env": {**s["env"], "total_agents": {"blue": 30000, "red": 20000}}}
     cfg = config_from_settings(s, rng_mode="keyed")
     e = common.engine_world(cfg)
-    e.seed_mt19937(2**40 + 5)
+    import random
+    for seed in (0, 18, 2**32 - 1, 2**40 + 5):            # random.seed(int): init_by_array over the 32-bit words
+        e.seed_mt19937(seed)
+        st = random.Random(seed).getstate()[1]
+        mt, idx = e.get_rng_mt19937()
+        assert idx == st[624] and np.array_equal(mt, np.array(st[:624], dtype=np.uint32)), seed
     e.init_world(init_params_from_settings(s))
     ags = e.download_agents()
     assert len(ags["id"]) == 50000 and len(set((ags["x"].astype(np.int64) * 1000 + ags["y"]).tolist())) == 50000

@@ -137,7 +137,7 @@ def test_dropin_event_log_plateau_rule_and_log_file(rng, tmp_path):
     exp_log, exited_at = list(ref.view.log), ref.exited_at
 
     run = rh.ReferenceRun(s, rng="mt")                  # a fresh reference View; the engine side draws its own words
-    h = dropin.install(run.ss, run.view, rng=rng, world_factory=common.oracle_world)
+    h = dropin.install(run.ss, run.view, rng=rng, world_factory=common.oracle_world, gui=(rng == "mt"))
     got_exit = None
     with rh._cwd(run.scratch):
         for _ in range(limit):
