@@ -408,20 +408,40 @@ __device__ static void warp_agent_turn(const DevWorld& w, const Ctx& c, int lx, 
 #define UT_MAXC 64                      // >= 2(2v+1)+1 for v <= 15
 struct UtilShared {
     double util[UT_MAXC], nb_inten[UT_MAXC], nb_metab[UT_MAXC];
-    int32_t food[UT_MAXC], neigh[UT_MAXC], nb_x[UT_MAXC], nb_y[UT_MAXC], nb_v[UT_MAXC];
+    int32_t food[UT_MAXC], neigh[UT_MAXC], nb_x[UT_MAXC], nb_y[UT_MAXC], nb_v[UT_MAXC], fsug[UT_MAXC];
 };
-struct KeyedStream { uint64_t akey; uint32_t j; };
-__device__ static inline uint32_t ks_randbelow(KeyedStream& ks, uint32_t nn) {          // random.py:242
+// The agent's keyed words, 32 at a time (lane l holds word base + l) and handed round by shuffle: every lane sees the
+// same draw, so the whole warp replays CPython's algorithms in step.
+struct KeyedStream { uint64_t akey; uint32_t j, base, batch; };
+__device__ static inline void ks_open(KeyedStream& ks, uint64_t akey, int lane) {
+    ks.akey = akey; ks.j = 0u; ks.base = 0u; ks.batch = ss_keyed_word(akey, (uint32_t)lane);
+}
+__device__ static inline uint32_t ks_word(KeyedStream& ks, int lane) {
+    if (ks.j - ks.base >= 32u) { ks.base += 32u; ks.batch = ss_keyed_word(ks.akey, ks.base + (uint32_t)lane); }
+    return __shfl_sync(FULL, ks.batch, (int)(ks.j++ - ks.base));
+}
+__device__ static inline uint32_t ks_randbelow(KeyedStream& ks, uint32_t nn, int lane) {         // random.py:242
     const int k = 32 - __clz(nn);
-    uint32_t r = ss_keyed_word(ks.akey, ks.j++) >> (32 - k);
-    while (r >= nn) r = ss_keyed_word(ks.akey, ks.j++) >> (32 - k);
+    uint32_t r = ks_word(ks, lane) >> (32 - k);
+    while (r >= nn) r = ks_word(ks, lane) >> (32 - k);
     return r;
 }
-__device__ static inline void ks_shuffle(KeyedStream& ks, int32_t* a, int n) {           // random.py:350
+// random.py:350 shuffle of a[0..n), n <= 64: the draws are sequential, the swaps are not -- every lane follows the
+// positions of its (up to) two elements through the swaps and stores them where they end
+// (p0, p1: where the elements that started at positions lane and lane + 32 are now; several shuffles compose)
+__device__ static inline void ks_shuffle_track(KeyedStream& ks, int n, int lane, int& p0, int& p1) {
     for (int i = n - 1; i >= 1; i--) {
-        const uint32_t j = ks_randbelow(ks, (uint32_t)i + 1u);
-        const int32_t t = a[i]; a[i] = a[j]; a[j] = t;
+        const int j = (int)ks_randbelow(ks, (uint32_t)i + 1u, lane);
+        p0 = p0 == i ? j : (p0 == j ? i : p0);
+        p1 = p1 == i ? j : (p1 == j ? i : p1);
     }
+}
+// the neighbour's share of utilicalcSugar that does not depend on the move (agent.py:870-872, 984): the days its sugar
+// lasts are sugar // metabolism; an integer-valued sugar (everything but the 0.01 floor) takes the integer quotient
+__device__ static inline double util_intensity(double sugar, int metab) {
+    const double days = (sugar >= 0.0 && sugar < 2147483647.0 && sugar == (double)(int)sugar)
+                            ? (double)((int)sugar / metab) : ss_py_floordiv(sugar, (double)metab);
+    return 1.0 / (1.0 + days);
 }
 template <bool WRAP, class Ctx>
 __device__ static void warp_utilicalc_turn(const DevWorld& w, const Ctx& c, UtilShared& us, int lx, int ly, int gx, int gy,
@@ -450,33 +470,51 @@ __device__ static void warp_utilicalc_turn(const DevWorld& w, const Ctx& c, Util
         m += __popc(bf); nb += __popc(bo);
     }
     __syncwarp();
+    // the loads the evaluation will want are issued now and land while the shuffles are replayed: int(sugar) of the
+    // moves, the records of the neighbours, the agent's own record and cell
+    const AgentRec* recp = &w.agents[slot];
+    double own_sugar = 0.0;
+    uint32_t own_attr = 0u;
+    int own_site = 0;
+    if (lane == 0) { own_sugar = __ldcg(&recp->sugar); own_attr = __ldcg(&recp->attr); own_site = (int)__ldcg(&w.isugar[pos]); }
+    const int32_t f0 = lane < m ? us.food[lane] : 0, f1 = lane + 32 < m ? us.food[lane + 32] : 0;
+    const int fs0 = lane < m ? (int)__ldcg(&w.isugar[f0]) : 0, fs1 = lane + 32 < m ? (int)__ldcg(&w.isugar[f1]) : 0;
+    const int32_t s0 = lane < nb ? us.neigh[lane] : 0, s1 = lane + 32 < nb ? us.neigh[lane + 32] : 0;
+    double bs0 = 0.0, bs1 = 0.0;
+    uint32_t ba0 = 0u, ba1 = 0u, bp0 = 0u, bp1 = 0u;
+    if (lane < nb) { const AgentRec* b = &w.agents[s0]; bs0 = __ldcg(&b->sugar); ba0 = __ldcg(&b->attr); bp0 = __ldcg(&b->pos); }
+    if (lane + 32 < nb) { const AgentRec* b = &w.agents[s1]; bs1 = __ldcg(&b->sugar); ba1 = __ldcg(&b->attr); bp1 = __ldcg(&b->pos); }
     KeyedStream ks;
-    ks.akey = ss_agent_key(skey, slot + 1u); ks.j = 0u;
+    ks_open(ks, ss_agent_key(skey, slot + 1u), lane);
+    int p0 = lane, p1 = lane + 32, q0 = lane, q1 = lane + 32;
+    ks_shuffle_track(ks, m, lane, p0, p1);      // getFood's shuffle, agent.py:369
+    ks_shuffle_track(ks, m, lane, p0, p1);      // agent.py:1033
+    ks_shuffle_track(ks, nb, lane, q0, q1);     // agent.py:405
+    __syncwarp();
+    if (lane < m) { us.food[p0] = f0; us.fsug[p0] = fs0; }
+    if (lane + 32 < m) { us.food[p1] = f1; us.fsug[p1] = fs1; }
+    if (lane < nb) {
+        us.neigh[q0] = s0; us.nb_inten[q0] = util_intensity(bs0, attr_metab(ba0)); us.nb_metab[q0] = (double)attr_metab(ba0);
+        us.nb_x[q0] = (int)bp0 / n; us.nb_y[q0] = (int)bp0 % n; us.nb_v[q0] = attr_vision(ba0);
+    }
+    if (lane + 32 < nb) {
+        us.neigh[q1] = s1; us.nb_inten[q1] = util_intensity(bs1, attr_metab(ba1)); us.nb_metab[q1] = (double)attr_metab(ba1);
+        us.nb_x[q1] = (int)bp1 / n; us.nb_y[q1] = (int)bp1 % n; us.nb_v[q1] = attr_vision(ba1);
+    }
     if (lane == 0) {
-        ks_shuffle(ks, us.food, m);           // getFood's shuffle, agent.py:369
-        ks_shuffle(ks, us.food, m);           // agent.py:1033
-        us.food[m] = pos;                     // agent.py:1035
-        ks_shuffle(ks, us.neigh, nb);         // agent.py:405
-        us.neigh[nb] = (int32_t)slot;         // agent.py:1039
+        us.food[m] = pos; us.fsug[m] = own_site;                                    // agent.py:1035
+        us.neigh[nb] = (int32_t)slot;                                               // agent.py:1039
+        us.nb_inten[nb] = util_intensity(own_sugar, attr_metab(own_attr)); us.nb_metab[nb] = (double)attr_metab(own_attr);
+        us.nb_x[nb] = gx; us.nb_y[nb] = gy; us.nb_v[nb] = a;
     }
     m += 1; nb += 1;
-    __syncwarp();
-    for (int q = lane; q < nb; q += 32) {
-        const AgentRec* b = &w.agents[us.neigh[q]];
-        const double bs = __ldcg(&b->sugar);
-        const uint32_t battr = __ldcg(&b->attr), bpos = __ldcg(&b->pos);
-        const double bm = (double)attr_metab(battr);
-        us.nb_inten[q] = 1.0 / (1.0 + ss_py_floordiv(bs, bm));                      // agent.py:870-872, 984
-        us.nb_metab[q] = bm;
-        us.nb_x[q] = (int)bpos / n; us.nb_y[q] = (int)bpos % n; us.nb_v[q] = attr_vision(battr);
-    }
     __syncwarp();
     const double extent = (double)(nb - 1);
     double lmax = 0.0;
     bool have = false;
     for (int p = lane; p < m; p += 32) {
         const int cell = us.food[p], mx = cell / n, my = cell % n;
-        const double site = (double)(int)__ldcg(&w.isugar[cell]);
+        const double site = (double)us.fsug[p];
         double u = 0.0;
         for (int q = 0; q < nb; q++) {
             const double dur = (site / us.nb_metab[q]) / w.cfg.max_capacity;
@@ -497,14 +535,16 @@ __device__ static void warp_utilicalc_turn(const DevWorld& w, const Ctx& c, Util
         if (oh && (!have || om > lmax)) { lmax = om; have = true; }
     }
     __syncwarp();
+    // max_locations in move-list order (agent.py:1105-1107): the maxima among moves 0..31 and 32..63 as two ballots
+    const unsigned b0 = __ballot_sync(FULL, lane < m && us.util[lane] == lmax);
+    const unsigned b1 = __ballot_sync(FULL, lane + 32 < m && us.util[min(lane + 32, UT_MAXC - 1)] == lmax);
+    const int n0 = __popc(b0), nmax = n0 + __popc(b1);
+    const int pick = (int)ks_randbelow(ks, (uint32_t)nmax, lane);                   // random.choice, agent.py:1108
+    const int pmove = pick < n0 ? (int)__fns(b0, 0u, pick + 1) : 32 + (int)__fns(b1, 0u, pick - n0 + 1);
     if (lane == 0) {
-        int nmax = 0;
-        for (int p = 0; p < m; p++)
-            if (us.util[p] == lmax) us.neigh[nmax++] = us.food[p];                  // neigh[] reused as max_locations
-        const int dest = us.neigh[ks_randbelow(ks, (uint32_t)nmax)];                // random.choice, agent.py:1108
-        const int sg = (int)__ldcg(&w.isugar[dest]);                                // agent.py:1128-1130
-        const AgentRec* recp = &w.agents[slot];
-        commit_turn(w, c, lx, ly, lx, ly, pos, dest, sg, a, true, slot, recp->sugar, recp->attr, iteration, env_time, next_phase,
+        const int dest = us.food[pmove];
+        const int sg = us.fsug[pmove];                                              // agent.py:1128-1130
+        commit_turn(w, c, lx, ly, lx, ly, pos, dest, sg, a, true, slot, own_sugar, own_attr, iteration, env_time, next_phase,
                     ts, (ow & OCC_RISK) != 0u);
     }
     __syncwarp();
