@@ -534,6 +534,7 @@ static void pass_geometry(ss_engine* e, int p, PassGeom* out) {
     }
     g.bx_lo = 0; g.bx_cnt = g.nwin;
     g.map_read = g.map_write = -1;
+    g.ring_per_agent = e->w.log != nullptr;
     *out = g;
 }
 

@@ -1175,7 +1175,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
     const int nb = w.pend_nb;
     if (g.map_read >= 0) {          // coarse pending map: nothing left in this window's core -> hand the entries on
         const uint32_t* mr = w.pendmap + (size_t)g.map_read * nb * nb;
-        const int Rm = V + 1;           // core of the smallest vision
+        const int Rm = g.ring_per_agent ? V + 1 : R;    // core of the smallest vision
         const int cx0 = (c.gx0 + Rm) >> 5, cx1 = (c.gx0 + c.ex - Rm - 1) >> 5;
         const int cy0 = (c.gy0 + Rm) >> 5, cy1 = (c.gy0 + c.ey - Rm - 1) >> 5;
         const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
@@ -1248,7 +1248,7 @@ __device__ __forceinline__ void solo_window(const DevWorld& w, const PassGeom& g
             m &= m - 1;
             const uint32_t ow = j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w;
             const int ly = ly0 + j;
-            const int Ra = (int)((ow >> 24) & 31u) + V;
+            const int Ra = g.ring_per_agent ? (int)((ow >> 24) & 31u) + V : R;
             if (!(lx >= Ra && lx < c.ex - Ra && ly >= Ra && ly < c.ey - Ra)) { ringbits |= 1u << (ly & 31); continue; }
             uint32_t key = ow;                                      // first scan: hashed below
             if (!first) {

@@ -70,4 +70,6 @@ struct PassGeom {                   // window tiling of one move pass
     int align;                      // window boundaries are multiples of this many cells (4: vector loads)
     int bx_lo, bx_cnt;              // window rows [bx_lo, bx_lo + bx_cnt) of this launch (multi-GPU: this rank's share)
     int map_read, map_write;        // coarse pending maps (32x32-cell blocks) of the previous / this launch, -1 = unused
+    int ring_per_agent;             // warp-per-window scan: ring = vision + vmax per agent instead of 2 vmax for all (fewer passes,
+                                    // a longer first pass: pays when every pass costs an exchange, i.e. in the sharded path)
 };
