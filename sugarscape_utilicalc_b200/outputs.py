@@ -81,21 +81,18 @@ def death_event(agent_id):
 
 
 def update_data_file(filename, data):
-    """Column-append of `data` to `filename`, one value per line (sugarscape.py:688-709)."""
-    try:
+    """Column-append of `data` to `filename` (sugarscape.py:688-709): value k goes to the end of line k, separated
+    by ", " from what the line already holds; lines beyond len(data) are kept as they are."""
+    rows = []
+    if os.path.exists(filename):
         with open(filename, "r") as f:
-            lines = f.readlines()
-    except FileNotFoundError:
-        lines = []
-    if len(lines) < len(data):
-        lines.extend([""] * (len(data) - len(lines)))
-    for i, value in enumerate(data):
-        if lines[i].strip():
-            lines[i] = lines[i].strip() + ", " + str(value) + "\n"
-        else:
-            lines[i] = str(value) + "\n"
+            rows = f.readlines()
+    rows += [""] * max(0, len(data) - len(rows))
+    for k, value in enumerate(data):
+        held = rows[k].strip()
+        rows[k] = (held + ", " if held else "") + str(value) + "\n"
     with open(filename, "w") as f:
-        f.writelines(lines)
+        f.writelines(rows)
 
 
 def ending_stats(iteration, population, metabolism_mean, vision_mean, gini, agent_wealth):
