@@ -153,6 +153,19 @@ def test_priority_is_a_keyed_bijection(n_slots):
     assert [kr.priority(rk2, half, s) for s in range(min(m, 64))] != pr[:min(m, 64)] or m < 4
 
 
+@pytest.mark.parametrize("n_slots", [1, 7, 300, 4097, 16777216])
+def test_host_side_keyed_priorities_equal_the_keyed_rng_definition(n_slots):
+    """outputs.keyed_priorities (numpy; orders a step's death events in keyed runs) against oracle/keyed_rng.py."""
+    from sugarscape_utilicalc_b200 import outputs
+    rng = np.random.default_rng(n_slots)
+    ids = np.unique(rng.integers(1, n_slots + 1, size=min(n_slots, 500)))
+    for seed, t in ((18, 0), (18, 41), (2**40 + 3, 7)):
+        skey = kr.step_key(seed, t)
+        rk, half = kr.round_keys(skey), kr.order_half_bits(n_slots)
+        exp = [kr.priority(rk, half, int(i) - 1) for i in ids]
+        assert outputs.keyed_priorities(seed, t, ids, n_slots).tolist() == exp
+
+
 def test_keyed_stream_uses_cpython_randbelow_and_shuffle():
     import random
 

@@ -56,6 +56,13 @@ def _worker(rank, world, port, q):
                 exp2 = np.random.default_rng(7000 + 100 * rnd + r).integers(
                     0, 256, size=max(lens2[r], 1) * sharded.COMPACT_BYTES, dtype=np.uint8)[: lens2[r] * sharded.COMPACT_BYTES]
                 ok &= np.array_equal(p2[r].numpy(), exp2) and np.array_equal(p1[r].numpy(), parts[r].numpy())
+            # the raw layout ss_shard_apply_gathered consumes: slice r at buf[r], compact entries at off2, counts (world, 2)
+            g = sharded.gather_logs(payload, n, pay2, n2, world, gather_counts, gather_padded)
+            ok &= g["counts_dev"].tolist() == [[lens[r], lens2[r]] for r in range(world)]
+            ok &= g["mx"] == max(lens) and g["mx2"] == max(lens2) and g["off2"] % 16 == 0 and g["buf"].shape == (world, g["stride"])
+            for r in range(world):
+                ok &= np.array_equal(g["buf"][r, : lens[r] * sharded.ENTRY_BYTES].numpy(), p1[r].numpy())
+                ok &= np.array_equal(g["buf"][r, g["off2"]: g["off2"] + lens2[r] * sharded.COMPACT_BYTES].numpy(), p2[r].numpy())
             # termination: every rank derives the same pending count from the gathered lengths
             pend = torch.tensor([100 - sum(counts)])
             dist.all_reduce(pend, op=dist.ReduceOp.MAX)
