@@ -1,0 +1,42 @@
+"""Checkpoint / resume of a run (the reference never serialises its state; a long engine run
+should be able to).  One `.npz` holds everything a step depends on: the settings.json dict, the RNG mode and stream
+position (the 624 MT19937 words + index, or the keyed seed), `View.iteration` / `Environment.time`, the three cell
+arrays and the agents in list order.  `restore` builds a fresh world from it; continuing there is bit-identical to
+never having stopped (tests/test_engine_gpu.py::test_checkpoint_resume, tests/test_oracle_golden.py on the CPU oracle).
+"""
+import json
+
+import numpy as np
+
+from .settings import config_from_settings
+
+
+def save(path, world, settings, rng, iteration, keyed_seed=None):
+    """world: Engine (or anything with its interface); iteration: timesteps taken since iteration 0 (= env time)."""
+    cells, ags = world.download_cells(), world.download_agents()
+    out = dict(settings_json=np.array(json.dumps(settings)), rng=np.array(rng), iteration=np.int64(iteration),
+               keyed_seed=np.int64(-1 if keyed_seed is None else keyed_seed),
+               sugar=cells["sugar"], cap=cells["cap"], pollution=cells["pollution"],
+               **{"agent_" + k: ags[k] for k in ("id", "x", "y", "vision", "metab", "sugar")})
+    if rng == "mt":
+        mt, idx = world.get_rng_mt19937()
+        out["mt"], out["mt_index"] = np.asarray(mt, dtype=np.uint32), np.int64(idx)
+    np.savez_compressed(path, **out)
+
+
+def restore(path, world_factory=None, **factory_kwargs):
+    """-> (world, settings, rng, iteration).  world_factory(cfg, **factory_kwargs) builds the backend (default: Engine)."""
+    z = np.load(path, allow_pickle=False)
+    settings, rng, iteration = json.loads(str(z["settings_json"])), str(z["rng"]), int(z["iteration"])
+    keyed_seed = int(z["keyed_seed"])
+    cfg = config_from_settings(settings, rng_mode=rng, keyed_seed=None if keyed_seed < 0 else keyed_seed,
+                               iteration=iteration, env_time=iteration)
+    if world_factory is None:
+        from .engine import Engine
+        world_factory = Engine
+    world = world_factory(cfg, **factory_kwargs)
+    world.upload_cells(z["sugar"], z["cap"], z["pollution"])
+    world.upload_agents(z["agent_id"], z["agent_x"], z["agent_y"], z["agent_vision"], z["agent_metab"], z["agent_sugar"])
+    if rng == "mt":
+        world.set_rng_mt19937(z["mt"], int(z["mt_index"]))
+    return world, settings, rng, iteration

@@ -189,3 +189,32 @@ def check_outputs_against_golden(name, kind, tmp_dir, path=-1):
                                  rec.gini, stats, rec.log)
     assert text == exp["log_file_text"]
     w.close()
+
+
+def check_checkpoint_resume(name, kind, tmp_dir, stop=7, total=15):
+    import numpy as np
+    from sugarscape_utilicalc_b200 import checkpoint
+    g = load_golden(name)
+    a = world_from_golden(g, kind)
+    sa = a.step(total)
+    b = world_from_golden(g, kind)
+    sb1 = b.step(stop)
+    path = os.path.join(str(tmp_dir), "ck.npz")
+    checkpoint.save(path, b, g["settings"], g["rng"], stop)
+    b.close()
+    factory = oracle_world if kind == "oracle" else None
+    c, settings, rng, it = checkpoint.restore(path, world_factory=factory)
+    assert (settings, rng, it) == (g["settings"], g["rng"], stop)
+    sc = c.step(total - stop)
+    for f in ("population", "metabolism_mean", "vision_mean", "gini", "acted", "deaths"):
+        assert np.array_equal(np.concatenate([sb1[f], sc[f]]), sa[f]), f
+    ca, cc, ga, gc = a.download_cells(), c.download_cells(), a.download_agents(), c.download_agents()
+    for k in ("sugar", "cap", "pollution", "occ"):
+        assert np.array_equal(ca[k], cc[k]), k
+    for k in ("id", "x", "y", "vision", "metab", "sugar"):
+        assert np.array_equal(ga[k], gc[k]), k
+    if g["rng"] == "mt":
+        ma, mc = a.get_rng_mt19937(), c.get_rng_mt19937()
+        assert ma[1] == mc[1] and np.array_equal(ma[0], mc[0])
+    a.close()
+    c.close()

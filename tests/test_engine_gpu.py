@@ -114,6 +114,12 @@ def test_world_initialisation_fills_the_lattice_and_large_grids():
     e.close()
 
 
+@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "c4_synth130_nopoll_keyed"])
+def test_checkpoint_resume(name, tmp_path):
+    """checkpoint.save / restore over the engine: stop at step 7, resume from the file in a fresh engine, same end state."""
+    common.check_checkpoint_resume(name, "engine", tmp_path, total=min(15, common.load_golden(name)["steps"]))
+
+
 def test_mt_exact_single_steps_equal_fused_steps():
     g = common.load_golden("c2_pollution_mt")
     w = common.world_from_golden(g, "engine")
