@@ -158,7 +158,8 @@ void  ss_host_free(void* p);
 
 /* Instrumentation.  counters: [0] kernel launches since create, [1] move passes,
  * [2] steps, [3] path (0 serial fused, 1 serial + lattice env kernels, 2 lattice),
- * [4] host syncs, [5] window extent | move-pass implementation << 16 (0 = CTA per window, 1 = warp per window). */
+ * [4] host syncs, [5] window extent | move-pass implementation << 16 (0 = CTA per window, 1 = warp per window, 2 = warp per window with a lane
+ * per agent); [6] watchdog firings and [10] internal faults of the lattice kernels (both must stay 0). */
 int  ss_get_counters(ss_engine* e, int64_t* out, int32_t n);
 /* accumulated device milliseconds per kernel class (needs option "profile"=1):
  * [0] prepare, [1] move passes, [2] stats, [3] grow/seasons, [4] diffusion, [5] serial;
