@@ -14,7 +14,15 @@
 extern "C" {
 cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
                              int stats_base, cudaStream_t stream);
-cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s);
+cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1, cudaStream_t s);
+size_t ss_dr_build_smem(int vmax);
+int ss_dr_mask_words(int vmax);
+cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s);
+cudaError_t ss_dr_encode_tmap(const DevWorld& w, void* tmap_storage, int* ok);
+cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void* tmap_storage, int use_tma, cudaStream_t s);
+cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t env_time, int sm_count, int single_round,
+                                unsigned seg_begin, unsigned seg_end, cudaStream_t s);
+cudaError_t ss_launch_dr_check(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D, double max_capacity,
                                  int grow, int sm_count, cudaStream_t stream);
@@ -41,7 +49,7 @@ cudaError_t ss_launch_apply_clog(const DevWorld& w, const void* entries, unsigne
 cudaError_t ss_launch_apply_gathered(const DevWorld& w, const void* base, unsigned long long stride, unsigned long long off_compact,
                                      const long long* counts, int world, int skip_rank, unsigned long long max_full,
                                      unsigned long long max_compact, int phase, int64_t iteration, cudaStream_t s);
-cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s);
+cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, int dr_mirror, cudaStream_t s);
 size_t ss_diffuse_handoff_bytes(int n);
 cudaError_t ss_launch_diffuse(const DevWorld& w, int* ticket_progress, double* handoff, int impl, cudaStream_t s);
 }
@@ -62,7 +70,14 @@ struct ss_engine {
     int ntile = 1, emin = 0;
     // move-pass implementation: 0 = one CTA per window, a warp per region (ss_move_pass_kernel);
     // 1 = one warp per window (ss_move_solo_kernel); -1 = by window count
+    // 3 = dependency rounds over the whole lattice (ss_rounds.cu: ss_dr_build_kernel + ss_dr_rounds_kernel)
     int pass_impl_option = -1, pass_impl = 0;
+    uint32_t dr_slots = 0;                     // allocation sizes of the dependency-round state
+    int dr_mwords = 0;
+    int mirror = 0;                            // which int(sugar) mirror is current: 1 = isugar (window passes), 2 = mw (rounds)
+    bool cap_fits_u7 = true;
+    int use_tma = 1, tma_ok = 0;
+    alignas(64) unsigned char tmap[128];
     int solo_window_max = 0;                   // 0 = by lattice size
     int shard_rank = 0, shard_world = 1;       // multi-GPU replicas (sharded.py)
     int shard_pass = 0;
@@ -168,6 +183,7 @@ extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) 
     return SS_OK;
 }
 
+static void dr_free(ss_engine* e);
 extern "C" void ss_destroy(ss_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
@@ -177,6 +193,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
     cudaFree(e->w.pendmap);
     cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
+    dr_free(e);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -187,6 +204,7 @@ extern "C" void ss_destroy(ss_engine* e) {
 }
 
 static int choose_path(ss_engine* e);
+static int dr_alloc(ss_engine* e);
 static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, double* d_f64, int* d_chk);
 
 // the cell arrays are in place on the device: derive what the kernels keep beside them
@@ -197,7 +215,9 @@ static int finish_cells(ss_engine* e) {
         CK(ss_launch_isugar(e->w, e->d_flags, e->stream));
         CK(cudaMemcpyAsync(&flag, e->d_flags, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
-        e->cap_fits_u8 = flag == 0;
+        e->cap_fits_u8 = (flag & 1) == 0;
+        e->cap_fits_u7 = flag == 0;
+        e->mirror = 1;
     }
     e->have_cells = true;
     if (e->have_agents) return choose_path(e);
@@ -282,6 +302,11 @@ static int choose_path(ss_engine* e) {
         } else if (want_solo && solo_ok) { g = gs; ntile = ntile_s; emin = emin_s; impl = e->pass_impl_option >= 1 ? e->pass_impl_option : SS_DEFAULT_SOLO_IMPL; }
         else if (!cta_ok) lattice_ok = false;
     }
+    // dependency rounds over the whole lattice: rule M with the keyed order, any lattice the conflict zone fits on
+    const bool dr_ok = e->cfg.rng_mode == SS_RNG_KEYED && e->cfg.rule_move_eat && V <= 15 && 4 * V + 1 <= n && e->cap_fits_u7 &&
+                       e->w.n_slots <= SS_MAX_SLOTS && e->shard_world == 1;
+    if (dr_ok && (e->pass_impl_option == 3 || e->pass_impl_option < 0)) { lattice_ok = true; impl = 3; }
+    else if (e->pass_impl_option == 3) lattice_ok = false;
     int path;
     if (e->path_option == PATH_LATTICE) {
         if (!lattice_ok)
@@ -298,6 +323,7 @@ static int choose_path(ss_engine* e) {
     e->geom = g;
     e->ntile = ntile; e->emin = emin; e->pass_impl = impl;
     e->path = path;
+    if (path == PATH_LATTICE && impl == 3) { const int rc = dr_alloc(e); if (rc) return rc; }
     if (path == PATH_LATTICE && g.nwin > 1 && n % 32 == 0 && !e->w.pendmap) {
         e->w.pend_nb = n / 32;
         if (cudaMalloc(&e->w.pendmap, sizeof(uint32_t) * 2 * (size_t)e->w.pend_nb * e->w.pend_nb) != cudaSuccess) e->w.pendmap = nullptr;
@@ -375,6 +401,7 @@ static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, dou
         if (err == 1) return set_err(e, SS_ERR_ARG, "duplicate agent id");
         if (err == 2) return set_err(e, SS_ERR_ARG, "two agents on one cell");
     }
+    if (e->mirror == 2) e->mirror = 0;          // occupancy changed: the cell-word mirror is rebuilt at the next step
     e->w.n_slots = ns;
     e->w.half = ss_order_half_bits(ns);
     e->w.vmax = vmax;
@@ -505,10 +532,56 @@ static int ensure_stats(ss_engine* e, int nsteps) {
     return SS_OK;
 }
 
+static void dr_free(ss_engine* e) {
+    DrState& d = e->w.dr;
+    cudaFree(d.self.mw); cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.self.ctl);
+    cudaFree(d.mask); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
+    memset(&d, 0, sizeof d);
+    e->dr_slots = 0; e->dr_mwords = 0;
+}
+
+// device state of the dependency rounds (ss_world.cuh DrState), sized by the lattice, the slots and the largest vision
+static int dr_alloc(ss_engine* e) {
+    DrState& d = e->w.dr;
+    const uint32_t ns = std::max<uint32_t>(e->w.n_slots, 1u);
+    const int mwords = ss_dr_mask_words(e->w.vmax);
+    if (!d.self.mw) {
+        CK(cudaMalloc(&d.self.mw, e->cells + 16));
+        CK(cudaMalloc(&d.self.dep, (e->cells / 2 + 2) * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.self.ctl, DR_CTL_WORDS * sizeof(unsigned int)));
+        CK(cudaMemsetAsync(d.self.dep, 0, (e->cells / 2 + 2) * sizeof(uint32_t), e->stream));
+        CK(cudaMemsetAsync(d.self.ctl, 0, DR_CTL_WORDS * sizeof(unsigned int), e->stream));
+    }
+    if (ns != e->dr_slots || mwords != e->dr_mwords) {
+        cudaFree(d.self.queue); cudaFree(d.mask); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
+        d.self.queue = nullptr; d.mask = nullptr; d.alive = nullptr; d.atrisk = nullptr; d.q1wait = nullptr;
+        const size_t words = (size_t)(ns + 31) / 32 + 1;
+        CK(cudaMalloc(&d.self.queue, sizeof(uint32_t) * ((size_t)ns + 64)));
+        CK(cudaMalloc(&d.mask, sizeof(unsigned long long) * (size_t)ns * mwords));
+        CK(cudaMalloc(&d.alive, sizeof(uint32_t) * words));
+        CK(cudaMalloc(&d.atrisk, sizeof(uint32_t) * words));
+        CK(cudaMalloc(&d.q1wait, sizeof(uint2) * (size_t)ns));
+        CK(cudaMemsetAsync(d.alive, 0, sizeof(uint32_t) * words, e->stream));
+        CK(cudaMemsetAsync(d.atrisk, 0, sizeof(uint32_t) * words, e->stream));
+        CK(cudaMemsetAsync(d.q1wait, 0, sizeof(uint2) * (size_t)ns, e->stream));
+        e->dr_slots = ns; e->dr_mwords = mwords;
+        if (e->mirror == 2) e->mirror = 0;
+    }
+    d.mwords = mwords;
+    d.queue_cap = ns;
+    d.self.occw = e->w.occw; d.self.sugar = e->w.sugar; d.self.poll = e->w.poll;
+    d.self.x0 = 0; d.self.rows = e->w.n;
+    d.lo = d.self; d.hi = d.self;
+    e->tma_ok = 0;
+    if (e->use_tma) CK(ss_dr_encode_tmap(e->w, e->tmap, &e->tma_ok));
+    return SS_OK;
+}
+
 static int env_phase(ss_engine* e) {
     {
         KTimer t(e, KT_GROW);
-        if (e->cfg.rule_grow) { CK(ss_launch_grow(e->w, e->iteration, e->sm_count, e->stream)); e->launches++; }
+        // the growback refreshes the int(sugar) mirror that is current (cell words of the rounds / isugar bytes)
+        if (e->cfg.rule_grow) { CK(ss_launch_grow(e->w, e->iteration, e->sm_count, e->mirror == 2, e->stream)); e->launches++; }
     }
     if (e->cfg.rule_pollution && e->iteration >= e->cfg.diffusion_start_time &&
         e->iteration % e->cfg.diffusion_rate == 0) {                                  // sugarscape.py:661-663
@@ -538,11 +611,50 @@ static void pass_geometry(ss_engine* e, int p, PassGeom* out) {
     *out = g;
 }
 
-static int lattice_step(ss_engine* e, int stats_index) {
+// one timestep as dependency rounds over the whole lattice: no window passes, no host round trips
+static int dr_step(ss_engine* e, int stats_index) {
+    if (e->mirror != 2) {           // after an upload or a change of path: cell words, alive / at-risk bitmaps, OCC_RISK flags
+        int flag = 0;
+        CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
+        CK(ss_launch_dr_mirror(e->w, e->d_flags, e->stream));
+        CK(cudaMemcpyAsync(&flag, e->d_flags, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->launches += 2; e->syncs++;
+        if (flag) return set_err(e, SS_ERR_UNSUPPORTED, "dependency rounds need cell sugar and capacities < 127");
+        e->mirror = 2;
+    }
     {
         KTimer t(e, KT_PREPARE);
         CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
-        CK(ss_launch_prepare(e->w, e->iteration, e->stream));
+        CK(ss_launch_prepare(e->w, e->iteration, 0, e->stream));
+        CK(ss_launch_dr_build(e->w, e->iteration, e->tmap, e->tma_ok && e->use_tma, e->stream));
+        e->launches += 4;
+    }
+    {
+        KTimer t(e, KT_MOVE);
+        CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
+        CK(ss_launch_dr_check(e->w, e->stream));
+        e->launches += 2; e->passes++;
+    }
+    {
+        KTimer t(e, KT_STATS);
+        CK(ss_launch_stats(e->w, stats_index, e->stream));
+        e->launches++;
+    }
+    return env_phase(e);
+}
+
+static int lattice_step(ss_engine* e, int stats_index) {
+    if (e->pass_impl == 3) return dr_step(e, stats_index);
+    if (e->mirror != 1) {           // the window passes read the isugar byte mirror
+        CK(ss_launch_isugar(e->w, e->d_flags, e->stream));
+        e->launches++;
+        e->mirror = 1;
+    }
+    {
+        KTimer t(e, KT_PREPARE);
+        CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
+        CK(ss_launch_prepare(e->w, e->iteration, 1, e->stream));
         e->launches += e->cfg.rule_can_starve ? 2 : 1;
     }
     {
@@ -818,6 +930,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "trace") { e->trace = (int)value; return SS_OK; }
     if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "solo_window") { e->solo_window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
+    if (k == "tma") { e->use_tma = (int)value; return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }
@@ -857,7 +970,7 @@ extern "C" int ss_shard_begin_step(ss_engine* e) {
     CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
     CK(cudaMemsetAsync(e->w.log_count, 0, sizeof(unsigned long long), e->stream));
     CK(cudaMemsetAsync(e->w.clog_count, 0, sizeof(unsigned long long), e->stream));
-    CK(ss_launch_prepare(e->w, e->iteration, e->stream));
+    CK(ss_launch_prepare(e->w, e->iteration, 1, e->stream));
     e->launches += e->cfg.rule_can_starve ? 2 : 1;
     e->shard_pass = 0;
     int rc = ensure_stats(e, 1);

@@ -1885,7 +1885,7 @@ __device__ static inline double grow1(double s, double alpha, double c) { const 
 
 __global__ void __launch_bounds__(256)
 ss_grow_kernel(double* __restrict__ sugar, const double* __restrict__ cap, uint8_t* __restrict__ isugar, double alpha,
-               size_t cells) {
+               size_t cells, int keep_bit7) {
     const size_t nquad = cells / 4;
     double2* s2 = reinterpret_cast<double2*>(sugar);
     const double2* c2 = reinterpret_cast<const double2*>(cap);
@@ -1897,20 +1897,24 @@ ss_grow_kernel(double* __restrict__ sugar, const double* __restrict__ cap, uint8
         a.x = grow1(a.x, alpha, ca.x); a.y = grow1(a.y, alpha, ca.y);
         b.x = grow1(b.x, alpha, cb.x); b.y = grow1(b.y, alpha, cb.y);
         s2[2 * i] = a; s2[2 * i + 1] = b;
-        if (isugar) i4[i] = make_uchar4((unsigned char)(int)a.x, (unsigned char)(int)a.y, (unsigned char)(int)b.x,
-                                        (unsigned char)(int)b.y);
+        if (isugar) {
+            uchar4 o = make_uchar4(0, 0, 0, 0);
+            if (keep_bit7) { o = i4[i]; o.x &= 0x80; o.y &= 0x80; o.z &= 0x80; o.w &= 0x80; }      // occupied bit of the cell words
+            i4[i] = make_uchar4(o.x | (unsigned char)(int)a.x, o.y | (unsigned char)(int)a.y, o.z | (unsigned char)(int)b.x,
+                                o.w | (unsigned char)(int)b.y);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (cells & 3)) {
         const size_t c = nquad * 4 + threadIdx.x;
         const double v = grow1(sugar[c], alpha, cap[c]);
         sugar[c] = v;
-        if (isugar) isugar[c] = (unsigned char)(int)v;
+        if (isugar) isugar[c] = (unsigned char)((keep_bit7 ? (isugar[c] & 0x80) : 0) | (unsigned char)(int)v);
     }
 }
 
 // sugarscape.py:642-655 + environment.py:146-155: two inclusive rectangles, north first
 __global__ void __launch_bounds__(256)
-ss_seasons_kernel(DevWorld w, double alpha_north, double alpha_south) {
+ss_seasons_kernel(DevWorld w, double alpha_north, double alpha_south, uint8_t* mirror, int keep_bit7) {
     const int n = w.n;
     const size_t cells = (size_t)n * n;
     const int32_t* rn = w.cfg.season_north;
@@ -1927,7 +1931,7 @@ ss_seasons_kernel(DevWorld w, double alpha_north, double alpha_south) {
         if (in_n) s = grow1(s, alpha_north, cp);
         if (in_s) s = grow1(s, alpha_south, cp);
         w.sugar[c] = s;
-        if (w.isugar) w.isugar[c] = (unsigned char)(int)s;
+        if (mirror) mirror[c] = (unsigned char)((keep_bit7 ? (mirror[c] & 0x80) : 0) | (unsigned char)(int)s);
     }
 }
 
@@ -2355,8 +2359,9 @@ __global__ void ss_isugar_kernel(const double* __restrict__ sugar, const double*
                                  size_t cells, int* flag) {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
         const double v = sugar[c];
-        if (!(v >= 0.0 && v < 256.0) || !(cap[c] < 256.0)) { *flag = 1; isugar[c] = 0; }
+        if (!(v >= 0.0 && v < 256.0) || !(cap[c] < 256.0)) { atomicOr(flag, 1); isugar[c] = 0; }
         else isugar[c] = (uint8_t)(int)v;
+        if (!(v < 127.0) || !(cap[c] < 127.0)) atomicOr(flag, 2);      // the one-byte cell words of ss_rounds.cu hold 7 bits
     }
 }
 // agent store + occupancy words from the uploaded View.agents arrays; err: 1 duplicate id, 2 two agents on a cell
@@ -2533,9 +2538,9 @@ cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, cudaStream_t s) {
+cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1, cudaStream_t s) {
     ss_begin_step_kernel<<<1, 1, 0, s>>>(w);
-    if (w.cfg.rule_can_starve && w.n_slots > 0)
+    if (stamp_q1 && w.cfg.rule_can_starve && w.n_slots > 0)
         ss_prepare_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w, iteration);
     return cudaGetLastError();
 }
@@ -2624,8 +2629,9 @@ cudaError_t ss_launch_stats(const DevWorld& w, int stats_index, cudaStream_t s) 
     return cudaGetLastError();
 }
 
-cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, cudaStream_t s) {
+cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, int dr_mirror, cudaStream_t s) {
     const size_t cells = (size_t)w.n * w.n;
+    uint8_t* mirror = dr_mirror ? w.dr.self.mw : w.isugar;
     if (w.cfg.rule_seasons) {
         if (!w.cfg.rule_grow) return cudaSuccess;
         const bool summer = (iteration % (2 * (int64_t)w.cfg.season_period)) < w.cfg.season_period;
@@ -2633,12 +2639,12 @@ cudaError_t ss_launch_grow(const DevWorld& w, int64_t iteration, int sm_count, c
         const double as = summer ? w.cfg.season_off_factor : w.cfg.season_on_factor;
         size_t blocks = (cells + 255) / 256;
         if (blocks > (size_t)sm_count * 16) blocks = (size_t)sm_count * 16;
-        ss_seasons_kernel<<<(unsigned)blocks, 256, 0, s>>>(w, an, as);
+        ss_seasons_kernel<<<(unsigned)blocks, 256, 0, s>>>(w, an, as, mirror, dr_mirror);
     } else if (w.cfg.rule_grow) {
         size_t blocks = (cells / 4 + 255) / 256;
         if (blocks > (size_t)sm_count * 16) blocks = (size_t)sm_count * 16;
         if (blocks < 1) blocks = 1;
-        ss_grow_kernel<<<(unsigned)blocks, 256, 0, s>>>(w.sugar, w.cap, w.isugar, w.cfg.grow_factor, cells);
+        ss_grow_kernel<<<(unsigned)blocks, 256, 0, s>>>(w.sugar, w.cap, mirror, w.cfg.grow_factor, cells, dr_mirror);
     }
     return cudaGetLastError();
 }

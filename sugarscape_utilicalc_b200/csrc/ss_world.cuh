@@ -27,6 +27,34 @@ struct ShardLogEntry {
     uint32_t kind_harvest;          // bits 0..7 kind (0 safe, 1 at-risk, 2 skipped), bits 8.. harvest
 };
 
+// Dependency rounds over the whole lattice (ss_rounds.cu): per-step dependency state.
+//   mw[c]     u8   bit 7 = cell occupied, bits 0..6 = int(sugar[c]) -- the one byte an agent reads per cross cell
+//   dep[c]    u16  (two per u32 word) bits 0..14 = unresolved predecessors of the agent that STARTED the step on c,
+//                  bit 15 = "lose the turn" (Q1: the predecessor in the list order died)
+//   mask[s]   mwords x u64 per slot: successors of agent s as a bitmap over its conflict zone (start-of-step positions)
+//   queue     cells in the order their agents became ready; round k is the segment appended during round k-1
+//   alive / atrisk  bitmaps by slot (list-order predecessor lookup for Q1); q1wait[s] = {cell waiting for s's outcome, step+1}
+struct DrPeer {                     // one strip of lattice rows [x0, x0 + rows) and its per-step state, as a kernel sees it
+    uint32_t* occw;                 // (local or peer-mapped device pointers; index (x - x0) * n + y)
+    uint8_t* mw;
+    double* sugar;
+    double* poll;
+    uint32_t* dep;
+    uint32_t* queue;
+    unsigned int* ctl;              // [0] queue tail, [1] barrier count, [2] barrier generation, [3] round, [4] remote flag, ...
+    int x0, rows;
+};
+#define DR_CTL_WORDS 64
+struct DrState {
+    DrPeer self, lo, hi;            // this strip and its ring neighbours (single strip: lo = hi = self)
+    unsigned long long* mask;
+    uint32_t* alive;
+    uint32_t* atrisk;
+    uint2* q1wait;
+    int mwords;
+    uint32_t queue_cap;
+};
+
 struct DevWorld {
     ss_config cfg;
     int n;                          // lattice edge N
@@ -59,6 +87,7 @@ struct DevWorld {
     uint2* clog;                    // ... and the turns of safe agents, 8 bytes each: x = slot | harvest << 24, y = new cell
     unsigned long long* clog_count; //     (old cell, occupancy word and turn stamp follow from the replica's own record)
     unsigned long long clog_cap;
+    DrState dr;                     // dependency rounds (ss_rounds.cu)
 };
 
 struct PassGeom {                   // window tiling of one move pass
