@@ -38,6 +38,7 @@ static_assert(sizeof(AgentRec) == 32, "AgentRec must be one 32-byte sector");
 enum { ST_ACTED = 1, ST_DIED = 2, ST_SKIPPED = 3 };
 
 #define ATTR_ALIVE 0x80000000u
+#define ATTR_RISK  0x40000000u         // dependency rounds: the agent may starve in its next turn (Q1 edge to its successor)
 __host__ __device__ inline uint32_t attr_pack(int vision, int metab, bool alive) {
     return (uint32_t)vision | ((uint32_t)metab << 8) | (alive ? ATTR_ALIVE : 0u);
 }

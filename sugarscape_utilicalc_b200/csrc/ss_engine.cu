@@ -16,7 +16,7 @@ cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_t
                              int stats_base, cudaStream_t stream);
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1, cudaStream_t s);
 size_t ss_dr_build_smem(int vmax);
-int ss_dr_mask_words(int vmax);
+cudaError_t ss_launch_dr_transpose(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_dr_encode_tmap(const DevWorld& w, void* tmap_storage, int* ok);
 cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void* tmap_storage, int use_tma, cudaStream_t s);
@@ -72,8 +72,7 @@ struct ss_engine {
     // 1 = one warp per window (ss_move_solo_kernel); -1 = by window count
     // 3 = dependency rounds over the whole lattice (ss_rounds.cu: ss_dr_build_kernel + ss_dr_rounds_kernel)
     int pass_impl_option = -1, pass_impl = 0;
-    uint32_t dr_slots = 0;                     // allocation sizes of the dependency-round state
-    int dr_mwords = 0;
+    uint32_t dr_slots = 0;                     // allocation size of the dependency-round state
     int mirror = 0;                            // which int(sugar) mirror is current: 1 = isugar (window passes), 2 = mw (rounds)
     bool cap_fits_u7 = true;
     int use_tma = 1, tma_ok = 0;
@@ -534,42 +533,50 @@ static int ensure_stats(ss_engine* e, int nsteps) {
 
 static void dr_free(ss_engine* e) {
     DrState& d = e->w.dr;
-    cudaFree(d.self.mw); cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.self.ctl);
-    cudaFree(d.mask); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
+    cudaFree(d.self.mw); cudaFree(d.self.mwx); cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.self.ctl);
+    cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
     memset(&d, 0, sizeof d);
-    e->dr_slots = 0; e->dr_mwords = 0;
+    e->dr_slots = 0;
 }
 
-// device state of the dependency rounds (ss_world.cuh DrState), sized by the lattice, the slots and the largest vision
+// device state of the dependency rounds (ss_world.cuh DrState), sized by the lattice and the slots
 static int dr_alloc(ss_engine* e) {
     DrState& d = e->w.dr;
     const uint32_t ns = std::max<uint32_t>(e->w.n_slots, 1u);
-    const int mwords = ss_dr_mask_words(e->w.vmax);
     if (!d.self.mw) {
-        CK(cudaMalloc(&d.self.mw, e->cells + 16));
-        CK(cudaMalloc(&d.self.dep, (e->cells / 2 + 2) * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.self.mw, e->cells + 64));
+        CK(cudaMalloc(&d.self.mwx, e->cells + 64));
         CK(cudaMalloc(&d.self.ctl, DR_CTL_WORDS * sizeof(unsigned int)));
-        CK(cudaMemsetAsync(d.self.dep, 0, (e->cells / 2 + 2) * sizeof(uint32_t), e->stream));
+        CK(cudaMemsetAsync(d.self.mw, 0, e->cells + 64, e->stream));
+        CK(cudaMemsetAsync(d.self.mwx, 0, e->cells + 64, e->stream));
         CK(cudaMemsetAsync(d.self.ctl, 0, DR_CTL_WORDS * sizeof(unsigned int), e->stream));
     }
-    if (ns != e->dr_slots || mwords != e->dr_mwords) {
-        cudaFree(d.self.queue); cudaFree(d.mask); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
-        d.self.queue = nullptr; d.mask = nullptr; d.alive = nullptr; d.atrisk = nullptr; d.q1wait = nullptr;
+    // successors beyond the 14 of a record: a run of the pool; sized for 16 more per agent, or for every cell of
+    // every conflict zone when that is less
+    const int V = std::max(e->w.vmax, 1);
+    const uint64_t zone = (uint64_t)(2 * V + 1) * (2 * V + 1) + 4 * V;
+    const uint64_t pool64 = std::min<uint64_t>((uint64_t)ns * 16u, (uint64_t)ns * zone) + 64;
+    const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(pool64, 0xfffffff0ull);
+    if (ns != e->dr_slots || pool_cap != d.pool_cap) {
+        cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
+        d.self.dep = nullptr; d.self.queue = nullptr; d.succ = nullptr; d.pool = nullptr; d.alive = nullptr; d.atrisk = nullptr; d.q1wait = nullptr;
         const size_t words = (size_t)(ns + 31) / 32 + 1;
+        CK(cudaMalloc(&d.self.dep, sizeof(uint32_t) * ((size_t)ns / 2 + 2)));
         CK(cudaMalloc(&d.self.queue, sizeof(uint32_t) * ((size_t)ns + 64)));
-        CK(cudaMalloc(&d.mask, sizeof(unsigned long long) * (size_t)ns * mwords));
+        CK(cudaMalloc(&d.succ, sizeof(uint4) * 4 * (size_t)ns));
+        CK(cudaMalloc(&d.pool, sizeof(uint32_t) * (size_t)pool_cap));
         CK(cudaMalloc(&d.alive, sizeof(uint32_t) * words));
         CK(cudaMalloc(&d.atrisk, sizeof(uint32_t) * words));
         CK(cudaMalloc(&d.q1wait, sizeof(uint2) * (size_t)ns));
+        CK(cudaMemsetAsync(d.self.dep, 0, sizeof(uint32_t) * ((size_t)ns / 2 + 2), e->stream));
         CK(cudaMemsetAsync(d.alive, 0, sizeof(uint32_t) * words, e->stream));
         CK(cudaMemsetAsync(d.atrisk, 0, sizeof(uint32_t) * words, e->stream));
         CK(cudaMemsetAsync(d.q1wait, 0, sizeof(uint2) * (size_t)ns, e->stream));
-        e->dr_slots = ns; e->dr_mwords = mwords;
+        e->dr_slots = ns; d.pool_cap = pool_cap;
         if (e->mirror == 2) e->mirror = 0;
     }
-    d.mwords = mwords;
     d.queue_cap = ns;
-    d.self.occw = e->w.occw; d.self.sugar = e->w.sugar; d.self.poll = e->w.poll;
+    d.self.occw = e->w.occw; d.self.sugar = e->w.sugar; d.self.poll = e->w.poll; d.self.agents = e->w.agents;
     d.self.x0 = 0; d.self.rows = e->w.n;
     d.lo = d.self; d.hi = d.self;
     e->tma_ok = 0;
@@ -581,7 +588,11 @@ static int env_phase(ss_engine* e) {
     {
         KTimer t(e, KT_GROW);
         // the growback refreshes the int(sugar) mirror that is current (cell words of the rounds / isugar bytes)
-        if (e->cfg.rule_grow) { CK(ss_launch_grow(e->w, e->iteration, e->sm_count, e->mirror == 2, e->stream)); e->launches++; }
+        if (e->cfg.rule_grow) {
+            CK(ss_launch_grow(e->w, e->iteration, e->sm_count, e->mirror == 2, e->stream));
+            e->launches++;
+            if (e->mirror == 2) { CK(ss_launch_dr_transpose(e->w, e->stream)); e->launches++; }     // the x-arm copy of the cell bytes
+        }
     }
     if (e->cfg.rule_pollution && e->iteration >= e->cfg.diffusion_start_time &&
         e->iteration % e->cfg.diffusion_rate == 0) {                                  // sugarscape.py:661-663
@@ -619,7 +630,7 @@ static int dr_step(ss_engine* e, int stats_index) {
         CK(ss_launch_dr_mirror(e->w, e->d_flags, e->stream));
         CK(cudaMemcpyAsync(&flag, e->d_flags, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
-        e->launches += 2; e->syncs++;
+        e->launches += 3; e->syncs++;
         if (flag) return set_err(e, SS_ERR_UNSUPPORTED, "dependency rounds need cell sugar and capacities < 127");
         e->mirror = 2;
     }
@@ -894,6 +905,11 @@ extern "C" int ss_get_counters(ss_engine* e, int64_t* out, int32_t n) {
         cudaMemcpy(&acc, e->w.acc, sizeof acc, cudaMemcpyDeviceToHost);
         const int64_t v2[5] = {(int64_t)acc.watchdog, (int64_t)acc.wd_info[0], (int64_t)acc.wd_info[1], (int64_t)acc.wd_info[2], (int64_t)acc.fault};
         for (int i = 6; i < n && i < 11; i++) out[i] = v2[i - 6];
+    }
+    if (n > 11) {                  // dependency rounds: grid barriers (= rounds) since the state was allocated
+        unsigned int rounds = 0;
+        if (e->w.dr.self.ctl) cudaMemcpy(&rounds, e->w.dr.self.ctl + 2, sizeof rounds, cudaMemcpyDeviceToHost);
+        out[11] = (int64_t)rounds;
     }
     if (n > 6 && e->w.dbg) {       // instrumentation counters of the move passes (option "debug")
         unsigned long long d[32];

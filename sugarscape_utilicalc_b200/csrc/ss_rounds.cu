@@ -10,13 +10,14 @@
 //                        cells in shared memory (TMA 2-D tile load, cp.async.bulk.tensor, for tiles that do not touch
 //                        the torus edge), turns them into (priority, vision) words + an occupancy bitmap, and one
 //                        thread per agent scans its conflict zone with the exact cross-intersection predicate:
-//                        predecessors are COUNTED (dep[cell]), successors are recorded as a bitmap over the zone
-//                        (mask[slot], 32 bytes for vision <= 7).  The list-order predecessor (the agent before it in
+//                        predecessors are COUNTED (dep[slot], an L2-resident u16 array), successors are recorded as a
+//                        list of slots (succ[slot]: one 64-byte record, the rare long lists continue in a pool).  The list-order predecessor (the agent before it in
 //                        the keyed order, found by walking the inverse priority map over the alive bitmap) adds one
 //                        more edge when it may starve this step (Q1: sugarscape.py:520 + 502-503, the agent after a
 //                        dying agent loses its turn).  Agents without predecessors enter the ready queue.
-//   ss_dr_rounds_kernel  one persistent cooperative kernel per step.  Round k: one thread per ready agent -- cross
-//                        scan on the one-byte cell words (occupied | int(sugar)), choice (agent.py:794-823 incl. the
+//   ss_dr_rounds_kernel  one persistent cooperative kernel per step.  Round k: one thread per ready agent -- both arms
+//                        of the cross as two 16-byte loads each on the one-byte cell words (occupied | int(sugar);
+//                        the x-arm from a transposed copy), choice (agent.py:794-823 incl. the
 //                        replay of the agent's Fisher-Yates draws for ties), harvest, pollution, metabolism, death
 //                        (sugarscape.py:566-601), statistics -- then one atomic decrement per successor; whoever
 //                        brings a counter to zero appends that agent to the queue.  A grid barrier separates the
@@ -36,7 +37,7 @@
 #define DR_TY 128                       // tile columns (y, contiguous in memory)
 #define DR_BUILD_THREADS 512
 #define DR_THREADS 512                  // rounds kernel
-#define DR_PUSH_CAP 4096                // staged queue entries per CTA between flushes
+#define DR_WARP_CAP 128                 // staged queue entries per warp between flushes
 #define DR_HIST_BINS 2048               // low wealth bins kept in shared memory per CTA
 #define DR_SKIP 0x80000000u             // queue entry flag: the agent loses its turn (Q1)
 
@@ -44,33 +45,6 @@
 __device__ static inline bool dr_crosses_meet(int dx, int dy, int a, int b) {
     const int adx = abs(dx), ady = abs(dy);
     return (adx <= a && ady <= b) || (ady <= a && adx <= b) || (dy == 0 && adx <= a + b) || (dx == 0 && ady <= a + b);
-}
-// bit of zone offset (dx, dy) in the successor bitmap: the square |dx|,|dy| <= V row by row, then the four arm
-// extensions (V < |d| <= 2V on an axis)
-__device__ static inline int dr_bit_index(int dx, int dy, int V) {
-    const int S = 2 * V + 1;
-    if (abs(dx) <= V && abs(dy) <= V) return (dx + V) * S + (dy + V);
-    const int base = S * S;
-    if (dy == 0) return dx < 0 ? base + (-dx - V - 1) : base + V + (dx - V - 1);
-    return dy < 0 ? base + 2 * V + (-dy - V - 1) : base + 3 * V + (dy - V - 1);
-}
-__device__ static inline void dr_bit_offset(int idx, int V, uint32_t magicS, int& dx, int& dy) {
-    const int S = 2 * V + 1, S2 = S * S;
-    if (idx < S2) {
-        const int r = (int)(((uint32_t)idx * magicS) >> 16);       // idx / S (exact for idx < 2^16 / S)
-        dx = r - V; dy = idx - r * S - V;
-        return;
-    }
-    const int t = idx - S2;
-    int arm = 0, d = t;
-    while (d >= V) { d -= V; arm++; }
-    d += V + 1;
-    dx = arm == 0 ? -d : arm == 1 ? d : 0;
-    dy = arm == 2 ? -d : arm == 3 ? d : 0;
-}
-__host__ __device__ static inline int dr_mask_words(int V) {
-    const int bits = (2 * V + 1) * (2 * V + 1) + 4 * V;
-    return bits <= 256 ? 4 : 16;
 }
 
 // strip addressing: which strip holds lattice row gx (already wrapped to [0, n)) and where.  which: 0 = this strip,
@@ -93,29 +67,17 @@ __device__ static inline DrLoc dr_loc(const DevWorld& w, int gx, int gy) {
     L.which = 2; L.idx = (uint32_t)above * (uint32_t)w.n + (uint32_t)gy;
     return L;
 }
-#define DR_F(field, L) ((!STRIPS || (L).which == 0) ? w.dr.self.field : ((L).which == 1 ? w.dr.lo.field : w.dr.hi.field))
-
-template <int MW> struct MaskAcc;
-template <> struct MaskAcc<4> {
-    unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-    __device__ inline void set(int idx) {
-        const unsigned long long b = 1ull << (idx & 63);
-        const int wi = idx >> 6;
-        if (wi == 0) m0 |= b; else if (wi == 1) m1 |= b; else if (wi == 2) m2 |= b; else m3 |= b;
-    }
-    __device__ inline void store(unsigned long long* p) const {
-        reinterpret_cast<ulonglong2*>(p)[0] = make_ulonglong2(m0, m1);
-        reinterpret_cast<ulonglong2*>(p)[1] = make_ulonglong2(m2, m3);
-    }
-};
-template <> struct MaskAcc<16> {
-    unsigned long long m[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    __device__ inline void set(int idx) { m[idx >> 6] |= 1ull << (idx & 63); }
-    __device__ inline void store(unsigned long long* p) const { for (int i = 0; i < 16; i++) p[i] = m[i]; }
-};
+#define DR_W(field, which) ((!STRIPS || (which) == 0) ? w.dr.self.field : ((which) == 1 ? w.dr.lo.field : w.dr.hi.field))
+#define DR_F(field, L) DR_W(field, (L).which)
+// the transposed cell byte of local cell idx = r * n + y of strip `which`: y * rows + r
+template <bool STRIPS>
+__device__ static inline size_t dr_xidx(const DevWorld& w, const DrLoc& L) {
+    const uint32_t r = L.idx / (uint32_t)w.n, y = L.idx - r * (uint32_t)w.n;
+    return (size_t)y * (size_t)DR_F(rows, L) + r;
+}
 
 // ------------------------------------------------------------------- mirrors and flags ----
-// mw from the uploaded state; flag bit 0: a value does not fit 7 bits (the path is then refused)
+// mw from the uploaded state; flag: a value does not fit 7 bits (the path is then refused)
 __global__ void ss_dr_mirror_kernel(DevWorld w, size_t cells, int* flag) {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
         const double v = w.sugar[c];
@@ -124,7 +86,21 @@ __global__ void ss_dr_mirror_kernel(DevWorld w, size_t cells, int* flag) {
         w.dr.self.mw[c] = (uint8_t)(iv | (w.occw[c] ? 0x80 : 0));
     }
 }
-// alive / at-risk bitmaps and the OCC_RISK flag of the occupancy words from the agent store (after an upload).
+// mwx = mw transposed (64 x 64-byte tiles through shared memory): after an upload and after every growback
+__global__ void __launch_bounds__(256)
+ss_dr_transpose_kernel(const uint8_t* __restrict__ mw, uint8_t* __restrict__ mwx, int rows, int n) {
+    __shared__ uint8_t t[64][68];
+    const int tiles_y = (n + 63) >> 6;
+    const int bx = blockIdx.x / tiles_y, by = blockIdx.x - bx * tiles_y;
+    const int r0 = bx << 6, y0 = by << 6;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int k = ty; k < 64; k += 4)
+        if (r0 + k < rows && y0 + tx < n) t[k][tx] = mw[(size_t)(r0 + k) * n + y0 + tx];
+    __syncthreads();
+    for (int k = ty; k < 64; k += 4)
+        if (y0 + k < n && r0 + tx < rows) mwx[(size_t)(y0 + k) * rows + r0 + tx] = t[tx][k];
+}
+// alive / at-risk bitmaps and the ATTR_RISK flag from the agent store (after an upload).
 // AT RISK = the agent starves this step unless it harvests something: sugar - metabolism <= 0.1 before its turn
 // (sugarscape.py:569, 306-309; agent.py:224-229).  Everybody else survives whatever happens, so only at-risk agents
 // create a Q1 edge to their successor in the list order.
@@ -135,13 +111,12 @@ __global__ void ss_dr_flags_kernel(DevWorld w) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool alive = false, risk = false;
     if (slot < w.n_slots) {
-        const AgentRec r = w.agents[slot];
-        alive = attr_alive(r.attr);
+        AgentRec* rp = &w.agents[slot];
+        const uint32_t attr = rp->attr;
+        alive = attr_alive(attr);
         if (alive) {
-            risk = dr_at_risk(w, r.sugar, attr_metab(r.attr));
-            uint32_t ow = w.occw[r.pos];
-            ow = risk ? (ow | OCC_RISK) : (ow & ~OCC_RISK);
-            w.occw[r.pos] = ow & ~OCC_Q1;
+            risk = dr_at_risk(w, rp->sugar, attr_metab(attr));
+            rp->attr = risk ? (attr | ATTR_RISK) : (attr & ~ATTR_RISK);
         }
     }
     const unsigned ba = __ballot_sync(FULL, alive), br = __ballot_sync(FULL, risk);
@@ -158,7 +133,41 @@ struct DrBuildArgs {
     int use_tma;
 };
 
-template <int MW, bool STRIPS>
+// Scan of one agent's conflict zone on the staged tile.  emit(dx, dy, word) is called for every conflicting agent of
+// HIGHER priority (a successor); returns the number of conflicting agents of lower priority (predecessors).
+template <class Emit>
+__device__ static inline uint32_t dr_scan_zone(const uint32_t* tile, const uint32_t* bm, int SY, int BW, int V, int lr, int lq,
+                                               uint32_t pa, int a, Emit emit) {
+    const int H = 2 * V;
+    uint32_t indeg = 0;
+    for (int dx = -H; dx <= H; dx++) {
+        const int r = lr + dx, adx = abs(dx);
+        if (adx > V) {                                             // beyond the square: only the cell on the axis
+            const uint32_t cv = tile[r * SY + lq];
+            if (cv && adx <= a + (int)(cv & 31u)) { if ((cv >> 5) < pa) indeg++; else emit(dx, 0, cv); }
+            continue;
+        }
+        const int R = dx == 0 ? H : V, qlo = lq - R, qhi = lq + R;
+        for (int wq = qlo >> 5; wq <= (qhi >> 5); wq++) {
+            uint32_t bits = bm[r * BW + wq];
+            const int base = wq << 5;
+            if (base < qlo) bits &= FULL << (qlo - base);
+            if (base + 31 > qhi) bits &= FULL >> (base + 31 - qhi);
+            while (bits) {
+                const int q = base + __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int dy = q - lq;
+                if (dx == 0 && dy == 0) continue;
+                const uint32_t cv = tile[r * SY + q];
+                if (!dr_crosses_meet(dx, dy, a, (int)(cv & 31u))) continue;
+                if ((cv >> 5) < pa) indeg++; else emit(dx, dy, cv);
+            }
+        }
+    }
+    return indeg;
+}
+
+template <bool STRIPS>
 __global__ void __launch_bounds__(DR_BUILD_THREADS)
 ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint32_t sm[];
@@ -191,13 +200,10 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                 ::"r"(smem_u32(tile)), "l"(&tmap), "r"(y0 - H), "r"(x0 - H - S.x0), "r"(smem_u32(&s_bar)) : "memory");
         }
-        // everybody waits for the box (phase 0)
-        {
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
-            }
+        uint32_t done = 0;                                 // everybody waits for the box (phase 0)
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
         }
     } else {
         __syncthreads();
@@ -230,35 +236,37 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
         const uint32_t me = tile[lr * SY + lq];
         const uint32_t pa = me >> 5;
         const int a = (int)(me & 31u);
-        const int gx = x0 + lr - H, gy = y0 + lq - H;
-        const uint32_t c = (uint32_t)(gx - S.x0) * (uint32_t)n + (uint32_t)gy;
-        const uint32_t slot = occ_slot(__ldcg(&S.occw[c]));
-        MaskAcc<MW> mk;
-        uint32_t indeg = 0;
-        for (int dx = -H; dx <= H; dx++) {
-            const int r = lr + dx, adx = abs(dx);
-            if (adx > V) {                                             // beyond the square: only the cell on the axis
-                const uint32_t cv = tile[r * SY + lq];
-                if (cv && adx <= a + (int)(cv & 31u)) { if ((cv >> 5) < pa) indeg++; else mk.set(dr_bit_index(dx, 0, V)); }
-                continue;
-            }
-            const int R = dx == 0 ? H : V, qlo = lq - R, qhi = lq + R;
-            for (int wq = qlo >> 5; wq <= (qhi >> 5); wq++) {
-                uint32_t bits = bm[r * BW + wq];
-                const int base = wq << 5;
-                if (base < qlo) bits &= FULL << (qlo - base);
-                if (base + 31 > qhi) bits &= FULL >> (base + 31 - qhi);
-                while (bits) {
-                    const int q = base + __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    const int dy = q - lq;
-                    if (dx == 0 && dy == 0) continue;
-                    const uint32_t cv = tile[r * SY + q];
-                    if (!dr_crosses_meet(dx, dy, a, (int)(cv & 31u))) continue;
-                    if ((cv >> 5) < pa) indeg++; else mk.set(dr_bit_index(dx, dy, V));
-                }
+        const uint32_t slot = ss_priority_inverse(ba.ok, pa);
+        const int row = x0 + lr - H - S.x0;                        // strip-local row of the agent
+        // successors: the first DR_SUCC_INLINE in the record, the rest in a run of the pool
+        uint32_t rec[16];
+        uint32_t nsucc = 0;
+        auto which_of = [&](int dx) -> uint32_t {
+            if (!STRIPS) return 0u;
+            const int r2 = row + dx;
+            return r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u);
+        };
+        uint32_t indeg = dr_scan_zone(tile, bm, SY, BW, V, lr, lq, pa, a, [&](int dx, int, uint32_t cv) {
+            if (nsucc < DR_SUCC_INLINE) rec[1 + nsucc] = ss_priority_inverse(ba.ok, cv >> 5) | (which_of(dx) << 24);
+            nsucc++;
+        });
+        rec[15] = 0u;
+        if (nsucc > DR_SUCC_INLINE) {
+            const uint32_t extra = nsucc - DR_SUCC_INLINE;
+            const uint32_t at = atomicAdd(&S.ctl[6], extra);
+            rec[15] = at;
+            if (at + extra <= w.dr.pool_cap) {
+                uint32_t i = 0;
+                dr_scan_zone(tile, bm, SY, BW, V, lr, lq, pa, a, [&](int dx, int, uint32_t cv) {
+                    if (i >= DR_SUCC_INLINE) w.dr.pool[at + i - DR_SUCC_INLINE] = ss_priority_inverse(ba.ok, cv >> 5) | (which_of(dx) << 24);
+                    i++;
+                });
+            } else {
+                atomicAdd(&S.ctl[7], 1u);                          // pool exhausted: reported as a fault by the step
+                nsucc = DR_SUCC_INLINE;
             }
         }
+        rec[0] = nsucc;
         // Q1: the agent before this one in the list order (the keyed order: ascending priority over the living
         // agents); if it may starve, its outcome decides whether this agent acts at all
         if (w.cfg.rule_can_starve) {
@@ -267,13 +275,19 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
                 if (s2 >= w.n_slots || !((__ldg(&w.dr.alive[s2 >> 5]) >> (s2 & 31)) & 1u)) continue;
                 if ((__ldg(&w.dr.atrisk[s2 >> 5]) >> (s2 & 31)) & 1u) {
                     indeg++;
-                    w.dr.q1wait[s2] = make_uint2(c, stamp);
+                    w.dr.q1wait[s2] = make_uint2(slot, stamp);
                 }
                 break;
             }
         }
-        reinterpret_cast<uint16_t*>(S.dep)[c] = (uint16_t)indeg;
-        mk.store(&w.dr.mask[(size_t)slot * MW]);
+        reinterpret_cast<uint16_t*>(S.dep)[slot] = (uint16_t)indeg;
+        uint4* sp = &w.dr.succ[(size_t)slot * 4];
+        const int used = 1 + (int)min(nsucc, (uint32_t)DR_SUCC_INLINE);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            // entries past the list's end are never read: skip the stores of whole unused quarters
+            if (i * 4 < used || (i == 3 && nsucc > DR_SUCC_INLINE)) sp[i] = make_uint4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+        }
         if (indeg == 0) { list[k] |= 0x8000u; atomicAdd(&s_ready, 1); }
     }
     __syncthreads();
@@ -283,64 +297,99 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
         for (int k = tid; k < nl; k += DR_BUILD_THREADS) {
             if (!(list[k] & 0x8000u)) continue;
             const int lr = (list[k] >> 8) & 127, lq = list[k] & 255;
-            const uint32_t c = (uint32_t)(x0 + lr - H - S.x0) * (uint32_t)n + (uint32_t)(y0 + lq - H);
-            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = c;
+            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = ss_priority_inverse(ba.ok, tile[lr * SY + lq] >> 5);
         }
     }
 }
 
 // ------------------------------------------------------------------------------- rounds ----
 struct DrAccum { unsigned sum_m, sum_v, acted, deaths, small, inexact, fault; };
+#define DR_WARPS (DR_THREADS / 32)
 struct DrShared {
     unsigned hist[DR_HIST_BINS];
-    uint32_t push[DR_PUSH_CAP];
+    uint32_t push[DR_WARPS][DR_WARP_CAP];
+    int cnt[DR_WARPS];
     unsigned long long acc[8];
-    int cnt;
-    unsigned base;
 };
 
-__device__ static inline void dr_push(const DevWorld& w, DrShared& sh, uint32_t e) {
-    const int pos = atomicAdd(&sh.cnt, 1);
-    if (pos < DR_PUSH_CAP) sh.push[pos] = e;
-    else w.dr.self.queue[atomicAdd(&w.dr.self.ctl[0], 1u)] = e;          // staging full: straight to the queue
+// appends to the warp's staging buffer (flushed by the warp between agents); a full buffer goes straight to the queue
+__device__ static inline void dr_push(const DevWorld& w, DrShared& sh, int warp, uint32_t e) {
+    const int pos = atomicAdd(&sh.cnt[warp], 1);
+    if (pos < DR_WARP_CAP) sh.push[warp][pos] = e;
+    else w.dr.self.queue[atomicAdd(&w.dr.self.ctl[0], 1u)] = e;
 }
-// one predecessor of the agent that started the step on lattice cell (gx, gy) is resolved
+__device__ static inline void dr_flush(const DevWorld& w, DrShared& sh, int warp, int lane) {
+    __syncwarp();
+    const int k = min(sh.cnt[warp], DR_WARP_CAP);
+    if (k > 0) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&w.dr.self.ctl[0], (unsigned)k);
+        base = __shfl_sync(FULL, base, 0);
+        for (int j = lane; j < k; j += 32) w.dr.self.queue[base + (unsigned)j] = sh.push[warp][j];
+    }
+    __syncwarp();
+    if (lane == 0) sh.cnt[warp] = 0;
+    __syncwarp();
+}
+// the result of one decrement of a successor's counter: the counter's old value decides who queues the successor
 template <bool STRIPS>
-__device__ static inline void dr_release(const DevWorld& w, DrShared& sh, DrAccum& acc, int gx, int gy, bool lose_turn) {
-    const DrLoc L = dr_loc<STRIPS>(w, gx, gy);
-    uint32_t* wp = &DR_F(dep, L)[L.idx >> 1];
-    const int shf = (int)(L.idx & 1u) << 4;
-    const uint32_t old = lose_turn ? atomicAdd(wp, 0x7fffu << shf) : atomicSub(wp, 1u << shf);
-    const uint32_t h = (old >> shf) & 0xffffu;
+__device__ static inline void dr_released(const DevWorld& w, DrShared& sh, int warp, DrAccum& acc, uint32_t ent, uint32_t old,
+                                          bool lose_turn) {
+    const uint32_t slot2 = ent & OCC_SLOT_MASK;
+    const uint32_t h = (old >> ((slot2 & 1u) << 4)) & 0xffffu;
     if ((h & 0x7fffu) == 1u) {
-        const uint32_t e = L.idx | ((lose_turn || (h >> 15)) ? DR_SKIP : 0u);
-        if (!STRIPS || L.which == 0) dr_push(w, sh, e);
-        else DR_F(queue, L)[atomicAdd(&DR_F(ctl, L)[0], 1u)] = e;        // a ring neighbour's agent
+        const uint32_t e = slot2 | ((lose_turn || (h >> 15)) ? DR_SKIP : 0u);
+        const int which = STRIPS ? (int)((ent >> 24) & 3u) : 0;
+        if (which == 0) dr_push(w, sh, warp, e);
+        else DR_W(queue, which)[atomicAdd(&DR_W(ctl, which)[0], 1u)] = e;          // a ring neighbour's agent
     } else if ((h & 0x7fffu) == 0u) acc.fault++;
+}
+template <bool STRIPS>
+__device__ static inline uint32_t dr_dec(const DevWorld& w, uint32_t ent) {
+    const uint32_t slot2 = ent & OCC_SLOT_MASK;
+    const int which = STRIPS ? (int)((ent >> 24) & 3u) : 0;
+    return atomicSub(&DR_W(dep, which)[slot2 >> 1], 1u << ((slot2 & 1u) << 4));
 }
 
 struct DrStep {
     int64_t iteration, env_time;
     uint64_t skey;
-    uint32_t next_phase, magicS;
+    uint32_t next_phase;
     int single_round;               // host-driven rounds (several strips on one GPU): run one round and return
     unsigned seg_begin, seg_end;    // ... over this queue segment
     unsigned nblocks;
 };
 
-// agent.py:361-371 getFood + 794-823 move(): one THREAD scans the cross on the one-byte cell words.  Candidates are
-// numbered k = offset + a on the x-arm (ascending raw x), then span + offset + a on the y-arm -- the order getFood
-// appends them in; best = (key desc, raw Manhattan distance asc, position in the shuffled food list asc).  At most
-// four candidates tie on (key, distance): one distance, two arms, two sides.
-template <int POLT, bool STRIPS>
-__device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a, uint32_t slot, uint64_t skey, uint8_t own,
-                                        DrAccum& acc, int& out_x, int& out_y, int& out_sg) {
+// 17 consecutive cell bytes (offsets -a..+a of one arm, a <= 8) out of two aligned 16-byte loads
+struct ArmWin { unsigned long long w0, w1, w2; };
+__device__ static inline ArmWin dr_load_arm(const uint8_t* base, size_t first) {
+    const size_t al = first & ~(size_t)15;
+    const int off = (int)(first - al);
+    const uint4 A = __ldcg(reinterpret_cast<const uint4*>(base + al)), B = __ldcg(reinterpret_cast<const uint4*>(base + al + 16));
+    unsigned long long q0 = (unsigned long long)A.x | ((unsigned long long)A.y << 32), q1 = (unsigned long long)A.z | ((unsigned long long)A.w << 32);
+    unsigned long long q2 = (unsigned long long)B.x | ((unsigned long long)B.y << 32), q3 = (unsigned long long)B.z | ((unsigned long long)B.w << 32);
+    if (off & 8) { q0 = q1; q1 = q2; q2 = q3; q3 = 0ull; }
+    const int r = (off & 7) * 8;
+    ArmWin W;
+    if (r) { W.w0 = (q0 >> r) | (q1 << (64 - r)); W.w1 = (q1 >> r) | (q2 << (64 - r)); W.w2 = (q2 >> r) | (q3 << (64 - r)); }
+    else { W.w0 = q0; W.w1 = q1; W.w2 = q2; }
+    return W;
+}
+__device__ static inline unsigned dr_arm_byte(const ArmWin& W, int i) {
+    return (unsigned)((i < 8 ? W.w0 >> (8 * i) : (i < 16 ? W.w1 >> (8 * (i - 8)) : W.w2)) & 0xffull);
+}
+
+// agent.py:361-371 getFood + 794-823 move(): one THREAD evaluates the cross.  cellbyte(arm, o) = the cell word at offset o
+// on the x-arm (arm 0) / y-arm (arm 1); cellpoll likewise the pollution.  Candidates are numbered k = offset + a on the
+// x-arm (ascending raw x), then span + offset + a on the y-arm -- the order getFood appends them in; best = (key desc, raw
+// Manhattan distance asc, position in the shuffled food list asc).  At most four candidates tie on (key, distance): one
+// distance, two arms, two sides.  Returns the chosen offset (arm, o) and harvest; arm = -1: stay.
+template <int POLT, class CellByte, class CellPoll>
+__device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a, uint32_t slot, uint64_t skey, int sg0, double pown,
+                                        DrAccum& acc, CellByte cellbyte, CellPoll cellpoll, int& out_arm, int& out_o, int& out_sg) {
     const int n = w.n;
     constexpr bool pol = POLT != 0;
     const int span = 2 * a + 1;
-    const int sg0 = own & 0x7f;
-    double pown = 0.0;
-    if (pol) { const DrLoc L = dr_loc<STRIPS>(w, gx, gy); pown = __ldcg(&DR_F(poll, L)[L.idx]); }
     unsigned long long fm = 0ull;           // free candidates, bit = candidate index k
     unsigned long long tl = 0ull;           // tied best candidates, 16 bits each: harvest << 8 | k
     int nt = 0, dmin = 0x7fffffff;
@@ -348,38 +397,30 @@ __device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a
     double dkmax = -1.0;
 #pragma unroll 1
     for (int d = 1; d <= a; d++) {
-        int cx[4], cy[4], kk[4];
-        cx[0] = ss_wrap1(gx - d, n); cy[0] = gy; kk[0] = a - d;
-        cx[1] = ss_wrap1(gx + d, n); cy[1] = gy; kk[1] = a + d;
-        cx[2] = gx; cy[2] = ss_wrap1(gy - d, n); kk[2] = span + a - d;
-        cx[3] = gx; cy[3] = ss_wrap1(gy + d, n); kk[3] = span + a + d;
-        uint8_t mv[4];
-        double pp[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const DrLoc L = dr_loc<STRIPS>(w, cx[u], cy[u]);
-            mv[u] = __ldcg(&DR_F(mw, L)[L.idx]);
-            pp[u] = pol ? __ldcg(&DR_F(poll, L)[L.idx]) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (mv[u] & 0x80) continue;
-            const int sg = mv[u];
-            fm |= 1ull << kk[u];
-            const int dist = abs(gx - cx[u]) + abs(gy - cy[u]);                     // agent.py:867-868 (raw coordinates)
-            const unsigned long long ent = ((unsigned long long)sg << 8) | (unsigned long long)kk[u];
+            const int arm = u >> 1, o = (u & 1) ? d : -d;
+            const unsigned mv = cellbyte(arm, o);
+            if (mv & 0x80u) continue;
+            const int sg = (int)mv;
+            const int kk = arm * span + a + o;
+            fm |= 1ull << kk;
+            // agent.py:867-868: raw coordinates, so a candidate reached across the torus edge is far away
+            const int cc = (arm ? gy : gx) + o;
+            const int dist = (cc < 0 || cc >= n) ? n - d : d;
+            const unsigned long long ent = ((unsigned long long)sg << 8) | (unsigned long long)kk;
             if (!pol) {
                 const uint32_t ik = (((uint32_t)sg << 20) | (0xfffffu - (uint32_t)dist)) + 1u;
                 if (ik > ikmax) { ikmax = ik; tl = ent; nt = 1; }
                 else if (ik == ikmax) { tl = (tl << 16) | ent; nt++; }
             } else {
-                const double key = (double)sg / (1.0 + (sg > 0 ? pp[u] : 0.0));
+                const double key = (double)sg / (1.0 + (sg > 0 ? cellpoll(arm, o) : 0.0));
                 if (key > dkmax || (key == dkmax && dist < dmin)) { dkmax = key; dmin = dist; tl = ent; nt = 1; }
                 else if (key == dkmax && dist == dmin) { tl = (tl << 16) | ent; nt++; }
             }
         }
     }
-    out_x = gx; out_y = gy; out_sg = sg0;
+    out_arm = -1; out_o = 0; out_sg = sg0;
     if (nt == 0) return;                                                            // no free cell in sight
     // own cell, appended last (agent.py:806); distance 0 wins every tie on the key
     if (!pol) { if (sg0 >= (int)((ikmax - 1u) >> 20)) return; }
@@ -417,42 +458,69 @@ __device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a
     }
     const uint32_t ent = (uint32_t)((tl >> (16 * win)) & 0xffffull);
     const int k = (int)(ent & 255u);
-    if (k < span) { out_x = ss_wrap1(gx + k - a, n); out_y = gy; }
-    else { out_x = gx; out_y = ss_wrap1(gy + k - span - a, n); }
+    out_arm = k >= span ? 1 : 0;
+    out_o = k - out_arm * span - a;
     out_sg = (int)(ent >> 8);
 }
 
-template <int POLT, int MW, bool STRIPS>
-__device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrShared& sh, DrAccum& acc, uint32_t entry) {
-    const int n = w.n, V = w.vmax;
+template <int POLT, bool STRIPS>
+__device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrShared& sh, int warp, DrAccum& acc, uint32_t entry) {
+    const int n = w.n;
     const DrPeer& S = w.dr.self;
-    const uint32_t c = entry & ~DR_SKIP;
+    const uint32_t slot = entry & OCC_SLOT_MASK;
     const bool skip = (entry & DR_SKIP) != 0u;
-    const uint32_t ow = __ldcg(&S.occw[c]);
-    if (!ow) { acc.fault++; return; }
-    const uint32_t slot = occ_slot(ow);
-    const int a = occ_vision(ow);
-    const bool risky = (ow & OCC_RISK) != 0u;
-    // loads the turn will want at its end, issued now: the agent's record and its successor bitmap
-    AgentRec* recp = &w.agents[slot];
-    double sugar = __ldcg(&recp->sugar);
-    uint32_t attr = __ldcg(&recp->attr);
-    unsigned long long m[MW];
-    {
-        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(&w.dr.mask[(size_t)slot * MW]);
+    // the agent's record and its successor list
+    AgentRec* recp = &S.agents[slot];
+    const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(recp));               // sugar, pos, attr
+    const uint4* sp = &w.dr.succ[(size_t)slot * 4];
+    uint4 sq[4];
+    sq[0] = __ldcg(&sp[0]);
+    double sugar = __longlong_as_double((long long)((unsigned long long)r0.x | ((unsigned long long)r0.y << 32)));
+    const uint32_t c = r0.z;
+    uint32_t attr = r0.w;
+    if (!attr_alive(attr)) { acc.fault++; return; }
+    const int a = attr_vision(attr);
+    const bool risky = (attr & ATTR_RISK) != 0u;
+    const uint32_t nsucc = sq[0].x;
 #pragma unroll
-        for (int i = 0; i < MW / 2; i++) { const ulonglong2 v = __ldcg(&mp[i]); m[2 * i] = v.x; m[2 * i + 1] = v.y; }
-    }
+    for (int i = 1; i < 4; i++) sq[i] = (nsucc + 1u > 4u * (uint32_t)i) ? __ldcg(&sp[i]) : make_uint4(0u, 0u, 0u, 0u);
     uint2 qw = make_uint2(0u, 0u);
     if (risky) qw = __ldcg(&w.dr.q1wait[slot]);
     const int lx = (int)(c / (uint32_t)n), gy = (int)(c - (uint32_t)lx * (uint32_t)n), gx = S.x0 + lx;
     bool died = false;
     if (!skip) {
-        const uint8_t own = __ldcg(&S.mw[c]);
-        int nx = gx, ny = gy, sg = 0;
-        if (w.cfg.rule_move_eat) dr_choose<POLT, STRIPS>(w, gx, gy, a, slot, st.skey, own, acc, nx, ny, sg);
+        int arm = -1, o = 0, sg = 0;
+        uint8_t own;
+        // both arms inside this strip and the torus edge out of sight: two wide loads per arm
+        const bool fast = a <= 8 && lx - a >= 0 && lx + a < S.rows && gy - a >= 0 && gy + a < n;
+        if (w.cfg.rule_move_eat) {
+            if (fast) {
+                const ArmWin wy = dr_load_arm(S.mw, (size_t)c - (size_t)a);
+                const ArmWin wx = dr_load_arm(S.mwx, (size_t)gy * (size_t)S.rows + (size_t)(lx - a));
+                own = (uint8_t)dr_arm_byte(wy, a);
+                double pown = 0.0;
+                if (POLT) pown = __ldcg(&S.poll[c]);
+                dr_choose<POLT>(w, gx, gy, a, slot, st.skey, own & 0x7f, pown, acc,
+                                [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
+                                [&](int am, int oo) { return __ldcg(&S.poll[am ? c + oo : (uint32_t)((int)c + oo * n)]); }, arm, o, sg);
+            } else {
+                own = __ldcg(&S.mw[c]);
+                double pown = 0.0;
+                if (POLT) pown = __ldcg(&S.poll[c]);
+                dr_choose<POLT>(w, gx, gy, a, slot, st.skey, own & 0x7f, pown, acc,
+                                [&](int am, int oo) {
+                                    const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
+                                    return (unsigned)__ldcg(&DR_F(mw, L)[L.idx]);
+                                },
+                                [&](int am, int oo) {
+                                    const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
+                                    return __ldcg(&DR_F(poll, L)[L.idx]);
+                                }, arm, o, sg);
+            }
+        } else own = __ldcg(&S.mw[c]);
+        const int nx = arm == 0 ? ss_wrap1(gx + o, n) : gx, ny = arm == 1 ? ss_wrap1(gy + o, n) : gy;
         const DrLoc D = dr_loc<STRIPS>(w, nx, ny);
-        const bool moved = !(D.which == 0 && D.idx == c);
+        const bool moved = arm >= 0;
         const bool pol = POLT != 0 && w.cfg.pollution_start_time <= st.env_time;
         const int metab = attr_metab(attr);
         double p = 0.0;
@@ -460,7 +528,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         if (w.cfg.rule_move_eat) {
             if (pol) p = p + (((double)sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));     // agent.py:825-826
             sugar = ss_set_sugar(ss_max0(sugar + (double)sg));                                     // agent.py:832
-            DR_F(sugar, D)[D.idx] = 0.0;                                                               // agent.py:864
+            DR_F(sugar, D)[D.idx] = 0.0;                                                           // agent.py:864
         }
         if (pol && sugar > 0.0) p = p + ((0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b));   // sugarscape.py:566-567
         if (pol) DR_F(poll, D)[D.idx] = p;
@@ -473,37 +541,60 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         } else acc.inexact++;
         died = w.cfg.rule_can_starve && sugar <= 0.1;                                              // sugarscape.py:306-309
         const bool risk_next = !died && dr_at_risk(w, sugar, metab);
-        uint32_t new_word = 0u;
-        if (!died) new_word = occ_pack(slot, a, st.next_phase) | (risk_next ? OCC_RISK : 0u);
-        if (moved) { S.occw[c] = 0u; S.mw[c] = own & 0x7f; }
+        const uint32_t new_word = died ? 0u : occ_pack(slot, a, st.next_phase);
+        const uint8_t new_mw = died ? 0 : 0x80;
+        if (moved) {
+            S.occw[c] = 0u;
+            S.mw[c] = own & 0x7f;
+            S.mwx[(size_t)gy * (size_t)S.rows + (size_t)lx] = own & 0x7f;
+        }
         DR_F(occw, D)[D.idx] = new_word;
-        DR_F(mw, D)[D.idx] = died ? 0 : 0x80;
+        DR_F(mw, D)[D.idx] = new_mw;
+        DR_F(mwx, D)[dr_xidx<STRIPS>(w, D)] = new_mw;
+        attr = (attr & ~ATTR_RISK) | (risk_next ? ATTR_RISK : 0u);
         if (died) {
             attr &= ~ATTR_ALIVE; acc.deaths++;
             atomicAnd(&w.dr.alive[slot >> 5], ~(1u << (slot & 31)));
         }
         if (risk_next != risky) atomicXor(&w.dr.atrisk[slot >> 5], 1u << (slot & 31));
-        recp->sugar = sugar;
-        recp->pos = D.idx;
-        recp->attr = attr;
-    } else {
-        S.occw[c] = (ow & 0x7fffffffu) | (st.next_phase << 31);
+        AgentRec* dst = &DR_F(agents, D)[slot];                    // the record travels with the agent
+        uint4 nr;
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(sugar);
+        nr.x = (uint32_t)sb; nr.y = (uint32_t)(sb >> 32); nr.z = D.idx; nr.w = attr;
+        *reinterpret_cast<uint4*>(dst) = nr;
+        if (STRIPS && D.which != 0) recp->attr = attr & ~ATTR_ALIVE;      // left this strip
     }
     // Q1: whoever follows this agent in the list order learns the outcome (a skipped agent did not die)
     if (risky && qw.y == (uint32_t)(st.iteration + 1)) {
-        const uint32_t qx = qw.x / (uint32_t)n;
-        dr_release<STRIPS>(w, sh, acc, S.x0 + (int)qx, (int)(qw.x - qx * (uint32_t)n), died);
+        const uint32_t s2 = qw.x & OCC_SLOT_MASK;
+        const int which = STRIPS ? (int)((qw.x >> 24) & 3u) : 0;
+        const int shf = (int)(s2 & 1u) << 4;
+        uint32_t* wp = &DR_W(dep, which)[s2 >> 1];
+        const uint32_t old = died ? atomicAdd(wp, 0x7fffu << shf) : atomicSub(wp, 1u << shf);
+        dr_released<STRIPS>(w, sh, warp, acc, qw.x, old, died);
     }
-    // conflict successors: start-of-step positions relative to this agent's start cell
+    // conflict successors: all decrements of the record are issued before the first result is looked at
+    {
+        const uint32_t e[16] = {sq[0].x, sq[0].y, sq[0].z, sq[0].w, sq[1].x, sq[1].y, sq[1].z, sq[1].w,
+                                sq[2].x, sq[2].y, sq[2].z, sq[2].w, sq[3].x, sq[3].y, sq[3].z, sq[3].w};
+        uint32_t old[DR_SUCC_INLINE];
 #pragma unroll
-    for (int i = 0; i < MW; i++) {
-        unsigned long long bits = m[i];
-        while (bits) {
-            const int b = __ffsll((long long)bits) - 1;
-            bits &= bits - 1ull;
-            int dx, dy;
-            dr_bit_offset(i * 64 + b, V, st.magicS, dx, dy);
-            dr_release<STRIPS>(w, sh, acc, ss_wrap1(gx + dx, n), ss_wrap1(gy + dy, n), false);
+        for (int i = 0; i < DR_SUCC_INLINE; i++) old[i] = (uint32_t)i < nsucc ? dr_dec<STRIPS>(w, e[1 + i]) : 0u;
+#pragma unroll
+        for (int i = 0; i < DR_SUCC_INLINE; i++)
+            if ((uint32_t)i < nsucc) dr_released<STRIPS>(w, sh, warp, acc, e[1 + i], old[i], false);
+        if (nsucc > DR_SUCC_INLINE) {
+            const uint32_t* pp = w.dr.pool + e[15];
+            const uint32_t extra = nsucc - DR_SUCC_INLINE;
+            for (uint32_t b = 0; b < extra; b += 4) {
+                uint32_t en[4], ol[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) en[i] = b + i < extra ? __ldcg(&pp[b + i]) : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) ol[i] = b + i < extra ? dr_dec<STRIPS>(w, en[i]) : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (b + i < extra) dr_released<STRIPS>(w, sh, warp, acc, en[i], ol[i], false);
+            }
         }
     }
 }
@@ -524,7 +615,7 @@ __device__ static inline unsigned dr_grid_barrier(unsigned int* ctl, unsigned nb
         } else {
             unsigned spins = 0;
             while (*(volatile unsigned*)&ctl[2] == gen) {
-                __nanosleep(64);
+                __nanosleep(32);
                 if (++spins > (1u << 26)) { acc.fault++; break; }      // a lost CTA: do not hang the GPU
             }
         }
@@ -535,49 +626,32 @@ __device__ static inline unsigned dr_grid_barrier(unsigned int* ctl, unsigned nb
     return *s_tail;
 }
 
-template <int POLT, int MW, bool STRIPS>
+template <int POLT, bool STRIPS>
 __global__ void __launch_bounds__(DR_THREADS, 2)
 ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __shared__ DrShared sh;
     __shared__ unsigned s_tail;
     const DrPeer& S = w.dr.self;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < DR_HIST_BINS; i += DR_THREADS) sh.hist[i] = 0u;
     if (tid < 8) sh.acc[tid] = 0ull;
-    if (tid == 0) sh.cnt = 0;
+    if (tid < DR_WARPS) sh.cnt[tid] = 0;
     __syncthreads();
     DrAccum acc = {0, 0, 0, 0, 0, 0, 0};
     unsigned seg_b = st.single_round ? st.seg_begin : 0u;
     unsigned seg_e = st.single_round ? st.seg_end : __ldcg(&S.ctl[5]);     // ctl[5]: tail after the build (ss_dr_seg0_kernel)
+    const unsigned gwarp = blockIdx.x * DR_WARPS + (unsigned)warp, nwarp = gridDim.x * DR_WARPS;
     for (;;) {
         const unsigned cnt = seg_e - seg_b;
         if (cnt == 0u) break;
-        for (unsigned base = blockIdx.x * DR_THREADS; base < cnt; base += gridDim.x * DR_THREADS) {
-            const unsigned i = base + (unsigned)tid;
-            if (i < cnt) dr_turn<POLT, MW, STRIPS>(w, st, sh, acc, __ldcg(&S.queue[seg_b + i]));
-            __syncthreads();
-            const int staged = sh.cnt;                    // the same value in every thread: nobody pushes between the barriers
-            __syncthreads();
-            if (staged >= DR_PUSH_CAP / 2) {
-                const int k = min(staged, DR_PUSH_CAP);
-                if (tid == 0) sh.base = atomicAdd(&S.ctl[0], (unsigned)k);
-                __syncthreads();
-                for (int j = tid; j < k; j += DR_THREADS) S.queue[sh.base + (unsigned)j] = sh.push[j];
-                __syncthreads();
-                if (tid == 0) sh.cnt = 0;
-                __syncthreads();
-            }
+        // a warp takes 32 consecutive queue entries at a time; no CTA-wide barrier inside a round
+        for (unsigned base = gwarp * 32u; base < cnt; base += nwarp * 32u) {
+            const unsigned i = base + (unsigned)lane;
+            if (i < cnt) dr_turn<POLT, STRIPS>(w, st, sh, warp, acc, __ldcg(&S.queue[seg_b + i]));
+            __syncwarp();
+            if (sh.cnt[warp] >= DR_WARP_CAP / 2) dr_flush(w, sh, warp, lane);
         }
-        {
-            const int k = min(sh.cnt, DR_PUSH_CAP);
-            if (k > 0) {
-                if (tid == 0) sh.base = atomicAdd(&S.ctl[0], (unsigned)k);
-                __syncthreads();
-                for (int j = tid; j < k; j += DR_THREADS) S.queue[sh.base + (unsigned)j] = sh.push[j];
-                __syncthreads();
-                if (tid == 0) sh.cnt = 0;
-            }
-        }
+        dr_flush(w, sh, warp, lane);
         if (st.single_round) break;
         seg_b = seg_e;
         seg_e = dr_grid_barrier(S.ctl, st.nblocks, acc, &s_tail);
@@ -588,7 +662,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     for (int q = 0; q < 7; q++) {
         unsigned v = vals[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if ((tid & 31) == 0 && v) atomicAdd(&sh.acc[q], (unsigned long long)v);
+        if (lane == 0 && v) atomicAdd(&sh.acc[q], (unsigned long long)v);
     }
     __syncthreads();
     unsigned long long* dst[7] = {&w.acc->sum_metab, &w.acc->sum_vision, &w.acc->acted, &w.acc->deaths, &w.acc->hist_small,
@@ -600,12 +674,14 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     }
 }
 
-// every agent that was alive at the start of the step must have passed through the queue
+// every agent that was alive at the start of the step must have passed through the queue; the successor pool must
+// have held every list
 __global__ void ss_dr_check_kernel(DevWorld w) {
     if (w.dr.self.ctl[0] != (unsigned)w.acc->pending) atomicAdd(&w.acc->fault, 1ull);
+    if (w.dr.self.ctl[7]) atomicAdd(&w.acc->fault, 1ull);
     w.acc->pending = 0ull;
 }
-__global__ void ss_dr_begin_kernel(DevWorld w) { w.dr.self.ctl[0] = 0u; }
+__global__ void ss_dr_begin_kernel(DevWorld w) { w.dr.self.ctl[0] = 0u; w.dr.self.ctl[6] = 0u; }
 __global__ void ss_dr_seg0_kernel(DevWorld w) { w.dr.self.ctl[5] = w.dr.self.ctl[0]; }
 
 // ---------------------------------------------------------------------------- launchers ----
@@ -626,21 +702,21 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int POLT, int MW, bool STRIPS>
+template <int POLT, bool STRIPS>
 static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cudaStream_t s) {
     static int per_sm = 0;
     if (!per_sm) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, MW, STRIPS>, DR_THREADS, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS>, DR_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     st.nblocks = (unsigned)(per_sm * sm_count);
     if (st.single_round) {
-        ss_dr_rounds_kernel<POLT, MW, STRIPS><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
+        ss_dr_rounds_kernel<POLT, STRIPS><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
         return cudaGetLastError();
     }
     void* args[2] = {(void*)&w, (void*)&st};
-    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, MW, STRIPS>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
 }
 
 extern "C" {
@@ -650,11 +726,18 @@ size_t ss_dr_build_smem(int vmax) {
     return (size_t)SX * SY * 4 + (size_t)SX * BW * 4 + (size_t)DR_TX * DR_TY * 2;
 }
 
+cudaError_t ss_launch_dr_transpose(const DevWorld& w, cudaStream_t s) {
+    const int rows = w.dr.self.rows, n = w.n;
+    const int tiles = ((rows + 63) / 64) * ((n + 63) / 64);
+    ss_dr_transpose_kernel<<<tiles, 256, 0, s>>>(w.dr.self.mw, w.dr.self.mwx, rows, n);
+    return cudaGetLastError();
+}
+
 cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s) {
     const size_t cells = (size_t)w.dr.self.rows * w.n;
     ss_dr_mirror_kernel<<<148 * 8, 256, 0, s>>>(w, cells, flag);
     if (w.n_slots) ss_dr_flags_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w);
-    return cudaGetLastError();
+    return ss_launch_dr_transpose(w, s);
 }
 
 // tmap_storage: 128 bytes, 64-byte aligned, host memory owned by the engine (re-encoded when the lattice changes)
@@ -679,10 +762,8 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     static size_t configured = 0;
     const size_t smem = ss_dr_build_smem(w.vmax);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ss_dr_build_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ss_dr_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -698,13 +779,8 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     if (use_tma) memcpy(&tm, tmap_storage, sizeof tm);
     const bool strips = w.dr.self.rows != w.n;
     const int grid = tiles_x * ba.tiles_y;
-    if (w.dr.mwords == 4) {
-        if (strips) ss_dr_build_kernel<4, true><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-        else ss_dr_build_kernel<4, false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-    } else {
-        if (strips) ss_dr_build_kernel<16, true><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-        else ss_dr_build_kernel<16, false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-    }
+    if (strips) ss_dr_build_kernel<true><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+    else ss_dr_build_kernel<false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
     ss_dr_seg0_kernel<<<1, 1, 0, s>>>(w);
     return cudaGetLastError();
 }
@@ -716,24 +792,16 @@ cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t en
     st.iteration = iteration; st.env_time = env_time;
     st.skey = ss_step_key(w.cfg.keyed_seed, iteration);
     st.next_phase = (uint32_t)((iteration + 1) & 1);
-    const uint32_t S = 2u * (uint32_t)w.vmax + 1u;
-    st.magicS = (65536u + S - 1u) / S;
     st.single_round = single_round; st.seg_begin = seg_begin; st.seg_end = seg_end; st.nblocks = 0;
     const bool pol = w.cfg.rule_pollution != 0;
     const bool strips = w.dr.self.rows != w.n;
-    if (strips) {
-        if (w.dr.mwords == 4) return pol ? launch_rounds<1, 4, true>(w, st, sm_count, s) : launch_rounds<0, 4, true>(w, st, sm_count, s);
-        return pol ? launch_rounds<1, 16, true>(w, st, sm_count, s) : launch_rounds<0, 16, true>(w, st, sm_count, s);
-    }
-    if (w.dr.mwords == 4) return pol ? launch_rounds<1, 4, false>(w, st, sm_count, s) : launch_rounds<0, 4, false>(w, st, sm_count, s);
-    return pol ? launch_rounds<1, 16, false>(w, st, sm_count, s) : launch_rounds<0, 16, false>(w, st, sm_count, s);
+    if (strips) return pol ? launch_rounds<1, true>(w, st, sm_count, s) : launch_rounds<0, true>(w, st, sm_count, s);
+    return pol ? launch_rounds<1, false>(w, st, sm_count, s) : launch_rounds<0, false>(w, st, sm_count, s);
 }
 
 cudaError_t ss_launch_dr_check(const DevWorld& w, cudaStream_t s) {
     ss_dr_check_kernel<<<1, 1, 0, s>>>(w);
     return cudaGetLastError();
 }
-
-int ss_dr_mask_words(int vmax) { return dr_mask_words(vmax); }
 
 }  // extern "C"

@@ -28,30 +28,38 @@ struct ShardLogEntry {
 };
 
 // Dependency rounds over the whole lattice (ss_rounds.cu): per-step dependency state.
-//   mw[c]     u8   bit 7 = cell occupied, bits 0..6 = int(sugar[c]) -- the one byte an agent reads per cross cell
-//   dep[c]    u16  (two per u32 word) bits 0..14 = unresolved predecessors of the agent that STARTED the step on c,
-//                  bit 15 = "lose the turn" (Q1: the predecessor in the list order died)
-//   mask[s]   mwords x u64 per slot: successors of agent s as a bitmap over its conflict zone (start-of-step positions)
-//   queue     cells in the order their agents became ready; round k is the segment appended during round k-1
-//   alive / atrisk  bitmaps by slot (list-order predecessor lookup for Q1); q1wait[s] = {cell waiting for s's outcome, step+1}
+//   mw[c]     u8   bit 7 = cell occupied, bits 0..6 = int(sugar[c]) -- the one byte an agent reads per cross cell;
+//                  mwx is the same array transposed (index y * rows + x - x0), so that BOTH arms of a cross are
+//                  contiguous bytes: two 16-byte loads per arm instead of one 64-byte DRAM atom per cell
+//   dep[s]    u16  by slot (two per u32 word; 33 MB at 16.7 M agents: L2-resident): bits 0..14 = unresolved
+//                  predecessors, bit 15 = "lose the turn" (Q1: the predecessor in the list order died)
+//   succ[s]   64-byte record by slot: [0] = number of successors, [1..14] = successor slots (bits 24..25: the strip
+//                  that holds it, 0 self / 1 lo / 2 hi), [15] = first entry of the remaining ones in `pool`
+//   queue     slots in the order their agents became ready; round k is the segment appended during round k-1
+//   alive / atrisk  bitmaps by slot (list-order predecessor lookup for Q1); q1wait[s] = {slot waiting for s's outcome
+//                  | strip << 24, step + 1}
 struct DrPeer {                     // one strip of lattice rows [x0, x0 + rows) and its per-step state, as a kernel sees it
-    uint32_t* occw;                 // (local or peer-mapped device pointers; index (x - x0) * n + y)
+    uint32_t* occw;                 // (local or peer-mapped device pointers; cell index (x - x0) * n + y)
     uint8_t* mw;
+    uint8_t* mwx;
     double* sugar;
     double* poll;
     uint32_t* dep;
     uint32_t* queue;
-    unsigned int* ctl;              // [0] queue tail, [1] barrier count, [2] barrier generation, [3] round, [4] remote flag, ...
+    unsigned int* ctl;              // [0] queue tail, [1] barrier count, [2] barrier generation, [3..4] tail snapshots, [5] tail after the build, [6] pool tail, [7] pool overflow
+    AgentRec* agents;
     int x0, rows;
 };
 #define DR_CTL_WORDS 64
+#define DR_SUCC_INLINE 14
 struct DrState {
     DrPeer self, lo, hi;            // this strip and its ring neighbours (single strip: lo = hi = self)
-    unsigned long long* mask;
+    uint4* succ;                    // 4 x uint4 per slot
+    uint32_t* pool;
+    uint32_t pool_cap;
     uint32_t* alive;
     uint32_t* atrisk;
     uint2* q1wait;
-    int mwords;
     uint32_t queue_cap;
 };
 

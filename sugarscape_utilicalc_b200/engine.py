@@ -183,6 +183,12 @@ class Engine:
         return dict(launches=int(out[0]), passes=int(out[1]), steps=int(out[2]), path=int(out[3]),
                     syncs=int(out[4]), window=int(out[5]) & 0xffff, pass_impl=int(out[5]) >> 16)
 
+    def rounds(self):
+        """Dependency rounds (grid barriers of ss_dr_rounds_kernel) since the engine's round state was allocated."""
+        out = np.zeros(12, dtype=np.int64)
+        self._check(self._lib.ss_get_counters(self._h, _ptr(out), 12), "ss_get_counters")
+        return int(out[11])
+
     def health(self):
         """Device-side consistency counters of the lattice path: watchdog firings of the spin waits and internal
         faults (a draw loop that did not terminate, more tied candidates than the geometry allows).  Both must be 0."""

@@ -17,5 +17,5 @@ for kv in sys.argv[4:]:
 e.upload_cells(w["sugar"], w["cap"], w["pollution"])
 e.upload_agents(w["id"], w["x"], w["y"], w["vision"], w["metab"], w["sugar_agent"])
 st = e.step(steps)
-print("population", st["population"].astype(int).tolist(), e.counters())
+print("population", st["population"].astype(int).tolist(), e.counters(), "rounds", e.rounds(), e.health())
 e.close()
