@@ -76,6 +76,7 @@ struct ss_engine {
     int mirror = 0;                            // which int(sugar) mirror is current: 1 = isugar (window passes), 2 = mw (rounds)
     bool cap_fits_u7 = true;
     int use_tma = 1, tma_ok = 0;
+    int l2_persist = 1;
     alignas(64) unsigned char tmap[128];
     int solo_window_max = 0;                   // 0 = by lattice size
     int shard_rank = 0, shard_world = 1;       // multi-GPU replicas (sharded.py)
@@ -534,7 +535,7 @@ static int ensure_stats(ss_engine* e, int nsteps) {
 static void dr_free(ss_engine* e) {
     DrState& d = e->w.dr;
     cudaFree(d.self.mw); cudaFree(d.self.mwx); cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.self.ctl);
-    cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
+    cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1flag); cudaFree(d.q1wait);
     memset(&d, 0, sizeof d);
     e->dr_slots = 0;
 }
@@ -558,7 +559,8 @@ static int dr_alloc(ss_engine* e) {
     const uint64_t pool64 = std::min<uint64_t>((uint64_t)ns * 16u, (uint64_t)ns * zone) + 64;
     const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(pool64, 0xfffffff0ull);
     if (ns != e->dr_slots || pool_cap != d.pool_cap) {
-        cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1wait);
+        cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1flag); cudaFree(d.q1wait);
+        d.q1flag = nullptr;
         d.self.dep = nullptr; d.self.queue = nullptr; d.succ = nullptr; d.pool = nullptr; d.alive = nullptr; d.atrisk = nullptr; d.q1wait = nullptr;
         const size_t words = (size_t)(ns + 31) / 32 + 1;
         CK(cudaMalloc(&d.self.dep, sizeof(uint32_t) * ((size_t)ns / 2 + 2)));
@@ -567,6 +569,8 @@ static int dr_alloc(ss_engine* e) {
         CK(cudaMalloc(&d.pool, sizeof(uint32_t) * (size_t)pool_cap));
         CK(cudaMalloc(&d.alive, sizeof(uint32_t) * words));
         CK(cudaMalloc(&d.atrisk, sizeof(uint32_t) * words));
+        CK(cudaMalloc(&d.q1flag, sizeof(uint32_t) * words));
+        CK(cudaMemsetAsync(d.q1flag, 0, sizeof(uint32_t) * words, e->stream));
         CK(cudaMalloc(&d.q1wait, sizeof(uint2) * (size_t)ns));
         CK(cudaMemsetAsync(d.self.dep, 0, sizeof(uint32_t) * ((size_t)ns / 2 + 2), e->stream));
         CK(cudaMemsetAsync(d.alive, 0, sizeof(uint32_t) * words, e->stream));
@@ -574,6 +578,25 @@ static int dr_alloc(ss_engine* e) {
         CK(cudaMemsetAsync(d.q1wait, 0, sizeof(uint2) * (size_t)ns, e->stream));
         e->dr_slots = ns; d.pool_cap = pool_cap;
         if (e->mirror == 2) e->mirror = 0;
+    }
+    {   // the predecessor counters take one atomic per edge of the step's DAG: keep them in L2 (access policy window on
+        // the engine's stream; the streaming traffic of a step would otherwise evict them between two touches)
+        int max_win = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+        const size_t bytes = sizeof(uint32_t) * ((size_t)ns / 2 + 2);
+        if (e->l2_persist && max_win > 0 && max_persist > 0) {
+            const size_t win = std::min<size_t>(bytes, (size_t)max_win);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)max_persist, win));
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = d.self.dep;
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
     }
     d.queue_cap = ns;
     d.self.occw = e->w.occw; d.self.sugar = e->w.sugar; d.self.poll = e->w.poll; d.self.agents = e->w.agents;
@@ -638,12 +661,25 @@ static int dr_step(ss_engine* e, int stats_index) {
         KTimer t(e, KT_PREPARE);
         CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
         CK(ss_launch_prepare(e->w, e->iteration, 0, e->stream));
+        if (e->trace) { CK(cudaStreamSynchronize(e->stream)); fprintf(stderr, "[ss] step %lld: build\n", (long long)e->iteration); }
         CK(ss_launch_dr_build(e->w, e->iteration, e->tmap, e->tma_ok && e->use_tma, e->stream));
-        e->launches += 4;
+        e->launches += 5;
+        if (e->trace) {
+            CK(cudaStreamSynchronize(e->stream));
+            unsigned ctl[8];
+            CK(cudaMemcpy(ctl, e->w.dr.self.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[ss] step %lld: built, ready %u, pool %u, overflow %u; rounds\n", (long long)e->iteration, ctl[0], ctl[6], ctl[7]);
+        }
     }
     {
         KTimer t(e, KT_MOVE);
         CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
+        if (e->trace) {
+            CK(cudaStreamSynchronize(e->stream));
+            unsigned ctl[8];
+            CK(cudaMemcpy(ctl, e->w.dr.self.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[ss] step %lld: rounds done, queue tail %u, barriers %u\n", (long long)e->iteration, ctl[0], ctl[2]);
+        }
         CK(ss_launch_dr_check(e->w, e->stream));
         e->launches += 2; e->passes++;
     }
@@ -947,6 +983,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "solo_window") { e->solo_window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "tma") { e->use_tma = (int)value; return SS_OK; }
+    if (k == "l2_persist") { e->l2_persist = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }

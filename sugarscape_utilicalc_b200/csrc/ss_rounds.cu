@@ -6,7 +6,7 @@
 // lower execution priority.  That is a DAG over the agents' start-of-step positions; this file evaluates it level by
 // level without windows, lists, sorts or host round trips:
 //
-//   ss_dr_build_kernel   one CTA per 64 x 128-cell tile stages the occupancy words of the tile and a halo of 2*vmax
+//   ss_dr_build_kernel   one CTA per 64 x 64-cell tile stages the occupancy words of the tile and a halo of 2*vmax
 //                        cells in shared memory (TMA 2-D tile load, cp.async.bulk.tensor, for tiles that do not touch
 //                        the torus edge), turns them into (priority, vision) words + an occupancy bitmap, and one
 //                        thread per agent scans its conflict zone with the exact cross-intersection predicate:
@@ -34,7 +34,7 @@
 
 #define FULL 0xffffffffu
 #define DR_TX 64                        // tile rows (x)
-#define DR_TY 128                       // tile columns (y, contiguous in memory)
+#define DR_TY 64                        // tile columns (y, contiguous in memory)
 #define DR_BUILD_THREADS 512
 #define DR_THREADS 512                  // rounds kernel
 #define DR_WARP_CAP 128                 // staged queue entries per warp between flushes
@@ -126,65 +126,76 @@ __global__ void ss_dr_flags_kernel(DevWorld w) {
 // -------------------------------------------------------------------------------- build ----
 __device__ static inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Q1, one thread per slot: the agent before this one in the list order (the keyed order: ascending priority over the
+// living agents) is found by walking the inverse priority map over the alive bitmap; if it may starve this step, its
+// outcome decides whether this agent acts at all -- one more predecessor (q1flag) and a note for the predecessor
+// (q1wait) whom to tell.
+__global__ void ss_dr_q1_kernel(DevWorld w, OrderKey ok, uint32_t stamp) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool flag = false;
+    if (slot < w.n_slots && ((w.dr.alive[slot >> 5] >> (slot & 31)) & 1u)) {
+        for (uint32_t p = ss_priority(ok, slot); p-- > 0u;) {
+            const uint32_t s2 = ss_priority_inverse(ok, p);
+            if (s2 >= w.n_slots || !((w.dr.alive[s2 >> 5] >> (s2 & 31)) & 1u)) continue;
+            if ((w.dr.atrisk[s2 >> 5] >> (s2 & 31)) & 1u) { flag = true; w.dr.q1wait[s2] = make_uint2(slot, stamp); }
+            break;
+        }
+    }
+    const unsigned b = __ballot_sync(FULL, flag);
+    if ((threadIdx.x & 31) == 0 && (slot >> 5) < ((w.n_slots + 31) >> 5)) w.dr.q1flag[slot >> 5] = b;
+}
+
 struct DrBuildArgs {
     OrderKey ok;
-    int64_t iteration;
     int tiles_y;
     int use_tma;
 };
 
-// Scan of one agent's conflict zone on the staged tile.  emit(dx, dy, word) is called for every conflicting agent of
-// HIGHER priority (a successor); returns the number of conflicting agents of lower priority (predecessors).
-template <class Emit>
-__device__ static inline uint32_t dr_scan_zone(const uint32_t* tile, const uint32_t* bm, int SY, int BW, int V, int lr, int lq,
-                                               uint32_t pa, int a, Emit emit) {
-    const int H = 2 * V;
-    uint32_t indeg = 0;
-    for (int dx = -H; dx <= H; dx++) {
-        const int r = lr + dx, adx = abs(dx);
-        if (adx > V) {                                             // beyond the square: only the cell on the axis
-            const uint32_t cv = tile[r * SY + lq];
-            if (cv && adx <= a + (int)(cv & 31u)) { if ((cv >> 5) < pa) indeg++; else emit(dx, 0, cv); }
-            continue;
-        }
-        const int R = dx == 0 ? H : V, qlo = lq - R, qhi = lq + R;
-        for (int wq = qlo >> 5; wq <= (qhi >> 5); wq++) {
-            uint32_t bits = bm[r * BW + wq];
-            const int base = wq << 5;
-            if (base < qlo) bits &= FULL << (qlo - base);
-            if (base + 31 > qhi) bits &= FULL >> (base + 31 - qhi);
-            while (bits) {
-                const int q = base + __ffs(bits) - 1;
-                bits &= bits - 1u;
-                const int dy = q - lq;
-                if (dx == 0 && dy == 0) continue;
-                const uint32_t cv = tile[r * SY + q];
-                if (!dr_crosses_meet(dx, dy, a, (int)(cv & 31u))) continue;
-                if ((cv >> 5) < pa) indeg++; else emit(dx, dy, cv);
-            }
-        }
+// G lanes work on one agent (G = 16 while vision <= 7, two agents per warp; else 32): lane t < 2V+1 takes row
+// dx = t - V of the square part of the conflict zone (the whole row segment of the axis for dx = 0), lane 2V+1 takes
+// the two arm extensions along x (from a column bitmap).  Each lane pulls its segment of the occupancy bitmap as one
+// window word, tests the occupied cells with the exact predicate, counts predecessors and marks successors.
+template <int G> struct DrWin;
+template <> struct DrWin<16> { typedef uint32_t T; };
+template <> struct DrWin<32> { typedef unsigned long long T; };
+template <int G>
+__device__ static inline typename DrWin<G>::T dr_window(const uint32_t* row, int lo, int width) {
+    typedef typename DrWin<G>::T T;
+    const int w0 = lo >> 5, sh = lo & 31;
+    if (G == 16) {
+        const uint32_t v = __funnelshift_r(row[w0], row[w0 + 1], sh);
+        return (T)(v & (width >= 32 ? FULL : ((1u << width) - 1u)));
     }
-    return indeg;
+    const unsigned long long a = (unsigned long long)row[w0] | ((unsigned long long)row[w0 + 1] << 32);
+    unsigned long long v = a >> sh;
+    if (sh) v |= (unsigned long long)row[w0 + 2] << (64 - sh);
+    return (T)(v & (width >= 64 ? ~0ull : ((1ull << width) - 1ull)));
 }
 
-template <bool STRIPS>
+template <bool STRIPS, int G>
 __global__ void __launch_bounds__(DR_BUILD_THREADS)
 ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorMap tmap) {
+    typedef typename DrWin<G>::T WinT;
     extern __shared__ __align__(128) uint32_t sm[];
-    __shared__ int s_n, s_ready, s_fill;
+    __shared__ int s_all, s_n, s_ready, s_fill;
     __shared__ unsigned s_base;
     __shared__ __align__(8) unsigned long long s_bar;
-    const int n = w.n, V = w.vmax, H = 2 * V, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H, BW = (SY + 31) >> 5;
-    uint32_t* tile = sm;                                   // [SX][SY] occupancy words -> (priority << 5 | vision)
-    uint32_t* bm = tile + SX * SY;                         // [SX][BW] occupancy bitmap
-    uint16_t* list = (uint16_t*)(bm + SX * BW);            // interior agents: r << 8 | q  (bit 15: ready)
+    __shared__ uint32_t s_rec[DR_BUILD_THREADS / G][16];
+    const int n = w.n, V = w.vmax, H = 2 * V, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H;
+    const int BW = ((SY + 31) >> 5) + 2, BWT = ((SX + 31) >> 5) + 2;
+    uint32_t* tileS = sm;                                  // [SX][SY] occupancy words as loaded (slot | vision | flags)
+    uint32_t* tileP = tileS + SX * SY;                     // [SX][SY] priority << 5 | vision, 0 = free
+    uint32_t* bm = tileP + SX * SY;                        // [SX][BW]  occupancy bitmap by row
+    uint32_t* bmt = bm + SX * BW;                          // [SY][BWT] ... and by column
+    uint16_t* alist = (uint16_t*)(bmt + SY * BWT);         // every agent of tile + halo: r * SY + q
+    uint16_t* ilist = alist + SX * SY;                     // the tile's own agents: r << 7 | q  (bit 15: ready)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = DR_BUILD_THREADS / 32;
     const DrPeer& S = w.dr.self;
     const int tx = blockIdx.x / ba.tiles_y, ty = blockIdx.x - tx * ba.tiles_y;
     const int x0 = S.x0 + tx * DR_TX, y0 = ty * DR_TY;     // lattice coordinates of the tile's first interior cell
     const int ex = min(DR_TX, S.x0 + S.rows - x0), ey = min(DR_TY, n - y0);      // interior extent
-    if (tid == 0) { s_n = 0; s_ready = 0; s_fill = 0; }
-    for (int i = tid; i < SX * BW; i += DR_BUILD_THREADS) bm[i] = 0u;
+    if (tid == 0) { s_all = 0; s_n = 0; s_ready = 0; s_fill = 0; }
+    for (int i = tid; i < SX * BW + SY * BWT; i += DR_BUILD_THREADS) bm[i] = 0u;
     // the tile and its halo lie inside this strip and inside [0, n) in y: one TMA box; otherwise plain loads with wraps
     const bool interior = ba.use_tma && x0 - H >= S.x0 && x0 + DR_TX + H <= S.x0 + S.rows && y0 - H >= 0 && y0 + DR_TY + H <= n;
     if (interior) {
@@ -198,7 +209,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                ::"r"(smem_u32(tile)), "l"(&tmap), "r"(y0 - H), "r"(x0 - H - S.x0), "r"(smem_u32(&s_bar)) : "memory");
+                ::"r"(smem_u32(tileS)), "l"(&tmap), "r"(y0 - H), "r"(x0 - H - S.x0), "r"(smem_u32(&s_bar)) : "memory");
         }
         uint32_t done = 0;                                 // everybody waits for the box (phase 0)
         while (!done) {
@@ -212,92 +223,139 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             for (int q = lane; q < SY; q += 32) {
                 const int gy = ss_wrap(y0 - H + q, n);
                 const DrLoc L = dr_loc<STRIPS>(w, gx, gy);
-                tile[r * SY + q] = __ldcg(&DR_F(occw, L)[L.idx]);
+                tileS[r * SY + q] = __ldcg(&DR_F(occw, L)[L.idx]);
             }
         }
         __syncthreads();
     }
-    // occupancy words -> (priority, vision), bitmap, list of the tile's own agents
+    // bitmaps and the lists of occupied cells
     for (int r = warp; r < SX; r += nwarps) {
         const bool row_in = r >= H && r < H + ex;
-        for (int q = lane; q < SY; q += 32) {
-            const uint32_t ow = tile[r * SY + q];
-            if (!ow) continue;
-            tile[r * SY + q] = (ss_priority(ba.ok, occ_slot(ow)) << 5) | (uint32_t)occ_vision(ow);
-            atomicOr(&bm[r * BW + (q >> 5)], 1u << (q & 31));
-            if (row_in && q >= H && q < H + ey) list[atomicAdd(&s_n, 1)] = (uint16_t)((r << 8) | q);
+        for (int q0 = 0; q0 < SY; q0 += 32) {
+            const int q = q0 + lane;
+            const uint32_t ow = q < SY ? tileS[r * SY + q] : 0u;
+            const unsigned m = __ballot_sync(FULL, ow != 0u);
+            if (!m) continue;
+            if (lane == 0) bm[r * BW + (q0 >> 5)] = m;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_all, __popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            const bool mine = ow != 0u && row_in && q >= H && q < H + ey;
+            const unsigned mi = __ballot_sync(FULL, mine);
+            int ibase = 0;
+            if (mi) { if (lane == 0) ibase = atomicAdd(&s_n, __popc(mi)); ibase = __shfl_sync(FULL, ibase, 0); }
+            if (ow != 0u) {
+                alist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * SY + q);
+                atomicOr(&bmt[q * BWT + (r >> 5)], 1u << (r & 31));
+                if (mine) ilist[ibase + __popc(mi & ((1u << lane) - 1u))] = (uint16_t)((r << 7) | q);
+            } else if (q < SY) tileP[r * SY + q] = 0u;
         }
     }
     __syncthreads();
+    // priorities of the occupied cells (every lane busy)
+    for (int k = tid; k < s_all; k += DR_BUILD_THREADS) {
+        const int pos = alist[k];
+        const uint32_t ow = tileS[pos];
+        tileP[pos] = (ss_priority(ba.ok, occ_slot(ow)) << 5) | (uint32_t)occ_vision(ow);
+    }
+    __syncthreads();
     const int nl = s_n;
-    const uint32_t stamp = (uint32_t)(ba.iteration + 1);
-    for (int k = tid; k < nl; k += DR_BUILD_THREADS) {
-        const int lr = list[k] >> 8, lq = list[k] & 255;
-        const uint32_t me = tile[lr * SY + lq];
-        const uint32_t pa = me >> 5;
-        const int a = (int)(me & 31u);
-        const uint32_t slot = ss_priority_inverse(ba.ok, pa);
-        const int row = x0 + lr - H - S.x0;                        // strip-local row of the agent
-        // successors: the first DR_SUCC_INLINE in the record, the rest in a run of the pool
-        uint32_t rec[16];
-        uint32_t nsucc = 0;
-        auto which_of = [&](int dx) -> uint32_t {
-            if (!STRIPS) return 0u;
-            const int r2 = row + dx;
-            return r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u);
-        };
-        uint32_t indeg = dr_scan_zone(tile, bm, SY, BW, V, lr, lq, pa, a, [&](int dx, int, uint32_t cv) {
-            if (nsucc < DR_SUCC_INLINE) rec[1 + nsucc] = ss_priority_inverse(ba.ok, cv >> 5) | (which_of(dx) << 24);
-            nsucc++;
-        });
-        rec[15] = 0u;
-        if (nsucc > DR_SUCC_INLINE) {
-            const uint32_t extra = nsucc - DR_SUCC_INLINE;
-            const uint32_t at = atomicAdd(&S.ctl[6], extra);
-            rec[15] = at;
-            if (at + extra <= w.dr.pool_cap) {
-                uint32_t i = 0;
-                dr_scan_zone(tile, bm, SY, BW, V, lr, lq, pa, a, [&](int dx, int, uint32_t cv) {
-                    if (i >= DR_SUCC_INLINE) w.dr.pool[at + i - DR_SUCC_INLINE] = ss_priority_inverse(ba.ok, cv >> 5) | (which_of(dx) << 24);
-                    i++;
-                });
-            } else {
-                atomicAdd(&S.ctl[7], 1u);                          // pool exhausted: reported as a fault by the step
-                nsucc = DR_SUCC_INLINE;
+    constexpr int GROUPS = DR_BUILD_THREADS / G;
+    const int grp = tid / G, gl = tid & (G - 1);
+    const unsigned gmask = G == 32 ? FULL : (0xffffu << (lane & 16));
+    uint32_t* myrec = s_rec[grp];
+    for (int k0 = 0; k0 < nl; k0 += GROUPS) {
+        const int k = k0 + grp;
+        const bool have = k < nl;                          // (uniform within a group)
+        int lr = 0, lq = 0, a = 0;
+        uint32_t pa = 0, slot = 0;
+        if (have) {
+            const int e = ilist[k];
+            lr = e >> 7; lq = e & 127;
+            const uint32_t me = tileP[lr * SY + lq];
+            pa = me >> 5; a = (int)(me & 31u);
+            slot = occ_slot(tileS[lr * SY + lq]);
+        }
+        // lane task: a row of the square (gl <= 2V), or the x-axis column (gl == 2V + 1)
+        const bool rowtask = gl <= 2 * V, coltask = gl == 2 * V + 1;
+        const int dxr = gl - V;
+        WinT win = 0;
+        int R = 0;
+        if (have && rowtask) {
+            R = dxr == 0 ? H : V;
+            win = dr_window<G>(&bm[(lr + dxr) * BW], lq - R, 2 * R + 1);
+            if (dxr == 0) win &= ~((WinT)1 << R);                              // not the agent itself
+        } else if (have && coltask) {
+            R = H;
+            win = dr_window<G>(&bmt[lq * BWT], lr - H, 2 * H + 1);
+            win &= ~((((WinT)1 << (2 * V + 1)) - (WinT)1) << (H - V));          // the square's rows are taken by the row lanes
+        }
+        uint32_t npred = 0, nsucc_l = 0;
+        WinT smask = 0;
+        {
+            WinT bits = win;
+            while (bits) {
+                const int j = G == 16 ? __ffs((uint32_t)bits) - 1 : __ffsll((long long)bits) - 1;
+                bits &= bits - (WinT)1;
+                const int dx = rowtask ? dxr : j - R, dy = rowtask ? j - R : 0;
+                const uint32_t cv = tileP[(lr + dx) * SY + lq + dy];
+                if (!dr_crosses_meet(dx, dy, a, (int)(cv & 31u))) continue;
+                if ((cv >> 5) < pa) npred++; else { nsucc_l++; smask |= (WinT)1 << j; }
             }
         }
-        rec[0] = nsucc;
-        // Q1: the agent before this one in the list order (the keyed order: ascending priority over the living
-        // agents); if it may starve, its outcome decides whether this agent acts at all
-        if (w.cfg.rule_can_starve) {
-            for (uint32_t p = pa; p-- > 0u;) {
-                const uint32_t s2 = ss_priority_inverse(ba.ok, p);
-                if (s2 >= w.n_slots || !((__ldg(&w.dr.alive[s2 >> 5]) >> (s2 & 31)) & 1u)) continue;
-                if ((__ldg(&w.dr.atrisk[s2 >> 5]) >> (s2 & 31)) & 1u) {
-                    indeg++;
-                    w.dr.q1wait[s2] = make_uint2(slot, stamp);
-                }
-                break;
-            }
-        }
-        reinterpret_cast<uint16_t*>(S.dep)[slot] = (uint16_t)indeg;
-        uint4* sp = &w.dr.succ[(size_t)slot * 4];
-        const int used = 1 + (int)min(nsucc, (uint32_t)DR_SUCC_INLINE);
+        // group totals and this lane's offset into the successor list
+        uint32_t off = nsucc_l, preds = npred;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            // entries past the list's end are never read: skip the stores of whole unused quarters
-            if (i * 4 < used || (i == 3 && nsucc > DR_SUCC_INLINE)) sp[i] = make_uint4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+        for (int o = 1; o < G; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(gmask, off, o, G);
+            if (gl >= o) off += t;
         }
-        if (indeg == 0) { list[k] |= 0x8000u; atomicAdd(&s_ready, 1); }
+        const uint32_t nsucc = __shfl_sync(gmask, off, G - 1, G);
+        off -= nsucc_l;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) preds += __shfl_xor_sync(gmask, preds, o, G);
+        uint32_t at = 0;
+        if (nsucc > DR_SUCC_INLINE) {
+            if (gl == 0) at = atomicAdd(&S.ctl[6], nsucc - DR_SUCC_INLINE);
+            at = __shfl_sync(gmask, at, 0, G);
+        }
+        const bool pool_ok = nsucc <= DR_SUCC_INLINE || at + (nsucc - DR_SUCC_INLINE) <= w.dr.pool_cap;
+        {
+            const int row = x0 + lr - H - S.x0;                                 // strip-local row of the agent
+            WinT bits = smask;
+            while (bits) {
+                const int j = G == 16 ? __ffs((uint32_t)bits) - 1 : __ffsll((long long)bits) - 1;
+                bits &= bits - (WinT)1;
+                const int dx = rowtask ? dxr : j - R, dy = rowtask ? j - R : 0;
+                uint32_t ent = occ_slot(tileS[(lr + dx) * SY + lq + dy]);
+                if (STRIPS) { const int r2 = row + dx; ent |= (r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u)) << 24; }
+                if (off < DR_SUCC_INLINE) myrec[1 + off] = ent;
+                else if (pool_ok) w.dr.pool[at + off - DR_SUCC_INLINE] = ent;
+                off++;
+            }
+        }
+        if (have && gl == 0) {
+            if (!pool_ok) atomicAdd(&S.ctl[7], 1u);                             // pool exhausted: reported as a fault by the step
+            myrec[0] = pool_ok ? nsucc : (uint32_t)DR_SUCC_INLINE;
+            myrec[15] = at;
+            const uint32_t indeg = preds + ((__ldg(&w.dr.q1flag[slot >> 5]) >> (slot & 31)) & 1u);
+            reinterpret_cast<uint16_t*>(S.dep)[slot] = (uint16_t)indeg;
+            if (indeg == 0) { ilist[k] |= 0x8000u; atomicAdd(&s_ready, 1); }
+        }
+        __syncwarp(gmask);
+        // the record: only the quarters the list reaches
+        if (have && gl < 4 && (gl * 4 < 1 + (int)min(nsucc, (uint32_t)DR_SUCC_INLINE) || (gl == 3 && nsucc > DR_SUCC_INLINE)))
+            w.dr.succ[(size_t)slot * 4 + gl] = make_uint4(myrec[4 * gl], myrec[4 * gl + 1], myrec[4 * gl + 2], myrec[4 * gl + 3]);
+        __syncwarp(gmask);
     }
     __syncthreads();
     if (tid == 0 && s_ready) s_base = atomicAdd(&S.ctl[0], (unsigned)s_ready);
     __syncthreads();
     if (s_ready) {
         for (int k = tid; k < nl; k += DR_BUILD_THREADS) {
-            if (!(list[k] & 0x8000u)) continue;
-            const int lr = (list[k] >> 8) & 127, lq = list[k] & 255;
-            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = ss_priority_inverse(ba.ok, tile[lr * SY + lq] >> 5);
+            if (!(ilist[k] & 0x8000u)) continue;
+            const int lr = (ilist[k] >> 7) & 255, lq = ilist[k] & 127;
+            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = occ_slot(tileS[lr * SY + lq]);
         }
     }
 }
@@ -722,8 +780,8 @@ static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cud
 extern "C" {
 
 size_t ss_dr_build_smem(int vmax) {
-    const int H = 2 * vmax, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H, BW = (SY + 31) >> 5;
-    return (size_t)SX * SY * 4 + (size_t)SX * BW * 4 + (size_t)DR_TX * DR_TY * 2;
+    const int H = 2 * vmax, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H, BW = ((SY + 31) >> 5) + 2, BWT = ((SX + 31) >> 5) + 2;
+    return (size_t)SX * SY * 8 + ((size_t)SX * BW + (size_t)SY * BWT) * 4 + (size_t)SX * SY * 2 + (size_t)DR_TX * DR_TY * 2 + 16;
 }
 
 cudaError_t ss_launch_dr_transpose(const DevWorld& w, cudaStream_t s) {
@@ -762,25 +820,32 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     static size_t configured = 0;
     const size_t smem = ss_dr_build_smem(w.vmax);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ss_dr_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ss_dr_build_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     ss_dr_begin_kernel<<<1, 1, 0, s>>>(w);
     DrBuildArgs ba;
     ba.ok = ss_order_key(ss_step_key(w.cfg.keyed_seed, iteration), w.half);
-    ba.iteration = iteration;
     ba.tiles_y = (w.n + DR_TY - 1) / DR_TY;
     ba.use_tma = use_tma;
+    if (w.cfg.rule_can_starve && w.n_slots) ss_dr_q1_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w, ba.ok, (uint32_t)(iteration + 1));
     const int tiles_x = (w.dr.self.rows + DR_TX - 1) / DR_TX;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     if (use_tma) memcpy(&tm, tmap_storage, sizeof tm);
     const bool strips = w.dr.self.rows != w.n;
     const int grid = tiles_x * ba.tiles_y;
-    if (strips) ss_dr_build_kernel<true><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-    else ss_dr_build_kernel<false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+    if (w.vmax <= 7) {
+        if (strips) ss_dr_build_kernel<true, 16><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+        else ss_dr_build_kernel<false, 16><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+    } else {
+        if (strips) ss_dr_build_kernel<true, 32><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+        else ss_dr_build_kernel<false, 32><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+    }
     ss_dr_seg0_kernel<<<1, 1, 0, s>>>(w);
     return cudaGetLastError();
 }

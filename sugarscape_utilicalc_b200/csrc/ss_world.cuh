@@ -59,6 +59,7 @@ struct DrState {
     uint32_t pool_cap;
     uint32_t* alive;
     uint32_t* atrisk;
+    uint32_t* q1flag;               // bitmap by slot: the list-order predecessor may starve this step
     uint2* q1wait;
     uint32_t queue_cap;
 };
