@@ -17,6 +17,8 @@ cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_t
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1, cudaStream_t s);
 size_t ss_dr_build_smem(int vmax);
 cudaError_t ss_launch_dr_transpose(const DevWorld& w, cudaStream_t s);
+cudaError_t ss_launch_dr_canon(const DevWorld& w, cudaStream_t s);
+cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, cudaStream_t s);
 cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_dr_encode_tmap(const DevWorld& w, void* tmap_storage, int* ok);
 cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void* tmap_storage, int use_tma, cudaStream_t s);
@@ -75,6 +77,7 @@ struct ss_engine {
     uint32_t dr_slots = 0;                     // allocation size of the dependency-round state
     int mirror = 0;                            // which int(sugar) mirror is current: 1 = isugar (window passes), 2 = mw (rounds)
     bool cap_fits_u7 = true;
+    bool dr_dirty = false;                      // sugar / occw hold what the rounds tidy lazily (dr_tidy)
     int use_tma = 1, tma_ok = 0;
     int l2_persist = 1;
     alignas(64) unsigned char tmap[128];
@@ -205,6 +208,7 @@ extern "C" void ss_destroy(ss_engine* e) {
 
 static int choose_path(ss_engine* e);
 static int dr_alloc(ss_engine* e);
+static int dr_tidy(ss_engine* e);
 static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, double* d_f64, int* d_chk);
 
 // the cell arrays are in place on the device: derive what the kernels keep beside them
@@ -227,6 +231,7 @@ static int finish_cells(ss_engine* e) {
 extern "C" int ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const double* pollution) {
     if (!e || !sugar || !cap) return set_err(e, SS_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));
+    { const int rc = dr_tidy(e); if (rc) return rc; }
     const size_t cb = e->cells * sizeof(double);
     CK(cudaMemcpyAsync(e->w.sugar, sugar, cb, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->w.cap, cap, cb, cudaMemcpyHostToDevice, e->stream));
@@ -336,6 +341,7 @@ extern "C" int ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, cons
     if (!e || n < 0 || (n > 0 && (!id || !x || !y || !vision || !metab || !sugar)))
         return set_err(e, SS_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));
+    { const int rc = dr_tidy(e); if (rc) return rc; }
     // stage the six View.agents columns; argument checks, the agent store and the occupancy words are built on the device
     const size_t nn = (size_t)std::max(n, 1);
     int32_t* d_i32 = nullptr;
@@ -464,6 +470,7 @@ extern "C" int ss_init_world(ss_engine* e, const ss_init_params* p) {
         if (p->childbearing[s][1] < p->childbearing[s][0] || p->childbearing[s][3] < p->childbearing[s][2])
             return set_err(e, SS_ERR_ARG, "empty fertility range in ss_init_params");
     CK(cudaSetDevice(e->device));
+    { const int rc = dr_tidy(e); if (rc) return rc; }
     const int N = e->w.n;
     double D[4] = {1, 1, 1, 1};
     for (int s = 0; s < p->n_sites; s++) {                                              // environment.py:118
@@ -595,7 +602,14 @@ static int dr_alloc(ss_engine* e) {
             av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            if (cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+            const cudaError_t pe = cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            if (pe != cudaSuccess) cudaGetLastError();
+            if (e->trace) {
+                size_t lim = 0;
+                cudaDeviceGetLimit(&lim, cudaLimitPersistingL2CacheSize);
+                fprintf(stderr, "[ss] L2 window: max window %d, max persisting %d, limit now %zu, window %zu bytes, hit ratio %.3f, rc %d\n",
+                        max_win, max_persist, lim, win, av.accessPolicyWindow.hitRatio, (int)pe);
+            }
         }
     }
     d.queue_cap = ns;
@@ -612,9 +626,9 @@ static int env_phase(ss_engine* e) {
         KTimer t(e, KT_GROW);
         // the growback refreshes the int(sugar) mirror that is current (cell words of the rounds / isugar bytes)
         if (e->cfg.rule_grow) {
-            CK(ss_launch_grow(e->w, e->iteration, e->sm_count, e->mirror == 2, e->stream));
+            if (e->mirror == 2) CK(ss_launch_dr_grow(e->w, e->iteration, e->stream));       // + both layouts of the cell bytes
+            else CK(ss_launch_grow(e->w, e->iteration, e->sm_count, 0, e->stream));
             e->launches++;
-            if (e->mirror == 2) { CK(ss_launch_dr_transpose(e->w, e->stream)); e->launches++; }     // the x-arm copy of the cell bytes
         }
     }
     if (e->cfg.rule_pollution && e->iteration >= e->cfg.diffusion_start_time &&
@@ -645,8 +659,19 @@ static void pass_geometry(ss_engine* e, int p, PassGeom* out) {
     *out = g;
 }
 
+// the rounds leave harvested cells' f64 sugar and vacated cells' occupancy words to be tidied lazily (ss_rounds.cu):
+// do it before anything but the rounds reads them
+static int dr_tidy(ss_engine* e) {
+    if (!e->dr_dirty) return SS_OK;
+    CK(ss_launch_dr_canon(e->w, e->stream));
+    e->launches++;
+    e->dr_dirty = false;
+    return SS_OK;
+}
+
 // one timestep as dependency rounds over the whole lattice: no window passes, no host round trips
 static int dr_step(ss_engine* e, int stats_index) {
+    e->dr_dirty = true;
     if (e->mirror != 2) {           // after an upload or a change of path: cell words, alive / at-risk bitmaps, OCC_RISK flags
         int flag = 0;
         CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
@@ -694,6 +719,7 @@ static int dr_step(ss_engine* e, int stats_index) {
 static int lattice_step(ss_engine* e, int stats_index) {
     if (e->pass_impl == 3) return dr_step(e, stats_index);
     if (e->mirror != 1) {           // the window passes read the isugar byte mirror
+        { const int rc = dr_tidy(e); if (rc) return rc; }
         CK(ss_launch_isugar(e->w, e->d_flags, e->stream));
         e->launches++;
         e->mirror = 1;
@@ -760,6 +786,7 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     CK(cudaSetDevice(e->device));
     int rc = ensure_stats(e, nsteps);
     if (rc) return rc;
+    if (e->path != PATH_LATTICE) { rc = dr_tidy(e); if (rc) return rc; if (e->mirror == 2) e->mirror = 0; }
     CK(cudaEventRecord(e->evs, e->stream));
     if (e->path == PATH_SERIAL_FUSED) {
         KTimer t(e, KT_SERIAL);
@@ -853,6 +880,7 @@ extern "C" int ss_agent_count(ss_engine* e) {
 extern "C" int ss_download_cells(ss_engine* e, double* sugar, double* cap, double* pollution, int32_t* occ_id) {
     if (!e) return set_err(e, SS_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));
+    { const int rc = dr_tidy(e); if (rc) return rc; }
     const size_t cb = e->cells * sizeof(double);
     if (sugar) CK(cudaMemcpyAsync(sugar, e->w.sugar, cb, cudaMemcpyDeviceToHost, e->stream));
     if (cap) CK(cudaMemcpyAsync(cap, e->w.cap, cb, cudaMemcpyDeviceToHost, e->stream));

@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "ss_world.cuh"
@@ -100,6 +101,96 @@ ss_dr_transpose_kernel(const uint8_t* __restrict__ mw, uint8_t* __restrict__ mwx
     for (int k = ty; k < 64; k += 4)
         if (y0 + k < n && r0 + tx < rows) mwx[(size_t)(y0 + k) * rows + r0 + tx] = t[tx][k];
 }
+// The turns leave two things to be tidied lazily: a harvested cell keeps its old f64 sugar and carries the marker 127
+// in its byte instead (the next growback -- or this kernel -- takes the sugar as 0), and a cell an agent left keeps
+// its occupancy word (the byte's occupied bit is what counts).  This kernel makes sugar / occw canonical again: before
+// a download and before any other path reads them.
+#define DR_HARVESTED 127u
+__global__ void ss_dr_canon_kernel(DevWorld w, size_t cells) {
+    const DrPeer& S = w.dr.self;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t b = S.mw[c];
+        if (!(b & 0x80)) S.occw[c] = 0u;
+        if ((b & 0x7f) == DR_HARVESTED) {
+            S.sugar[c] = 0.0;
+            const size_t r = c / (size_t)w.n, y = c - r * (size_t)w.n;
+            S.mw[c] = b & 0x80;
+            S.mwx[y * (size_t)S.rows + r] = b & 0x80;
+        }
+    }
+}
+// environment.py:133-155 growback (whole lattice or the two season rectangles) on 64 x 64-cell tiles, fused with the
+// refresh of the cell bytes in both layouts: 8 + 8 + 1 bytes read, 8 + 1 + 1 written per cell.
+struct DrGrowArgs {
+    int seasons;
+    double alpha, alpha_north, alpha_south;
+};
+__global__ void __launch_bounds__(256)
+ss_dr_grow_kernel(DevWorld w, DrGrowArgs ga) {
+    __shared__ uint8_t t[64][68];
+    const DrPeer& S = w.dr.self;
+    const int n = w.n, rows = S.rows;
+    const int tiles_y = (n + 63) >> 6;
+    const int bx = blockIdx.x / tiles_y, by = blockIdx.x - bx * tiles_y;
+    const int r0 = bx << 6, y0 = by << 6;
+    const int32_t* rn = w.cfg.season_north;
+    const int32_t* rs = w.cfg.season_south;
+    const int n_imin = max(rn[0], 0), n_jmin = max(rn[1], 0), n_imax = min(rn[2] + 1, n), n_jmax = min(rn[3] + 1, n);
+    const int s_imin = max(rs[0], 0), s_jmin = max(rs[1], 0), s_imax = min(rs[2] + 1, n), s_jmax = min(rs[3] + 1, n);
+    const int tq = (threadIdx.x & 31) * 2, tr = threadIdx.x >> 5;
+    const bool vec = (n & 1) == 0;
+    for (int k = tr; k < 64; k += 8) {
+        const int r = r0 + k;
+        if (r >= rows) break;
+        const int x = S.x0 + r;
+        const size_t c = (size_t)r * n + y0 + tq;
+        double sv[2] = {0.0, 0.0}, cv[2] = {0.0, 0.0};
+        uint8_t bv[2] = {0, 0};
+        const bool in0 = y0 + tq < n, in1 = y0 + tq + 1 < n;
+        if (vec && in1) {
+            const double2 s2 = *reinterpret_cast<const double2*>(&S.sugar[c]);
+            const double2 c2 = __ldcs(reinterpret_cast<const double2*>(&w.cap[c]));
+            const uchar2 b2 = *reinterpret_cast<const uchar2*>(&S.mw[c]);
+            sv[0] = s2.x; sv[1] = s2.y; cv[0] = c2.x; cv[1] = c2.y; bv[0] = b2.x; bv[1] = b2.y;
+        } else {
+            if (in0) { sv[0] = S.sugar[c]; cv[0] = w.cap[c]; bv[0] = S.mw[c]; }
+            if (in1) { sv[1] = S.sugar[c + 1]; cv[1] = w.cap[c + 1]; bv[1] = S.mw[c + 1]; }
+        }
+        bool grew[2] = {false, false};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int y = y0 + tq + u;
+            double s = (bv[u] & 0x7f) == DR_HARVESTED ? 0.0 : sv[u];
+            if (ga.seasons) {
+                const bool in_n = x >= n_imin && x < n_imax && y >= n_jmin && y < n_jmax;
+                const bool in_s = x >= s_imin && x < s_imax && y >= s_jmin && y < s_jmax;
+                if (in_n) { const double v = s + ga.alpha_north; s = v <= cv[u] ? v : cv[u]; }
+                if (in_s) { const double v = s + ga.alpha_south; s = v <= cv[u] ? v : cv[u]; }
+                grew[u] = in_n || in_s;
+            } else {
+                const double v = s + ga.alpha; s = v <= cv[u] ? v : cv[u];
+                grew[u] = true;
+            }
+            if (grew[u]) { sv[u] = s; bv[u] = (uint8_t)((bv[u] & 0x80) | (uint8_t)(int)s); }
+        }
+        if (vec && in1) {
+            if (grew[0] || grew[1]) {
+                // (a cell that did not grow keeps its stale sugar under the harvested marker: write back what was read)
+                *reinterpret_cast<double2*>(&S.sugar[c]) = make_double2(sv[0], sv[1]);
+                *reinterpret_cast<uchar2*>(&S.mw[c]) = make_uchar2(bv[0], bv[1]);
+            }
+        } else {
+            if (in0 && grew[0]) { S.sugar[c] = sv[0]; S.mw[c] = bv[0]; }
+            if (in1 && grew[1]) { S.sugar[c + 1] = sv[1]; S.mw[c + 1] = bv[1]; }
+        }
+        t[k][tq] = bv[0]; t[k][tq + 1] = bv[1];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int k = ty; k < 64; k += 4)
+        if (y0 + k < n && r0 + tx < rows) S.mwx[(size_t)(y0 + k) * rows + r0 + tx] = t[tx][k];
+}
+
 // alive / at-risk bitmaps and the ATTR_RISK flag from the agent store (after an upload).
 // AT RISK = the agent starves this step unless it harvests something: sugar - metabolism <= 0.1 before its turn
 // (sugarscape.py:569, 306-309; agent.py:224-229).  Everybody else survives whatever happens, so only at-risk agents
@@ -151,18 +242,19 @@ struct DrBuildArgs {
     int use_tma;
 };
 
-// G lanes work on one agent (G = 16 while vision <= 7, two agents per warp; else 32): lane t < 2V+1 takes row
-// dx = t - V of the square part of the conflict zone (the whole row segment of the axis for dx = 0), lane 2V+1 takes
-// the two arm extensions along x (from a column bitmap).  Each lane pulls its segment of the occupancy bitmap as one
-// window word, tests the occupied cells with the exact predicate, counts predecessors and marks successors.
-template <int G> struct DrWin;
-template <> struct DrWin<16> { typedef uint32_t T; };
-template <> struct DrWin<32> { typedef unsigned long long T; };
-template <int G>
-__device__ static inline typename DrWin<G>::T dr_window(const uint32_t* row, int lo, int width) {
-    typedef typename DrWin<G>::T T;
+// Conflict graph of one tile.  The work is split by its shape: the uniform part -- pulling the occupied cells of an
+// agent's conflict zone out of the row / column bitmaps -- runs one THREAD per agent (a warp takes up to 32 agents);
+// the irregular part -- one (agent, occupied cell) pair each: exact predicate, priorities, predecessor or successor --
+// runs one LANE per pair on the warp's pair list in shared memory, so every lane is busy whatever the local density.
+// WIDE = vision > 7 (64-bit windows, 32-bit pair entries).
+template <bool WIDE> struct DrWide;
+template <> struct DrWide<false> { typedef uint32_t Win; typedef uint16_t Pair; enum { SHIFT = 5 }; };
+template <> struct DrWide<true> { typedef unsigned long long Win; typedef uint32_t Pair; enum { SHIFT = 7 }; };
+template <bool WIDE>
+__device__ static inline typename DrWide<WIDE>::Win dr_window(const uint32_t* row, int lo, int width) {
+    typedef typename DrWide<WIDE>::Win T;
     const int w0 = lo >> 5, sh = lo & 31;
-    if (G == 16) {
+    if (!WIDE) {
         const uint32_t v = __funnelshift_r(row[w0], row[w0 + 1], sh);
         return (T)(v & (width >= 32 ? FULL : ((1u << width) - 1u)));
     }
@@ -171,24 +263,29 @@ __device__ static inline typename DrWin<G>::T dr_window(const uint32_t* row, int
     if (sh) v |= (unsigned long long)row[w0 + 2] << (64 - sh);
     return (T)(v & (width >= 64 ? ~0ull : ((1ull << width) - 1ull)));
 }
+template <bool WIDE> __device__ static inline int dr_popc(typename DrWide<WIDE>::Win v) { return WIDE ? __popcll((unsigned long long)v) : __popc((uint32_t)v); }
+template <bool WIDE> __device__ static inline int dr_ffs(typename DrWide<WIDE>::Win v) { return WIDE ? __ffsll((long long)v) - 1 : __ffs((uint32_t)v) - 1; }
 
-template <bool STRIPS, int G>
+#define DR_PAIR_CAP 1024                // pair list entries per warp
+template <bool STRIPS, bool WIDE>
 __global__ void __launch_bounds__(DR_BUILD_THREADS)
 ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorMap tmap) {
-    typedef typename DrWin<G>::T WinT;
+    typedef typename DrWide<WIDE>::Win WinT;
+    typedef typename DrWide<WIDE>::Pair PairT;
+    constexpr int PS = DrWide<WIDE>::SHIFT;                // bits per coordinate in a pair entry
     extern __shared__ __align__(128) uint32_t sm[];
     __shared__ int s_all, s_n, s_ready, s_fill;
     __shared__ unsigned s_base;
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_rec[DR_BUILD_THREADS / G][16];
+    __shared__ uint32_t s_cnt[DR_BUILD_THREADS / 32][2][32];   // per warp and agent of the batch: predecessors, successors
     const int n = w.n, V = w.vmax, H = 2 * V, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H;
-    const int BW = ((SY + 31) >> 5) + 2, BWT = ((SX + 31) >> 5) + 2;
-    uint32_t* tileS = sm;                                  // [SX][SY] occupancy words as loaded (slot | vision | flags)
-    uint32_t* tileP = tileS + SX * SY;                     // [SX][SY] priority << 5 | vision, 0 = free
+    const int BW = ((SY + 31) >> 5) + (WIDE ? 2 : 1), BWT = ((SX + 31) >> 5) + (WIDE ? 2 : 1);
+    uint32_t* tileS = sm;                                  // [SX][SY] occupancy words (slot | vision | flags), 0 = free
+    uint32_t* tileP = tileS + SX * SY;                     // [SX][SY] priority << 5 | vision
     uint32_t* bm = tileP + SX * SY;                        // [SX][BW]  occupancy bitmap by row
     uint32_t* bmt = bm + SX * BW;                          // [SY][BWT] ... and by column
-    uint16_t* alist = (uint16_t*)(bmt + SY * BWT);         // every agent of tile + halo: r * SY + q
-    uint16_t* ilist = alist + SX * SY;                     // the tile's own agents: r << 7 | q  (bit 15: ready)
+    uint16_t* ilist = (uint16_t*)(bmt + SY * BWT);         // the tile's own agents: r << 7 | q  (bit 15: ready)
+    uint16_t* alist = ilist + DR_TX * DR_TY;               // every agent of tile + halo: r * SY + q; later the warps' pair lists
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = DR_BUILD_THREADS / 32;
     const DrPeer& S = w.dr.self;
     const int tx = blockIdx.x / ba.tiles_y, ty = blockIdx.x - tx * ba.tiles_y;
@@ -216,6 +313,11 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
         }
+        // a word counts only where the cell byte says "occupied" (the turns leave the words of vacated cells behind)
+        for (int r = warp; r < SX; r += nwarps) {
+            const uint8_t* src = S.mw + (size_t)(x0 - H - S.x0 + r) * n + (y0 - H);
+            for (int q = lane; q < SY; q += 32) if (!(__ldcg(&src[q]) & 0x80)) tileS[r * SY + q] = 0u;
+        }
     } else {
         __syncthreads();
         for (int r = warp; r < SX; r += nwarps) {
@@ -223,11 +325,11 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             for (int q = lane; q < SY; q += 32) {
                 const int gy = ss_wrap(y0 - H + q, n);
                 const DrLoc L = dr_loc<STRIPS>(w, gx, gy);
-                tileS[r * SY + q] = __ldcg(&DR_F(occw, L)[L.idx]);
+                tileS[r * SY + q] = (__ldcg(&DR_F(mw, L)[L.idx]) & 0x80) ? __ldcg(&DR_F(occw, L)[L.idx]) : 0u;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
     // bitmaps and the lists of occupied cells
     for (int r = warp; r < SX; r += nwarps) {
         const bool row_in = r >= H && r < H + ex;
@@ -248,7 +350,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
                 alist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * SY + q);
                 atomicOr(&bmt[q * BWT + (r >> 5)], 1u << (r & 31));
                 if (mine) ilist[ibase + __popc(mi & ((1u << lane) - 1u))] = (uint16_t)((r << 7) | q);
-            } else if (q < SY) tileP[r * SY + q] = 0u;
+            }
         }
     }
     __syncthreads();
@@ -260,13 +362,14 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
     }
     __syncthreads();
     const int nl = s_n;
-    constexpr int GROUPS = DR_BUILD_THREADS / G;
-    const int grp = tid / G, gl = tid & (G - 1);
-    const unsigned gmask = G == 32 ? FULL : (0xffffu << (lane & 16));
-    uint32_t* myrec = s_rec[grp];
-    for (int k0 = 0; k0 < nl; k0 += GROUPS) {
-        const int k = k0 + grp;
-        const bool have = k < nl;                          // (uniform within a group)
+    PairT* pairs = reinterpret_cast<PairT*>(alist) + warp * DR_PAIR_CAP;       // (the list of all agents is dead by now)
+    uint32_t* cnt_p = s_cnt[warp][0];
+    uint32_t* cnt_s = s_cnt[warp][1];
+    const int per_warp = min(32, (nl + nwarps - 1) / nwarps);                   // agents of a batch: spread over the warps
+    const unsigned below = (1u << lane) - 1u;
+    for (int b0 = 0; b0 < nl; b0 += per_warp * nwarps) {
+        const int k = b0 + warp * per_warp + lane;
+        const bool have = lane < per_warp && k < nl;
         int lr = 0, lq = 0, a = 0;
         uint32_t pa = 0, slot = 0;
         if (have) {
@@ -276,77 +379,132 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             pa = me >> 5; a = (int)(me & 31u);
             slot = occ_slot(tileS[lr * SY + lq]);
         }
-        // lane task: a row of the square (gl <= 2V), or the x-axis column (gl == 2V + 1)
-        const bool rowtask = gl <= 2 * V, coltask = gl == 2 * V + 1;
-        const int dxr = gl - V;
-        WinT win = 0;
-        int R = 0;
-        if (have && rowtask) {
-            R = dxr == 0 ? H : V;
-            win = dr_window<G>(&bm[(lr + dxr) * BW], lq - R, 2 * R + 1);
-            if (dxr == 0) win &= ~((WinT)1 << R);                              // not the agent itself
-        } else if (have && coltask) {
-            R = H;
-            win = dr_window<G>(&bmt[lq * BWT], lr - H, 2 * H + 1);
-            win &= ~((((WinT)1 << (2 * V + 1)) - (WinT)1) << (H - V));          // the square's rows are taken by the row lanes
+        // the occupied cells of the zone: 2V+1 row windows (the axis row reaches 2V) and the x-arm beyond the square
+        // from the column bitmap
+        auto row_win = [&](int dx) -> WinT {
+            const int R = dx == 0 ? H : V;
+            WinT v = dr_window<WIDE>(&bm[(lr + dx) * BW], lq - R, 2 * R + 1);
+            if (dx == 0) v &= ~((WinT)1 << R);                                  // not the agent itself
+            return v;
+        };
+        auto col_win = [&]() -> WinT {
+            WinT v = dr_window<WIDE>(&bmt[lq * BWT], lr - H, 2 * H + 1);
+            return v & ~((((WinT)1 << (2 * V + 1)) - (WinT)1) << (H - V));     // the square's rows are counted by the row windows
+        };
+        uint32_t cnt = 0;
+        if (have) {
+            for (int dx = -V; dx <= V; dx++) cnt += (uint32_t)dr_popc<WIDE>(row_win(dx));
+            cnt += (uint32_t)dr_popc<WIDE>(col_win());
         }
-        uint32_t npred = 0, nsucc_l = 0;
-        WinT smask = 0;
-        {
-            WinT bits = win;
-            while (bits) {
-                const int j = G == 16 ? __ffs((uint32_t)bits) - 1 : __ffsll((long long)bits) - 1;
-                bits &= bits - (WinT)1;
-                const int dx = rowtask ? dxr : j - R, dy = rowtask ? j - R : 0;
-                const uint32_t cv = tileP[(lr + dx) * SY + lq + dy];
-                if (!dr_crosses_meet(dx, dy, a, (int)(cv & 31u))) continue;
-                if ((cv >> 5) < pa) npred++; else { nsucc_l++; smask |= (WinT)1 << j; }
-            }
-        }
-        // group totals and this lane's offset into the successor list
-        uint32_t off = nsucc_l, preds = npred;
+        uint32_t end = cnt;                                                     // inclusive scan over the batch
 #pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(gmask, off, o, G);
-            if (gl >= o) off += t;
-        }
-        const uint32_t nsucc = __shfl_sync(gmask, off, G - 1, G);
-        off -= nsucc_l;
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) preds += __shfl_xor_sync(gmask, preds, o, G);
-        uint32_t at = 0;
-        if (nsucc > DR_SUCC_INLINE) {
-            if (gl == 0) at = atomicAdd(&S.ctl[6], nsucc - DR_SUCC_INLINE);
-            at = __shfl_sync(gmask, at, 0, G);
-        }
-        const bool pool_ok = nsucc <= DR_SUCC_INLINE || at + (nsucc - DR_SUCC_INLINE) <= w.dr.pool_cap;
-        {
-            const int row = x0 + lr - H - S.x0;                                 // strip-local row of the agent
-            WinT bits = smask;
-            while (bits) {
-                const int j = G == 16 ? __ffs((uint32_t)bits) - 1 : __ffsll((long long)bits) - 1;
-                bits &= bits - (WinT)1;
-                const int dx = rowtask ? dxr : j - R, dy = rowtask ? j - R : 0;
-                uint32_t ent = occ_slot(tileS[(lr + dx) * SY + lq + dy]);
-                if (STRIPS) { const int r2 = row + dx; ent |= (r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u)) << 24; }
-                if (off < DR_SUCC_INLINE) myrec[1 + off] = ent;
-                else if (pool_ok) w.dr.pool[at + off - DR_SUCC_INLINE] = ent;
-                off++;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, end, o); if (lane >= o) end += t; }
+        cnt_p[lane] = 0u; cnt_s[lane] = 0u;
+        uint32_t my_at = 0;
+        bool pool_bad = false;
+        // sub-batches whose pairs fit the list (nearly always one)
+        uint32_t done_pairs = 0;
+        int first = 0;
+        while (first < 32) {
+            // lanes first.. whose pairs end within the capacity
+            const unsigned fit = __ballot_sync(FULL, lane >= first && end - done_pairs <= (uint32_t)DR_PAIR_CAP);
+            int upto = first;                                                   // first lane that does not fit
+            { const unsigned nf = ~fit & ~((1u << first) - 1u); upto = nf ? __ffs(nf) - 1 : 32; }
+            if (upto == first) upto = first + 1;                                // (a single agent always fits: zone < capacity)
+            const bool in_sub = lane >= first && lane < upto;
+            const uint32_t sub_begin = __shfl_sync(FULL, end - cnt, first);
+            const uint32_t sub_total = __shfl_sync(FULL, end, upto - 1) - sub_begin;
+            if (in_sub && have) {
+                uint32_t o = end - cnt - sub_begin;
+                for (int dx = -V; dx <= V; dx++) {
+                    const int R = dx == 0 ? H : V;
+                    WinT bits = row_win(dx);
+                    while (bits) {
+                        const int j = dr_ffs<WIDE>(bits);
+                        bits &= bits - (WinT)1;
+                        pairs[o++] = (PairT)(((uint32_t)lane << (2 * PS)) | ((uint32_t)(dx + H) << PS) | (uint32_t)(j - R + H));
+                    }
+                }
+                WinT bits = col_win();
+                while (bits) {
+                    const int j = dr_ffs<WIDE>(bits);
+                    bits &= bits - (WinT)1;
+                    pairs[o++] = (PairT)(((uint32_t)lane << (2 * PS)) | ((uint32_t)j << PS) | (uint32_t)H);
+                }
             }
+            __syncwarp();
+            // one pair per lane; pass 1 writes the successors beyond the record into their pool runs (rare)
+            const uint32_t geo = (uint32_t)lr | ((uint32_t)lq << 8) | ((uint32_t)a << 16);
+            for (int pass = 0; pass < 2; pass++) {
+                for (uint32_t i0 = 0; i0 < sub_total; i0 += 32) {
+                    const uint32_t i = i0 + (uint32_t)lane;
+                    const bool valid = i < sub_total;
+                    const uint32_t e = valid ? (uint32_t)pairs[i] : 0u;
+                    const int ag = (int)(e >> (2 * PS));
+                    const uint32_t g = __shfl_sync(FULL, geo, ag);
+                    const uint32_t pag = __shfl_sync(FULL, pa, ag), sag = __shfl_sync(FULL, slot, ag), atg = __shfl_sync(FULL, my_at, ag);
+                    bool is_pred = false, is_succ = false;
+                    uint32_t ent = 0;
+                    if (valid) {
+                        const int dx = (int)((e >> PS) & ((1u << PS) - 1u)) - H, dy = (int)(e & ((1u << PS) - 1u)) - H;
+                        const int alr = (int)(g & 255u), alq = (int)((g >> 8) & 255u), aa = (int)(g >> 16);
+                        const int pos = (alr + dx) * SY + alq + dy;
+                        const uint32_t cv = tileP[pos];
+                        if (dr_crosses_meet(dx, dy, aa, (int)(cv & 31u))) {
+                            if ((cv >> 5) < pag) is_pred = true;
+                            else {
+                                is_succ = true;
+                                ent = occ_slot(tileS[pos]);
+                                if (STRIPS) { const int r2 = x0 + alr - H - S.x0 + dx; ent |= (r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u)) << 24; }
+                            }
+                        }
+                    }
+                    // lanes of one agent are neighbours in the list: segment masks, no atomics
+                    const unsigned peers = __match_any_sync(FULL, valid ? ag : 32 + lane);
+                    const unsigned bp = __ballot_sync(FULL, is_pred) & peers, bs = __ballot_sync(FULL, is_succ) & peers;
+                    const uint32_t had = cnt_s[ag & 31];
+                    __syncwarp();
+                    if (is_succ) {
+                        const uint32_t idx = had + (uint32_t)__popc(bs & below);
+                        if (pass == 0) { if (idx < DR_SUCC_INLINE) reinterpret_cast<uint32_t*>(w.dr.succ)[(size_t)sag * 16 + 1 + idx] = ent; }
+                        else if (idx >= DR_SUCC_INLINE) w.dr.pool[atg + idx - DR_SUCC_INLINE] = ent;
+                    }
+                    if (valid && (peers & below) == 0u) {                       // the segment's first lane keeps the counts
+                        cnt_s[ag] = had + (uint32_t)__popc(bs);
+                        if (pass == 0) cnt_p[ag] += (uint32_t)__popc(bp);
+                    }
+                    __syncwarp();
+                }
+                if (pass == 1) break;
+                // successors beyond the record: a run of the pool each, then the second walk
+                const uint32_t ns = cnt_s[lane];
+                const bool over = in_sub && have && ns > DR_SUCC_INLINE;
+                if (!__any_sync(FULL, over)) break;
+                if (over) {
+                    my_at = atomicAdd(&S.ctl[6], ns - DR_SUCC_INLINE);
+                    if (my_at + (ns - DR_SUCC_INLINE) > w.dr.pool_cap) { atomicAdd(&S.ctl[7], 1u); my_at = 0xffffffffu; }
+                }
+                const bool bad = my_at == 0xffffffffu;
+                if (__any_sync(FULL, bad)) { if (bad) { my_at = 0; pool_bad = true; } break; }     // pool exhausted: a fault of the step
+                __syncwarp();
+                if (in_sub) cnt_s[lane] = 0u;                                   // (counted again by the second walk)
+                __syncwarp();
+            }
+            done_pairs += sub_total;
+            first = upto;
+            if (!__any_sync(FULL, have && lane >= first)) break;
         }
-        if (have && gl == 0) {
-            if (!pool_ok) atomicAdd(&S.ctl[7], 1u);                             // pool exhausted: reported as a fault by the step
-            myrec[0] = pool_ok ? nsucc : (uint32_t)DR_SUCC_INLINE;
-            myrec[15] = at;
+        __syncwarp();
+        if (have) {
+            const uint32_t nsucc = pool_bad ? (uint32_t)DR_SUCC_INLINE : cnt_s[lane], preds = cnt_p[lane];
+            uint32_t* rec = reinterpret_cast<uint32_t*>(w.dr.succ) + (size_t)slot * 16;
+            rec[0] = nsucc;
+            if (nsucc > DR_SUCC_INLINE) rec[15] = my_at;
             const uint32_t indeg = preds + ((__ldg(&w.dr.q1flag[slot >> 5]) >> (slot & 31)) & 1u);
             reinterpret_cast<uint16_t*>(S.dep)[slot] = (uint16_t)indeg;
             if (indeg == 0) { ilist[k] |= 0x8000u; atomicAdd(&s_ready, 1); }
         }
-        __syncwarp(gmask);
-        // the record: only the quarters the list reaches
-        if (have && gl < 4 && (gl * 4 < 1 + (int)min(nsucc, (uint32_t)DR_SUCC_INLINE) || (gl == 3 && nsucc > DR_SUCC_INLINE)))
-            w.dr.succ[(size_t)slot * 4 + gl] = make_uint4(myrec[4 * gl], myrec[4 * gl + 1], myrec[4 * gl + 2], myrec[4 * gl + 3]);
-        __syncwarp(gmask);
+        __syncwarp();
     }
     __syncthreads();
     if (tid == 0 && s_ready) s_base = atomicAdd(&S.ctl[0], (unsigned)s_ready);
@@ -460,7 +618,7 @@ __device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a
             const int arm = u >> 1, o = (u & 1) ? d : -d;
             const unsigned mv = cellbyte(arm, o);
             if (mv & 0x80u) continue;
-            const int sg = (int)mv;
+            const int sg = mv == DR_HARVESTED ? 0 : (int)mv;
             const int kk = arm * span + a + o;
             fm |= 1ull << kk;
             // agent.py:867-868: raw coordinates, so a candidate reached across the torus edge is far away
@@ -558,14 +716,14 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                 own = (uint8_t)dr_arm_byte(wy, a);
                 double pown = 0.0;
                 if (POLT) pown = __ldcg(&S.poll[c]);
-                dr_choose<POLT>(w, gx, gy, a, slot, st.skey, own & 0x7f, pown, acc,
+                dr_choose<POLT>(w, gx, gy, a, slot, st.skey, (own & 0x7f) == DR_HARVESTED ? 0 : (own & 0x7f), pown, acc,
                                 [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
                                 [&](int am, int oo) { return __ldcg(&S.poll[am ? c + oo : (uint32_t)((int)c + oo * n)]); }, arm, o, sg);
             } else {
                 own = __ldcg(&S.mw[c]);
                 double pown = 0.0;
                 if (POLT) pown = __ldcg(&S.poll[c]);
-                dr_choose<POLT>(w, gx, gy, a, slot, st.skey, own & 0x7f, pown, acc,
+                dr_choose<POLT>(w, gx, gy, a, slot, st.skey, (own & 0x7f) == DR_HARVESTED ? 0 : (own & 0x7f), pown, acc,
                                 [&](int am, int oo) {
                                     const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
                                     return (unsigned)__ldcg(&DR_F(mw, L)[L.idx]);
@@ -586,7 +744,8 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         if (w.cfg.rule_move_eat) {
             if (pol) p = p + (((double)sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));     // agent.py:825-826
             sugar = ss_set_sugar(ss_max0(sugar + (double)sg));                                     // agent.py:832
-            DR_F(sugar, D)[D.idx] = 0.0;                                                           // agent.py:864
+            // agent.py:864 cell.sugar = 0: the cell's byte takes the marker "harvested" below; the f64 value is
+            // dropped by the next growback (or ss_dr_canon_kernel), which saves a scattered 8-byte store per turn
         }
         if (pol && sugar > 0.0) p = p + ((0.0 * w.cfg.pollution_a) + ((double)metab * w.cfg.pollution_b));   // sugarscape.py:566-567
         if (pol) DR_F(poll, D)[D.idx] = p;
@@ -600,9 +759,9 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         died = w.cfg.rule_can_starve && sugar <= 0.1;                                              // sugarscape.py:306-309
         const bool risk_next = !died && dr_at_risk(w, sugar, metab);
         const uint32_t new_word = died ? 0u : occ_pack(slot, a, st.next_phase);
-        const uint8_t new_mw = died ? 0 : 0x80;
+        const uint8_t new_mw = (uint8_t)((died ? 0u : 0x80u) | (w.cfg.rule_move_eat ? DR_HARVESTED : (own & 0x7fu)));
         if (moved) {
-            S.occw[c] = 0u;
+            // (the cell's occupancy word stays behind: a word counts only where the byte says "occupied")
             S.mw[c] = own & 0x7f;
             S.mwx[(size_t)gy * (size_t)S.rows + (size_t)lx] = own & 0x7f;
         }
@@ -780,14 +939,36 @@ static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cud
 extern "C" {
 
 size_t ss_dr_build_smem(int vmax) {
-    const int H = 2 * vmax, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H, BW = ((SY + 31) >> 5) + 2, BWT = ((SX + 31) >> 5) + 2;
-    return (size_t)SX * SY * 8 + ((size_t)SX * BW + (size_t)SY * BWT) * 4 + (size_t)SX * SY * 2 + (size_t)DR_TX * DR_TY * 2 + 16;
+    const int H = 2 * vmax, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H, pad = vmax <= 7 ? 1 : 2;
+    const int BW = ((SY + 31) >> 5) + pad, BWT = ((SX + 31) >> 5) + pad;
+    const size_t pairs = (size_t)(DR_BUILD_THREADS / 32) * 1024 * (vmax <= 7 ? 2 : 4);     // the warps' pair lists
+    return (size_t)SX * SY * 8 + ((size_t)SX * BW + (size_t)SY * BWT) * 4 + (size_t)DR_TX * DR_TY * 2 +
+           std::max((size_t)SX * SY * 2 + 8, pairs) + 32;
 }
 
 cudaError_t ss_launch_dr_transpose(const DevWorld& w, cudaStream_t s) {
     const int rows = w.dr.self.rows, n = w.n;
     const int tiles = ((rows + 63) / 64) * ((n + 63) / 64);
     ss_dr_transpose_kernel<<<tiles, 256, 0, s>>>(w.dr.self.mw, w.dr.self.mwx, rows, n);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_dr_canon(const DevWorld& w, cudaStream_t s) {
+    ss_dr_canon_kernel<<<148 * 8, 256, 0, s>>>(w, (size_t)w.dr.self.rows * w.n);
+    return cudaGetLastError();
+}
+
+// sugarscape.py:642-659: growback of the whole lattice, or of the two season regions with the season's factors
+cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, cudaStream_t s) {
+    DrGrowArgs ga;
+    ga.seasons = w.cfg.rule_seasons; ga.alpha = w.cfg.grow_factor; ga.alpha_north = ga.alpha_south = 0.0;
+    if (w.cfg.rule_seasons) {
+        const bool summer = (iteration % (2 * (int64_t)w.cfg.season_period)) < w.cfg.season_period;
+        ga.alpha_north = summer ? w.cfg.season_on_factor : w.cfg.season_off_factor;
+        ga.alpha_south = summer ? w.cfg.season_off_factor : w.cfg.season_on_factor;
+    }
+    const int tiles = ((w.dr.self.rows + 63) / 64) * ((w.n + 63) / 64);
+    ss_dr_grow_kernel<<<tiles, 256, 0, s>>>(w, ga);
     return cudaGetLastError();
 }
 
@@ -820,10 +1001,10 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     static size_t configured = 0;
     const size_t smem = ss_dr_build_smem(w.vmax);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ss_dr_build_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ss_dr_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ss_dr_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -840,11 +1021,11 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     const bool strips = w.dr.self.rows != w.n;
     const int grid = tiles_x * ba.tiles_y;
     if (w.vmax <= 7) {
-        if (strips) ss_dr_build_kernel<true, 16><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-        else ss_dr_build_kernel<false, 16><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+        if (strips) ss_dr_build_kernel<true, false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+        else ss_dr_build_kernel<false, false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
     } else {
-        if (strips) ss_dr_build_kernel<true, 32><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
-        else ss_dr_build_kernel<false, 32><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+        if (strips) ss_dr_build_kernel<true, true><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
+        else ss_dr_build_kernel<false, true><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
     }
     ss_dr_seg0_kernel<<<1, 1, 0, s>>>(w);
     return cudaGetLastError();

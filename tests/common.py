@@ -146,13 +146,15 @@ def smoke_check():
     w = world_from_golden(g, "engine")
     run_against_golden(g, w, exact_gini=True, max_steps=20)
     w.close()
-    s, init = synthetic_case(200, pollution=True)
+    # the kernels of the bench's step at a small size: ss_dr_build_kernel (TMA tile load) + ss_dr_rounds_kernel,
+    # ss_dr_grow_kernel, ss_diffuse_col_kernel, ss_stats_kernel
+    s, init = synthetic_case(512, pollution=True)
     cfg = config_from_settings(s, rng_mode="keyed")
     e, o = engine_world(cfg), oracle_world(cfg)
     init_world(e, init, "keyed")
     init_world(o, init, "keyed")
-    compare_worlds(e, o, 6, what="synthetic 200x200")
-    assert e.counters()["path"] == 2, "lattice path was not selected"
+    compare_worlds(e, o, 6, what="synthetic 512x512")
+    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 3, "dependency rounds were not selected"
     e.close()
 
 

@@ -136,12 +136,16 @@ def test_keyed_serial_path(name):
     w.close()
 
 
+@pytest.mark.parametrize("impl", [3, 0])
 @pytest.mark.parametrize("name", KEYED_MOVE_CASES)
-def test_keyed_lattice_path(name):
-    """Parallel dependency rounds reproduce the sequential loop of the reference (keyed words)."""
+def test_keyed_lattice_path(name, impl):
+    """Parallel dependency rounds reproduce the sequential loop of the reference (keyed words): the whole-lattice
+    rounds of ss_rounds.cu (pass_impl 3, the default) and the window passes (pass_impl 0) on the reference's goldens."""
     g = common.load_golden(name)
-    w = common.world_from_golden(g, "engine", path=2)
-    assert w.counters()["path"] == 2
+    cfg = config_from_settings(g["settings"], rng_mode=g["rng"])
+    w = common.engine_world(cfg, path=2, options={"pass_impl": impl})
+    common.init_world(w, common.golden_init(g), g["rng"], g["init_mt"], int(g["init_mt_index"]))
+    assert w.counters()["path"] == 2 and w.counters()["pass_impl"] == impl
     common.run_against_golden(g, w, exact_gini=False)
     w.close()
 
@@ -150,26 +154,31 @@ def test_keyed_lattice_path(name):
     (64, True, 12, (1, 6)), (177, True, 10, (1, 6)), (200, False, 10, (1, 6)), (257, True, 8, (1, 6)),
     (300, True, 8, (1, 10)), (512, True, 8, (1, 6)), (1000, True, 5, (1, 6)), (1024, False, 6, (1, 6)),
 ])
-@pytest.mark.parametrize("impl", ["cta_per_window", "warp_per_window", "lane_per_agent"])
+@pytest.mark.parametrize("impl", ["dependency_rounds", "dependency_rounds_no_tma", "cta_per_window", "warp_per_window", "lane_per_agent"])
 def test_lattice_vs_oracle_synthetic(n, pollution, steps, vision, impl):
-    """The move-pass kernels (ss_move_pass_kernel: a CTA per window, a warp per region; ss_move_solo_kernel: a warp
-    per window, here with windows of at most 96 cells so that small lattices have several, taking its agents one at a
-    time or -- pass_impl 2 -- 32 at a time, one lane each) against the CPU oracle."""
+    """The agent-phase kernels against the CPU oracle: the dependency rounds over the whole lattice (ss_dr_build_kernel +
+    ss_dr_rounds_kernel, the default; also with the TMA tile load switched off) and the move-pass kernels
+    (ss_move_pass_kernel: a CTA per window, a warp per region; ss_move_solo_kernel: a warp per window, here with windows
+    of at most 96 cells so that small lattices have several, taking its agents one at a time or -- pass_impl 2 -- 32 at
+    a time, one lane each)."""
     s, init = common.synthetic_case(n, pollution, vision=vision)
     cfg = config_from_settings(s, rng_mode="keyed")
     solo = {"warp_per_window": 1, "lane_per_agent": 2}.get(impl, 0)
-    opts = {"pass_impl": 0} if not solo else {"pass_impl": solo, "solo_window": 96 if vision[1] <= 6 else 120}
+    if impl.startswith("dependency_rounds"):
+        opts = {"pass_impl": 3, "tma": 0 if impl.endswith("no_tma") else 1}
+    else:
+        opts = {"pass_impl": 0} if not solo else {"pass_impl": solo, "solo_window": 96 if vision[1] <= 6 else 120}
     e, o = common.engine_world(cfg, options=opts), common.oracle_world(cfg)
     common.init_world(e, init, "keyed")
     common.init_world(o, init, "keyed")
     assert e.counters()["path"] == 2
-    assert e.counters()["pass_impl"] == (solo if n >= 177 else 0)
+    assert e.counters()["pass_impl"] == (3 if "pass_impl" in opts and opts["pass_impl"] == 3 else (solo if n >= 177 else 0))
     common.compare_worlds(e, o, steps, what="synthetic %d %s" % (n, impl))
     e.close()
     o.close()
 
 
-@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 1, "solo_window": 128},
+@pytest.mark.parametrize("opts", [{"pass_impl": 3}, {"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 1, "solo_window": 128},
                                   {"pass_impl": 2, "solo_window": 72}])
 def test_lattice_dense_population(opts):
     """density 1/3: deep dependency chains, many ties, many deaths (Q1 skips); density 0.9 overflows the key lists
@@ -229,7 +238,7 @@ def test_lattice_utilicalc_equals_serial_kernel_and_small_lattices_stay_serial()
     b.close()
 
 
-@pytest.mark.parametrize("opts", [{"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 2, "solo_window": 72}])
+@pytest.mark.parametrize("opts", [{"pass_impl": 3}, {"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 2, "solo_window": 72}])
 def test_lattice_seasons(opts):
     s, init = common.synthetic_case(260, False, seasons=True)
     s["rule_params"]["seasons"]["period"] = 3
@@ -295,8 +304,8 @@ def test_unsupported_configurations_fail_loudly():
 def test_empty_population_and_extinction():
     s, init = common.synthetic_case(64, False)
     cfg = config_from_settings(s, rng_mode="keyed")
-    for path in (0, 2):
-        e, o = common.engine_world(cfg, path), common.oracle_world(cfg)
+    for path, impl in ((0, -1), (2, 3), (2, 0)):
+        e, o = common.engine_world(cfg, path, options={"pass_impl": impl}), common.oracle_world(cfg)
         for w in (e, o):
             w.upload_cells(np.zeros((64, 64)), np.zeros((64, 64)), None)      # barren: everyone starves
             w.upload_agents(init["id"][:40], init["x"][:40], init["y"][:40], init["vision"][:40], init["metab"][:40],
@@ -381,8 +390,54 @@ def test_full_size_c4_against_oracle():
     e, o = common.engine_world(cfg), common.oracle_world(cfg)
     common.init_world(e, init, "keyed")
     common.init_world(o, init, "keyed")
-    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 1      # warp-per-window kernel at this size
+    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 3      # dependency rounds over the whole lattice
     common.compare_worlds(e, o, 3, what="C4 full size")
+    e.close()
+    o.close()
+
+
+@pytest.mark.timeout(900)
+def test_full_size_c5_against_oracle():
+    """BASELINE config 5 at full size (16384 x 16384, 16,777,216 agents) -- the configuration the bench line is quoted on:
+    the engine's default path against the CPU oracle, bit-exact on cell sugar, occupancy, the agents (list order,
+    positions, sugar) and the statistics, two whole timesteps (the oracle needs ~15 s per step)."""
+    n = 16384
+    s, init = common.synthetic_case(n, False)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 3
+    for t in range(2):
+        sa, sb = e.step(1), o.step(1)
+        for f in ("population", "metabolism_mean", "vision_mean", "acted", "deaths"):
+            assert np.array_equal(sa[f], sb[f]), (f, t, sa[f], sb[f])
+        np.testing.assert_allclose(sa["gini"], sb["gini"], rtol=1e-9, atol=1e-12)
+        ga, gb = e.download_agents(), o.download_agents()
+        for k in ("id", "x", "y", "vision", "metab", "sugar"):
+            assert np.array_equal(ga[k], gb[k]), "step %d: agents differ in %s" % (t + 1, k)
+        del ga, gb
+        cb = o.download_cells()
+        ca = e.download_cells(cap=False, pollution=False)
+        assert np.array_equal(ca["occ"], cb["occ"]), "step %d: occupancy differs" % (t + 1)
+        assert np.array_equal(ca["sugar"], cb["sugar"]), "step %d: cell sugar differs" % (t + 1)
+        del ca, cb
+    assert e.health() == dict(watchdog=0, fault=0)
+    e.close()
+    o.close()
+
+
+@pytest.mark.timeout(600)
+def test_full_size_c4_utilicalc_against_oracle():
+    """The utilicalc rule at the C4 size (4096 x 4096, 1,048,576 agents; `c4u` of bench.py): two whole timesteps against
+    the CPU oracle, bit-exact."""
+    s, init = common.synthetic_case(4096, False, utilicalc=True)
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert e.counters()["path"] == 2
+    common.compare_worlds(e, o, 2, what="c4u full size")
     e.close()
     o.close()
 
