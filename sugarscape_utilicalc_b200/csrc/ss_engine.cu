@@ -559,11 +559,11 @@ static int dr_alloc(ss_engine* e) {
         CK(cudaMemsetAsync(d.self.mwx, 0, e->cells + 64, e->stream));
         CK(cudaMemsetAsync(d.self.ctl, 0, DR_CTL_WORDS * sizeof(unsigned int), e->stream));
     }
-    // successors beyond the 14 of a record: a run of the pool; sized for 16 more per agent, or for every cell of
-    // every conflict zone when that is less
+    // successors beyond the 14 of a record: a run of the pool; sized for every cell of every conflict zone (the
+    // worst case) up to 2^26 entries, beyond that for 16 more per agent
     const int V = std::max(e->w.vmax, 1);
     const uint64_t zone = (uint64_t)(2 * V + 1) * (2 * V + 1) + 4 * V;
-    const uint64_t pool64 = std::min<uint64_t>((uint64_t)ns * 16u, (uint64_t)ns * zone) + 64;
+    const uint64_t pool64 = std::min<uint64_t>((uint64_t)ns * zone, std::max<uint64_t>((uint64_t)ns * 16u, 1ull << 26)) + 64;
     const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(pool64, 0xfffffff0ull);
     if (ns != e->dr_slots || pool_cap != d.pool_cap) {
         cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1flag); cudaFree(d.q1wait);

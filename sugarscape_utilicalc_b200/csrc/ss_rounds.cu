@@ -278,7 +278,8 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
     __shared__ unsigned s_base;
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_cnt[DR_BUILD_THREADS / 32][2][32];   // per warp and agent of the batch: predecessors, successors
-    const int n = w.n, V = w.vmax, H = 2 * V, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H;
+    // HP: the halo as staged, 2V rounded up to a multiple of 4 cells (the TMA box wants rows of a multiple of 32 bytes)
+    const int n = w.n, V = w.vmax, H = 2 * V, HP = (H + 3) & ~3, SX = DR_TX + 2 * HP, SY = DR_TY + 2 * HP;
     const int BW = ((SY + 31) >> 5) + (WIDE ? 2 : 1), BWT = ((SX + 31) >> 5) + (WIDE ? 2 : 1);
     uint32_t* tileS = sm;                                  // [SX][SY] occupancy words (slot | vision | flags), 0 = free
     uint32_t* tileP = tileS + SX * SY;                     // [SX][SY] priority << 5 | vision
@@ -294,7 +295,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
     if (tid == 0) { s_all = 0; s_n = 0; s_ready = 0; s_fill = 0; }
     for (int i = tid; i < SX * BW + SY * BWT; i += DR_BUILD_THREADS) bm[i] = 0u;
     // the tile and its halo lie inside this strip and inside [0, n) in y: one TMA box; otherwise plain loads with wraps
-    const bool interior = ba.use_tma && x0 - H >= S.x0 && x0 + DR_TX + H <= S.x0 + S.rows && y0 - H >= 0 && y0 + DR_TY + H <= n;
+    const bool interior = ba.use_tma && x0 - HP >= S.x0 && x0 + DR_TX + HP <= S.x0 + S.rows && y0 - HP >= 0 && y0 + DR_TY + HP <= n;
     if (interior) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
@@ -306,7 +307,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                ::"r"(smem_u32(tileS)), "l"(&tmap), "r"(y0 - H), "r"(x0 - H - S.x0), "r"(smem_u32(&s_bar)) : "memory");
+                ::"r"(smem_u32(tileS)), "l"(&tmap), "r"(y0 - HP), "r"(x0 - HP - S.x0), "r"(smem_u32(&s_bar)) : "memory");
         }
         uint32_t done = 0;                                 // everybody waits for the box (phase 0)
         while (!done) {
@@ -315,15 +316,15 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
         }
         // a word counts only where the cell byte says "occupied" (the turns leave the words of vacated cells behind)
         for (int r = warp; r < SX; r += nwarps) {
-            const uint8_t* src = S.mw + (size_t)(x0 - H - S.x0 + r) * n + (y0 - H);
+            const uint8_t* src = S.mw + (size_t)(x0 - HP - S.x0 + r) * n + (y0 - HP);
             for (int q = lane; q < SY; q += 32) if (!(__ldcg(&src[q]) & 0x80)) tileS[r * SY + q] = 0u;
         }
     } else {
         __syncthreads();
         for (int r = warp; r < SX; r += nwarps) {
-            const int gx = ss_wrap(x0 - H + r, n);
+            const int gx = ss_wrap(x0 - HP + r, n);
             for (int q = lane; q < SY; q += 32) {
-                const int gy = ss_wrap(y0 - H + q, n);
+                const int gy = ss_wrap(y0 - HP + q, n);
                 const DrLoc L = dr_loc<STRIPS>(w, gx, gy);
                 tileS[r * SY + q] = (__ldcg(&DR_F(mw, L)[L.idx]) & 0x80) ? __ldcg(&DR_F(occw, L)[L.idx]) : 0u;
             }
@@ -332,7 +333,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
     __syncthreads();
     // bitmaps and the lists of occupied cells
     for (int r = warp; r < SX; r += nwarps) {
-        const bool row_in = r >= H && r < H + ex;
+        const bool row_in = r >= HP && r < HP + ex;
         for (int q0 = 0; q0 < SY; q0 += 32) {
             const int q = q0 + lane;
             const uint32_t ow = q < SY ? tileS[r * SY + q] : 0u;
@@ -342,7 +343,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_all, __popc(m));
             base = __shfl_sync(FULL, base, 0);
-            const bool mine = ow != 0u && row_in && q >= H && q < H + ey;
+            const bool mine = ow != 0u && row_in && q >= HP && q < HP + ey;
             const unsigned mi = __ballot_sync(FULL, mine);
             int ibase = 0;
             if (mi) { if (lane == 0) ibase = atomicAdd(&s_n, __popc(mi)); ibase = __shfl_sync(FULL, ibase, 0); }
@@ -455,7 +456,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
                             else {
                                 is_succ = true;
                                 ent = occ_slot(tileS[pos]);
-                                if (STRIPS) { const int r2 = x0 + alr - H - S.x0 + dx; ent |= (r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u)) << 24; }
+                                if (STRIPS) { const int r2 = x0 + alr - HP - S.x0 + dx; ent |= (r2 < 0 ? 1u : (r2 >= S.rows ? 2u : 0u)) << 24; }
                             }
                         }
                     }
@@ -939,7 +940,7 @@ static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cud
 extern "C" {
 
 size_t ss_dr_build_smem(int vmax) {
-    const int H = 2 * vmax, SX = DR_TX + 2 * H, SY = DR_TY + 2 * H, pad = vmax <= 7 ? 1 : 2;
+    const int HP = (2 * vmax + 3) & ~3, SX = DR_TX + 2 * HP, SY = DR_TY + 2 * HP, pad = vmax <= 7 ? 1 : 2;
     const int BW = ((SY + 31) >> 5) + pad, BWT = ((SX + 31) >> 5) + pad;
     const size_t pairs = (size_t)(DR_BUILD_THREADS / 32) * 1024 * (vmax <= 7 ? 2 : 4);     // the warps' pair lists
     return (size_t)SX * SY * 8 + ((size_t)SX * BW + (size_t)SY * BWT) * 4 + (size_t)DR_TX * DR_TY * 2 +
@@ -983,7 +984,7 @@ cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s) {
 cudaError_t ss_dr_encode_tmap(const DevWorld& w, void* tmap_storage, int* ok) {
     *ok = 0;
     EncodeTiledFn enc = encode_tiled_fn();
-    const int n = w.n, H = 2 * w.vmax;
+    const int n = w.n, H = (2 * w.vmax + 3) & ~3;         // the staged halo (ss_dr_build_kernel)
     if (!enc || n % 4 != 0) return cudaSuccess;
     const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)w.dr.self.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
