@@ -195,6 +195,40 @@ int  ss_shard_pending(ss_engine* e, uint64_t* pending);
 int  ss_shard_end_step(ss_engine* e, ss_step_stats* out);
 #define SS_SHARD_ENTRY_BYTES 48
 
+/* Row strips (one engine per GPU; sugarscape_utilicalc_b200/strips.py) -- BASELINE config 5: "row-strip sharded with
+ * NVLink halo exchange and agent migration".  Rank r of `world` holds the lattice rows [r N / world, (r+1) N / world) --
+ * cells, occupancy and the records of the agents standing on them; the toroidal neighbour relation of the reference
+ * (agent.py:362-368) makes the strips a ring.  Nothing is exchanged by the host: the kernels reach the two ring
+ * neighbours' border rows (halo of the conflict graph, crosses and moves across the border, migrating agent records) and
+ * every strip's dependency counters (the list-order quirk Q1 couples arbitrary agents) through peer-mapped device
+ * pointers over NVLink; small replicated directories (alive / at-risk bitmaps, the strip that holds each agent) are
+ * kept in step by per-strip delta lists; the per-step sums and the wealth histogram are merged over the strips, so
+ * every rank reports the same statistics.
+ *   ss_create_strip; ss_set_option("global_slots" = max Agent.id over all strips, "global_vmax" = max vision);
+ *   ss_upload_cells (rows x N arrays of the strip); ss_upload_agents (the agents standing on the strip, lattice
+ *   coordinates); ss_strip_init_directory (id, x, metabolism, sugar of the agents of ALL strips);
+ *   ss_strip_ipc_export -> exchange the handles -> ss_strip_ipc_connect for every other rank (ss_strip_export /
+ *   ss_strip_connect when the peers live in the same process); a barrier over the ranks; then ss_strip_step.
+ * ss_download_cells / ss_download_agents / ss_agent_count return the strip's share.  SS_STRIP_NPTR pointers / handles
+ * per strip. */
+#define SS_STRIP_NPTR 11
+#define SS_STRIP_HANDLE_BYTES 64
+int  ss_create_strip(const ss_config* cfg, int32_t device, int32_t rank, int32_t world, ss_engine** out);
+int  ss_strip_init_directory(ss_engine* e, int32_t n_all, const int32_t* id, const int32_t* x, const int32_t* metab,
+                             const double* sugar);
+int  ss_strip_export(ss_engine* e, uint64_t* ptrs);
+int  ss_strip_connect(ss_engine* e, int32_t peer_rank, const uint64_t* ptrs);
+int  ss_strip_ipc_export(ss_engine* e, void* handles);
+int  ss_strip_ipc_connect(ss_engine* e, int32_t peer_rank, const void* handles);
+/* Replaces: nsteps calls of View.updateGame() on the whole lattice, this rank's share; the strips synchronise on the
+ * device (flag words in peer memory between the phases and between the dependency rounds). */
+int  ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out);
+/* The same step phase by phase with the host as the barrier (several strips on one GPU, one process: the parity
+ * tests).  phase 0 begin + conflict graph, 1 one dependency round over the queue segment [seg_begin, seg_end), 2 after
+ * the rounds, 3 statistics + growback.  Every strip finishes a phase before any strip starts the next. */
+int  ss_strip_phase(ss_engine* e, int32_t phase, uint32_t seg_begin, uint32_t seg_end, uint32_t* tail_out,
+                    ss_step_stats* stats_out);
+
 #ifdef __cplusplus
 }
 #endif

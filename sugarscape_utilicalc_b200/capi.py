@@ -58,6 +58,8 @@ EXPORTS = (
     "ss_download_cells", "ss_download_agents", "ss_get_counters", "ss_get_kernel_times",
     "ss_set_option", "ss_version", "ss_shard_enable", "ss_shard_begin_step", "ss_shard_pass", "ss_shard_apply",
     "ss_shard_apply_gathered", "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free", "ss_seed_mt19937", "ss_init_world",
+    "ss_create_strip", "ss_strip_init_directory", "ss_strip_export", "ss_strip_connect", "ss_strip_ipc_export",
+    "ss_strip_ipc_connect", "ss_strip_step", "ss_strip_phase",
 )
 
 _lib = None
@@ -106,6 +108,14 @@ def lib():
     L.ss_shard_apply_gathered.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_int32, C.c_uint64, C.c_uint64]
     L.ss_shard_pending.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ss_shard_end_step.argtypes = [vp, vp]
+    L.ss_create_strip.argtypes = [C.POINTER(SsConfig), C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.ss_strip_init_directory.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+    L.ss_strip_export.argtypes = [vp, vp]
+    L.ss_strip_connect.argtypes = [vp, C.c_int32, vp]
+    L.ss_strip_ipc_export.argtypes = [vp, vp]
+    L.ss_strip_ipc_connect.argtypes = [vp, C.c_int32, vp]
+    L.ss_strip_step.argtypes = [vp, C.c_int32, vp]
+    L.ss_strip_phase.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), vp]
     L.ss_host_alloc.argtypes = [C.c_size_t]
     L.ss_host_alloc.restype = vp
     L.ss_host_free.argtypes = [vp]

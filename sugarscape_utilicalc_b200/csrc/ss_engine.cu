@@ -25,6 +25,10 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
 cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t env_time, int sm_count, int single_round,
                                 unsigned seg_begin, unsigned seg_end, cudaStream_t s);
 cudaError_t ss_launch_dr_check(const DevWorld& w, cudaStream_t s);
+cudaError_t ss_launch_dr_directory(const DevWorld& w, int n_all, const int32_t* id, const int32_t* x, const int32_t* metab,
+                                   const double* sugar, cudaStream_t s);
+cudaError_t ss_launch_dr_after_rounds(const DevWorld& w, cudaStream_t s);
+cudaError_t ss_launch_dr_strip_barrier(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D, double max_capacity,
                                  int grow, int sm_count, cudaStream_t stream);
@@ -32,7 +36,9 @@ cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, in
                                   size_t stride, double* sugar, int32_t* result, cudaStream_t stream);
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
+cudaError_t ss_launch_validate_rows(int n, const int32_t* x, int x0, int rows, int* out, cudaStream_t s);
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s);
+cudaError_t ss_launch_count_alive(const DevWorld& w, unsigned long long* out, cudaStream_t s);
 cudaError_t ss_launch_validate_agents(int n, int N, const int32_t* id, const int32_t* x, const int32_t* y, const int32_t* vision,
                                       const int32_t* metab, int* out3, cudaStream_t s);
 uint32_t ss_export_blocks(uint32_t domain);
@@ -78,6 +84,13 @@ struct ss_engine {
     int mirror = 0;                            // which int(sugar) mirror is current: 1 = isugar (window passes), 2 = mw (rounds)
     bool cap_fits_u7 = true;
     bool dr_dirty = false;                      // sugar / occw hold what the rounds tidy lazily (dr_tidy)
+    // row strips (one engine per GPU): this engine holds the lattice rows [x0, x0 + rows)
+    int strip_rank = 0, strip_world = 1, x0 = 0, rows = 0;
+    uint32_t global_slots = 0;                  // max Agent.id over all strips (options "global_slots", "global_vmax")
+    int global_vmax = 0;
+    int peers_connected = 0;
+    bool peers_ipc = false;
+    void* ipc_ptrs[DR_MAX_STRIPS][16];
     int use_tma = 1, tma_ok = 0;
     int l2_persist = 1;
     alignas(64) unsigned char tmap[128];
@@ -95,6 +108,7 @@ struct ss_engine {
     int trace = 0;
     bool cap_fits_u8 = true;
     unsigned long long* h_pending = nullptr;   // pinned
+    unsigned long long* h_dev_count = nullptr; // device scalar
     int n_uploaded = 0;                        // agents of the last upload (w.order holds their slots in list order)
     int64_t launches = 0, passes = 0, steps = 0, syncs = 0;
     bool profile = false;
@@ -120,7 +134,21 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 extern "C" const char* ss_version(void) { return "sugarscape_b200 0.1 (sm_100a)"; }
 extern "C" const char* ss_last_error(ss_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
 
-extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) {
+static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32_t world, ss_engine** out);
+extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) { return create_impl(cfg, device, 0, 1, out); }
+// one strip of the lattice rows per engine / GPU: rank r of `world` holds the rows [r N / world, (r + 1) N / world)
+extern "C" int ss_create_strip(const ss_config* cfg, int32_t device, int32_t rank, int32_t world, ss_engine** out) {
+    ss_engine* e = nullptr;
+    if (!cfg || !out) return set_err(e, SS_ERR_ARG, "null argument");
+    if (world < 1 || world > DR_MAX_STRIPS || rank < 0 || rank >= world) return set_err(e, SS_ERR_ARG, "bad rank / world (at most 8 strips)");
+    if (world > 1) {
+        if (cfg->rng_mode != SS_RNG_KEYED || !cfg->rule_move_eat || cfg->rule_pollution)
+            return set_err(e, SS_ERR_UNSUPPORTED, "row strips run rule M with the keyed order, without the pollution rule");
+        if (cfg->grid_size / world < 8) return set_err(e, SS_ERR_UNSUPPORTED, "strips need at least 8 rows each");
+    }
+    return create_impl(cfg, device, rank, world, out);
+}
+static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32_t world, ss_engine** out) {
     ss_engine* e = nullptr;
     if (!cfg || !out) return set_err(e, SS_ERR_ARG, "null argument");
     if (cfg->grid_size < 3) return set_err(e, SS_ERR_ARG, "grid_size must be >= 3");
@@ -143,7 +171,13 @@ extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) 
     memset(&e->w, 0, sizeof e->w);
     e->w.cfg = *cfg;
     e->w.n = cfg->grid_size;
-    e->cells = (size_t)cfg->grid_size * cfg->grid_size;
+    e->strip_rank = rank; e->strip_world = world;
+    e->x0 = (int)(((long long)rank * cfg->grid_size) / world);
+    e->rows = (int)(((long long)(rank + 1) * cfg->grid_size) / world) - e->x0;
+    e->w.x0 = e->x0; e->w.rows = e->rows;
+    e->w.dr.world = world; e->w.dr.rank = rank;
+    memset(e->ipc_ptrs, 0, sizeof e->ipc_ptrs);
+    e->cells = (size_t)e->rows * cfg->grid_size;
     e->iteration = cfg->iteration;
     e->env_time = cfg->env_time;
     auto bail = [&](cudaError_t ce, const char* what) {
@@ -169,6 +203,7 @@ extern "C" int ss_create(const ss_config* cfg, int32_t device, ss_engine** out) 
     const int nbands = (cfg->grid_size + 31) / 32;
     if ((ce = cudaMalloc(&e->d_flags, sizeof(int) * (size_t)(nbands + 1))) != cudaSuccess) return bail(ce, "cudaMalloc flags");
     if ((ce = cudaMallocHost(&e->h_pending, sizeof(unsigned long long))) != cudaSuccess) return bail(ce, "cudaMallocHost");
+    if ((ce = cudaMalloc(&e->h_dev_count, sizeof(unsigned long long))) != cudaSuccess) return bail(ce, "cudaMalloc count");
     cudaMemset(e->w.sugar, 0, cb);
     cudaMemset(e->w.cap, 0, cb);
     cudaMemset(e->w.poll, 0, cb);
@@ -198,6 +233,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
     dr_free(e);
     if (e->h_pending) cudaFreeHost(e->h_pending);
+    cudaFree(e->h_dev_count);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evs) cudaEventDestroy(e->evs);
@@ -310,6 +346,13 @@ static int choose_path(ss_engine* e) {
     // dependency rounds over the whole lattice: rule M with the keyed order, any lattice the conflict zone fits on
     const bool dr_ok = e->cfg.rng_mode == SS_RNG_KEYED && e->cfg.rule_move_eat && V <= 15 && 4 * V + 1 <= n && e->cap_fits_u7 &&
                        e->w.n_slots <= SS_MAX_SLOTS && e->shard_world == 1;
+    if (e->strip_world > 1) {
+        if (!dr_ok) return set_err(e, SS_ERR_UNSUPPORTED, "row strips need the dependency rounds (keyed order, rule M, vision <= 15, capacities < 127)");
+        // a conflict zone (2 vmax rows either side) must not reach beyond the two ring neighbours
+        if (n / e->strip_world < 4 * V + 1) return set_err(e, SS_ERR_UNSUPPORTED, "strips need at least 4 * max vision + 1 rows each");
+        e->geom = g; e->ntile = 1; e->emin = 0; e->pass_impl = 3; e->path = PATH_LATTICE;
+        return dr_alloc(e);
+    }
     if (dr_ok && (e->pass_impl_option == 3 || e->pass_impl_option < 0)) { lattice_ok = true; impl = 3; }
     else if (e->pass_impl_option == 3) lattice_ok = false;
     int path;
@@ -378,8 +421,16 @@ static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, dou
         case 6: return set_err(e, SS_ERR_ARG, "metabolism out of range [1,65535]");
         default: return set_err(e, SS_ERR_ARG, "agent off the grid");
     }
-    const int32_t max_id = chk[1];
-    const int vmax = std::max(chk[2], 1);
+    if (e->strip_world > 1) {
+        int bad = 0;
+        CK(cudaMemsetAsync(d_chk, 0, sizeof(int), e->stream));
+        CK(ss_launch_validate_rows(n, d_i32 + nn, e->x0, e->rows, d_chk, e->stream));
+        CK(cudaMemcpyAsync(&bad, d_chk, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (bad) return set_err(e, SS_ERR_ARG, "agent outside this engine's strip of rows");
+    }
+    const int32_t max_id = std::max<int32_t>(chk[1], (int32_t)e->global_slots);
+    const int vmax = std::max(std::max(chk[2], 1), e->global_vmax);
     if ((uint32_t)max_id > SS_MAX_SLOTS) return set_err(e, SS_ERR_UNSUPPORTED, "agent id exceeds 2^24");
     const uint32_t ns = (uint32_t)std::max(max_id, 1);
     const uint32_t phase = (uint32_t)(e->iteration & 1);
@@ -543,8 +594,15 @@ static void dr_free(ss_engine* e) {
     DrState& d = e->w.dr;
     cudaFree(d.self.mw); cudaFree(d.self.mwx); cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.self.ctl);
     cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1flag); cudaFree(d.q1wait);
+    cudaFree(d.self.delta); cudaFree(d.home); cudaFree(d.acc_g); cudaFree(d.hist_g);
+    if (e->peers_ipc)
+        for (int r = 0; r < DR_MAX_STRIPS; r++)
+            for (int k = 0; k < 16; k++) if (e->ipc_ptrs[r][k]) cudaIpcCloseMemHandle(e->ipc_ptrs[r][k]);
+    memset(e->ipc_ptrs, 0, sizeof e->ipc_ptrs);
+    const int rank = d.rank, world = d.world;
     memset(&d, 0, sizeof d);
-    e->dr_slots = 0;
+    d.rank = rank; d.world = world;
+    e->dr_slots = 0; e->peers_connected = 0;
 }
 
 // device state of the dependency rounds (ss_world.cuh DrState), sized by the lattice and the slots
@@ -567,6 +625,8 @@ static int dr_alloc(ss_engine* e) {
     const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(pool64, 0xfffffff0ull);
     if (ns != e->dr_slots || pool_cap != d.pool_cap) {
         cudaFree(d.self.dep); cudaFree(d.self.queue); cudaFree(d.succ); cudaFree(d.pool); cudaFree(d.alive); cudaFree(d.atrisk); cudaFree(d.q1flag); cudaFree(d.q1wait);
+        cudaFree(d.self.delta); cudaFree(d.home); cudaFree(d.acc_g); cudaFree(d.hist_g);
+        d.self.delta = nullptr; d.home = nullptr; d.acc_g = nullptr; d.hist_g = nullptr;
         d.q1flag = nullptr;
         d.self.dep = nullptr; d.self.queue = nullptr; d.succ = nullptr; d.pool = nullptr; d.alive = nullptr; d.atrisk = nullptr; d.q1wait = nullptr;
         const size_t words = (size_t)(ns + 31) / 32 + 1;
@@ -583,7 +643,17 @@ static int dr_alloc(ss_engine* e) {
         CK(cudaMemsetAsync(d.alive, 0, sizeof(uint32_t) * words, e->stream));
         CK(cudaMemsetAsync(d.atrisk, 0, sizeof(uint32_t) * words, e->stream));
         CK(cudaMemsetAsync(d.q1wait, 0, sizeof(uint2) * (size_t)ns, e->stream));
+        if (e->strip_world > 1) {               // the replicated directory, this strip's delta list, the merged statistics
+            d.delta_cap = ns + 64;
+            CK(cudaMalloc(&d.self.delta, sizeof(uint32_t) * (size_t)d.delta_cap));
+            CK(cudaMalloc(&d.home, (size_t)ns + 16));
+            CK(cudaMalloc(&d.acc_g, sizeof(StepAccum)));
+            CK(cudaMalloc(&d.hist_g, SS_GINI_BINS * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(d.home, 0, (size_t)ns + 16, e->stream));
+            CK(cudaMemsetAsync(d.acc_g, 0, sizeof(StepAccum), e->stream));
+        }
         e->dr_slots = ns; d.pool_cap = pool_cap;
+        e->peers_connected = 0;
         if (e->mirror == 2) e->mirror = 0;
     }
     {   // the predecessor counters take one atomic per edge of the step's DAG: keep them in L2 (access policy window on
@@ -614,8 +684,14 @@ static int dr_alloc(ss_engine* e) {
     }
     d.queue_cap = ns;
     d.self.occw = e->w.occw; d.self.sugar = e->w.sugar; d.self.poll = e->w.poll; d.self.agents = e->w.agents;
-    d.self.x0 = 0; d.self.rows = e->w.n;
-    d.lo = d.self; d.hi = d.self;
+    d.self.acc = reinterpret_cast<unsigned long long*>(e->w.acc); d.self.hist = e->w.hist;
+    d.self.x0 = e->x0; d.self.rows = e->rows;
+    d.rank = e->strip_rank; d.world = e->strip_world;
+    if (!e->peers_connected) { d.lo = d.self; d.hi = d.self; }
+    d.all[e->strip_rank] = d.self;
+    if (e->peers_connected) {                   // (the neighbours' views stay; this strip's own view is refreshed)
+        if (e->strip_world == 1) { d.lo = d.self; d.hi = d.self; }
+    }
     e->tma_ok = 0;
     if (e->use_tma) CK(ss_dr_encode_tmap(e->w, e->tmap, &e->tma_ok));
     return SS_OK;
@@ -782,6 +858,7 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     if (nsteps < 0) return set_err(e, SS_ERR_ARG, "nsteps < 0");
     if (!e->have_cells || !e->have_agents) return set_err(e, SS_ERR_STATE, "upload cells and agents before stepping");
     if (e->path < 0) return set_err(e, SS_ERR_STATE, "no execution path (upload_agents failed?)");
+    if (e->strip_world > 1) return set_err(e, SS_ERR_STATE, "a strip engine steps with ss_strip_step / ss_strip_phase");
     if (nsteps == 0) return SS_OK;
     CK(cudaSetDevice(e->device));
     int rc = ensure_stats(e, nsteps);
@@ -864,6 +941,15 @@ static int fetch_population(ss_engine* e, std::vector<AgentRec>* recs_out, std::
     return SS_OK;
 }
 
+// strips: the agents standing on this strip (the population counter of the statistics covers all strips)
+static unsigned long long strip_population(ss_engine* e) {
+    unsigned long long cnt = 0;
+    cudaMemsetAsync(e->h_dev_count, 0, sizeof(unsigned long long), e->stream);
+    ss_launch_count_alive(e->w, e->h_dev_count, e->stream);
+    cudaMemcpyAsync(&cnt, e->h_dev_count, sizeof cnt, cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+    return cnt;
+}
 extern "C" int ss_agent_count(ss_engine* e) {
     if (!e || !e->have_agents) return 0;
     cudaSetDevice(e->device);
@@ -872,6 +958,7 @@ extern "C" int ss_agent_count(ss_engine* e) {
         cudaMemcpy(&cnt, e->w.n_order, sizeof cnt, cudaMemcpyDeviceToHost);
         return cnt;
     }
+    if (e->strip_world > 1) return (int)strip_population(e);
     StepAccum acc;
     cudaMemcpy(&acc, e->w.acc, sizeof acc, cudaMemcpyDeviceToHost);
     return (int)acc.population;
@@ -908,7 +995,7 @@ extern "C" int ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t
         StepAccum acc;
         CK(cudaMemcpyAsync(&acc, e->w.acc, sizeof acc, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
-        const size_t pop = (size_t)acc.population, stride = std::max<size_t>(pop, 1);
+        const size_t pop = e->strip_world > 1 ? (size_t)strip_population(e) : (size_t)acc.population, stride = std::max<size_t>(pop, 1);
         uint32_t* d_cnt = nullptr;
         int32_t* d_cols = nullptr;
         double* d_sugar = nullptr;
@@ -942,7 +1029,7 @@ extern "C" int ss_download_agents(ss_engine* e, int32_t* id, int32_t* x, int32_t
     for (size_t i = 0; i < order.size(); i++) {
         const AgentRec& r = recs[order[i]];
         if (id) id[i] = order[i] + 1;
-        if (x) x[i] = (int32_t)(r.pos / N);
+        if (x) x[i] = e->x0 + (int32_t)(r.pos / N);
         if (y) y[i] = (int32_t)(r.pos % N);
         if (vision) vision[i] = attr_vision(r.attr);
         if (metab) metab[i] = attr_metab(r.attr);
@@ -1011,6 +1098,8 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "window") { e->window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "solo_window") { e->solo_window_max = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "tma") { e->use_tma = (int)value; return SS_OK; }
+    if (k == "global_slots") { e->global_slots = (uint32_t)value; return SS_OK; }
+    if (k == "global_vmax") { e->global_vmax = (int)value; return SS_OK; }
     if (k == "l2_persist") { e->l2_persist = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
@@ -1152,5 +1241,215 @@ extern "C" int ss_shard_end_step(ss_engine* e, ss_step_stats* out) {
     if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->syncs++;
+    return SS_OK;
+}
+
+
+// ------------------------------------------------------------------------------- row strips ----
+// One engine per GPU holds a strip of lattice rows and the agents standing on it; the kernels of ss_rounds.cu reach the
+// two ring neighbours' rows (halo of the conflict graph, crosses and moves across the border, migrating records) and
+// every strip's counters (Q1 notifications) through peer-mapped device pointers.  sugarscape_utilicalc_b200/strips.py.
+#define SS_STRIP_NPTR 11
+static void strip_ptrs(ss_engine* e, void* p[SS_STRIP_NPTR]) {
+    const DrPeer& s = e->w.dr.self;
+    void* v[SS_STRIP_NPTR] = {s.occw, s.mw, s.mwx, s.sugar, s.dep, s.queue, s.ctl, s.agents, s.delta, s.acc, s.hist};
+    for (int k = 0; k < SS_STRIP_NPTR; k++) p[k] = v[k];
+}
+static int strip_attach(ss_engine* e, int peer_rank, void* const p[SS_STRIP_NPTR]) {
+    const int P = e->strip_world, N = e->w.n;
+    DrPeer q;
+    memset(&q, 0, sizeof q);
+    q.occw = (uint32_t*)p[0]; q.mw = (uint8_t*)p[1]; q.mwx = (uint8_t*)p[2]; q.sugar = (double*)p[3]; q.poll = nullptr;
+    q.dep = (uint32_t*)p[4]; q.queue = (uint32_t*)p[5]; q.ctl = (unsigned int*)p[6]; q.agents = (AgentRec*)p[7];
+    q.delta = (uint32_t*)p[8]; q.acc = (unsigned long long*)p[9]; q.hist = (uint32_t*)p[10];
+    q.x0 = (int)(((long long)peer_rank * N) / P);
+    q.rows = (int)(((long long)(peer_rank + 1) * N) / P) - q.x0;
+    DrState& d = e->w.dr;
+    d.all[peer_rank] = q;
+    if (peer_rank == (e->strip_rank + P - 1) % P) d.lo = q;
+    if (peer_rank == (e->strip_rank + 1) % P) d.hi = q;
+    e->peers_connected++;
+    return SS_OK;
+}
+static int strip_ready(ss_engine* e, const char* what) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (e->strip_world < 2) return set_err(e, SS_ERR_STATE, std::string(what) + ": not a strip engine (ss_create_strip with world > 1)");
+    if (!e->have_cells || !e->have_agents || e->path != PATH_LATTICE || e->pass_impl != 3)
+        return set_err(e, SS_ERR_STATE, std::string(what) + ": upload the strip's cells and agents first");
+    return SS_OK;
+}
+
+// the strip's peer-visible arrays as raw device pointers (peers in the same process) ...
+extern "C" int ss_strip_export(ss_engine* e, uint64_t* ptrs) {
+    int rc = strip_ready(e, "ss_strip_export");
+    if (rc) return rc;
+    void* p[SS_STRIP_NPTR];
+    strip_ptrs(e, p);
+    for (int k = 0; k < SS_STRIP_NPTR; k++) ptrs[k] = (uint64_t)(uintptr_t)p[k];
+    return SS_OK;
+}
+// ... and as CUDA IPC handles (one process per GPU): SS_STRIP_NPTR x 64 bytes
+extern "C" int ss_strip_ipc_export(ss_engine* e, void* handles) {
+    int rc = strip_ready(e, "ss_strip_ipc_export");
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    void* p[SS_STRIP_NPTR];
+    strip_ptrs(e, p);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int k = 0; k < SS_STRIP_NPTR; k++) CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handles) + k, p[k]));
+    return SS_OK;
+}
+extern "C" int ss_strip_connect(ss_engine* e, int32_t peer_rank, const uint64_t* ptrs) {
+    int rc = strip_ready(e, "ss_strip_connect");
+    if (rc) return rc;
+    if (peer_rank < 0 || peer_rank >= e->strip_world || peer_rank == e->strip_rank || !ptrs) return set_err(e, SS_ERR_ARG, "bad peer");
+    void* p[SS_STRIP_NPTR];
+    for (int k = 0; k < SS_STRIP_NPTR; k++) p[k] = (void*)(uintptr_t)ptrs[k];
+    return strip_attach(e, peer_rank, p);
+}
+extern "C" int ss_strip_ipc_connect(ss_engine* e, int32_t peer_rank, const void* handles) {
+    int rc = strip_ready(e, "ss_strip_ipc_connect");
+    if (rc) return rc;
+    if (peer_rank < 0 || peer_rank >= e->strip_world || peer_rank == e->strip_rank || !handles) return set_err(e, SS_ERR_ARG, "bad peer");
+    CK(cudaSetDevice(e->device));
+    void* p[SS_STRIP_NPTR];
+    for (int k = 0; k < SS_STRIP_NPTR; k++) {
+        CK(cudaIpcOpenMemHandle(&p[k], reinterpret_cast<const cudaIpcMemHandle_t*>(handles)[k], cudaIpcMemLazyEnablePeerAccess));
+        e->ipc_ptrs[peer_rank][k] = p[k];
+    }
+    e->peers_ipc = true;
+    return strip_attach(e, peer_rank, p);
+}
+
+// After the uploads: the strip's cell bytes and agent flags, and the replicated directories (alive / at-risk bitmaps,
+// the strip that holds each agent) from the agents of the WHOLE world -- every rank passes the same arrays.
+extern "C" int ss_strip_init_directory(ss_engine* e, int32_t n_all, const int32_t* id, const int32_t* x, const int32_t* metab,
+                                       const double* sugar) {
+    int rc = strip_ready(e, "ss_strip_init_directory");
+    if (rc) return rc;
+    if (n_all < 0 || (n_all > 0 && (!id || !x || !metab || !sugar))) return set_err(e, SS_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t nn = (size_t)std::max(n_all, 1);
+    int32_t* d_i32 = nullptr;
+    double* d_f64 = nullptr;
+    struct Staging { int32_t*& a; double*& b; ~Staging() { cudaFree(a); cudaFree(b); } } staging{d_i32, d_f64};
+    CK(cudaMalloc(&d_i32, sizeof(int32_t) * 3 * nn));
+    CK(cudaMalloc(&d_f64, sizeof(double) * nn));
+    const int32_t* cols[3] = {id, x, metab};
+    for (int k = 0; k < 3 && n_all > 0; k++) CK(cudaMemcpyAsync(d_i32 + k * nn, cols[k], sizeof(int32_t) * n_all, cudaMemcpyHostToDevice, e->stream));
+    if (n_all > 0) CK(cudaMemcpyAsync(d_f64, sugar, sizeof(double) * n_all, cudaMemcpyHostToDevice, e->stream));
+    const size_t words = (size_t)(e->dr_slots + 31) / 32 + 1;
+    CK(cudaMemsetAsync(e->w.dr.alive, 0, sizeof(uint32_t) * words, e->stream));
+    CK(cudaMemsetAsync(e->w.dr.atrisk, 0, sizeof(uint32_t) * words, e->stream));
+    CK(ss_launch_dr_directory(e->w, n_all, d_i32, d_i32 + nn, d_i32 + 2 * nn, d_f64, e->stream));
+    int flag = 0;
+    CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
+    CK(ss_launch_dr_mirror(e->w, e->d_flags, e->stream));
+    CK(cudaMemcpyAsync(&flag, e->d_flags, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    StepAccum acc;
+    memset(&acc, 0, sizeof acc);
+    acc.population = (unsigned long long)n_all;
+    CK(cudaMemcpyAsync(e->w.dr.acc_g, &acc, sizeof acc, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->launches += 4; e->syncs++;
+    if (flag) return set_err(e, SS_ERR_UNSUPPORTED, "dependency rounds need cell sugar and capacities < 127");
+    e->mirror = 2;
+    return SS_OK;
+}
+
+static int strip_connected(ss_engine* e, const char* what) {
+    int rc = strip_ready(e, what);
+    if (rc) return rc;
+    if (e->peers_connected < e->strip_world - 1) return set_err(e, SS_ERR_STATE, std::string(what) + ": connect every peer strip first");
+    if (e->mirror != 2) return set_err(e, SS_ERR_STATE, std::string(what) + ": ss_strip_init_directory first");
+    return SS_OK;
+}
+static int strip_begin_build(ss_engine* e) {
+    e->dr_dirty = true;
+    CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
+    CK(ss_launch_prepare(e->w, e->iteration, 0, e->stream));
+    CK(ss_launch_dr_build(e->w, e->iteration, e->tmap, e->tma_ok && e->use_tma, e->stream));
+    e->launches += 5;
+    return SS_OK;
+}
+static int strip_finish(ss_engine* e, int stats_index) {
+    DevWorld g = e->w;                          // the statistics kernel on the merged sums
+    g.acc = reinterpret_cast<StepAccum*>(e->w.dr.acc_g);
+    g.hist = e->w.dr.hist_g;
+    CK(ss_launch_stats(g, stats_index, e->stream));
+    e->launches++;
+    int rc = env_phase(e);
+    if (rc) return rc;
+    e->iteration++; e->env_time++; e->steps++;
+    e->stepped = true;
+    return SS_OK;
+}
+
+// Host-driven phases (several strips on one GPU, driven by one process: tests).  0: begin + conflict graph; 1: one round
+// over the queue segment [seg_begin, seg_end); 2: after the rounds (statistics merged over the strips, delta lists
+// applied); 3: statistics + growback.  Every strip finishes a phase before any strip starts the next one.
+// *tail_out = the strip's queue tail after the phase; *stats_out (phase 3) = the step's statistics.
+extern "C" int ss_strip_phase(ss_engine* e, int32_t phase, uint32_t seg_begin, uint32_t seg_end, uint32_t* tail_out, ss_step_stats* stats_out) {
+    int rc = strip_connected(e, "ss_strip_phase");
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    if (phase == 0) {
+        rc = ensure_stats(e, 1);
+        if (rc) return rc;
+        rc = strip_begin_build(e);
+        if (rc) return rc;
+    } else if (phase == 1) {
+        if (seg_end > seg_begin) {
+            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 1, seg_begin, seg_end, e->stream));
+            e->launches++;
+        }
+    } else if (phase == 2) {
+        CK(ss_launch_dr_check(e->w, e->stream));
+        CK(ss_launch_dr_after_rounds(e->w, e->stream));
+        e->launches += 3; e->passes++;
+    } else if (phase == 3) {
+        rc = strip_finish(e, 0);
+        if (rc) return rc;
+        if (stats_out) CK(cudaMemcpyAsync(stats_out, e->w.stats, sizeof(ss_step_stats), cudaMemcpyDeviceToHost, e->stream));
+    } else return set_err(e, SS_ERR_ARG, "bad phase");
+    uint32_t tail = 0;
+    CK(cudaMemcpyAsync(&tail, e->w.dr.self.ctl, sizeof tail, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    if (tail_out) *tail_out = tail;
+    return SS_OK;
+}
+
+// One process per GPU: nsteps timesteps with the strips synchronised on the device (barriers over peer memory between
+// the phases and between the rounds); no host round trip inside a step.
+extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
+    int rc = strip_connected(e, "ss_strip_step");
+    if (rc) return rc;
+    if (nsteps < 0) return set_err(e, SS_ERR_ARG, "nsteps < 0");
+    if (nsteps == 0) return SS_OK;
+    CK(cudaSetDevice(e->device));
+    rc = ensure_stats(e, nsteps);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->evs, e->stream));
+    for (int t = 0; t < nsteps; t++) {
+        rc = strip_begin_build(e);
+        if (rc) return rc;
+        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // every strip's counters and queue are set up
+        CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
+        CK(ss_launch_dr_check(e->w, e->stream));
+        CK(ss_launch_dr_after_rounds(e->w, e->stream));
+        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // everybody has read everybody's sums and delta list
+        rc = strip_finish(e, t);
+        if (rc) return rc;
+        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // every strip's growback is done: the halos are final
+        e->launches += 7; e->passes++;
+    }
+    CK(cudaEventRecord(e->eve, e->stream));
+    if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->evs, e->eve);
+    e->kt[KT_LAST_CALL] = ms;
     return SS_OK;
 }

@@ -2365,14 +2365,18 @@ __global__ void ss_isugar_kernel(const double* __restrict__ sugar, const double*
     }
 }
 // agent store + occupancy words from the uploaded View.agents arrays; err: 1 duplicate id, 2 two agents on a cell
-__global__ void ss_build_agents_kernel(int n, int N, uint32_t phase, const int32_t* __restrict__ id, const int32_t* __restrict__ x,
+__global__ void ss_validate_rows_kernel(int n, const int32_t* __restrict__ x, int x0, int rows, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (x[i] < x0 || x[i] >= x0 + rows)) *out = 1;
+}
+__global__ void ss_build_agents_kernel(int n, int N, int x0, uint32_t phase, const int32_t* __restrict__ id, const int32_t* __restrict__ x,
                                        const int32_t* __restrict__ y, const int32_t* __restrict__ vision,
                                        const int32_t* __restrict__ metab, const double* __restrict__ sugar, AgentRec* recs,
                                        uint32_t* occw, int32_t* order, int* err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t s = (uint32_t)id[i] - 1u;
-    const uint32_t c = (uint32_t)x[i] * (uint32_t)N + (uint32_t)y[i];
+    const uint32_t c = (uint32_t)(x[i] - x0) * (uint32_t)N + (uint32_t)y[i];
     const uint32_t attr = attr_pack(vision[i], metab[i], true);
     if (atomicCAS(&recs[s].attr, 0u, attr) != 0u) { atomicMax(err, 1); return; }
     if (atomicCAS(&occw[c], 0u, occ_pack(s, vision[i], phase)) != 0u) { atomicMax(err, 2); return; }
@@ -2402,6 +2406,11 @@ __global__ void ss_validate_agents_kernel(int n, int N, const int32_t* __restric
         atomicMax(&out[1], mid);
         atomicMax(&out[2], mv);
     }
+}
+__global__ void ss_count_alive_kernel(const AgentRec* __restrict__ agents, uint32_t n_slots, unsigned long long* out) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = __ballot_sync(0xffffffffu, slot < n_slots && attr_alive(agents[slot].attr));
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 __global__ void ss_occ_ids_kernel(const uint32_t* __restrict__ occw, int32_t* __restrict__ ids, size_t cells) {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
@@ -2470,7 +2479,7 @@ ss_export_scan_kernel(uint32_t* __restrict__ blockcnt, uint32_t nblocks, uint32_
     if (threadIdx.x == 0) *total = carry;
 }
 __global__ void __launch_bounds__(EXPORT_THREADS)
-ss_export_emit_kernel(const AgentRec* __restrict__ agents, OrderKey ok, uint32_t n_slots, uint32_t domain, int n,
+ss_export_emit_kernel(const AgentRec* __restrict__ agents, OrderKey ok, uint32_t n_slots, uint32_t domain, int n, int x0,
                       const uint32_t* __restrict__ blockoff, int32_t* __restrict__ id, int32_t* __restrict__ x,
                       int32_t* __restrict__ y, int32_t* __restrict__ vision, int32_t* __restrict__ metab,
                       double* __restrict__ sugar) {
@@ -2492,7 +2501,7 @@ ss_export_emit_kernel(const AgentRec* __restrict__ agents, OrderKey ok, uint32_t
         if (!((live >> k) & 1u)) continue;
         const AgentRec r = agents[slot[k]];
         id[at] = (int32_t)(slot[k] + 1u);
-        x[at] = (int32_t)(r.pos / (uint32_t)n);
+        x[at] = x0 + (int32_t)(r.pos / (uint32_t)n);
         y[at] = (int32_t)(r.pos % (uint32_t)n);
         vision[at] = attr_vision(r.attr);
         metab[at] = attr_metab(r.attr);
@@ -2505,13 +2514,13 @@ ss_export_emit_kernel(const AgentRec* __restrict__ agents, OrderKey ok, uint32_t
 extern "C" {
 
 cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s) {
-    ss_isugar_kernel<<<148 * 8, 256, 0, s>>>(w.sugar, w.cap, w.isugar, (size_t)w.n * w.n, flag);
+    ss_isugar_kernel<<<148 * 8, 256, 0, s>>>(w.sugar, w.cap, w.isugar, (size_t)w.rows * w.n, flag);
     return cudaGetLastError();
 }
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s) {
     if (n > 0)
-        ss_build_agents_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, w.n, phase, id, x, y, vision, metab, sugar, w.agents, w.occw,
+        ss_build_agents_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, w.n, w.x0, phase, id, x, y, vision, metab, sugar, w.agents, w.occw,
                                                                w.order, err);
     return cudaGetLastError();
 }
@@ -2524,8 +2533,12 @@ cudaError_t ss_launch_export_agents(const DevWorld& w, uint64_t step_key, uint32
     const uint32_t nb = ss_export_blocks(domain);
     ss_export_count_kernel<<<nb, EXPORT_THREADS, 0, s>>>(w.agents, ok, w.n_slots, domain, blockcnt);
     ss_export_scan_kernel<<<1, 1024, 0, s>>>(blockcnt, nb, total);
-    ss_export_emit_kernel<<<nb, EXPORT_THREADS, 0, s>>>(w.agents, ok, w.n_slots, domain, w.n, blockcnt, cols, cols + stride,
+    ss_export_emit_kernel<<<nb, EXPORT_THREADS, 0, s>>>(w.agents, ok, w.n_slots, domain, w.n, w.x0, blockcnt, cols, cols + stride,
                                                        cols + 2 * stride, cols + 3 * stride, cols + 4 * stride, sugar);
+    return cudaGetLastError();
+}
+cudaError_t ss_launch_validate_rows(int n, const int32_t* x, int x0, int rows, int* out, cudaStream_t s) {
+    if (n > 0) ss_validate_rows_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, x, x0, rows, out);
     return cudaGetLastError();
 }
 cudaError_t ss_launch_validate_agents(int n, int N, const int32_t* id, const int32_t* x, const int32_t* y, const int32_t* vision,
@@ -2533,8 +2546,12 @@ cudaError_t ss_launch_validate_agents(int n, int N, const int32_t* id, const int
     if (n > 0) ss_validate_agents_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, N, id, x, y, vision, metab, out3);
     return cudaGetLastError();
 }
+cudaError_t ss_launch_count_alive(const DevWorld& w, unsigned long long* out, cudaStream_t s) {
+    if (w.n_slots) ss_count_alive_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w.agents, w.n_slots, out);
+    return cudaGetLastError();
+}
 cudaError_t ss_launch_occ_ids(const DevWorld& w, int32_t* ids, cudaStream_t s) {
-    ss_occ_ids_kernel<<<148 * 8, 256, 0, s>>>(w.occw, ids, (size_t)w.n * w.n);
+    ss_occ_ids_kernel<<<148 * 8, 256, 0, s>>>(w.occw, ids, (size_t)w.rows * w.n);
     return cudaGetLastError();
 }
 

@@ -60,7 +60,7 @@ __device__ static inline DrLoc dr_loc(const DevWorld& w, int gx, int gy) {
     if ((unsigned)r < (unsigned)w.dr.self.rows) { L.which = 0; L.idx = (uint32_t)r * (uint32_t)w.n + (uint32_t)gy; return L; }
     int below = w.dr.self.x0 - gx;               // 1.. if gx is just below the strip (mod n)
     if (below < 0) below += w.n;
-    if (below <= 4 * SS_MAX_VISION && below <= w.dr.lo.rows) {
+    if (below <= 2 * w.vmax) {
         L.which = 1; L.idx = (uint32_t)(w.dr.lo.rows - below) * (uint32_t)w.n + (uint32_t)gy; return L;
     }
     int above = gx - (w.dr.self.x0 + w.dr.self.rows);
@@ -70,6 +70,7 @@ __device__ static inline DrLoc dr_loc(const DevWorld& w, int gx, int gy) {
 }
 #define DR_W(field, which) ((!STRIPS || (which) == 0) ? w.dr.self.field : ((which) == 1 ? w.dr.lo.field : w.dr.hi.field))
 #define DR_F(field, L) DR_W(field, (L).which)
+#define DR_A(field, rank) (STRIPS ? w.dr.all[(rank)].field : w.dr.self.field)
 // the transposed cell byte of local cell idx = r * n + y of strip `which`: y * rows + r
 template <bool STRIPS>
 __device__ static inline size_t dr_xidx(const DevWorld& w, const DrLoc& L) {
@@ -211,8 +212,57 @@ __global__ void ss_dr_flags_kernel(DevWorld w) {
         }
     }
     const unsigned ba = __ballot_sync(FULL, alive), br = __ballot_sync(FULL, risk);
-    if ((threadIdx.x & 31) == 0 && (slot >> 5) < ((w.n_slots + 31) >> 5)) { w.dr.alive[slot >> 5] = ba; w.dr.atrisk[slot >> 5] = br; }
+    // (strips: the bitmaps cover the agents of every strip and come from ss_dr_directory_kernel)
+    if (w.dr.world == 1 && (threadIdx.x & 31) == 0 && (slot >> 5) < ((w.n_slots + 31) >> 5)) { w.dr.alive[slot >> 5] = ba; w.dr.atrisk[slot >> 5] = br; }
 }
+// strips: the replicated directories from the agents of the WHOLE world (every rank gets the same arrays at upload):
+// alive / at-risk bitmaps and the strip that holds each agent
+__global__ void ss_dr_directory_kernel(DevWorld w, int n_all, const int32_t* __restrict__ id, const int32_t* __restrict__ x,
+                                       const int32_t* __restrict__ metab, const double* __restrict__ sugar) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    const uint32_t slot = (uint32_t)id[i] - 1u;
+    if (slot >= w.n_slots) return;
+    atomicOr(&w.dr.alive[slot >> 5], 1u << (slot & 31));
+    if (dr_at_risk(w, sugar[i], metab[i])) atomicOr(&w.dr.atrisk[slot >> 5], 1u << (slot & 31));
+    w.dr.home[slot] = (uint8_t)(((long long)(x[i] + 1) * w.dr.world - 1) / w.n);      // rows [r n / P, (r + 1) n / P) belong to rank r
+}
+// strips, after the rounds: every rank applies every strip's delta list to its replicated directories
+__global__ void __launch_bounds__(256)
+ss_dr_apply_delta_kernel(DevWorld w) {
+    const int p = blockIdx.y;
+    if (p >= w.dr.world) return;
+    const DrPeer& P = w.dr.all[p];
+    const unsigned cnt = __ldcg(&P.ctl[DR_CTL_DELTA]);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t e = __ldcg(&P.delta[i]);
+        const uint32_t slot = e & OCC_SLOT_MASK, kind = e >> 24;
+        if (kind & DR_DELTA_DIED) atomicAnd(&w.dr.alive[slot >> 5], ~(1u << (slot & 31)));
+        if (kind & DR_DELTA_RISK) atomicXor(&w.dr.atrisk[slot >> 5], 1u << (slot & 31));
+        if (kind & DR_DELTA_TO_LO) w.dr.home[slot] = (uint8_t)(p == 0 ? w.dr.world - 1 : p - 1);
+        if (kind & DR_DELTA_TO_HI) w.dr.home[slot] = (uint8_t)(p == w.dr.world - 1 ? 0 : p + 1);
+    }
+}
+// strips: the step's sums and the wealth histogram over all strips (every rank computes the same statistics)
+__global__ void __launch_bounds__(256)
+ss_dr_merge_stats_kernel(DevWorld w) {
+    const int P = w.dr.world;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SS_GINI_BINS; i += gridDim.x * blockDim.x) {
+        uint32_t h = 0;
+        for (int p = 0; p < P; p++) h += __ldcg(&w.dr.all[p].hist[i]);
+        w.dr.hist_g[i] = h;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        // StepAccum: sum_metab, sum_vision, acted, deaths, pending, population, hist_small, inexact, fault, ...
+        const int f = threadIdx.x == 4 ? 8 : threadIdx.x;        // (pending is per strip: its slot carries the faults here)
+        if (f != 5) {
+            unsigned long long v = 0;
+            for (int p = 0; p < P; p++) v += __ldcg(&w.dr.all[p].acc[f]);
+            w.dr.acc_g[f] = v;
+        }
+    }
+}
+
 
 // -------------------------------------------------------------------------------- build ----
 __device__ static inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -508,6 +558,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
         __syncwarp();
     }
     __syncthreads();
+    if (tid == 0 && nl) atomicAdd(&S.ctl[DR_CTL_AGENTS], (unsigned)nl);
     if (tid == 0 && s_ready) s_base = atomicAdd(&S.ctl[0], (unsigned)s_ready);
     __syncthreads();
     if (s_ready) {
@@ -770,11 +821,19 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         DR_F(mw, D)[D.idx] = new_mw;
         DR_F(mwx, D)[dr_xidx<STRIPS>(w, D)] = new_mw;
         attr = (attr & ~ATTR_RISK) | (risk_next ? ATTR_RISK : 0u);
-        if (died) {
-            attr &= ~ATTR_ALIVE; acc.deaths++;
-            atomicAnd(&w.dr.alive[slot >> 5], ~(1u << (slot & 31)));
+        if (died) { attr &= ~ATTR_ALIVE; acc.deaths++; }
+        if (!STRIPS) {
+            if (died) atomicAnd(&w.dr.alive[slot >> 5], ~(1u << (slot & 31)));
+            if (risk_next != risky) atomicXor(&w.dr.atrisk[slot >> 5], 1u << (slot & 31));
+        } else {
+            // the directories are replicated on every strip: what changed goes to this strip's delta list
+            const uint32_t kind = (died ? DR_DELTA_DIED : 0u) | (risk_next != risky ? DR_DELTA_RISK : 0u) |
+                                  (D.which == 1 ? DR_DELTA_TO_LO : 0u) | (D.which == 2 ? DR_DELTA_TO_HI : 0u);
+            if (kind) {
+                const unsigned at = atomicAdd(&S.ctl[DR_CTL_DELTA], 1u);
+                if (at < w.dr.delta_cap) S.delta[at] = slot | (kind << 24); else acc.fault++;
+            }
         }
-        if (risk_next != risky) atomicXor(&w.dr.atrisk[slot >> 5], 1u << (slot & 31));
         AgentRec* dst = &DR_F(agents, D)[slot];                    // the record travels with the agent
         uint4 nr;
         const unsigned long long sb = (unsigned long long)__double_as_longlong(sugar);
@@ -785,11 +844,16 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
     // Q1: whoever follows this agent in the list order learns the outcome (a skipped agent did not die)
     if (risky && qw.y == (uint32_t)(st.iteration + 1)) {
         const uint32_t s2 = qw.x & OCC_SLOT_MASK;
-        const int which = STRIPS ? (int)((qw.x >> 24) & 3u) : 0;
+        const int home = STRIPS ? (int)w.dr.home[s2] : 0;              // the successor may stand anywhere on the lattice
         const int shf = (int)(s2 & 1u) << 4;
-        uint32_t* wp = &DR_W(dep, which)[s2 >> 1];
+        uint32_t* wp = &DR_A(dep, home)[s2 >> 1];
         const uint32_t old = died ? atomicAdd(wp, 0x7fffu << shf) : atomicSub(wp, 1u << shf);
-        dr_released<STRIPS>(w, sh, warp, acc, qw.x, old, died);
+        const uint32_t h = (old >> shf) & 0xffffu;
+        if ((h & 0x7fffu) == 1u) {
+            const uint32_t e = s2 | ((died || (h >> 15)) ? DR_SKIP : 0u);
+            if (!STRIPS || home == w.dr.rank) dr_push(w, sh, warp, e);
+            else DR_A(queue, home)[atomicAdd(&DR_A(ctl, home)[DR_CTL_TAIL], 1u)] = e;
+        } else if ((h & 0x7fffu) == 0u) acc.fault++;
     }
     // conflict successors: all decrements of the record are issued before the first result is looked at
     {
@@ -817,38 +881,85 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
     }
 }
 
+// Barrier over the strips (one GPU each) through peer memory: every strip publishes the next sequence number into
+// every strip's flag words (stores over NVLink) and waits until its own words show that number from everybody.
+// One thread; the caller has made this strip's writes visible to it (grid barrier / kernel boundary).
+#define DR_CTL_SEQ 11
+__device__ static inline bool dr_strip_sync(const DevWorld& w, unsigned seq, int word, unsigned payload, unsigned* any_payload) {
+    const int P = w.dr.world, me = w.dr.rank;
+    __threadfence_system();
+    for (int p = 0; p < P; p++) *(volatile unsigned*)&w.dr.all[p].ctl[DR_CTL_FLAGS + 2 * me + word] = (seq << 1) | (payload & 1u);
+    unsigned any = 0;
+    bool ok = true;
+    for (int p = 0; p < P; p++) {
+        unsigned v, spins = 0;
+        while (((v = *(volatile unsigned*)&w.dr.self.ctl[DR_CTL_FLAGS + 2 * p + word]) >> 1) < seq) {
+            __nanosleep(20);
+            if (++spins > (1u << 26)) { ok = false; break; }           // a lost peer: do not hang the GPU
+        }
+        any |= v & 1u;
+    }
+    __threadfence_system();
+    if (any_payload) *any_payload = any;
+    return ok;
+}
+__global__ void ss_dr_strip_barrier_kernel(DevWorld w) {
+    unsigned int* ctl = w.dr.self.ctl;
+    const unsigned seq = ++ctl[DR_CTL_SEQ];
+    if (!dr_strip_sync(w, seq, 0, 0u, nullptr)) atomicAdd(&w.acc->fault, 1ull);
+}
+
 // Grid barrier between rounds (cooperative launch: all CTAs are resident).  The last CTA to arrive snapshots the queue
 // tail into ctl[3 + (generation & 1)] before it releases the others, so every CTA sees the same next segment even if a
-// fast CTA is already appending to the queue again.  Returns the snapshot.
-__device__ static inline unsigned dr_grid_barrier(unsigned int* ctl, unsigned nblocks, DrAccum& acc, unsigned* s_tail) {
+// fast CTA is already appending to the queue again.  With strips on several GPUs (XSYNC) the same CTA first waits for
+// every strip to finish the round -- their turns may have queued agents here -- and then learns whether any strip has
+// work left.  Returns the snapshot; *more = the agent phase goes on.
+template <bool XSYNC>
+__device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nblocks, unsigned seg_end, DrAccum& acc,
+                                                  unsigned* s_tail, bool* more) {
+    unsigned int* ctl = w.dr.self.ctl;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned gen = *(volatile unsigned*)&ctl[2];
         if (atomicAdd(&ctl[1], 1u) == nblocks - 1u) {
             ctl[1] = 0u;
-            *(volatile unsigned*)&ctl[3 + (gen & 1u)] = *(volatile unsigned*)&ctl[0];
+            unsigned any = 0;
+            if (XSYNC) {
+                const unsigned seq = ++ctl[DR_CTL_SEQ];
+                if (!dr_strip_sync(w, seq, 0, 0u, nullptr)) acc.fault++;
+                const unsigned tail = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
+                if (!dr_strip_sync(w, seq, 1, tail != seg_end ? 1u : 0u, &any)) acc.fault++;
+                *(volatile unsigned*)&ctl[3 + (gen & 1u)] = tail;
+            } else {
+                const unsigned tail = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
+                *(volatile unsigned*)&ctl[3 + (gen & 1u)] = tail;
+                any = tail != seg_end ? 1u : 0u;
+            }
+            *(volatile unsigned*)&ctl[DR_CTL_MORE + (gen & 1u)] = any;
             __threadfence();
             atomicAdd(&ctl[2], 1u);
         } else {
             unsigned spins = 0;
             while (*(volatile unsigned*)&ctl[2] == gen) {
                 __nanosleep(32);
-                if (++spins > (1u << 26)) { acc.fault++; break; }      // a lost CTA: do not hang the GPU
+                if (++spins > (1u << 27)) { acc.fault++; break; }      // a lost CTA: do not hang the GPU
             }
         }
         __threadfence();
-        *s_tail = *(volatile unsigned*)&ctl[3 + (gen & 1u)];
+        s_tail[0] = *(volatile unsigned*)&ctl[3 + (gen & 1u)];
+        s_tail[1] = *(volatile unsigned*)&ctl[DR_CTL_MORE + (gen & 1u)];
     }
     __syncthreads();
-    return *s_tail;
+    *more = s_tail[1] != 0u;
+    return s_tail[0];
 }
 
-template <int POLT, bool STRIPS>
+template <int POLT, bool STRIPS, bool XSYNC>
 __global__ void __launch_bounds__(DR_THREADS, 2)
 ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __shared__ DrShared sh;
-    __shared__ unsigned s_tail;
+    __shared__ unsigned s_tail[2];
     const DrPeer& S = w.dr.self;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < DR_HIST_BINS; i += DR_THREADS) sh.hist[i] = 0u;
@@ -857,11 +968,10 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __syncthreads();
     DrAccum acc = {0, 0, 0, 0, 0, 0, 0};
     unsigned seg_b = st.single_round ? st.seg_begin : 0u;
-    unsigned seg_e = st.single_round ? st.seg_end : __ldcg(&S.ctl[5]);     // ctl[5]: tail after the build (ss_dr_seg0_kernel)
+    unsigned seg_e = st.single_round ? st.seg_end : __ldcg(&S.ctl[DR_CTL_TAIL0]);       // the tail after the build (ss_dr_seg0_kernel)
     const unsigned gwarp = blockIdx.x * DR_WARPS + (unsigned)warp, nwarp = gridDim.x * DR_WARPS;
     for (;;) {
         const unsigned cnt = seg_e - seg_b;
-        if (cnt == 0u) break;
         // a warp takes 32 consecutive queue entries at a time; no CTA-wide barrier inside a round
         for (unsigned base = gwarp * 32u; base < cnt; base += nwarp * 32u) {
             const unsigned i = base + (unsigned)lane;
@@ -872,7 +982,9 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
         dr_flush(w, sh, warp, lane);
         if (st.single_round) break;
         seg_b = seg_e;
-        seg_e = dr_grid_barrier(S.ctl, st.nblocks, acc, &s_tail);
+        bool more;
+        seg_e = dr_grid_barrier<XSYNC>(w, st.nblocks, seg_e, acc, s_tail, &more);
+        if (!more) break;
     }
     // statistics of this CTA's turns (sugarscape.py:575-583)
     unsigned vals[7] = {acc.sum_m, acc.sum_v, acc.acted, acc.deaths, acc.small, acc.inexact, acc.fault};
@@ -895,12 +1007,15 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
 // every agent that was alive at the start of the step must have passed through the queue; the successor pool must
 // have held every list
 __global__ void ss_dr_check_kernel(DevWorld w) {
-    if (w.dr.self.ctl[0] != (unsigned)w.acc->pending) atomicAdd(&w.acc->fault, 1ull);
+    if (w.dr.self.ctl[DR_CTL_TAIL] != w.dr.self.ctl[DR_CTL_AGENTS]) atomicAdd(&w.acc->fault, 1ull);
     if (w.dr.self.ctl[7]) atomicAdd(&w.acc->fault, 1ull);
     w.acc->pending = 0ull;
 }
-__global__ void ss_dr_begin_kernel(DevWorld w) { w.dr.self.ctl[0] = 0u; w.dr.self.ctl[6] = 0u; }
-__global__ void ss_dr_seg0_kernel(DevWorld w) { w.dr.self.ctl[5] = w.dr.self.ctl[0]; }
+__global__ void ss_dr_begin_kernel(DevWorld w) {
+    unsigned int* c = w.dr.self.ctl;
+    c[DR_CTL_TAIL] = 0u; c[DR_CTL_POOL] = 0u; c[DR_CTL_DELTA] = 0u; c[DR_CTL_AGENTS] = 0u;
+}
+__global__ void ss_dr_seg0_kernel(DevWorld w) { w.dr.self.ctl[DR_CTL_TAIL0] = w.dr.self.ctl[DR_CTL_TAIL]; }
 
 // ---------------------------------------------------------------------------- launchers ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -920,21 +1035,21 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int POLT, bool STRIPS>
+template <int POLT, bool STRIPS, bool XSYNC>
 static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cudaStream_t s) {
     static int per_sm = 0;
     if (!per_sm) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS>, DR_THREADS, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS, XSYNC>, DR_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     st.nblocks = (unsigned)(per_sm * sm_count);
     if (st.single_round) {
-        ss_dr_rounds_kernel<POLT, STRIPS><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
+        ss_dr_rounds_kernel<POLT, STRIPS, XSYNC><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
         return cudaGetLastError();
     }
     void* args[2] = {(void*)&w, (void*)&st};
-    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS, XSYNC>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
 }
 
 extern "C" {
@@ -1019,7 +1134,7 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     if (use_tma) memcpy(&tm, tmap_storage, sizeof tm);
-    const bool strips = w.dr.self.rows != w.n;
+    const bool strips = w.dr.world > 1;
     const int grid = tiles_x * ba.tiles_y;
     if (w.vmax <= 7) {
         if (strips) ss_dr_build_kernel<true, false><<<grid, DR_BUILD_THREADS, smem, s>>>(w, ba, tm);
@@ -1041,9 +1156,27 @@ cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t en
     st.next_phase = (uint32_t)((iteration + 1) & 1);
     st.single_round = single_round; st.seg_begin = seg_begin; st.seg_end = seg_end; st.nblocks = 0;
     const bool pol = w.cfg.rule_pollution != 0;
-    const bool strips = w.dr.self.rows != w.n;
-    if (strips) return pol ? launch_rounds<1, true>(w, st, sm_count, s) : launch_rounds<0, true>(w, st, sm_count, s);
-    return pol ? launch_rounds<1, false>(w, st, sm_count, s) : launch_rounds<0, false>(w, st, sm_count, s);
+    const bool strips = w.dr.world > 1;
+    if (strips) {                   // (strips: no pollution rule; the in-kernel barrier over the strips unless the host drives the rounds)
+        if (single_round) return launch_rounds<0, true, false>(w, st, sm_count, s);
+        return launch_rounds<0, true, true>(w, st, sm_count, s);
+    }
+    return pol ? launch_rounds<1, false, false>(w, st, sm_count, s) : launch_rounds<0, false, false>(w, st, sm_count, s);
+}
+
+cudaError_t ss_launch_dr_directory(const DevWorld& w, int n_all, const int32_t* id, const int32_t* x, const int32_t* metab,
+                                   const double* sugar, cudaStream_t s) {
+    if (n_all > 0) ss_dr_directory_kernel<<<(n_all + 255) / 256, 256, 0, s>>>(w, n_all, id, x, metab, sugar);
+    return cudaGetLastError();
+}
+cudaError_t ss_launch_dr_after_rounds(const DevWorld& w, cudaStream_t s) {
+    ss_dr_merge_stats_kernel<<<64, 256, 0, s>>>(w);
+    ss_dr_apply_delta_kernel<<<dim3(64, (unsigned)w.dr.world), 256, 0, s>>>(w);
+    return cudaGetLastError();
+}
+cudaError_t ss_launch_dr_strip_barrier(const DevWorld& w, cudaStream_t s) {
+    ss_dr_strip_barrier_kernel<<<1, 1, 0, s>>>(w);
+    return cudaGetLastError();
 }
 
 cudaError_t ss_launch_dr_check(const DevWorld& w, cudaStream_t s) {

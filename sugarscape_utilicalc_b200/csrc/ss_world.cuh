@@ -46,14 +46,38 @@ struct DrPeer {                     // one strip of lattice rows [x0, x0 + rows)
     double* poll;
     uint32_t* dep;
     uint32_t* queue;
-    unsigned int* ctl;              // [0] queue tail, [1] barrier count, [2] barrier generation, [3..4] tail snapshots, [5] tail after the build, [6] pool tail, [7] pool overflow
+    unsigned int* ctl;              // see DR_CTL_*
     AgentRec* agents;
+    uint32_t* delta;                // what this strip's turns changed in the replicated directories (alive / at-risk / home)
+    unsigned long long* acc;        // StepAccum of the strip (statistics are merged over the strips)
+    uint32_t* hist;
     int x0, rows;
 };
+// control words of a strip (device memory, written by the kernels; peers write [DR_CTL_FLAGS..) over NVLink)
+#define DR_CTL_TAIL 0               // queue tail
+#define DR_CTL_BAR 1                // grid barrier: arrivals, [2] generation, [3..4] tail snapshots
+#define DR_CTL_TAIL0 5              // queue tail after the build
+#define DR_CTL_POOL 6               // successor pool tail, [7] pool overflows
+#define DR_CTL_DELTA 8              // entries of the delta list
+#define DR_CTL_AGENTS 9             // agents the build kernel saw (every one of them must pass through the queue)
+#define DR_CTL_MORE 10              // after a round: does any strip have work left (written with the snapshots)
+#define DR_CTL_FLAGS 16             // [16 + 2r], [17 + 2r]: what strip r published (round barrier: sequence number, count)
 #define DR_CTL_WORDS 64
+#define DR_MAX_STRIPS 8
+// delta list entries: slot | kind << 24
+#define DR_DELTA_DIED 1u
+#define DR_DELTA_RISK 2u            // the at-risk bit flipped
+#define DR_DELTA_TO_LO 4u           // the agent went to the strip below / above
+#define DR_DELTA_TO_HI 8u
 #define DR_SUCC_INLINE 14
 struct DrState {
     DrPeer self, lo, hi;            // this strip and its ring neighbours (single strip: lo = hi = self)
+    DrPeer all[DR_MAX_STRIPS];      // every strip by rank (Q1 notifications, delta lists, statistics)
+    int rank, world;
+    uint8_t* home;                  // by slot: the strip that holds the agent (replicated; strips only)
+    uint32_t delta_cap;
+    unsigned long long* acc_g;      // merged StepAccum / histogram (strips: every rank computes the same statistics)
+    uint32_t* hist_g;
     uint4* succ;                    // 4 x uint4 per slot
     uint32_t* pool;
     uint32_t pool_cap;
@@ -67,6 +91,7 @@ struct DrState {
 struct DevWorld {
     ss_config cfg;
     int n;                          // lattice edge N
+    int x0, rows;                   // the lattice rows this engine holds: [x0, x0 + rows) (all of them unless it is a strip)
     uint32_t n_slots;               // max Agent.id
     int half;                       // Feistel half width for the keyed order
     double* sugar;

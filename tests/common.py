@@ -134,7 +134,7 @@ def compare_worlds(a, b, steps, exact_gini=False, every=1, what=""):
                    sugar_agent=gb["sugar"])
         assert_state_equal(ca, ga, exp, ordered=True, what="%s step %d" % (what, t + k))
     for w in (a, b):            # engines: no watchdog firing, no internal fault on the device
-        engines = [r.eng for r in w.ranks] if hasattr(w, "ranks") else [w] if hasattr(w, "health") else []
+        engines = [getattr(r, "eng", r) for r in w.ranks] if hasattr(w, "ranks") else [w] if hasattr(w, "health") else []
         for e in engines:
             assert e.health() == dict(watchdog=0, fault=0), what
 

@@ -382,6 +382,38 @@ def test_multi_gpu_replicas_on_reference_golden():
     v.close()
 
 
+@pytest.mark.parametrize("world,n,density,vision,seasons", [(2, 300, 1 / 16, (1, 6), False), (3, 512, 1 / 16, (1, 6), False),
+                                                         (4, 600, 1 / 8, (1, 6), True), (8, 1024, 1 / 16, (1, 6), False),
+                                                         (2, 260, 1 / 3, (1, 4), False), (4, 640, 1 / 16, (1, 10), False)])
+def test_row_strips_equal_oracle(world, n, density, vision, seasons):
+    """The multi-GPU decomposition (BASELINE config 5: row strips, halo reads, agent migration over peer memory) with
+    the strips of `world` ranks on one GPU: each strip holds only its rows and its agents, the kernels are the ones of
+    the real run (ss_dr_build_kernel / ss_dr_rounds_kernel with STRIPS, delta lists, merged statistics), the host stands
+    in for the device-side barriers.  Bit-exact against the CPU oracle, every step."""
+    from sugarscape_utilicalc_b200.strips import VirtualStrips
+    s, init = common.synthetic_case(n, False, density=density, vision=vision, seasons=seasons)
+    if seasons:
+        s["rule_params"]["seasons"]["period"] = 3
+    cfg = config_from_settings(s, rng_mode="keyed")
+    v, o = VirtualStrips(cfg, world), common.oracle_world(cfg)
+    common.init_world(v, init, "keyed")
+    common.init_world(o, init, "keyed")
+    common.compare_worlds(v, o, 8, what="row strips %d" % world)
+    assert sum(e.rows for e in v.ranks) == n and v.agent_count() == len(o.download_agents()["id"])
+    v.close()
+    o.close()
+
+
+def test_row_strips_on_reference_golden():
+    from sugarscape_utilicalc_b200.strips import VirtualStrips
+    g = common.load_golden("c4_synth130_nopoll_keyed")
+    cfg = config_from_settings(g["settings"], rng_mode="keyed")
+    v = VirtualStrips(cfg, 2)
+    common.init_world(v, common.golden_init(g), "keyed")
+    common.run_against_golden(g, v, exact_gini=False)
+    v.close()
+
+
 def test_full_size_c4_against_oracle():
     """BASELINE config 4 at full size (4096 x 4096, 1,048,576 agents, pollution with diffusion every step):
     the lattice path against the CPU oracle, bit-exact, three whole timesteps."""
