@@ -202,6 +202,10 @@ def run_engine_single(args, wl):
     acted2 = float(st2["acted"].sum())
     ab = algorithmic_bytes(n, wl["pollution"], acted2 / K)
     kt["move"] += kt["settle"]          # the agent phase = move passes + the deferred settle pass
+    if cnt["pass_impl"] == 3:           # dependency rounds: "prepare" is the conflict-graph kernel -- part of the agent phase
+        kt["build"] = kt["prepare"]
+        kt["move"] += kt["prepare"]
+        kt["prepare"] = 0.0
     classes = {"move": ("move", ab["move"]), "grow": ("grow", ab["grow"]), "diffuse": ("diffuse", ab["diffuse"])}
     kernels = {}
     tot = sum(kt[k] for k in ("prepare", "move", "stats", "grow", "diffuse"))
@@ -219,8 +223,10 @@ def run_engine_single(args, wl):
     # the step's launches)
     traffic_tbl = {("c5", "move", 1): 24.4e9, ("c4", "move", 1): 1.515e9, ("c4", "diffuse", 1): 210.7e6, ("c4", "diffuse", 0): 210.7e6}
     traffic = traffic_tbl.get((wl.get("key"), dom, cnt["pass_impl"]))
-    move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel", "ss_move_solo_kernel (lanes)"][cnt["pass_impl"]]
-    roofline = {"bound": "hbm", "kernel": {"move": move_kernel + " (all passes of a step) + ss_settle_kernel",
+    move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel", "ss_move_solo_kernel (lanes)",
+                   "ss_dr_build_kernel + ss_dr_rounds_kernel"][cnt["pass_impl"]]
+    roofline = {"bound": "hbm", "kernel": {"move": move_kernel + (" (conflict graph + all dependency rounds of a step)" if cnt["pass_impl"] == 3
+                                                                  else " (all passes of a step) + ss_settle_kernel"),
                                            "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic,
@@ -229,6 +235,15 @@ def run_engine_single(args, wl):
                 "ms_per_launch_set": kernels[dom]["ms_per_step"]}
     whole_bytes = ab["move"] + ab["grow"] + ab["diffuse"]
     step_frac = whole_bytes / (ms / K * 1e-3) / 1e9 / peak
+    if "build" in kt:
+        kernels["conflict graph (part of move)"] = {"ms_per_step": kt["build"] / K}
+        kernels["dependency rounds (part of move)"] = {"ms_per_step": (kt["move"] - kt["build"]) / K, "rounds_per_step": eng.rounds() / (W + 2.0 * K)}
+    # digest of the state after W + 2K steps: a multi-GPU run of the same workload and step counts prints the same one
+    from sugarscape_utilicalc_b200.strips import state_digest
+    dga = eng.download_agents()
+    dg = state_digest(dga["id"], dga["x"], dga["y"], dga["sugar"], n)
+    health = eng.health()
+    del dga
     eng.close()
     # ---------------- e2e: public API with host buffers ----------------
     # The caller's arrays live in page-locked host memory (ss_host_alloc), allocated and filled before the clock starts;
@@ -287,7 +302,11 @@ def run_engine_single(args, wl):
         "cell_updates_per_s": n * n * K / (ms * 1e-3),
         "population": [int(pop0), int(st["population"][-1])],
         "passes_per_step": cnt["passes"] / K, "gpu_launches": cnt["launches"],
-        "move_pass": {"impl": ["cta_per_window", "warp_per_window", "lane_per_agent"][cnt["pass_impl"]], "window": cnt["window"]},
+        "move_pass": {"impl": ["cta_per_window", "warp_per_window", "lane_per_agent", "dependency_rounds"][cnt["pass_impl"]], "window": cnt["window"]},
+        "digest": {"xor": dg[0], "sum": dg[1], "agents": dg[2], "after_steps": W + 2 * K,
+                   "what": "order-independent digest of (id, cell, sugar) of the living agents; the --gpus N lines of the same "
+                           "workload and step counts carry the same digest"},
+        "health": health,
         "host_syncs_per_step": cnt["syncs"] / K,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts,
@@ -351,8 +370,8 @@ def main():
         run_reference(args, wl)
         return
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        from sugarscape_utilicalc_b200 import sharded
-        sharded.bench_main(args, wl)
+        from sugarscape_utilicalc_b200 import strips
+        strips.bench_main(args, wl)
         return
     run_engine_single(args, wl)
 

@@ -212,7 +212,7 @@ int  ss_shard_end_step(ss_engine* e, ss_step_stats* out);
  * ss_download_cells / ss_download_agents / ss_agent_count return the strip's share.  SS_STRIP_NPTR pointers / handles
  * per strip. */
 #define SS_STRIP_NPTR 11
-#define SS_STRIP_HANDLE_BYTES 64
+#define SS_STRIP_HANDLE_BYTES 72   /* cudaIpcMemHandle_t of the allocation + offset of the array inside it */
 int  ss_create_strip(const ss_config* cfg, int32_t device, int32_t rank, int32_t world, ss_engine** out);
 int  ss_strip_init_directory(ss_engine* e, int32_t n_all, const int32_t* id, const int32_t* x, const int32_t* metab,
                              const double* sugar);

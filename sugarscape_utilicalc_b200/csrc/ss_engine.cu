@@ -1288,15 +1288,30 @@ extern "C" int ss_strip_export(ss_engine* e, uint64_t* ptrs) {
     for (int k = 0; k < SS_STRIP_NPTR; k++) ptrs[k] = (uint64_t)(uintptr_t)p[k];
     return SS_OK;
 }
-// ... and as CUDA IPC handles (one process per GPU): SS_STRIP_NPTR x 64 bytes
+// ... and as CUDA IPC handles (one process per GPU): SS_STRIP_NPTR x (64-byte handle of the allocation the array lives in
+// + 8-byte offset of the array inside it -- the driver serves small cudaMallocs from shared blocks, and a handle always
+// names the whole block)
+struct StripIpcEntry { cudaIpcMemHandle_t handle; uint64_t offset; };
+static_assert(sizeof(StripIpcEntry) == 72, "IPC entry size");
+typedef int (*MemGetAddressRangeFn)(unsigned long long*, size_t*, unsigned long long);
 extern "C" int ss_strip_ipc_export(ss_engine* e, void* handles) {
     int rc = strip_ready(e, "ss_strip_ipc_export");
     if (rc) return rc;
     CK(cudaSetDevice(e->device));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn)
+        return set_err(e, SS_ERR_CUDA, "cuMemGetAddressRange is not available");
     void* p[SS_STRIP_NPTR];
     strip_ptrs(e, p);
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    for (int k = 0; k < SS_STRIP_NPTR; k++) CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handles) + k, p[k]));
+    StripIpcEntry* out = reinterpret_cast<StripIpcEntry*>(handles);
+    for (int k = 0; k < SS_STRIP_NPTR; k++) {
+        unsigned long long base = 0;
+        size_t size = 0;
+        if (((MemGetAddressRangeFn)fn)(&base, &size, (unsigned long long)(uintptr_t)p[k]) != 0) return set_err(e, SS_ERR_CUDA, "cuMemGetAddressRange failed");
+        CK(cudaIpcGetMemHandle(&out[k].handle, (void*)(uintptr_t)base));
+        out[k].offset = (uint64_t)((unsigned long long)(uintptr_t)p[k] - base);
+    }
     return SS_OK;
 }
 extern "C" int ss_strip_connect(ss_engine* e, int32_t peer_rank, const uint64_t* ptrs) {
@@ -1313,9 +1328,16 @@ extern "C" int ss_strip_ipc_connect(ss_engine* e, int32_t peer_rank, const void*
     if (peer_rank < 0 || peer_rank >= e->strip_world || peer_rank == e->strip_rank || !handles) return set_err(e, SS_ERR_ARG, "bad peer");
     CK(cudaSetDevice(e->device));
     void* p[SS_STRIP_NPTR];
+    const StripIpcEntry* in = reinterpret_cast<const StripIpcEntry*>(handles);
     for (int k = 0; k < SS_STRIP_NPTR; k++) {
-        CK(cudaIpcOpenMemHandle(&p[k], reinterpret_cast<const cudaIpcMemHandle_t*>(handles)[k], cudaIpcMemLazyEnablePeerAccess));
-        e->ipc_ptrs[peer_rank][k] = p[k];
+        void* base = nullptr;
+        for (int j = 0; j < k && !base; j++)                // several arrays of one block: the block is opened once
+            if (memcmp(&in[j].handle, &in[k].handle, sizeof(cudaIpcMemHandle_t)) == 0) base = (char*)p[j] - in[j].offset;
+        if (!base) {
+            CK(cudaIpcOpenMemHandle(&base, in[k].handle, cudaIpcMemLazyEnablePeerAccess));
+            e->ipc_ptrs[peer_rank][k] = base;
+        }
+        p[k] = (char*)base + in[k].offset;
     }
     e->peers_ipc = true;
     return strip_attach(e, peer_rank, p);

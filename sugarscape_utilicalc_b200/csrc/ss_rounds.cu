@@ -884,7 +884,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
 // Barrier over the strips (one GPU each) through peer memory: every strip publishes the next sequence number into
 // every strip's flag words (stores over NVLink) and waits until its own words show that number from everybody.
 // One thread; the caller has made this strip's writes visible to it (grid barrier / kernel boundary).
-#define DR_CTL_SEQ 11
+#define DR_CTL_SEQ 12                   // (10, 11: the two "more work" words of the round barrier)
 __device__ static inline bool dr_strip_sync(const DevWorld& w, unsigned seq, int word, unsigned payload, unsigned* any_payload) {
     const int P = w.dr.world, me = w.dr.rank;
     __threadfence_system();

@@ -21,7 +21,7 @@ from .capi import STATS_DTYPE, SsConfig
 from .engine import Engine, EngineError, _ptr
 
 NPTR = 11
-HANDLE_BYTES = 64
+HANDLE_BYTES = 72
 
 
 def strip_rows(n, rank, world):
@@ -69,6 +69,20 @@ class StripEngine(Engine):
         self._check(self._lib.ss_strip_init_directory(self._h, len(ids), _ptr(ids), _ptr(x), _ptr(met), _ptr(sug)),
                     "ss_strip_init_directory")
         self.n_slots = int(ids.max()) if len(ids) else 1
+
+    def upload_strip(self, cells, agents, pinned=False):
+        """cells: the strip's rows of sugar and cap; agents: id, x, y, vision, metab, sugar_agent of the WHOLE world."""
+        self._check(self._lib.ss_upload_cells(self._h, _ptr(cells["sugar"]), _ptr(cells["cap"]), None), "ss_upload_cells")
+        ids, x, y, vis, met, sug = (agents[k] for k in ("id", "x", "y", "vision", "metab", "sugar_agent"))
+        self.set_option("global_slots", int(ids.max()) if len(ids) else 1)
+        self.set_option("global_vmax", int(vis.max()) if len(vis) else 1)
+        m = (x >= self.x0) & (x < self.x1)
+        loc = [np.ascontiguousarray(a[m]) for a in (ids, x, y, vis, met, sug)]
+        self._check(self._lib.ss_upload_agents(self._h, int(m.sum()), *[_ptr(a) for a in loc]), "ss_upload_agents")
+        self._check(self._lib.ss_strip_init_directory(self._h, len(ids), _ptr(ids), _ptr(x), _ptr(met), _ptr(sug)),
+                    "ss_strip_init_directory")
+        self.n_slots = int(ids.max()) if len(ids) else 1
+        return int(m.sum())
 
     def export_ptrs(self):
         p = np.zeros(NPTR, dtype=np.uint64)
@@ -206,3 +220,146 @@ def connect_over_torch(eng, dist):
         if j != eng.rank:
             eng.connect_ipc(j, allh[j].cpu().numpy())
     dist.barrier()
+
+
+def state_digest(ids, x, y, sugar, n):
+    """Order-independent digest of a population (ids, cells, sugar): equal on every decomposition of the same run."""
+    ids = np.asarray(ids, dtype=np.uint64)
+    cell = np.asarray(x, dtype=np.uint64) * np.uint64(n) + np.asarray(y, dtype=np.uint64)
+    h = (ids * np.uint64(0x9E3779B97F4A7C15)) ^ ((cell + np.uint64(1)) * np.uint64(0xD1342543DE82EF95))
+    h ^= np.round(np.asarray(sugar, dtype=np.float64) * 100.0).astype(np.int64).astype(np.uint64) * np.uint64(0xA24BAED4963EE407)
+    return int(np.bitwise_xor.reduce(h)) if len(h) else 0, int(np.add.reduce(h, dtype=np.uint64)) if len(h) else 0, int(len(h))
+
+
+def bench_main(args, wl):
+    """bench.py --gpus N under torchrun: one rank per GPU, one strip of rows each (strong scaling of the workload)."""
+    import json
+    import os
+    import sys
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import config_from_settings, synthetic
+    from .clocks import ClockSampler
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = wl["n"]
+    if wl["pollution"] or wl.get("utilicalc"):
+        raise SystemExit("row strips run rule M without the pollution rule (workload c5 or <n>)")
+    settings = synthetic.synthetic_settings(n, pollution=False)
+    cfg = config_from_settings(settings, rng_mode="keyed")
+    x0, x1 = strip_rows(n, rank, world)
+    t0 = time.time()
+    w = synthetic.tiled_world_strip(n, x0, x1)
+    if rank == 0:
+        sys.stderr.write("[bench] strip world %dx%d rows [%d,%d), %d agents generated in %.1fs\n" % (n, n, x0, x1, len(w["id"]), time.time() - t0))
+    K, W = args.steps, args.warmup
+    dev = torch.device("cuda", local)
+
+    def run(k_steps, warm):
+        eng = StripEngine(cfg, rank, world, device=local)
+        t_a = time.perf_counter()
+        mine = eng.upload_strip(w, w)
+        t_b = time.perf_counter()
+        connect_over_torch(eng, dist)
+        pops0 = len(w["id"])
+        if warm:
+            pops0 = int(eng.step(warm)["population"][-1])
+        dist.barrier()
+        torch.cuda.synchronize()
+        t_c = time.perf_counter()
+        st = eng.step(k_steps)
+        torch.cuda.synchronize()
+        t_d = time.perf_counter()
+        ms = torch.tensor([eng.kernel_times()["last_call"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return eng, st, pops0, float(ms.item()), dict(upload=t_b - t_a, steps=t_d - t_c), mine
+
+    sampler = ClockSampler(local)
+    eng, st, pop0, ms, _, mine = run(K, W)
+    sampler.start()
+    st2 = eng.step(K)                              # the timed steps once more for the clock record and the launch count
+    clocks = sampler.stop()
+    ms2 = torch.tensor([eng.kernel_times()["last_call"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    cnt = eng.counters()
+    health = eng.health()
+    # digest of the state after W + 2K steps: the same on every decomposition (compare the N = 1 line)
+    ags = eng.download_agents()
+    x_, s_, c_ = state_digest(ags["id"], ags["x"], ags["y"], ags["sugar"], n)
+    parts = [None] * world
+    dist.all_gather_object(parts, (x_, s_, c_, health, int(mine)))
+    eng.close()
+    # end to end through the public API: strip upload from host arrays, K steps with the statistics read back, download
+    dist.barrier()
+    t_e0 = time.perf_counter()
+    eng = StripEngine(cfg, rank, world, device=local)
+    eng.upload_strip(w, w)
+    connect_over_torch(eng, dist)
+    ste = eng.step(K)
+    cells = eng.download_cells(cap=False, pollution=False)
+    ags2 = eng.download_agents()
+    torch.cuda.synchronize()
+    t_e = torch.tensor([time.perf_counter() - t_e0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    h2d = torch.tensor([16.0 * (x1 - x0) * n + 20.0 * len(w["id"]) + 28.0 * mine], dtype=torch.float64, device=dev)
+    d2h = torch.tensor([12.0 * (x1 - x0) * n + 28.0 * len(ags2["id"]) + 48.0 * K], dtype=torch.float64, device=dev)
+    dist.all_reduce(h2d); dist.all_reduce(d2h)
+    eng.close()
+    del cells, ags2
+    if rank == 0:
+        try:
+            peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        pops = np.concatenate([[pop0], st["population"][:-1]])
+        agent_steps = float(pops.sum())
+        value = agent_steps / (ms * 1e-3)
+        popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
+        acted = float(st["acted"].sum()) / K
+        alg = (24.0 * n * n + (76 + 48 * 3.5) * acted) / world          # per rank and step (SURVEY 8d)
+        V = int(w["vision"].max())
+        halo = 2 * ((2 * V + 3) // 4 * 4) * n * 5                          # border rows of occupancy words + cell bytes, both neighbours
+        xd, sd, cd = 0, 0, 0
+        for p in parts:
+            xd ^= p[0]; sd = (sd + p[1]) % (1 << 64); cd += p[2]
+        line = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl["label"], "grid": n, "agents": len(w["id"]),
+                       "decomposition": "row strips: rank r holds rows [r N / P, (r+1) N / P) and the agents on them; halo reads, "
+                                        "moves, migrating records and dependency counters over peer memory (CUDA IPC / NVLink); "
+                                        "device-side barriers between phases and dependency rounds",
+                       "l2": "working set per rank %.2f GB >> 126 MB L2, no flush needed" % (20.0 * n * n / world / 1e9),
+                       "timing": "CUDA events on every rank's stream around ss_strip_step(K), max over ranks"},
+            "cell_updates_per_s": n * n * K / (ms * 1e-3),
+            "population": [int(pop0), int(st["population"][-1])],
+            "ms_per_step_second_run": float(ms2.item()) / K,
+            "passes_per_step": 1.0, "host_syncs_per_step": cnt["syncs"] / max(cnt["steps"], 1),
+            "gpu_launches": int(cnt["launches"]),
+            "move_pass": {"impl": "dependency_rounds (ss_dr_build_kernel + ss_dr_rounds_kernel, strips)"},
+            "e2e": {"value": float(popse.sum()) / float(t_e.item()), "unit": "agent-steps/s",
+                    "h2d_bytes_per_step": float(h2d.item()) / K, "d2h_bytes_per_step": float(d2h.item()) / K,
+                    "steps": K, "seconds": float(t_e.item()),
+                    "what": "per rank: StripEngine; upload of the strip's cells and agents (+ the whole world's agent columns for the "
+                            "replicated directories) from host arrays; IPC connect; step(K) with the statistics read back; download of "
+                            "the strip's cells and agents; max over ranks"},
+            "roofline": {"bound": "hbm", "kernel": "whole step of one rank (conflict graph + dependency rounds + growback)",
+                         "achieved": alg / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms / K * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+            "nvlink": {"halo_bytes_per_rank_and_step": halo, "achieved_gbs": halo / (ms / K * 1e-3) / 1e9, "peak_gbs": 770.0,
+                       "what": "border rows read from the two ring neighbours by the conflict-graph kernel; border agents' cells, "
+                               "migrating records and cross-strip counters add a few 100 KB"},
+            "digest": {"xor": xd, "sum": sd, "agents": cd, "after_steps": W + 2 * K,
+                       "what": "order-independent digest of (id, cell, sugar) of the living agents, merged over the ranks: equal to the "
+                               "N=1 line's digest"},
+            "strips": [{"rank": i, "agents_at_upload": p[4], "health": p[3]} for i, p in enumerate(parts)],
+            "clocks": clocks, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -39,6 +39,11 @@ def tiled_world(n, density=1.0 / 16.0, seed=1234, vision=(1, 6), metab=(1, 4), e
     cap50 = two_peak_capacity(tile, DEFAULT_SITES, max_capacity)
     idx = np.arange(n) % tile
     cap = np.ascontiguousarray(cap50[np.ix_(idx, idx)])
+    return dict(_agents(n, density, seed, vision, metab, endowment), cap=cap, sugar=cap.copy(),
+                pollution=np.zeros((n, n), dtype=np.float64))
+
+
+def _agents(n, density, seed, vision, metab, endowment):
     rng = np.random.Generator(np.random.PCG64(seed))
     n_agents = int(n * n * density)
     cells = np.empty(0, dtype=np.int64)
@@ -49,7 +54,6 @@ def tiled_world(n, density=1.0 / 16.0, seed=1234, vision=(1, 6), metab=(1, 4), e
         cells = allc[np.sort(first)]
     cells = cells[:n_agents]
     world = dict(
-        cap=cap, sugar=cap.copy(), pollution=np.zeros((n, n), dtype=np.float64),
         id=np.arange(1, n_agents + 1, dtype=np.int32),
         x=(cells // n).astype(np.int32), y=(cells % n).astype(np.int32),
         vision=rng.integers(vision[0], vision[1] + 1, size=n_agents, dtype=np.int32),
@@ -57,6 +61,17 @@ def tiled_world(n, density=1.0 / 16.0, seed=1234, vision=(1, 6), metab=(1, 4), e
         sugar_agent=rng.integers(endowment[0], endowment[1] + 1, size=n_agents).astype(np.float64),
     )
     return world
+
+
+def tiled_world_strip(n, x0, x1, **kw):
+    """The same world as tiled_world(n), but only the lattice rows [x0, x1) of the cell arrays (one rank's strip of a
+    multi-GPU run); the agent arrays are those of the whole world."""
+    tile, max_capacity = kw.get("tile", 50), kw.get("max_capacity", 10)
+    cap50 = two_peak_capacity(tile, DEFAULT_SITES, max_capacity)
+    cap = np.ascontiguousarray(cap50[np.ix_(np.arange(x0, x1) % tile, np.arange(n) % tile)])
+    ag = _agents(n, kw.get("density", 1.0 / 16.0), kw.get("seed", 1234), kw.get("vision", (1, 6)), kw.get("metab", (1, 4)),
+                 kw.get("endowment", (5, 25)))
+    return dict(ag, cap=cap, sugar=cap.copy())
 
 
 #: settings.json of the reference with only the fields the hot path reads filled in
