@@ -267,27 +267,31 @@ ss_dr_merge_stats_kernel(DevWorld w) {
 // -------------------------------------------------------------------------------- build ----
 __device__ static inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Q1, one thread per slot: the agent before this one in the list order (the keyed order: ascending priority over the
-// living agents) is found by walking the inverse priority map over the alive bitmap; if it may starve this step, its
-// outcome decides whether this agent acts at all -- one more predecessor (q1flag) and a note for the predecessor
-// (q1wait) whom to tell.
-__global__ void ss_dr_q1_kernel(DevWorld w, OrderKey ok, uint32_t stamp) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool flag = false;
-    if (slot < w.n_slots && ((w.dr.alive[slot >> 5] >> (slot & 31)) & 1u)) {
-        for (uint32_t p = ss_priority(ok, slot); p-- > 0u;) {
-            const uint32_t s2 = ss_priority_inverse(ok, p);
-            if (s2 >= w.n_slots || !((w.dr.alive[s2 >> 5] >> (s2 & 31)) & 1u)) continue;
-            if ((w.dr.atrisk[s2 >> 5] >> (s2 & 31)) & 1u) { flag = true; w.dr.q1wait[s2] = make_uint2(slot, stamp); }
-            break;
-        }
+// Q1 (sugarscape.py:520 + 502-503: the agent after a dying agent loses its turn): the list order is the keyed order --
+// ascending priority over the living agents -- so an agent's neighbours in the list are found by walking the inverse
+// priority map over the replicated alive bitmap.  If the agent before this one may starve this step, its outcome
+// decides whether this agent acts at all: one more predecessor.
+__device__ static inline bool dr_q1_pred_at_risk(const DevWorld& w, const OrderKey& ok, uint32_t prio) {
+    for (uint32_t p = prio; p-- > 0u;) {
+        const uint32_t s2 = ss_priority_inverse(ok, p);
+        if (s2 >= w.n_slots || !((__ldg(&w.dr.alive[s2 >> 5]) >> (s2 & 31)) & 1u)) continue;
+        return ((__ldg(&w.dr.atrisk[s2 >> 5]) >> (s2 & 31)) & 1u) != 0u;
     }
-    const unsigned b = __ballot_sync(FULL, flag);
-    if ((threadIdx.x & 31) == 0 && (slot >> 5) < ((w.n_slots + 31) >> 5)) w.dr.q1flag[slot >> 5] = b;
+    return false;
+}
+// ... and an agent that may starve notes whom to tell: the next living agent in the list (slot + 1, 0 = nobody)
+__device__ static inline uint32_t dr_q1_successor(const DevWorld& w, const OrderKey& ok, uint32_t prio) {
+    const uint32_t domain = 1u << (2 * ok.half);
+    for (uint32_t p = prio + 1u; p < domain; p++) {
+        const uint32_t s2 = ss_priority_inverse(ok, p);
+        if (s2 < w.n_slots && ((__ldg(&w.dr.alive[s2 >> 5]) >> (s2 & 31)) & 1u)) return s2 + 1u;
+    }
+    return 0u;
 }
 
 struct DrBuildArgs {
     OrderKey ok;
+    uint32_t stamp;                 // iteration + 1
     int tiles_y;
     int use_tma;
 };
@@ -551,7 +555,14 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             uint32_t* rec = reinterpret_cast<uint32_t*>(w.dr.succ) + (size_t)slot * 16;
             rec[0] = nsucc;
             if (nsucc > DR_SUCC_INLINE) rec[15] = my_at;
-            const uint32_t indeg = preds + ((__ldg(&w.dr.q1flag[slot >> 5]) >> (slot & 31)) & 1u);
+            uint32_t indeg = preds;
+            if (w.cfg.rule_can_starve) {
+                if (dr_q1_pred_at_risk(w, ba.ok, pa)) indeg++;
+                if ((__ldg(&w.dr.atrisk[slot >> 5]) >> (slot & 31)) & 1u) {
+                    const uint32_t nxt = dr_q1_successor(w, ba.ok, pa);
+                    w.dr.q1wait[slot] = make_uint2(nxt ? nxt - 1u : 0u, nxt ? ba.stamp : 0u);
+                }
+            }
             reinterpret_cast<uint16_t*>(S.dep)[slot] = (uint16_t)indeg;
             if (indeg == 0) { ilist[k] |= 0x8000u; atomicAdd(&s_ready, 1); }
         }
@@ -912,10 +923,10 @@ __global__ void ss_dr_strip_barrier_kernel(DevWorld w) {
 // Grid barrier between rounds (cooperative launch: all CTAs are resident).  The last CTA to arrive snapshots the queue
 // tail into ctl[3 + (generation & 1)] before it releases the others, so every CTA sees the same next segment even if a
 // fast CTA is already appending to the queue again.  With strips on several GPUs (XSYNC) the same CTA first waits for
-// every strip to finish the round -- their turns may have queued agents here -- and then learns whether any strip has
-// work left.  Returns the snapshot; *more = the agent phase goes on.
+// every strip to finish the round -- their turns may have queued agents here -- and learns whether any strip had
+// agents in it.  Returns the snapshot; *more = the agent phase goes on.
 template <bool XSYNC>
-__device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nblocks, unsigned seg_end, DrAccum& acc,
+__device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nblocks, unsigned seg_end, bool had_work, DrAccum& acc,
                                                   unsigned* s_tail, bool* more) {
     unsigned int* ctl = w.dr.self.ctl;
     __syncthreads();
@@ -926,11 +937,12 @@ __device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nb
             ctl[1] = 0u;
             unsigned any = 0;
             if (XSYNC) {
+                // one exchange per round: "this strip is through with round k, and it had agents in it".  Once every
+                // strip has said so, whatever the round queued anywhere is in place; the agent phase ends after the
+                // first round in which no strip had any agent (nothing can have been queued then).
                 const unsigned seq = ++ctl[DR_CTL_SEQ];
-                if (!dr_strip_sync(w, seq, 0, 0u, nullptr)) acc.fault++;
-                const unsigned tail = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
-                if (!dr_strip_sync(w, seq, 1, tail != seg_end ? 1u : 0u, &any)) acc.fault++;
-                *(volatile unsigned*)&ctl[3 + (gen & 1u)] = tail;
+                if (!dr_strip_sync(w, seq, 0, had_work ? 1u : 0u, &any)) acc.fault++;
+                *(volatile unsigned*)&ctl[3 + (gen & 1u)] = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
             } else {
                 const unsigned tail = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
                 *(volatile unsigned*)&ctl[3 + (gen & 1u)] = tail;
@@ -983,7 +995,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
         if (st.single_round) break;
         seg_b = seg_e;
         bool more;
-        seg_e = dr_grid_barrier<XSYNC>(w, st.nblocks, seg_e, acc, s_tail, &more);
+        seg_e = dr_grid_barrier<XSYNC>(w, st.nblocks, seg_e, cnt != 0u, acc, s_tail, &more);
         if (!more) break;
     }
     // statistics of this CTA's turns (sugarscape.py:575-583)
@@ -1127,9 +1139,9 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
     ss_dr_begin_kernel<<<1, 1, 0, s>>>(w);
     DrBuildArgs ba;
     ba.ok = ss_order_key(ss_step_key(w.cfg.keyed_seed, iteration), w.half);
+    ba.stamp = (uint32_t)(iteration + 1);
     ba.tiles_y = (w.n + DR_TY - 1) / DR_TY;
     ba.use_tma = use_tma;
-    if (w.cfg.rule_can_starve && w.n_slots) ss_dr_q1_kernel<<<(w.n_slots + 255) / 256, 256, 0, s>>>(w, ba.ok, (uint32_t)(iteration + 1));
     const int tiles_x = (w.dr.self.rows + DR_TX - 1) / DR_TX;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
