@@ -1398,7 +1398,10 @@ static int strip_finish(ss_engine* e, int stats_index) {
     DevWorld g = e->w;                          // the statistics kernel on the merged sums
     g.acc = reinterpret_cast<StepAccum*>(e->w.dr.acc_g);
     g.hist = e->w.dr.hist_g;
-    CK(ss_launch_stats(g, stats_index, e->stream));
+    {
+        KTimer tm(e, KT_STATS);
+        CK(ss_launch_stats(g, stats_index, e->stream));
+    }
     e->launches++;
     int rc = env_phase(e);
     if (rc) return rc;
@@ -1454,16 +1457,28 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     if (rc) return rc;
     CK(cudaEventRecord(e->evs, e->stream));
     for (int t = 0; t < nsteps; t++) {
-        rc = strip_begin_build(e);
+        {
+            KTimer tm(e, KT_PREPARE);                               // (option "profile": device time per phase, with a host sync each)
+            rc = strip_begin_build(e);
+            if (rc) return rc;
+        }
+        {
+            KTimer tm(e, KT_MOVE);
+            CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip's counters and queue are set up
+            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
+        }
+        {
+            KTimer tm(e, KT_SERIAL);                                // ("serial" slot: merge of the statistics + delta lists + barrier)
+            CK(ss_launch_dr_check(e->w, e->stream));
+            CK(ss_launch_dr_after_rounds(e->w, e->stream));
+            CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // everybody has read everybody's sums and delta list
+        }
+        rc = strip_finish(e, t);                                    // statistics kernel + growback (timed as "grow")
         if (rc) return rc;
-        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // every strip's counters and queue are set up
-        CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
-        CK(ss_launch_dr_check(e->w, e->stream));
-        CK(ss_launch_dr_after_rounds(e->w, e->stream));
-        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // everybody has read everybody's sums and delta list
-        rc = strip_finish(e, t);
-        if (rc) return rc;
-        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // every strip's growback is done: the halos are final
+        {
+            KTimer tm(e, KT_SETTLE);
+            CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip's growback is done: the halos are final
+        }
         e->launches += 7; e->passes++;
     }
     CK(cudaEventRecord(e->eve, e->stream));

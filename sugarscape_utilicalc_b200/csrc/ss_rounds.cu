@@ -41,6 +41,8 @@
 #define DR_WARP_CAP 128                 // staged queue entries per warp between flushes
 #define DR_HIST_BINS 2048               // low wealth bins kept in shared memory per CTA
 #define DR_SKIP 0x80000000u             // queue entry flag: the agent loses its turn (Q1)
+#define DR_REMOTE 0x20000000u           // queue entry flag: released by an agent of another strip
+#define DR_VALID 0x40000000u            // queue entry flag: the entry is written (strips: a neighbour may still be writing it)
 
 // ------------------------------------------------------------------------------ helpers ----
 __device__ static inline bool dr_crosses_meet(int dx, int dy, int a, int b) {
@@ -576,7 +578,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
         for (int k = tid; k < nl; k += DR_BUILD_THREADS) {
             if (!(ilist[k] & 0x8000u)) continue;
             const int lr = (ilist[k] >> 7) & 255, lq = ilist[k] & 127;
-            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = occ_slot(tileS[lr * SY + lq]);
+            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = occ_slot(tileS[lr * SY + lq]) | DR_VALID;
         }
     }
 }
@@ -617,10 +619,10 @@ __device__ static inline void dr_released(const DevWorld& w, DrShared& sh, int w
     const uint32_t slot2 = ent & OCC_SLOT_MASK;
     const uint32_t h = (old >> ((slot2 & 1u) << 4)) & 0xffffu;
     if ((h & 0x7fffu) == 1u) {
-        const uint32_t e = slot2 | ((lose_turn || (h >> 15)) ? DR_SKIP : 0u);
+        const uint32_t e = slot2 | DR_VALID | ((lose_turn || (h >> 15)) ? DR_SKIP : 0u);
         const int which = STRIPS ? (int)((ent >> 24) & 3u) : 0;
         if (which == 0) dr_push(w, sh, warp, e);
-        else DR_W(queue, which)[atomicAdd(&DR_W(ctl, which)[0], 1u)] = e;          // a ring neighbour's agent
+        else DR_W(queue, which)[atomicAdd(&DR_W(ctl, which)[0], 1u)] = e | DR_REMOTE;          // a ring neighbour's agent
     } else if ((h & 0x7fffu) == 0u) acc.fault++;
 }
 template <bool STRIPS>
@@ -783,14 +785,21 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                                 [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
                                 [&](int am, int oo) { return __ldcg(&S.poll[am ? c + oo : (uint32_t)((int)c + oo * n)]); }, arm, o, sg);
             } else {
+                // near the torus edge or a strip border, or vision > 8: cell by cell through the strip addressing --
+                // every load is issued before the first is looked at (a neighbour strip's rows are an NVLink round trip away)
                 own = __ldcg(&S.mw[c]);
                 double pown = 0.0;
                 if (POLT) pown = __ldcg(&S.poll[c]);
+                uint8_t cb[2][2 * 15 + 1];
+#pragma unroll 1
+                for (int oo = -a; oo <= a; oo++) {
+                    if (oo == 0) continue;
+                    const DrLoc Lx = dr_loc<STRIPS>(w, ss_wrap1(gx + oo, n), gy), Ly = dr_loc<STRIPS>(w, gx, ss_wrap1(gy + oo, n));
+                    cb[0][oo + a] = __ldcg(&DR_F(mw, Lx)[Lx.idx]);
+                    cb[1][oo + a] = __ldcg(&DR_F(mw, Ly)[Ly.idx]);
+                }
                 dr_choose<POLT>(w, gx, gy, a, slot, st.skey, (own & 0x7f) == DR_HARVESTED ? 0 : (own & 0x7f), pown, acc,
-                                [&](int am, int oo) {
-                                    const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
-                                    return (unsigned)__ldcg(&DR_F(mw, L)[L.idx]);
-                                },
+                                [&](int am, int oo) { return (unsigned)cb[am][oo + a]; },
                                 [&](int am, int oo) {
                                     const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
                                     return __ldcg(&DR_F(poll, L)[L.idx]);
@@ -861,9 +870,9 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         const uint32_t old = died ? atomicAdd(wp, 0x7fffu << shf) : atomicSub(wp, 1u << shf);
         const uint32_t h = (old >> shf) & 0xffffu;
         if ((h & 0x7fffu) == 1u) {
-            const uint32_t e = s2 | ((died || (h >> 15)) ? DR_SKIP : 0u);
+            const uint32_t e = s2 | DR_VALID | ((died || (h >> 15)) ? DR_SKIP : 0u);
             if (!STRIPS || home == w.dr.rank) dr_push(w, sh, warp, e);
-            else DR_A(queue, home)[atomicAdd(&DR_A(ctl, home)[DR_CTL_TAIL], 1u)] = e;
+            else DR_A(queue, home)[atomicAdd(&DR_A(ctl, home)[DR_CTL_TAIL], 1u)] = e | DR_REMOTE;
         } else if ((h & 0x7fffu) == 0u) acc.fault++;
     }
     // conflict successors: all decrements of the record are issued before the first result is looked at
@@ -922,9 +931,13 @@ __global__ void ss_dr_strip_barrier_kernel(DevWorld w) {
 
 // Grid barrier between rounds (cooperative launch: all CTAs are resident).  The last CTA to arrive snapshots the queue
 // tail into ctl[3 + (generation & 1)] before it releases the others, so every CTA sees the same next segment even if a
-// fast CTA is already appending to the queue again.  With strips on several GPUs (XSYNC) the same CTA first waits for
-// every strip to finish the round -- their turns may have queued agents here -- and learns whether any strip had
-// agents in it.  Returns the snapshot; *more = the agent phase goes on.
+// fast CTA is already appending to the queue again.  With strips on several GPUs (XSYNC) the same CTA first meets the
+// other strips: one exchange per round, "this strip is through with round k, and it had agents in it".  Once every strip
+// has said so, whatever the round queued anywhere is in place (the exchange fences at system scope; the CTAs' own
+// fences order their stores before their arrival), and the agent phase ends after the first round in which no strip had
+// any agent -- nothing can have been queued then.  (Measured alternative: strips running their rounds without a common
+// barrier, waiting only for the entries they miss -- 64 instead of 37 rounds per step and slower; DESIGN.md.)
+// Returns the snapshot; *more = the agent phase goes on.
 template <bool XSYNC>
 __device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nblocks, unsigned seg_end, bool had_work, DrAccum& acc,
                                                   unsigned* s_tail, bool* more) {
@@ -935,19 +948,14 @@ __device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nb
         const unsigned gen = *(volatile unsigned*)&ctl[2];
         if (atomicAdd(&ctl[1], 1u) == nblocks - 1u) {
             ctl[1] = 0u;
-            unsigned any = 0;
+            unsigned any;
             if (XSYNC) {
-                // one exchange per round: "this strip is through with round k, and it had agents in it".  Once every
-                // strip has said so, whatever the round queued anywhere is in place; the agent phase ends after the
-                // first round in which no strip had any agent (nothing can have been queued then).
                 const unsigned seq = ++ctl[DR_CTL_SEQ];
                 if (!dr_strip_sync(w, seq, 0, had_work ? 1u : 0u, &any)) acc.fault++;
-                *(volatile unsigned*)&ctl[3 + (gen & 1u)] = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
-            } else {
-                const unsigned tail = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
-                *(volatile unsigned*)&ctl[3 + (gen & 1u)] = tail;
-                any = tail != seg_end ? 1u : 0u;
             }
+            const unsigned tail = *(volatile unsigned*)&ctl[DR_CTL_TAIL];
+            if (!XSYNC) any = tail != seg_end ? 1u : 0u;
+            *(volatile unsigned*)&ctl[3 + (gen & 1u)] = tail;
             *(volatile unsigned*)&ctl[DR_CTL_MORE + (gen & 1u)] = any;
             __threadfence();
             atomicAdd(&ctl[2], 1u);
@@ -984,10 +992,13 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     const unsigned gwarp = blockIdx.x * DR_WARPS + (unsigned)warp, nwarp = gridDim.x * DR_WARPS;
     for (;;) {
         const unsigned cnt = seg_e - seg_b;
-        // a warp takes 32 consecutive queue entries at a time; no CTA-wide barrier inside a round
-        for (unsigned base = gwarp * 32u; base < cnt; base += nwarp * 32u) {
+        // a warp takes consecutive queue entries, 32 at a time in the big rounds; a small round is spread over all warps
+        // (the lanes of a warp run their divergent turns one after the other: fewer lanes, shorter round); no CTA-wide
+        // barrier inside a round
+        const unsigned per = min(32u, max(1u, (cnt + nwarp - 1u) / nwarp));
+        for (unsigned base = gwarp * per; base < cnt; base += nwarp * per) {
             const unsigned i = base + (unsigned)lane;
-            if (i < cnt) dr_turn<POLT, STRIPS>(w, st, sh, warp, acc, __ldcg(&S.queue[seg_b + i]));
+            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS>(w, st, sh, warp, acc, __ldcg(&S.queue[seg_b + i]));
             __syncwarp();
             if (sh.cnt[warp] >= DR_WARP_CAP / 2) dr_flush(w, sh, warp, lane);
         }

