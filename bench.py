@@ -12,12 +12,17 @@ Workloads:
 The JSON line carries: value (state resident in HBM, device-timed with CUDA events on the
 engine's stream), e2e (through the public Python API with host buffers: upload + K steps
 with per-step stats read-back + download), roofline of the dominant kernel class measured
-live with CUDA events in a second instrumented run, cpu_baseline (the C oracle port on a
-bounded sample of the same world) and the GPU clocks sampled during the timed region.
+live with CUDA events in a second instrumented run, cpu_baseline (the reference's Python loop
+on a bounded sample of the same landscape, with the C oracle port beside it), `secondary`
+(short runs of c4 and c5u with their per-kernel rooflines), a decomposition-independent
+digest of the final state and the GPU clocks sampled during the timed region.
+--gpus N (under torchrun): the same workload as row strips, one rank per GPU
+(sugarscape_utilicalc_b200/strips.py).
 
---impl reference times the reference's CPU algorithm (the oracle port, oracle/ss_oracle.c --
-the Python reference itself cannot travel to the GPU box) on the host, single-threaded
-like the reference's loop.
+--impl reference times the reference's own pure-Python loop (the unmodified sources staged under
+baseline/_ref by __graft_entry__.build(); headless, one core -- the loop is sequential) on the
+shipped presets and on the workload's landscape at 200^2 and 800^2, with the C port
+(oracle/ss_oracle.c) beside it.
 """
 import argparse
 import json
@@ -45,6 +50,31 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernels_sha():
+    """Hash of the CUDA sources: a DRAM-traffic figure in profiles/traffic.json counts only for the kernels it was captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "sugarscape_utilicalc_b200", "csrc")
+    for f in ("ss_device.cuh", "ss_world.cuh", "ss_lattice.cu", "ss_rounds.cu"):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def recorded_traffic(workload_key, kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the class's launches of one step, from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by tools/ncu_traffic.py); None when there is none for these kernel sources."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        e = t["entries"][workload_key][kernel_class]
+        if t.get("kernels_sha") != kernels_sha():
+            return None, "profiles/traffic.json was captured on other kernel sources (sha %s): stale" % t.get("kernels_sha")
+        return float(e["dram_bytes_per_step"]), e["source"]
+    except Exception:
+        return None, None
 
 
 def workload(name):
@@ -134,28 +164,90 @@ def replicas_throughput(wl, steps=3):
                     "not a parallel run of one world" % (procs, steps), "wall_s": time.perf_counter() - t0}
 
 
+REF_STAGE = os.path.join(ROOT, "baseline", "_ref")
+
+
+def python_reference_figures(args, wl):
+    """The reference's own pure-Python loop (View.updateGame of the UNMODIFIED sources staged under baseline/_ref by
+    __graft_entry__.build()), headless (Tk / matplotlib stubbed; oracle/ref_harness.py), one core -- the loop is
+    sequential.  Shipped presets in full, and the bench workload's landscape and rules at 200^2 and 800^2."""
+    os.environ["SS_REFERENCE"] = REF_STAGE
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness as rh
+    out = {"presets": {}, "synthetic": {}}
+
+    def timed(run, steps):
+        pops, t0 = [], time.perf_counter()
+        for _ in range(steps):
+            pops.append(len(run.view.agents))
+            run.step()
+            if run.exited_at is not None:
+                break
+        return float(sum(pops)), time.perf_counter() - t0, len(pops)
+
+    presets = [("settings.json as shipped (utilicalc)", None, {}, 100), ("settings.json with moveEat", None, {"moveEat": True, "utilicalc": False}, 100),
+               ("examples/seasons", "seasons", {}, 500), ("examples/pollution", "pollution", {}, 500),
+               ("examples/utilicalc_sugar", "utilicalc_sugar", {}, 500)]
+    for label, preset, rules, steps in presets:
+        s = rh.load_settings(preset)
+        s["rules"].update(rules)
+        r = rh.ReferenceRun(s, rng="mt")
+        a, dt, done = timed(r, steps)
+        out["presets"][label] = {"agent_steps_per_s": a / dt, "steps": done, "seconds": dt}
+    for n, steps in ((200, 10), (800, max(1, min(args.steps, 6)))):
+        w = synthetic.tiled_world(n)
+        s = synthetic.synthetic_settings(n, pollution=wl["pollution"], utilicalc=wl.get("utilicalc", False))
+        r = rh.ReferenceRun(s, rng="keyed", world=w)
+        if n == 800:
+            timed(r, min(args.warmup, 1))
+        a, dt, done = timed(r, steps)
+        out["synthetic"]["%dx%d" % (n, n)] = {"agent_steps_per_s": a / dt, "cell_updates_per_s": n * n * done / dt, "agents": len(w["id"]),
+                                              "steps": done, "seconds": dt}
+    return out
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    py = None
+    why_not = None
+    if os.path.isfile(os.path.join(REF_STAGE, "sugarscape.py")):
+        try:
+            py = python_reference_figures(args, wl)
+        except Exception as ex:                          # reported, never hidden: the C port below still gives a line
+            why_not = "%s: %s" % (type(ex).__name__, ex)
+    else:
+        why_not = "baseline/_ref/sugarscape.py is missing (staged by __graft_entry__.build() where /root/reference exists)"
     settings, w = make_world(dict(wl, n=min(wl["n"], 4096)))
     ns = 2048 if wl["pollution"] else 4096
     ns = min(ns, w["cap"].shape[0])
     r = oracle_sample(settings, w, ns, args.steps, args.warmup)
-    value = r["agent_steps"] / r["seconds"]
-    sample = ("C port of the reference's sequential loop (oracle/ss_oracle.c; the Python reference cannot travel to the "
-              "GPU box), 1 thread, %dx%d sub-lattice of the workload's landscape with %d agents, %d steps after %d warm-up"
-              % (r["n"], r["n"], r["agents"], r["steps"], args.warmup))
+    port_value = r["agent_steps"] / r["seconds"]
+    port = {"value": port_value, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+            "sample": "C port of the reference's sequential loop (oracle/ss_oracle.c), 1 thread, %dx%d sub-lattice of the workload's "
+                      "landscape with %d agents, %d steps after %d warm-up" % (r["n"], r["n"], r["agents"], r["steps"], args.warmup),
+            "replicas": replicas_throughput(wl)}
+    if py is not None:
+        big = py["synthetic"]["800x800"]
+        value, ms_step = big["agent_steps_per_s"], 1e3 * big["seconds"] / big["steps"]
+        cpu = {"value": value, "unit": "agent-steps/s", "cores": 1, "kind": "reference-python", "host_cpus": os.cpu_count(),
+               "sample": "the reference's pure-Python loop (View.updateGame of the unmodified sources under baseline/_ref, headless, "
+                         "CPython %d.%d, 1 core: the loop is sequential) on the workload's landscape and rules at 800x800 / %d agents, "
+                         "%d steps; shipped presets and the 200x200 world under `python_reference`" % (
+                             sys.version_info[0], sys.version_info[1], big["agents"], big["steps"]),
+               "python_reference": py, "c_port": port}
+    else:
+        value, ms_step = port_value, 1e3 * r["seconds"] / r["steps"]
+        cpu = dict(port, host_cpus=os.cpu_count(), python_reference_unavailable=why_not)
     line = {
         "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["label"], "timing": "host wall clock, bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count(), "replicas": replicas_throughput(wl)},
+        "config": {"workload": wl["label"], "timing": "host wall clock, bounded sample (cpu_baseline.sample)"},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "cell_updates_per_s": r["n"] * r["n"] * r["steps"] / r["seconds"],
     }
     print(json.dumps(line), flush=True)
 
@@ -164,6 +256,39 @@ def algorithmic_bytes(n, pollution, acted, mean_vision=3.5):
     """grow 24 B/cell, diffusion 16 B/cell, move 100+80v (pollution) / 76+48v B/agent-step."""
     per_agent = (100 + 80 * mean_vision) if pollution else (76 + 48 * mean_vision)
     return dict(grow=24.0 * n * n, diffuse=16.0 * n * n if pollution else 0.0, move=per_agent * acted)
+
+
+def secondary_run(wl2, w2, peak, steps=5, warm=3):
+    """A short device-timed run of another scale configuration, with the per-kernel-class rooflines."""
+    from sugarscape_utilicalc_b200.engine import Engine
+    settings2 = synthetic.synthetic_settings(wl2["n"], pollution=wl2["pollution"], utilicalc=wl2.get("utilicalc", False))
+    if w2 is None:
+        w2 = synthetic.tiled_world(wl2["n"])
+    eng = Engine(config_from_settings(settings2, rng_mode="keyed"))
+    upload(eng, w2)
+    pop0 = int(eng.step(warm)["population"][-1])
+    st = eng.step(steps)
+    ms = eng.kernel_times()["last_call"]
+    pops = np.concatenate([[pop0], st["population"][:-1]])
+    eng.set_option("profile", 1)
+    eng.set_option("reset_times", 0)
+    st2 = eng.step(steps)
+    kt = eng.kernel_times()
+    cnt = eng.counters()
+    health = eng.health()
+    eng.close()
+    ab = algorithmic_bytes(wl2["n"], wl2["pollution"], float(st2["acted"].sum()) / steps)
+    agent_ms = (kt["prepare"] + kt["move"] + kt["settle"]) / steps
+    out = {"workload": wl2["label"], "value": float(pops.sum()) / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms / steps,
+           "steps": steps, "warmup": warm, "pass_impl": cnt["pass_impl"], "passes_per_step": cnt["passes"] / (warm + 2.0 * steps),
+           "health": health, "kernels": {}}
+    for name, t, nbytes in (("agent phase", agent_ms, ab["move"]), ("grow", kt["grow"] / steps, ab["grow"]),
+                            ("diffuse", kt["diffuse"] / steps, ab["diffuse"])):
+        if t > 0:
+            tr, src = recorded_traffic(wl2.get("key"), name.split()[0])
+            out["kernels"][name] = {"ms_per_step": t, "algorithmic_bytes_per_step": nbytes, "achieved_gbs": nbytes / (t * 1e-3) / 1e9,
+                                    "frac": nbytes / (t * 1e-3) / 1e9 / peak, "traffic": tr, "traffic_source": src}
+    return out
 
 
 def run_engine_single(args, wl):
@@ -218,19 +343,15 @@ def run_engine_single(args, wl):
     kernels["prepare+stats"] = {"ms_per_step": (kt["prepare"] + kt["stats"]) / K,
                                 "share": (kt["prepare"] + kt["stats"]) / tot}
     dom = max(("move", "grow", "diffuse"), key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
-    # DRAM bytes of the dominant kernel's launches of one step, from the committed ncu --set full captures
-    # (profiles/r01d_ncu_full_move_solo_c5.csv, r01c_*_c4.csv: dram__bytes_read.sum + dram__bytes_write.sum, summed over
-    # the step's launches)
-    traffic_tbl = {("c5", "move", 1): 24.4e9, ("c4", "move", 1): 1.515e9, ("c4", "diffuse", 1): 210.7e6, ("c4", "diffuse", 0): 210.7e6}
-    traffic = traffic_tbl.get((wl.get("key"), dom, cnt["pass_impl"]))
+    traffic, traffic_src = recorded_traffic(wl.get("key"), dom)
     move_kernel = ["ss_move_pass_kernel", "ss_move_solo_kernel", "ss_move_solo_kernel (lanes)",
                    "ss_dr_build_kernel + ss_dr_rounds_kernel"][cnt["pass_impl"]]
     roofline = {"bound": "hbm", "kernel": {"move": move_kernel + (" (conflict graph + all dependency rounds of a step)" if cnt["pass_impl"] == 3
                                                                   else " (all passes of a step) + ss_settle_kernel"),
-                                           "grow": "ss_grow_kernel", "diffuse": "ss_diffuse_kernel"}[dom],
+                                           "grow": "ss_dr_grow_kernel" if cnt["pass_impl"] == 3 else "ss_grow_kernel", "diffuse": "ss_diffuse_col_kernel"}[dom],
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic,
-                "traffic_source": "profiles/r01d_ncu_full_move_solo_c5.csv / r01c_ncu_full_*_c4.csv (bytes per step, same launch set)" if traffic else None,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "ms_per_launch_set": kernels[dom]["ms_per_step"]}
     whole_bytes = ab["move"] + ab["grow"] + ab["diffuse"]
@@ -292,6 +413,37 @@ def run_engine_single(args, wl):
                "sample": "oracle/ss_oracle.c (C port of the reference loop), 1 thread, %dx%d sub-lattice of the same "
                          "world, %d agents, 5 steps (%.1f s)" % (r["n"], r["n"], r["agents"], r["seconds"]),
                "host_cpus": os.cpu_count()}
+        # ... and the reference's own Python loop on a smaller sample of the same landscape (the --impl reference arm
+        # runs the presets and the 800^2 world in full)
+        if os.path.isfile(os.path.join(REF_STAGE, "sugarscape.py")):
+            try:
+                os.environ["SS_REFERENCE"] = REF_STAGE
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import ref_harness as rh
+                nr = 400
+                wr = synthetic.tiled_world(nr)
+                rr = rh.ReferenceRun(synthetic.synthetic_settings(nr, pollution=wl["pollution"], utilicalc=wl.get("utilicalc", False)),
+                                     rng="keyed", world=wr)
+                t0 = time.perf_counter()
+                acted = 0
+                for _ in range(6):
+                    acted += len(rr.view.agents)
+                    rr.step()
+                dt = time.perf_counter() - t0
+                cpu = {"value": acted / dt, "unit": "agent-steps/s", "cores": 1, "kind": "reference", "host_cpus": os.cpu_count(),
+                       "sample": "the reference's pure-Python loop (unmodified sources under baseline/_ref, headless, 1 core) on the same "
+                                 "landscape and rules at %dx%d / %d agents, 6 steps (%.1f s)" % (nr, nr, len(wr["id"]), dt),
+                       "c_port": cpu}
+            except Exception as ex:
+                cpu["python_reference_unavailable"] = "%s: %s" % (type(ex).__name__, ex)
+    # ---------------- the other scale configurations, short (BASELINE configs 3/4: utilicalc, pollution + diffusion) ----------------
+    secondary = {}
+    if not args.no_secondary and wl.get("key") == "c5":
+        for key in ("c4", "c5u"):
+            try:
+                secondary[key] = secondary_run(workload(key), w if key == "c5u" else None, peak)
+            except Exception as ex:
+                secondary[key] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     line = {
         "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -316,6 +468,7 @@ def run_engine_single(args, wl):
         "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": whole_bytes, "frac_of_peak": step_frac},
         "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "upload_s": t_upload,
+        "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
 
@@ -358,6 +511,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SS_BENCH_WORKLOAD", "c5"))
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short c4 / c5u runs of the N=1 line")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="engine option (ss_set_option) for A/B runs, e.g. --opt pass_impl=0")
     args = ap.parse_args()

@@ -63,6 +63,9 @@ def lib():
         L.sso_upload_cells.argtypes = [vp, vp, vp, vp]
         L.sso_upload_agents.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
         L.sso_set_rng_mt19937.argtypes = [vp, vp, C.c_int32]
+        L.sso_set_min_slots.argtypes = [vp, C.c_int32]
+        L.sso_get_slots.argtypes = [vp]
+        L.sso_get_slots.restype = C.c_int32
         L.sso_get_rng_mt19937.argtypes = [vp, vp, C.POINTER(C.c_int32)]
         L.sso_step.argtypes = [vp, C.c_int32, vp]
         L.sso_download_cells.argtypes = [vp, vp, vp, vp, vp]
@@ -114,6 +117,15 @@ class OracleWorld:
         sugar = np.ascontiguousarray(sugar, dtype=np.float64)
         self._check(lib().sso_upload_agents(self._h, len(id), _ptr(id), _ptr(x), _ptr(y), _ptr(vision),
                                             _ptr(metab), _ptr(sugar)))
+
+    def set_option(self, name, value):
+        """Mirror of Engine.set_option for the one option the oracle knows: "global_slots" (order width of a resumed run)."""
+        if name != "global_slots":
+            raise ValueError("oracle: unknown option " + name)
+        self._check(lib().sso_set_min_slots(self._h, int(value)))
+
+    def n_slots(self):
+        return int(lib().sso_get_slots(self._h))
 
     def set_rng_mt19937(self, state, index):
         st = np.ascontiguousarray(state, dtype=np.uint32)

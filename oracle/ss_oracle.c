@@ -42,6 +42,7 @@ struct sso_world {
     int32_t* occ;             /* slot or -1 */
     /* agent store, indexed by slot = id - 1 */
     int32_t n_slots;
+    int32_t min_slots;
     int32_t *ax, *ay, *avision, *ametab;
     double* asugar;
     uint8_t* alive;
@@ -480,6 +481,7 @@ int sso_upload_agents(sso_world* w, int32_t n, const int32_t* id, const int32_t*
     free(w->ax); free(w->ay); free(w->avision); free(w->ametab); free(w->asugar); free(w->alive);
     free(w->order); free(w->wealth); free(w->sortk); free(w->sortk2);
     int32_t ns = max_id > 0 ? max_id : 1;
+    if (w->min_slots > ns) ns = w->min_slots;      /* a resumed run keeps the order width of the original upload */
     w->n_slots = ns;
     w->ax = (int32_t*)calloc((size_t)ns, sizeof(int32_t));
     w->ay = (int32_t*)calloc((size_t)ns, sizeof(int32_t));
@@ -509,6 +511,12 @@ int sso_upload_agents(sso_world* w, int32_t n, const int32_t* id, const int32_t*
     w->half = order_half_bits(ns);
     return 0;
 }
+
+/* The keyed execution order is a bijection on a power-of-two domain sized by the largest Agent.id at upload
+ * (sugarscape.py:517 as restated by oracle/keyed_rng.py); a run resumed from a checkpoint must keep that size even if the
+ * agent with the largest id has died since -- before sso_upload_agents. */
+int sso_set_min_slots(sso_world* w, int32_t n_slots) { w->min_slots = n_slots; return 0; }
+int32_t sso_get_slots(sso_world* w) { return w->n_slots; }
 
 int sso_set_rng_mt19937(sso_world* w, const uint32_t state[624], int32_t index) {
     if (index < 0 || index > 624) return fail("MT19937 index out of range");

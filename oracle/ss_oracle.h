@@ -62,6 +62,8 @@ int  sso_upload_cells(sso_world* w, const double* sugar, const double* cap, cons
 /* n agents in LIST ORDER (View.agents); id[] are the reference ids (>=1, unique) */
 int  sso_upload_agents(sso_world* w, int32_t n, const int32_t* id, const int32_t* x, const int32_t* y,
                        const int32_t* vision, const int32_t* metab, const double* sugar);
+int  sso_set_min_slots(sso_world* w, int32_t n_slots);   /* before sso_upload_agents: order width of a resumed run */
+int32_t sso_get_slots(sso_world* w);
 int  sso_set_rng_mt19937(sso_world* w, const uint32_t state[624], int32_t index);
 int  sso_get_rng_mt19937(sso_world* w, uint32_t state[624], int32_t* index);
 int  sso_step(sso_world* w, int32_t nsteps, sso_step_stats* out /* nsteps entries */);

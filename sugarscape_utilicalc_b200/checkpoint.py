@@ -14,7 +14,11 @@ from .settings import config_from_settings
 def save(path, world, settings, rng, iteration, keyed_seed=None):
     """world: Engine (or anything with its interface); iteration: timesteps taken since iteration 0 (= env time)."""
     cells, ags = world.download_cells(), world.download_agents()
+    # the keyed execution order is sized by the largest Agent.id of the ORIGINAL upload: saved, so that the resumed run
+    # keeps the order even if that agent has died since
+    n_slots = int(world.n_slots()) if hasattr(world, "n_slots") else int(max(ags["id"], default=1))
     out = dict(settings_json=np.array(json.dumps(settings)), rng=np.array(rng), iteration=np.int64(iteration),
+               n_slots=np.int64(n_slots),
                keyed_seed=np.int64(-1 if keyed_seed is None else keyed_seed),
                sugar=cells["sugar"], cap=cells["cap"], pollution=cells["pollution"],
                **{"agent_" + k: ags[k] for k in ("id", "x", "y", "vision", "metab", "sugar")})
@@ -35,6 +39,8 @@ def restore(path, world_factory=None, **factory_kwargs):
         from .engine import Engine
         world_factory = Engine
     world = world_factory(cfg, **factory_kwargs)
+    if "n_slots" in z.files and hasattr(world, "set_option"):
+        world.set_option("global_slots", int(z["n_slots"]))
     world.upload_cells(z["sugar"], z["cap"], z["pollution"])
     world.upload_agents(z["agent_id"], z["agent_x"], z["agent_y"], z["agent_vision"], z["agent_metab"], z["agent_sugar"])
     if rng == "mt":

@@ -200,23 +200,21 @@ static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32
     if ((ce = cudaMalloc(&e->w.n_order, sizeof(int32_t))) != cudaSuccess) return bail(ce, "cudaMalloc n_order");
     if ((ce = cudaMalloc(&e->w.acc, sizeof(StepAccum))) != cudaSuccess) return bail(ce, "cudaMalloc acc");
     if ((ce = cudaMalloc(&e->w.hist, SS_GINI_BINS * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc hist");
+    if ((ce = cudaMalloc(&e->w.outliers, SS_GINI_OUTLIERS * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc outliers");
     const int nbands = (cfg->grid_size + 31) / 32;
     if ((ce = cudaMalloc(&e->d_flags, sizeof(int) * (size_t)(nbands + 1))) != cudaSuccess) return bail(ce, "cudaMalloc flags");
     if ((ce = cudaMallocHost(&e->h_pending, sizeof(unsigned long long))) != cudaSuccess) return bail(ce, "cudaMallocHost");
     if ((ce = cudaMalloc(&e->h_dev_count, sizeof(unsigned long long))) != cudaSuccess) return bail(ce, "cudaMalloc count");
-    cudaMemset(e->w.sugar, 0, cb);
-    cudaMemset(e->w.cap, 0, cb);
-    cudaMemset(e->w.poll, 0, cb);
-    cudaMemset(e->w.occw, 0, e->cells * sizeof(uint32_t));
-    cudaMemset(e->w.mt, 0, 624 * sizeof(uint32_t));
     int32_t mti0 = 624;
-    cudaMemcpy(e->w.mti, &mti0, sizeof mti0, cudaMemcpyHostToDevice);
-    cudaMemset(e->w.n_order, 0, sizeof(int32_t));
-    cudaMemset(e->w.acc, 0, sizeof(StepAccum));
-    cudaEventCreate(&e->ev0);
-    cudaEventCreate(&e->ev1);
-    cudaEventCreate(&e->evs);
-    cudaEventCreate(&e->eve);
+    if ((ce = cudaMemset(e->w.sugar, 0, cb)) != cudaSuccess || (ce = cudaMemset(e->w.cap, 0, cb)) != cudaSuccess ||
+        (ce = cudaMemset(e->w.poll, 0, cb)) != cudaSuccess || (ce = cudaMemset(e->w.occw, 0, e->cells * sizeof(uint32_t))) != cudaSuccess ||
+        (ce = cudaMemset(e->w.mt, 0, 624 * sizeof(uint32_t))) != cudaSuccess ||
+        (ce = cudaMemcpy(e->w.mti, &mti0, sizeof mti0, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemset(e->w.n_order, 0, sizeof(int32_t))) != cudaSuccess || (ce = cudaMemset(e->w.acc, 0, sizeof(StepAccum))) != cudaSuccess)
+        return bail(ce, "initialising device memory");
+    if ((ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
+        (ce = cudaEventCreate(&e->evs)) != cudaSuccess || (ce = cudaEventCreate(&e->eve)) != cudaSuccess)
+        return bail(ce, "cudaEventCreate");
     *out = e;
     return SS_OK;
 }
@@ -230,7 +228,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.n_order); cudaFree(e->w.wealth);
     cudaFree(e->w.sortkeys); cudaFree(e->w.mt); cudaFree(e->w.mti); cudaFree(e->w.stats);
     cudaFree(e->w.pendmap);
-    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
+    cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->w.outliers); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
     dr_free(e);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     cudaFree(e->h_dev_count);
@@ -882,7 +880,7 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
             } else {
                 rc = lattice_step(e, t);
             }
-            if (rc) return rc;
+            if (rc) { e->path = -1; return rc; }       // the state is mid-step: unusable until the next upload (SS_ERR_STATE)
             e->iteration++; e->env_time++; e->steps++;
         }
     }
@@ -973,13 +971,13 @@ extern "C" int ss_download_cells(ss_engine* e, double* sugar, double* cap, doubl
     if (cap) CK(cudaMemcpyAsync(cap, e->w.cap, cb, cudaMemcpyDeviceToHost, e->stream));
     if (pollution) CK(cudaMemcpyAsync(pollution, e->w.poll, cb, cudaMemcpyDeviceToHost, e->stream));
     int32_t* d_ids = nullptr;
+    struct Guard { int32_t*& p; ~Guard() { cudaFree(p); } } guard{d_ids};       // freed on every exit
     if (occ_id) {
         CK(cudaMalloc(&d_ids, e->cells * sizeof(int32_t)));
         CK(ss_launch_occ_ids(e->w, d_ids, e->stream));
         CK(cudaMemcpyAsync(occ_id, d_ids, e->cells * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     }
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(d_ids);
     return SS_OK;
 }
 
@@ -1062,6 +1060,7 @@ extern "C" int ss_get_counters(ss_engine* e, int64_t* out, int32_t n) {
         if (e->w.dr.self.ctl) cudaMemcpy(&rounds, e->w.dr.self.ctl + 2, sizeof rounds, cudaMemcpyDeviceToHost);
         out[11] = (int64_t)rounds;
     }
+    if (n > 12) out[12] = (int64_t)e->w.n_slots;      // width of the keyed order: the largest Agent.id the engine was sized for
     if (n > 6 && e->w.dbg) {       // instrumentation counters of the move passes (option "debug")
         unsigned long long d[32];
         cudaMemcpy(d, e->w.dbg, sizeof d, cudaMemcpyDeviceToHost);
@@ -1120,6 +1119,10 @@ extern "C" int ss_shard_enable(ss_engine* e, int32_t rank, int32_t world) {
         const int rc = choose_path(e);
         if (rc) return rc;
         if (e->path != PATH_LATTICE) return set_err(e, SS_ERR_STATE, "sharding needs the lattice path");
+    }
+    if (e->w.log && e->w.log_cap < 8ull * e->w.n_slots + 4096) {       // a larger population was uploaded since: new logs
+        cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
+        e->w.log = nullptr; e->w.log_count = nullptr; e->w.clog = nullptr; e->w.clog_count = nullptr;
     }
     if (!e->w.log) {
         e->w.log_cap = 8ull * e->w.n_slots + 4096;     // warps reserve 8 entries at a time: <= 7 unused per valid one
@@ -1398,6 +1401,7 @@ static int strip_finish(ss_engine* e, int stats_index) {
     DevWorld g = e->w;                          // the statistics kernel on the merged sums
     g.acc = reinterpret_cast<StepAccum*>(e->w.dr.acc_g);
     g.hist = e->w.dr.hist_g;
+    g.outliers = nullptr;                       // (wealth outside the histogram: Gini is reported as NaN on strips)
     {
         KTimer tm(e, KT_STATS);
         CK(ss_launch_stats(g, stats_index, e->stream));

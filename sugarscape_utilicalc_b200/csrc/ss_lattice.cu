@@ -77,7 +77,7 @@ __global__ void ss_prepare_kernel(DevWorld w, int64_t iteration) {
 __global__ void ss_begin_step_kernel(DevWorld w) {
     StepAccum* a = w.acc;
     a->sum_metab = 0; a->sum_vision = 0; a->acted = 0; a->deaths = 0;
-    a->pending = a->population; a->hist_small = 0; a->inexact = 0;
+    a->pending = a->population; a->hist_small = 0; a->inexact = 0; a->outliers = 0;
 }
 
 // --------------------------------------------------------------------------- move pass ----
@@ -345,7 +345,7 @@ __device__ static inline void commit_turn(const DevWorld& w, const Ctx& c, int l
     ts.acted++;
     if (sugar == 0.01) ts.small++;
     else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
-    else ts.inexact++;
+    else { ts.inexact++; ss_note_outlier(w, sugar); }
     const bool died = w.cfg.rule_can_starve && sugar <= 0.1;          // sugarscape.py:306-309
     if (died) new_word = 0u;
     c.put_occ(lx, ly, 0u);
@@ -1723,7 +1723,7 @@ ss_apply_log_kernel(DevWorld w, const ShardLogEntry* entries, unsigned long long
     const double sugar = en.sugar;
     if (sugar == 0.01) atomicAdd(&w.acc->hist_small, 1ull);
     else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) atomicAdd(&w.hist[(int)sugar], 1u);
-    else atomicAdd(&w.acc->inexact, 1ull);
+    else { atomicAdd(&w.acc->inexact, 1ull); ss_note_outlier(w, sugar); }
 }
 
 // The compact entries (safe agents: move now, settle later).  Phase 0 clears the cell the agent left -- its position in
@@ -1796,7 +1796,7 @@ ss_settle_kernel(DevWorld w, int64_t iteration, int64_t env_time) {
         else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) {
             const int bin = (int)sugar;
             if (bin < SETTLE_BINS) atomicAdd(&hist_s[bin], 1u); else atomicAdd(&w.hist[bin], 1u);
-        } else inexact++;
+        } else { inexact++; ss_note_outlier(w, sugar); }
         if (w.cfg.rule_can_starve && sugar <= 0.1) fault++;           // a "safe" agent starved: must not happen
     }
     unsigned vals[6] = {sum_m, sum_v, acted, small, inexact, fault};
@@ -1863,7 +1863,31 @@ ss_stats_kernel(DevWorld w, int stats_index) {
         const double total_area = s_area[0] + 0.01 * c0 * c0 / 2.0;
         const double fair = height * nw / 2.0;
         double gini = fair == 0.0 ? 1.0 : (fair - total_area) / fair;
-        if (a->inexact || a->fault) gini = __longlong_as_double(0x7ff8000000000000ll);
+        if (a->inexact && !a->fault && w.outliers && a->outliers == a->inexact && a->outliers <= SS_GINI_OUTLIERS) {
+            // wealth values outside the histogram (rare): the same sums, one thread, bins and sorted outliers merged in
+            // value order -- c entries of value v after height H add c H + v c^2 / 2 (sugarscape.py:269-280)
+            const int no = (int)a->outliers;
+            double* o = w.outliers;
+            for (int i = 1; i < no; i++) {                            // insertion sort (at most SS_GINI_OUTLIERS values)
+                const double v = o[i];
+                int j = i - 1;
+                while (j >= 0 && o[j] > v) { o[j + 1] = o[j]; j--; }
+                o[j + 1] = v;
+            }
+            double H = 0.0, area = 0.0, cnt_all = 0.0;
+            int k = 0;
+            auto add = [&](double c, double v) { area += c * H + v * c * c / 2.0; H += c * v; cnt_all += c; };
+            while (k < no && o[k] < 0.01) add(1.0, o[k++]);
+            add(c0, 0.01);
+            for (int v = 0; v < SS_GINI_BINS; v++) {
+                while (k < no && o[k] < (double)v) add(1.0, o[k++]);
+                const double c = (double)w.hist[v];
+                if (c > 0.0) add(c, (double)v);
+            }
+            while (k < no) add(1.0, o[k++]);
+            const double fair2 = H * cnt_all / 2.0;
+            gini = fair2 == 0.0 ? 1.0 : (fair2 - area) / fair2;
+        } else if (a->inexact || a->fault) gini = __longlong_as_double(0x7ff8000000000000ll);
         a->population -= a->deaths;
         const double pop = (double)a->population;
         ss_step_stats st;

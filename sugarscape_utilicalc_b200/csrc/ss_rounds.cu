@@ -827,7 +827,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         else if (sugar >= 0.0 && sugar < (double)SS_GINI_BINS && sugar == (double)(int)sugar) {
             const int bin = (int)sugar;
             if (bin < DR_HIST_BINS) atomicAdd(&sh.hist[bin], 1u); else atomicAdd(&w.hist[bin], 1u);
-        } else acc.inexact++;
+        } else { acc.inexact++; ss_note_outlier(w, sugar); }
         died = w.cfg.rule_can_starve && sugar <= 0.1;                                              // sugarscape.py:306-309
         const bool risk_next = !died && dr_at_risk(w, sugar, metab);
         const uint32_t new_word = died ? 0u : occ_pack(slot, a, st.next_phase);

@@ -16,7 +16,9 @@ struct StepAccum {                  // per-step reduction targets of the lattice
     unsigned long long fault;       // internal consistency violations (must stay 0)
     unsigned long long watchdog;    // spin-wait watchdog firings since upload (diagnostic; 0 in healthy runs)
     unsigned long long wd_info[3];
+    unsigned long long outliers;    // entries of DevWorld::outliers (wealth values outside the histogram, kept one by one)
 };
+#define SS_GINI_OUTLIERS 4096       // the statistics stay exact with up to this many such values per step
 
 // One resolved turn, as shipped to the other ranks' replicas (multi-GPU, see sharded.py)
 struct ShardLogEntry {
@@ -111,6 +113,7 @@ struct DevWorld {
     // lattice path
     StepAccum* acc;
     uint32_t* hist;                 // SS_GINI_BINS
+    double* outliers;               // SS_GINI_OUTLIERS
     int vmax;                       // max vision over all agents
     unsigned long long* dbg;        // optional instrumentation counters (32 entries) or null
     uint32_t* pendmap;              // 2 x pend_nb^2 counters: agents a launch left pending, per 32x32-cell block
@@ -123,6 +126,13 @@ struct DevWorld {
     unsigned long long clog_cap;
     DrState dr;                     // dependency rounds (ss_rounds.cu)
 };
+
+// A wealth value the histogram has no bin for (non-integer -- a fractional uploaded endowment -- or >= SS_GINI_BINS):
+// kept individually, merged in value order by ss_stats_kernel.
+__device__ inline void ss_note_outlier(const DevWorld& w, double sugar) {
+    const unsigned long long at = atomicAdd(&w.acc->outliers, 1ull);
+    if (at < SS_GINI_OUTLIERS) w.outliers[at] = sugar;
+}
 
 struct PassGeom {                   // window tiling of one move pass
     int nwin;                       // windows per dimension

@@ -44,7 +44,7 @@ class DropinHandle:
         self.events, self.gui = events, gui
         self.keyed_seed = ss.seed if keyed_seed is None else keyed_seed
         self.list_ids = [a.id for a in view.agents]
-        self.n_slots = max(self.list_ids, default=1)
+        self.n_slots = max(max(self.list_ids, default=1), int(world.n_slots()) if hasattr(world, "n_slots") else 1)
 
     def _order_before_step(self):
         """The order `updateGame` walks the agents in (sugarscape.py:517-520), recomputed on the host."""

@@ -189,6 +189,13 @@ class Engine:
         self._check(self._lib.ss_get_counters(self._h, _ptr(out), 12), "ss_get_counters")
         return int(out[11])
 
+    def n_slots(self):
+        """The largest Agent.id the engine is sized for (the keyed execution order is a bijection on a domain of that size:
+        a resumed run must keep it, see checkpoint.py)."""
+        out = np.zeros(13, dtype=np.int64)
+        self._check(self._lib.ss_get_counters(self._h, _ptr(out), 13), "ss_get_counters")
+        return int(out[12])
+
     def health(self):
         """Device-side consistency counters of the lattice path: watchdog firings of the spin waits and internal
         faults (a draw loop that did not terminate, more tied candidates than the geometry allows).  Both must be 0."""

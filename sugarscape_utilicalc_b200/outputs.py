@@ -174,7 +174,7 @@ class RunRecorder:
         self.data_file = data_file
         self.events = events
         self.list_ids = list(int(i) for i in (world.download_agents()["id"] if list_ids is None else list_ids))
-        self.n_slots = max(self.list_ids, default=1)
+        self.n_slots = max(max(self.list_ids, default=1), int(world.n_slots()) if hasattr(world, "n_slots") else 1)
 
     def _order_before_step(self):
         if self.rng == "mt":
@@ -203,7 +203,7 @@ class RunRecorder:
         if self.iteration == 100:
             self.pop_at_100 = self.population[-1]
             self.gini_at_100 = self.gini[-1]
-        if self.iteration >= 200:
+        if self.iteration >= 200 and len(self.population) >= 200:      # (a recorder started on a resumed run has no history yet)
             self.population_200_ago = self.population[len(self.population) - 200]
         if self.population[-1] == self.population_200_ago:
             update_data_file(self.data_file, [self.seed, self.pop_at_100, round(self.gini_at_100, 2), str(self.population[-1])])

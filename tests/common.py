@@ -220,3 +220,42 @@ def check_checkpoint_resume(name, kind, tmp_dir, stop=7, total=15):
         assert ma[1] == mc[1] and np.array_equal(ma[0], mc[0])
     a.close()
     c.close()
+
+
+def check_resume_after_top_id_died(kind, tmp_dir):
+    """the keyed execution order is sized by the largest Agent.id of the original upload.  Here that agent
+    starves before the checkpoint (ids up to 257 -> 5 bits per half; the survivors' largest id is < 256 -> 4 bits if the
+    width were recomputed): the resumed run must still equal the uninterrupted one."""
+    from sugarscape_utilicalc_b200 import checkpoint
+    n = 64
+    s, init = synthetic_case(n, False)
+    init = {k: (v[:200].copy() if k in ("id", "x", "y", "vision", "metab", "sugar_agent") else v) for k, v in init.items()}
+    init["id"] = init["id"].copy()
+    init["id"][-1] = 257                                    # the largest id ...
+    init["sugar_agent"][-1] = 1.0                           # ... starves in the first steps
+    init["metab"][-1] = 4
+    s["env"]["max_capacity"] = 10
+    cfg = config_from_settings(s, rng_mode="keyed")
+    mk = (lambda c: oracle_world(c)) if kind == "oracle" else (lambda c: engine_world(c))
+    a = mk(cfg)
+    barren = np.zeros((n, n))
+    a.upload_cells(barren, init["cap"] * 0.0, None)
+    a.upload_agents(init["id"], init["x"], init["y"], init["vision"], init["metab"], init["sugar_agent"])
+    sa = a.step(8)
+    b = mk(cfg)
+    b.upload_cells(barren, init["cap"] * 0.0, None)
+    b.upload_agents(init["id"], init["x"], init["y"], init["vision"], init["metab"], init["sugar_agent"])
+    sb1 = b.step(3)
+    assert 257 not in b.download_agents()["id"].tolist(), "the agent with the largest id should have starved by now"
+    path = os.path.join(str(tmp_dir), "ck.npz")
+    checkpoint.save(path, b, s, "keyed", 3)
+    b.close()
+    c, _, _, _ = checkpoint.restore(path, world_factory=(oracle_world if kind == "oracle" else None))
+    sc = c.step(5)
+    for f in ("population", "metabolism_mean", "vision_mean", "acted", "deaths"):
+        assert np.array_equal(np.concatenate([sb1[f], sc[f]]), sa[f]), f
+    ga, gc = a.download_agents(), c.download_agents()
+    for k in ("id", "x", "y", "sugar"):
+        assert np.array_equal(ga[k], gc[k]), k
+    a.close()
+    c.close()

@@ -120,6 +120,10 @@ def test_checkpoint_resume(name, tmp_path):
     common.check_checkpoint_resume(name, "engine", tmp_path, total=min(15, common.load_golden(name)["steps"]))
 
 
+def test_checkpoint_resume_keeps_the_order_width_when_the_top_id_died(tmp_path):
+    common.check_resume_after_top_id_died("engine", tmp_path)
+
+
 def test_mt_exact_single_steps_equal_fused_steps():
     g = common.load_golden("c2_pollution_mt")
     w = common.world_from_golden(g, "engine")
@@ -299,6 +303,29 @@ def test_unsupported_configurations_fail_loudly():
     e.upload_cells(init["sugar"], init["cap"], init["pollution"])
     with pytest.raises(EngineError):
         e.upload_agents(bad["id"], bad["x"], bad["y"], bad["vision"], bad["metab"], bad["sugar_agent"])
+
+
+@pytest.mark.parametrize("impl", [3, 0, 1])
+def test_gini_with_wealth_outside_the_histogram(impl):
+    """fractional endowments (non-integer wealth) and wealth >= 65536 have no histogram bin: the statistics stay
+    exact (outliers merged in value order) instead of reporting NaN."""
+    s, init = common.synthetic_case(200, False)
+    init = dict(init)
+    sa = init["sugar_agent"].copy()
+    sa[::7] += 0.375
+    sa[5] = 70000.0
+    sa[11] = 123456.5
+    init["sugar_agent"] = sa
+    cfg = config_from_settings(s, rng_mode="keyed")
+    e, o = common.engine_world(cfg, options={"pass_impl": impl, "solo_window": 72}), common.oracle_world(cfg)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    a, b = e.step(6), o.step(6)
+    assert np.isfinite(a["gini"]).all()
+    np.testing.assert_allclose(a["gini"], b["gini"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(a["population"], b["population"])
+    e.close()
+    o.close()
 
 
 def test_empty_population_and_extinction():

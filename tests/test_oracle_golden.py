@@ -29,3 +29,17 @@ def test_checkpoint_resume_is_bit_identical(name, tmp_path):
     """checkpoint.save / restore (here over the CPU oracle): a run stopped at step 7 and resumed from the file ends
     where the uninterrupted run ends -- cells, agents in list order, statistics, MT19937 state."""
     common.check_checkpoint_resume(name, "oracle", tmp_path)
+
+
+def test_checkpoint_resume_keeps_the_order_width_when_the_top_id_died(tmp_path):
+    common.check_resume_after_top_id_died("oracle", tmp_path)
+
+
+def test_run_recorder_started_on_a_resumed_run_has_no_history(tmp_path):
+    """RunRecorder(iteration=250) must not index a population series it does not have."""
+    from sugarscape_utilicalc_b200 import outputs
+    g = common.load_golden("c1_default_moveeat_keyed")
+    w = common.world_from_golden(g, "oracle")
+    rec = outputs.RunRecorder(g["settings"], w, rng="keyed", data_file=str(tmp_path / "data.txt"), iteration=250)
+    rec.step()
+    assert rec.iteration == 251 and len(rec.population) == 1
