@@ -342,8 +342,9 @@ static int choose_path(ss_engine* e) {
         else if (!cta_ok) lattice_ok = false;
     }
     // dependency rounds over the whole lattice: rule M with the keyed order, any lattice the conflict zone fits on
-    const bool dr_ok = e->cfg.rng_mode == SS_RNG_KEYED && e->cfg.rule_move_eat && V <= 15 && 4 * V + 1 <= n && e->cap_fits_u7 &&
-                       e->w.n_slots <= SS_MAX_SLOTS && e->shard_world == 1;
+    // (and the utilicalc rule, whose turn reads the records of the agents on its cross: same conflict predicate; one GPU)
+    const bool dr_ok = e->cfg.rng_mode == SS_RNG_KEYED && (e->cfg.rule_move_eat || (e->cfg.rule_utilicalc && e->strip_world <= 1)) &&
+                       V <= 15 && 4 * V + 1 <= n && e->cap_fits_u7 && e->w.n_slots <= SS_MAX_SLOTS && e->shard_world == 1;
     if (e->strip_world > 1) {
         if (!dr_ok) return set_err(e, SS_ERR_UNSUPPORTED, "row strips need the dependency rounds (keyed order, rule M, vision <= 15, capacities < 127)");
         // a conflict zone (2 vmax rows either side) must not reach beyond the two ring neighbours

@@ -744,7 +744,141 @@ __device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a
     out_sg = (int)(ent >> 8);
 }
 
-template <int POLT, bool STRIPS>
+// ------------------------------------------------------------------------------------------
+// agent.py:1025-1141 utilicalcMove(), sugar-only (utilicalcSugar agent.py:980-992): one THREAD takes the whole turn.
+// The welfare evaluation is fused into the movement scan: the two arms are scanned once for free cells (the moves,
+// agent.py:361-371 getFood) and occupants (agent.py:391-407 getVisionNeighbourhood), the three Fisher-Yates shuffles are
+// replayed on the agent's keyed words (the sums below are compared for EQUALITY, agent.py:1105, so the neighbours are
+// summed in their shuffled order, and random.choice picks among the maxima in the moves' shuffled order), and a move's
+// utility is one f64 that never leaves the thread.  A (move, neighbour) term counts only when the neighbour would see
+// the agent there (`cert`); the other terms are +-0.0 in the reference and leave the sum as it is, so they are skipped.
+// Candidates are numbered as in dr_choose: k = offset + a on the x-arm, span + offset + a on the y-arm; 255 = own cell.
+#define DR_UT_MAX (4 * 15 + 2)
+#define DR_UT_OWN 255
+__device__ static inline double dr_util_intensity(double sugar, int metab) {        // agent.py:870-872, 984
+    const double days = (sugar >= 0.0 && sugar < 2147483647.0 && sugar == (double)(int)sugar)
+                            ? (double)((int)sugar / metab) : ss_py_floordiv(sugar, (double)metab);
+    return 1.0 / (1.0 + days);
+}
+struct DrKeyed { uint64_t akey; uint32_t j; };
+__device__ static inline uint32_t dr_randbelow(DrKeyed& ks, uint32_t nn, DrAccum& acc) {      // random.py:242 _randbelow
+    const int kbits = 32 - __clz(nn);
+    uint32_t r = ss_keyed_word(ks.akey, ks.j++) >> (32 - kbits);
+    while (r >= nn) {
+        r = ss_keyed_word(ks.akey, ks.j++) >> (32 - kbits);
+        if (ks.j > 100000u) { acc.fault++; r = 0u; break; }
+    }
+    return r;
+}
+template <class CellByte, class CellWord, class CellRec>
+__device__ static inline void dr_util_choose(const DevWorld& w, int gx, int gy, int a, uint32_t slot, uint64_t skey, unsigned own_byte,
+                                             double own_sugar, int own_metab, DrAccum& acc, CellByte cellbyte, CellWord cellword,
+                                             CellRec cellrec, int& out_arm, int& out_o, int& out_sg) {
+    const int n = w.n, span = 2 * a + 1;
+    uint8_t mv[DR_UT_MAX];              // moves: candidate numbers, own cell last
+    uint8_t nk[DR_UT_MAX];              // neighbours as found: candidate number of the cell (own last), vision
+    uint8_t nv[DR_UT_MAX];
+    uint8_t perm[DR_UT_MAX];            // ... and their shuffled order
+    double ni[DR_UT_MAX], nm[DR_UT_MAX];        // 1 / (1 + days to starvation), metabolism
+    double ut[DR_UT_MAX];
+    int m = 0, nb = 0;
+#pragma unroll 1
+    for (int k = 0; k < 2 * span; k++) {
+        const int arm = k >= span ? 1 : 0, o = k - arm * span - a;
+        if (o == 0) continue;                                   // own cell: occupied by the agent, and not a neighbour
+        if (cellbyte(arm, o) & 0x80u) nk[nb++] = (uint8_t)k; else mv[m++] = (uint8_t)k;
+    }
+    // the neighbours' records, four in flight: occupancy word -> slot -> record
+#pragma unroll 1
+    for (int q0 = 0; q0 < nb; q0 += 4) {
+        uint32_t wd[4];
+        uint4 rc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            wd[u] = 0u;
+            if (q0 + u < nb) { const int k = nk[q0 + u], arm = k >= span ? 1 : 0; wd[u] = cellword(arm, k - arm * span - a); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            rc[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (q0 + u < nb) { const int k = nk[q0 + u], arm = k >= span ? 1 : 0; rc[u] = cellrec(arm, k - arm * span - a, occ_slot(wd[u])); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (q0 + u >= nb) continue;
+            if (wd[u] == 0u || !attr_alive(rc[u].w)) acc.fault++;
+            const double bs = __longlong_as_double((long long)((unsigned long long)rc[u].x | ((unsigned long long)rc[u].y << 32)));
+            const int bm = attr_metab(rc[u].w);
+            ni[q0 + u] = dr_util_intensity(bs, bm); nm[q0 + u] = (double)bm; nv[q0 + u] = (uint8_t)attr_vision(rc[u].w);
+        }
+    }
+    DrKeyed ks;
+    ks.akey = ss_agent_key(skey, slot + 1u); ks.j = 0u;
+#pragma unroll 1
+    for (int rep = 0; rep < 2; rep++)                           // getFood's shuffle (agent.py:369), then agent.py:1033
+#pragma unroll 1
+        for (int i = m - 1; i >= 1; i--) {                      // random.py:350
+            const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
+            const uint8_t t = mv[i]; mv[i] = mv[jj]; mv[jj] = t;
+        }
+    mv[m++] = DR_UT_OWN;                                        // agent.py:1035
+    for (int q = 0; q < nb; q++) perm[q] = (uint8_t)q;
+#pragma unroll 1
+    for (int i = nb - 1; i >= 1; i--) {                         // agent.py:405
+        const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
+        const uint8_t t = perm[i]; perm[i] = perm[jj]; perm[jj] = t;
+    }
+    const double extent = (double)nb;
+    nk[nb] = DR_UT_OWN; nv[nb] = (uint8_t)a; ni[nb] = dr_util_intensity(own_sugar, own_metab); nm[nb] = (double)own_metab;     // agent.py:1039
+    perm[nb] = (uint8_t)nb;
+    nb++;
+    double umax = 0.0;
+#pragma unroll 1
+    for (int p = 0; p < m; p++) {
+        const int k = mv[p];
+        int mx = gx, my = gy;
+        unsigned b = own_byte;
+        if (k != DR_UT_OWN) {
+            const int arm = k >= span ? 1 : 0, o = k - arm * span - a;
+            if (arm) my = ss_wrap1(gy + o, n); else mx = ss_wrap1(gx + o, n);
+            b = cellbyte(arm, o);
+        }
+        const double site = (double)((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu));
+        double u = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < nb; q++) {
+            const int i = perm[q], kb = nk[i], bv = nv[i];
+            int bx = gx, by = gy;
+            if (kb != DR_UT_OWN) {
+                const int arm = kb >= span ? 1 : 0, o = kb - arm * span - a;
+                if (arm) by = ss_wrap1(gy + o, n); else bx = ss_wrap1(gx + o, n);
+            }
+            const bool cert = (bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv);         // agent.py:109-110, raw coordinates
+            if (!cert) continue;
+            const double dur = (site / nm[i]) / w.cfg.max_capacity;
+            double t = ((ni[i] + dur) + 0.5 * 0.0) + extent;
+            if (kb != DR_UT_OWN) t *= -1.0;
+            u += t;
+        }
+        ut[p] = u;
+        if (p == 0 || u > umax) umax = u;
+    }
+    int nmax = 0;
+    for (int p = 0; p < m; p++) nmax += ut[p] == umax ? 1 : 0;
+    int pick = (int)dr_randbelow(ks, (uint32_t)nmax, acc);     // random.choice, agent.py:1108
+    int k = DR_UT_OWN;
+    for (int p = 0; p < m; p++)
+        if (ut[p] == umax && pick-- == 0) { k = mv[p]; break; }
+    out_arm = -1; out_o = 0;
+    unsigned b = own_byte;
+    if (k != DR_UT_OWN) {
+        out_arm = k >= span ? 1 : 0; out_o = k - out_arm * span - a;
+        b = cellbyte(out_arm, out_o);
+    }
+    out_sg = (int)((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu));                                        // agent.py:1128-1130
+}
+
+template <int POLT, bool STRIPS, bool UTIL>
 __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrShared& sh, int warp, DrAccum& acc, uint32_t entry) {
     const int n = w.n;
     const DrPeer& S = w.dr.self;
@@ -774,13 +908,19 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         uint8_t own;
         // both arms inside this strip and the torus edge out of sight: two wide loads per arm
         const bool fast = a <= 8 && lx - a >= 0 && lx + a < S.rows && gy - a >= 0 && gy + a < n;
-        if (w.cfg.rule_move_eat) {
+        if (UTIL || w.cfg.rule_move_eat) {
             if (fast) {
                 const ArmWin wy = dr_load_arm(S.mw, (size_t)c - (size_t)a);
                 const ArmWin wx = dr_load_arm(S.mwx, (size_t)gy * (size_t)S.rows + (size_t)(lx - a));
                 own = (uint8_t)dr_arm_byte(wy, a);
                 double pown = 0.0;
                 if (POLT) pown = __ldcg(&S.poll[c]);
+                if (UTIL)
+                    dr_util_choose(w, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
+                                   [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
+                                   [&](int am, int oo) { return __ldcg(&S.occw[am ? c + oo : (uint32_t)((int)c + oo * n)]); },
+                                   [&](int, int, uint32_t s2) { return __ldcg(reinterpret_cast<const uint4*>(&S.agents[s2])); }, arm, o, sg);
+                else
                 dr_choose<POLT>(w, gx, gy, a, slot, st.skey, (own & 0x7f) == DR_HARVESTED ? 0 : (own & 0x7f), pown, acc,
                                 [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
                                 [&](int am, int oo) { return __ldcg(&S.poll[am ? c + oo : (uint32_t)((int)c + oo * n)]); }, arm, o, sg);
@@ -798,6 +938,18 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                     cb[0][oo + a] = __ldcg(&DR_F(mw, Lx)[Lx.idx]);
                     cb[1][oo + a] = __ldcg(&DR_F(mw, Ly)[Ly.idx]);
                 }
+                if (UTIL)
+                    dr_util_choose(w, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
+                                   [&](int am, int oo) { return (unsigned)cb[am][oo + a]; },
+                                   [&](int am, int oo) {
+                                       const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
+                                       return __ldcg(&DR_F(occw, L)[L.idx]);
+                                   },
+                                   [&](int am, int oo, uint32_t s2) {
+                                       const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
+                                       return __ldcg(reinterpret_cast<const uint4*>(&DR_F(agents, L)[s2]));
+                                   }, arm, o, sg);
+                else
                 dr_choose<POLT>(w, gx, gy, a, slot, st.skey, (own & 0x7f) == DR_HARVESTED ? 0 : (own & 0x7f), pown, acc,
                                 [&](int am, int oo) { return (unsigned)cb[am][oo + a]; },
                                 [&](int am, int oo) {
@@ -813,9 +965,9 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         const int metab = attr_metab(attr);
         double p = 0.0;
         if (pol) p = __ldcg(&DR_F(poll, D)[D.idx]);
-        if (w.cfg.rule_move_eat) {
+        if (UTIL || w.cfg.rule_move_eat) {
             if (pol) p = p + (((double)sg * w.cfg.pollution_a) + (0.0 * w.cfg.pollution_b));     // agent.py:825-826
-            sugar = ss_set_sugar(ss_max0(sugar + (double)sg));                                     // agent.py:832
+            sugar = ss_set_sugar(ss_max0(sugar + (double)sg));                                     // agent.py:832 / 1128-1130
             // agent.py:864 cell.sugar = 0: the cell's byte takes the marker "harvested" below; the f64 value is
             // dropped by the next growback (or ss_dr_canon_kernel), which saves a scattered 8-byte store per turn
         }
@@ -831,7 +983,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         died = w.cfg.rule_can_starve && sugar <= 0.1;                                              // sugarscape.py:306-309
         const bool risk_next = !died && dr_at_risk(w, sugar, metab);
         const uint32_t new_word = died ? 0u : occ_pack(slot, a, st.next_phase);
-        const uint8_t new_mw = (uint8_t)((died ? 0u : 0x80u) | (w.cfg.rule_move_eat ? DR_HARVESTED : (own & 0x7fu)));
+        const uint8_t new_mw = (uint8_t)((died ? 0u : 0x80u) | ((UTIL || w.cfg.rule_move_eat) ? DR_HARVESTED : (own & 0x7fu)));
         if (moved) {
             // (the cell's occupancy word stays behind: a word counts only where the byte says "occupied")
             S.mw[c] = own & 0x7f;
@@ -975,7 +1127,7 @@ __device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nb
     return s_tail[0];
 }
 
-template <int POLT, bool STRIPS, bool XSYNC>
+template <int POLT, bool STRIPS, bool XSYNC, bool UTIL>
 __global__ void __launch_bounds__(DR_THREADS, 2)
 ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __shared__ DrShared sh;
@@ -998,7 +1150,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
         const unsigned per = min(32u, max(1u, (cnt + nwarp - 1u) / nwarp));
         for (unsigned base = gwarp * per; base < cnt; base += nwarp * per) {
             const unsigned i = base + (unsigned)lane;
-            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS>(w, st, sh, warp, acc, __ldcg(&S.queue[seg_b + i]));
+            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS, UTIL>(w, st, sh, warp, acc, __ldcg(&S.queue[seg_b + i]));
             __syncwarp();
             if (sh.cnt[warp] >= DR_WARP_CAP / 2) dr_flush(w, sh, warp, lane);
         }
@@ -1058,21 +1210,21 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int POLT, bool STRIPS, bool XSYNC>
+template <int POLT, bool STRIPS, bool XSYNC, bool UTIL>
 static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cudaStream_t s) {
     static int per_sm = 0;
     if (!per_sm) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS, XSYNC>, DR_THREADS, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL>, DR_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     st.nblocks = (unsigned)(per_sm * sm_count);
     if (st.single_round) {
-        ss_dr_rounds_kernel<POLT, STRIPS, XSYNC><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
+        ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
         return cudaGetLastError();
     }
     void* args[2] = {(void*)&w, (void*)&st};
-    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS, XSYNC>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
 }
 
 extern "C" {
@@ -1181,10 +1333,11 @@ cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t en
     const bool pol = w.cfg.rule_pollution != 0;
     const bool strips = w.dr.world > 1;
     if (strips) {                   // (strips: no pollution rule; the in-kernel barrier over the strips unless the host drives the rounds)
-        if (single_round) return launch_rounds<0, true, false>(w, st, sm_count, s);
-        return launch_rounds<0, true, true>(w, st, sm_count, s);
+        if (single_round) return launch_rounds<0, true, false, false>(w, st, sm_count, s);
+        return launch_rounds<0, true, true, false>(w, st, sm_count, s);
     }
-    return pol ? launch_rounds<1, false, false>(w, st, sm_count, s) : launch_rounds<0, false, false>(w, st, sm_count, s);
+    if (w.cfg.rule_utilicalc) return launch_rounds<0, false, false, true>(w, st, sm_count, s);   // (never with pollution: the reference crashes)
+    return pol ? launch_rounds<1, false, false, false>(w, st, sm_count, s) : launch_rounds<0, false, false, false>(w, st, sm_count, s);
 }
 
 cudaError_t ss_launch_dr_directory(const DevWorld& w, int n_all, const int32_t* id, const int32_t* x, const int32_t* metab,

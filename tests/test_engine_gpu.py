@@ -208,38 +208,54 @@ def test_lattice_dense_population(opts):
     common.compare_worlds(e, o, 4, what="dense 256 (0.9)")
 
 
+@pytest.mark.parametrize("impl", ["dependency_rounds", "warp_per_window"])
 @pytest.mark.parametrize("n,density,vision,steps,window", [(260, 1 / 16, (1, 6), 10, 96), (300, 1 / 8, (1, 6), 8, 96),
                                                             (512, 1 / 16, (1, 10), 6, 128), (257, 1 / 3, (1, 4), 8, 96),
-                                                            (1000, 1 / 16, (1, 6), 4, 0)])
-def test_lattice_utilicalc_vs_oracle(n, density, vision, steps, window):
-    """The utilicalc rule (agent.py:1025-1141) in the warp-per-window kernel, keyed words: the welfare evaluation fused
-    into the movement scan, every agent settled on the spot -- bit-exact against the CPU oracle (positions, sugar,
-    deaths incl. the Q1 skips, statistics)."""
+                                                            (1000, 1 / 16, (1, 6), 4, 0), (64, 1 / 4, (1, 15), 6, 0)])
+def test_lattice_utilicalc_vs_oracle(n, density, vision, steps, window, impl):
+    """The utilicalc rule (agent.py:1025-1141), keyed words: the welfare evaluation fused into the movement scan, every
+    agent settled on the spot -- as dependency rounds over the whole lattice (one thread per turn, the default) and in the
+    warp-per-window kernel (one warp per turn); bit-exact against the CPU oracle (positions, sugar, deaths incl. the Q1
+    skips, statistics)."""
     s, init = common.synthetic_case(n, False, density=density, vision=vision, utilicalc=True)
     cfg = config_from_settings(s, rng_mode="keyed")
-    e, o = common.engine_world(cfg, options={"solo_window": window} if window else None), common.oracle_world(cfg)
+    if impl == "dependency_rounds":
+        opts, want = {"pass_impl": 3}, 3
+    else:
+        if n < 177:
+            pytest.skip("a single window")
+        opts, want = dict({"pass_impl": 1}, **({"solo_window": window} if window else {})), 1
+    e, o = common.engine_world(cfg, options=opts), common.oracle_world(cfg)
     common.init_world(e, init, "keyed")
     common.init_world(o, init, "keyed")
-    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 1
-    common.compare_worlds(e, o, steps, what="utilicalc %d" % n)
+    assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == want
+    common.compare_worlds(e, o, steps, what="utilicalc %d %s" % (n, impl))
     e.close()
     o.close()
 
 
-def test_lattice_utilicalc_equals_serial_kernel_and_small_lattices_stay_serial():
-    g = common.load_golden("c1_default_utilicalc_keyed")
+@pytest.mark.parametrize("name", [c for c in KEYED_CASES if "utilicalc" in c])
+def test_keyed_utilicalc_rounds_on_reference_golden(name):
+    """The utilicalc turn of the dependency rounds on the goldens recorded from the unmodified reference (keyed words
+    served through the shim): the shipped 50 x 50 presets run on the lattice path too."""
+    g = common.load_golden(name)
     w = common.world_from_golden(g, "engine")
-    assert w.counters()["path"] == 0                      # 50 x 50: a single window -> the serial kernel
+    assert w.counters()["path"] == 2 and w.counters()["pass_impl"] == 3
+    common.run_against_golden(g, w, exact_gini=False)
     w.close()
+
+
+def test_lattice_utilicalc_equals_serial_kernel():
     s, init = common.synthetic_case(400, False, utilicalc=True)
     cfg = config_from_settings(s, rng_mode="keyed")
-    a, b = common.engine_world(cfg), common.engine_world(cfg, path=0)
-    common.init_world(a, init, "keyed")
-    common.init_world(b, init, "keyed")
-    assert (a.counters()["path"], b.counters()["path"]) == (2, 1)
-    common.compare_worlds(a, b, 6, exact_gini=False, what="utilicalc lattice vs serial")
-    a.close()
-    b.close()
+    for opts, impl in (({}, 3), ({"pass_impl": 1}, 1)):
+        a, b = common.engine_world(cfg, options=opts), common.engine_world(cfg, path=0)
+        common.init_world(a, init, "keyed")
+        common.init_world(b, init, "keyed")
+        assert (a.counters()["path"], b.counters()["path"], a.counters()["pass_impl"]) == (2, 1, impl)
+        common.compare_worlds(a, b, 6 if impl == 3 else 3, exact_gini=False, what="utilicalc lattice (%d) vs serial" % impl)
+        a.close()
+        b.close()
 
 
 @pytest.mark.parametrize("opts", [{"pass_impl": 3}, {"pass_impl": 0}, {"pass_impl": 1, "solo_window": 72}, {"pass_impl": 2, "solo_window": 72}])

@@ -1,13 +1,17 @@
-"""Step timings of the dependency-round path: python tools/dr_time.py <n> <pollution 0/1> <steps> [option=value ...]"""
+"""Step timings of the dependency-round path: python tools/dr_time.py <n> <pollution 0/1> <steps> [util=1] [option=value ...]"""
 import sys, os, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import common
 from sugarscape_utilicalc_b200 import config_from_settings
 n, pol, steps = int(sys.argv[1]), int(sys.argv[2]) != 0, int(sys.argv[3])
 opts = {"pass_impl": 3}
+util = False
 for kv in sys.argv[4:]:
-    opts[kv.split("=")[0]] = int(kv.split("=")[1])
-s, init = common.synthetic_case(n, pol)
+    if kv.split("=")[0] == "util":
+        util = int(kv.split("=")[1]) != 0
+    else:
+        opts[kv.split("=")[0]] = int(kv.split("=")[1])
+s, init = common.synthetic_case(n, pol, utilicalc=util)
 cfg = config_from_settings(s, rng_mode="keyed")
 e = common.engine_world(cfg, options=opts)
 common.init_world(e, init, "keyed")
