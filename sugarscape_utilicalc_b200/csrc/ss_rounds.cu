@@ -585,6 +585,23 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
 
 // ------------------------------------------------------------------------------- rounds ----
 struct DrAccum { unsigned sum_m, sum_v, acted, deaths, small, inexact, fault; };
+// the agent's keyed words in sequence: word j = mix64(akey + j * golden) >> 32 (ss_device.cuh), the sum kept running
+struct DrKeyed { uint64_t x; uint32_t j; };
+__device__ static inline void dr_keyed_open(DrKeyed& ks, uint64_t skey, uint32_t slot) { ks.x = ss_agent_key(skey, slot + 1u); ks.j = 0u; }
+__device__ static inline uint32_t dr_keyed_next(DrKeyed& ks) {
+    const uint64_t z = ks.x;
+    ks.x += SS_GOLDEN; ks.j++;
+    return (uint32_t)(ss_mix64(z) >> 32);
+}
+__device__ static inline uint32_t dr_randbelow(DrKeyed& ks, uint32_t nn, DrAccum& acc) {      // random.py:242 _randbelow
+    const int kbits = 32 - __clz(nn);
+    uint32_t r = dr_keyed_next(ks) >> (32 - kbits);
+    while (r >= nn) {
+        r = dr_keyed_next(ks) >> (32 - kbits);
+        if (ks.j > 100000u) { acc.fault++; r = 0u; break; }
+    }
+    return r;
+}
 #define DR_WARPS (DR_THREADS / 32)
 struct DrShared {
     unsigned hist[DR_HIST_BINS];
@@ -713,18 +730,12 @@ __device__ static inline void dr_choose(const DevWorld& w, int gx, int gy, int a
         int p[4];
 #pragma unroll
         for (int t = 0; t < 4; t++) p[t] = t < nt ? __popcll(fm & ((1ull << (int)((tl >> (16 * t)) & 255ull)) - 1ull)) : -1;
-        const uint64_t akey = ss_agent_key(skey, slot + 1u);
-        uint32_t j = 0;
+        DrKeyed ks;
+        dr_keyed_open(ks, skey, slot);
         int left = nt;
 #pragma unroll 1
         for (int i = n_free - 1; i >= 1 && left > 1; i--) {                         // random.py:350 shuffle
-            const uint32_t nn = (uint32_t)i + 1u;
-            const int kbits = 32 - __clz(nn);
-            uint32_t rj = ss_keyed_word(akey, j++) >> (32 - kbits);                 // random.py:242 _randbelow
-            while (rj >= nn) {
-                rj = ss_keyed_word(akey, j++) >> (32 - kbits);
-                if (j > 100000u) { acc.fault++; break; }
-            }
+            const uint32_t rj = dr_randbelow(ks, (uint32_t)i + 1u, acc);
             // the element at index rj moves to index i and is final there; L[i] moves to rj
 #pragma unroll
             for (int t = 0; t < 4; t++) {
@@ -760,26 +771,29 @@ __device__ static inline double dr_util_intensity(double sugar, int metab) {    
                             ? (double)((int)sugar / metab) : ss_py_floordiv(sugar, (double)metab);
     return 1.0 / (1.0 + days);
 }
-struct DrKeyed { uint64_t akey; uint32_t j; };
-__device__ static inline uint32_t dr_randbelow(DrKeyed& ks, uint32_t nn, DrAccum& acc) {      // random.py:242 _randbelow
-    const int kbits = 32 - __clz(nn);
-    uint32_t r = ss_keyed_word(ks.akey, ks.j++) >> (32 - kbits);
-    while (r >= nn) {
-        r = ss_keyed_word(ks.akey, ks.j++) >> (32 - kbits);
-        if (ks.j > 100000u) { acc.fault++; r = 0u; break; }
-    }
-    return r;
+// (site / metabolism) / maxCapacity of utilicalcSugar (agent.py:985-986) for the values that occur: cell sugar < 128,
+// metabolism 1..DR_DUR_M -- two f64 divisions per (move, neighbour) term otherwise.  Filled per CTA with the same two
+// IEEE divisions (ss_dr_rounds_kernel).
+#define DR_DUR_M 8
+__device__ static inline double dr_duration(const DevWorld& w, const double* durtab, int site, int metab) {
+    if (metab >= 1 && metab <= DR_DUR_M) return durtab[(metab - 1) * 128 + site];
+    return ((double)site / (double)metab) / w.cfg.max_capacity;
+}
+// a cell of the cross as the utilities see it: raw coordinates (agent.py:109-110 getDistance works on Agent.x / .y)
+__device__ static inline uint32_t dr_cross_xy(int gx, int gy, int n, int arm, int o) {
+    const int x = arm ? gx : ss_wrap1(gx + o, n), y = arm ? ss_wrap1(gy + o, n) : gy;
+    return ((uint32_t)x << 16) | (uint32_t)y;
 }
 template <class CellByte, class CellWord, class CellRec>
-__device__ static inline void dr_util_choose(const DevWorld& w, int gx, int gy, int a, uint32_t slot, uint64_t skey, unsigned own_byte,
-                                             double own_sugar, int own_metab, DrAccum& acc, CellByte cellbyte, CellWord cellword,
-                                             CellRec cellrec, int& out_arm, int& out_o, int& out_sg) {
+__device__ static inline void dr_util_choose(const DevWorld& w, const double* durtab, int gx, int gy, int a, uint32_t slot, uint64_t skey,
+                                             unsigned own_byte, double own_sugar, int own_metab, DrAccum& acc, CellByte cellbyte,
+                                             CellWord cellword, CellRec cellrec, int& out_arm, int& out_o, int& out_sg) {
     const int n = w.n, span = 2 * a + 1;
     uint8_t mv[DR_UT_MAX];              // moves: candidate numbers, own cell last
-    uint8_t nk[DR_UT_MAX];              // neighbours as found: candidate number of the cell (own last), vision
-    uint8_t nv[DR_UT_MAX];
-    uint8_t perm[DR_UT_MAX];            // ... and their shuffled order
-    double ni[DR_UT_MAX], nm[DR_UT_MAX];        // 1 / (1 + days to starvation), metabolism
+    uint8_t nk[DR_UT_MAX];              // neighbours: candidate numbers of their cells
+    uint32_t nxy[DR_UT_MAX];            // ... in their shuffled order, own last: x << 16 | y,
+    uint32_t nvm[DR_UT_MAX];            //     vision | metabolism << 8 | self << 31,
+    double ni[DR_UT_MAX];               //     1 / (1 + days to starvation)
     double ut[DR_UT_MAX];
     int m = 0, nb = 0;
 #pragma unroll 1
@@ -788,7 +802,22 @@ __device__ static inline void dr_util_choose(const DevWorld& w, int gx, int gy, 
         if (o == 0) continue;                                   // own cell: occupied by the agent, and not a neighbour
         if (cellbyte(arm, o) & 0x80u) nk[nb++] = (uint8_t)k; else mv[m++] = (uint8_t)k;
     }
-    // the neighbours' records, four in flight: occupancy word -> slot -> record
+    DrKeyed ks;
+    dr_keyed_open(ks, skey, slot);
+#pragma unroll 1
+    for (int rep = 0; rep < 2; rep++)                           // getFood's shuffle (agent.py:369), then agent.py:1033
+#pragma unroll 1
+        for (int i = m - 1; i >= 1; i--) {                      // random.py:350
+            const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
+            const uint8_t t = mv[i]; mv[i] = mv[jj]; mv[jj] = t;
+        }
+    mv[m++] = DR_UT_OWN;                                        // agent.py:1035
+#pragma unroll 1
+    for (int i = nb - 1; i >= 1; i--) {                         // agent.py:405
+        const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
+        const uint8_t t = nk[i]; nk[i] = nk[jj]; nk[jj] = t;
+    }
+    // the neighbours' records in that order, four in flight: occupancy word -> slot -> record
 #pragma unroll 1
     for (int q0 = 0; q0 < nb; q0 += 4) {
         uint32_t wd[4];
@@ -808,56 +837,40 @@ __device__ static inline void dr_util_choose(const DevWorld& w, int gx, int gy, 
             if (q0 + u >= nb) continue;
             if (wd[u] == 0u || !attr_alive(rc[u].w)) acc.fault++;
             const double bs = __longlong_as_double((long long)((unsigned long long)rc[u].x | ((unsigned long long)rc[u].y << 32)));
-            const int bm = attr_metab(rc[u].w);
-            ni[q0 + u] = dr_util_intensity(bs, bm); nm[q0 + u] = (double)bm; nv[q0 + u] = (uint8_t)attr_vision(rc[u].w);
+            const int bm = attr_metab(rc[u].w), k = nk[q0 + u], arm = k >= span ? 1 : 0;
+            ni[q0 + u] = dr_util_intensity(bs, bm);
+            nxy[q0 + u] = dr_cross_xy(gx, gy, n, arm, k - arm * span - a);
+            nvm[q0 + u] = (uint32_t)attr_vision(rc[u].w) | ((uint32_t)bm << 8);
         }
-    }
-    DrKeyed ks;
-    ks.akey = ss_agent_key(skey, slot + 1u); ks.j = 0u;
-#pragma unroll 1
-    for (int rep = 0; rep < 2; rep++)                           // getFood's shuffle (agent.py:369), then agent.py:1033
-#pragma unroll 1
-        for (int i = m - 1; i >= 1; i--) {                      // random.py:350
-            const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
-            const uint8_t t = mv[i]; mv[i] = mv[jj]; mv[jj] = t;
-        }
-    mv[m++] = DR_UT_OWN;                                        // agent.py:1035
-    for (int q = 0; q < nb; q++) perm[q] = (uint8_t)q;
-#pragma unroll 1
-    for (int i = nb - 1; i >= 1; i--) {                         // agent.py:405
-        const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
-        const uint8_t t = perm[i]; perm[i] = perm[jj]; perm[jj] = t;
     }
     const double extent = (double)nb;
-    nk[nb] = DR_UT_OWN; nv[nb] = (uint8_t)a; ni[nb] = dr_util_intensity(own_sugar, own_metab); nm[nb] = (double)own_metab;     // agent.py:1039
-    perm[nb] = (uint8_t)nb;
+    ni[nb] = dr_util_intensity(own_sugar, own_metab);           // agent.py:1039: the agent itself, last
+    nxy[nb] = ((uint32_t)gx << 16) | (uint32_t)gy;
+    nvm[nb] = (uint32_t)a | ((uint32_t)own_metab << 8) | 0x80000000u;
     nb++;
     double umax = 0.0;
 #pragma unroll 1
     for (int p = 0; p < m; p++) {
         const int k = mv[p];
-        int mx = gx, my = gy;
+        uint32_t mxy = ((uint32_t)gx << 16) | (uint32_t)gy;
         unsigned b = own_byte;
         if (k != DR_UT_OWN) {
             const int arm = k >= span ? 1 : 0, o = k - arm * span - a;
-            if (arm) my = ss_wrap1(gy + o, n); else mx = ss_wrap1(gx + o, n);
+            mxy = dr_cross_xy(gx, gy, n, arm, o);
             b = cellbyte(arm, o);
         }
-        const double site = (double)((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu));
+        const int mx = (int)(mxy >> 16), my = (int)(mxy & 0xffffu);
+        const int site = (int)((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu));
         double u = 0.0;
 #pragma unroll 1
         for (int q = 0; q < nb; q++) {
-            const int i = perm[q], kb = nk[i], bv = nv[i];
-            int bx = gx, by = gy;
-            if (kb != DR_UT_OWN) {
-                const int arm = kb >= span ? 1 : 0, o = kb - arm * span - a;
-                if (arm) by = ss_wrap1(gy + o, n); else bx = ss_wrap1(gx + o, n);
-            }
-            const bool cert = (bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv);         // agent.py:109-110, raw coordinates
+            const uint32_t xy = nxy[q], vm = nvm[q];
+            const int bx = (int)(xy >> 16), by = (int)(xy & 0xffffu), bv = (int)(vm & 0xffu);
+            const bool cert = (bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv);         // agent.py:109-110
             if (!cert) continue;
-            const double dur = (site / nm[i]) / w.cfg.max_capacity;
-            double t = ((ni[i] + dur) + 0.5 * 0.0) + extent;
-            if (kb != DR_UT_OWN) t *= -1.0;
+            const double dur = dr_duration(w, durtab, site, (int)((vm >> 8) & 0xffffu));
+            double t = ((ni[q] + dur) + 0.5 * 0.0) + extent;
+            if (!(vm >> 31)) t *= -1.0;
             u += t;
         }
         ut[p] = u;
@@ -879,7 +892,7 @@ __device__ static inline void dr_util_choose(const DevWorld& w, int gx, int gy, 
 }
 
 template <int POLT, bool STRIPS, bool UTIL>
-__device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrShared& sh, int warp, DrAccum& acc, uint32_t entry) {
+__device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrShared& sh, const double* durtab, int warp, DrAccum& acc, uint32_t entry) {
     const int n = w.n;
     const DrPeer& S = w.dr.self;
     const uint32_t slot = entry & OCC_SLOT_MASK;
@@ -916,7 +929,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                 double pown = 0.0;
                 if (POLT) pown = __ldcg(&S.poll[c]);
                 if (UTIL)
-                    dr_util_choose(w, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
+                    dr_util_choose(w, durtab, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
                                    [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
                                    [&](int am, int oo) { return __ldcg(&S.occw[am ? c + oo : (uint32_t)((int)c + oo * n)]); },
                                    [&](int, int, uint32_t s2) { return __ldcg(reinterpret_cast<const uint4*>(&S.agents[s2])); }, arm, o, sg);
@@ -939,7 +952,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                     cb[1][oo + a] = __ldcg(&DR_F(mw, Ly)[Ly.idx]);
                 }
                 if (UTIL)
-                    dr_util_choose(w, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
+                    dr_util_choose(w, durtab, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
                                    [&](int am, int oo) { return (unsigned)cb[am][oo + a]; },
                                    [&](int am, int oo) {
                                        const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
@@ -1132,8 +1145,11 @@ __global__ void __launch_bounds__(DR_THREADS, 2)
 ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __shared__ DrShared sh;
     __shared__ unsigned s_tail[2];
+    __shared__ double s_dur[UTIL ? DR_DUR_M * 128 : 1];
     const DrPeer& S = w.dr.self;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (UTIL)
+        for (int i = tid; i < DR_DUR_M * 128; i += DR_THREADS) s_dur[i] = ((double)(i & 127) / (double)((i >> 7) + 1)) / w.cfg.max_capacity;
     for (int i = tid; i < DR_HIST_BINS; i += DR_THREADS) sh.hist[i] = 0u;
     if (tid < 8) sh.acc[tid] = 0ull;
     if (tid < DR_WARPS) sh.cnt[tid] = 0;
@@ -1150,7 +1166,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
         const unsigned per = min(32u, max(1u, (cnt + nwarp - 1u) / nwarp));
         for (unsigned base = gwarp * per; base < cnt; base += nwarp * per) {
             const unsigned i = base + (unsigned)lane;
-            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS, UTIL>(w, st, sh, warp, acc, __ldcg(&S.queue[seg_b + i]));
+            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS, UTIL>(w, st, sh, s_dur, warp, acc, __ldcg(&S.queue[seg_b + i]));
             __syncwarp();
             if (sh.cnt[warp] >= DR_WARP_CAP / 2) dr_flush(w, sh, warp, lane);
         }
