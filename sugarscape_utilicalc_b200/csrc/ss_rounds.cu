@@ -780,19 +780,20 @@ __device__ static inline double dr_duration(const DevWorld& w, const double* dur
     return ((double)site / (double)metab) / w.cfg.max_capacity;
 }
 // a cell of the cross as the utilities see it: raw coordinates (agent.py:109-110 getDistance works on Agent.x / .y)
-__device__ static inline uint32_t dr_cross_xy(int gx, int gy, int n, int arm, int o) {
-    const int x = arm ? gx : ss_wrap1(gx + o, n), y = arm ? ss_wrap1(gy + o, n) : gy;
-    return ((uint32_t)x << 16) | (uint32_t)y;
+__device__ static inline void dr_cross_xy(int gx, int gy, int n, int arm, int o, int& x, int& y) {
+    x = arm ? gx : ss_wrap1(gx + o, n); y = arm ? ss_wrap1(gy + o, n) : gy;
 }
+// NOWRAP: both arms lie inside [0, n) (raw coordinates = wrapped coordinates): which candidate cells a neighbour would
+// see the agent on follows from offsets alone.
 template <class CellByte, class CellWord, class CellRec>
-__device__ static inline void dr_util_choose(const DevWorld& w, const double* durtab, int gx, int gy, int a, uint32_t slot, uint64_t skey,
-                                             unsigned own_byte, double own_sugar, int own_metab, DrAccum& acc, CellByte cellbyte,
-                                             CellWord cellword, CellRec cellrec, int& out_arm, int& out_o, int& out_sg) {
+__device__ static inline void dr_util_choose(const DevWorld& w, const double* durtab, bool nowrap, int gx, int gy, int a, uint32_t slot,
+                                             uint64_t skey, unsigned own_byte, double own_sugar, int own_metab, DrAccum& acc,
+                                             CellByte cellbyte, CellWord cellword, CellRec cellrec, int& out_arm, int& out_o, int& out_sg) {
     const int n = w.n, span = 2 * a + 1;
-    uint8_t mv[DR_UT_MAX];              // moves: candidate numbers, own cell last
+    uint16_t mv[DR_UT_MAX];             // moves: candidate number | int(sugar) << 8, own cell last
     uint8_t nk[DR_UT_MAX];              // neighbours: candidate numbers of their cells
-    uint32_t nxy[DR_UT_MAX];            // ... in their shuffled order, own last: x << 16 | y,
-    uint32_t nvm[DR_UT_MAX];            //     vision | metabolism << 8 | self << 31,
+    unsigned long long seen[DR_UT_MAX]; // ... in their shuffled order, own last: the candidates they would see the agent on (bit 63: own cell),
+    uint32_t nvm[DR_UT_MAX];            //     metabolism << 8 | self << 31,
     double ni[DR_UT_MAX];               //     1 / (1 + days to starvation)
     double ut[DR_UT_MAX];
     int m = 0, nb = 0;
@@ -800,7 +801,9 @@ __device__ static inline void dr_util_choose(const DevWorld& w, const double* du
     for (int k = 0; k < 2 * span; k++) {
         const int arm = k >= span ? 1 : 0, o = k - arm * span - a;
         if (o == 0) continue;                                   // own cell: occupied by the agent, and not a neighbour
-        if (cellbyte(arm, o) & 0x80u) nk[nb++] = (uint8_t)k; else mv[m++] = (uint8_t)k;
+        const unsigned b = cellbyte(arm, o);
+        if (b & 0x80u) nk[nb++] = (uint8_t)k;
+        else mv[m++] = (uint16_t)((unsigned)k | (((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu)) << 8));
     }
     DrKeyed ks;
     dr_keyed_open(ks, skey, slot);
@@ -809,9 +812,9 @@ __device__ static inline void dr_util_choose(const DevWorld& w, const double* du
 #pragma unroll 1
         for (int i = m - 1; i >= 1; i--) {                      // random.py:350
             const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
-            const uint8_t t = mv[i]; mv[i] = mv[jj]; mv[jj] = t;
+            const uint16_t t = mv[i]; mv[i] = mv[jj]; mv[jj] = t;
         }
-    mv[m++] = DR_UT_OWN;                                        // agent.py:1035
+    mv[m++] = (uint16_t)(DR_UT_OWN | (((own_byte & 0x7fu) == DR_HARVESTED ? 0u : (own_byte & 0x7fu)) << 8));        // agent.py:1035
 #pragma unroll 1
     for (int i = nb - 1; i >= 1; i--) {                         // agent.py:405
         const int jj = (int)dr_randbelow(ks, (uint32_t)i + 1u, acc);
@@ -837,41 +840,65 @@ __device__ static inline void dr_util_choose(const DevWorld& w, const double* du
             if (q0 + u >= nb) continue;
             if (wd[u] == 0u || !attr_alive(rc[u].w)) acc.fault++;
             const double bs = __longlong_as_double((long long)((unsigned long long)rc[u].x | ((unsigned long long)rc[u].y << 32)));
-            const int bm = attr_metab(rc[u].w), k = nk[q0 + u], arm = k >= span ? 1 : 0;
+            const int bm = attr_metab(rc[u].w), bv = attr_vision(rc[u].w), k = nk[q0 + u], arm = k >= span ? 1 : 0, ob = k - arm * span - a;
             ni[q0 + u] = dr_util_intensity(bs, bm);
-            nxy[q0 + u] = dr_cross_xy(gx, gy, n, arm, k - arm * span - a);
-            nvm[q0 + u] = (uint32_t)attr_vision(rc[u].w) | ((uint32_t)bm << 8);
+            nvm[q0 + u] = (uint32_t)bm << 8;
+            // certainty (agent.py:982, 109-110): the neighbour sees a cell iff it shares a raw coordinate with it and the
+            // other one differs by at most its vision
+            unsigned long long sm = 0ull;
+            if (nowrap) {
+                // same arm, offsets within its vision; the own cell likewise; never a cell of the other arm
+                const int lo = max(-a, ob - bv), hi = min(a, ob + bv);
+                sm = ((2ull << (hi - lo)) - 1ull) << (arm * span + a + lo);
+                if (abs(ob) <= bv) sm |= 1ull << 63;
+            } else {
+                int bx, by;
+                dr_cross_xy(gx, gy, n, arm, ob, bx, by);
+#pragma unroll 1
+                for (int k2 = 0; k2 < 2 * span; k2++) {
+                    const int arm2 = k2 >= span ? 1 : 0, o2 = k2 - arm2 * span - a;
+                    int mx, my;
+                    dr_cross_xy(gx, gy, n, arm2, o2, mx, my);
+                    if ((bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv)) sm |= 1ull << k2;
+                }
+                if ((bx == gx && abs(by - gy) <= bv) || (by == gy && abs(bx - gx) <= bv)) sm |= 1ull << 63;
+            }
+            seen[q0 + u] = sm;
         }
     }
     const double extent = (double)nb;
     ni[nb] = dr_util_intensity(own_sugar, own_metab);           // agent.py:1039: the agent itself, last
-    nxy[nb] = ((uint32_t)gx << 16) | (uint32_t)gy;
-    nvm[nb] = (uint32_t)a | ((uint32_t)own_metab << 8) | 0x80000000u;
+    nvm[nb] = ((uint32_t)own_metab << 8) | 0x80000000u;
+    {
+        unsigned long long sm = ~0ull;                          // every candidate lies within the agent's own vision ...
+        if (!nowrap) {                                          // ... in raw coordinates unless it was reached across the torus edge
+            sm = 1ull << 63;
+#pragma unroll 1
+            for (int k2 = 0; k2 < 2 * span; k2++) {
+                const int arm2 = k2 >= span ? 1 : 0, o2 = k2 - arm2 * span - a;
+                int mx, my;
+                dr_cross_xy(gx, gy, n, arm2, o2, mx, my);
+                if ((gx == mx && abs(gy - my) <= a) || (gy == my && abs(gx - mx) <= a)) sm |= 1ull << k2;
+            }
+        }
+        seen[nb] = sm;
+    }
     nb++;
     double umax = 0.0;
 #pragma unroll 1
     for (int p = 0; p < m; p++) {
-        const int k = mv[p];
-        uint32_t mxy = ((uint32_t)gx << 16) | (uint32_t)gy;
-        unsigned b = own_byte;
-        if (k != DR_UT_OWN) {
-            const int arm = k >= span ? 1 : 0, o = k - arm * span - a;
-            mxy = dr_cross_xy(gx, gy, n, arm, o);
-            b = cellbyte(arm, o);
-        }
-        const int mx = (int)(mxy >> 16), my = (int)(mxy & 0xffffu);
-        const int site = (int)((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu));
+        const unsigned e = mv[p];
+        const int bit = (e & 255u) == DR_UT_OWN ? 63 : (int)(e & 255u), site = (int)(e >> 8);
         double u = 0.0;
 #pragma unroll 1
         for (int q = 0; q < nb; q++) {
-            const uint32_t xy = nxy[q], vm = nvm[q];
-            const int bx = (int)(xy >> 16), by = (int)(xy & 0xffffu), bv = (int)(vm & 0xffu);
-            const bool cert = (bx == mx && abs(by - my) <= bv) || (by == my && abs(bx - mx) <= bv);         // agent.py:109-110
-            if (!cert) continue;
+            // branch-free: the lanes of a warp are at different (move, neighbour) pairs of different agents.  A neighbour
+            // that would not see the agent there contributes +-0.0 in the reference: the sum stays as it is.
+            const uint32_t vm = nvm[q];
+            const bool cert = ((seen[q] >> bit) & 1ull) != 0ull;
             const double dur = dr_duration(w, durtab, site, (int)((vm >> 8) & 0xffffu));
-            double t = ((ni[q] + dur) + 0.5 * 0.0) + extent;
-            if (!(vm >> 31)) t *= -1.0;
-            u += t;
+            const double t = ((ni[q] + dur) + 0.5 * 0.0) + extent;
+            u += cert ? ((vm >> 31) ? t : -t) : 0.0;
         }
         ut[p] = u;
         if (p == 0 || u > umax) umax = u;
@@ -879,16 +906,13 @@ __device__ static inline void dr_util_choose(const DevWorld& w, const double* du
     int nmax = 0;
     for (int p = 0; p < m; p++) nmax += ut[p] == umax ? 1 : 0;
     int pick = (int)dr_randbelow(ks, (uint32_t)nmax, acc);     // random.choice, agent.py:1108
-    int k = DR_UT_OWN;
+    unsigned e = mv[m - 1];
     for (int p = 0; p < m; p++)
-        if (ut[p] == umax && pick-- == 0) { k = mv[p]; break; }
+        if (ut[p] == umax && pick-- == 0) { e = mv[p]; break; }
+    const int k = (int)(e & 255u);
     out_arm = -1; out_o = 0;
-    unsigned b = own_byte;
-    if (k != DR_UT_OWN) {
-        out_arm = k >= span ? 1 : 0; out_o = k - out_arm * span - a;
-        b = cellbyte(out_arm, out_o);
-    }
-    out_sg = (int)((b & 0x7fu) == DR_HARVESTED ? 0u : (b & 0x7fu));                                        // agent.py:1128-1130
+    if (k != DR_UT_OWN) { out_arm = k >= span ? 1 : 0; out_o = k - out_arm * span - a; }
+    out_sg = (int)(e >> 8);                                     // agent.py:1128-1130
 }
 
 template <int POLT, bool STRIPS, bool UTIL>
@@ -929,7 +953,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                 double pown = 0.0;
                 if (POLT) pown = __ldcg(&S.poll[c]);
                 if (UTIL)
-                    dr_util_choose(w, durtab, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
+                    dr_util_choose(w, durtab, true, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
                                    [&](int am, int oo) { return dr_arm_byte(am ? wy : wx, a + oo); },
                                    [&](int am, int oo) { return __ldcg(&S.occw[am ? c + oo : (uint32_t)((int)c + oo * n)]); },
                                    [&](int, int, uint32_t s2) { return __ldcg(reinterpret_cast<const uint4*>(&S.agents[s2])); }, arm, o, sg);
@@ -952,7 +976,8 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
                     cb[1][oo + a] = __ldcg(&DR_F(mw, Ly)[Ly.idx]);
                 }
                 if (UTIL)
-                    dr_util_choose(w, durtab, gx, gy, a, slot, st.skey, own, sugar, attr_metab(attr), acc,
+                    dr_util_choose(w, durtab, gx - a >= 0 && gx + a < n && gy - a >= 0 && gy + a < n, gx, gy, a, slot, st.skey, own, sugar,
+                                   attr_metab(attr), acc,
                                    [&](int am, int oo) { return (unsigned)cb[am][oo + a]; },
                                    [&](int am, int oo) {
                                        const DrLoc L = dr_loc<STRIPS>(w, am ? gx : ss_wrap1(gx + oo, n), am ? ss_wrap1(gy + oo, n) : gy);
@@ -1160,10 +1185,11 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     const unsigned gwarp = blockIdx.x * DR_WARPS + (unsigned)warp, nwarp = gridDim.x * DR_WARPS;
     for (;;) {
         const unsigned cnt = seg_e - seg_b;
-        // a warp takes consecutive queue entries, 32 at a time in the big rounds; a small round is spread over all warps
-        // (the lanes of a warp run their divergent turns one after the other: fewer lanes, shorter round); no CTA-wide
-        // barrier inside a round
-        const unsigned per = min(32u, max(1u, (cnt + nwarp - 1u) / nwarp));
+        // a warp takes consecutive queue entries, up to 32 at a time, one lane each; every warp gets the same number of
+        // batches (the lanes of a warp run their divergent turns one after the other: a small round is spread over all
+        // warps -- fewer lanes, shorter round); no CTA-wide barrier inside a round
+        const unsigned batches = max(1u, (cnt + 32u * nwarp - 1u) / (32u * nwarp));
+        const unsigned per = min(32u, max(1u, (cnt + batches * nwarp - 1u) / (batches * nwarp)));
         for (unsigned base = gwarp * per; base < cnt; base += nwarp * per) {
             const unsigned i = base + (unsigned)lane;
             if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS, UTIL>(w, st, sh, s_dur, warp, acc, __ldcg(&S.queue[seg_b + i]));
