@@ -18,7 +18,7 @@ cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1
 size_t ss_dr_build_smem(int vmax);
 cudaError_t ss_launch_dr_transpose(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_dr_canon(const DevWorld& w, cudaStream_t s);
-cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, cudaStream_t s);
+cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, int max_ctas, cudaStream_t s);
 cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_dr_encode_tmap(const DevWorld& w, void* tmap_storage, int* ok);
 cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void* tmap_storage, int use_tma, cudaStream_t s);
@@ -84,6 +84,13 @@ struct ss_engine {
     int mirror = 0;                            // which int(sugar) mirror is current: 1 = isugar (window passes), 2 = mw (rounds)
     bool cap_fits_u7 = true;
     bool dr_dirty = false;                      // sugar / occw hold what the rounds tidy lazily (dr_tidy)
+    // dependency rounds: statistics, growback and diffusion of step t run on a second stream beside the conflict-graph
+    // kernel of step t + 1 (which reads occupancy and priorities only); the rounds of t + 1 wait for them
+    cudaStream_t stream_env = nullptr;
+    cudaEvent_t ev_rounds = nullptr, ev_env = nullptr;
+    bool env_in_flight = false;
+    int overlap_option = 1;
+    int grow_ctas_per_sm = 2;                   // ... as a few CTAs per SM that fit beside the conflict-graph CTAs
     // row strips (one engine per GPU): this engine holds the lattice rows [x0, x0 + rows)
     int strip_rank = 0, strip_world = 1, x0 = 0, rows = 0;
     uint32_t global_slots = 0;                  // max Agent.id over all strips (options "global_slots", "global_vmax")
@@ -189,6 +196,13 @@ static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32
     if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce, "cudaSetDevice");
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "stream");
+    {
+        int lo = 0, hi = 0;             // (greatest priority = lowest number: the second stream's CTAs go first when an SM has room)
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((ce = cudaStreamCreateWithPriority(&e->stream_env, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(ce, "stream");
+    }
+    if ((ce = cudaEventCreateWithFlags(&e->ev_rounds, cudaEventDisableTiming)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_env, cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "cudaEventCreate");
     const size_t cb = e->cells * sizeof(double);
     if ((ce = cudaMalloc(&e->w.sugar, cb)) != cudaSuccess) return bail(ce, "cudaMalloc sugar");
     if ((ce = cudaMalloc(&e->w.cap, cb)) != cudaSuccess) return bail(ce, "cudaMalloc cap");
@@ -237,6 +251,9 @@ extern "C" void ss_destroy(ss_engine* e) {
     if (e->evs) cudaEventDestroy(e->evs);
     if (e->eve) cudaEventDestroy(e->eve);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream_env) cudaStreamDestroy(e->stream_env);
+    if (e->ev_rounds) cudaEventDestroy(e->ev_rounds);
+    if (e->ev_env) cudaEventDestroy(e->ev_env);
     delete e;
 }
 
@@ -696,13 +713,15 @@ static int dr_alloc(ss_engine* e) {
     return SS_OK;
 }
 
-static int env_phase(ss_engine* e) {
+static int env_phase(ss_engine* e, cudaStream_t stream = nullptr) {
+    if (!stream) stream = e->stream;
     {
         KTimer t(e, KT_GROW);
         // the growback refreshes the int(sugar) mirror that is current (cell words of the rounds / isugar bytes)
         if (e->cfg.rule_grow) {
-            if (e->mirror == 2) CK(ss_launch_dr_grow(e->w, e->iteration, e->stream));       // + both layouts of the cell bytes
-            else CK(ss_launch_grow(e->w, e->iteration, e->sm_count, 0, e->stream));
+            if (e->mirror == 2)                                                     // + both layouts of the cell bytes
+                CK(ss_launch_dr_grow(e->w, e->iteration, stream == e->stream ? 0 : e->grow_ctas_per_sm * e->sm_count, stream));
+            else CK(ss_launch_grow(e->w, e->iteration, e->sm_count, 0, stream));
             e->launches++;
         }
     }
@@ -710,9 +729,17 @@ static int env_phase(ss_engine* e) {
         e->iteration % e->cfg.diffusion_rate == 0) {                                  // sugarscape.py:661-663
         KTimer t(e, KT_DIFFUSE);
         if (!e->d_handoff) CK(cudaMalloc(&e->d_handoff, ss_diffuse_handoff_bytes(e->w.n)));
-        CK(ss_launch_diffuse(e->w, e->d_flags, e->d_handoff, e->diffuse_impl, e->stream));
+        CK(ss_launch_diffuse(e->w, e->d_flags, e->d_handoff, e->diffuse_impl, stream));
         e->launches++;
     }
+    return SS_OK;
+}
+
+// the main stream waits for what the second stream still runs (end of a stepping call; before anything else touches the state)
+static int env_join(ss_engine* e) {
+    if (!e->env_in_flight) return SS_OK;
+    CK(cudaStreamWaitEvent(e->stream, e->ev_env, 0));
+    e->env_in_flight = false;
     return SS_OK;
 }
 
@@ -757,12 +784,16 @@ static int dr_step(ss_engine* e, int stats_index) {
         if (flag) return set_err(e, SS_ERR_UNSUPPORTED, "dependency rounds need cell sugar and capacities < 127");
         e->mirror = 2;
     }
+    // the conflict graph of this step reads occupancy, priorities and the alive / at-risk bitmaps -- nothing the previous
+    // step's statistics, growback or diffusion touch -- so it runs beside them; the rounds need all of it
+    const bool overlap = e->overlap_option && !e->profile && !e->trace;
     {
         KTimer t(e, KT_PREPARE);
-        CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
-        CK(ss_launch_prepare(e->w, e->iteration, 0, e->stream));
         if (e->trace) { CK(cudaStreamSynchronize(e->stream)); fprintf(stderr, "[ss] step %lld: build\n", (long long)e->iteration); }
         CK(ss_launch_dr_build(e->w, e->iteration, e->tmap, e->tma_ok && e->use_tma, e->stream));
+        { const int rc = env_join(e); if (rc) return rc; }
+        CK(cudaMemsetAsync(e->w.hist, 0, SS_GINI_BINS * sizeof(uint32_t), e->stream));
+        CK(ss_launch_prepare(e->w, e->iteration, 0, e->stream));
         e->launches += 5;
         if (e->trace) {
             CK(cudaStreamSynchronize(e->stream));
@@ -783,12 +814,24 @@ static int dr_step(ss_engine* e, int stats_index) {
         CK(ss_launch_dr_check(e->w, e->stream));
         e->launches += 2; e->passes++;
     }
+    cudaStream_t env_stream = e->stream;
+    if (overlap) {
+        env_stream = e->stream_env;
+        CK(cudaEventRecord(e->ev_rounds, e->stream));
+        CK(cudaStreamWaitEvent(env_stream, e->ev_rounds, 0));
+    }
     {
         KTimer t(e, KT_STATS);
-        CK(ss_launch_stats(e->w, stats_index, e->stream));
+        CK(ss_launch_stats(e->w, stats_index, env_stream));
         e->launches++;
     }
-    return env_phase(e);
+    const int rc = env_phase(e, env_stream);
+    if (rc) return rc;
+    if (overlap) {
+        CK(cudaEventRecord(e->ev_env, env_stream));
+        e->env_in_flight = true;
+    }
+    return SS_OK;
 }
 
 static int lattice_step(ss_engine* e, int stats_index) {
@@ -886,6 +929,7 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
         }
     }
     e->stepped = true;
+    { const int rcj = env_join(e); if (rcj) return rcj; }
     CK(cudaEventRecord(e->eve, e->stream));
     if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1101,6 +1145,8 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "global_slots") { e->global_slots = (uint32_t)value; return SS_OK; }
     if (k == "global_vmax") { e->global_vmax = (int)value; return SS_OK; }
     if (k == "l2_persist") { e->l2_persist = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
+    if (k == "overlap") { e->overlap_option = (int)value; return SS_OK; }
+    if (k == "grow_ctas") { e->grow_ctas_per_sm = (int)value; return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }

@@ -37,7 +37,12 @@
 #define DR_TX 64                        // tile rows (x)
 #define DR_TY 64                        // tile columns (y, contiguous in memory)
 #define DR_BUILD_THREADS 512
+#ifndef DR_THREADS
 #define DR_THREADS 512                  // rounds kernel
+#endif
+#ifndef DR_MIN_BLOCKS
+#define DR_MIN_BLOCKS 2                 // ... resident CTAs per SM the register allocation aims at
+#endif
 #define DR_WARP_CAP 128                 // staged queue entries per warp between flushes
 #define DR_HIST_BINS 2048               // low wealth bins kept in shared memory per CTA
 #define DR_SKIP 0x80000000u             // queue entry flag: the agent loses its turn (Q1)
@@ -125,7 +130,7 @@ __global__ void ss_dr_canon_kernel(DevWorld w, size_t cells) {
 // environment.py:133-155 growback (whole lattice or the two season rectangles) on 64 x 64-cell tiles, fused with the
 // refresh of the cell bytes in both layouts: 8 + 8 + 1 bytes read, 8 + 1 + 1 written per cell.
 struct DrGrowArgs {
-    int seasons;
+    int seasons, tiles;
     double alpha, alpha_north, alpha_south;
 };
 __global__ void __launch_bounds__(256)
@@ -134,7 +139,9 @@ ss_dr_grow_kernel(DevWorld w, DrGrowArgs ga) {
     const DrPeer& S = w.dr.self;
     const int n = w.n, rows = S.rows;
     const int tiles_y = (n + 63) >> 6;
-    const int bx = blockIdx.x / tiles_y, by = blockIdx.x - bx * tiles_y;
+    // (one CTA per tile, or -- beside the conflict-graph kernel of the next step -- a few CTAs per SM that walk the tiles)
+    for (int tile = blockIdx.x; tile < ga.tiles; tile += gridDim.x) {
+    const int bx = tile / tiles_y, by = tile - bx * tiles_y;
     const int r0 = bx << 6, y0 = by << 6;
     const int32_t* rn = w.cfg.season_north;
     const int32_t* rs = w.cfg.season_south;
@@ -192,6 +199,8 @@ ss_dr_grow_kernel(DevWorld w, DrGrowArgs ga) {
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     for (int k = ty; k < 64; k += 4)
         if (y0 + k < n && r0 + tx < rows) S.mwx[(size_t)(y0 + k) * rows + r0 + tx] = t[tx][k];
+    __syncthreads();
+    }
 }
 
 // alive / at-risk bitmaps and the ATTR_RISK flag from the agent store (after an upload).
@@ -1166,7 +1175,7 @@ __device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nb
 }
 
 template <int POLT, bool STRIPS, bool XSYNC, bool UTIL>
-__global__ void __launch_bounds__(DR_THREADS, 2)
+__global__ void __launch_bounds__(DR_THREADS, DR_MIN_BLOCKS)
 ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __shared__ DrShared sh;
     __shared__ unsigned s_tail[2];
@@ -1292,7 +1301,7 @@ cudaError_t ss_launch_dr_canon(const DevWorld& w, cudaStream_t s) {
 }
 
 // sugarscape.py:642-659: growback of the whole lattice, or of the two season regions with the season's factors
-cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, cudaStream_t s) {
+cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, int max_ctas, cudaStream_t s) {
     DrGrowArgs ga;
     ga.seasons = w.cfg.rule_seasons; ga.alpha = w.cfg.grow_factor; ga.alpha_north = ga.alpha_south = 0.0;
     if (w.cfg.rule_seasons) {
@@ -1301,7 +1310,8 @@ cudaError_t ss_launch_dr_grow(const DevWorld& w, int64_t iteration, cudaStream_t
         ga.alpha_south = summer ? w.cfg.season_off_factor : w.cfg.season_on_factor;
     }
     const int tiles = ((w.dr.self.rows + 63) / 64) * ((w.n + 63) / 64);
-    ss_dr_grow_kernel<<<tiles, 256, 0, s>>>(w, ga);
+    ga.tiles = tiles;
+    ss_dr_grow_kernel<<<max_ctas > 0 ? std::min(tiles, max_ctas) : tiles, 256, 0, s>>>(w, ga);
     return cudaGetLastError();
 }
 

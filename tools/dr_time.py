@@ -9,6 +9,9 @@ util = False
 for kv in sys.argv[4:]:
     if kv.split("=")[0] == "util":
         util = int(kv.split("=")[1]) != 0
+    elif kv.split("=")[0] == "lib":         # an A/B build of the library (tools/build_alt.sh)
+        from sugarscape_utilicalc_b200 import capi
+        capi.LIB_PATH = os.path.join(os.path.dirname(capi.LIB_PATH), "alt_%s.so" % kv.split("=")[1])
     else:
         opts[kv.split("=")[0]] = int(kv.split("=")[1])
 s, init = common.synthetic_case(n, pol, utilicalc=util)
