@@ -13,7 +13,8 @@ RNG_MT19937 = 0
 RNG_KEYED = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsugarscape_b200.so")
+# (SS_B200_LIB: an A/B build of the same library, tools/build_alt.sh)
+LIB_PATH = os.environ.get("SS_B200_LIB") or os.path.join(_HERE, "csrc", "libsugarscape_b200.so")
 
 
 class SsConfig(C.Structure):

@@ -2111,7 +2111,9 @@ ss_diffuse_kernel(double* __restrict__ p, int n, int* ticket, int* progress) {
 // slots from the compute warp) keep a shared ring of old values filled with cp.async, write finished chunks back, load
 // the row above the band once the previous band (previous ticket) has published it through its global progress flag,
 // and publish this band's progress.  Producer/consumer counters live in shared memory.
+#ifndef DCOL_R
 #define DCOL_R 4
+#endif
 #define DCOL_ROWS (32 * DCOL_R)
 #define DCOL_H 3
 __device__ __forceinline__ double dcol_lds(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
