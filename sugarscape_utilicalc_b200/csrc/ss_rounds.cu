@@ -339,8 +339,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
     typedef typename DrWide<WIDE>::Pair PairT;
     constexpr int PS = DrWide<WIDE>::SHIFT;                // bits per coordinate in a pair entry
     extern __shared__ __align__(128) uint32_t sm[];
-    __shared__ int s_all, s_n, s_ready, s_fill;
-    __shared__ unsigned s_base;
+    __shared__ int s_all, s_n;
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_cnt[DR_BUILD_THREADS / 32][2][32];   // per warp and agent of the batch: predecessors, successors
     // HP: the halo as staged, 2V rounded up to a multiple of 4 cells (the TMA box wants rows of a multiple of 32 bytes)
@@ -357,7 +356,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
     const int tx = blockIdx.x / ba.tiles_y, ty = blockIdx.x - tx * ba.tiles_y;
     const int x0 = S.x0 + tx * DR_TX, y0 = ty * DR_TY;     // lattice coordinates of the tile's first interior cell
     const int ex = min(DR_TX, S.x0 + S.rows - x0), ey = min(DR_TY, n - y0);      // interior extent
-    if (tid == 0) { s_all = 0; s_n = 0; s_ready = 0; s_fill = 0; }
+    if (tid == 0) { s_all = 0; s_n = 0; }
     for (int i = tid; i < SX * BW + SY * BWT; i += DR_BUILD_THREADS) bm[i] = 0u;
     // the tile and its halo lie inside this strip and inside [0, n) in y: one TMA box; otherwise plain loads with wraps
     const bool interior = ba.use_tma && x0 - HP >= S.x0 && x0 + DR_TX + HP <= S.x0 + S.rows && y0 - HP >= 0 && y0 + DR_TY + HP <= n;
@@ -374,15 +373,29 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                 ::"r"(smem_u32(tileS)), "l"(&tmap), "r"(y0 - HP), "r"(x0 - HP - S.x0), "r"(smem_u32(&s_bar)) : "memory");
         }
+        // a word counts only where the cell byte says "occupied" (the turns leave the words of vacated cells behind):
+        // the bytes of the staged rows, four cells per lane, are fetched while the box is in flight
+        // (rows start at multiples of 4 bytes: n % 4 == 0 with the TMA path, y0 and HP are multiples of 4; SX, SY <= 128)
+        uint32_t mb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = warp + i * nwarps;
+            mb[i] = 0x80808080u;
+            if (r < SX && 4 * lane < SY)
+                mb[i] = __ldcg(reinterpret_cast<const uint32_t*>(S.mw + (size_t)(x0 - HP - S.x0 + r) * n + (y0 - HP)) + lane);
+        }
         uint32_t done = 0;                                 // everybody waits for the box (phase 0)
         while (!done) {
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
         }
-        // a word counts only where the cell byte says "occupied" (the turns leave the words of vacated cells behind)
-        for (int r = warp; r < SX; r += nwarps) {
-            const uint8_t* src = S.mw + (size_t)(x0 - HP - S.x0 + r) * n + (y0 - HP);
-            for (int q = lane; q < SY; q += 32) if (!(__ldcg(&src[q]) & 0x80)) tileS[r * SY + q] = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = warp + i * nwarps;
+            if (r < SX && 4 * lane < SY) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (!((mb[i] >> (8 * j)) & 0x80u)) tileS[r * SY + 4 * lane + j] = 0u;
+            }
         }
     } else {
         __syncthreads();
@@ -561,6 +574,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             if (!__any_sync(FULL, have && lane >= first)) break;
         }
         __syncwarp();
+        bool ready = false;
         if (have) {
             const uint32_t nsucc = pool_bad ? (uint32_t)DR_SUCC_INLINE : cnt_s[lane], preds = cnt_p[lane];
             uint32_t* rec = reinterpret_cast<uint32_t*>(w.dr.succ) + (size_t)slot * 16;
@@ -575,21 +589,20 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
                 }
             }
             reinterpret_cast<uint16_t*>(S.dep)[slot] = (uint16_t)indeg;
-            if (indeg == 0) { ilist[k] |= 0x8000u; atomicAdd(&s_ready, 1); }
+            ready = indeg == 0;
+        }
+        // agents without predecessors enter the queue: one reservation per warp and batch (the other warps of the CTA
+        // work on while it is in flight)
+        const unsigned rm = __ballot_sync(FULL, ready);
+        if (rm) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&S.ctl[DR_CTL_TAIL], (unsigned)__popc(rm));
+            base = __shfl_sync(FULL, base, 0);
+            if (ready) S.queue[base + (unsigned)__popc(rm & below)] = slot | DR_VALID;
         }
         __syncwarp();
     }
-    __syncthreads();
     if (tid == 0 && nl) atomicAdd(&S.ctl[DR_CTL_AGENTS], (unsigned)nl);
-    if (tid == 0 && s_ready) s_base = atomicAdd(&S.ctl[0], (unsigned)s_ready);
-    __syncthreads();
-    if (s_ready) {
-        for (int k = tid; k < nl; k += DR_BUILD_THREADS) {
-            if (!(ilist[k] & 0x8000u)) continue;
-            const int lr = (ilist[k] >> 7) & 255, lq = ilist[k] & 127;
-            S.queue[s_base + (unsigned)atomicAdd(&s_fill, 1)] = occ_slot(tileS[lr * SY + lq]) | DR_VALID;
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------- rounds ----

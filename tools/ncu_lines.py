@@ -1,11 +1,12 @@
 """Per-source-line aggregation of an `ncu --page source --print-source cuda,sass --csv` export: instructions executed and
-warp-stall samples per CUDA source line (python tools/ncu_lines.py <csv> [top N])."""
+warp-stall samples per CUDA source line (python tools/ncu_lines.py <csv> [top N] [substring of the kernel name])."""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-hdr, cur_file, agg = None, None, {}
+only = sys.argv[3] if len(sys.argv) > 3 else None
+hdr, cur_file, agg, use = None, None, {}, True
 for r in rows:
     if not r:
         continue
@@ -13,6 +14,9 @@ for r in rows:
         cur_file = r[1].split('/')[-1]
         continue
     if r[0] == 'Function Name':
+        use = only is None or only in r[1]
+        continue
+    if not use:
         continue
     if r[0] == 'Line No':
         hdr = r
