@@ -20,6 +20,16 @@
  *   - lattice arrays are (N,N) row-major with linear index x*N + y, where x is the
  *     reference's FIRST grid index (grid[i][j], i = agent.x) -- "lattice-major".
  *   - unsupported rule combinations fail in ss_create: there is no CPU fallback.
+ *
+ * Limits (a run outside them fails with SS_ERR_UNSUPPORTED in ss_create / ss_upload_agents, never silently)
+ *   - Agent.id <= 2^24 = 16,777,216 on the lattice paths (a cell's occupancy word keeps the slot in 24 bits; BASELINE
+ *     config 5 sits exactly on it), <= 2^22 on the serial path (SS_RNG_MT19937: one CTA walks the list).
+ *   - vision <= 15 and N >= 4 * max vision + 1 on the lattice paths (larger: serial path).
+ *   - cell sugar and capacity < 127 for the dependency rounds (one byte per cell: occupied | int(sugar)), < 256 for the
+ *     window passes; larger capacities run on the serial path.
+ *   - wealth statistics: exact for any wealth (integer wealth < 65536 through a histogram, everything else through an
+ *     outlier list of 4096 values per step; beyond that the step reports gini = NaN and raises the `inexact` counter).
+ *   - row strips (ss_create_strip): rule M without pollution, keyed order, >= 4 * max vision + 1 rows per strip.
  */
 #ifndef SUGARSCAPE_B200_H
 #define SUGARSCAPE_B200_H
