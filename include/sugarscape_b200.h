@@ -75,6 +75,14 @@ typedef struct {
     uint64_t keyed_seed;          /* seed of the keyed word source (SS_RNG_KEYED)          */
     int64_t iteration;            /* View.iteration at upload                              */
     int64_t env_time;             /* Environment.time at upload                            */
+    /* limited lifespan + procreation (serial path, SS_RNG_MT19937; ss_upload_agents_life) */
+    int32_t rule_limited_lifespan;/* rules.limitedLifespan sugarscape.py:588-597; setSugar floors at 0 (agent.py:226) */
+    int32_t rule_procreate;       /* rules.procreate       sugarscape.py:543-554, agent.py:653-773 */
+    int32_t tags_length;          /* rule_params.tags.tags_length: createChild draws random() per differing tag bit
+                                     (agent.py:727-737), with or without the tags rule                               */
+    int32_t foresight_lo;         /* Environment.foresightRange, (0, 0) unless rules.foresight: Agent.__init__ of a  */
+    int32_t foresight_hi;         /* child spends randint(lo, hi) on generateForesight (agent.py:165, 329-333)       */
+    int32_t reserved0;
 } ss_config;
 
 /* What one updateGame() appends to View.population / metabolismMean / visionMean / gini

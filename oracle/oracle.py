@@ -24,6 +24,8 @@ class SsoConfig(C.Structure):
         ("grow_factor", C.c_double), ("season_on_factor", C.c_double), ("season_off_factor", C.c_double),
         ("pollution_a", C.c_double), ("pollution_b", C.c_double), ("max_capacity", C.c_double),
         ("keyed_seed", C.c_uint64), ("iteration", C.c_int64), ("env_time", C.c_int64),
+        ("rule_limited_lifespan", C.c_int32), ("rule_procreate", C.c_int32), ("tags_length", C.c_int32),
+        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -71,6 +73,13 @@ def lib():
         L.sso_download_cells.argtypes = [vp, vp, vp, vp, vp]
         L.sso_agent_count.argtypes = [vp]
         L.sso_download_agents.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.sso_upload_agents_life.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.sso_download_agents_life.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.sso_id_increment.argtypes = [vp]
+        L.sso_id_increment.restype = C.c_int32
+        L.sso_event_count.argtypes = [vp]
+        L.sso_event_count.restype = C.c_int32
+        L.sso_get_events.argtypes = [vp, C.c_int32, vp]
         _lib = L
     return _lib
 
@@ -157,3 +166,28 @@ class OracleWorld:
         self._check(lib().sso_download_agents(self._h, _ptr(id), _ptr(x), _ptr(y), _ptr(vision), _ptr(metab),
                                               _ptr(sugar)))
         return dict(id=id, x=x, y=y, vision=vision, metab=metab, sugar=sugar)
+
+    # limitedLifespan / procreate
+    LIFE_COLUMNS = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
+
+    def upload_agents_life(self, id_increment, age, max_age, sex, fert_lo, fert_hi, endowment, tags, alive=None):
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        age, max_age, sex, fert_lo, fert_hi, tags, alive = map(i32, (age, max_age, sex, fert_lo, fert_hi, tags, alive))
+        endowment = np.ascontiguousarray(endowment, dtype=np.float64)
+        self._check(lib().sso_upload_agents_life(self._h, len(age), int(id_increment), _ptr(age), _ptr(max_age), _ptr(sex),
+                                                 _ptr(fert_lo), _ptr(fert_hi), _ptr(endowment), _ptr(tags), _ptr(alive)))
+
+    def download_agents_life(self):
+        k = lib().sso_agent_count(self._h)
+        cols = {c: np.empty(k, dtype=np.float64 if c == "endowment" else np.int32) for c in self.LIFE_COLUMNS}
+        self._check(lib().sso_download_agents_life(self._h, *[_ptr(cols[c]) for c in self.LIFE_COLUMNS]))
+        cols["id_increment"] = int(lib().sso_id_increment(self._h))
+        return cols
+
+    def events(self):
+        """(k, 4) int32: kind | step << 8, a, b, c of the last step() call (see ss_oracle.h)."""
+        k = int(lib().sso_event_count(self._h))
+        out = np.zeros((k, 4), dtype=np.int32)
+        if k:
+            self._check(lib().sso_get_events(self._h, k, _ptr(out)))
+        return out

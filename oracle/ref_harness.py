@@ -303,6 +303,16 @@ class ReferenceRun:
             vision=np.array([a.vision for a in ags], dtype=np.int32),
             metab=np.array([a.sugarMetabolism for a in ags], dtype=np.int32),
             sugar_agent=np.array([a.sugar for a in ags], dtype=np.float64),
+            # what the lifespan / procreation rules read (agent.py:134-151, 204-206)
+            age=np.array([a.age for a in ags], dtype=np.int32),
+            max_age=np.array([a.maxAge for a in ags], dtype=np.int32),
+            sex=np.array([a.sex for a in ags], dtype=np.int32),
+            fert_lo=np.array([a.fertility[0] for a in ags], dtype=np.int32),
+            fert_hi=np.array([a.fertility[1] for a in ags], dtype=np.int32),
+            endowment=np.array([a.sugarEndowment for a in ags], dtype=np.float64),
+            tags=np.array([a.tags for a in ags], dtype=np.int32),
+            alive=np.array([1 if a.alive else 0 for a in ags], dtype=np.int32),
+            id_increment=int(env.idIncrement),
         )
         mt, idx = self.mt_state()
         snap["mt"], snap["mt_index"] = mt, idx

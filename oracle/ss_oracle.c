@@ -15,6 +15,8 @@
  *   Agent.utilicalcSugar       agent.py:980-992
  *   Agent.utilicalcMove        agent.py:1025-1141
  *   Agent.setSugar             agent.py:224-229
+ *   Agent.incAge / mate / findFreeLocationAround / createChild / isFertile / getNeighbourhood
+ *                              agent.py:636-639, 653-679, 681-696, 698-750, 764-773, 373-389   
  *   Environment.grow/growRegion environment.py:133-155
  *   Environment.polluteSite    environment.py:312-315
  *   Environment.spreadPollution environment.py:317-350
@@ -45,7 +47,19 @@ struct sso_world {
     int32_t min_slots;
     int32_t *ax, *ay, *avision, *ametab;
     double* asugar;
-    uint8_t* alive;
+    uint8_t* alive;           /* in View.agents (and on the lattice) */
+    /* SURVEY 8 f3 (limitedLifespan / procreate): Agent.age, maxAge, sex, fertility, sugarEndowment (= sugarCostForMating,
+     * agent.py:204-206 with the (0, 0) cost range), tags, Agent.alive (0 for an agent that reached maxAge: it stays in the
+     * list and on the lattice for one more turn, sugarscape.py:588-601) */
+    int32_t cap_slots;        /* allocation of the per-slot arrays and of order / wealth */
+    int32_t id_increment;     /* Environment.idIncrement: ids handed out so far */
+    int have_life;
+    int32_t *age, *max_age, *sex, *fert_lo, *fert_hi, *tags;
+    double* endow;
+    uint8_t* living;
+    int32_t* events;          /* 4 per event: kind | step << 8, a, b, c -- kind 1: a mated with b and created c; 2: a died of
+                                 starvation; 3: a died of old age (sugarscape.py:551, 597-600) */
+    int32_t n_events, cap_events, step_in_call;
     /* persistent list order (slots) */
     int32_t* order;
     int32_t n_order;
@@ -171,8 +185,11 @@ static double py_floordiv(double vx, double wx) {
     }
     return fl;
 }
-/* agent.py:224-229 setSugar (limitedLifespan off -> floor .01) */
-static inline double set_sugar(double amount) { return amount > 0.01 ? amount : 0.01; }
+/* agent.py:224-229 setSugar: max(amount, 0 if limitedLifespan else .01) */
+static inline double set_sugar(const sso_world* w, double amount) {
+    const double fl = w->cfg.rule_limited_lifespan ? 0.0 : 0.01;
+    return amount > fl ? amount : fl;
+}
 static inline double max0(double v) { return v > 0.0 ? v : 0.0; }
 
 /* environment.py:312-315 */
@@ -234,7 +251,7 @@ static void agent_move(sso_world* w, int s) {
         }
     }
     if (w->cfg.rule_pollution) pollute_site(w, best, (double)best_sg, 0.0);   /* agent.py:825-826 */
-    w->asugar[s] = set_sugar(max0(w->asugar[s] + (double)best_sg));            /* agent.py:832 */
+    w->asugar[s] = set_sugar(w, max0(w->asugar[s] + (double)best_sg));            /* agent.py:832 */
     int old = x * n + y;
     if (best != old) {                                                          /* agent.py:856-862 */
         w->occ[old] = -1;
@@ -288,8 +305,115 @@ static void agent_utilicalc(sso_world* w, int s) {
     w->ax[s] = dest / n;
     w->ay[s] = dest % n;
     int sg = (int)w->sugar[dest];
-    w->asugar[s] = set_sugar(max0(w->asugar[s] + (double)sg));
+    w->asugar[s] = set_sugar(w, max0(w->asugar[s] + (double)sg));
     w->sugar[dest] = 0.0;
+}
+
+/* ------------------------------------------------------------ lifespan + procreation ---- */
+static int ensure_capacity(sso_world* w, int32_t need) {
+    if (need <= w->cap_slots) return 0;
+    int32_t nc = w->cap_slots > 0 ? w->cap_slots : 1;
+    while (nc < need) nc *= 2;
+#define GROW(p, T) do { T* q = (T*)realloc(p, (size_t)nc * sizeof(T)); if (!q) return fail("out of memory"); \
+                        memset(q + w->cap_slots, 0, (size_t)(nc - w->cap_slots) * sizeof(T)); p = q; } while (0)
+    GROW(w->ax, int32_t); GROW(w->ay, int32_t); GROW(w->avision, int32_t); GROW(w->ametab, int32_t);
+    GROW(w->asugar, double); GROW(w->alive, uint8_t); GROW(w->order, int32_t); GROW(w->wealth, double);
+    GROW(w->sortk, uint64_t); GROW(w->sortk2, uint64_t);
+    GROW(w->age, int32_t); GROW(w->max_age, int32_t); GROW(w->sex, int32_t); GROW(w->fert_lo, int32_t);
+    GROW(w->fert_hi, int32_t); GROW(w->tags, int32_t); GROW(w->endow, double); GROW(w->living, uint8_t);
+#undef GROW
+    w->cap_slots = nc;
+    return 0;
+}
+static void add_event(sso_world* w, int kind, int a, int b, int c) {
+    if (w->n_events == w->cap_events) {
+        int32_t nc = w->cap_events ? 2 * w->cap_events : 1024;
+        int32_t* q = (int32_t*)realloc(w->events, (size_t)nc * 4 * sizeof(int32_t));
+        if (!q) return;
+        w->events = q; w->cap_events = nc;
+    }
+    int32_t* e = w->events + 4 * (size_t)w->n_events++;
+    e[0] = kind | (w->step_in_call << 8); e[1] = a; e[2] = b; e[3] = c;
+}
+/* agent.py:764-773 isFertile, no-spice branch (sugarCostForMating = the endowment, agent.py:204-206) */
+static int is_fertile(const sso_world* w, int s) {
+    return w->fert_lo[s] <= w->age[s] && w->age[s] <= w->fert_hi[s] && w->asugar[s] >= w->endow[s];
+}
+/* agent.py:681-696 findFreeLocationAround: no torus here (isLocationValid), x-line then y-line, randint over the list */
+static int find_free_around(sso_world* w, int x, int y) {
+    int n = w->n, loc[6], m = 0;
+    for (int i = x - 1; i <= x + 1; i++)
+        if (i >= 0 && i < n && w->occ[i * n + y] < 0) loc[m++] = i * n + y;
+    for (int j = y - 1; j <= y + 1; j++)
+        if (j >= 0 && j < n && w->occ[x * n + j] < 0) loc[m++] = x * n + j;
+    if (!m) return -1;
+    return loc[randbelow(w, (uint32_t)m)];
+}
+/* random.py random(): (a * 2^26 + b) / 2^53 with a = genrand >> 5, b = genrand >> 6 (_randommodule.c) */
+static double random_random(sso_world* w) {
+    uint32_t a = next_word(w) >> 5, b = next_word(w) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+/* agent.py:698-750 createChild(parent = b) of agent s at cell loc; the child joins the end of View.agents
+ * (sugarscape.py:550) and is met by the running loop in this very step */
+static int create_child(sso_world* w, int s, int b, int loc) {
+    int g[2] = {s, b};
+    int metab = w->ametab[g[randbelow(w, 2u)]];
+    (void)randbelow(w, 2u);                                   /* spiceMetabolism */
+    int vision = w->avision[g[randbelow(w, 2u)]];
+    double endow = 0.5 * (w->endow[s] + w->endow[b]);
+    w->asugar[s] = set_sugar(w, max0(w->asugar[s] - 0.5 * w->endow[s]));
+    w->asugar[b] = set_sugar(w, max0(w->asugar[b] - 0.5 * w->endow[b]));
+    int max_age = w->max_age[g[randbelow(w, 2u)]];
+    int sex = (int)randbelow(w, 2u);
+    int fg = g[randbelow(w, 2u)];
+    int32_t mask = 1, tags = 0;
+    for (int t = 0; t < w->cfg.tags_length; t++) {            /* agent.py:727-737 */
+        int32_t t1 = w->tags[s] & mask, t2 = w->tags[b] & mask;
+        if (t1 == t2 || random_random(w) < 0.5) tags |= t1; else tags |= t2;
+        mask <<= 1;
+    }
+    int c = w->id_increment;                                  /* slot = id - 1; Environment.getNewId */
+    if (ensure_capacity(w, c + 1)) return -1;
+    w->id_increment = c + 1;
+    if (c + 1 > w->n_slots) w->n_slots = c + 1;
+    w->ax[c] = loc / w->n; w->ay[c] = loc % w->n;
+    w->ametab[c] = metab; w->avision[c] = vision;
+    w->endow[c] = endow;
+    w->asugar[c] = set_sugar(w, endow);                       /* setInitialSugarEndowment */
+    w->age[c] = 0; w->max_age[c] = max_age; w->sex[c] = sex;
+    w->fert_lo[c] = w->fert_lo[fg]; w->fert_hi[c] = w->fert_hi[fg];
+    w->tags[c] = tags;
+    w->alive[c] = 1; w->living[c] = 1;
+    (void)randbelow(w, (uint32_t)(w->cfg.foresight_hi - w->cfg.foresight_lo + 1));   /* generateForesight, agent.py:165 */
+    w->occ[loc] = c;
+    w->order[w->n_order++] = c;
+    add_event(w, 1, s + 1, b + 1, c + 1);
+    return 0;
+}
+/* sugarscape.py:543-554 + agent.py:653-679 mate(): every fertile neighbour of the other sex, in shuffled order */
+static void procreate(sso_world* w, int s) {
+    int n = w->n, x = w->ax[s], y = w->ay[s];
+    int32_t nb[4];
+    int m = 0;
+    for (int xx = x - 1; xx <= x + 1; xx++) {                 /* agent.py:373-389 getNeighbourhood */
+        if (xx == x) continue;
+        int c = wrap(xx, n) * n + y;
+        if (w->occ[c] >= 0) nb[m++] = w->occ[c];
+    }
+    for (int yy = y - 1; yy <= y + 1; yy++) {
+        if (yy == y) continue;
+        int c = x * n + wrap(yy, n);
+        if (w->occ[c] >= 0) nb[m++] = w->occ[c];
+    }
+    shuffle_i32(w, nb, m);
+    for (int k = 0; k < m; k++) {
+        int b = nb[k];
+        if (w->sex[b] == w->sex[s] || !is_fertile(w, b)) continue;
+        int loc = find_free_around(w, w->ax[s], w->ay[s]);
+        if (loc < 0) loc = find_free_around(w, w->ax[b], w->ay[b]);
+        if (loc >= 0 && is_fertile(w, s)) create_child(w, s, b, loc);
+    }
 }
 
 static int cmp_double(const void* a, const void* b) {
@@ -375,17 +499,28 @@ static void one_step(sso_world* w, sso_step_stats* st) {
         if (cfg->rng_mode == 1) keyed_begin_agent(w, s + 1);
         if (cfg->rule_move_eat) agent_move(w, s);
         if (cfg->rule_utilicalc) agent_utilicalc(w, s);
+        if (cfg->rule_procreate && is_fertile(w, s)) procreate(w, s);        /* sugarscape.py:543-554 */
         /* sugarscape.py:566-567 consumption pollution */
         if (cfg->rule_pollution && w->asugar[s] > 0.0)
             pollute_site(w, w->ax[s] * n + w->ay[s], 0.0, (double)w->ametab[s]);
         /* sugarscape.py:569 */
-        w->asugar[s] = set_sugar(max0(w->asugar[s] - (double)w->ametab[s]));
+        w->asugar[s] = set_sugar(w, max0(w->asugar[s] - (double)w->ametab[s]));
         sum_m += (double)w->ametab[s];
         sum_v += (double)w->avision[s];
         w->wealth[nw++] = w->asugar[s];
         acted++;
-        if (cfg->rule_can_starve && w->asugar[s] <= 0.1) {      /* sugarscape.py:306-309, 593-601 */
+        int living = w->have_life ? w->living[s] : 1;          /* Agent.alive: 0 for an agent that reached maxAge last step */
+        if (cfg->rule_can_starve && w->asugar[s] <= 0.1) living = 0;    /* sugarscape.py:306-309 */
+        if (living && cfg->rule_limited_lifespan) {             /* sugarscape.py:588-591 + agent.py:636-639 incAge */
+            w->age[s]++;
+            w->living[s] = (uint8_t)(w->max_age[s] > w->age[s]);        /* (the agent stays for one more turn) */
+        }
+        if (!living) {                                          /* sugarscape.py:593-601 */
             w->alive[s] = 0;
+            if (w->have_life) {
+                w->living[s] = 0;
+                add_event(w, cfg->rule_limited_lifespan && w->age[s] > w->max_age[s] ? 3 : 2, s + 1, 0, 0);
+            }
             w->occ[w->ax[s] * n + w->ay[s]] = -1;
             deaths++;
             skip_next = 1;
@@ -450,11 +585,19 @@ int sso_create(const sso_config* cfg, sso_world** out) {
     return 0;
 }
 
+static void free_agents(sso_world* w) {
+    free(w->ax); free(w->ay); free(w->avision); free(w->ametab); free(w->asugar); free(w->alive);
+    free(w->order); free(w->wealth); free(w->sortk); free(w->sortk2);
+    free(w->age); free(w->max_age); free(w->sex); free(w->fert_lo); free(w->fert_hi); free(w->tags); free(w->endow); free(w->living);
+    w->ax = w->ay = w->avision = w->ametab = w->order = w->age = w->max_age = w->sex = w->fert_lo = w->fert_hi = w->tags = NULL;
+    w->asugar = w->wealth = w->endow = NULL; w->alive = w->living = NULL; w->sortk = w->sortk2 = NULL;
+    w->cap_slots = 0;
+}
 void sso_destroy(sso_world* w) {
     if (!w) return;
     free(w->sugar); free(w->cap); free(w->poll); free(w->occ);
-    free(w->ax); free(w->ay); free(w->avision); free(w->ametab); free(w->asugar); free(w->alive);
-    free(w->order); free(w->wealth); free(w->sortk); free(w->sortk2);
+    free_agents(w);
+    free(w->events);
     free(w);
 }
 
@@ -478,21 +621,13 @@ int sso_upload_agents(sso_world* w, int32_t n, const int32_t* id, const int32_t*
         if (metab[i] < 1) return fail("metabolism must be >= 1");
         if (x[i] < 0 || x[i] >= w->n || y[i] < 0 || y[i] >= w->n) return fail("agent off the grid");
     }
-    free(w->ax); free(w->ay); free(w->avision); free(w->ametab); free(w->asugar); free(w->alive);
-    free(w->order); free(w->wealth); free(w->sortk); free(w->sortk2);
+    free_agents(w);
     int32_t ns = max_id > 0 ? max_id : 1;
     if (w->min_slots > ns) ns = w->min_slots;      /* a resumed run keeps the order width of the original upload */
     w->n_slots = ns;
-    w->ax = (int32_t*)calloc((size_t)ns, sizeof(int32_t));
-    w->ay = (int32_t*)calloc((size_t)ns, sizeof(int32_t));
-    w->avision = (int32_t*)calloc((size_t)ns, sizeof(int32_t));
-    w->ametab = (int32_t*)calloc((size_t)ns, sizeof(int32_t));
-    w->asugar = (double*)calloc((size_t)ns, sizeof(double));
-    w->alive = (uint8_t*)calloc((size_t)ns, 1);
-    w->order = (int32_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
-    w->wealth = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
-    w->sortk = (uint64_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(uint64_t));
-    w->sortk2 = (uint64_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(uint64_t));
+    w->id_increment = max_id;
+    w->have_life = 0;
+    if (ensure_capacity(w, ns)) return -1;         /* every per-slot array, the list and the scratch arrays (n <= ns) */
     size_t cells = (size_t)w->n * (size_t)w->n;
     for (size_t c = 0; c < cells; c++) w->occ[c] = -1;
     for (int i = 0; i < n; i++) {
@@ -532,7 +667,56 @@ int sso_get_rng_mt19937(sso_world* w, uint32_t state[624], int32_t* index) {
 
 int sso_step(sso_world* w, int32_t nsteps, sso_step_stats* out) {
     sso_step_stats tmp;
-    for (int t = 0; t < nsteps; t++) one_step(w, out ? &out[t] : &tmp);
+    if ((w->cfg.rule_limited_lifespan || w->cfg.rule_procreate) && !w->have_life)
+        return fail("limitedLifespan / procreate: sso_upload_agents_life first");
+    w->n_events = 0;
+    for (int t = 0; t < nsteps; t++) { w->step_in_call = t; one_step(w, out ? &out[t] : &tmp); }
+    return 0;
+}
+
+/* the Agent fields of the lifespan / procreation rules for the n agents of the last sso_upload_agents, same
+ * order; id_increment = Environment.idIncrement (ids handed out so far, >= the largest id) */
+int sso_upload_agents_life(sso_world* w, int32_t n, int32_t id_increment, const int32_t* age, const int32_t* max_age,
+                           const int32_t* sex, const int32_t* fert_lo, const int32_t* fert_hi, const double* endowment,
+                           const int32_t* tags, const int32_t* alive) {
+    if (n != w->n_order) return fail("sso_upload_agents_life: n differs from the uploaded agents");
+    if (w->cfg.rng_mode != 0) return fail("limitedLifespan / procreate: MT19937 mode only");
+    if (w->cfg.rule_utilicalc) return fail("limitedLifespan / procreate: rule M only");
+    if (w->cfg.tags_length < 0 || w->cfg.tags_length > 30) return fail("tags_length out of range [0,30]");
+    if (id_increment < w->n_slots && id_increment < w->id_increment) return fail("id_increment below the largest id");
+    for (int i = 0; i < n; i++) {
+        int s = w->order[i];
+        w->age[s] = age[i]; w->max_age[s] = max_age[i]; w->sex[s] = sex[i];
+        w->fert_lo[s] = fert_lo[i]; w->fert_hi[s] = fert_hi[i];
+        w->endow[s] = endowment[i]; w->tags[s] = tags[i];
+        w->living[s] = (uint8_t)(alive ? (alive[i] != 0) : 1);
+    }
+    if (id_increment > w->id_increment) w->id_increment = id_increment;
+    w->have_life = 1;
+    return 0;
+}
+int sso_download_agents_life(sso_world* w, int32_t* age, int32_t* max_age, int32_t* sex, int32_t* fert_lo, int32_t* fert_hi,
+                             double* endowment, int32_t* tags, int32_t* alive) {
+    if (!w->have_life) return fail("no life columns uploaded");
+    for (int i = 0; i < w->n_order; i++) {
+        int s = w->order[i];
+        if (age) age[i] = w->age[s];
+        if (max_age) max_age[i] = w->max_age[s];
+        if (sex) sex[i] = w->sex[s];
+        if (fert_lo) fert_lo[i] = w->fert_lo[s];
+        if (fert_hi) fert_hi[i] = w->fert_hi[s];
+        if (endowment) endowment[i] = w->endow[s];
+        if (tags) tags[i] = w->tags[s];
+        if (alive) alive[i] = w->living[s];
+    }
+    return 0;
+}
+int32_t sso_id_increment(sso_world* w) { return w->id_increment; }
+/* events of the last sso_step call, in execution order: 4 ints each (see struct sso_world) */
+int32_t sso_event_count(sso_world* w) { return w->n_events; }
+int sso_get_events(sso_world* w, int32_t max_events, int32_t* out) {
+    int32_t k = w->n_events < max_events ? w->n_events : max_events;
+    if (k > 0) memcpy(out, w->events, (size_t)k * 4 * sizeof(int32_t));
     return 0;
 }
 

@@ -42,6 +42,11 @@ typedef struct {
     uint64_t keyed_seed;          /* seed of the keyed word source                          */
     int64_t iteration;            /* View.iteration at upload                               */
     int64_t env_time;             /* Environment.time at upload                             */
+    int32_t rule_limited_lifespan;/* rules.limitedLifespan                                  */
+    int32_t rule_procreate;       /* rules.procreate                                        */
+    int32_t tags_length;          /* rule_params.tags.tags_length                           */
+    int32_t foresight_lo, foresight_hi;   /* Environment.foresightRange                     */
+    int32_t reserved0;
 } sso_config;
 
 typedef struct {
@@ -72,6 +77,18 @@ int  sso_agent_count(sso_world* w);
 /* living agents in list order */
 int  sso_download_agents(sso_world* w, int32_t* id, int32_t* x, int32_t* y, int32_t* vision,
                          int32_t* metab, double* sugar);
+/* SURVEY 8 f3 (limitedLifespan / procreate; MT19937 mode, rule M): the Agent fields the rules read, for the n agents of
+ * the last sso_upload_agents in the same order; id_increment = Environment.idIncrement */
+int  sso_upload_agents_life(sso_world* w, int32_t n, int32_t id_increment, const int32_t* age, const int32_t* max_age,
+                            const int32_t* sex, const int32_t* fert_lo, const int32_t* fert_hi, const double* endowment,
+                            const int32_t* tags, const int32_t* alive);
+int  sso_download_agents_life(sso_world* w, int32_t* age, int32_t* max_age, int32_t* sex, int32_t* fert_lo, int32_t* fert_hi,
+                              double* endowment, int32_t* tags, int32_t* alive);
+int32_t sso_id_increment(sso_world* w);
+/* events of the last sso_step call in execution order, 4 ints each: kind | step << 8, a, b, c -- kind 1: a mated with b
+ * and created c (sugarscape.py:551); 2: a died of starvation; 3: a died of old age (sugarscape.py:597-600) */
+int32_t sso_event_count(sso_world* w);
+int  sso_get_events(sso_world* w, int32_t max_events, int32_t* out);
 const char* sso_last_error(void);
 
 #ifdef __cplusplus

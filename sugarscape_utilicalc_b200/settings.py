@@ -31,8 +31,8 @@ class UnsupportedRuleError(Exception):
 
 
 #: rules.* keys the engine implements; everything else must be false
-SUPPORTED_RULES = ("grow", "seasons", "moveEat", "canStarve", "pollution", "utilicalc")
-UNSUPPORTED_RULES = ("tags", "combat", "limitedLifespan", "replacement", "procreate", "transmit", "spice",
+SUPPORTED_RULES = ("grow", "seasons", "moveEat", "canStarve", "pollution", "utilicalc", "limitedLifespan", "procreate")
+UNSUPPORTED_RULES = ("tags", "combat", "replacement", "transmit", "spice",
                      "trade", "foresight", "credit", "inheritance", "disease")
 
 
@@ -77,6 +77,9 @@ def check_supported(settings):
     if rules["utilicalc"] and rules["pollution"]:
         raise UnsupportedRuleError(
             "utilicalc+pollution raises KeyError: 'duration' in the reference (agent.py:880); parity is unpinned")
+    if (rules.get("limitedLifespan", False) or rules.get("procreate", False)) and not rules["moveEat"]:
+        raise UnsupportedRuleError("limitedLifespan / procreate are built with rule M (moveEat) only: with utilicalc the "
+                                   "reference needs spice (examples/utilicalc_spice raises KeyError 'proximity')")
 
 
 def config_from_settings(settings, rng_mode="mt", keyed_seed=None, iteration=0, env_time=0):
@@ -115,6 +118,14 @@ def config_from_settings(settings, rng_mode="mt", keyed_seed=None, iteration=0, 
     cfg.keyed_seed = int(env["random_seed"] if keyed_seed is None else keyed_seed) & ((1 << 64) - 1)
     cfg.iteration = int(iteration)
     cfg.env_time = int(env_time)
+    cfg.rule_limited_lifespan = int(bool(rules.get("limitedLifespan", False)))
+    cfg.rule_procreate = int(bool(rules.get("procreate", False)))
+    if cfg.rule_limited_lifespan or cfg.rule_procreate:
+        if rng_mode != "mt":
+            raise UnsupportedRuleError("limitedLifespan / procreate run in the MT19937-exact mode only (births change the "
+                                       "id range the keyed order is sized by)")
+        cfg.tags_length = int(rp["tags"]["tags_length"])                    # sugarscape.py:110
+    cfg.foresight_lo, cfg.foresight_hi = 0, 0                               # Environment.foresightRange without the rule
     return cfg
 
 

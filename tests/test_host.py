@@ -47,11 +47,24 @@ def test_rule_check_matches_reference_order_and_messages():
 
 
 def test_out_of_scope_rules_are_refused_loudly():
-    for r in ("tags", "limitedLifespan", "replacement", "procreate", "transmit", "spice", "disease"):
+    for r in ("tags", "replacement", "transmit", "spice", "disease"):
         s = _settings()
         s["rules"][r] = True
         with pytest.raises((UnsupportedRuleError, ConflictingRuleException, MissingRuleException)):
             config_from_settings(s)
+    # limitedLifespan / procreate run with rule M in the MT19937-exact mode -- and nowhere else
+    for r in ("limitedLifespan", "procreate"):
+        s = _settings()
+        s["rules"][r] = True
+        if s["rules"]["utilicalc"]:
+            with pytest.raises(UnsupportedRuleError):    # (with utilicalc the reference needs spice and crashes)
+                config_from_settings(s)
+        s["rules"]["moveEat"], s["rules"]["utilicalc"] = True, False
+        cfg = config_from_settings(s, rng_mode="mt")
+        assert (cfg.rule_limited_lifespan, cfg.rule_procreate) == (int(r == "limitedLifespan"), int(r == "procreate"))
+        assert cfg.tags_length == s["rule_params"]["tags"]["tags_length"]
+        with pytest.raises(UnsupportedRuleError):
+            config_from_settings(s, rng_mode="keyed")
     s = _settings()
     s["rules"]["moveEat"], s["rules"]["utilicalc"], s["rules"]["pollution"] = False, True, True
     with pytest.raises(UnsupportedRuleError):            # the reference raises KeyError 'duration' (agent.py:880)
