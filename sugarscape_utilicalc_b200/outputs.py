@@ -24,6 +24,20 @@ _GOLDEN = 0x9E3779B97F4A7C15
 _C_ROUND = 0xA24BAED4963EE407
 
 
+def event_lines(events):
+    """The `appendToLog` lines of the engine's event records (`Engine.events()`: kind | step << 8, a, b, c per event, in
+    execution order): sugarscape.py:551 "Agent A mated with agent B and created agent C", :597-600 "Agent A
+    died of old age" / "... of starvation" -- each with the four-space indent of `indent="    "`."""
+    out = []
+    for e in np.asarray(events).reshape(-1, 4):
+        kind = int(e[0]) & 255
+        if kind == 1:
+            out.append("    Agent %d mated with agent %d and created agent %d" % (e[1], e[2], e[3]))
+        else:
+            out.append("    Agent %d died of %s" % (e[1], "old age" if kind == 3 else "starvation"))
+    return out
+
+
 def _mix64(z):
     z &= _M64
     z ^= z >> 30

@@ -20,6 +20,10 @@ GOLDEN_CASES = [
 ]
 
 
+LIFE_CASES = ["f3_evolution_metabolism_mt", "f3_procreate_only_mt"]      # SURVEY 8 f3, recorded by make_golden.py f3
+LIFE_COLUMNS = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
+
+
 def load_golden(name):
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
     g["settings"] = json.loads(str(g["settings_json"]))
@@ -46,14 +50,20 @@ def engine_world(cfg, path=-1, options=None):
 def init_world(world, init, rng, mt=None, mt_index=None):
     world.upload_cells(init["sugar"], init["cap"], init["pollution"])
     world.upload_agents(init["id"], init["x"], init["y"], init["vision"], init["metab"], init["sugar_agent"])
+    if init.get("life") is not None:
+        world.upload_agents_life(init["id_increment"], **init["life"])
     if rng == "mt":
         world.set_rng_mt19937(mt, mt_index)
 
 
 def golden_init(g):
-    return dict(sugar=g["init_sugar"], cap=g["init_cap"], pollution=g["init_pollution"], id=g["init_order"],
+    init = dict(sugar=g["init_sugar"], cap=g["init_cap"], pollution=g["init_pollution"], id=g["init_order"],
                 x=g["init_x"], y=g["init_y"], vision=g["init_vision"], metab=g["init_metab"],
                 sugar_agent=g["init_sugar_agent"])
+    if "init_life_age" in g:
+        init["life"] = {k: g["init_life_" + k] for k in LIFE_COLUMNS}
+        init["id_increment"] = int(g["init_id_increment"])
+    return init
 
 
 def world_from_golden(g, kind, path=-1):
@@ -83,14 +93,19 @@ def assert_state_equal(cells, agents, exp, ordered=True, what=""):
 def run_against_golden(g, world, exact_gini=True, chunk=None, max_steps=None):
     """Step `world` through the golden run; compare the stat series every step and the full
     state at every checkpoint."""
+    from sugarscape_utilicalc_b200 import outputs
     steps = g["steps"] if max_steps is None else min(max_steps, g["steps"])
     cps = sorted(int(k[2:].split("_")[0]) for k in g if k.startswith("cp") and k.endswith("_occ"))
     cps = [c for c in cps if c <= steps]
+    life = "init_life_age" in g
+    log = []
     t = 0
     for cp in cps:
         while t < cp:
             k = cp - t if chunk is None else min(chunk, cp - t)
             st = world.step(k)
+            if life:
+                log += outputs.event_lines(world.events())
             sl = slice(t, t + k)
             assert np.array_equal(st["population"], g["population"][sl]), "population differs in steps %d..%d" % (t, t + k)
             assert np.array_equal(st["metabolism_mean"], g["metabolismMean"][sl]), "metabolismMean differs"
@@ -101,7 +116,15 @@ def run_against_golden(g, world, exact_gini=True, chunk=None, max_steps=None):
                 np.testing.assert_allclose(st["gini"], g["gini"][sl], rtol=1e-9, atol=1e-12)
             t += k
         exp = {k2: g["cp%d_%s" % (cp, k2)] for k2 in ("sugar", "pollution", "occ", "order", "x", "y", "sugar_agent")}
-        assert_state_equal(world.download_cells(), world.download_agents(), exp, ordered=True, what="step %d" % cp)
+        ags = world.download_agents()
+        assert_state_equal(world.download_cells(), ags, exp, ordered=True, what="step %d" % cp)
+        if life:            # the fields the lifespan / procreation rules carry, and the event lines so far
+            lf = world.download_agents_life()
+            for c in LIFE_COLUMNS:
+                assert np.array_equal(lf[c], g["cp%d_life_%s" % (cp, c)]), "step %d: Agent.%s differs" % (cp, c)
+            assert np.array_equal(ags["vision"], g["cp%d_life_vision" % cp]) and np.array_equal(ags["metab"], g["cp%d_life_metab" % cp])
+            assert lf["id_increment"] == int(g["cp%d_id_increment" % cp]), "Environment.idIncrement differs"
+            assert log == str(g["log_text"]).split("\n")[:int(g["cp%d_log_lines" % cp])], "event log differs by step %d" % cp
     if g["rng"] == "mt" and steps == g["steps"]:
         mt, idx = world.get_rng_mt19937()
         assert idx == int(g["final_mt_index"]) and np.array_equal(mt, g["final_mt"]), "MT19937 state differs"

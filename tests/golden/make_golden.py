@@ -32,13 +32,20 @@ def pos_digest(snap):
     return zlib.crc32(arr.tobytes())
 
 
-def record(name, settings, steps, rng, world=None):
+LIFE = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
+
+
+def record(name, settings, steps, rng, world=None, life=False):
     r = rh.ReferenceRun(settings, rng=rng, world=world)
     out = {"settings_json": json.dumps(settings), "rng": rng, "steps": steps}
     s0 = r.snapshot()
     for k in ("sugar", "cap", "pollution", "order", "x", "y", "vision", "metab", "sugar_agent", "mt"):
         out["init_" + k] = s0[k]
     out["init_mt_index"] = s0["mt_index"]
+    if life:
+        for k in LIFE:
+            out["init_life_" + k] = s0[k]
+        out["init_id_increment"] = s0["id_increment"]
     dig = np.zeros((steps, 5), dtype=np.float64)  # sum agent sugar, sum cell sugar, sum pollution, pos crc, mt idx
     for t in range(steps):
         r.step()
@@ -48,6 +55,11 @@ def record(name, settings, steps, rng, world=None):
         if (t + 1) in CHECKPOINTS or t + 1 == steps:
             for k in ("sugar", "pollution", "occ", "order", "x", "y", "sugar_agent"):
                 out["cp%d_%s" % (t + 1, k)] = sn[k]
+            if life:
+                for k in LIFE + ("vision", "metab"):
+                    out["cp%d_life_%s" % (t + 1, k)] = sn[k]
+                out["cp%d_id_increment" % (t + 1)] = sn["id_increment"]
+                out["cp%d_log_lines" % (t + 1)] = len(r.view.log)
     st = r.stats()
     out["population"] = np.array(st["population"], dtype=np.float64)
     out["metabolismMean"] = np.array(st["metabolismMean"], dtype=np.float64)
@@ -56,13 +68,26 @@ def record(name, settings, steps, rng, world=None):
     out["digest"] = dig
     out["final_mt"], out["final_mt_index"] = sn["mt"], sn["mt_index"]
     out["exited_at"] = -1 if r.exited_at is None else r.exited_at
+    if life:
+        out["log_text"] = "\n".join(r.view.log)         # the event lines of the run (sugarscape.py:551, 597-600)
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print("%-28s rng=%-5s steps=%-4d pop %d -> %d  (%d KB)" % (
         name, rng, steps, len(s0["order"]), st["population"][-1], os.path.getsize(path) // 1024))
 
 
+def main_life():
+    """SURVEY 8 f3: examples/evolution_metabolism as shipped (grow + moveEat + canStarve + limitedLifespan + procreate;
+    examples/tag_flipping has the same settings), and the same world with procreation alone."""
+    record("f3_evolution_metabolism_mt", rh.load_settings("evolution_metabolism"), 300, "mt", life=True)
+    s = rh.load_settings("evolution_metabolism")
+    s["rules"]["limitedLifespan"] = False
+    record("f3_procreate_only_mt", s, 120, "mt", life=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "f3":
+        return main_life()
     default = rh.load_settings()
     move_eat = rh.load_settings()
     move_eat["rules"]["moveEat"], move_eat["rules"]["utilicalc"] = True, False
@@ -84,6 +109,7 @@ def main():
         w = synthetic.tiled_world(n)
         s = synthetic.synthetic_settings(n, pollution=pol)
         record("c4_synth%d_%s_keyed" % (n, "poll" if pol else "nopoll"), s, steps, "keyed", world=w)
+    main_life()
 
 
 if __name__ == "__main__":

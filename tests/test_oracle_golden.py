@@ -12,6 +12,18 @@ def test_oracle_matches_reference_golden(name):
     w.close()
 
 
+@pytest.mark.parametrize("name", common.LIFE_CASES)
+def test_oracle_lifespan_and_procreation_match_reference_golden(name):
+    """examples/evolution_metabolism (= examples/tag_flipping) as shipped, and procreation without the
+    lifespan rule -- cells, agents in list order (newborns act in the step they are born in, an agent that reached maxAge
+    stays for one more turn), age / sex / fertility / endowment / tags, Environment.idIncrement, the event lines and the
+    MT19937 state, step by step against the unmodified reference."""
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "oracle")
+    assert common.run_against_golden(g, w, exact_gini=True, chunk=3) == g["steps"]
+    w.close()
+
+
 def test_oracle_chunked_steps_equal_single_steps():
     g = common.load_golden("c2_pollution_mt")
     w = common.world_from_golden(g, "oracle")
