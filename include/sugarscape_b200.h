@@ -147,6 +147,25 @@ int  ss_upload_cells(ss_engine* e, const double* sugar, const double* cap, const
 int  ss_upload_agents(ss_engine* e, int32_t n, const int32_t* id, const int32_t* x, const int32_t* y,
                       const int32_t* vision, const int32_t* metab, const double* sugar);
 
+/* SURVEY 8 f3 -- limitedLifespan + procreate (rule M, SS_RNG_MT19937, serial path).
+ * Replaces: Agent.age / maxAge / sex / fertility / sugarEndowment (= sugarCostForMating) / tags / alive (agent.py:134-151,
+ * 204-206) as read by incAge (agent.py:636-639), isFertile (764-773), mate (653-679), createChild (698-750) and
+ * updateGame's aging / removal branch (sugarscape.py:543-554, 588-601); Environment.idIncrement (environment.py:202-204).
+ * ss_upload_agents_life: the columns of the n agents of the last ss_upload_agents, same order (alive may be NULL = all 1);
+ * required before ss_step when either rule is on.  ss_download_agents_life: the same columns in View.agents order
+ * (ss_agent_count entries -- an agent that reached maxAge stays in the list with alive = 0 for one more step, exactly
+ * as in the reference).  Children get ids id_increment + 1, ...; ss_download_agents / ss_download_cells report them.
+ * ss_event_count / ss_get_events: the appendToLog events of the last ss_step call in execution order, 4 ints each:
+ * kind | (step << 8), a, b, c -- kind 1 "Agent a mated with agent b and created agent c" (sugarscape.py:551), 2 "Agent a
+ * died of starvation", 3 "Agent a died of old age" (sugarscape.py:597-600). */
+int  ss_upload_agents_life(ss_engine* e, int32_t n, int32_t id_increment, const int32_t* age, const int32_t* max_age,
+                           const int32_t* sex, const int32_t* fert_lo, const int32_t* fert_hi, const double* endowment,
+                           const int32_t* tags, const int32_t* alive);
+int  ss_download_agents_life(ss_engine* e, int32_t* age, int32_t* max_age, int32_t* sex, int32_t* fert_lo, int32_t* fert_hi,
+                             double* endowment, int32_t* tags, int32_t* alive, int32_t* id_increment);
+int  ss_event_count(ss_engine* e, int32_t* count);
+int  ss_get_events(ss_engine* e, int32_t max_events, int32_t* out);
+
 /* Replaces: the global `random` state (random.getstate()[1]; sugarscape.py:160-162). */
 int  ss_set_rng_mt19937(ss_engine* e, const uint32_t state[624], int32_t index);
 int  ss_get_rng_mt19937(ss_engine* e, uint32_t state[624], int32_t* index);

@@ -63,6 +63,7 @@ EXPORTS = (
     "ss_shard_apply_gathered", "ss_shard_pending", "ss_shard_end_step", "ss_host_alloc", "ss_host_free", "ss_seed_mt19937", "ss_init_world",
     "ss_create_strip", "ss_strip_init_directory", "ss_strip_export", "ss_strip_connect", "ss_strip_ipc_export",
     "ss_strip_ipc_connect", "ss_strip_step", "ss_strip_phase",
+    "ss_upload_agents_life", "ss_download_agents_life", "ss_event_count", "ss_get_events",
 )
 
 _lib = None
@@ -119,6 +120,10 @@ def lib():
     L.ss_strip_ipc_connect.argtypes = [vp, C.c_int32, vp]
     L.ss_strip_step.argtypes = [vp, C.c_int32, vp]
     L.ss_strip_phase.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), vp]
+    L.ss_upload_agents_life.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ss_download_agents_life.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32)]
+    L.ss_event_count.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.ss_get_events.argtypes = [vp, C.c_int32, vp]
     L.ss_host_alloc.argtypes = [C.c_size_t]
     L.ss_host_alloc.restype = vp
     L.ss_host_free.argtypes = [vp]

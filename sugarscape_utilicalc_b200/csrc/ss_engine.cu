@@ -10,9 +10,10 @@
 #include <vector>
 
 #include "ss_world.cuh"
+#include "ss_life.cuh"
 
 extern "C" {
-cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
+cudaError_t ss_launch_serial(const DevWorld& w, const LifeWorld& lw, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
                              int stats_base, cudaStream_t stream);
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1, cudaStream_t s);
 size_t ss_dr_build_smem(int vmax);
@@ -90,6 +91,12 @@ struct ss_engine {
     cudaEvent_t ev_rounds = nullptr, ev_env = nullptr;
     bool env_in_flight = false;
     int overlap_option = 1;
+    // SURVEY 8 f3 (limitedLifespan / procreate; serial path, MT19937 mode): see ss_life.cuh
+    LifeWorld lw{};
+    bool have_life = false;
+    uint32_t slot_capacity = 0;                 // allocation of agents / order / wealth / sortkeys (>= n_slots; births need room)
+    int32_t n_events = 0;                       // events of the last ss_step call
+    int life_slack = -1;                        // option "life_capacity_slack" (tests): room for births instead of the default
     int grow_ctas_per_sm = 2;                   // ... as a few CTAs per SM that fit beside the conflict-graph CTAs
     // row strips (one engine per GPU): this engine holds the lattice rows [x0, x0 + rows)
     int strip_rank = 0, strip_world = 1, x0 = 0, rows = 0;
@@ -168,6 +175,15 @@ static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32
     if (cfg->rule_pollution && cfg->diffusion_rate < 1) return set_err(e, SS_ERR_ARG, "diffusion_rate must be >= 1");
     if (cfg->rule_seasons && cfg->season_period < 1) return set_err(e, SS_ERR_ARG, "season period must be >= 1");
     if (cfg->rng_mode != SS_RNG_MT19937 && cfg->rng_mode != SS_RNG_KEYED) return set_err(e, SS_ERR_ARG, "bad rng_mode");
+    if (cfg->rule_limited_lifespan || cfg->rule_procreate) {
+        if (cfg->rng_mode != SS_RNG_MT19937)
+            return set_err(e, SS_ERR_UNSUPPORTED, "limitedLifespan / procreate run in the MT19937-exact mode (births change the id range the keyed order is sized by)");
+        if (!cfg->rule_move_eat || cfg->rule_utilicalc)
+            return set_err(e, SS_ERR_UNSUPPORTED, "limitedLifespan / procreate are built with rule M (moveEat); with utilicalc the reference needs spice");
+        if (world > 1) return set_err(e, SS_ERR_UNSUPPORTED, "limitedLifespan / procreate: one GPU (serial order)");
+        if (cfg->tags_length < 0 || cfg->tags_length > 30) return set_err(e, SS_ERR_ARG, "tags_length out of range [0,30]");
+        if (cfg->foresight_hi < cfg->foresight_lo) return set_err(e, SS_ERR_ARG, "foresight range");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return set_err(e, SS_ERR_CUDA, "no CUDA device: the engine has no CPU fallback");
@@ -244,6 +260,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.pendmap);
     cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->w.outliers); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
     dr_free(e);
+    cudaFree(e->lw.rec); cudaFree(e->lw.id_increment); cudaFree(e->lw.events); cudaFree(e->lw.n_events); cudaFree(e->lw.status);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     cudaFree(e->h_dev_count);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -261,6 +278,8 @@ static int choose_path(ss_engine* e);
 static int dr_alloc(ss_engine* e);
 static int dr_tidy(ss_engine* e);
 static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, double* d_f64, int* d_chk);
+static int life_grow(ss_engine* e, uint32_t cap);
+static int life_after_launch(ss_engine* e, int* steps);
 
 // the cell arrays are in place on the device: derive what the kernels keep beside them
 static int finish_cells(ss_engine* e) {
@@ -452,13 +471,35 @@ static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, dou
     const uint32_t phase = (uint32_t)(e->iteration & 1);
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.wealth); cudaFree(e->w.sortkeys);
     e->w.agents = nullptr; e->w.order = nullptr; e->w.wealth = nullptr; e->w.sortkeys = nullptr;
-    const int P = next_pow2((int)ns);
-    CK(cudaMalloc(&e->w.agents, sizeof(AgentRec) * ns));
-    CK(cudaMalloc(&e->w.order, sizeof(int32_t) * ns));
+    // births take new ids: room for them up front, enlarged between launches when a run needs more
+    const bool life = e->cfg.rule_limited_lifespan || e->cfg.rule_procreate;
+    const uint32_t cap = life ? ns + (e->life_slack >= 0 ? (uint32_t)e->life_slack : std::max<uint32_t>(65536u, 16u * ns)) : ns;
+    e->slot_capacity = cap;
+    e->have_life = false;
+    const int P = next_pow2((int)cap);
+    CK(cudaMalloc(&e->w.agents, sizeof(AgentRec) * cap));
+    CK(cudaMalloc(&e->w.order, sizeof(int32_t) * cap));
     CK(cudaMalloc(&e->w.wealth, sizeof(double) * P));
     CK(cudaMalloc(&e->w.sortkeys, sizeof(unsigned long long) * P));
+    if (life) {
+        cudaFree(e->lw.rec); e->lw.rec = nullptr;
+        CK(cudaMalloc(&e->lw.rec, sizeof(LifeRec) * cap));
+        CK(cudaMemsetAsync(e->lw.rec, 0, sizeof(LifeRec) * cap, e->stream));
+        e->lw.capacity = (int32_t)cap;
+        if (!e->lw.id_increment) {
+            e->lw.ev_cap = 1 << 20;
+            CK(cudaMalloc(&e->lw.id_increment, sizeof(int32_t)));
+            CK(cudaMalloc(&e->lw.n_events, sizeof(int32_t)));
+            CK(cudaMalloc(&e->lw.status, 2 * sizeof(int32_t)));
+            CK(cudaMalloc(&e->lw.events, sizeof(int32_t) * 4 * (size_t)e->lw.ev_cap));
+        }
+        CK(cudaMemsetAsync(e->lw.n_events, 0, sizeof(int32_t), e->stream));
+        CK(cudaMemsetAsync(e->lw.status, 0, 2 * sizeof(int32_t), e->stream));
+        CK(cudaMemcpyAsync(e->lw.id_increment, &max_id, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        e->n_events = 0;
+    }
     {
-        CK(cudaMemsetAsync(e->w.agents, 0, sizeof(AgentRec) * ns, e->stream));
+        CK(cudaMemsetAsync(e->w.agents, 0, sizeof(AgentRec) * cap, e->stream));
         CK(cudaMemsetAsync(e->w.occw, 0, sizeof(uint32_t) * e->cells, e->stream));
         CK(cudaMemsetAsync(e->d_flags, 0, sizeof(int), e->stream));
         CK(ss_launch_build_agents(e->w, n, phase, d_i32, d_i32 + nn, d_i32 + 2 * nn, d_i32 + 3 * nn, d_i32 + 4 * nn, d_f64,
@@ -482,6 +523,83 @@ static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, dou
     e->have_agents = true;
     e->stepped = false;
     return choose_path(e);
+}
+
+// Agent.age / maxAge / sex / fertility / sugarEndowment / tags / alive (agent.py:134-151, 204-206) of the n agents
+// of the last ss_upload_agents, same order; id_increment = Environment.idIncrement (environment.py:202-204)
+extern "C" int ss_upload_agents_life(ss_engine* e, int32_t n, int32_t id_increment, const int32_t* age, const int32_t* max_age,
+                                     const int32_t* sex, const int32_t* fert_lo, const int32_t* fert_hi, const double* endowment,
+                                     const int32_t* tags, const int32_t* alive) {
+    if (!e || n < 0 || (n > 0 && (!age || !max_age || !sex || !fert_lo || !fert_hi || !endowment || !tags)))
+        return set_err(e, SS_ERR_ARG, "null argument");
+    if (!(e->cfg.rule_limited_lifespan || e->cfg.rule_procreate))
+        return set_err(e, SS_ERR_STATE, "the engine was created without limitedLifespan / procreate");
+    if (!e->have_agents || n != e->n_uploaded) return set_err(e, SS_ERR_STATE, "ss_upload_agents_life: n differs from the uploaded agents");
+    if (id_increment < (int32_t)e->w.n_slots && n > 0) return set_err(e, SS_ERR_ARG, "id_increment below the largest id");
+    CK(cudaSetDevice(e->device));
+    std::vector<int32_t> order((size_t)std::max(n, 1));
+    if (n) CK(cudaMemcpy(order.data(), e->w.order, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    if ((uint32_t)id_increment > e->slot_capacity) {
+        const int rc = life_grow(e, (uint32_t)id_increment + (e->life_slack >= 0 ? (uint32_t)e->life_slack : std::max<uint32_t>(65536u, 16u * (uint32_t)n)));
+        if (rc) return rc;
+    }
+    std::vector<LifeRec> recs(e->slot_capacity);
+    memset(recs.data(), 0, sizeof(LifeRec) * recs.size());
+    for (int i = 0; i < n; i++) {
+        LifeRec& r = recs[(size_t)order[i]];
+        r.age = age[i]; r.max_age = max_age[i]; r.sex = sex[i]; r.fert_lo = fert_lo[i]; r.fert_hi = fert_hi[i];
+        r.tags = tags[i]; r.living = alive ? (alive[i] != 0) : 1; r.endow = endowment[i];
+    }
+    CK(cudaMemcpyAsync(e->lw.rec, recs.data(), sizeof(LifeRec) * recs.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->lw.id_increment, &id_increment, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_life = true;
+    return SS_OK;
+}
+
+// ... the same columns of the agents in View.agents order (ss_agent_count entries; an agent that reached maxAge is still in
+// the list with alive = 0 for one step), and Environment.idIncrement
+extern "C" int ss_download_agents_life(ss_engine* e, int32_t* age, int32_t* max_age, int32_t* sex, int32_t* fert_lo, int32_t* fert_hi,
+                                       double* endowment, int32_t* tags, int32_t* alive, int32_t* id_increment) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->have_life) return set_err(e, SS_ERR_STATE, "no life columns uploaded");
+    CK(cudaSetDevice(e->device));
+    int32_t cnt = 0, idinc = 0;
+    CK(cudaMemcpy(&cnt, e->w.n_order, sizeof cnt, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&idinc, e->lw.id_increment, sizeof idinc, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> order((size_t)std::max(cnt, 1));
+    std::vector<LifeRec> recs((size_t)std::max(idinc, 1));
+    if (cnt) CK(cudaMemcpy(order.data(), e->w.order, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    if (idinc) CK(cudaMemcpy(recs.data(), e->lw.rec, sizeof(LifeRec) * (size_t)idinc, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; i++) {
+        const LifeRec& r = recs[(size_t)order[i]];
+        if (age) age[i] = r.age;
+        if (max_age) max_age[i] = r.max_age;
+        if (sex) sex[i] = r.sex;
+        if (fert_lo) fert_lo[i] = r.fert_lo;
+        if (fert_hi) fert_hi[i] = r.fert_hi;
+        if (endowment) endowment[i] = r.endow;
+        if (tags) tags[i] = r.tags;
+        if (alive) alive[i] = r.living;
+    }
+    if (id_increment) *id_increment = idinc;
+    return SS_OK;
+}
+
+// events of the last ss_step call in execution order, 4 ints each: kind | step << 8, a, b, c -- kind 1: agent a mated with
+// agent b and created agent c (sugarscape.py:551); 2: a died of starvation; 3: a died of old age (sugarscape.py:597-600)
+extern "C" int ss_event_count(ss_engine* e, int32_t* count) {
+    if (!e || !count) return set_err(e, SS_ERR_ARG, "null argument");
+    *count = e->have_life ? e->n_events : 0;
+    return SS_OK;
+}
+extern "C" int ss_get_events(ss_engine* e, int32_t max_events, int32_t* out) {
+    if (!e || (max_events > 0 && !out)) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->have_life) return SS_OK;
+    CK(cudaSetDevice(e->device));
+    const int32_t k = std::min(max_events, e->n_events);
+    if (k > 0) CK(cudaMemcpy(out, e->lw.events, sizeof(int32_t) * 4 * (size_t)k, cudaMemcpyDeviceToHost));
+    return SS_OK;
 }
 
 extern "C" int ss_set_rng_mt19937(ss_engine* e, const uint32_t state[624], int32_t index) {
@@ -895,6 +1013,57 @@ static int lattice_step(ss_engine* e, int stats_index) {
     return env_phase(e);
 }
 
+// enlarge the agent store, the list, the scratch arrays and the life records (births take new ids)
+static int life_grow(ss_engine* e, uint32_t cap) {
+    const uint32_t old = e->slot_capacity;
+    if (cap <= old) return SS_OK;
+    if (cap > (1u << 22)) return set_err(e, SS_ERR_UNSUPPORTED, "serial path limited to 4M agent ids");
+    AgentRec* agents = nullptr; int32_t* order = nullptr; double* wealth = nullptr; unsigned long long* sortkeys = nullptr; LifeRec* rec = nullptr;
+    const int P = next_pow2((int)cap);
+    CK(cudaMalloc(&agents, sizeof(AgentRec) * cap));
+    CK(cudaMalloc(&order, sizeof(int32_t) * cap));
+    CK(cudaMalloc(&wealth, sizeof(double) * P));
+    CK(cudaMalloc(&sortkeys, sizeof(unsigned long long) * P));
+    CK(cudaMalloc(&rec, sizeof(LifeRec) * cap));
+    CK(cudaMemsetAsync(agents, 0, sizeof(AgentRec) * cap, e->stream));
+    CK(cudaMemsetAsync(rec, 0, sizeof(LifeRec) * cap, e->stream));
+    CK(cudaMemcpyAsync(agents, e->w.agents, sizeof(AgentRec) * old, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(order, e->w.order, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(rec, e->lw.rec, sizeof(LifeRec) * old, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.wealth); cudaFree(e->w.sortkeys); cudaFree(e->lw.rec);
+    e->w.agents = agents; e->w.order = order; e->w.wealth = wealth; e->w.sortkeys = sortkeys; e->lw.rec = rec;
+    e->slot_capacity = cap; e->lw.capacity = (int32_t)cap;
+    return SS_OK;
+}
+// after a launch of the serial kernel with the life rules: how many of the *steps it completed (it stops before a step the
+// store or the event buffer may not hold -- then they are enlarged), the ids handed out so far, faults
+static int life_after_launch(ss_engine* e, int* steps) {
+    int32_t st[2] = {0, 0}, idinc = 0, nev = 0;
+    CK(cudaMemcpyAsync(st, e->lw.status, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&idinc, e->lw.id_increment, sizeof idinc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&nev, e->lw.n_events, sizeof nev, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->syncs++;
+    if (st[1]) return set_err(e, SS_ERR_STATE, "a birth found the agent store or the event buffer full (state unusable)");
+    e->w.n_slots = (uint32_t)std::max<int32_t>(idinc, 1);
+    e->n_events = nev;
+    if (st[0] < *steps) {           // stopped early: more room, the caller launches the rest
+        int32_t n_order = 0;
+        CK(cudaMemcpy(&n_order, e->w.n_order, sizeof n_order, cudaMemcpyDeviceToHost));
+        if ((long long)nev + 10ll * n_order + 64 > e->lw.ev_cap) {
+            if (st[0] == 0 && nev == 0) return set_err(e, SS_ERR_UNSUPPORTED, "population too large for the event buffer");
+            if (st[0] == 0) return set_err(e, SS_ERR_STATE, "event buffer full: call ss_step with fewer steps at a time and read ss_get_events in between");
+        }
+        const uint32_t need = (uint32_t)idinc + 8u * (uint32_t)n_order + 64u;       // what the kernel asks for before a step
+        const int rc = life_grow(e, e->life_slack >= 0 ? need + (uint32_t)e->life_slack
+                                                       : std::max<uint32_t>(2u * e->slot_capacity, need + 65536u));
+        if (rc) return rc;
+    }
+    *steps = st[0];
+    return SS_OK;
+}
+
 extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     if (!e) return set_err(e, SS_ERR_ARG, "null argument");
     if (nsteps < 0) return set_err(e, SS_ERR_ARG, "nsteps < 0");
@@ -907,18 +1076,34 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     if (rc) return rc;
     if (e->path != PATH_LATTICE) { rc = dr_tidy(e); if (rc) return rc; if (e->mirror == 2) e->mirror = 0; }
     CK(cudaEventRecord(e->evs, e->stream));
+    const bool life = e->cfg.rule_limited_lifespan || e->cfg.rule_procreate;
+    if (life) {
+        if (!e->have_life) return set_err(e, SS_ERR_STATE, "limitedLifespan / procreate: ss_upload_agents_life after ss_upload_agents");
+        CK(cudaMemsetAsync(e->lw.n_events, 0, sizeof(int32_t), e->stream));
+    }
+    const LifeWorld no_life{};
     if (e->path == PATH_SERIAL_FUSED) {
         KTimer t(e, KT_SERIAL);
-        CK(ss_launch_serial(e->w, e->iteration, e->env_time, nsteps, 1, 0, e->stream));
-        e->launches++;
-        e->iteration += nsteps; e->env_time += nsteps; e->steps += nsteps;
+        int done = 0;
+        while (done < nsteps) {
+            CK(ss_launch_serial(e->w, life ? e->lw : no_life, e->iteration, e->env_time, nsteps - done, 1, done, e->stream));
+            e->launches++;
+            int k = nsteps - done;
+            if (life) { rc = life_after_launch(e, &k); if (rc) { e->path = -1; return rc; } }
+            e->iteration += k; e->env_time += k; e->steps += k;
+            done += k;
+        }
     } else {
         for (int t = 0; t < nsteps; t++) {
             if (e->path == PATH_SERIAL_ENV) {
                 {
                     KTimer tm(e, KT_SERIAL);
-                    CK(ss_launch_serial(e->w, e->iteration, e->env_time, 1, 0, t, e->stream));
-                    e->launches++;
+                    for (int k = 0; k == 0;) {
+                        CK(ss_launch_serial(e->w, life ? e->lw : no_life, e->iteration, e->env_time, 1, 0, t, e->stream));
+                        e->launches++;
+                        k = 1;
+                        if (life) { rc = life_after_launch(e, &k); if (rc) { e->path = -1; return rc; } }
+                    }
                 }
                 rc = env_phase(e);
             } else {
@@ -1147,6 +1332,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "l2_persist") { e->l2_persist = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "overlap") { e->overlap_option = (int)value; return SS_OK; }
     if (k == "grow_ctas") { e->grow_ctas_per_sm = (int)value; return SS_OK; }
+    if (k == "life_capacity_slack") { e->life_slack = (int)value; return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     return set_err(e, SS_ERR_ARG, "unknown option: " + k);
 }

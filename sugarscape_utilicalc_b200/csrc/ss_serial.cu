@@ -14,6 +14,7 @@
 // sequential parts (Fisher-Yates shuffles on the RNG stream, the commit).  All warps join
 // for the order sort (keyed mode), the Gini sort and the environment phase.
 #include "ss_world.cuh"
+#include "ss_life.cuh"
 
 #define SERIAL_THREADS 256
 #define FULL 0xffffffffu
@@ -70,6 +71,8 @@ __device__ static uint32_t randbelow(SerialShared& sh, uint32_t n) {
     while (r >= n) r = rng_word(sh) >> (32 - k);
     return r;
 }
+// agent.py:224-229 setSugar: max(amount, 0 if limitedLifespan else .01)
+__device__ static inline double set_sugar_floor(double amount, double fl) { return amount > fl ? amount : fl; }
 // random.py:350 shuffle
 __device__ static void shuffle_i32(SerialShared& sh, int32_t* a, int n) {
     for (int i = n - 1; i >= 1; i--) {
@@ -140,7 +143,7 @@ __device__ static inline void pollute_site(const DevWorld& w, int64_t env_time, 
 }
 
 // agent.py:794-865 move(), no-spice branch
-__device__ static void warp_move(const DevWorld& w, SerialShared& sh, int s, int64_t env_time, int lane) {
+__device__ static void warp_move(const DevWorld& w, SerialShared& sh, int s, int64_t env_time, int lane, double fl) {
     const int n = w.n;
     AgentRec* rec = &w.agents[s];
     const int pos = (int)rec->pos, x = pos / n, y = pos % n, v = attr_vision(rec->attr);
@@ -169,7 +172,7 @@ __device__ static void warp_move(const DevWorld& w, SerialShared& sh, int s, int
     }
     if (lane == 0) {
         if (w.cfg.rule_pollution) pollute_site(w, env_time, best.c, (double)best.sg, 0.0);  // agent.py:825
-        rec->sugar = ss_set_sugar(ss_max0(rec->sugar + (double)best.sg));                  // agent.py:832
+        rec->sugar = set_sugar_floor(ss_max0(rec->sugar + (double)best.sg), fl);           // agent.py:832
         if (best.c != pos) {                                                                // agent.py:856-862
             uint32_t ow = w.occw[pos];
             w.occw[pos] = 0u;
@@ -251,6 +254,95 @@ __device__ static void warp_utilicalc(const DevWorld& w, SerialShared& sh, int s
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------
+// procreation (sugarscape.py:543-554; agent.py:653-679 mate, 681-696 findFreeLocationAround, 698-750 createChild,
+// 764-773 isFertile, 373-389 getNeighbourhood).  At most four neighbours: lane 0 does all of it, every draw on the MT19937 stream
+// in the reference's order.
+__device__ static inline bool life_fertile(const DevWorld& w, const LifeWorld& lw, int s) {
+    const LifeRec& r = lw.rec[s];
+    return r.fert_lo <= r.age && r.age <= r.fert_hi && w.agents[s].sugar >= r.endow;
+}
+__device__ static int life_free_around(const DevWorld& w, SerialShared& sh, int x, int y) {
+    const int n = w.n;
+    int loc[6], m = 0;
+    for (int i = x - 1; i <= x + 1; i++)                                  // no torus: isLocationValid (environment.py:165-167)
+        if (i >= 0 && i < n && w.occw[i * n + y] == 0u) loc[m++] = i * n + y;
+    for (int j = y - 1; j <= y + 1; j++)
+        if (j >= 0 && j < n && w.occw[x * n + j] == 0u) loc[m++] = x * n + j;
+    if (!m) return -1;
+    return loc[randbelow(sh, (uint32_t)m)];                               // random.randint(0, length - 1)
+}
+__device__ static inline double life_random(SerialShared& sh) {           // random.random(): 53 bits of two words
+    const uint32_t a = rng_word(sh) >> 5, b = rng_word(sh) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+__device__ static inline void life_event(const LifeWorld& lw, int step, int kind, int a, int b, int c) {
+    const int at = *lw.n_events;
+    if (at >= lw.ev_cap) { lw.status[1]++; return; }
+    int32_t* e = lw.events + 4 * (size_t)at;
+    e[0] = kind | (step << 8); e[1] = a; e[2] = b; e[3] = c;
+    *lw.n_events = at + 1;
+}
+// returns the new length of the list (the child joins its end and is met by the running loop in this very step)
+__device__ static int life_procreate(const DevWorld& w, const LifeWorld& lw, SerialShared& sh, int s, int n_order, int step, double fl) {
+    const int n = w.n;
+    const int pos = (int)w.agents[s].pos, x = pos / n, y = pos % n;
+    int32_t nb[4];
+    int m = 0;
+    for (int xx = x - 1; xx <= x + 1; xx++) {                             // getNeighbourhood: torus, x-line then y-line
+        if (xx == x) continue;
+        const uint32_t ow = w.occw[ss_wrap(xx, n) * n + y];
+        if (ow != 0u) nb[m++] = (int32_t)occ_slot(ow);
+    }
+    for (int yy = y - 1; yy <= y + 1; yy++) {
+        if (yy == y) continue;
+        const uint32_t ow = w.occw[x * n + ss_wrap(yy, n)];
+        if (ow != 0u) nb[m++] = (int32_t)occ_slot(ow);
+    }
+    shuffle_i32(sh, nb, m);
+    for (int k = 0; k < m; k++) {
+        const int b = nb[k];
+        if (lw.rec[b].sex == lw.rec[s].sex || !life_fertile(w, lw, b)) continue;
+        int loc = life_free_around(w, sh, x, y);
+        if (loc < 0) { const int pb = (int)w.agents[b].pos; loc = life_free_around(w, sh, pb / n, pb % n); }
+        if (loc < 0 || !life_fertile(w, lw, s)) continue;
+        // createChild: genitors = [self, partner]
+        const int g[2] = {s, b};
+        const int metab = attr_metab(w.agents[g[randbelow(sh, 2u)]].attr);
+        (void)randbelow(sh, 2u);                                          // spiceMetabolism
+        const int vision = attr_vision(w.agents[g[randbelow(sh, 2u)]].attr);
+        const double endow = 0.5 * (lw.rec[s].endow + lw.rec[b].endow);
+        w.agents[s].sugar = set_sugar_floor(ss_max0(w.agents[s].sugar - 0.5 * lw.rec[s].endow), fl);
+        w.agents[b].sugar = set_sugar_floor(ss_max0(w.agents[b].sugar - 0.5 * lw.rec[b].endow), fl);
+        const int max_age = lw.rec[g[randbelow(sh, 2u)]].max_age;
+        const int sex = (int)randbelow(sh, 2u);
+        const int fg = g[randbelow(sh, 2u)];
+        int32_t mask = 1, tags = 0;
+        for (int t = 0; t < w.cfg.tags_length; t++) {                     // agent.py:727-737
+            const int32_t t1 = lw.rec[s].tags & mask, t2 = lw.rec[b].tags & mask;
+            if (t1 == t2 || life_random(sh) < 0.5) tags |= t1; else tags |= t2;
+            mask <<= 1;
+        }
+        const int c = *lw.id_increment;                                   // slot = id - 1 (Environment.getNewId)
+        (void)randbelow(sh, (uint32_t)(w.cfg.foresight_hi - w.cfg.foresight_lo + 1));      // Agent.__init__: generateForesight
+        if (c >= lw.capacity) { lw.status[1]++; continue; }               // (the launch stops before a step that could get here)
+        *lw.id_increment = c + 1;
+        AgentRec a;
+        a.sugar = set_sugar_floor(endow, fl);                             // setInitialSugarEndowment
+        a.pos = (uint32_t)loc; a.attr = attr_pack(vision, metab, true);
+        a.status = 0u; a.pred = 0u; a.pred_step = 0u; a.turn = 0u;
+        w.agents[c] = a;
+        LifeRec r;
+        r.age = 0; r.max_age = max_age; r.sex = sex; r.fert_lo = lw.rec[fg].fert_lo; r.fert_hi = lw.rec[fg].fert_hi;
+        r.tags = tags; r.living = 1; r.pad = 0; r.endow = endow;
+        lw.rec[c] = r;
+        w.occw[loc] = occ_pack((uint32_t)c, vision, 0u);
+        w.order[n_order++] = c;                                           // sugarscape.py:550
+        life_event(lw, step, 1, s + 1, b + 1, c + 1);
+    }
+    return n_order;
+}
+
 // ---------------------------------------------------------------- environment phase (CTA) ----
 __device__ static inline void grow_cell(const DevWorld& w, int c, double alpha) {      // environment.py:133-139
     double v = w.sugar[c] + alpha;
@@ -301,16 +393,23 @@ __device__ static void cta_environment(const DevWorld& w, int64_t iteration) {
 
 // ------------------------------------------------------------------------------ kernel ----
 __global__ void __launch_bounds__(SERIAL_THREADS, 1)
-ss_serial_kernel(DevWorld w, int64_t iteration0, int64_t env_time0, int nsteps, int fused_env, int stats_base) {
+ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0, int nsteps, int fused_env, int stats_base) {
     __shared__ SerialShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 624; i += blockDim.x) sh.mt[i] = w.mt[i];
     if (tid == 0) { sh.mti = *w.mti; sh.rng_mode = w.cfg.rng_mode; }
     __syncthreads();
     const OrderKey dummy = ss_order_key(0, w.half);
-    for (int step = 0; step < nsteps; step++) {
+    const bool life = lw.rec != nullptr;
+    const double fl = w.cfg.rule_limited_lifespan ? 0.0 : 0.01;           // agent.py:226
+    int step = 0;
+    for (; step < nsteps; step++) {
         const int64_t iteration = iteration0 + step, env_time = env_time0 + step;
         int n_order = *w.n_order;
+        // births: a turn creates at most four children and logs at most five events; the launch stops before a step the
+        // agent store or the event buffer may not hold (the host enlarges them and continues)
+        if (life && ((long long)*lw.id_increment + 8ll * n_order + 64 > lw.capacity ||
+                     (long long)*lw.n_events + 10ll * n_order + 64 > lw.ev_cap)) break;
         // ---- execution order, sugarscape.py:517 ----
         if (w.cfg.rng_mode == SS_RNG_MT19937) {
             if (tid == 0) shuffle_i32(sh, w.order, n_order);
@@ -346,22 +445,37 @@ ss_serial_kernel(DevWorld w, int64_t iteration0, int64_t env_time0, int nsteps, 
                     sh.j = 0;
                 }
                 __syncwarp();
-                if (w.cfg.rule_move_eat) warp_move(w, sh, s, env_time, lane);
+                if (w.cfg.rule_move_eat) warp_move(w, sh, s, env_time, lane, fl);
                 if (w.cfg.rule_utilicalc) warp_utilicalc(w, sh, s, lane);
+                if (life && w.cfg.rule_procreate) {                                  // sugarscape.py:543-554
+                    if (lane == 0 && life_fertile(w, lw, s)) n_order = life_procreate(w, lw, sh, s, n_order, stats_base + step, fl);
+                    n_order = __shfl_sync(FULL, n_order, 0);
+                }
                 int died = 0;
                 if (lane == 0) {
                     AgentRec* rec = &w.agents[s];
                     const int metab = attr_metab(rec->attr);
                     if (w.cfg.rule_pollution && rec->sugar > 0.0)                     // sugarscape.py:566-567
                         pollute_site(w, env_time, (int)rec->pos, 0.0, (double)metab);
-                    rec->sugar = ss_set_sugar(ss_max0(rec->sugar - (double)metab));  // sugarscape.py:569
+                    rec->sugar = set_sugar_floor(ss_max0(rec->sugar - (double)metab), fl);   // sugarscape.py:569
                     sh.sum_m += (double)metab;
                     sh.sum_v += (double)attr_vision(rec->attr);
                     w.wealth[sh.nw++] = rec->sugar;
                     sh.acted++;
-                    if (w.cfg.rule_can_starve && rec->sugar <= 0.1) {                 // sugarscape.py:306-309
+                    bool living = life ? lw.rec[s].living != 0 : true;              // Agent.alive (0: reached maxAge last step)
+                    if (w.cfg.rule_can_starve && rec->sugar <= 0.1) living = false;   // sugarscape.py:306-309
+                    if (living && w.cfg.rule_limited_lifespan) {                      // sugarscape.py:588-591, agent.py:636-639
+                        LifeRec& lr = lw.rec[s];
+                        lr.age++;
+                        lr.living = lr.max_age > lr.age ? 1 : 0;                      // (it stays for one more turn)
+                    }
+                    if (!living) {                                                    // sugarscape.py:593-601
                         rec->attr &= ~ATTR_ALIVE;
                         w.occw[rec->pos] = 0u;                                        // sugarscape.py:595
+                        if (life) {
+                            lw.rec[s].living = 0;
+                            life_event(lw, stats_base + step, w.cfg.rule_limited_lifespan && lw.rec[s].age > lw.rec[s].max_age ? 3 : 2, s + 1, 0, 0);
+                        }
                         sh.deaths++;
                         died = 1;
                     } else {
@@ -406,11 +520,12 @@ ss_serial_kernel(DevWorld w, int64_t iteration0, int64_t env_time0, int nsteps, 
     }
     for (int i = tid; i < 624; i += blockDim.x) w.mt[i] = sh.mt[i];
     if (tid == 0) *w.mti = sh.mti;
+    if (life && tid == 0) lw.status[0] = step;
 }
 
-extern "C" cudaError_t ss_launch_serial(const DevWorld& w, int64_t iteration, int64_t env_time, int nsteps,
+extern "C" cudaError_t ss_launch_serial(const DevWorld& w, const LifeWorld& lw, int64_t iteration, int64_t env_time, int nsteps,
                                         int fused_env, int stats_base, cudaStream_t stream) {
-    ss_serial_kernel<<<1, SERIAL_THREADS, 0, stream>>>(w, iteration, env_time, nsteps, fused_env, stats_base);
+    ss_serial_kernel<<<1, SERIAL_THREADS, 0, stream>>>(w, lw, iteration, env_time, nsteps, fused_env, stats_base);
     return cudaGetLastError();
 }
 

@@ -176,6 +176,43 @@ class Engine:
                                                  _ptr(sugar)), "ss_download_agents")
         return dict(id=id, x=x, y=y, vision=vision, metab=metab, sugar=sugar)
 
+    # -- limitedLifespan + procreate ---------------------------------------------
+    LIFE_COLUMNS = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
+
+    def upload_agents_life(self, id_increment, age, max_age, sex, fert_lo, fert_hi, endowment, tags, alive=None):
+        """Agent.age / maxAge / sex / fertility[0] / fertility[1] / sugarEndowment / tags / alive of the agents of the last
+        upload_agents (same order) and Environment.idIncrement -- required before step() when rules.limitedLifespan or
+        rules.procreate is on (agent.py:134-151, 204-206; environment.py:202-204)."""
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        age, max_age, sex, fert_lo, fert_hi, tags, alive = map(i32, (age, max_age, sex, fert_lo, fert_hi, tags, alive))
+        endowment = np.ascontiguousarray(endowment, dtype=np.float64)
+        if not (len(age) == len(max_age) == len(sex) == len(fert_lo) == len(fert_hi) == len(tags) == len(endowment)):
+            raise ValueError("life columns must have equal length")
+        self._check(self._lib.ss_upload_agents_life(self._h, len(age), int(id_increment), _ptr(age), _ptr(max_age), _ptr(sex),
+                                                    _ptr(fert_lo), _ptr(fert_hi), _ptr(endowment), _ptr(tags), _ptr(alive)),
+                    "ss_upload_agents_life")
+
+    def download_agents_life(self):
+        """The same columns in View.agents order (an agent that reached maxAge is still listed, alive = 0, for one more
+        step -- as in the reference), plus `id_increment`."""
+        k = self.agent_count()
+        cols = {c: np.empty(k, dtype=np.float64 if c == "endowment" else np.int32) for c in self.LIFE_COLUMNS}
+        idinc = C.c_int32()
+        self._check(self._lib.ss_download_agents_life(self._h, *[_ptr(cols[c]) for c in self.LIFE_COLUMNS], C.byref(idinc)),
+                    "ss_download_agents_life")
+        cols["id_increment"] = idinc.value
+        return cols
+
+    def events(self):
+        """(k, 4) int32 event records of the last step() call in execution order: kind | step << 8, a, b, c (kind 1: a
+        mated with b and created c; 2: a died of starvation; 3: a died of old age); `outputs.event_lines` formats them."""
+        cnt = C.c_int32()
+        self._check(self._lib.ss_event_count(self._h, C.byref(cnt)), "ss_event_count")
+        out = np.zeros((cnt.value, 4), dtype=np.int32)
+        if cnt.value:
+            self._check(self._lib.ss_get_events(self._h, cnt.value, _ptr(out)), "ss_get_events")
+        return out
+
     # -- instrumentation -------------------------------------------------------------------
     def counters(self):
         out = np.zeros(6, dtype=np.int64)

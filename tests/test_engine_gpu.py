@@ -27,6 +27,64 @@ def test_mt_exact_presets(name):
     w.close()
 
 
+@pytest.mark.parametrize("name", common.LIFE_CASES)
+def test_lifespan_and_procreation_match_reference_golden(name):
+    """SURVEY 8 f3 on the GPU (ss_serial_kernel, MT19937-exact): examples/evolution_metabolism (= examples/tag_flipping) as
+    shipped and procreation without the lifespan rule, against the goldens recorded from the unmodified reference -- cells,
+    agents in list order (newborns act in the step they are born in, an agent that reached maxAge stays for one more turn),
+    age / sex / fertility / endowment / tags, Environment.idIncrement, the event lines, the statistics and the final
+    MT19937 state."""
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "engine")
+    assert w.counters()["path"] == 0
+    assert common.run_against_golden(g, w, exact_gini=True) == g["steps"]
+    w.close()
+
+
+def test_lifespan_and_procreation_single_steps_and_store_growth():
+    """... stepping one step at a time gives the same run, and so does a population that outgrows the room the agent store
+    was allocated with (the kernel stops before such a step, the host enlarges the store and continues)."""
+    g = common.load_golden("f3_evolution_metabolism_mt")
+    w = common.world_from_golden(g, "engine")
+    common.run_against_golden(g, w, exact_gini=True, chunk=1, max_steps=60)
+    w.close()
+    cfg = config_from_settings(g["settings"], rng_mode="mt")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    init = common.golden_init(g)
+    for w in (e, o):
+        common.init_world(w, init, "mt", g["init_mt"], int(g["init_mt_index"]))
+    e.set_option("life_capacity_slack", 16)                 # (test hook: next to no room for births)
+    common.init_world(e, init, "mt", g["init_mt"], int(g["init_mt_index"]))
+    for _ in range(4):
+        se, so = e.step(25), o.step(25)
+        for f in ("population", "metabolism_mean", "vision_mean", "gini", "acted", "deaths"):
+            assert np.array_equal(se[f], so[f]), f
+        assert np.array_equal(e.events(), o.events())
+        ge, go = e.download_agents(), o.download_agents()
+        for k in ("id", "x", "y", "vision", "metab", "sugar"):
+            assert np.array_equal(ge[k], go[k]), k
+        le, lo = e.download_agents_life(), o.download_agents_life()
+        for k in common.LIFE_COLUMNS + ("id_increment",):
+            assert np.array_equal(le[k], lo[k]), k
+    e.close()
+    o.close()
+
+
+def test_life_rules_need_their_columns_and_the_mt_mode():
+    from sugarscape_utilicalc_b200.engine import EngineError
+    g = common.load_golden("f3_evolution_metabolism_mt")
+    cfg = config_from_settings(g["settings"], rng_mode="mt")
+    e = common.engine_world(cfg)
+    init = dict(common.golden_init(g), life=None)
+    common.init_world(e, init, "mt", g["init_mt"], int(g["init_mt_index"]))
+    with pytest.raises(EngineError):
+        e.step(1)                                           # ss_upload_agents_life first
+    e.close()
+    cfg.rng_mode = 1
+    with pytest.raises(EngineError):
+        common.engine_world(cfg)
+
+
 @pytest.mark.parametrize("name", common.OUTPUT_CASES)
 def test_on_disk_outputs_match_reference_golden(name, tmp_path):
     """SURVEY 8 f1 on the GPU: event log in execution order, plateau exit, data.txt and createLogFile text."""
