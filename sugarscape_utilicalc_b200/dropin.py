@@ -12,6 +12,7 @@ The state lives in HBM between calls; `sync_back()` is the read the GUI needs be
 `rng="mt"` continues the reference's global `random` stream bit-exactly (and writes the MT19937
 state back on `sync_back`); `rng="keyed"` selects the parallel path.
 """
+import copy
 import random as _pyrandom
 
 import numpy as np
@@ -33,7 +34,16 @@ def _snapshot_view(view):
         id=np.array([a.id for a in ags], dtype=np.int32), x=np.array([a.x for a in ags], dtype=np.int32),
         y=np.array([a.y for a in ags], dtype=np.int32), vision=np.array([a.vision for a in ags], dtype=np.int32),
         metab=np.array([a.sugarMetabolism for a in ags], dtype=np.int32),
-        sugar_agent=np.array([a.sugar for a in ags], dtype=np.float64))
+        sugar_agent=np.array([a.sugar for a in ags], dtype=np.float64),
+        # what the lifespan / procreation rules read (agent.py:134-151, 204-206)
+        life=dict(age=np.array([a.age for a in ags], dtype=np.int32), max_age=np.array([a.maxAge for a in ags], dtype=np.int32),
+                  sex=np.array([a.sex for a in ags], dtype=np.int32),
+                  fert_lo=np.array([a.fertility[0] for a in ags], dtype=np.int32),
+                  fert_hi=np.array([a.fertility[1] for a in ags], dtype=np.int32),
+                  endowment=np.array([a.sugarEndowment for a in ags], dtype=np.float64),
+                  tags=np.array([a.tags for a in ags], dtype=np.int32),
+                  alive=np.array([1 if a.alive else 0 for a in ags], dtype=np.int32)),
+        id_increment=int(env.idIncrement))
 
 
 class DropinHandle:
@@ -44,6 +54,7 @@ class DropinHandle:
         self.events, self.gui = events, gui
         self.keyed_seed = ss.seed if keyed_seed is None else keyed_seed
         self.list_ids = [a.id for a in view.agents]
+        self.life = bool(ss.rules["limitedLifespan"] or ss.rules["procreate"])
         self.n_slots = max(max(self.list_ids, default=1), int(world.n_slots()) if hasattr(world, "n_slots") else 1)
 
     def _order_before_step(self):
@@ -59,9 +70,12 @@ class DropinHandle:
         events in execution order (:598-600), iteration / env.time (:670-671), the GUI refresh calls (:665-675, with
         `gui=True`: the state is synced back first), the step-100 sample and the plateau rule (:676-686)."""
         v = self.view
-        order = self._order_before_step() if self.events else None
+        order = self._order_before_step() if self.events and not self.life else None
         st = self.world.step(1)[0]
-        if self.events:
+        if self.events and self.life:         # births and deaths in execution order, reported by the engine
+            for line in outputs.event_lines(self.world.events()):
+                v.appendToLog(line.strip(), indent="    ")
+        elif self.events:
             self.list_ids = [int(i) for i in self.world.download_agents()["id"]]
             for i in outputs.deaths_in_order(order, self.list_ids):
                 v.appendToLog("Agent " + str(i) + " died of starvation", indent="    ")
@@ -102,12 +116,29 @@ class DropinHandle:
                 c[0] = float(sugar[i, j])
                 c[4] = None
                 c[5] = float(poll[i, j])
+        lf = self.world.download_agents_life() if self.life else None
+        if lf is not None:
+            env.idIncrement = int(lf["id_increment"])
         alive = []
         for k in range(len(ags["id"])):
-            a = self.by_id[int(ags["id"][k])]
+            a = self.by_id.get(int(ags["id"][k]))
+            if a is None:                     # born on the device: an Agent object for the GUI (no constructor: it draws)
+                a = copy.copy(alive[0] if alive else next(iter(self.by_id.values())))
+                a.id = int(ags["id"][k])
+                a.sugarMetabolism, a.vision = int(ags["metab"][k]), int(ags["vision"][k])
+                a.tradeLog, a.sugarLog, a.spiceLog, a.loanLog, a.log = [], [], [], [], []
+                a.lent, a.borrowed, a.childIds, a.diseases = [], [], [], {}
+                self.by_id[a.id] = a
             a.x, a.y = int(ags["x"][k]), int(ags["y"][k])
             s = float(ags["sugar"][k])
             a.sugar = int(s) if s == int(s) else s
+            if lf is not None:
+                a.age, a.maxAge, a.sex = int(lf["age"][k]), int(lf["max_age"][k]), int(lf["sex"][k])
+                a.fertility = (int(lf["fert_lo"][k]), int(lf["fert_hi"][k]))
+                e = float(lf["endowment"][k])
+                a.sugarEndowment = a.sugarCostForMating = int(e) if e == int(e) and isinstance(a.sugarEndowment, int) else e
+                a.setTags((int(lf["tags"][k]), a.tagsLength))
+                a.alive = bool(lf["alive"][k])
             env.grid[a.x][a.y][4] = a
             alive.append(a)
         living = set(id(a) for a in alive)
@@ -139,6 +170,8 @@ def install(ss, view, rng="mt", keyed_seed=None, world_factory=None, events=True
     s = _snapshot_view(view)
     world.upload_cells(s["sugar"], s["cap"], s["pollution"])
     world.upload_agents(s["id"], s["x"], s["y"], s["vision"], s["metab"], s["sugar_agent"])
+    if cfg.rule_limited_lifespan or cfg.rule_procreate:
+        world.upload_agents_life(s["id_increment"], **s["life"])
     if rng == "mt":
         st = _pyrandom.getstate()[1]
         world.set_rng_mt19937(np.array(st[:624], dtype=np.uint32), int(st[624]))

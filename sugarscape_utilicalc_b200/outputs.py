@@ -187,6 +187,8 @@ class RunRecorder:
         self.gini_at_100 = 0
         self.data_file = data_file
         self.events = events
+        # with births the engine reports the step's events itself (mating lines, deaths) in execution order
+        self.life = bool(settings["rules"].get("limitedLifespan") or settings["rules"].get("procreate"))
         self.list_ids = list(int(i) for i in (world.download_agents()["id"] if list_ids is None else list_ids))
         self.n_slots = max(max(self.list_ids, default=1), int(world.n_slots()) if hasattr(world, "n_slots") else 1)
 
@@ -199,9 +201,11 @@ class RunRecorder:
 
     def step(self):
         """One timestep with the observable effects of sugarscape.py:575-619 and 670-682."""
-        order = self._order_before_step() if self.events else None
+        order = self._order_before_step() if self.events and not self.life else None
         st = self.world.step(1)[0]
-        if self.events:
+        if self.events and self.life:
+            self.log.extend(event_lines(self.world.events()))
+        elif self.events:
             self.list_ids = [int(i) for i in self.world.download_agents()["id"]]
             for i in deaths_in_order(order, self.list_ids):
                 self.log.append(death_event(i))

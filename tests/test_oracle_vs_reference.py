@@ -110,6 +110,73 @@ def test_dropin_install_glue_with_reference_view():
         assert np.array_equal(a[k], b[k]), k
 
 
+LIFE_KEYS = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
+
+
+def test_lifespan_and_procreation_oracle_vs_live_reference():
+    """examples/tag_flipping (limitedLifespan + procreate) step by step against the unmodified reference --
+    cells, agents in list order, the fields the two rules carry, Environment.idIncrement, the event lines, the MT19937
+    stream."""
+    import ref_harness as rh
+    from sugarscape_utilicalc_b200 import outputs
+    s = rh.load_settings("tag_flipping")
+    ref = rh.ReferenceRun(s)
+    s0 = ref.snapshot()
+    o = common.oracle_world(config_from_settings(s, rng_mode="mt"))
+    init = dict(sugar=s0["sugar"], cap=s0["cap"], pollution=s0["pollution"], id=s0["order"], x=s0["x"], y=s0["y"],
+                vision=s0["vision"], metab=s0["metab"], sugar_agent=s0["sugar_agent"], life={k: s0[k] for k in LIFE_KEYS},
+                id_increment=s0["id_increment"])
+    common.init_world(o, init, "mt", s0["mt"], s0["mt_index"])
+    log = []
+    for t in range(80):
+        ref.step()
+        st = o.step(1)
+        log += outputs.event_lines(o.events())
+        sn, ga, gl, gc = ref.snapshot(), o.download_agents(), o.download_agents_life(), o.download_cells()
+        assert np.array_equal(ga["id"], sn["order"]) and np.array_equal(ga["x"], sn["x"]) and np.array_equal(ga["y"], sn["y"]), t
+        assert np.array_equal(ga["sugar"], sn["sugar_agent"]) and np.array_equal(gc["occ"], sn["occ"]) and np.array_equal(gc["sugar"], sn["sugar"]), t
+        for k in LIFE_KEYS:
+            assert np.array_equal(gl[k], sn[k]), (t, k)
+        assert gl["id_increment"] == sn["id_increment"] and st["population"][0] == ref.view.population[-1] and st["gini"][0] == ref.view.gini[-1]
+        mt, idx = o.get_rng_mt19937()
+        assert idx == sn["mt_index"] and np.array_equal(mt, sn["mt"]), t
+    assert log == ref.view.log and len(log) > 100
+    o.close()
+
+
+def test_dropin_with_births_hands_a_working_view_back():
+    """`dropin.install` under limitedLifespan + procreate: the installed updateGame keeps View.log complete (mating lines and
+    deaths in execution order), sync_back gives the children Agent objects, and the reference's own loop continues from the
+    synced View exactly as its uninterrupted run does."""
+    import random
+    import ref_harness as rh
+    from sugarscape_utilicalc_b200 import dropin
+    s = rh.load_settings("evolution_metabolism")
+    ref = rh.ReferenceRun(s)
+    ref.run(30)
+    exp, exp_log, exp_stats = ref.snapshot(), list(ref.view.log), ref.stats()
+    run = rh.ReferenceRun(s)
+    h = dropin.install(run.ss, run.view, rng="mt", world_factory=common.oracle_world)
+    for _ in range(30):
+        run.view.updateGame()
+    h.sync_back()
+    got = run.snapshot()
+    for k in ("sugar", "occ", "order", "x", "y", "sugar_agent", "vision", "metab", "mt") + LIFE_KEYS:
+        assert np.array_equal(got[k], exp[k]), k
+    assert got["id_increment"] == exp["id_increment"] and run.view.log == exp_log and run.stats() == exp_stats
+    state = random.getstate()
+    run.view.updateGame = h.original_update
+    for _ in range(5):
+        run.step()
+    random.setstate(state)
+    for _ in range(5):
+        ref.step()
+    a, b = run.snapshot(), ref.snapshot()
+    for k in ("sugar", "occ", "order", "x", "y", "sugar_agent", "mt") + LIFE_KEYS:
+        assert np.array_equal(a[k], b[k]), k
+    assert run.view.log == ref.view.log
+
+
 def _moveeat_settings(rh):
     s = rh.load_settings(None)
     s["rules"]["moveEat"], s["rules"]["utilicalc"] = True, False
