@@ -126,6 +126,9 @@ typedef struct {
                                      reference indexes the "male" tuple with sex 0                          */
     int32_t foresight_lo, foresight_hi;               /* Environment.foresightRange, (0,0) without the rule:
                                      Agent.__init__ draws from it regardless (agent.py:165, 329-333)        */
+    int32_t group_tags[4];        /* `distributions`: the tags of each group (tags0, 2^tags_length - 1; sugarscape.py:104-105,
+                                     142-148) -- kept with limitedLifespan / procreate, where ss_init_world also
+                                     leaves the engine as after ss_upload_agents_life (age 0, maxAge, sex, fertility drawn) */
 } ss_init_params;
 
 /* Replaces: Environment.addSugarSite x n_sites (environment.py:114-126), setMaxCapacity, env.grow(maxCapacity),

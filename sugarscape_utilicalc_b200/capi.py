@@ -47,7 +47,7 @@ class SsInitParams(C.Structure):
         ("grow_to_capacity", C.c_int32), ("n_groups", C.c_int32), ("group_count", C.c_int32 * 4),
         ("max_metabolism", C.c_int32), ("max_vision", C.c_int32), ("endowment_min", C.c_int32), ("endowment_max", C.c_int32),
         ("age_min", C.c_int32), ("age_max", C.c_int32), ("childbearing", (C.c_int32 * 4) * 2),
-        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32),
+        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("group_tags", C.c_int32 * 4),
     ]
 
 

@@ -34,7 +34,7 @@ cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D, double max_capacity,
                                  int grow, int sm_count, cudaStream_t stream);
 cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, int32_t* rowfree, int32_t* superfree, int32_t* cols,
-                                  size_t stride, double* sugar, int32_t* result, cudaStream_t stream);
+                                  size_t stride, double* sugar, int32_t* life_cols, int32_t* result, cudaStream_t stream);
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
 cudaError_t ss_launch_validate_rows(int n, const int32_t* x, int x0, int rows, int* out, cudaStream_t s);
@@ -685,13 +685,30 @@ extern "C" int ss_init_world(ss_engine* e, const ss_init_params* p) {
     const int nsuper = (N + 30) / 32 + 1;
     CK(cudaMalloc(&d_scratch, sizeof(int32_t) * ((size_t)N + nsuper + 2)));
     int32_t* d_result = d_scratch + N + nsuper;
-    CK(ss_launch_init_agents(e->w, p, d_scratch, d_scratch + N, d_i32, nn, d_f64, d_result, e->stream));
+    // with the lifespan / procreation rules the drawn maxAge, sex and fertility (and the group's tags) are kept
+    const bool life = e->cfg.rule_limited_lifespan || e->cfg.rule_procreate;
+    int32_t* d_life = nullptr;
+    struct LifeStaging { int32_t*& p; ~LifeStaging() { cudaFree(p); } } life_staging{d_life};
+    if (life) CK(cudaMalloc(&d_life, sizeof(int32_t) * 5 * nn));
+    CK(ss_launch_init_agents(e->w, p, d_scratch, d_scratch + N, d_i32, nn, d_f64, d_life, d_result, e->stream));
     int32_t result[2] = {0, 0};
     CK(cudaMemcpyAsync(result, d_result, sizeof result, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     int rc = finish_cells(e);
     if (rc) return rc;
-    return finish_agents(e, result[0], d_i32, nn, d_f64, d_chk);
+    std::vector<int32_t> hl;
+    std::vector<double> hs;
+    if (life) {             // (before finish_agents frees nothing of these, but keep the order simple: copy out first)
+        hl.resize(5 * nn); hs.resize(nn);
+        CK(cudaMemcpy(hl.data(), d_life, sizeof(int32_t) * 5 * nn, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hs.data(), d_f64, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+    }
+    rc = finish_agents(e, result[0], d_i32, nn, d_f64, d_chk);
+    if (rc || !life) return rc;
+    const int32_t n = result[0];
+    std::vector<int32_t> age((size_t)std::max(n, 1), 0);                               // Agent.setAge: age = 0 (agent.py:236-238)
+    return ss_upload_agents_life(e, n, result[1], age.data(), hl.data(), hl.data() + nn, hl.data() + 2 * nn, hl.data() + 3 * nn,
+                                 hs.data(), hl.data() + 4 * nn, nullptr);              // endowment = the drawn initial sugar
 }
 
 extern "C" int ss_set_rng_keyed(ss_engine* e, uint64_t seed) {

@@ -571,6 +571,7 @@ struct InitAgents {
     int max_metabolism, max_vision, endow_min, endow_max, age_min, age_max;
     int childbearing[2][4];
     int foresight_lo, foresight_hi;
+    int group_tags[4];
 };
 // position of the k-th unit (0-based) in the prefix sums of 32 lane values; returns the lane and leaves k relative to it
 __device__ static inline int warp_select(int v, int lane, long long& k, long long& total_out) {
@@ -590,7 +591,8 @@ __device__ static inline int warp_select(int v, int lane, long long& k, long lon
 }
 __global__ void __launch_bounds__(32)
 ss_init_agents_kernel(DevWorld w, InitAgents ip, int32_t* rowfree, int32_t* superfree, int32_t* id_out, int32_t* x_out,
-                      int32_t* y_out, int32_t* vision_out, int32_t* metab_out, double* sugar_out, int32_t* result) {
+                      int32_t* y_out, int32_t* vision_out, int32_t* metab_out, double* sugar_out, int32_t* life_out, size_t life_stride,
+                      int32_t* result) {
     __shared__ SerialShared sh;
     const int lane = threadIdx.x, n = w.n, n1 = n - 1, nsuper = (n1 + 31) / 32;
     for (int i = lane; i < 624; i += 32) sh.mt[i] = w.mt[i];
@@ -632,12 +634,16 @@ ss_init_agents_kernel(DevWorld w, InitAgents ip, int32_t* rowfree, int32_t* supe
                 const int metab = 1 + (int)randbelow(sh, (uint32_t)ip.max_metabolism);            // sugarscape.py:250
                 const int endow = ip.endow_min + (int)randbelow(sh, (uint32_t)(ip.endow_max - ip.endow_min + 1));
                 const int vision = 1 + (int)randbelow(sh, (uint32_t)ip.max_vision);               // :256
-                (void)randbelow(sh, (uint32_t)(ip.age_max - ip.age_min + 1));                     // :257
+                const int max_age = ip.age_min + (int)randbelow(sh, (uint32_t)(ip.age_max - ip.age_min + 1));     // :257 setAge
                 const int sex = (int)randbelow(sh, 2u);                                           // :258
-                (void)randbelow(sh, (uint32_t)(ip.childbearing[sex][1] - ip.childbearing[sex][0] + 1));   // :260
-                (void)randbelow(sh, (uint32_t)(ip.childbearing[sex][3] - ip.childbearing[sex][2] + 1));   // :261
+                const int f_lo = ip.childbearing[sex][0] + (int)randbelow(sh, (uint32_t)(ip.childbearing[sex][1] - ip.childbearing[sex][0] + 1));   // :260
+                const int f_hi = ip.childbearing[sex][2] + (int)randbelow(sh, (uint32_t)(ip.childbearing[sex][3] - ip.childbearing[sex][2] + 1));   // :261
                 id_out[count] = nid; x_out[count] = row; y_out[count] = col;
                 vision_out[count] = vision; metab_out[count] = metab; sugar_out[count] = (double)endow;
+                if (life_out) {
+                    life_out[count] = max_age; life_out[life_stride + count] = sex; life_out[2 * life_stride + count] = f_lo;
+                    life_out[3 * life_stride + count] = f_hi; life_out[4 * life_stride + count] = ip.group_tags[g];
+                }
             }
             F--; count++;
             __syncwarp();
@@ -659,7 +665,8 @@ extern "C" cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, cons
 }
 
 extern "C" cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, int32_t* rowfree, int32_t* superfree,
-                                             int32_t* cols, size_t stride, double* sugar, int32_t* result, cudaStream_t stream) {
+                                             int32_t* cols, size_t stride, double* sugar, int32_t* life_cols, int32_t* result,
+                                             cudaStream_t stream) {
     InitAgents ip;
     ip.n_groups = p->n_groups;
     for (int g = 0; g < 4; g++) ip.group_count[g] = g < p->n_groups ? p->group_count[g] : 0;
@@ -667,7 +674,8 @@ extern "C" cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_pa
     ip.endow_min = p->endowment_min; ip.endow_max = p->endowment_max; ip.age_min = p->age_min; ip.age_max = p->age_max;
     for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) ip.childbearing[s][k] = p->childbearing[s][k];
     ip.foresight_lo = p->foresight_lo; ip.foresight_hi = p->foresight_hi;
+    for (int g = 0; g < 4; g++) ip.group_tags[g] = p->group_tags[g];
     ss_init_agents_kernel<<<1, 32, 0, stream>>>(w, ip, rowfree, superfree, cols, cols + stride, cols + 2 * stride, cols + 3 * stride,
-                                                 cols + 4 * stride, sugar, result);
+                                                 cols + 4 * stride, sugar, life_cols, stride, result);
     return cudaGetLastError();
 }

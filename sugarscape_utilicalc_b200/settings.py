@@ -154,4 +154,6 @@ def init_params_from_settings(settings):
         for k, key in enumerate(("min_start", "max_start", "min_end", "max_end")):
             p.childbearing[sex][k] = r[key]
     p.foresight_lo, p.foresight_hi = 0, 0                               # Environment.foresightRange without the rule
+    tg = settings["rule_params"]["tags"]
+    p.group_tags[0], p.group_tags[1] = int(tg["tags0"]), 2 ** int(tg["tags_length"]) - 1      # sugarscape.py:104-105
     return p

@@ -91,7 +91,7 @@ def test_on_disk_outputs_match_reference_golden(name, tmp_path):
     common.check_outputs_against_golden(name, "engine", tmp_path)
 
 
-@pytest.mark.parametrize("name", MT_CASES)
+@pytest.mark.parametrize("name", MT_CASES + common.LIFE_CASES)
 def test_world_initialisation_on_device_equals_reference(name):
     """`random.seed(seed)` + the reference's `__main__` set-up (sugar sites, growback to capacity,
     Agent() + initAgent per agent) run on the device -- capacity / sugar fields, every agent's id, cell, vision,
@@ -111,8 +111,36 @@ def test_world_initialisation_on_device_equals_reference(name):
         assert np.array_equal(ags[key], g[gk]), key
     mt, idx = e.get_rng_mt19937()
     assert np.array_equal(mt, g["init_mt"]) and idx == int(g["init_mt_index"])
+    if name in common.LIFE_CASES:       # the drawn maxAge, sex and fertility and the groups' tags are kept
+        lf = e.download_agents_life()
+        for c in common.LIFE_COLUMNS:
+            assert np.array_equal(lf[c], g["init_life_" + c]), c
+        assert lf["id_increment"] == int(g["init_id_increment"])
     common.run_against_golden(g, e, exact_gini=True, max_steps=40)
     e.close()
+
+
+def test_headless_run_with_births_equals_the_reference_log(tmp_path, monkeypatch):
+    """`python -m sugarscape_utilicalc_b200 examples/evolution_metabolism/settings.json --steps 120`: the event log of the
+    run (mating lines and deaths in execution order) equals the reference's."""
+    import json
+    from sugarscape_utilicalc_b200 import __main__ as runner, outputs
+    g = common.load_golden("f3_evolution_metabolism_mt")
+    (tmp_path / "settings.json").write_text(json.dumps(g["settings"]))
+    monkeypatch.chdir(tmp_path)
+    seen = {}
+    real = outputs.RunRecorder
+
+    class Spy(real):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            seen["rec"] = self
+    monkeypatch.setattr(outputs, "RunRecorder", Spy)
+    assert runner.main(["settings.json", "--quiet", "--steps", "120"]) == 0
+    rec = seen["rec"]
+    assert rec.population == [int(p) for p in g["population"][:120]]
+    assert rec.log == str(g["log_text"]).split("\n")[:int(g["cp100_log_lines"])] + rec.log[int(g["cp100_log_lines"]):]
+    assert len(rec.log) > int(g["cp100_log_lines"])
 
 
 def test_headless_run_of_settings_json_equals_reference_outputs(tmp_path, monkeypatch):
