@@ -1,7 +1,8 @@
 """Checkpoint / resume of a run (the reference never serialises its state; a long engine run
 should be able to).  One `.npz` holds everything a step depends on: the settings.json dict, the RNG mode and stream
 position (the 624 MT19937 words + index, or the keyed seed), `View.iteration` / `Environment.time`, the three cell
-arrays and the agents in list order.  `restore` builds a fresh world from it; continuing there is bit-identical to
+arrays and the agents in list order (with the lifespan / procreation rules also their age, maxAge, sex, fertility, endowment,
+tags and alive flag, and Environment.idIncrement).  `restore` builds a fresh world from it; continuing there is bit-identical to
 never having stopped (tests/test_engine_gpu.py::test_checkpoint_resume, tests/test_oracle_golden.py on the CPU oracle).
 """
 import json
@@ -9,6 +10,8 @@ import json
 import numpy as np
 
 from .settings import config_from_settings
+
+LIFE_COLUMNS = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
 
 
 def save(path, world, settings, rng, iteration, keyed_seed=None):
@@ -22,6 +25,10 @@ def save(path, world, settings, rng, iteration, keyed_seed=None):
                keyed_seed=np.int64(-1 if keyed_seed is None else keyed_seed),
                sugar=cells["sugar"], cap=cells["cap"], pollution=cells["pollution"],
                **{"agent_" + k: ags[k] for k in ("id", "x", "y", "vision", "metab", "sugar")})
+    if settings["rules"].get("limitedLifespan") or settings["rules"].get("procreate"):
+        lf = world.download_agents_life()
+        out.update({"life_" + k: lf[k] for k in LIFE_COLUMNS})
+        out["id_increment"] = np.int64(lf["id_increment"])
     if rng == "mt":
         mt, idx = world.get_rng_mt19937()
         out["mt"], out["mt_index"] = np.asarray(mt, dtype=np.uint32), np.int64(idx)
@@ -43,6 +50,8 @@ def restore(path, world_factory=None, **factory_kwargs):
         world.set_option("global_slots", int(z["n_slots"]))
     world.upload_cells(z["sugar"], z["cap"], z["pollution"])
     world.upload_agents(z["agent_id"], z["agent_x"], z["agent_y"], z["agent_vision"], z["agent_metab"], z["agent_sugar"])
+    if "id_increment" in z.files:
+        world.upload_agents_life(int(z["id_increment"]), **{k: z["life_" + k] for k in LIFE_COLUMNS})
     if rng == "mt":
         world.set_rng_mt19937(z["mt"], int(z["mt_index"]))
     return world, settings, rng, iteration

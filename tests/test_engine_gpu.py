@@ -200,7 +200,7 @@ def test_world_initialisation_fills_the_lattice_and_large_grids():
     e.close()
 
 
-@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "c4_synth130_nopoll_keyed"])
+@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "c4_synth130_nopoll_keyed", "f3_evolution_metabolism_mt"])
 def test_checkpoint_resume(name, tmp_path):
     """checkpoint.save / restore over the engine: stop at step 7, resume from the file in a fresh engine, same end state."""
     common.check_checkpoint_resume(name, "engine", tmp_path, total=min(15, common.load_golden(name)["steps"]))
