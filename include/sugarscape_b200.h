@@ -82,7 +82,9 @@ typedef struct {
                                      (agent.py:727-737), with or without the tags rule                               */
     int32_t foresight_lo;         /* Environment.foresightRange, (0, 0) unless rules.foresight: Agent.__init__ of a  */
     int32_t foresight_hi;         /* child spends randint(lo, hi) on generateForesight (agent.py:165, 329-333)       */
-    int32_t reserved0;
+    int32_t rule_spice;           /* rules.spice: second resource, Cobb-Douglas welfare in move()
+                                     (agent.py:833-853, 1220-1251), spice metabolism / starvation (sugarscape.py:571-572,
+                                     311-314); serial path; ss_upload_cells_spice + ss_upload_agents_spice               */
 } ss_config;
 
 /* What one updateGame() appends to View.population / metabolismMean / visionMean / gini

@@ -25,7 +25,7 @@ class SsoConfig(C.Structure):
         ("pollution_a", C.c_double), ("pollution_b", C.c_double), ("max_capacity", C.c_double),
         ("keyed_seed", C.c_uint64), ("iteration", C.c_int64), ("env_time", C.c_int64),
         ("rule_limited_lifespan", C.c_int32), ("rule_procreate", C.c_int32), ("tags_length", C.c_int32),
-        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("reserved0", C.c_int32),
+        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("rule_spice", C.c_int32),
     ]
 
 
@@ -75,6 +75,10 @@ def lib():
         L.sso_download_agents.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.sso_upload_agents_life.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.sso_download_agents_life.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.sso_upload_cells_spice.argtypes = [vp, vp, vp]
+        L.sso_download_cells_spice.argtypes = [vp, vp, vp]
+        L.sso_upload_agents_spice.argtypes = [vp, C.c_int32, vp, vp, vp]
+        L.sso_download_agents_spice.argtypes = [vp, vp, vp, vp]
         L.sso_id_increment.argtypes = [vp]
         L.sso_id_increment.restype = C.c_int32
         L.sso_event_count.argtypes = [vp]
@@ -191,3 +195,29 @@ class OracleWorld:
         if k:
             self._check(lib().sso_get_events(self._h, k, _ptr(out)))
         return out
+
+    # spice
+    def upload_cells_spice(self, spice, spice_cap):
+        a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (spice, spice_cap))
+        self._check(lib().sso_upload_cells_spice(self._h, _ptr(a), _ptr(b)))
+
+    def download_cells_spice(self):
+        n = self.n
+        a, b = np.empty((n, n)), np.empty((n, n))
+        self._check(lib().sso_download_cells_spice(self._h, _ptr(a), _ptr(b)))
+        return dict(spice=a, spice_cap=b)
+
+    def upload_agents_spice(self, spice_metab, spice, endowment=None):
+        m = np.ascontiguousarray(spice_metab, dtype=np.int32)
+        sp = np.ascontiguousarray(spice, dtype=np.float64)
+        en = None if endowment is None else np.ascontiguousarray(endowment, dtype=np.float64)
+        self._check(lib().sso_upload_agents_spice(self._h, len(m), _ptr(m), _ptr(sp), _ptr(en)))
+
+    def download_agents_spice(self):
+        k = lib().sso_agent_count(self._h)
+        m, sp, en = np.empty(k, dtype=np.int32), np.empty(k), np.empty(k)
+        self._check(lib().sso_download_agents_spice(self._h, _ptr(m), _ptr(sp), _ptr(en)))
+        return dict(spice_metab=m, spice=sp, spice_endowment=en)
+
+    def pow_faults(self):
+        return int(lib().sso_pow_faults())

@@ -313,6 +313,11 @@ class ReferenceRun:
             tags=np.array([a.tags for a in ags], dtype=np.int32),
             alive=np.array([1 if a.alive else 0 for a in ags], dtype=np.int32),
             id_increment=int(env.idIncrement),
+            # spice
+            spice_cap=np.array([[g[i][j][3] for j in range(n)] for i in range(n)], dtype=np.float64),
+            spice_metab=np.array([a.spiceMetabolism for a in ags], dtype=np.int32),
+            spice_agent=np.array([a.spice for a in ags], dtype=np.float64),
+            spice_endowment=np.array([a.spiceEndowment for a in ags], dtype=np.float64),
         )
         mt, idx = self.mt_state()
         snap["mt"], snap["mt_index"] = mt, idx

@@ -25,6 +25,7 @@
  *   genrand_uint32() >> (32-k)); or the keyed word source of oracle/keyed_rng.py.
  */
 #include "ss_oracle.h"
+#include "../sugarscape_utilicalc_b200/csrc/ss_pow.h"   /* x ** y of the reference, bit for bit */
 
 #include <math.h>
 #include <stdio.h>
@@ -41,6 +42,7 @@ struct sso_world {
     sso_config cfg;
     int n;
     double *sugar, *cap, *poll;
+    double *spice, *spice_cap;    /* Environment.grid slots [1], [3] (environment.py:24-34) */
     int32_t* occ;             /* slot or -1 */
     /* agent store, indexed by slot = id - 1 */
     int32_t n_slots;
@@ -57,6 +59,10 @@ struct sso_world {
     int32_t *age, *max_age, *sex, *fert_lo, *fert_hi, *tags;
     double* endow;
     uint8_t* living;
+    /* Agent.spice, spiceMetabolism, spiceEndowment (= spiceCostForMating) */
+    int have_spice;
+    double *aspice, *sp_endow;
+    int32_t* asp_metab;
     int32_t* events;          /* 4 per event: kind | step << 8, a, b, c -- kind 1: a mated with b and created c; 2: a died of
                                  starvation; 3: a died of old age (sugarscape.py:551, 597-600) */
     int32_t n_events, cap_events, step_in_call;
@@ -262,6 +268,55 @@ static void agent_move(sso_world* w, int s) {
     w->sugar[best] = 0.0;                                                       /* agent.py:864 */
 }
 
+/* agent.py:231-236 setSpice: same floor as setSugar */
+#define set_spice set_sugar
+/* float_pow (CPython floatobject.c) for positive finite bases: iw == 0 and iv == 1 are answered before libm's pow() */
+static const ss_pow_tables POW_T = {SS_POW_LOG_HDR, SS_POW_LOG_TAB, SS_POW_EXP_HDR, SS_POW_EXP_TAB};
+static int g_pow_bad;
+static double py_pow(double x, double y) {
+    if (y == 0.0) return 1.0;
+    if (x == 1.0) return 1.0;
+    return ss_pow_pos(&POW_T, x, y, &g_pow_bad);
+}
+/* agent.py:1220-1251 getWelfare(x=, y=), no tags, no foresight: Cobb-Douglas in the wealth the agent would have on the cell --
+ * `if x and y:` (Q9): a cell on row 0 or column 0 does not count its sugar and spice */
+static double welfare_at(sso_world* w, int s, int cx, int cy) {
+    double w1 = w->asugar[s], w2 = w->aspice[s];
+    if (cx != 0 && cy != 0) {
+        int c = cx * w->n + cy;
+        w1 = w1 + (double)(int)w->sugar[c];
+        w2 = w2 + (double)(int)w->spice[c];
+    }
+    double m1 = (double)w->ametab[s], m2 = (double)w->asp_metab[s], mt = (double)(w->ametab[s] + w->asp_metab[s]);
+    if (!(w1 > 0.0 && w2 > 0.0)) return 0.0;
+    return py_pow(w1, m1 / mt) * py_pow(w2, m2 / mt);
+}
+/* agent.py:794-865 move(), spice branch (833-853): closest cell of highest welfare, both resources harvested */
+static void agent_move_spice(sso_world* w, int s) {
+    int n = w->n, x = w->ax[s], y = w->ay[s];
+    int32_t food[MAXC];
+    int m = get_food(w, s, food);
+    food[m++] = x * n + y;
+    int best = -1, best_d = 0;
+    double best_w = 0.0;
+    for (int p = 0; p < m; p++) {
+        int c = food[p], cx = c / n, cy = c % n;
+        double wf = welfare_at(w, s, cx, cy);
+        int d = abs(x - cx) + abs(y - cy);
+        if (best < 0 || wf > best_w || (wf == best_w && d < best_d)) { best = c; best_w = wf; best_d = d; }
+    }
+    int sg = (int)w->sugar[best], sp = (int)w->spice[best];
+    w->aspice[s] = set_spice(w, max0(w->aspice[s] + (double)sp));                /* agent.py:851 */
+    w->asugar[s] = set_sugar(w, max0(w->asugar[s] + (double)sg));                /* agent.py:852 */
+    int old = x * n + y;
+    if (best != old) {
+        w->occ[old] = -1; w->occ[best] = s;
+        w->ax[s] = best / n; w->ay[s] = best % n;
+    }
+    w->sugar[best] = 0.0;                                                        /* agent.py:864-865 */
+    w->spice[best] = 0.0;
+}
+
 /* agent.py:1025-1141 utilicalcMove(), sugar-only variant (utilicalcSugar 980-992) */
 static void agent_utilicalc(sso_world* w, int s) {
     int n = w->n, x = w->ax[s], y = w->ay[s];
@@ -321,6 +376,7 @@ static int ensure_capacity(sso_world* w, int32_t need) {
     GROW(w->sortk, uint64_t); GROW(w->sortk2, uint64_t);
     GROW(w->age, int32_t); GROW(w->max_age, int32_t); GROW(w->sex, int32_t); GROW(w->fert_lo, int32_t);
     GROW(w->fert_hi, int32_t); GROW(w->tags, int32_t); GROW(w->endow, double); GROW(w->living, uint8_t);
+    GROW(w->aspice, double); GROW(w->sp_endow, double); GROW(w->asp_metab, int32_t);
 #undef GROW
     w->cap_slots = nc;
     return 0;
@@ -337,7 +393,8 @@ static void add_event(sso_world* w, int kind, int a, int b, int c) {
 }
 /* agent.py:764-773 isFertile, no-spice branch (sugarCostForMating = the endowment, agent.py:204-206) */
 static int is_fertile(const sso_world* w, int s) {
-    return w->fert_lo[s] <= w->age[s] && w->age[s] <= w->fert_hi[s] && w->asugar[s] >= w->endow[s];
+    return w->fert_lo[s] <= w->age[s] && w->age[s] <= w->fert_hi[s] && w->asugar[s] >= w->endow[s] &&
+           (!w->cfg.rule_spice || w->aspice[s] >= w->sp_endow[s]);
 }
 /* agent.py:681-696 findFreeLocationAround: no torus here (isLocationValid), x-line then y-line, randint over the list */
 static int find_free_around(sso_world* w, int x, int y) {
@@ -359,11 +416,16 @@ static double random_random(sso_world* w) {
 static int create_child(sso_world* w, int s, int b, int loc) {
     int g[2] = {s, b};
     int metab = w->ametab[g[randbelow(w, 2u)]];
-    (void)randbelow(w, 2u);                                   /* spiceMetabolism */
+    int sp_metab = w->asp_metab[g[randbelow(w, 2u)]];         /* spiceMetabolism (drawn with or without the spice rule) */
     int vision = w->avision[g[randbelow(w, 2u)]];
     double endow = 0.5 * (w->endow[s] + w->endow[b]);
+    double sp_endow = 0.5 * (w->sp_endow[s] + w->sp_endow[b]);
     w->asugar[s] = set_sugar(w, max0(w->asugar[s] - 0.5 * w->endow[s]));
     w->asugar[b] = set_sugar(w, max0(w->asugar[b] - 0.5 * w->endow[b]));
+    if (w->cfg.rule_spice) {                                  /* agent.py:712-714 */
+        w->aspice[s] = set_spice(w, max0(w->aspice[s] - 0.5 * w->sp_endow[s]));
+        w->aspice[b] = set_spice(w, max0(w->aspice[b] - 0.5 * w->sp_endow[b]));
+    }
     int max_age = w->max_age[g[randbelow(w, 2u)]];
     int sex = (int)randbelow(w, 2u);
     int fg = g[randbelow(w, 2u)];
@@ -381,6 +443,8 @@ static int create_child(sso_world* w, int s, int b, int loc) {
     w->ametab[c] = metab; w->avision[c] = vision;
     w->endow[c] = endow;
     w->asugar[c] = set_sugar(w, endow);                       /* setInitialSugarEndowment */
+    w->asp_metab[c] = sp_metab; w->sp_endow[c] = sp_endow;
+    w->aspice[c] = w->cfg.rule_spice ? set_spice(w, sp_endow) : 0.0;
     w->age[c] = 0; w->max_age[c] = max_age; w->sex[c] = sex;
     w->fert_lo[c] = w->fert_lo[fg]; w->fert_hi[c] = w->fert_hi[fg];
     w->tags[c] = tags;
@@ -437,6 +501,10 @@ static double calculate_gini(double* wealth, int n) {
 static inline void grow_cell(sso_world* w, int c, double alpha) {
     double v = w->sugar[c] + alpha;
     w->sugar[c] = v <= w->cap[c] ? v : w->cap[c];
+    if (w->cfg.rule_spice) {                       /* environment.py:141-142 */
+        double u = w->spice[c] + alpha;
+        w->spice[c] = u <= w->spice_cap[c] ? u : w->spice_cap[c];
+    }
 }
 /* environment.py:146-155 */
 static void grow_region(sso_world* w, const int32_t r[4], double alpha) {
@@ -489,7 +557,7 @@ static void one_step(sso_world* w, sso_step_stats* st) {
         radix_sort_u64(w->sortk, w->sortk2, w->n_order);
         for (int i = 0; i < w->n_order; i++) w->order[i] = (int32_t)(w->sortk[i] & 0xffffffffu);
     }
-    double sum_m = 0.0, sum_v = 0.0;
+    double sum_m = 0.0, sum_m2 = 0.0, sum_v = 0.0;
     int nw = 0, kept = 0, acted = 0, deaths = 0, skip_next = 0;
     /* sugarscape.py:520: `for agent in self.agents` while removeAgent() does list.remove:
        the agent following each dying agent loses its turn (Q1). */
@@ -497,7 +565,7 @@ static void one_step(sso_world* w, sso_step_stats* st) {
         int s = w->order[i];
         if (skip_next) { skip_next = 0; w->order[kept++] = s; continue; }
         if (cfg->rng_mode == 1) keyed_begin_agent(w, s + 1);
-        if (cfg->rule_move_eat) agent_move(w, s);
+        if (cfg->rule_move_eat) { if (cfg->rule_spice) agent_move_spice(w, s); else agent_move(w, s); }
         if (cfg->rule_utilicalc) agent_utilicalc(w, s);
         if (cfg->rule_procreate && is_fertile(w, s)) procreate(w, s);        /* sugarscape.py:543-554 */
         /* sugarscape.py:566-567 consumption pollution */
@@ -505,12 +573,16 @@ static void one_step(sso_world* w, sso_step_stats* st) {
             pollute_site(w, w->ax[s] * n + w->ay[s], 0.0, (double)w->ametab[s]);
         /* sugarscape.py:569 */
         w->asugar[s] = set_sugar(w, max0(w->asugar[s] - (double)w->ametab[s]));
+        if (cfg->rule_spice)                                    /* sugarscape.py:571-572 */
+            w->aspice[s] = set_spice(w, max0(w->aspice[s] - (double)w->asp_metab[s]));
         sum_m += (double)w->ametab[s];
+        if (cfg->rule_spice) sum_m2 += (double)w->asp_metab[s];
         sum_v += (double)w->avision[s];
-        w->wealth[nw++] = w->asugar[s];
+        w->wealth[nw++] = cfg->rule_spice ? w->asugar[s] + w->aspice[s] : w->asugar[s];      /* sugarscape.py:580-583 */
         acted++;
         int living = w->have_life ? w->living[s] : 1;          /* Agent.alive: 0 for an agent that reached maxAge last step */
         if (cfg->rule_can_starve && w->asugar[s] <= 0.1) living = 0;    /* sugarscape.py:306-309 */
+        if (cfg->rule_can_starve && cfg->rule_spice && w->aspice[s] <= 0.1) living = 0;      /* sugarscape.py:311-314 */
         if (living && cfg->rule_limited_lifespan) {             /* sugarscape.py:588-591 + agent.py:636-639 incAge */
             w->age[s]++;
             w->living[s] = (uint8_t)(w->max_age[s] > w->age[s]);        /* (the agent stays for one more turn) */
@@ -530,7 +602,7 @@ static void one_step(sso_world* w, sso_step_stats* st) {
     }
     w->n_order = kept;
     st->population = (double)kept;
-    st->metabolism_mean = kept > 0 ? sum_m / (double)kept : 0.0;
+    st->metabolism_mean = kept > 0 ? (cfg->rule_spice ? ((sum_m + sum_m2) / 2.0) / (double)kept : sum_m / (double)kept) : 0.0;   /* sugarscape.py:608-612 */
     st->vision_mean = kept > 0 ? sum_v / (double)kept : 0.0;
     st->gini = kept > 0 ? calculate_gini(w->wealth, nw) : 0.0;
     st->acted = (double)acted;
@@ -566,6 +638,7 @@ int sso_create(const sso_config* cfg, sso_world** out) {
     if (cfg->rule_utilicalc && cfg->rule_pollution) return fail("utilicalc+pollution crashes in the reference (agent.py:880)");
     if (cfg->rule_pollution && cfg->diffusion_rate < 1) return fail("diffusion_rate must be >= 1");
     if (cfg->rule_seasons && cfg->season_period < 1) return fail("season period must be >= 1");
+    if (cfg->rule_spice && (!cfg->rule_move_eat || cfg->rule_pollution)) return fail("spice: with rule M, without pollution (sugarscape.py:195-197)");
     sso_world* w = (sso_world*)calloc(1, sizeof *w);
     if (!w) return fail("out of memory");
     w->cfg = *cfg;
@@ -575,7 +648,9 @@ int sso_create(const sso_config* cfg, sso_world** out) {
     w->cap = (double*)calloc(cells, sizeof(double));
     w->poll = (double*)calloc(cells, sizeof(double));
     w->occ = (int32_t*)malloc(cells * sizeof(int32_t));
-    if (!w->sugar || !w->cap || !w->poll || !w->occ) { sso_destroy(w); return fail("out of memory"); }
+    w->spice = (double*)calloc(cells, sizeof(double));
+    w->spice_cap = (double*)calloc(cells, sizeof(double));
+    if (!w->sugar || !w->cap || !w->poll || !w->occ || !w->spice || !w->spice_cap) { sso_destroy(w); return fail("out of memory"); }
     for (size_t c = 0; c < cells; c++) w->occ[c] = -1;
     w->iteration = cfg->iteration;
     w->env_time = cfg->env_time;
@@ -589,13 +664,15 @@ static void free_agents(sso_world* w) {
     free(w->ax); free(w->ay); free(w->avision); free(w->ametab); free(w->asugar); free(w->alive);
     free(w->order); free(w->wealth); free(w->sortk); free(w->sortk2);
     free(w->age); free(w->max_age); free(w->sex); free(w->fert_lo); free(w->fert_hi); free(w->tags); free(w->endow); free(w->living);
+    free(w->aspice); free(w->sp_endow); free(w->asp_metab);
+    w->aspice = w->sp_endow = NULL; w->asp_metab = NULL;
     w->ax = w->ay = w->avision = w->ametab = w->order = w->age = w->max_age = w->sex = w->fert_lo = w->fert_hi = w->tags = NULL;
     w->asugar = w->wealth = w->endow = NULL; w->alive = w->living = NULL; w->sortk = w->sortk2 = NULL;
     w->cap_slots = 0;
 }
 void sso_destroy(sso_world* w) {
     if (!w) return;
-    free(w->sugar); free(w->cap); free(w->poll); free(w->occ);
+    free(w->sugar); free(w->cap); free(w->poll); free(w->occ); free(w->spice); free(w->spice_cap);
     free_agents(w);
     free(w->events);
     free(w);
@@ -627,6 +704,7 @@ int sso_upload_agents(sso_world* w, int32_t n, const int32_t* id, const int32_t*
     w->n_slots = ns;
     w->id_increment = max_id;
     w->have_life = 0;
+    w->have_spice = 0;
     if (ensure_capacity(w, ns)) return -1;         /* every per-slot array, the list and the scratch arrays (n <= ns) */
     size_t cells = (size_t)w->n * (size_t)w->n;
     for (size_t c = 0; c < cells; c++) w->occ[c] = -1;
@@ -665,8 +743,44 @@ int sso_get_rng_mt19937(sso_world* w, uint32_t state[624], int32_t* index) {
     return 0;
 }
 
+/* Environment.grid slots [1] spice and [3] spice capacity; Agent.spice / spiceMetabolism / spiceEndowment of the n
+ * agents of the last sso_upload_agents, same order (endowment may be NULL: = spice) */
+int sso_upload_cells_spice(sso_world* w, const double* spice, const double* spice_cap) {
+    size_t cells = (size_t)w->n * (size_t)w->n;
+    memcpy(w->spice, spice, cells * sizeof(double));
+    memcpy(w->spice_cap, spice_cap, cells * sizeof(double));
+    return 0;
+}
+int sso_download_cells_spice(sso_world* w, double* spice, double* spice_cap) {
+    size_t cells = (size_t)w->n * (size_t)w->n;
+    if (spice) memcpy(spice, w->spice, cells * sizeof(double));
+    if (spice_cap) memcpy(spice_cap, w->spice_cap, cells * sizeof(double));
+    return 0;
+}
+int sso_upload_agents_spice(sso_world* w, int32_t n, const int32_t* spice_metab, const double* spice, const double* endowment) {
+    if (n != w->n_order) return fail("sso_upload_agents_spice: n differs from the uploaded agents");
+    for (int i = 0; i < n; i++) {
+        int s = w->order[i];
+        if (spice_metab[i] < 1) return fail("spice metabolism must be >= 1");
+        w->asp_metab[s] = spice_metab[i]; w->aspice[s] = spice[i]; w->sp_endow[s] = endowment ? endowment[i] : spice[i];
+    }
+    w->have_spice = 1;
+    return 0;
+}
+int sso_download_agents_spice(sso_world* w, int32_t* spice_metab, double* spice, double* endowment) {
+    for (int i = 0; i < w->n_order; i++) {
+        int s = w->order[i];
+        if (spice_metab) spice_metab[i] = w->asp_metab[s];
+        if (spice) spice[i] = w->aspice[s];
+        if (endowment) endowment[i] = w->sp_endow[s];
+    }
+    return 0;
+}
+int sso_pow_faults(void) { return g_pow_bad; }
+
 int sso_step(sso_world* w, int32_t nsteps, sso_step_stats* out) {
     sso_step_stats tmp;
+    if (w->cfg.rule_spice && !w->have_spice) return fail("spice: sso_upload_agents_spice first");
     if ((w->cfg.rule_limited_lifespan || w->cfg.rule_procreate) && !w->have_life)
         return fail("limitedLifespan / procreate: sso_upload_agents_life first");
     w->n_events = 0;

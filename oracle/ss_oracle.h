@@ -46,7 +46,7 @@ typedef struct {
     int32_t rule_procreate;       /* rules.procreate                                        */
     int32_t tags_length;          /* rule_params.tags.tags_length                           */
     int32_t foresight_lo, foresight_hi;   /* Environment.foresightRange                     */
-    int32_t reserved0;
+    int32_t rule_spice;           /* rules.spice                                            */
 } sso_config;
 
 typedef struct {
@@ -89,6 +89,13 @@ int32_t sso_id_increment(sso_world* w);
  * and created c (sugarscape.py:551); 2: a died of starvation; 3: a died of old age (sugarscape.py:597-600) */
 int32_t sso_event_count(sso_world* w);
 int  sso_get_events(sso_world* w, int32_t max_events, int32_t* out);
+/* Environment.grid slots [1], [3]; Agent.spice / spiceMetabolism / spiceEndowment (NULL: = spice) of the
+ * agents of the last sso_upload_agents, same order */
+int  sso_upload_cells_spice(sso_world* w, const double* spice, const double* spice_cap);
+int  sso_download_cells_spice(sso_world* w, double* spice, double* spice_cap);
+int  sso_upload_agents_spice(sso_world* w, int32_t n, const int32_t* spice_metab, const double* spice, const double* endowment);
+int  sso_download_agents_spice(sso_world* w, int32_t* spice_metab, double* spice, double* endowment);
+int  sso_pow_faults(void);   /* operands ss_pow_pos had no answer for (must stay 0) */
 const char* sso_last_error(void);
 
 #ifdef __cplusplus

@@ -30,7 +30,7 @@ class SsConfig(C.Structure):
         ("pollution_a", C.c_double), ("pollution_b", C.c_double), ("max_capacity", C.c_double),
         ("keyed_seed", C.c_uint64), ("iteration", C.c_int64), ("env_time", C.c_int64),
         ("rule_limited_lifespan", C.c_int32), ("rule_procreate", C.c_int32), ("tags_length", C.c_int32),
-        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("reserved0", C.c_int32),
+        ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("rule_spice", C.c_int32),
     ]
 
 

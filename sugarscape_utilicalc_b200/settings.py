@@ -31,8 +31,8 @@ class UnsupportedRuleError(Exception):
 
 
 #: rules.* keys the engine implements; everything else must be false
-SUPPORTED_RULES = ("grow", "seasons", "moveEat", "canStarve", "pollution", "utilicalc", "limitedLifespan", "procreate")
-UNSUPPORTED_RULES = ("tags", "combat", "replacement", "transmit", "spice",
+SUPPORTED_RULES = ("grow", "seasons", "moveEat", "canStarve", "pollution", "utilicalc", "limitedLifespan", "procreate", "spice")
+UNSUPPORTED_RULES = ("tags", "combat", "replacement", "transmit",
                      "trade", "foresight", "credit", "inheritance", "disease")
 
 
@@ -126,6 +126,9 @@ def config_from_settings(settings, rng_mode="mt", keyed_seed=None, iteration=0, 
                                        "id range the keyed order is sized by)")
         cfg.tags_length = int(rp["tags"]["tags_length"])                    # sugarscape.py:110
     cfg.foresight_lo, cfg.foresight_hi = 0, 0                               # Environment.foresightRange without the rule
+    cfg.rule_spice = int(bool(rules.get("spice", False)))
+    if cfg.rule_spice and not rules["moveEat"]:
+        raise UnsupportedRuleError("spice is built with rule M (moveEat): examples/utilicalc_spice raises KeyError 'proximity' in the reference")
     return cfg
 
 
