@@ -171,6 +171,18 @@ int  ss_download_agents_life(ss_engine* e, int32_t* age, int32_t* max_age, int32
 int  ss_event_count(ss_engine* e, int32_t* count);
 int  ss_get_events(ss_engine* e, int32_t max_events, int32_t* out);
 
+/* SURVEY 8 f2 -- spice (rule M, serial path).
+ * Replaces: Environment.grid slots [1] spice and [3] spice capacity (environment.py:24-34, 102-104, 141-142) and
+ * Agent.spice / spiceMetabolism / spiceEndowment (= spiceCostForMating; agent.py:127-131, 210-216) as read by the spice branch
+ * of move() (agent.py:833-853: arg-max of the Cobb-Douglas welfare getWelfare, 1220-1251 -- w1 ** (m1/mt) * w2 ** (m2/mt),
+ * with `x ** y` computed as the reference's libm does, bit for bit: csrc/ss_pow.h), by the spice metabolism and starvation
+ * of updateGame (sugarscape.py:571-572, 311-314) and by createChild / isFertile (agent.py:712-714, 768-771).
+ * Both uploads are required before ss_step when rules.spice is on; endowment may be NULL (= spice). */
+int  ss_upload_cells_spice(ss_engine* e, const double* spice, const double* spice_cap);
+int  ss_download_cells_spice(ss_engine* e, double* spice, double* spice_cap);
+int  ss_upload_agents_spice(ss_engine* e, int32_t n, const int32_t* spice_metab, const double* spice, const double* endowment);
+int  ss_download_agents_spice(ss_engine* e, int32_t* spice_metab, double* spice, double* endowment);
+
 /* Replaces: the global `random` state (random.getstate()[1]; sugarscape.py:160-162). */
 int  ss_set_rng_mt19937(ss_engine* e, const uint32_t state[624], int32_t index);
 int  ss_get_rng_mt19937(ss_engine* e, uint32_t state[624], int32_t* index);

@@ -64,6 +64,7 @@ EXPORTS = (
     "ss_create_strip", "ss_strip_init_directory", "ss_strip_export", "ss_strip_connect", "ss_strip_ipc_export",
     "ss_strip_ipc_connect", "ss_strip_step", "ss_strip_phase",
     "ss_upload_agents_life", "ss_download_agents_life", "ss_event_count", "ss_get_events",
+    "ss_upload_cells_spice", "ss_download_cells_spice", "ss_upload_agents_spice", "ss_download_agents_spice",
 )
 
 _lib = None
@@ -124,6 +125,10 @@ def lib():
     L.ss_download_agents_life.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32)]
     L.ss_event_count.argtypes = [vp, C.POINTER(C.c_int32)]
     L.ss_get_events.argtypes = [vp, C.c_int32, vp]
+    L.ss_upload_cells_spice.argtypes = [vp, vp, vp]
+    L.ss_download_cells_spice.argtypes = [vp, vp, vp]
+    L.ss_upload_agents_spice.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.ss_download_agents_spice.argtypes = [vp, vp, vp, vp]
     L.ss_host_alloc.argtypes = [C.c_size_t]
     L.ss_host_alloc.restype = vp
     L.ss_host_free.argtypes = [vp]

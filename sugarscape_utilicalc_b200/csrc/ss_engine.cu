@@ -13,7 +13,7 @@
 #include "ss_life.cuh"
 
 extern "C" {
-cudaError_t ss_launch_serial(const DevWorld& w, const LifeWorld& lw, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
+cudaError_t ss_launch_serial(const DevWorld& w, const LifeWorld& lw, const SpiceWorld& sw, int64_t iteration, int64_t env_time, int nsteps, int fused_env,
                              int stats_base, cudaStream_t stream);
 cudaError_t ss_launch_prepare(const DevWorld& w, int64_t iteration, int stamp_q1, cudaStream_t s);
 size_t ss_dr_build_smem(int vmax);
@@ -96,6 +96,9 @@ struct ss_engine {
     bool have_life = false;
     uint32_t slot_capacity = 0;                 // allocation of agents / order / wealth / sortkeys (>= n_slots; births need room)
     int32_t n_events = 0;                       // events of the last ss_step call
+    // SURVEY 8 f2 (spice; serial path with the fused environment phase)
+    SpiceWorld sw{};
+    bool have_spice = false;
     int life_slack = -1;                        // option "life_capacity_slack" (tests): room for births instead of the default
     int grow_ctas_per_sm = 2;                   // ... as a few CTAs per SM that fit beside the conflict-graph CTAs
     // row strips (one engine per GPU): this engine holds the lattice rows [x0, x0 + rows)
@@ -184,6 +187,12 @@ static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32
         if (cfg->tags_length < 0 || cfg->tags_length > 30) return set_err(e, SS_ERR_ARG, "tags_length out of range [0,30]");
         if (cfg->foresight_hi < cfg->foresight_lo) return set_err(e, SS_ERR_ARG, "foresight range");
     }
+    if (cfg->rule_spice) {
+        if (!cfg->rule_move_eat || cfg->rule_utilicalc)
+            return set_err(e, SS_ERR_UNSUPPORTED, "spice is built with rule M (moveEat); utilicalc + spice raises KeyError 'proximity' in the reference");
+        if (cfg->rule_pollution) return set_err(e, SS_ERR_ARG, "pollution and spice cannot be used together");   // sugarscape.py:195-197
+        if (world > 1) return set_err(e, SS_ERR_UNSUPPORTED, "spice: one GPU (serial order)");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return set_err(e, SS_ERR_CUDA, "no CUDA device: the engine has no CPU fallback");
@@ -231,6 +240,12 @@ static int create_impl(const ss_config* cfg, int32_t device, int32_t rank, int32
     if ((ce = cudaMalloc(&e->w.acc, sizeof(StepAccum))) != cudaSuccess) return bail(ce, "cudaMalloc acc");
     if ((ce = cudaMalloc(&e->w.hist, SS_GINI_BINS * sizeof(uint32_t))) != cudaSuccess) return bail(ce, "cudaMalloc hist");
     if ((ce = cudaMalloc(&e->w.outliers, SS_GINI_OUTLIERS * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc outliers");
+    if (cfg->rule_spice) {
+        if ((ce = cudaMalloc(&e->sw.spice, cb)) != cudaSuccess || (ce = cudaMalloc(&e->sw.spice_cap, cb)) != cudaSuccess ||
+            (ce = cudaMalloc(&e->sw.pow_faults, sizeof(int32_t))) != cudaSuccess) return bail(ce, "cudaMalloc spice");
+        if ((ce = cudaMemset(e->sw.spice, 0, cb)) != cudaSuccess || (ce = cudaMemset(e->sw.spice_cap, 0, cb)) != cudaSuccess ||
+            (ce = cudaMemset(e->sw.pow_faults, 0, sizeof(int32_t))) != cudaSuccess) return bail(ce, "initialising device memory");
+    }
     const int nbands = (cfg->grid_size + 31) / 32;
     if ((ce = cudaMalloc(&e->d_flags, sizeof(int) * (size_t)(nbands + 1))) != cudaSuccess) return bail(ce, "cudaMalloc flags");
     if ((ce = cudaMallocHost(&e->h_pending, sizeof(unsigned long long))) != cudaSuccess) return bail(ce, "cudaMallocHost");
@@ -261,6 +276,7 @@ extern "C" void ss_destroy(ss_engine* e) {
     cudaFree(e->w.acc); cudaFree(e->w.hist); cudaFree(e->w.outliers); cudaFree(e->d_flags); cudaFree(e->d_handoff); cudaFree(e->w.log); cudaFree(e->w.log_count); cudaFree(e->w.clog); cudaFree(e->w.clog_count);
     dr_free(e);
     cudaFree(e->lw.rec); cudaFree(e->lw.id_increment); cudaFree(e->lw.events); cudaFree(e->lw.n_events); cudaFree(e->lw.status);
+    cudaFree(e->sw.spice); cudaFree(e->sw.spice_cap); cudaFree(e->sw.aspice); cudaFree(e->sw.sp_endow); cudaFree(e->sw.asp_metab); cudaFree(e->sw.pow_faults);
     if (e->h_pending) cudaFreeHost(e->h_pending);
     cudaFree(e->h_dev_count);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -401,6 +417,10 @@ static int choose_path(ss_engine* e) {
     } else {
         path = lattice_ok ? PATH_LATTICE : (n <= 256 ? PATH_SERIAL_FUSED : PATH_SERIAL_ENV);
     }
+    if (e->cfg.rule_spice) {            // the serial kernel's own environment phase grows the spice too
+        if (e->path_option == PATH_LATTICE) return set_err(e, SS_ERR_UNSUPPORTED, "spice runs on the serial path");
+        path = PATH_SERIAL_FUSED;
+    }
     if (path != PATH_LATTICE && e->w.n_slots > (1u << 22))
         return set_err(e, SS_ERR_UNSUPPORTED, "serial path limited to 4M agents");
     e->geom = g;
@@ -481,6 +501,17 @@ static int finish_agents(ss_engine* e, int32_t n, int32_t* d_i32, size_t nn, dou
     CK(cudaMalloc(&e->w.order, sizeof(int32_t) * cap));
     CK(cudaMalloc(&e->w.wealth, sizeof(double) * P));
     CK(cudaMalloc(&e->w.sortkeys, sizeof(unsigned long long) * P));
+    if (e->cfg.rule_spice) {
+        cudaFree(e->sw.aspice); cudaFree(e->sw.sp_endow); cudaFree(e->sw.asp_metab);
+        e->sw.aspice = nullptr; e->sw.sp_endow = nullptr; e->sw.asp_metab = nullptr;
+        CK(cudaMalloc(&e->sw.aspice, sizeof(double) * cap));
+        CK(cudaMalloc(&e->sw.sp_endow, sizeof(double) * cap));
+        CK(cudaMalloc(&e->sw.asp_metab, sizeof(int32_t) * cap));
+        CK(cudaMemsetAsync(e->sw.aspice, 0, sizeof(double) * cap, e->stream));
+        CK(cudaMemsetAsync(e->sw.sp_endow, 0, sizeof(double) * cap, e->stream));
+        CK(cudaMemsetAsync(e->sw.asp_metab, 0, sizeof(int32_t) * cap, e->stream));
+        e->have_spice = false;
+    }
     if (life) {
         cudaFree(e->lw.rec); e->lw.rec = nullptr;
         CK(cudaMalloc(&e->lw.rec, sizeof(LifeRec) * cap));
@@ -583,6 +614,70 @@ extern "C" int ss_download_agents_life(ss_engine* e, int32_t* age, int32_t* max_
         if (alive) alive[i] = r.living;
     }
     if (id_increment) *id_increment = idinc;
+    return SS_OK;
+}
+
+// Environment.grid slots [1] spice and [3] spice capacity (environment.py:24-34, 102-104)
+extern "C" int ss_upload_cells_spice(ss_engine* e, const double* spice, const double* spice_cap) {
+    if (!e || !spice || !spice_cap) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->cfg.rule_spice) return set_err(e, SS_ERR_STATE, "the engine was created without the spice rule");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->sw.spice, spice, e->cells * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->sw.spice_cap, spice_cap, e->cells * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SS_OK;
+}
+extern "C" int ss_download_cells_spice(ss_engine* e, double* spice, double* spice_cap) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->cfg.rule_spice) return set_err(e, SS_ERR_STATE, "the engine was created without the spice rule");
+    CK(cudaSetDevice(e->device));
+    if (spice) CK(cudaMemcpyAsync(spice, e->sw.spice, e->cells * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (spice_cap) CK(cudaMemcpyAsync(spice_cap, e->sw.spice_cap, e->cells * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SS_OK;
+}
+// Agent.spice / spiceMetabolism / spiceEndowment (= spiceCostForMating; NULL: = spice) of the n agents of the last
+// ss_upload_agents, same order (agent.py:127-131, 210-216)
+extern "C" int ss_upload_agents_spice(ss_engine* e, int32_t n, const int32_t* spice_metab, const double* spice, const double* endowment) {
+    if (!e || n < 0 || (n > 0 && (!spice_metab || !spice))) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->cfg.rule_spice) return set_err(e, SS_ERR_STATE, "the engine was created without the spice rule");
+    if (!e->have_agents || n != e->n_uploaded) return set_err(e, SS_ERR_STATE, "ss_upload_agents_spice: n differs from the uploaded agents");
+    CK(cudaSetDevice(e->device));
+    std::vector<int32_t> order((size_t)std::max(n, 1));
+    if (n) CK(cudaMemcpy(order.data(), e->w.order, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    std::vector<double> a(e->slot_capacity, 0.0), b(e->slot_capacity, 0.0);
+    std::vector<int32_t> m(e->slot_capacity, 0);
+    for (int i = 0; i < n; i++) {
+        if (spice_metab[i] < 1 || spice_metab[i] > 65535) return set_err(e, SS_ERR_ARG, "spice metabolism out of range [1,65535]");
+        const size_t s = (size_t)order[i];
+        a[s] = spice[i]; b[s] = endowment ? endowment[i] : spice[i]; m[s] = spice_metab[i];
+    }
+    CK(cudaMemcpy(e->sw.aspice, a.data(), sizeof(double) * a.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->sw.sp_endow, b.data(), sizeof(double) * b.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->sw.asp_metab, m.data(), sizeof(int32_t) * m.size(), cudaMemcpyHostToDevice));
+    e->have_spice = true;
+    return SS_OK;
+}
+// ... in View.agents order (ss_agent_count entries)
+extern "C" int ss_download_agents_spice(ss_engine* e, int32_t* spice_metab, double* spice, double* endowment) {
+    if (!e) return set_err(e, SS_ERR_ARG, "null argument");
+    if (!e->have_spice) return set_err(e, SS_ERR_STATE, "no spice columns uploaded");
+    CK(cudaSetDevice(e->device));
+    int32_t cnt = 0;
+    CK(cudaMemcpy(&cnt, e->w.n_order, sizeof cnt, cudaMemcpyDeviceToHost));
+    const size_t ns = e->w.n_slots;
+    std::vector<int32_t> order((size_t)std::max(cnt, 1)), m(ns);
+    std::vector<double> a(ns), b(ns);
+    if (cnt) CK(cudaMemcpy(order.data(), e->w.order, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(a.data(), e->sw.aspice, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), e->sw.sp_endow, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(m.data(), e->sw.asp_metab, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; i++) {
+        const size_t s = (size_t)order[i];
+        if (spice_metab) spice_metab[i] = m[s];
+        if (spice) spice[i] = a[s];
+        if (endowment) endowment[i] = b[s];
+    }
     return SS_OK;
 }
 
@@ -1048,6 +1143,16 @@ static int life_grow(ss_engine* e, uint32_t cap) {
     CK(cudaMemcpyAsync(order, e->w.order, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaMemcpyAsync(rec, e->lw.rec, sizeof(LifeRec) * old, cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (e->cfg.rule_spice) {
+        double *a = nullptr, *b = nullptr; int32_t* m = nullptr;
+        CK(cudaMalloc(&a, sizeof(double) * cap)); CK(cudaMalloc(&b, sizeof(double) * cap)); CK(cudaMalloc(&m, sizeof(int32_t) * cap));
+        CK(cudaMemset(a, 0, sizeof(double) * cap)); CK(cudaMemset(b, 0, sizeof(double) * cap)); CK(cudaMemset(m, 0, sizeof(int32_t) * cap));
+        CK(cudaMemcpy(a, e->sw.aspice, sizeof(double) * old, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(b, e->sw.sp_endow, sizeof(double) * old, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(m, e->sw.asp_metab, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice));
+        cudaFree(e->sw.aspice); cudaFree(e->sw.sp_endow); cudaFree(e->sw.asp_metab);
+        e->sw.aspice = a; e->sw.sp_endow = b; e->sw.asp_metab = m;
+    }
     cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.wealth); cudaFree(e->w.sortkeys); cudaFree(e->lw.rec);
     e->w.agents = agents; e->w.order = order; e->w.wealth = wealth; e->w.sortkeys = sortkeys; e->lw.rec = rec;
     e->slot_capacity = cap; e->lw.capacity = (int32_t)cap;
@@ -1098,12 +1203,13 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
         if (!e->have_life) return set_err(e, SS_ERR_STATE, "limitedLifespan / procreate: ss_upload_agents_life after ss_upload_agents");
         CK(cudaMemsetAsync(e->lw.n_events, 0, sizeof(int32_t), e->stream));
     }
+    if (e->cfg.rule_spice && !e->have_spice) return set_err(e, SS_ERR_STATE, "spice: ss_upload_cells_spice and ss_upload_agents_spice before stepping");
     const LifeWorld no_life{};
     if (e->path == PATH_SERIAL_FUSED) {
         KTimer t(e, KT_SERIAL);
         int done = 0;
         while (done < nsteps) {
-            CK(ss_launch_serial(e->w, life ? e->lw : no_life, e->iteration, e->env_time, nsteps - done, 1, done, e->stream));
+            CK(ss_launch_serial(e->w, life ? e->lw : no_life, e->sw, e->iteration, e->env_time, nsteps - done, 1, done, e->stream));
             e->launches++;
             int k = nsteps - done;
             if (life) { rc = life_after_launch(e, &k); if (rc) { e->path = -1; return rc; } }
@@ -1116,7 +1222,7 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
                 {
                     KTimer tm(e, KT_SERIAL);
                     for (int k = 0; k == 0;) {
-                        CK(ss_launch_serial(e->w, life ? e->lw : no_life, e->iteration, e->env_time, 1, 0, t, e->stream));
+                        CK(ss_launch_serial(e->w, life ? e->lw : no_life, e->sw, e->iteration, e->env_time, 1, 0, t, e->stream));
                         e->launches++;
                         k = 1;
                         if (life) { rc = life_after_launch(e, &k); if (rc) { e->path = -1; return rc; } }
@@ -1131,6 +1237,12 @@ extern "C" int ss_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
         }
     }
     e->stepped = true;
+    if (e->cfg.rule_spice) {            // an operand the restated pow has no answer for would have made the welfare NaN: never silently
+        int32_t pf = 0;
+        CK(cudaMemcpyAsync(&pf, e->sw.pow_faults, sizeof pf, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (pf) { e->path = -1; return set_err(e, SS_ERR_STATE, "welfare: a pow operand outside the restated libm path (state unusable)"); }
+    }
     { const int rcj = env_join(e); if (rcj) return rcj; }
     CK(cudaEventRecord(e->eve, e->stream));
     if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, e->stream));

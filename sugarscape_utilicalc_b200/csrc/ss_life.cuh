@@ -22,3 +22,14 @@ struct LifeWorld {
     int32_t* status;            // [0] timesteps this launch completed (it stops before a step the store may not hold),
                                 // [1] faults: a birth found the store or the event buffer full (must stay 0)
 };
+
+// the spice rule's state (serial path).  Environment.grid slots [1] spice and [3] spice capacity; Agent.spice,
+// spiceMetabolism, spiceEndowment (= spiceCostForMating) by slot.
+struct SpiceWorld {
+    double* spice;              // cells; null when the rule is off
+    double* spice_cap;
+    double* aspice;             // by slot (same capacity as the agent store)
+    double* sp_endow;
+    int32_t* asp_metab;
+    int32_t* pow_faults;        // operands the restated pow had no answer for (must stay 0)
+};

@@ -15,6 +15,8 @@
 // for the order sort (keyed mode), the Gini sort and the environment phase.
 #include "ss_world.cuh"
 #include "ss_life.cuh"
+#define SS_POW_TABLE_QUAL __device__ const
+#include "ss_pow.h"          // x ** y of the reference, bit for bit
 
 #define SERIAL_THREADS 256
 #define FULL 0xffffffffu
@@ -31,7 +33,7 @@ struct SerialShared {
     double nb_inten[SS_MAXC];
     double nb_metab[SS_MAXC];
     int32_t nb_x[SS_MAXC], nb_y[SS_MAXC], nb_v[SS_MAXC];
-    double sum_m, sum_v;
+    double sum_m, sum_m2, sum_v;
     int nw, kept, acted, deaths;
 };
 
@@ -184,6 +186,69 @@ __device__ static void warp_move(const DevWorld& w, SerialShared& sh, int s, int
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------
+// agent.py:794-865 move(), spice branch (833-853) with the Cobb-Douglas welfare of agent.py:1220-1251 (no tags, no
+// foresight): w1 ** (m1 / mt) * w2 ** (m2 / mt) in the wealth the agent would have on the cell -- `if x and y:` (Q9): a cell on
+// row 0 or column 0 does not count its resources.  The arg-max compares these floats, so x ** y is the reference's libm pow
+// bit for bit (ss_pow.h); float_pow answers y == 0 and x == 1 itself.  One lane per candidate.
+__device__ static inline double spice_pow(const SpiceWorld& sw, double x, double y) {
+    if (y == 0.0) return 1.0;
+    if (x == 1.0) return 1.0;
+    ss_pow_tables T;
+    T.log_hdr = SS_POW_LOG_HDR; T.log_tab = SS_POW_LOG_TAB; T.exp_hdr = SS_POW_EXP_HDR; T.exp_tab = SS_POW_EXP_TAB;
+    int bad = 0;
+    const double r = ss_pow_pos(&T, x, y, &bad);
+    if (bad) atomicAdd(sw.pow_faults, 1);
+    return r;
+}
+__device__ static void warp_move_spice(const DevWorld& w, const SpiceWorld& sw, SerialShared& sh, int s, int lane, double fl) {
+    const int n = w.n;
+    AgentRec* rec = &w.agents[s];
+    const int pos = (int)rec->pos, x = pos / n, y = pos % n, v = attr_vision(rec->attr);
+    int m = warp_scan_cross<false>(w, x, y, v, sh.food, lane);
+    if (lane == 0) { shuffle_i32(sh, sh.food, m); sh.food[m] = pos; }    // agent.py:369, 806
+    m += 1;
+    __syncwarp();
+    const double own1 = rec->sugar, own2 = sw.aspice[s];
+    const int im1 = attr_metab(rec->attr), im2 = sw.asp_metab[s];
+    const double e1 = (double)im1 / (double)(im1 + im2), e2 = (double)im2 / (double)(im1 + im2);
+    Best best; best.p = -1; best.key = 0; best.d = 0; best.c = 0; best.sg = 0;
+    for (int p = lane; p < m; p += 32) {
+        Best b;
+        b.c = sh.food[p]; b.p = p; b.sg = 0;
+        const int cx = b.c / n, cy = b.c % n;
+        double w1 = own1, w2 = own2;
+        if (cx != 0 && cy != 0) { w1 = w1 + (double)(int)w.sugar[b.c]; w2 = w2 + (double)(int)sw.spice[b.c]; }
+        b.key = (w1 > 0.0 && w2 > 0.0) ? spice_pow(sw, w1, e1) * spice_pow(sw, w2, e2) : 0.0;
+        b.d = abs(x - cx) + abs(y - cy);                               // agent.py:867-868
+        if (better(b, best)) best = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best b;
+        b.key = __shfl_xor_sync(FULL, best.key, o);
+        b.d = __shfl_xor_sync(FULL, best.d, o);
+        b.p = __shfl_xor_sync(FULL, best.p, o);
+        b.c = __shfl_xor_sync(FULL, best.c, o);
+        b.sg = 0;
+        if (better(b, best)) best = b;
+    }
+    if (lane == 0) {
+        const int sg = (int)w.sugar[best.c], sp = (int)sw.spice[best.c];
+        sw.aspice[s] = set_sugar_floor(ss_max0(sw.aspice[s] + (double)sp), fl);            // agent.py:851
+        rec->sugar = set_sugar_floor(ss_max0(rec->sugar + (double)sg), fl);                // agent.py:852
+        if (best.c != pos) {
+            const uint32_t ow = w.occw[pos];
+            w.occw[pos] = 0u;
+            w.occw[best.c] = ow;
+            rec->pos = (uint32_t)best.c;
+        }
+        w.sugar[best.c] = 0.0;                                                              // agent.py:864-865
+        sw.spice[best.c] = 0.0;
+    }
+    __syncwarp();
+}
+
 // agent.py:1025-1141 utilicalcMove(), sugar-only (utilicalcSugar agent.py:980-992)
 __device__ static void warp_utilicalc(const DevWorld& w, SerialShared& sh, int s, int lane) {
     const int n = w.n;
@@ -258,9 +323,10 @@ __device__ static void warp_utilicalc(const DevWorld& w, SerialShared& sh, int s
 // procreation (sugarscape.py:543-554; agent.py:653-679 mate, 681-696 findFreeLocationAround, 698-750 createChild,
 // 764-773 isFertile, 373-389 getNeighbourhood).  At most four neighbours: lane 0 does all of it, every draw on the MT19937 stream
 // in the reference's order.
-__device__ static inline bool life_fertile(const DevWorld& w, const LifeWorld& lw, int s) {
+__device__ static inline bool life_fertile(const DevWorld& w, const LifeWorld& lw, const SpiceWorld& sw, int s) {
     const LifeRec& r = lw.rec[s];
-    return r.fert_lo <= r.age && r.age <= r.fert_hi && w.agents[s].sugar >= r.endow;
+    return r.fert_lo <= r.age && r.age <= r.fert_hi && w.agents[s].sugar >= r.endow &&
+           (!w.cfg.rule_spice || sw.aspice[s] >= sw.sp_endow[s]);
 }
 __device__ static int life_free_around(const DevWorld& w, SerialShared& sh, int x, int y) {
     const int n = w.n;
@@ -284,7 +350,8 @@ __device__ static inline void life_event(const LifeWorld& lw, int step, int kind
     *lw.n_events = at + 1;
 }
 // returns the new length of the list (the child joins its end and is met by the running loop in this very step)
-__device__ static int life_procreate(const DevWorld& w, const LifeWorld& lw, SerialShared& sh, int s, int n_order, int step, double fl) {
+__device__ static int life_procreate(const DevWorld& w, const LifeWorld& lw, const SpiceWorld& sw, SerialShared& sh, int s, int n_order,
+                                     int step, double fl) {
     const int n = w.n;
     const int pos = (int)w.agents[s].pos, x = pos / n, y = pos % n;
     int32_t nb[4];
@@ -302,18 +369,26 @@ __device__ static int life_procreate(const DevWorld& w, const LifeWorld& lw, Ser
     shuffle_i32(sh, nb, m);
     for (int k = 0; k < m; k++) {
         const int b = nb[k];
-        if (lw.rec[b].sex == lw.rec[s].sex || !life_fertile(w, lw, b)) continue;
+        if (lw.rec[b].sex == lw.rec[s].sex || !life_fertile(w, lw, sw, b)) continue;
         int loc = life_free_around(w, sh, x, y);
         if (loc < 0) { const int pb = (int)w.agents[b].pos; loc = life_free_around(w, sh, pb / n, pb % n); }
-        if (loc < 0 || !life_fertile(w, lw, s)) continue;
+        if (loc < 0 || !life_fertile(w, lw, sw, s)) continue;
         // createChild: genitors = [self, partner]
         const int g[2] = {s, b};
         const int metab = attr_metab(w.agents[g[randbelow(sh, 2u)]].attr);
-        (void)randbelow(sh, 2u);                                          // spiceMetabolism
+        const int gsp = g[randbelow(sh, 2u)];                              // spiceMetabolism (drawn with or without the spice rule)
         const int vision = attr_vision(w.agents[g[randbelow(sh, 2u)]].attr);
         const double endow = 0.5 * (lw.rec[s].endow + lw.rec[b].endow);
         w.agents[s].sugar = set_sugar_floor(ss_max0(w.agents[s].sugar - 0.5 * lw.rec[s].endow), fl);
         w.agents[b].sugar = set_sugar_floor(ss_max0(w.agents[b].sugar - 0.5 * lw.rec[b].endow), fl);
+        int sp_metab = 0;
+        double sp_endow = 0.0;
+        if (w.cfg.rule_spice) {                                           // agent.py:712-714
+            sp_metab = sw.asp_metab[gsp];
+            sp_endow = 0.5 * (sw.sp_endow[s] + sw.sp_endow[b]);
+            sw.aspice[s] = set_sugar_floor(ss_max0(sw.aspice[s] - 0.5 * sw.sp_endow[s]), fl);
+            sw.aspice[b] = set_sugar_floor(ss_max0(sw.aspice[b] - 0.5 * sw.sp_endow[b]), fl);
+        }
         const int max_age = lw.rec[g[randbelow(sh, 2u)]].max_age;
         const int sex = (int)randbelow(sh, 2u);
         const int fg = g[randbelow(sh, 2u)];
@@ -336,6 +411,7 @@ __device__ static int life_procreate(const DevWorld& w, const LifeWorld& lw, Ser
         r.age = 0; r.max_age = max_age; r.sex = sex; r.fert_lo = lw.rec[fg].fert_lo; r.fert_hi = lw.rec[fg].fert_hi;
         r.tags = tags; r.living = 1; r.pad = 0; r.endow = endow;
         lw.rec[c] = r;
+        if (w.cfg.rule_spice) { sw.asp_metab[c] = sp_metab; sw.sp_endow[c] = sp_endow; sw.aspice[c] = set_sugar_floor(sp_endow, fl); }
         w.occw[loc] = occ_pack((uint32_t)c, vision, 0u);
         w.order[n_order++] = c;                                           // sugarscape.py:550
         life_event(lw, step, 1, s + 1, b + 1, c + 1);
@@ -344,16 +420,20 @@ __device__ static int life_procreate(const DevWorld& w, const LifeWorld& lw, Ser
 }
 
 // ---------------------------------------------------------------- environment phase (CTA) ----
-__device__ static inline void grow_cell(const DevWorld& w, int c, double alpha) {      // environment.py:133-139
+__device__ static inline void grow_cell(const DevWorld& w, const SpiceWorld& sw, int c, double alpha) {      // environment.py:133-142
     double v = w.sugar[c] + alpha;
     double cp = w.cap[c];
     w.sugar[c] = v <= cp ? v : cp;
+    if (sw.spice) {
+        const double u = sw.spice[c] + alpha, cs = sw.spice_cap[c];
+        sw.spice[c] = u <= cs ? u : cs;
+    }
 }
 __device__ static inline bool in_region(const int32_t r[4], int n, int x, int y) {     // environment.py:146-155
     int imin = max(r[0], 0), jmin = max(r[1], 0), imax = min(r[2] + 1, n), jmax = min(r[3] + 1, n);
     return x >= imin && x < imax && y >= jmin && y < jmax;
 }
-__device__ static void cta_environment(const DevWorld& w, int64_t iteration) {
+__device__ static void cta_environment(const DevWorld& w, const SpiceWorld& sw, int64_t iteration) {
     const int n = w.n, cells = n * n;
     if (w.cfg.rule_seasons) {                                             // sugarscape.py:642-655
         if (w.cfg.rule_grow) {
@@ -362,12 +442,12 @@ __device__ static void cta_environment(const DevWorld& w, int64_t iteration) {
             double as = summer ? w.cfg.season_off_factor : w.cfg.season_on_factor;
             for (int c = threadIdx.x; c < cells; c += blockDim.x) {
                 int x = c / n, y = c % n;
-                if (in_region(w.cfg.season_north, n, x, y)) grow_cell(w, c, an);
-                if (in_region(w.cfg.season_south, n, x, y)) grow_cell(w, c, as);
+                if (in_region(w.cfg.season_north, n, x, y)) grow_cell(w, sw, c, an);
+                if (in_region(w.cfg.season_south, n, x, y)) grow_cell(w, sw, c, as);
             }
         }
     } else if (w.cfg.rule_grow) {                                         // sugarscape.py:657-659
-        for (int c = threadIdx.x; c < cells; c += blockDim.x) grow_cell(w, c, w.cfg.grow_factor);
+        for (int c = threadIdx.x; c < cells; c += blockDim.x) grow_cell(w, sw, c, w.cfg.grow_factor);
     }
     __syncthreads();
     // sugarscape.py:661-663 + environment.py:317-350: in-place sweep == anti-diagonal wavefront
@@ -393,7 +473,7 @@ __device__ static void cta_environment(const DevWorld& w, int64_t iteration) {
 
 // ------------------------------------------------------------------------------ kernel ----
 __global__ void __launch_bounds__(SERIAL_THREADS, 1)
-ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0, int nsteps, int fused_env, int stats_base) {
+ss_serial_kernel(DevWorld w, LifeWorld lw, SpiceWorld sw, int64_t iteration0, int64_t env_time0, int nsteps, int fused_env, int stats_base) {
     __shared__ SerialShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 624; i += blockDim.x) sh.mt[i] = w.mt[i];
@@ -427,7 +507,7 @@ ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0
             for (int i = tid; i < n_order; i += blockDim.x) w.order[i] = (int32_t)(w.sortkeys[i] & 0xffffffffu);
         }
         (void)dummy;
-        if (tid == 0) { sh.sum_m = 0.0; sh.sum_v = 0.0; sh.nw = 0; sh.kept = 0; sh.acted = 0; sh.deaths = 0; }
+        if (tid == 0) { sh.sum_m = 0.0; sh.sum_m2 = 0.0; sh.sum_v = 0.0; sh.nw = 0; sh.kept = 0; sh.acted = 0; sh.deaths = 0; }
         __syncthreads();
         // ---- agent loop, sugarscape.py:520-601 (warp 0) ----
         if (warp == 0) {
@@ -445,10 +525,13 @@ ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0
                     sh.j = 0;
                 }
                 __syncwarp();
-                if (w.cfg.rule_move_eat) warp_move(w, sh, s, env_time, lane, fl);
+                if (w.cfg.rule_move_eat) {
+                    if (w.cfg.rule_spice) warp_move_spice(w, sw, sh, s, lane, fl);
+                    else warp_move(w, sh, s, env_time, lane, fl);
+                }
                 if (w.cfg.rule_utilicalc) warp_utilicalc(w, sh, s, lane);
                 if (life && w.cfg.rule_procreate) {                                  // sugarscape.py:543-554
-                    if (lane == 0 && life_fertile(w, lw, s)) n_order = life_procreate(w, lw, sh, s, n_order, stats_base + step, fl);
+                    if (lane == 0 && life_fertile(w, lw, sw, s)) n_order = life_procreate(w, lw, sw, sh, s, n_order, stats_base + step, fl);
                     n_order = __shfl_sync(FULL, n_order, 0);
                 }
                 int died = 0;
@@ -460,10 +543,18 @@ ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0
                     rec->sugar = set_sugar_floor(ss_max0(rec->sugar - (double)metab), fl);   // sugarscape.py:569
                     sh.sum_m += (double)metab;
                     sh.sum_v += (double)attr_vision(rec->attr);
-                    w.wealth[sh.nw++] = rec->sugar;
+                    double wealth = rec->sugar;
+                    if (w.cfg.rule_spice) {                                           // sugarscape.py:571-572, 576-583
+                        const int m2 = sw.asp_metab[s];
+                        sw.aspice[s] = set_sugar_floor(ss_max0(sw.aspice[s] - (double)m2), fl);
+                        sh.sum_m2 += (double)m2;
+                        wealth = rec->sugar + sw.aspice[s];
+                    }
+                    w.wealth[sh.nw++] = wealth;
                     sh.acted++;
                     bool living = life ? lw.rec[s].living != 0 : true;              // Agent.alive (0: reached maxAge last step)
                     if (w.cfg.rule_can_starve && rec->sugar <= 0.1) living = false;   // sugarscape.py:306-309
+                    if (w.cfg.rule_can_starve && w.cfg.rule_spice && sw.aspice[s] <= 0.1) living = false;    // sugarscape.py:311-314
                     if (living && w.cfg.rule_limited_lifespan) {                      // sugarscape.py:588-591, agent.py:636-639
                         LifeRec& lr = lw.rec[s];
                         lr.age++;
@@ -498,7 +589,8 @@ ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0
             if (tid == 0) {
                 ss_step_stats st;
                 st.population = (double)kept;
-                st.metabolism_mean = kept > 0 ? sh.sum_m / (double)kept : 0.0;
+                st.metabolism_mean = kept > 0 ? (w.cfg.rule_spice ? ((sh.sum_m + sh.sum_m2) / 2.0) / (double)kept    // sugarscape.py:608-612
+                                                                   : sh.sum_m / (double)kept) : 0.0;
                 st.vision_mean = kept > 0 ? sh.sum_v / (double)kept : 0.0;
                 double height = 0.0, area = 0.0;
                 for (int i = 0; i < nw; i++) {
@@ -515,7 +607,7 @@ ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0
             }
         }
         __syncthreads();
-        if (fused_env) cta_environment(w, iteration);
+        if (fused_env) cta_environment(w, sw, iteration);
         __syncthreads();
     }
     for (int i = tid; i < 624; i += blockDim.x) w.mt[i] = sh.mt[i];
@@ -523,9 +615,9 @@ ss_serial_kernel(DevWorld w, LifeWorld lw, int64_t iteration0, int64_t env_time0
     if (life && tid == 0) lw.status[0] = step;
 }
 
-extern "C" cudaError_t ss_launch_serial(const DevWorld& w, const LifeWorld& lw, int64_t iteration, int64_t env_time, int nsteps,
-                                        int fused_env, int stats_base, cudaStream_t stream) {
-    ss_serial_kernel<<<1, SERIAL_THREADS, 0, stream>>>(w, lw, iteration, env_time, nsteps, fused_env, stats_base);
+extern "C" cudaError_t ss_launch_serial(const DevWorld& w, const LifeWorld& lw, const SpiceWorld& sw, int64_t iteration, int64_t env_time,
+                                        int nsteps, int fused_env, int stats_base, cudaStream_t stream) {
+    ss_serial_kernel<<<1, SERIAL_THREADS, 0, stream>>>(w, lw, sw, iteration, env_time, nsteps, fused_env, stats_base);
     return cudaGetLastError();
 }
 

@@ -213,6 +213,34 @@ class Engine:
             self._check(self._lib.ss_get_events(self._h, cnt.value, _ptr(out)), "ss_get_events")
         return out
 
+    # -- spice --------------------------------------------------------------------
+    def upload_cells_spice(self, spice, spice_cap):
+        """Environment.grid slots [1] spice and [3] spice capacity, (N,N) like the sugar arrays."""
+        a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (spice, spice_cap))
+        if a.size != self.n * self.n or b.size != self.n * self.n:
+            raise ValueError("cell arrays must be (N,N)")
+        self._check(self._lib.ss_upload_cells_spice(self._h, _ptr(a), _ptr(b)), "ss_upload_cells_spice")
+
+    def download_cells_spice(self):
+        a, b = np.empty((self.n, self.n)), np.empty((self.n, self.n))
+        self._check(self._lib.ss_download_cells_spice(self._h, _ptr(a), _ptr(b)), "ss_download_cells_spice")
+        return dict(spice=a, spice_cap=b)
+
+    def upload_agents_spice(self, spice_metab, spice, endowment=None):
+        """Agent.spiceMetabolism / spice / spiceEndowment of the agents of the last upload_agents, same order."""
+        m = np.ascontiguousarray(spice_metab, dtype=np.int32)
+        sp = np.ascontiguousarray(spice, dtype=np.float64)
+        en = None if endowment is None else np.ascontiguousarray(endowment, dtype=np.float64)
+        if len(m) != len(sp) or (en is not None and len(en) != len(m)):
+            raise ValueError("spice columns must have equal length")
+        self._check(self._lib.ss_upload_agents_spice(self._h, len(m), _ptr(m), _ptr(sp), _ptr(en)), "ss_upload_agents_spice")
+
+    def download_agents_spice(self):
+        k = self.agent_count()
+        m, sp, en = np.empty(k, dtype=np.int32), np.empty(k), np.empty(k)
+        self._check(self._lib.ss_download_agents_spice(self._h, _ptr(m), _ptr(sp), _ptr(en)), "ss_download_agents_spice")
+        return dict(spice_metab=m, spice=sp, spice_endowment=en)
+
     # -- instrumentation -------------------------------------------------------------------
     def counters(self):
         out = np.zeros(6, dtype=np.int64)

@@ -22,6 +22,7 @@ GOLDEN_CASES = [
 
 LIFE_CASES = ["f3_evolution_metabolism_mt", "f3_procreate_only_mt"]      # SURVEY 8 f3, recorded by make_golden.py f3
 LIFE_COLUMNS = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
+SPICE_CASES = ["f2_spice_mt", "f2_spice_life_mt"]                         # SURVEY 8 f2, recorded by make_golden.py f2
 
 
 def load_golden(name):
@@ -50,6 +51,10 @@ def engine_world(cfg, path=-1, options=None):
 def init_world(world, init, rng, mt=None, mt_index=None):
     world.upload_cells(init["sugar"], init["cap"], init["pollution"])
     world.upload_agents(init["id"], init["x"], init["y"], init["vision"], init["metab"], init["sugar_agent"])
+    if init.get("spice") is not None:
+        sp = init["spice"]
+        world.upload_cells_spice(sp["spice"], sp["spice_cap"])
+        world.upload_agents_spice(sp["spice_metab"], sp["spice_agent"], sp["spice_endowment"])
     if init.get("life") is not None:
         world.upload_agents_life(init["id_increment"], **init["life"])
     if rng == "mt":
@@ -63,6 +68,8 @@ def golden_init(g):
     if "init_life_age" in g:
         init["life"] = {k: g["init_life_" + k] for k in LIFE_COLUMNS}
         init["id_increment"] = int(g["init_id_increment"])
+    if "init_spice" in g:
+        init["spice"] = {k: g["init_" + k] for k in ("spice", "spice_cap", "spice_metab", "spice_agent", "spice_endowment")}
     return init
 
 
@@ -118,6 +125,11 @@ def run_against_golden(g, world, exact_gini=True, chunk=None, max_steps=None):
         exp = {k2: g["cp%d_%s" % (cp, k2)] for k2 in ("sugar", "pollution", "occ", "order", "x", "y", "sugar_agent")}
         ags = world.download_agents()
         assert_state_equal(world.download_cells(), ags, exp, ordered=True, what="step %d" % cp)
+        if "init_spice" in g:       # the second resource on the cells and in the agents
+            assert np.array_equal(world.download_cells_spice()["spice"], g["cp%d_spice" % cp]), "step %d: cell spice differs" % cp
+            sp = world.download_agents_spice()
+            assert np.array_equal(sp["spice"], g["cp%d_spice_agent" % cp]), "step %d: agent spice differs" % cp
+            assert np.array_equal(sp["spice_metab"], g["cp%d_spice_metab" % cp]) and np.array_equal(sp["spice_endowment"], g["cp%d_spice_endowment" % cp])
         if life:            # the fields the lifespan / procreation rules carry, and the event lines so far
             lf = world.download_agents_life()
             for c in LIFE_COLUMNS:

@@ -35,7 +35,11 @@ def pos_digest(snap):
 LIFE = ("age", "max_age", "sex", "fert_lo", "fert_hi", "endowment", "tags", "alive")
 
 
-def record(name, settings, steps, rng, world=None, life=False):
+SPICE_CELLS = ("spice", "spice_cap")
+SPICE_AGENTS = ("spice_metab", "spice_agent", "spice_endowment")
+
+
+def record(name, settings, steps, rng, world=None, life=False, spice=False):
     r = rh.ReferenceRun(settings, rng=rng, world=world)
     out = {"settings_json": json.dumps(settings), "rng": rng, "steps": steps}
     s0 = r.snapshot()
@@ -46,6 +50,9 @@ def record(name, settings, steps, rng, world=None, life=False):
         for k in LIFE:
             out["init_life_" + k] = s0[k]
         out["init_id_increment"] = s0["id_increment"]
+    if spice:
+        for k in SPICE_CELLS + SPICE_AGENTS:
+            out["init_" + k] = s0[k]
     dig = np.zeros((steps, 5), dtype=np.float64)  # sum agent sugar, sum cell sugar, sum pollution, pos crc, mt idx
     for t in range(steps):
         r.step()
@@ -55,6 +62,9 @@ def record(name, settings, steps, rng, world=None, life=False):
         if (t + 1) in CHECKPOINTS or t + 1 == steps:
             for k in ("sugar", "pollution", "occ", "order", "x", "y", "sugar_agent"):
                 out["cp%d_%s" % (t + 1, k)] = sn[k]
+            if spice:
+                for k in ("spice",) + SPICE_AGENTS:
+                    out["cp%d_%s" % (t + 1, k)] = sn[k]
             if life:
                 for k in LIFE + ("vision", "metab"):
                     out["cp%d_life_%s" % (t + 1, k)] = sn[k]
@@ -85,9 +95,22 @@ def main_life():
     record("f3_procreate_only_mt", s, 120, "mt", life=True)
 
 
+def main_spice():
+    """examples/trade_price_volume without the trade rule (grow + moveEat + canStarve + spice), and
+    examples/readme_example without trade (+ limitedLifespan + procreate)."""
+    s = rh.load_settings("trade_price_volume")
+    s["rules"]["trade"] = False
+    record("f2_spice_mt", s, 300, "mt", spice=True)
+    s = rh.load_settings("readme_example")
+    s["rules"]["trade"] = False
+    record("f2_spice_life_mt", s, 120, "mt", life=True, spice=True)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "f3":
         return main_life()
+    if len(sys.argv) > 1 and sys.argv[1] == "f2":
+        return main_spice()
     default = rh.load_settings()
     move_eat = rh.load_settings()
     move_eat["rules"]["moveEat"], move_eat["rules"]["utilicalc"] = True, False
@@ -110,6 +133,7 @@ def main():
         s = synthetic.synthetic_settings(n, pollution=pol)
         record("c4_synth%d_%s_keyed" % (n, "poll" if pol else "nopoll"), s, steps, "keyed", world=w)
     main_life()
+    main_spice()
 
 
 if __name__ == "__main__":

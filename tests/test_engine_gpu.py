@@ -70,6 +70,33 @@ def test_lifespan_and_procreation_single_steps_and_store_growth():
     o.close()
 
 
+@pytest.mark.parametrize("name", common.SPICE_CASES)
+def test_spice_matches_reference_golden(name):
+    """SURVEY 8 f2 on the GPU (ss_serial_kernel): examples/trade_price_volume and examples/readme_example without the trade
+    rule, against the goldens recorded from the unmodified reference -- spice on the cells and in the agents, the arg-max of the
+    Cobb-Douglas welfare with the reference's libm pow restated bit for bit (csrc/ss_pow.h), spice metabolism / starvation,
+    statistics, and with the life rules createChild / isFertile in both resources; final MT19937 state."""
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "engine")
+    assert w.counters()["path"] == 0
+    assert common.run_against_golden(g, w, exact_gini=True) == g["steps"]
+    w.close()
+
+
+def test_spice_single_steps_and_missing_uploads():
+    from sugarscape_utilicalc_b200.engine import EngineError
+    g = common.load_golden("f2_spice_mt")
+    w = common.world_from_golden(g, "engine")
+    common.run_against_golden(g, w, exact_gini=True, chunk=1, max_steps=50)
+    w.close()
+    cfg = config_from_settings(g["settings"], rng_mode="mt")
+    e = common.engine_world(cfg)
+    common.init_world(e, dict(common.golden_init(g), spice=None), "mt", g["init_mt"], int(g["init_mt_index"]))
+    with pytest.raises(EngineError):
+        e.step(1)                                           # ss_upload_agents_spice first
+    e.close()
+
+
 def test_life_rules_need_their_columns_and_the_mt_mode():
     from sugarscape_utilicalc_b200.engine import EngineError
     g = common.load_golden("f3_evolution_metabolism_mt")

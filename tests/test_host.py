@@ -47,11 +47,19 @@ def test_rule_check_matches_reference_order_and_messages():
 
 
 def test_out_of_scope_rules_are_refused_loudly():
-    for r in ("tags", "replacement", "transmit", "spice", "disease"):
+    for r in ("tags", "replacement", "transmit", "disease"):
         s = _settings()
         s["rules"][r] = True
         with pytest.raises((UnsupportedRuleError, ConflictingRuleException, MissingRuleException)):
             config_from_settings(s)
+    # spice runs with rule M (with utilicalc the reference crashes: KeyError 'proximity')
+    s = _settings()
+    s["rules"]["spice"] = True
+    if s["rules"]["utilicalc"]:
+        with pytest.raises(UnsupportedRuleError):
+            config_from_settings(s)
+    s["rules"]["moveEat"], s["rules"]["utilicalc"] = True, False
+    assert config_from_settings(s, rng_mode="mt").rule_spice == 1
     # limitedLifespan / procreate run with rule M in the MT19937-exact mode -- and nowhere else
     for r in ("limitedLifespan", "procreate"):
         s = _settings()

@@ -24,6 +24,38 @@ def test_oracle_lifespan_and_procreation_match_reference_golden(name):
     w.close()
 
 
+@pytest.mark.parametrize("name", common.SPICE_CASES)
+def test_oracle_spice_matches_reference_golden(name):
+    """examples/trade_price_volume and examples/readme_example without the trade rule -- spice on the cells and
+    in the agents, the Cobb-Douglas welfare of move() (w1 ** (m1/mt) * w2 ** (m2/mt), compared for the arg-max: x ** y is the
+    reference's libm pow bit for bit, csrc/ss_pow.h), spice metabolism and starvation, statistics -- step by step against
+    the unmodified reference."""
+    g = common.load_golden(name)
+    w = common.world_from_golden(g, "oracle")
+    assert common.run_against_golden(g, w, exact_gini=True, chunk=5) == g["steps"]
+    assert w.pow_faults() == 0
+    w.close()
+
+
+def test_pow_restatement_equals_libm_and_python():
+    """csrc/ss_pow.h (glibc 2.39 __pow_fma restated from its disassembly, tables read out of libm) against this machine's
+    libm pow() -- which is what CPython's float ** float calls -- on random operands of the welfare domain."""
+    import ctypes
+    import math
+    import random
+    import subprocess
+    import os
+    d = os.path.join(common.ROOT, "oracle", "pow_glibc")
+    exe = os.path.join(d, "test_pow")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(d, "test_pow.c"), "-lm"])
+    out = subprocess.check_output([exe, "2000000"]).decode()
+    assert out.strip().endswith(" 0 mismatches"), out
+    rng = random.Random(5)
+    for _ in range(2000):                                   # Python's own ** is that libm pow
+        x, m1, m2 = rng.randint(1, 500) * rng.choice([1.0, 0.25]), rng.randint(1, 9), rng.randint(1, 9)
+        assert x ** (m1 / (m1 + m2)) == math.pow(x, m1 / (m1 + m2))
+
+
 def test_oracle_chunked_steps_equal_single_steps():
     g = common.load_golden("c2_pollution_mt")
     w = common.world_from_golden(g, "oracle")
