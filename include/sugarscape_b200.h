@@ -131,6 +131,9 @@ typedef struct {
     int32_t group_tags[4];        /* `distributions`: the tags of each group (tags0, 2^tags_length - 1; sugarscape.py:104-105,
                                      142-148) -- kept with limitedLifespan / procreate, where ss_init_world also
                                      leaves the engine as after ss_upload_agents_life (age 0, maxAge, sex, fertility drawn) */
+    int32_t n_spice_sites;        /* rules.spice: addSpiceSite(southeast), (northwest) (sugarscape.py:1508-1513);   */
+    int32_t spice_site_x[4], spice_site_y[4], spice_site_radius[4];   /* each agent then also draws spiceMetabolism and its
+                                     spice endowment (sugarscape.py:253-255); the engine is left as after the spice uploads   */
 } ss_init_params;
 
 /* Replaces: Environment.addSugarSite x n_sites (environment.py:114-126), setMaxCapacity, env.grow(maxCapacity),

@@ -48,6 +48,7 @@ class SsInitParams(C.Structure):
         ("max_metabolism", C.c_int32), ("max_vision", C.c_int32), ("endowment_min", C.c_int32), ("endowment_max", C.c_int32),
         ("age_min", C.c_int32), ("age_max", C.c_int32), ("childbearing", (C.c_int32 * 4) * 2),
         ("foresight_lo", C.c_int32), ("foresight_hi", C.c_int32), ("group_tags", C.c_int32 * 4),
+        ("n_spice_sites", C.c_int32), ("spice_site_x", C.c_int32 * 4), ("spice_site_y", C.c_int32 * 4), ("spice_site_radius", C.c_int32 * 4),
     ]
 
 

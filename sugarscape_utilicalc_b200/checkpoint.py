@@ -29,6 +29,10 @@ def save(path, world, settings, rng, iteration, keyed_seed=None):
         lf = world.download_agents_life()
         out.update({"life_" + k: lf[k] for k in LIFE_COLUMNS})
         out["id_increment"] = np.int64(lf["id_increment"])
+    if settings["rules"].get("spice"):
+        cs, sp = world.download_cells_spice(), world.download_agents_spice()
+        out.update(spice=cs["spice"], spice_cap=cs["spice_cap"], agent_spice_metab=sp["spice_metab"], agent_spice=sp["spice"],
+                   agent_spice_endowment=sp["spice_endowment"])
     if rng == "mt":
         mt, idx = world.get_rng_mt19937()
         out["mt"], out["mt_index"] = np.asarray(mt, dtype=np.uint32), np.int64(idx)
@@ -50,6 +54,9 @@ def restore(path, world_factory=None, **factory_kwargs):
         world.set_option("global_slots", int(z["n_slots"]))
     world.upload_cells(z["sugar"], z["cap"], z["pollution"])
     world.upload_agents(z["agent_id"], z["agent_x"], z["agent_y"], z["agent_vision"], z["agent_metab"], z["agent_sugar"])
+    if "spice" in z.files:
+        world.upload_cells_spice(z["spice"], z["spice_cap"])
+        world.upload_agents_spice(z["agent_spice_metab"], z["agent_spice"], z["agent_spice_endowment"])
     if "id_increment" in z.files:
         world.upload_agents_life(int(z["id_increment"]), **{k: z["life_" + k] for k in LIFE_COLUMNS})
     if rng == "mt":

@@ -32,9 +32,9 @@ cudaError_t ss_launch_dr_after_rounds(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_dr_strip_barrier(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_isugar(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D, double max_capacity,
-                                 int grow, int sm_count, cudaStream_t stream);
+                                 int grow, int sm_count, double* cap_out, double* val_out, cudaStream_t stream);
 cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, int32_t* rowfree, int32_t* superfree, int32_t* cols,
-                                  size_t stride, double* sugar, int32_t* life_cols, int32_t* result, cudaStream_t stream);
+                                  size_t stride, double* sugar, int32_t* life_cols, int32_t* spice_cols, int32_t* result, cudaStream_t stream);
 cudaError_t ss_launch_build_agents(const DevWorld& w, int n, uint32_t phase, const int32_t* id, const int32_t* x, const int32_t* y,
                                    const int32_t* vision, const int32_t* metab, const double* sugar, int* err, cudaStream_t s);
 cudaError_t ss_launch_validate_rows(int n, const int32_t* x, int x0, int rows, int* out, cudaStream_t s);
@@ -759,7 +759,18 @@ extern "C" int ss_init_world(ss_engine* e, const ss_init_params* p) {
         D[s] = sqrt((double)(a * a + b * b)) * ((double)p->site_radius[s] / (double)N);
     }
     CK(ss_launch_init_sites(e->w, p->n_sites, p->site_x, p->site_y, D, e->cfg.max_capacity, p->grow_to_capacity, e->sm_count,
-                            e->stream));
+                            nullptr, nullptr, e->stream));
+    if (e->cfg.rule_spice) {                                                            // sugarscape.py:1508-1513
+        if (p->n_spice_sites < 0 || p->n_spice_sites > 4) return set_err(e, SS_ERR_ARG, "at most 4 spice sites");
+        double Ds[4] = {1, 1, 1, 1};
+        for (int s = 0; s < p->n_spice_sites; s++) {
+            if (p->spice_site_radius[s] <= 0) return set_err(e, SS_ERR_ARG, "site radius must be positive");
+            const long long a = std::max(p->spice_site_x[s], N - p->spice_site_x[s]), b = std::max(p->spice_site_y[s], N - p->spice_site_y[s]);
+            Ds[s] = sqrt((double)(a * a + b * b)) * ((double)p->spice_site_radius[s] / (double)N);
+        }
+        CK(ss_launch_init_sites(e->w, p->n_spice_sites, p->spice_site_x, p->spice_site_y, Ds, e->cfg.max_capacity, p->grow_to_capacity,
+                                e->sm_count, e->sw.spice_cap, e->sw.spice, e->stream));
+    }
     long long total = 0;
     for (int g = 0; g < p->n_groups; g++) {
         if (p->group_count[g] < 0) return set_err(e, SS_ERR_ARG, "negative agent count");
@@ -785,7 +796,10 @@ extern "C" int ss_init_world(ss_engine* e, const ss_init_params* p) {
     int32_t* d_life = nullptr;
     struct LifeStaging { int32_t*& p; ~LifeStaging() { cudaFree(p); } } life_staging{d_life};
     if (life) CK(cudaMalloc(&d_life, sizeof(int32_t) * 5 * nn));
-    CK(ss_launch_init_agents(e->w, p, d_scratch, d_scratch + N, d_i32, nn, d_f64, d_life, d_result, e->stream));
+    int32_t* d_spice = nullptr;                                                         // spiceMetabolism, spice endowment
+    struct SpiceStaging { int32_t*& p; ~SpiceStaging() { cudaFree(p); } } spice_staging{d_spice};
+    if (e->cfg.rule_spice) CK(cudaMalloc(&d_spice, sizeof(int32_t) * 2 * nn));
+    CK(ss_launch_init_agents(e->w, p, d_scratch, d_scratch + N, d_i32, nn, d_f64, d_life, d_spice, d_result, e->stream));
     int32_t result[2] = {0, 0};
     CK(cudaMemcpyAsync(result, d_result, sizeof result, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -798,8 +812,20 @@ extern "C" int ss_init_world(ss_engine* e, const ss_init_params* p) {
         CK(cudaMemcpy(hl.data(), d_life, sizeof(int32_t) * 5 * nn, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hs.data(), d_f64, sizeof(double) * nn, cudaMemcpyDeviceToHost));
     }
+    std::vector<int32_t> hsp;
+    if (e->cfg.rule_spice) {
+        hsp.resize(2 * nn);
+        CK(cudaMemcpy(hsp.data(), d_spice, sizeof(int32_t) * 2 * nn, cudaMemcpyDeviceToHost));
+    }
     rc = finish_agents(e, result[0], d_i32, nn, d_f64, d_chk);
-    if (rc || !life) return rc;
+    if (rc) return rc;
+    if (e->cfg.rule_spice) {
+        std::vector<double> sp((size_t)std::max(result[0], 1));
+        for (int i = 0; i < result[0]; i++) sp[(size_t)i] = (double)hsp[nn + (size_t)i];
+        rc = ss_upload_agents_spice(e, result[0], hsp.data(), sp.data(), nullptr);
+        if (rc) return rc;
+    }
+    if (!life) return rc;
     const int32_t n = result[0];
     std::vector<int32_t> age((size_t)std::max(n, 1), 0);                               // Agent.setAge: age = 0 (agent.py:236-238)
     return ss_upload_agents_life(e, n, result[1], age.data(), hl.data(), hl.data() + nn, hl.data() + 2 * nn, hl.data() + 3 * nn,

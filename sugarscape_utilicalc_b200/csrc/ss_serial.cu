@@ -633,7 +633,7 @@ struct InitSites {
     double max_capacity;
     int grow;
 };
-__global__ void ss_init_sites_kernel(DevWorld w, InitSites sp) {
+__global__ void ss_init_sites_kernel(DevWorld w, InitSites sp, double* cap_out, double* val_out, int clear_rest) {
     const int n = w.n;
     const size_t cells = (size_t)n * n;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < cells; idx += (size_t)gridDim.x * blockDim.x) {
@@ -646,11 +646,10 @@ __global__ void ss_init_sites_kernel(DevWorld w, InitSites sp) {
             c = c <= sp.max_capacity ? c : sp.max_capacity;                   // min(c, maxCapacity)
             if (c > cap) cap = c;
         }
-        w.cap[idx] = cap;
+        cap_out[idx] = cap;
         const double grown = 0.0 + sp.max_capacity;                           // environment.py:137: min(cur + alpha, cap)
-        w.sugar[idx] = sp.grow ? (grown <= cap ? grown : cap) : 0.0;
-        w.poll[idx] = 0.0;
-        w.occw[idx] = 0u;
+        val_out[idx] = sp.grow ? (grown <= cap ? grown : cap) : 0.0;
+        if (clear_rest) { w.poll[idx] = 0.0; w.occw[idx] = 0u; }
     }
 }
 
@@ -684,7 +683,7 @@ __device__ static inline int warp_select(int v, int lane, long long& k, long lon
 __global__ void __launch_bounds__(32)
 ss_init_agents_kernel(DevWorld w, InitAgents ip, int32_t* rowfree, int32_t* superfree, int32_t* id_out, int32_t* x_out,
                       int32_t* y_out, int32_t* vision_out, int32_t* metab_out, double* sugar_out, int32_t* life_out, size_t life_stride,
-                      int32_t* result) {
+                      int32_t* spice_out, int32_t* result) {
     __shared__ SerialShared sh;
     const int lane = threadIdx.x, n = w.n, n1 = n - 1, nsuper = (n1 + 31) / 32;
     for (int i = lane; i < 624; i += 32) sh.mt[i] = w.mt[i];
@@ -725,6 +724,10 @@ ss_init_agents_kernel(DevWorld w, InitAgents ip, int32_t* rowfree, int32_t* supe
                 rowfree[row]--; superfree[sr]--;
                 const int metab = 1 + (int)randbelow(sh, (uint32_t)ip.max_metabolism);            // sugarscape.py:250
                 const int endow = ip.endow_min + (int)randbelow(sh, (uint32_t)(ip.endow_max - ip.endow_min + 1));
+                if (spice_out) {                                                                  // :253-255 (rules.spice)
+                    spice_out[count] = 1 + (int)randbelow(sh, (uint32_t)ip.max_metabolism);
+                    spice_out[life_stride + count] = ip.endow_min + (int)randbelow(sh, (uint32_t)(ip.endow_max - ip.endow_min + 1));
+                }
                 const int vision = 1 + (int)randbelow(sh, (uint32_t)ip.max_vision);               // :256
                 const int max_age = ip.age_min + (int)randbelow(sh, (uint32_t)(ip.age_max - ip.age_min + 1));     // :257 setAge
                 const int sex = (int)randbelow(sh, 2u);                                           // :258
@@ -747,18 +750,20 @@ ss_init_agents_kernel(DevWorld w, InitAgents ip, int32_t* rowfree, int32_t* supe
 }
 
 extern "C" cudaError_t ss_launch_init_sites(const DevWorld& w, int n_sites, const int* sx, const int* sy, const double* D,
-                                            double max_capacity, int grow, int sm_count, cudaStream_t stream) {
+                                            double max_capacity, int grow, int sm_count, double* cap_out, double* val_out,
+                                            cudaStream_t stream) {
     InitSites sp;
     sp.n_sites = n_sites;
     for (int s = 0; s < 4; s++) { sp.sx[s] = s < n_sites ? sx[s] : 0; sp.sy[s] = s < n_sites ? sy[s] : 0; sp.D[s] = s < n_sites ? D[s] : 1.0; }
     sp.max_capacity = max_capacity; sp.grow = grow;
-    ss_init_sites_kernel<<<sm_count * 8, 256, 0, stream>>>(w, sp);
+    // (cap_out / val_out: the sugar arrays, or the spice arrays of SURVEY 8 f2)
+    ss_init_sites_kernel<<<sm_count * 8, 256, 0, stream>>>(w, sp, cap_out ? cap_out : w.cap, val_out ? val_out : w.sugar, cap_out == nullptr);
     return cudaGetLastError();
 }
 
 extern "C" cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_params* p, int32_t* rowfree, int32_t* superfree,
-                                             int32_t* cols, size_t stride, double* sugar, int32_t* life_cols, int32_t* result,
-                                             cudaStream_t stream) {
+                                             int32_t* cols, size_t stride, double* sugar, int32_t* life_cols, int32_t* spice_cols,
+                                             int32_t* result, cudaStream_t stream) {
     InitAgents ip;
     ip.n_groups = p->n_groups;
     for (int g = 0; g < 4; g++) ip.group_count[g] = g < p->n_groups ? p->group_count[g] : 0;
@@ -768,6 +773,6 @@ extern "C" cudaError_t ss_launch_init_agents(const DevWorld& w, const ss_init_pa
     ip.foresight_lo = p->foresight_lo; ip.foresight_hi = p->foresight_hi;
     for (int g = 0; g < 4; g++) ip.group_tags[g] = p->group_tags[g];
     ss_init_agents_kernel<<<1, 32, 0, stream>>>(w, ip, rowfree, superfree, cols, cols + stride, cols + 2 * stride, cols + 3 * stride,
-                                                 cols + 4 * stride, sugar, life_cols, stride, result);
+                                                 cols + 4 * stride, sugar, life_cols, stride, spice_cols, result);
     return cudaGetLastError();
 }

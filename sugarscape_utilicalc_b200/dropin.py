@@ -43,7 +43,13 @@ def _snapshot_view(view):
                   endowment=np.array([a.sugarEndowment for a in ags], dtype=np.float64),
                   tags=np.array([a.tags for a in ags], dtype=np.int32),
                   alive=np.array([1 if a.alive else 0 for a in ags], dtype=np.int32)),
-        id_increment=int(env.idIncrement))
+        id_increment=int(env.idIncrement),
+        # spice
+        spice=dict(spice=np.array([[g[i][j][1] for j in range(n)] for i in range(n)], dtype=np.float64),
+                   spice_cap=np.array([[g[i][j][3] for j in range(n)] for i in range(n)], dtype=np.float64),
+                   spice_metab=np.array([a.spiceMetabolism for a in ags], dtype=np.int32),
+                   spice_agent=np.array([a.spice for a in ags], dtype=np.float64),
+                   spice_endowment=np.array([a.spiceEndowment for a in ags], dtype=np.float64)))
 
 
 class DropinHandle:
@@ -55,6 +61,7 @@ class DropinHandle:
         self.keyed_seed = ss.seed if keyed_seed is None else keyed_seed
         self.list_ids = [a.id for a in view.agents]
         self.life = bool(ss.rules["limitedLifespan"] or ss.rules["procreate"])
+        self.spice = bool(ss.rules["spice"])
         self.n_slots = max(max(self.list_ids, default=1), int(world.n_slots()) if hasattr(world, "n_slots") else 1)
 
     def _order_before_step(self):
@@ -109,11 +116,15 @@ class DropinHandle:
         cells, ags = self.world.download_cells(), self.world.download_agents()
         n = env.gridWidth
         sugar, poll = cells["sugar"], cells["pollution"]
+        spice = self.world.download_cells_spice()["spice"] if self.spice else None
+        sp = self.world.download_agents_spice() if self.spice else None
         for i in range(n):
             row = env.grid[i]
             for j in range(n):
                 c = row[j]
                 c[0] = float(sugar[i, j])
+                if spice is not None:
+                    c[1] = float(spice[i, j])
                 c[4] = None
                 c[5] = float(poll[i, j])
         lf = self.world.download_agents_life() if self.life else None
@@ -132,6 +143,11 @@ class DropinHandle:
             a.x, a.y = int(ags["x"][k]), int(ags["y"][k])
             s = float(ags["sugar"][k])
             a.sugar = int(s) if s == int(s) else s
+            if sp is not None:
+                v2, e2 = float(sp["spice"][k]), float(sp["spice_endowment"][k])
+                a.spice = int(v2) if v2 == int(v2) else v2
+                a.spiceMetabolism = int(sp["spice_metab"][k])
+                a.spiceEndowment = a.spiceCostForMating = int(e2) if e2 == int(e2) else e2
             if lf is not None:
                 a.age, a.maxAge, a.sex = int(lf["age"][k]), int(lf["max_age"][k]), int(lf["sex"][k])
                 a.fertility = (int(lf["fert_lo"][k]), int(lf["fert_hi"][k]))
@@ -170,6 +186,10 @@ def install(ss, view, rng="mt", keyed_seed=None, world_factory=None, events=True
     s = _snapshot_view(view)
     world.upload_cells(s["sugar"], s["cap"], s["pollution"])
     world.upload_agents(s["id"], s["x"], s["y"], s["vision"], s["metab"], s["sugar_agent"])
+    if cfg.rule_spice:
+        sp = s["spice"]
+        world.upload_cells_spice(sp["spice"], sp["spice_cap"])
+        world.upload_agents_spice(sp["spice_metab"], sp["spice_agent"], sp["spice_endowment"])
     if cfg.rule_limited_lifespan or cfg.rule_procreate:
         world.upload_agents_life(s["id_increment"], **s["life"])
     if rng == "mt":

@@ -159,4 +159,9 @@ def init_params_from_settings(settings):
     p.foresight_lo, p.foresight_hi = 0, 0                               # Environment.foresightRange without the rule
     tg = settings["rule_params"]["tags"]
     p.group_tags[0], p.group_tags[1] = int(tg["tags0"]), 2 ** int(tg["tags_length"]) - 1      # sugarscape.py:104-105
+    if rules.get("spice"):                                              # sugarscape.py:1508-1513: southeast, northwest
+        sp_sites = [env["sites"]["se"], env["sites"]["nw"]]
+        p.n_spice_sites = len(sp_sites)
+        for k, s in enumerate(sp_sites):
+            p.spice_site_x[k], p.spice_site_y[k], p.spice_site_radius[k] = s["x"], s["y"], s["radius"]
     return p

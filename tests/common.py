@@ -229,7 +229,7 @@ def check_outputs_against_golden(name, kind, tmp_dir, path=-1):
 
 
 def check_checkpoint_resume(name, kind, tmp_dir, stop=7, total=15):
-    if name.startswith("f3_"):
+    if name.startswith("f3_") or name.startswith("f2_"):
         stop, total = 70, 90        # past the first births, deaths and agents at maxAge
     import numpy as np
     from sugarscape_utilicalc_b200 import checkpoint
@@ -252,6 +252,11 @@ def check_checkpoint_resume(name, kind, tmp_dir, stop=7, total=15):
         assert np.array_equal(ca[k], cc[k]), k
     for k in ("id", "x", "y", "vision", "metab", "sugar"):
         assert np.array_equal(ga[k], gc[k]), k
+    if "init_spice" in g:
+        assert np.array_equal(a.download_cells_spice()["spice"], c.download_cells_spice()["spice"])
+        sa_, sc_ = a.download_agents_spice(), c.download_agents_spice()
+        for k in ("spice_metab", "spice", "spice_endowment"):
+            assert np.array_equal(sa_[k], sc_[k]), k
     if "init_life_age" in g:
         la, lc = a.download_agents_life(), c.download_agents_life()
         for k in LIFE_COLUMNS + ("id_increment",):

@@ -118,7 +118,7 @@ def test_on_disk_outputs_match_reference_golden(name, tmp_path):
     common.check_outputs_against_golden(name, "engine", tmp_path)
 
 
-@pytest.mark.parametrize("name", MT_CASES + common.LIFE_CASES)
+@pytest.mark.parametrize("name", MT_CASES + common.LIFE_CASES + common.SPICE_CASES)
 def test_world_initialisation_on_device_equals_reference(name):
     """`random.seed(seed)` + the reference's `__main__` set-up (sugar sites, growback to capacity,
     Agent() + initAgent per agent) run on the device -- capacity / sugar fields, every agent's id, cell, vision,
@@ -138,7 +138,12 @@ def test_world_initialisation_on_device_equals_reference(name):
         assert np.array_equal(ags[key], g[gk]), key
     mt, idx = e.get_rng_mt19937()
     assert np.array_equal(mt, g["init_mt"]) and idx == int(g["init_mt_index"])
-    if name in common.LIFE_CASES:       # the drawn maxAge, sex and fertility and the groups' tags are kept
+    if name in common.SPICE_CASES:      # the spice peaks and every agent's spiceMetabolism / spice endowment
+        cs, sp = e.download_cells_spice(), e.download_agents_spice()
+        assert np.array_equal(cs["spice"], g["init_spice"]) and np.array_equal(cs["spice_cap"], g["init_spice_cap"])
+        assert np.array_equal(sp["spice_metab"], g["init_spice_metab"]) and np.array_equal(sp["spice"], g["init_spice_agent"])
+        assert np.array_equal(sp["spice_endowment"], g["init_spice_endowment"])
+    if "init_life_age" in g:            # the drawn maxAge, sex and fertility and the groups' tags are kept
         lf = e.download_agents_life()
         for c in common.LIFE_COLUMNS:
             assert np.array_equal(lf[c], g["init_life_" + c]), c
@@ -227,7 +232,7 @@ def test_world_initialisation_fills_the_lattice_and_large_grids():
     e.close()
 
 
-@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "c4_synth130_nopoll_keyed", "f3_evolution_metabolism_mt"])
+@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "c4_synth130_nopoll_keyed", "f3_evolution_metabolism_mt", "f2_spice_life_mt"])
 def test_checkpoint_resume(name, tmp_path):
     """checkpoint.save / restore over the engine: stop at step 7, resume from the file in a fresh engine, same end state."""
     common.check_checkpoint_resume(name, "engine", tmp_path, total=min(15, common.load_golden(name)["steps"]))

@@ -68,7 +68,7 @@ def test_run_recorder_outputs_match_reference_golden(name, tmp_path):
     common.check_outputs_against_golden(name, "oracle", tmp_path)
 
 
-@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "f3_evolution_metabolism_mt"])
+@pytest.mark.parametrize("name", ["c2_pollution_mt", "c2_seasons_keyed", "c1_default_utilicalc_mt", "f3_evolution_metabolism_mt", "f2_spice_life_mt"])
 def test_checkpoint_resume_is_bit_identical(name, tmp_path):
     """checkpoint.save / restore (here over the CPU oracle): a run stopped at step 7 and resumed from the file ends
     where the uninterrupted run ends -- cells, agents in list order, statistics, MT19937 state."""

@@ -177,6 +177,40 @@ def test_dropin_with_births_hands_a_working_view_back():
     assert run.view.log == ref.view.log
 
 
+def test_dropin_with_spice_and_births_hands_a_working_view_back():
+    """SURVEY 8 f2 + f3 through `dropin.install` on examples/readme_example without trade: spice on the cells and in the agents,
+    births, the event log -- and the reference's own loop continues from the synced View."""
+    import random
+    import ref_harness as rh
+    from sugarscape_utilicalc_b200 import dropin
+    s = rh.load_settings("readme_example")
+    s["rules"]["trade"] = False
+    keys = ("sugar", "spice", "occ", "order", "x", "y", "sugar_agent", "spice_agent", "spice_metab", "spice_endowment", "mt") + LIFE_KEYS
+    ref = rh.ReferenceRun(s)
+    ref.run(25)
+    exp, exp_log, exp_stats = ref.snapshot(), list(ref.view.log), ref.stats()
+    run = rh.ReferenceRun(s)
+    h = dropin.install(run.ss, run.view, rng="mt", world_factory=common.oracle_world)
+    for _ in range(25):
+        run.view.updateGame()
+    h.sync_back()
+    got = run.snapshot()
+    for k in keys:
+        assert np.array_equal(got[k], exp[k]), k
+    assert run.view.log == exp_log and run.stats() == exp_stats
+    state = random.getstate()
+    run.view.updateGame = h.original_update
+    for _ in range(5):
+        run.step()
+    random.setstate(state)
+    for _ in range(5):
+        ref.step()
+    a, b = run.snapshot(), ref.snapshot()
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+    assert run.view.log == ref.view.log
+
+
 def _moveeat_settings(rh):
     s = rh.load_settings(None)
     s["rules"]["moveEat"], s["rules"]["utilicalc"] = True, False
