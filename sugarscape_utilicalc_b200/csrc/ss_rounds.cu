@@ -458,17 +458,20 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             pa = me >> 5; a = (int)(me & 31u);
             slot = occ_slot(tileS[lr * SY + lq]);
         }
-        // the occupied cells of the zone: 2V+1 row windows (the axis row reaches 2V) and the x-arm beyond the square
-        // from the column bitmap
+        // the occupied cells of the zone: 2V+1 row windows and the x-arm beyond the square from the column bitmap.  The zone
+        // is what the predicate can reach from THIS agent's vision a, whatever the other's (b <= V): rows |dx| <= a see
+        // |dy| <= V, rows a < |dx| <= V see |dy| <= a, the axes reach a + V.
+        auto radius = [&](int dx) -> int { return dx == 0 ? a + V : (abs(dx) <= a ? V : a); };
         auto row_win = [&](int dx) -> WinT {
-            const int R = dx == 0 ? H : V;
+            const int R = radius(dx);
             WinT v = dr_window<WIDE>(&bm[(lr + dx) * BW], lq - R, 2 * R + 1);
             if (dx == 0) v &= ~((WinT)1 << R);                                  // not the agent itself
             return v;
         };
         auto col_win = [&]() -> WinT {
             WinT v = dr_window<WIDE>(&bmt[lq * BWT], lr - H, 2 * H + 1);
-            return v & ~((((WinT)1 << (2 * V + 1)) - (WinT)1) << (H - V));     // the square's rows are counted by the row windows
+            v &= ~((((WinT)1 << (2 * V + 1)) - (WinT)1) << (H - V));            // the square's rows are counted by the row windows
+            return v & ((((WinT)2 << (2 * (a + V))) - (WinT)1) << (H - (a + V)));      // ... and nothing beyond a + V
         };
         uint32_t cnt = 0;
         if (have) {
@@ -496,7 +499,7 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
             if (in_sub && have) {
                 uint32_t o = end - cnt - sub_begin;
                 for (int dx = -V; dx <= V; dx++) {
-                    const int R = dx == 0 ? H : V;
+                    const int R = radius(dx);
                     WinT bits = row_win(dx);
                     while (bits) {
                         const int j = dr_ffs<WIDE>(bits);
