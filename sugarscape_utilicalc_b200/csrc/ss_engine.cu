@@ -24,7 +24,7 @@ cudaError_t ss_launch_dr_mirror(const DevWorld& w, int* flag, cudaStream_t s);
 cudaError_t ss_dr_encode_tmap(const DevWorld& w, void* tmap_storage, int* ok);
 cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void* tmap_storage, int use_tma, cudaStream_t s);
 cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t env_time, int sm_count, int single_round,
-                                unsigned seg_begin, unsigned seg_end, cudaStream_t s);
+                                unsigned seg_begin, unsigned seg_end, int async_queue, cudaStream_t s);
 cudaError_t ss_launch_dr_check(const DevWorld& w, cudaStream_t s);
 cudaError_t ss_launch_dr_directory(const DevWorld& w, int n_all, const int32_t* id, const int32_t* x, const int32_t* metab,
                                    const double* sugar, cudaStream_t s);
@@ -91,6 +91,7 @@ struct ss_engine {
     cudaEvent_t ev_rounds = nullptr, ev_env = nullptr;
     bool env_in_flight = false;
     int overlap_option = 1;
+    int async_queue = 0;                        // option "async_queue": the rounds kernel as a work list without round barriers
     // SURVEY 8 f3 (limitedLifespan / procreate; serial path, MT19937 mode): see ss_life.cuh
     LifeWorld lw{};
     bool have_life = false;
@@ -1043,6 +1044,9 @@ static int dr_step(ss_engine* e, int stats_index) {
     // the conflict graph of this step reads occupancy, priorities and the alive / at-risk bitmaps -- nothing the previous
     // step's statistics, growback or diffusion touch -- so it runs beside them; the rounds need all of it
     const bool overlap = e->overlap_option && !e->profile && !e->trace;
+    // work-list mode of the rounds kernel (one GPU): entries are taken as they are published, so the queue starts empty
+    const int async_q = e->async_queue && e->strip_world <= 1;
+    if (async_q) { CK(cudaMemsetAsync(e->w.dr.self.queue, 0, sizeof(uint32_t) * ((size_t)e->dr_slots + 64), e->stream)); e->launches++; }
     {
         KTimer t(e, KT_PREPARE);
         if (e->trace) { CK(cudaStreamSynchronize(e->stream)); fprintf(stderr, "[ss] step %lld: build\n", (long long)e->iteration); }
@@ -1060,7 +1064,7 @@ static int dr_step(ss_engine* e, int stats_index) {
     }
     {
         KTimer t(e, KT_MOVE);
-        CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
+        CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, async_q, e->stream));
         if (e->trace) {
             CK(cudaStreamSynchronize(e->stream));
             unsigned ctl[8];
@@ -1486,6 +1490,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "global_vmax") { e->global_vmax = (int)value; return SS_OK; }
     if (k == "l2_persist") { e->l2_persist = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "overlap") { e->overlap_option = (int)value; return SS_OK; }
+    if (k == "async_queue") { e->async_queue = (int)value; return SS_OK; }
     if (k == "grow_ctas") { e->grow_ctas_per_sm = (int)value; return SS_OK; }
     if (k == "life_capacity_slack") { e->life_slack = (int)value; return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
@@ -1817,7 +1822,7 @@ extern "C" int ss_strip_phase(ss_engine* e, int32_t phase, uint32_t seg_begin, u
         if (rc) return rc;
     } else if (phase == 1) {
         if (seg_end > seg_begin) {
-            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 1, seg_begin, seg_end, e->stream));
+            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 1, seg_begin, seg_end, 0, e->stream));
             e->launches++;
         }
     } else if (phase == 2) {
@@ -1857,7 +1862,7 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
         {
             KTimer tm(e, KT_MOVE);
             CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip's counters and queue are set up
-            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, e->stream));
+            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, 0, e->stream));
         }
         {
             KTimer tm(e, KT_SERIAL);                                // ("serial" slot: merge of the statistics + delta lists + barrier)

@@ -639,7 +639,7 @@ struct DrShared {
 __device__ static inline void dr_push(const DevWorld& w, DrShared& sh, int warp, uint32_t e) {
     const int pos = atomicAdd(&sh.cnt[warp], 1);
     if (pos < DR_WARP_CAP) sh.push[warp][pos] = e;
-    else w.dr.self.queue[atomicAdd(&w.dr.self.ctl[0], 1u)] = e;
+    else { __threadfence(); w.dr.self.queue[atomicAdd(&w.dr.self.ctl[0], 1u)] = e; }      // (fence: see the work-list mode)
 }
 __device__ static inline void dr_flush(const DevWorld& w, DrShared& sh, int warp, int lane) {
     __syncwarp();
@@ -940,7 +940,7 @@ __device__ static inline void dr_util_choose(const DevWorld& w, const double* du
     out_sg = (int)(e >> 8);                                     // agent.py:1128-1130
 }
 
-template <int POLT, bool STRIPS, bool UTIL>
+template <int POLT, bool STRIPS, bool UTIL, bool ASYNC>
 __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrShared& sh, const double* durtab, int warp, DrAccum& acc, uint32_t entry) {
     const int n = w.n;
     const DrPeer& S = w.dr.self;
@@ -1076,6 +1076,9 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         *reinterpret_cast<uint4*>(dst) = nr;
         if (STRIPS && D.which != 0) recp->attr = attr & ~ATTR_ALIVE;      // left this strip
     }
+    // (no round barrier orders this turn's stores before the turns it releases: a fence does, once, ahead of every counter
+    // it decrements; whoever brings a counter to zero fences again before it publishes the queue entry, dr_flush)
+    if (ASYNC) __threadfence();
     // Q1: whoever follows this agent in the list order learns the outcome (a skipped agent did not die)
     if (risky && qw.y == (uint32_t)(st.iteration + 1)) {
         const uint32_t s2 = qw.x & OCC_SLOT_MASK;
@@ -1120,6 +1123,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
 // every strip's flag words (stores over NVLink) and waits until its own words show that number from everybody.
 // One thread; the caller has made this strip's writes visible to it (grid barrier / kernel boundary).
 #define DR_CTL_SEQ 12                   // (10, 11: the two "more work" words of the round barrier)
+#define DR_CTL_HEAD 13                  // work-list mode: queue positions handed out so far
 __device__ static inline bool dr_strip_sync(const DevWorld& w, unsigned seq, int word, unsigned payload, unsigned* any_payload) {
     const int P = w.dr.world, me = w.dr.rank;
     __threadfence_system();
@@ -1190,7 +1194,7 @@ __device__ static inline unsigned dr_grid_barrier(const DevWorld& w, unsigned nb
     return s_tail[0];
 }
 
-template <int POLT, bool STRIPS, bool XSYNC, bool UTIL>
+template <int POLT, bool STRIPS, bool XSYNC, bool UTIL, bool ASYNC>
 __global__ void __launch_bounds__(DR_THREADS, DR_MIN_BLOCKS)
 ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     __shared__ DrShared sh;
@@ -1208,6 +1212,50 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
     unsigned seg_b = st.single_round ? st.seg_begin : 0u;
     unsigned seg_e = st.single_round ? st.seg_end : __ldcg(&S.ctl[DR_CTL_TAIL0]);       // the tail after the build (ss_dr_seg0_kernel)
     const unsigned gwarp = blockIdx.x * DR_WARPS + (unsigned)warp, nwarp = gridDim.x * DR_WARPS;
+    if (ASYNC) {
+        // No rounds: the queue is a work list.  A warp claims the next positions of the queue -- 32 while the backlog is
+        // large, fewer (down to one: the lanes of a warp run their divergent turns one after the other) when entries
+        // only trickle in -- and its lanes wait for their entries to be published (the queue was zeroed before the
+        // build; an entry is written once, with DR_VALID), take their turn, and publish whom they released.  Every agent
+        // the build saw passes through the queue exactly once, in an order that is a topological order of the conflict
+        // graph: whoever holds the lowest unprocessed position never waits for a later one.
+        const unsigned total = __ldcg(&S.ctl[DR_CTL_AGENTS]);
+        unsigned int* head = &S.ctl[DR_CTL_HEAD];
+        for (;;) {
+            unsigned base = 0u, want = 0u;
+            if (lane == 0) {
+                const unsigned h = *(volatile unsigned*)head, t = *(volatile unsigned*)&S.ctl[DR_CTL_TAIL];
+                const unsigned backlog = t > h ? t - h : 0u;
+                want = min(32u, max(1u, backlog / nwarp));
+                base = h < total ? atomicAdd(head, want) : total;
+            }
+            base = __shfl_sync(FULL, base, 0); want = __shfl_sync(FULL, want, 0);
+            if (base >= total) break;
+            const unsigned pos = base + (unsigned)lane;
+            bool pending = (unsigned)lane < want && pos < total;
+            unsigned idle = 0;
+            for (;;) {
+                uint32_t e = 0u;
+                if (pending) e = *(volatile uint32_t*)&S.queue[pos];
+                const bool ready = pending && (e & DR_VALID) != 0u;
+                if (__any_sync(FULL, ready)) {
+                    if (ready) {
+                        __threadfence();                    // the entry, then what its publisher wrote before it
+                        dr_turn<POLT, STRIPS, UTIL, true>(w, st, sh, s_dur, warp, acc, e);
+                        pending = false;
+                    }
+                    __syncwarp();
+                    __threadfence();
+                    dr_flush(w, sh, warp, lane);
+                    idle = 0;
+                } else {
+                    __nanosleep(100);
+                    if (++idle > (1u << 24)) { acc.fault++; pending = false; }      // a lost entry: do not hang the GPU
+                }
+                if (!__any_sync(FULL, pending)) break;
+            }
+        }
+    } else
     for (;;) {
         const unsigned cnt = seg_e - seg_b;
         // a warp takes consecutive queue entries, up to 32 at a time, one lane each; every warp gets the same number of
@@ -1217,7 +1265,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
         const unsigned per = min(32u, max(1u, (cnt + batches * nwarp - 1u) / (batches * nwarp)));
         for (unsigned base = gwarp * per; base < cnt; base += nwarp * per) {
             const unsigned i = base + (unsigned)lane;
-            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS, UTIL>(w, st, sh, s_dur, warp, acc, __ldcg(&S.queue[seg_b + i]));
+            if ((unsigned)lane < per && i < cnt) dr_turn<POLT, STRIPS, UTIL, ASYNC>(w, st, sh, s_dur, warp, acc, __ldcg(&S.queue[seg_b + i]));
             __syncwarp();
             if (sh.cnt[warp] >= DR_WARP_CAP / 2) dr_flush(w, sh, warp, lane);
         }
@@ -1255,7 +1303,7 @@ __global__ void ss_dr_check_kernel(DevWorld w) {
 }
 __global__ void ss_dr_begin_kernel(DevWorld w) {
     unsigned int* c = w.dr.self.ctl;
-    c[DR_CTL_TAIL] = 0u; c[DR_CTL_POOL] = 0u; c[DR_CTL_DELTA] = 0u; c[DR_CTL_AGENTS] = 0u;
+    c[DR_CTL_TAIL] = 0u; c[DR_CTL_POOL] = 0u; c[DR_CTL_DELTA] = 0u; c[DR_CTL_AGENTS] = 0u; c[DR_CTL_HEAD] = 0u;
 }
 __global__ void ss_dr_seg0_kernel(DevWorld w) { w.dr.self.ctl[DR_CTL_TAIL0] = w.dr.self.ctl[DR_CTL_TAIL]; }
 
@@ -1277,21 +1325,21 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int POLT, bool STRIPS, bool XSYNC, bool UTIL>
+template <int POLT, bool STRIPS, bool XSYNC, bool UTIL, bool ASYNC>
 static cudaError_t launch_rounds(const DevWorld& w, DrStep st, int sm_count, cudaStream_t s) {
     static int per_sm = 0;
     if (!per_sm) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL>, DR_THREADS, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL, ASYNC>, DR_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     st.nblocks = (unsigned)(per_sm * sm_count);
     if (st.single_round) {
-        ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
+        ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL, ASYNC><<<st.nblocks, DR_THREADS, 0, s>>>(w, st);
         return cudaGetLastError();
     }
     void* args[2] = {(void*)&w, (void*)&st};
-    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)ss_dr_rounds_kernel<POLT, STRIPS, XSYNC, UTIL, ASYNC>, dim3(st.nblocks), dim3(DR_THREADS), args, 0, s);
 }
 
 extern "C" {
@@ -1392,7 +1440,7 @@ cudaError_t ss_launch_dr_build(const DevWorld& w, int64_t iteration, const void*
 
 // single_round = 0: the whole agent phase in one cooperative launch; 1: the queue segment [seg_begin, seg_end) only
 cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t env_time, int sm_count, int single_round,
-                                unsigned seg_begin, unsigned seg_end, cudaStream_t s) {
+                                unsigned seg_begin, unsigned seg_end, int async_queue, cudaStream_t s) {
     DrStep st;
     st.iteration = iteration; st.env_time = env_time;
     st.skey = ss_step_key(w.cfg.keyed_seed, iteration);
@@ -1401,11 +1449,15 @@ cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t en
     const bool pol = w.cfg.rule_pollution != 0;
     const bool strips = w.dr.world > 1;
     if (strips) {                   // (strips: no pollution rule; the in-kernel barrier over the strips unless the host drives the rounds)
-        if (single_round) return launch_rounds<0, true, false, false>(w, st, sm_count, s);
-        return launch_rounds<0, true, true, false>(w, st, sm_count, s);
+        if (single_round) return launch_rounds<0, true, false, false, false>(w, st, sm_count, s);
+        return launch_rounds<0, true, true, false, false>(w, st, sm_count, s);
     }
-    if (w.cfg.rule_utilicalc) return launch_rounds<0, false, false, true>(w, st, sm_count, s);   // (never with pollution: the reference crashes)
-    return pol ? launch_rounds<1, false, false, false>(w, st, sm_count, s) : launch_rounds<0, false, false, false>(w, st, sm_count, s);
+    if (async_queue) {              // one GPU: no rounds at all, the warps take queue entries as they are published
+        if (w.cfg.rule_utilicalc) return launch_rounds<0, false, false, true, true>(w, st, sm_count, s);
+        return pol ? launch_rounds<1, false, false, false, true>(w, st, sm_count, s) : launch_rounds<0, false, false, false, true>(w, st, sm_count, s);
+    }
+    if (w.cfg.rule_utilicalc) return launch_rounds<0, false, false, true, false>(w, st, sm_count, s);   // (never with pollution: the reference crashes)
+    return pol ? launch_rounds<1, false, false, false, false>(w, st, sm_count, s) : launch_rounds<0, false, false, false, false>(w, st, sm_count, s);
 }
 
 cudaError_t ss_launch_dr_directory(const DevWorld& w, int n_all, const int32_t* id, const int32_t* x, const int32_t* metab,

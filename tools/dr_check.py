@@ -37,10 +37,12 @@ def timing(n, pollution, steps=10, impl=3):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    extra = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in sys.argv[2:]}        # e.g. async_queue=1
+    o3 = dict({"pass_impl": 3}, **extra)
     if what in ("all", "check"):
-        check(64, False, 6); check(64, True, 6)
-        check(200, False, 8); check(177, True, 8); check(257, True, 6); check(300, True, 6, vision=(1, 10))
-        check(512, False, 6, opts={"pass_impl": 3, "tma": 0}); check(512, True, 6); check(1000, True, 4)
-        check(150, True, 10, density=1 / 3); check(256, True, 4, density=0.9, vision=(1, 4))
+        check(64, False, 6, opts=o3); check(64, True, 6, opts=o3)
+        check(200, False, 8, opts=o3); check(177, True, 8, opts=o3); check(257, True, 6, opts=o3); check(300, True, 6, vision=(1, 10), opts=o3)
+        check(512, False, 6, opts=dict(o3, tma=0)); check(512, True, 6, opts=o3); check(1000, True, 4, opts=o3)
+        check(150, True, 10, density=1 / 3, opts=o3); check(256, True, 4, density=0.9, vision=(1, 4), opts=o3)
     if what in ("all", "time"):
         timing(4096, True); timing(4096, False); timing(16384, False, steps=5)
