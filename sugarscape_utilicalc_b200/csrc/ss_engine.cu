@@ -91,7 +91,7 @@ struct ss_engine {
     cudaEvent_t ev_rounds = nullptr, ev_env = nullptr;
     bool env_in_flight = false;
     int overlap_option = 1;
-    int async_queue = 0;                        // option "async_queue": the rounds kernel as a work list without round barriers
+    int async_queue = 1;                        // option "async_queue": the rounds kernel as a work list without round barriers
     // SURVEY 8 f3 (limitedLifespan / procreate; serial path, MT19937 mode): see ss_life.cuh
     LifeWorld lw{};
     bool have_life = false;

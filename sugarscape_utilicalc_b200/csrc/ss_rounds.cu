@@ -40,6 +40,12 @@
 #ifndef DR_THREADS
 #define DR_THREADS 512                  // rounds kernel
 #endif
+#ifndef DR_ASYNC_MUL
+#define DR_ASYNC_MUL 8u                 // work-list mode: a warp claims backlog * MUL / warps positions, at most 32
+#endif
+#ifndef DR_ASYNC_SLEEP
+#define DR_ASYNC_SLEEP 100              // ... and polls for unpublished entries every so many ns
+#endif
 #ifndef DR_MIN_BLOCKS
 #define DR_MIN_BLOCKS 2                 // ... resident CTAs per SM the register allocation aims at
 #endif
@@ -1226,7 +1232,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
             if (lane == 0) {
                 const unsigned h = *(volatile unsigned*)head, t = *(volatile unsigned*)&S.ctl[DR_CTL_TAIL];
                 const unsigned backlog = t > h ? t - h : 0u;
-                want = min(32u, max(1u, backlog / nwarp));
+                want = min(32u, max(1u, (backlog * DR_ASYNC_MUL) / nwarp));
                 base = h < total ? atomicAdd(head, want) : total;
             }
             base = __shfl_sync(FULL, base, 0); want = __shfl_sync(FULL, want, 0);
@@ -1249,7 +1255,7 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
                     dr_flush(w, sh, warp, lane);
                     idle = 0;
                 } else {
-                    __nanosleep(100);
+                    __nanosleep(DR_ASYNC_SLEEP);
                     if (++idle > (1u << 24)) { acc.fault++; pending = false; }      // a lost entry: do not hang the GPU
                 }
                 if (!__any_sync(FULL, pending)) break;

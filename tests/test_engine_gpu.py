@@ -276,7 +276,8 @@ def test_keyed_lattice_path(name, impl):
     (64, True, 12, (1, 6)), (177, True, 10, (1, 6)), (200, False, 10, (1, 6)), (257, True, 8, (1, 6)),
     (300, True, 8, (1, 10)), (512, True, 8, (1, 6)), (1000, True, 5, (1, 6)), (1024, False, 6, (1, 6)),
 ])
-@pytest.mark.parametrize("impl", ["dependency_rounds", "dependency_rounds_no_tma", "cta_per_window", "warp_per_window", "lane_per_agent"])
+@pytest.mark.parametrize("impl", ["dependency_rounds", "dependency_rounds_no_tma", "dependency_rounds_with_barriers", "cta_per_window", "warp_per_window",
+                                  "lane_per_agent"])
 def test_lattice_vs_oracle_synthetic(n, pollution, steps, vision, impl):
     """The agent-phase kernels against the CPU oracle: the dependency rounds over the whole lattice (ss_dr_build_kernel +
     ss_dr_rounds_kernel, the default; also with the TMA tile load switched off) and the move-pass kernels
@@ -287,7 +288,8 @@ def test_lattice_vs_oracle_synthetic(n, pollution, steps, vision, impl):
     cfg = config_from_settings(s, rng_mode="keyed")
     solo = {"warp_per_window": 1, "lane_per_agent": 2}.get(impl, 0)
     if impl.startswith("dependency_rounds"):
-        opts = {"pass_impl": 3, "tma": 0 if impl.endswith("no_tma") else 1}
+        # (default: the rounds kernel as a work list; "with_barriers": one grid barrier per dependency round, as the strips run it)
+        opts = {"pass_impl": 3, "tma": 0 if impl.endswith("no_tma") else 1, "async_queue": 0 if impl.endswith("with_barriers") else 1}
     else:
         opts = {"pass_impl": 0} if not solo else {"pass_impl": solo, "solo_window": 96 if vision[1] <= 6 else 120}
     e, o = common.engine_world(cfg, options=opts), common.oracle_world(cfg)
