@@ -91,6 +91,7 @@ struct ss_engine {
     cudaEvent_t ev_rounds = nullptr, ev_env = nullptr;
     bool env_in_flight = false;
     int overlap_option = 1;
+    int async_queue_strips = 0;                 // option "async_queue_strips": the same over the strips' peer-mapped queues
     int async_queue = 1;                        // option "async_queue": the rounds kernel as a work list without round barriers
     // SURVEY 8 f3 (limitedLifespan / procreate; serial path, MT19937 mode): see ss_life.cuh
     LifeWorld lw{};
@@ -1491,6 +1492,7 @@ extern "C" int ss_set_option(ss_engine* e, const char* name, int64_t value) {
     if (k == "l2_persist") { e->l2_persist = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
     if (k == "overlap") { e->overlap_option = (int)value; return SS_OK; }
     if (k == "async_queue") { e->async_queue = (int)value; return SS_OK; }
+    if (k == "async_queue_strips") { e->async_queue_strips = (int)value; return SS_OK; }
     if (k == "grow_ctas") { e->grow_ctas_per_sm = (int)value; return SS_OK; }
     if (k == "life_capacity_slack") { e->life_slack = (int)value; return SS_OK; }
     if (k == "pass_impl") { e->pass_impl_option = (int)value; if (e->have_agents) return choose_path(e); return SS_OK; }
@@ -1854,15 +1856,18 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     if (rc) return rc;
     CK(cudaEventRecord(e->evs, e->stream));
     for (int t = 0; t < nsteps; t++) {
+        const int async_q = e->async_queue_strips;                 // work-list mode: no exchange per round, the strips meet after the kernel
         {
             KTimer tm(e, KT_PREPARE);                               // (option "profile": device time per phase, with a host sync each)
+            if (async_q) CK(cudaMemsetAsync(e->w.dr.self.queue, 0, sizeof(uint32_t) * ((size_t)e->dr_slots + 64), e->stream));
             rc = strip_begin_build(e);
             if (rc) return rc;
         }
         {
             KTimer tm(e, KT_MOVE);
             CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip's counters and queue are set up
-            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, 0, e->stream));
+            CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, async_q, e->stream));
+            if (async_q) CK(ss_launch_dr_strip_barrier(e->w, e->stream));      // every strip has drained its queue
         }
         {
             KTimer tm(e, KT_SERIAL);                                // ("serial" slot: merge of the statistics + delta lists + barrier)

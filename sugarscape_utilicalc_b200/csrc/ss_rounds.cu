@@ -616,6 +616,9 @@ ss_dr_build_kernel(DevWorld w, DrBuildArgs ba, const __grid_constant__ CUtensorM
 
 // ------------------------------------------------------------------------------- rounds ----
 struct DrAccum { unsigned sum_m, sum_v, acted, deaths, small, inexact, fault; };
+// work-list mode: what orders a turn's stores ahead of the counters it decrements and of the entries it publishes --
+// device scope on one GPU, system scope when counters, queues and cells of other strips (GPUs) are involved
+template <bool STRIPS> __device__ static inline void dr_fence() { if (STRIPS) __threadfence_system(); else __threadfence(); }
 // the agent's keyed words in sequence: word j = mix64(akey + j * golden) >> 32 (ss_device.cuh), the sum kept running
 struct DrKeyed { uint64_t x; uint32_t j; };
 __device__ static inline void dr_keyed_open(DrKeyed& ks, uint64_t skey, uint32_t slot) { ks.x = ss_agent_key(skey, slot + 1u); ks.j = 0u; }
@@ -661,7 +664,7 @@ __device__ static inline void dr_flush(const DevWorld& w, DrShared& sh, int warp
     __syncwarp();
 }
 // the result of one decrement of a successor's counter: the counter's old value decides who queues the successor
-template <bool STRIPS>
+template <bool STRIPS, bool ASYNC>
 __device__ static inline void dr_released(const DevWorld& w, DrShared& sh, int warp, DrAccum& acc, uint32_t ent, uint32_t old,
                                           bool lose_turn) {
     const uint32_t slot2 = ent & OCC_SLOT_MASK;
@@ -670,7 +673,10 @@ __device__ static inline void dr_released(const DevWorld& w, DrShared& sh, int w
         const uint32_t e = slot2 | DR_VALID | ((lose_turn || (h >> 15)) ? DR_SKIP : 0u);
         const int which = STRIPS ? (int)((ent >> 24) & 3u) : 0;
         if (which == 0) dr_push(w, sh, warp, e);
-        else DR_W(queue, which)[atomicAdd(&DR_W(ctl, which)[0], 1u)] = e | DR_REMOTE;          // a ring neighbour's agent
+        else {                                                                                  // a ring neighbour's agent
+            if (ASYNC) dr_fence<STRIPS>();              // (the counter's other decrements, then the entry: see dr_flush)
+            DR_W(queue, which)[atomicAdd(&DR_W(ctl, which)[0], 1u)] = e | DR_REMOTE;
+        }
     } else if ((h & 0x7fffu) == 0u) acc.fault++;
 }
 template <bool STRIPS>
@@ -1084,7 +1090,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
     }
     // (no round barrier orders this turn's stores before the turns it releases: a fence does, once, ahead of every counter
     // it decrements; whoever brings a counter to zero fences again before it publishes the queue entry, dr_flush)
-    if (ASYNC) __threadfence();
+    if (ASYNC) dr_fence<STRIPS>();
     // Q1: whoever follows this agent in the list order learns the outcome (a skipped agent did not die)
     if (risky && qw.y == (uint32_t)(st.iteration + 1)) {
         const uint32_t s2 = qw.x & OCC_SLOT_MASK;
@@ -1096,7 +1102,10 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         if ((h & 0x7fffu) == 1u) {
             const uint32_t e = s2 | DR_VALID | ((died || (h >> 15)) ? DR_SKIP : 0u);
             if (!STRIPS || home == w.dr.rank) dr_push(w, sh, warp, e);
-            else DR_A(queue, home)[atomicAdd(&DR_A(ctl, home)[DR_CTL_TAIL], 1u)] = e | DR_REMOTE;
+            else {
+                if (ASYNC) dr_fence<STRIPS>();
+                DR_A(queue, home)[atomicAdd(&DR_A(ctl, home)[DR_CTL_TAIL], 1u)] = e | DR_REMOTE;
+            }
         } else if ((h & 0x7fffu) == 0u) acc.fault++;
     }
     // conflict successors: all decrements of the record are issued before the first result is looked at
@@ -1108,7 +1117,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         for (int i = 0; i < DR_SUCC_INLINE; i++) old[i] = (uint32_t)i < nsucc ? dr_dec<STRIPS>(w, e[1 + i]) : 0u;
 #pragma unroll
         for (int i = 0; i < DR_SUCC_INLINE; i++)
-            if ((uint32_t)i < nsucc) dr_released<STRIPS>(w, sh, warp, acc, e[1 + i], old[i], false);
+            if ((uint32_t)i < nsucc) dr_released<STRIPS, ASYNC>(w, sh, warp, acc, e[1 + i], old[i], false);
         if (nsucc > DR_SUCC_INLINE) {
             const uint32_t* pp = w.dr.pool + e[15];
             const uint32_t extra = nsucc - DR_SUCC_INLINE;
@@ -1119,7 +1128,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
 #pragma unroll
                 for (int i = 0; i < 4; i++) ol[i] = b + i < extra ? dr_dec<STRIPS>(w, en[i]) : 0u;
 #pragma unroll
-                for (int i = 0; i < 4; i++) if (b + i < extra) dr_released<STRIPS>(w, sh, warp, acc, en[i], ol[i], false);
+                for (int i = 0; i < 4; i++) if (b + i < extra) dr_released<STRIPS, ASYNC>(w, sh, warp, acc, en[i], ol[i], false);
             }
         }
     }
@@ -1246,12 +1255,12 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
                 const bool ready = pending && (e & DR_VALID) != 0u;
                 if (__any_sync(FULL, ready)) {
                     if (ready) {
-                        __threadfence();                    // the entry, then what its publisher wrote before it
+                        dr_fence<STRIPS>();                 // the entry, then what its publisher wrote before it
                         dr_turn<POLT, STRIPS, UTIL, true>(w, st, sh, s_dur, warp, acc, e);
                         pending = false;
                     }
                     __syncwarp();
-                    __threadfence();
+                    dr_fence<STRIPS>();
                     dr_flush(w, sh, warp, lane);
                     idle = 0;
                 } else {
@@ -1456,6 +1465,9 @@ cudaError_t ss_launch_dr_rounds(const DevWorld& w, int64_t iteration, int64_t en
     const bool strips = w.dr.world > 1;
     if (strips) {                   // (strips: no pollution rule; the in-kernel barrier over the strips unless the host drives the rounds)
         if (single_round) return launch_rounds<0, true, false, false, false>(w, st, sm_count, s);
+        // (work list: every strip drains its own queue -- its neighbours publish into it over NVLink -- and the strips
+        // meet again after the kernel; else one exchange per dependency round inside the kernel)
+        if (async_queue) return launch_rounds<0, true, false, false, true>(w, st, sm_count, s);
         return launch_rounds<0, true, true, false, false>(w, st, sm_count, s);
     }
     if (async_queue) {              // one GPU: no rounds at all, the warps take queue entries as they are published
