@@ -91,7 +91,7 @@ struct ss_engine {
     cudaEvent_t ev_rounds = nullptr, ev_env = nullptr;
     bool env_in_flight = false;
     int overlap_option = 1;
-    int async_queue_strips = 0;                 // option "async_queue_strips": the same over the strips' peer-mapped queues
+    int async_queue_strips = 1;                 // option "async_queue_strips": the same over the strips' peer-mapped queues
     int async_queue = 1;                        // option "async_queue": the rounds kernel as a work list without round barriers
     // SURVEY 8 f3 (limitedLifespan / procreate; serial path, MT19937 mode): see ss_life.cuh
     LifeWorld lw{};
@@ -1792,17 +1792,18 @@ static int strip_begin_build(ss_engine* e) {
     e->launches += 5;
     return SS_OK;
 }
-static int strip_finish(ss_engine* e, int stats_index) {
+static int strip_finish(ss_engine* e, int stats_index, cudaStream_t stream = nullptr) {
+    if (!stream) stream = e->stream;
     DevWorld g = e->w;                          // the statistics kernel on the merged sums
     g.acc = reinterpret_cast<StepAccum*>(e->w.dr.acc_g);
     g.hist = e->w.dr.hist_g;
     g.outliers = nullptr;                       // (wealth outside the histogram: Gini is reported as NaN on strips)
     {
         KTimer tm(e, KT_STATS);
-        CK(ss_launch_stats(g, stats_index, e->stream));
+        CK(ss_launch_stats(g, stats_index, stream));
     }
     e->launches++;
-    int rc = env_phase(e);
+    int rc = env_phase(e, stream);
     if (rc) return rc;
     e->iteration++; e->env_time++; e->steps++;
     e->stepped = true;
@@ -1855,6 +1856,10 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
     rc = ensure_stats(e, nsteps);
     if (rc) return rc;
     CK(cudaEventRecord(e->evs, e->stream));
+    // Statistics and growback of step t run on the second stream beside the conflict graph of step t + 1 (which reads the
+    // neighbours' border rows for occupancy only); the barrier ahead of the rounds then stands for both "every strip's
+    // counters and queue are set up" and "every strip's growback is done: the halos are final".
+    const bool overlap = e->overlap_option && !e->profile;
     for (int t = 0; t < nsteps; t++) {
         const int async_q = e->async_queue_strips;                 // work-list mode: no exchange per round, the strips meet after the kernel
         {
@@ -1865,7 +1870,9 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
         }
         {
             KTimer tm(e, KT_MOVE);
-            CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip's counters and queue are set up
+            rc = env_join(e);                                       // this strip's growback of the previous step
+            if (rc) return rc;
+            CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip: conflict graph built, previous growback done
             CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, async_q, e->stream));
             if (async_q) CK(ss_launch_dr_strip_barrier(e->w, e->stream));      // every strip has drained its queue
         }
@@ -1875,13 +1882,25 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
             CK(ss_launch_dr_after_rounds(e->w, e->stream));
             CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // everybody has read everybody's sums and delta list
         }
-        rc = strip_finish(e, t);                                    // statistics kernel + growback (timed as "grow")
-        if (rc) return rc;
-        {
+        if (overlap) {
+            CK(cudaEventRecord(e->ev_rounds, e->stream));
+            CK(cudaStreamWaitEvent(e->stream_env, e->ev_rounds, 0));
+            rc = strip_finish(e, t, e->stream_env);                 // statistics kernel + growback
+            if (rc) return rc;
+            CK(cudaEventRecord(e->ev_env, e->stream_env));
+            e->env_in_flight = true;
+        } else {
+            rc = strip_finish(e, t);                                // (timed as "grow")
+            if (rc) return rc;
             KTimer tm(e, KT_SETTLE);
             CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip's growback is done: the halos are final
         }
         e->launches += 7; e->passes++;
+    }
+    if (overlap) {
+        rc = env_join(e);
+        if (rc) return rc;
+        CK(ss_launch_dr_strip_barrier(e->w, e->stream));            // ... before anybody reads a neighbour's rows again
     }
     CK(cudaEventRecord(e->eve, e->stream));
     if (out) CK(cudaMemcpyAsync(out, e->w.stats, sizeof(ss_step_stats) * (size_t)nsteps, cudaMemcpyDeviceToHost, e->stream));

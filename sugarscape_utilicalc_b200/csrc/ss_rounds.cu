@@ -976,7 +976,7 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
     uint2 qw = make_uint2(0u, 0u);
     if (risky) qw = __ldcg(&w.dr.q1wait[slot]);
     const int lx = (int)(c / (uint32_t)n), gy = (int)(c - (uint32_t)lx * (uint32_t)n), gx = S.x0 + lx;
-    bool died = false;
+    bool died = false, wrote_far = false;
     if (!skip) {
         int arm = -1, o = 0, sg = 0;
         uint8_t own;
@@ -1086,11 +1086,26 @@ __device__ static inline void dr_turn(const DevWorld& w, const DrStep& st, DrSha
         const unsigned long long sb = (unsigned long long)__double_as_longlong(sugar);
         nr.x = (uint32_t)sb; nr.y = (uint32_t)(sb >> 32); nr.z = D.idx; nr.w = attr;
         *reinterpret_cast<uint4*>(dst) = nr;
-        if (STRIPS && D.which != 0) recp->attr = attr & ~ATTR_ALIVE;      // left this strip
+        if (STRIPS && D.which != 0) { recp->attr = attr & ~ATTR_ALIVE; wrote_far = true; }      // left this strip
     }
     // (no round barrier orders this turn's stores before the turns it releases: a fence does, once, ahead of every counter
     // it decrements; whoever brings a counter to zero fences again before it publishes the queue entry, dr_flush)
-    if (ASYNC) dr_fence<STRIPS>();
+    if (ASYNC) {
+        // (strips: system scope only for a turn that wrote to or notifies another strip -- a move across the border, a
+        // successor or the Q1 successor over there, a successor list that continues in the pool; the interior stays at
+        // device scope)
+        bool far = false;
+        if (STRIPS) {
+            const uint32_t ev[16] = {sq[0].x, sq[0].y, sq[0].z, sq[0].w, sq[1].x, sq[1].y, sq[1].z, sq[1].w,
+                                     sq[2].x, sq[2].y, sq[2].z, sq[2].w, sq[3].x, sq[3].y, sq[3].z, sq[3].w};
+            uint32_t strips_or = 0u;
+#pragma unroll
+            for (int i = 0; i < DR_SUCC_INLINE; i++) if ((uint32_t)i < nsucc) strips_or |= ev[1 + i];
+            far = wrote_far || (strips_or & 0x03000000u) != 0u || nsucc > DR_SUCC_INLINE ||
+                  (risky && qw.y == (uint32_t)(st.iteration + 1));
+        }
+        if (far) __threadfence_system(); else __threadfence();
+    }
     // Q1: whoever follows this agent in the list order learns the outcome (a skipped agent did not die)
     if (risky && qw.y == (uint32_t)(st.iteration + 1)) {
         const uint32_t s2 = qw.x & OCC_SLOT_MASK;
@@ -1255,12 +1270,12 @@ ss_dr_rounds_kernel(DevWorld w, DrStep st) {
                 const bool ready = pending && (e & DR_VALID) != 0u;
                 if (__any_sync(FULL, ready)) {
                     if (ready) {
-                        dr_fence<STRIPS>();                 // the entry, then what its publisher wrote before it
+                        if (STRIPS && (e & DR_REMOTE)) __threadfence_system(); else __threadfence();      // the entry, then what its publisher wrote before it
                         dr_turn<POLT, STRIPS, UTIL, true>(w, st, sh, s_dur, warp, acc, e);
                         pending = false;
                     }
                     __syncwarp();
-                    dr_fence<STRIPS>();
+                    __threadfence();                        // (the entries published here are local; the ones for other strips fence on their own)
                     dr_flush(w, sh, warp, lane);
                     idle = 0;
                 } else {
