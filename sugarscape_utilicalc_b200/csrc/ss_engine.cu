@@ -1874,7 +1874,9 @@ extern "C" int ss_strip_step(ss_engine* e, int32_t nsteps, ss_step_stats* out) {
             if (rc) return rc;
             CK(ss_launch_dr_strip_barrier(e->w, e->stream));        // every strip: conflict graph built, previous growback done
             CK(ss_launch_dr_rounds(e->w, e->iteration, e->env_time, e->sm_count, 0, 0u, 0u, async_q, e->stream));
-            if (async_q) CK(ss_launch_dr_strip_barrier(e->w, e->stream));      // every strip has drained its queue
+            // every strip has drained its queue and added its sums (the rounds kernel does that after its last turn -- also
+            // after the last exchange of the version with one exchange per round)
+            CK(ss_launch_dr_strip_barrier(e->w, e->stream));
         }
         {
             KTimer tm(e, KT_SERIAL);                                // ("serial" slot: merge of the statistics + delta lists + barrier)

@@ -15,13 +15,16 @@
 //                        the keyed order, found by walking the inverse priority map over the alive bitmap) adds one
 //                        more edge when it may starve this step (Q1: sugarscape.py:520 + 502-503, the agent after a
 //                        dying agent loses its turn).  Agents without predecessors enter the ready queue.
-//   ss_dr_rounds_kernel  one persistent cooperative kernel per step.  Round k: one thread per ready agent -- both arms
+//   ss_dr_rounds_kernel  one persistent cooperative kernel per step.  One thread per ready agent -- both arms
 //                        of the cross as two 16-byte loads each on the one-byte cell words (occupied | int(sugar);
 //                        the x-arm from a transposed copy), choice (agent.py:794-823 incl. the
-//                        replay of the agent's Fisher-Yates draws for ties), harvest, pollution, metabolism, death
-//                        (sugarscape.py:566-601), statistics -- then one atomic decrement per successor; whoever
-//                        brings a counter to zero appends that agent to the queue.  A grid barrier separates the
-//                        rounds; the kernel ends when a round appended nothing.
+//                        replay of the agent's Fisher-Yates draws for ties; or the utilicalc turn, agent.py:1025-1141),
+//                        harvest, pollution, metabolism, death (sugarscape.py:566-601), statistics -- then one atomic
+//                        decrement per successor; whoever brings a counter to zero appends that agent to the queue.
+//                        The queue is run as a WORK LIST: warps claim its next positions and wait for the entries to be
+//                        published, fences order a turn's stores ahead of the counters it decrements -- no barrier
+//                        between dependency rounds (the version with one grid barrier per round stays: option
+//                        async_queue = 0, and the host-driven strips of the tests).
 //
 // Everything an agent's turn needs is settled in the turn (no deferred pass), so the only per-step kernels around
 // these two are the statistics and the growback.
