@@ -1161,31 +1161,38 @@ static int life_grow(ss_engine* e, uint32_t cap) {
     const uint32_t old = e->slot_capacity;
     if (cap <= old) return SS_OK;
     if (cap > (1u << 22)) return set_err(e, SS_ERR_UNSUPPORTED, "serial path limited to 4M agent ids");
-    AgentRec* agents = nullptr; int32_t* order = nullptr; double* wealth = nullptr; unsigned long long* sortkeys = nullptr; LifeRec* rec = nullptr;
     const int P = next_pow2((int)cap);
-    CK(cudaMalloc(&agents, sizeof(AgentRec) * cap));
-    CK(cudaMalloc(&order, sizeof(int32_t) * cap));
-    CK(cudaMalloc(&wealth, sizeof(double) * P));
-    CK(cudaMalloc(&sortkeys, sizeof(unsigned long long) * P));
-    CK(cudaMalloc(&rec, sizeof(LifeRec) * cap));
-    CK(cudaMemsetAsync(agents, 0, sizeof(AgentRec) * cap, e->stream));
-    CK(cudaMemsetAsync(rec, 0, sizeof(LifeRec) * cap, e->stream));
-    CK(cudaMemcpyAsync(agents, e->w.agents, sizeof(AgentRec) * old, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(order, e->w.order, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(rec, e->lw.rec, sizeof(LifeRec) * old, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    if (e->cfg.rule_spice) {
-        double *a = nullptr, *b = nullptr; int32_t* m = nullptr;
-        CK(cudaMalloc(&a, sizeof(double) * cap)); CK(cudaMalloc(&b, sizeof(double) * cap)); CK(cudaMalloc(&m, sizeof(int32_t) * cap));
-        CK(cudaMemset(a, 0, sizeof(double) * cap)); CK(cudaMemset(b, 0, sizeof(double) * cap)); CK(cudaMemset(m, 0, sizeof(int32_t) * cap));
-        CK(cudaMemcpy(a, e->sw.aspice, sizeof(double) * old, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(b, e->sw.sp_endow, sizeof(double) * old, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(m, e->sw.asp_metab, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice));
-        cudaFree(e->sw.aspice); cudaFree(e->sw.sp_endow); cudaFree(e->sw.asp_metab);
-        e->sw.aspice = a; e->sw.sp_endow = b; e->sw.asp_metab = m;
+    const bool spice = e->cfg.rule_spice != 0;
+    struct Fresh {          // the new arrays; whatever is still here when the function leaves (an error) is freed
+        AgentRec* agents = nullptr; int32_t* order = nullptr; double* wealth = nullptr; unsigned long long* sortkeys = nullptr;
+        LifeRec* rec = nullptr; double* aspice = nullptr; double* sp_endow = nullptr; int32_t* asp_metab = nullptr;
+        ~Fresh() { cudaFree(agents); cudaFree(order); cudaFree(wealth); cudaFree(sortkeys); cudaFree(rec); cudaFree(aspice); cudaFree(sp_endow); cudaFree(asp_metab); }
+    } f;
+    CK(cudaMalloc(&f.agents, sizeof(AgentRec) * cap));
+    CK(cudaMalloc(&f.order, sizeof(int32_t) * cap));
+    CK(cudaMalloc(&f.wealth, sizeof(double) * P));
+    CK(cudaMalloc(&f.sortkeys, sizeof(unsigned long long) * P));
+    CK(cudaMalloc(&f.rec, sizeof(LifeRec) * cap));
+    CK(cudaMemsetAsync(f.agents, 0, sizeof(AgentRec) * cap, e->stream));
+    CK(cudaMemsetAsync(f.rec, 0, sizeof(LifeRec) * cap, e->stream));
+    CK(cudaMemcpyAsync(f.agents, e->w.agents, sizeof(AgentRec) * old, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(f.order, e->w.order, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(f.rec, e->lw.rec, sizeof(LifeRec) * old, cudaMemcpyDeviceToDevice, e->stream));
+    if (spice) {
+        CK(cudaMalloc(&f.aspice, sizeof(double) * cap));
+        CK(cudaMalloc(&f.sp_endow, sizeof(double) * cap));
+        CK(cudaMalloc(&f.asp_metab, sizeof(int32_t) * cap));
+        CK(cudaMemsetAsync(f.aspice, 0, sizeof(double) * cap, e->stream));
+        CK(cudaMemsetAsync(f.sp_endow, 0, sizeof(double) * cap, e->stream));
+        CK(cudaMemsetAsync(f.asp_metab, 0, sizeof(int32_t) * cap, e->stream));
+        CK(cudaMemcpyAsync(f.aspice, e->sw.aspice, sizeof(double) * old, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(f.sp_endow, e->sw.sp_endow, sizeof(double) * old, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(f.asp_metab, e->sw.asp_metab, sizeof(int32_t) * old, cudaMemcpyDeviceToDevice, e->stream));
     }
-    cudaFree(e->w.agents); cudaFree(e->w.order); cudaFree(e->w.wealth); cudaFree(e->w.sortkeys); cudaFree(e->lw.rec);
-    e->w.agents = agents; e->w.order = order; e->w.wealth = wealth; e->w.sortkeys = sortkeys; e->lw.rec = rec;
+    CK(cudaStreamSynchronize(e->stream));
+    std::swap(e->w.agents, f.agents); std::swap(e->w.order, f.order); std::swap(e->w.wealth, f.wealth);
+    std::swap(e->w.sortkeys, f.sortkeys); std::swap(e->lw.rec, f.rec);          // (the old arrays leave with `f`)
+    if (spice) { std::swap(e->sw.aspice, f.aspice); std::swap(e->sw.sp_endow, f.sp_endow); std::swap(e->sw.asp_metab, f.asp_metab); }
     e->slot_capacity = cap; e->lw.capacity = (int32_t)cap;
     return SS_OK;
 }

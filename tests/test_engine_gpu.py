@@ -83,6 +83,28 @@ def test_spice_matches_reference_golden(name):
     w.close()
 
 
+def test_spice_with_keyed_words_equals_oracle():
+    """... and with the keyed word source (serial kernel, keyed order by the CTA-wide sort): engine against the oracle."""
+    g = common.load_golden("f2_spice_mt")
+    cfg = config_from_settings(g["settings"], rng_mode="keyed")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    init = common.golden_init(g)
+    common.init_world(e, init, "keyed")
+    common.init_world(o, init, "keyed")
+    assert e.counters()["path"] == 0
+    for _ in range(6):
+        se, so = e.step(10), o.step(10)
+        for f in ("population", "metabolism_mean", "vision_mean", "gini", "acted", "deaths"):
+            assert np.array_equal(se[f], so[f]), f
+        ge, go = e.download_agents(), o.download_agents()
+        for k in ("id", "x", "y", "sugar"):
+            assert np.array_equal(ge[k], go[k]), k
+        assert np.array_equal(e.download_agents_spice()["spice"], o.download_agents_spice()["spice"])
+        assert np.array_equal(e.download_cells_spice()["spice"], o.download_cells_spice()["spice"])
+    e.close()
+    o.close()
+
+
 def test_spice_single_steps_and_missing_uploads():
     from sugarscape_utilicalc_b200.engine import EngineError
     g = common.load_golden("f2_spice_mt")

@@ -177,6 +177,31 @@ def test_dropin_with_births_hands_a_working_view_back():
     assert run.view.log == ref.view.log
 
 
+def test_spice_with_keyed_words_oracle_vs_live_reference():
+    """SURVEY 8 f2 with the keyed word source (the reference consumes it through the shim): examples/trade_price_volume
+    without trade, step by step."""
+    import ref_harness as rh
+    s = rh.load_settings("trade_price_volume")
+    s["rules"]["trade"] = False
+    ref = rh.ReferenceRun(s, rng="keyed")
+    s0 = ref.snapshot()
+    o = common.oracle_world(config_from_settings(s, rng_mode="keyed"))
+    init = dict(sugar=s0["sugar"], cap=s0["cap"], pollution=s0["pollution"], id=s0["order"], x=s0["x"], y=s0["y"],
+                vision=s0["vision"], metab=s0["metab"], sugar_agent=s0["sugar_agent"],
+                spice={k: s0[k] for k in ("spice", "spice_cap", "spice_metab", "spice_agent", "spice_endowment")})
+    common.init_world(o, init, "keyed")
+    for t in range(40):
+        ref.step()
+        st = o.step(1)
+        sn, ga, gs, gc = ref.snapshot(), o.download_agents(), o.download_agents_spice(), o.download_cells()
+        assert np.array_equal(ga["id"], sn["order"]) and np.array_equal(ga["x"], sn["x"]) and np.array_equal(ga["y"], sn["y"]), t
+        assert np.array_equal(ga["sugar"], sn["sugar_agent"]) and np.array_equal(gs["spice"], sn["spice_agent"]), t
+        assert np.array_equal(gc["occ"], sn["occ"]) and np.array_equal(o.download_cells_spice()["spice"], sn["spice"]), t
+        assert st["population"][0] == ref.view.population[-1] and st["gini"][0] == ref.view.gini[-1], t
+    assert o.pow_faults() == 0
+    o.close()
+
+
 def test_dropin_with_spice_and_births_hands_a_working_view_back():
     """SURVEY 8 f2 + f3 through `dropin.install` on examples/readme_example without trade: spice on the cells and in the agents,
     births, the event log -- and the reference's own loop continues from the synced View."""
