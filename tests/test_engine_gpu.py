@@ -119,6 +119,68 @@ def test_spice_single_steps_and_missing_uploads():
     e.close()
 
 
+@pytest.mark.parametrize("seed,grid,blue,red,spice,lifespan,procreate,ages,start", [
+    (3, 20, 60, 60, True, True, True, (4, 10), 0), (77, 14, 90, 90, False, True, True, (60, 100), 1),
+    (123, 36, 120, 120, True, False, True, (60, 100), 12), (9, 24, 150, 10, True, True, False, (4, 10), 12),
+    (2024, 30, 200, 200, False, False, True, (60, 100), 0), (5, 12, 70, 70, True, True, True, (60, 100), 1)])
+def test_random_worlds_with_spice_and_life_rules_engine_vs_oracle(seed, grid, blue, red, spice, lifespan, procreate, ages, start):
+    """SURVEY 8 f2 + f3 on small random worlds (short lives, fertility from birth, crowded lattices): the world of `__main__`
+    built on the device, handed to the oracle as is, then both stepped -- cells, agents, the rules' fields, event records,
+    statistics, MT19937 stream.  (The oracle itself is checked on hundreds of such worlds against the live reference:
+    tests/test_oracle_vs_reference.py.)"""
+    import copy
+    from sugarscape_utilicalc_b200 import init_params_from_settings
+    s = copy.deepcopy(common.load_golden("f2_spice_life_mt")["settings"])
+    s["rules"].update(spice=spice, limitedLifespan=lifespan, procreate=procreate)
+    s["view"]["grid_size"] = {"x": grid, "y": grid}
+    s["env"]["random_seed"] = seed
+    s["env"]["total_agents"] = {"blue": blue, "red": red}
+    for site in s["env"]["sites"].values():
+        site["x"], site["y"], site["radius"] = site["x"] % grid, site["y"] % grid, max(2, site["radius"] * grid // 50)
+    s["agents"]["max_agent_vision"] = min(s["agents"]["max_agent_vision"], (grid - 1) // 2)
+    s["agents"]["death_age_range"] = {"min": ages[0], "max": ages[1]}
+    for who in ("male", "female"):
+        s["agents"]["fertility_age_ranges"][who].update(min_start=start, max_start=start + 3)
+    cfg = config_from_settings(s, rng_mode="mt")
+    e, o = common.engine_world(cfg), common.oracle_world(cfg)
+    e.seed_mt19937(seed)
+    e.init_world(init_params_from_settings(s))
+    cells, ags = e.download_cells(), e.download_agents()
+    init = dict(sugar=cells["sugar"], cap=cells["cap"], pollution=cells["pollution"], id=ags["id"], x=ags["x"], y=ags["y"],
+                vision=ags["vision"], metab=ags["metab"], sugar_agent=ags["sugar"])
+    if spice:
+        cs, sp = e.download_cells_spice(), e.download_agents_spice()
+        init["spice"] = dict(spice=cs["spice"], spice_cap=cs["spice_cap"], spice_metab=sp["spice_metab"], spice_agent=sp["spice"],
+                             spice_endowment=sp["spice_endowment"])
+    if lifespan or procreate:
+        lf = e.download_agents_life()
+        init["life"], init["id_increment"] = {k: lf[k] for k in common.LIFE_COLUMNS}, lf["id_increment"]
+    mt, idx = e.get_rng_mt19937()
+    common.init_world(o, init, "mt", mt, idx)
+    for t in range(15):
+        se, so = e.step(2), o.step(2)
+        for f in ("population", "metabolism_mean", "vision_mean", "gini", "acted", "deaths"):
+            assert np.array_equal(se[f], so[f]), (t, f)
+        ge, go, ce, co = e.download_agents(), o.download_agents(), e.download_cells(), o.download_cells()
+        for k in ("id", "x", "y", "vision", "metab", "sugar"):
+            assert np.array_equal(ge[k], go[k]), (t, k)
+        assert np.array_equal(ce["occ"], co["occ"]) and np.array_equal(ce["sugar"], co["sugar"]), t
+        if spice:
+            a, b = e.download_agents_spice(), o.download_agents_spice()
+            for k in ("spice_metab", "spice", "spice_endowment"):
+                assert np.array_equal(a[k], b[k]), (t, k)
+            assert np.array_equal(e.download_cells_spice()["spice"], o.download_cells_spice()["spice"]), t
+        if lifespan or procreate:
+            a, b = e.download_agents_life(), o.download_agents_life()
+            for k in common.LIFE_COLUMNS + ("id_increment",):
+                assert np.array_equal(a[k], b[k]), (t, k)
+            assert np.array_equal(e.events(), o.events()), t
+        me, mo = e.get_rng_mt19937(), o.get_rng_mt19937()
+        assert me[1] == mo[1] and np.array_equal(me[0], mo[0]), t
+    e.close()
+    o.close()
+
+
 def test_life_rules_need_their_columns_and_the_mt_mode():
     from sugarscape_utilicalc_b200.engine import EngineError
     g = common.load_golden("f3_evolution_metabolism_mt")

@@ -144,6 +144,77 @@ def test_lifespan_and_procreation_oracle_vs_live_reference():
     o.close()
 
 
+@settings(max_examples=int(os.environ.get("SS_LIFE_EXAMPLES", "40")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(grid=st.integers(12, 36), seed=st.integers(0, 10 ** 6), blue=st.integers(5, 120), red=st.integers(5, 120),
+       spice=st.booleans(), lifespan=st.booleans(), procreate=st.booleans(), seasons=st.booleans(),
+       endow=st.sampled_from([(5, 25), (50, 100)]), ages=st.sampled_from([(4, 10), (60, 100)]), start=st.sampled_from([0, 1, 12]))
+def test_random_worlds_with_spice_and_life_rules(grid, seed, blue, red, spice, lifespan, procreate, seasons, endow, ages, start):
+    """SURVEY 8 f2 + f3 on random small worlds built by the reference's own initialisation: any combination of spice,
+    limitedLifespan and procreate (short lives, early fertility and crowded lattices included), step by step -- cells, agents,
+    the fields of the rules, event lines, MT19937 stream."""
+    import ref_harness as rh
+    from sugarscape_utilicalc_b200 import outputs
+    s = rh.load_settings("readme_example")
+    s["rules"].update(trade=False, spice=spice, limitedLifespan=lifespan, procreate=procreate, seasons=seasons)
+    s["view"]["grid_size"] = {"x": grid, "y": grid}
+    s["env"]["random_seed"] = seed
+    s["env"]["total_agents"] = {"blue": blue, "red": red}
+    for k, site in s["env"]["sites"].items():
+        site["x"], site["y"], site["radius"] = site["x"] % grid, site["y"] % grid, max(2, site["radius"] * grid // 50)
+    for d in s["env"]["agent_distributions"].values():
+        d["x_min"], d["x_max"], d["y_min"], d["y_max"] = 0, grid - 1, 0, grid - 1
+    s["agents"]["max_agent_vision"] = min(s["agents"]["max_agent_vision"], (grid - 1) // 2)
+    s["agents"]["initial_endowments"] = {"min": endow[0], "max": endow[1]}
+    s["agents"]["death_age_range"] = {"min": ages[0], "max": ages[1]}
+    for who in ("male", "female"):
+        s["agents"]["fertility_age_ranges"][who].update(min_start=start, max_start=start + 3)
+    if seasons:
+        s["rule_params"]["seasons"]["period"] = 3
+        for reg in s["rule_params"]["seasons"]["regions"].values():
+            reg["start_x"], reg["end_x"], reg["start_y"], reg["end_y"] = 0, grid - 1, reg["start_y"] % grid, min(reg["end_y"], grid - 1)
+    ref = rh.ReferenceRun(s)
+    s0 = ref.snapshot()
+    cfg = config_from_settings(s, rng_mode="mt")
+    o = common.oracle_world(cfg)
+    init = dict(sugar=s0["sugar"], cap=s0["cap"], pollution=s0["pollution"], id=s0["order"], x=s0["x"], y=s0["y"],
+                vision=s0["vision"], metab=s0["metab"], sugar_agent=s0["sugar_agent"])
+    if spice:
+        init["spice"] = {k: s0[k] for k in ("spice", "spice_cap", "spice_metab", "spice_agent", "spice_endowment")}
+    if lifespan or procreate:
+        init["life"], init["id_increment"] = {k: s0[k] for k in LIFE_KEYS}, s0["id_increment"]
+    common.init_world(o, init, "mt", s0["mt"], s0["mt_index"])
+    log = []
+    for t in range(25):
+        ref.step()
+        st_ = o.step(1)
+        if lifespan or procreate:
+            log += outputs.event_lines(o.events())
+        sn, ga, gc = ref.snapshot(), o.download_agents(), o.download_cells()
+        assert np.array_equal(ga["id"], sn["order"]) and np.array_equal(ga["x"], sn["x"]) and np.array_equal(ga["y"], sn["y"]), t
+        assert np.array_equal(ga["sugar"], sn["sugar_agent"]) and np.array_equal(gc["occ"], sn["occ"]) and np.array_equal(gc["sugar"], sn["sugar"]), t
+        assert np.array_equal(ga["vision"], sn["vision"]) and np.array_equal(ga["metab"], sn["metab"]), t
+        if spice:
+            gs = o.download_agents_spice()
+            assert np.array_equal(gs["spice"], sn["spice_agent"]) and np.array_equal(gs["spice_metab"], sn["spice_metab"]), t
+            assert np.array_equal(gs["spice_endowment"], sn["spice_endowment"]) and np.array_equal(o.download_cells_spice()["spice"], sn["spice"]), t
+        if lifespan or procreate:
+            gl = o.download_agents_life()
+            for k in LIFE_KEYS:
+                assert np.array_equal(gl[k], sn[k]), (t, k)
+            assert gl["id_increment"] == sn["id_increment"], t
+        v = ref.view
+        assert st_["population"][0] == v.population[-1] and st_["gini"][0] == v.gini[-1], t
+        assert st_["metabolism_mean"][0] == v.metabolismMean[-1] and st_["vision_mean"][0] == v.visionMean[-1], t
+        mt, idx = o.get_rng_mt19937()
+        assert idx == sn["mt_index"] and np.array_equal(mt, sn["mt"]), t
+        if not len(sn["order"]):
+            break
+    if lifespan or procreate:
+        assert log == ref.view.log
+    assert o.pow_faults() == 0
+    o.close()
+
+
 def test_dropin_with_births_hands_a_working_view_back():
     """`dropin.install` under limitedLifespan + procreate: the installed updateGame keeps View.log complete (mating lines and
     deaths in execution order), sync_back gives the children Agent objects, and the reference's own loop continues from the
