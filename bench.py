@@ -53,13 +53,16 @@ def measured_peak():
 
 
 def kernels_sha():
-    """Hash of the CUDA sources: a DRAM-traffic figure in profiles/traffic.json counts only for the kernels it was captured on."""
+    """Hash of the CUDA sources' code (// comments and white space dropped): a DRAM-traffic figure in profiles/traffic.json
+    counts only for the kernels it was captured on."""
     import hashlib
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, "sugarscape_utilicalc_b200", "csrc")
     for f in ("ss_device.cuh", "ss_world.cuh", "ss_lattice.cu", "ss_rounds.cu"):
-        with open(os.path.join(d, f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(d, f), "r") as fh:
+            code = "".join(re.sub(r"//.*$", "", line) for line in fh.read().splitlines())
+        h.update(re.sub(r"\s+", "", code).encode())
     return h.hexdigest()[:16]
 
 

@@ -1,26 +1,25 @@
-// ss_lattice.cu -- parallel timestep kernels over the lattice-major cell store (keyed RNG).
+// ss_lattice.cu -- kernels over the lattice-major cell store (keyed RNG) that are not the dependency rounds of ss_rounds.cu:
 //
-// One timestep (View.updateGame, sugarscape.py:506-686) =
-//   ss_prepare_kernel   Q1 bookkeeping: at-risk agents stamp their successor in the execution
-//                       order (sugarscape.py:520 + 502-503: the agent after a dying agent
-//                       loses its turn)
-//   ss_move_pass_kernel agent phase in dependency rounds (agent.py:361-371 getFood,
-//                       agent.py:794-865 move, sugarscape.py:566-601 pollute / metabolise /
-//                       starve), repeated over shifted window tilings until no agent is pending
-//   ss_stats_kernel     population / means / Gini (sugarscape.py:603-619, 269-280)
-//   ss_grow_kernel / ss_seasons_kernel   growback (environment.py:133-155)
-//   ss_diffuse_kernel   in-place pollution sweep as a skewed wavefront (environment.py:317-350)
+//   ss_stats_kernel      population / means / Gini of a step (sugarscape.py:603-619, 269-280): every lattice path
+//   ss_grow_kernel / ss_seasons_kernel   growback (environment.py:133-155) where the one-byte cell words are not in use
+//   ss_diffuse_col_kernel  in-place pollution sweep as a column-chain wavefront (environment.py:317-350): every lattice path
+//   upload / download helpers (mirrors, agent store + occupancy build, export in keyed order)
+//   the replay kernels of the replicated multi-GPU scheme (sharded.py)
+//   and the agent phase of ROUND 1, kept as tested alternatives (pass_impl 0-2) and for that scheme:
+//   ss_prepare_kernel    Q1 bookkeeping: at-risk agents stamp their successor in the execution order (sugarscape.py:520 +
+//                        502-503: the agent after a dying agent loses its turn)
+//   ss_move_pass_kernel / ss_move_solo_kernel   window passes (agent.py:361-371 getFood, agent.py:794-865 move,
+//                        sugarscape.py:566-601 pollute / metabolise / starve), repeated over shifted window tilings until no
+//                        agent is pending; ss_settle_kernel finishes the turns of the agents that cannot starve
 //
-// Dependency rounds.  The execution order of a step is the ascending keyed priority of the
-// agent slot.  Two agents conflict iff their vision crosses share a cell; every read and
-// write of an agent's turn lies inside its own cross, so an agent may take its turn as
-// soon as every conflicting agent of lower priority has taken its own -- the result is
-// identical to the sequential loop.  A CTA owns one window of the lattice (disjoint
-// windows per launch, so CTAs never touch the same cells), stages the window's occupancy
-// words in shared memory, derives a pending bitmap, and resolves the agents of the
-// window's core (>= 2*vmax from the window edge, so that every possible conflict partner
-// is visible) round by round; agents of the outer ring act as blockers and are resolved
-// by a later launch whose tiling is shifted by half a window.
+// Window passes.  The execution order of a step is the ascending keyed priority of the agent slot.  Two agents conflict iff
+// their vision crosses share a cell; every read and write of an agent's turn lies inside its own cross, so an agent may take
+// its turn as soon as every conflicting agent of lower priority has taken its own -- the result is identical to the
+// sequential loop.  A launch cuts the lattice into disjoint windows (so CTAs / warps never touch the same cells); the agents
+// of a window's core (>= 2*vmax from the window edge, so that every possible conflict partner is visible) are resolved in
+// priority order, agents of the outer ring act as blockers and are resolved by a later launch whose tiling is shifted.
+// ss_move_pass_kernel: a CTA per window staged in shared memory, a warp per region; ss_move_solo_kernel: a warp per window,
+// cells read straight from L2.  The default agent phase is ss_rounds.cu (section 3.4).
 #include "ss_world.cuh"
 
 #define FULL 0xffffffffu

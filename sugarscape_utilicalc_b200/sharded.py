@@ -1,16 +1,15 @@
-"""Multi-GPU timestep: one process per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing.
+"""Multi-GPU timestep of ROUND 1 (kept with its tests; `bench.py --gpus N` runs the row strips of strips.py): one process
+per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing.
 
-Decomposition.  Every rank holds a replica of the lattice and the agent store
-(C5 needs 8.3 GB of the 180 GB) and, in every move pass, resolves only the agents of ITS contiguous
-share of the window rows -- windows of one launch are disjoint, so ranks never touch the same cells.
-The turns a rank resolved are appended on the device to a log of 48-byte entries (agent, old cell,
-new cell, new occupancy word, deferred-turn stamp or the synchronously settled state).  After the
-pass the ranks all-gather their log slices and replay the other ranks' entries on their replica
-(`ss_apply_log_kernel`: same stores, same arithmetic -> replicas stay bit-identical).  This is the
-exchange step of the path: what crosses NVLink per step is 48 B per agent (0.8 GB at C5) instead
-of lattice halos; agent migration is implicit in the log.  Growback, settle, statistics and
-diffusion run on every replica (1.3 ms of the 88 ms C5 step).  Passes repeat until the (replicated)
-pending counter is zero.
+Decomposition.  Every rank holds a replica of the lattice and the agent store and, in every move
+pass of the window kernels, resolves only the agents of ITS contiguous share of the window rows -- windows of one launch are
+disjoint, so ranks never touch the same cells.  The turns a rank resolved are appended on the device to two logs: 8-byte
+entries for the agents that cannot starve (slot | harvest, new cell) and 48-byte entries for synchronously settled turns and
+Q1 skips.  After the pass the ranks all-gather both slices in one buffer and replay the other ranks' entries on their replica
+(`ss_apply_clog_kernel` / `ss_apply_log_kernel`: same stores, same arithmetic -> replicas stay bit-identical).  What crosses
+NVLink per step is about 10 B per agent instead of lattice halos; agent migration is implicit in the log.  Growback, settle,
+statistics and diffusion run on every replica, and every replica replays all other ranks' turns: the scheme scaled 1.40x at
+8 GPUs (13.6 ms per C5 step), which is why round 2 replaced it by row strips (4.04x, 2.77 ms).
 
 `VirtualRanks` runs P replicas inside one process on one GPU with the same code path (device
 pointers instead of NCCL) -- the GPU parity test of the N>1 path; the gloo test
