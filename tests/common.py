@@ -191,6 +191,13 @@ def smoke_check():
     compare_worlds(e, o, 6, what="synthetic 512x512")
     assert e.counters()["path"] == 2 and e.counters()["pass_impl"] == 3, "dependency rounds were not selected"
     e.close()
+    o.close()
+    # spice with the restated libm pow, limited lifespan + procreation (serial kernel, goldens from the reference)
+    for name in ("f2_spice_life_mt", "f3_evolution_metabolism_mt"):
+        g = load_golden(name)
+        w = world_from_golden(g, "engine")
+        run_against_golden(g, w, exact_gini=True, max_steps=20)
+        w.close()
 
 
 OUTPUT_CASES = ["c1_default_moveeat_mt", "c1_default_moveeat_keyed", "c2_pollution_mt"]
