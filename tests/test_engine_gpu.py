@@ -122,7 +122,9 @@ def test_spice_single_steps_and_missing_uploads():
 @pytest.mark.parametrize("seed,grid,blue,red,spice,lifespan,procreate,ages,start", [
     (3, 20, 60, 60, True, True, True, (4, 10), 0), (77, 14, 90, 90, False, True, True, (60, 100), 1),
     (123, 36, 120, 120, True, False, True, (60, 100), 12), (9, 24, 150, 10, True, True, False, (4, 10), 12),
-    (2024, 30, 200, 200, False, False, True, (60, 100), 0), (5, 12, 70, 70, True, True, True, (60, 100), 1)])
+    (2024, 30, 200, 200, False, False, True, (60, 100), 0), (5, 12, 70, 70, True, True, True, (60, 100), 1),
+    (11, 300, 1500, 1500, False, True, True, (60, 100), 12),        # N > 256: serial agents + the lattice's environment kernels
+    (12, 280, 900, 900, True, True, True, (60, 100), 12)])          # ... with spice: the serial kernel's own environment phase
 def test_random_worlds_with_spice_and_life_rules_engine_vs_oracle(seed, grid, blue, red, spice, lifespan, procreate, ages, start):
     """SURVEY 8 f2 + f3 on small random worlds (short lives, fertility from birth, crowded lattices): the world of `__main__`
     built on the device, handed to the oracle as is, then both stepped -- cells, agents, the rules' fields, event records,
