@@ -190,7 +190,9 @@ def python_reference_figures(args, wl):
 
     presets = [("settings.json as shipped (utilicalc)", None, {}, 100), ("settings.json with moveEat", None, {"moveEat": True, "utilicalc": False}, 100),
                ("examples/seasons", "seasons", {}, 500), ("examples/pollution", "pollution", {}, 500),
-               ("examples/utilicalc_sugar", "utilicalc_sugar", {}, 500)]
+               ("examples/utilicalc_sugar", "utilicalc_sugar", {}, 500),
+               ("examples/evolution_metabolism (limitedLifespan + procreate)", "evolution_metabolism", {}, 300),
+               ("examples/trade_price_volume without trade (spice)", "trade_price_volume", {"trade": False}, 300)]
     for label, preset, rules, steps in presets:
         s = rh.load_settings(preset)
         s["rules"].update(rules)
